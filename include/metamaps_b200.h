@@ -1,0 +1,158 @@
+/*
+ * metamaps_b200.h -- C ABI of the B200-native MetaMaps compute core.
+ *
+ * The reference (DiltheyLab/MetaMaps) has no FFI; its hot path is reached through two C++
+ * constructors and one function, all driven by `metamaps mapDirectly` / `metamaps classify`:
+ *
+ *   skch::Sketch::Sketch(Parameters&, size_t maxMemory, std::function<void(Sketch*,size_t)>*)
+ *                                                   src/map/include/winSketch.hpp:157   (index build)
+ *   skch::Map::Map(const Parameters&, const Sketch&, PostProcessResultsFn_t)
+ *                                                   src/map/include/computeMap.hpp:85   (L1 + L2 mapping)
+ *   mapWrap::addMappingQualities(...)               src/map/mapWrap.h:215               (mapping quality)
+ *   meta::doEM(const Parameters&, const std::string&)  src/meta/fEM.h:466               (EM classification)
+ *
+ * Each entry point below replaces the array-level work of one of those seams; the file parsing,
+ * text formatting and taxonomy book-keeping stay in the C++ host (metamaps_b200/csrc/host).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MM_E* code otherwise; mm_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - plain pointers + sizes; the caller owns every buffer it passes; the library owns handles until the
+ *     matching *_destroy;  "host" pointers are ordinary host memory, "_dev" entry points take CUDA
+ *     device pointers on the context's device;
+ *   - one mm_ctx per GPU, used by one host thread at a time; work is issued on the context's CUDA stream
+ *     and every entry point returns after its results are complete unless stated otherwise;
+ *   - there is no CPU implementation: if no CUDA device is usable, mm_ctx_create fails.
+ *
+ * Sequences are ASCII (any case, any byte; non-ACGT bytes are hashed verbatim like the reference does,
+ * commonFunc.hpp:44-51,106), concatenated, with n+1 byte offsets.
+ */
+#ifndef METAMAPS_B200_H
+#define METAMAPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_OK 0
+#define MM_EINVAL (-22)
+#define MM_ENOMEM (-12)
+#define MM_ECUDA (-5)
+#define MM_ENODEV (-19)
+#define MM_ERANGE (-34)
+
+typedef struct mm_ctx mm_ctx;
+typedef struct mm_index mm_index;
+
+const char* mm_last_error(void);
+const char* mm_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int mm_ctx_create(int device, mm_ctx** out);
+void mm_ctx_destroy(mm_ctx* ctx);
+/* Device-time (ms, CUDA events on the context stream) and launch count of the kernels issued by the last
+ * mm_* call on this context; bench.py uses these for `gpu_launches` and the roofline block. */
+int mm_ctx_last_timing(mm_ctx* ctx, double* total_ms, int64_t* n_launches);
+/* Per-stage device time of the last mm_map_* call: K1 sketch, K3 read sketch, K4 L1, K5 L2 (classify, sweep,
+ * strand), plus algorithmic byte counters: s_total, hits, candidates, span elements. */
+int mm_ctx_last_map_stats(mm_ctx* ctx, double* stage_ms /*[8]*/, int64_t* counters /*[8]*/);
+
+/* ---- K1: winnowed minimizers  (replaces CommonFunc::addMinimizers, commonFunc.hpp:92-175) --------- */
+/* Sketches n_seqs sequences; results stay on the device until fetched.  *n_total = number of minimizers. */
+int mm_sketch_batch(mm_ctx* ctx, const char* seqs, const int64_t* offsets, int32_t n_seqs, int k, int w,
+                    int64_t* n_total);
+/* counts: n_seqs+1 prefix offsets; hash/wpos/strand: n_total entries, per sequence in emission order;
+ * strand is +1 / -1 (base_types.hpp:126). */
+int mm_sketch_fetch(mm_ctx* ctx, int64_t* counts, uint32_t* hash, int32_t* wpos, int32_t* strand);
+
+/* ---- K2: reference index  (replaces skch::Sketch, winSketch.hpp:157-365,452-517) ------------------ */
+int mm_index_create(mm_ctx* ctx, int k, int w, mm_index** out);
+/* Appends contigs in DB.fa order; contig i of the j-th call gets the next sequence id (winSketch.hpp:258-345,
+ * contigs shorter than w or k keep an id but contribute no minimizers). */
+int mm_index_add(mm_index* idx, const char* seqs, const int64_t* offsets, int32_t n_seqs);
+int mm_index_add_dev(mm_index* idx, const void* seqs_dev, const int64_t* offsets_host, int32_t n_seqs);
+/* Sorts, builds the hash->positions table and the occurrence threshold (computeFreqHist, winSketch.hpp:452-495). */
+int mm_index_finalize(mm_index* idx);
+int mm_index_stats(const mm_index* idx, int64_t* n_minimizers, int64_t* n_unique, int32_t* freq_threshold,
+                   int32_t* n_contigs, int64_t* device_bytes);
+/* minimizerIndex in (seqId,wpos) order, for parity tests. */
+int mm_index_fetch(const mm_index* idx, uint32_t* hash, int32_t* seq_id, int32_t* wpos, int32_t* strand);
+/* minimizerPosLookupIndex probe, for parity tests: count (0 = absent) of each hash. */
+int mm_index_lookup(const mm_index* idx, const uint32_t* hashes, int64_t n, int32_t* counts);
+void mm_index_destroy(mm_index* idx);
+
+/* ---- K3-K5: map a batch of reads  (replaces skch::Map::mapSingleQuerySeq, computeMap.hpp:228-538) -- */
+typedef struct mm_map_params {
+  float perc_identity;   /* --pi, default 80 (parseCmdArgs.hpp:345-354) */
+  int32_t min_read_len;  /* -m; reads shorter than max(w,k,m) are skipped (computeMap.hpp:137) */
+  int32_t report_all;    /* --all: 1 keeps every accepted mapping; 0 keeps identity >= best-1 (computeMap.hpp:561-563) */
+  int32_t reserved;
+} mm_map_params;
+
+typedef struct mm_map_summary {
+  int64_t n_reads;       /* reads in the batch */
+  int64_t n_too_short;   /* skipped by the length rule */
+  int64_t n_candidates;  /* L1 candidate loci (all evaluated by L2) */
+  int64_t n_mappings;    /* candidates passing the L2 identity filter (computeMap.hpp:415) */
+  int64_t n_reads_mapped;
+  int64_t total_bases_mapped_reads; /* bases of reads that were long enough (the Mbp of the metric) */
+} mm_map_summary;
+
+/* Host ASCII reads in.  Results stay in the context until the next mm_map_* call. */
+int mm_map_batch(mm_ctx* ctx, const mm_index* idx, const char* reads, const int64_t* offsets, int32_t n_reads,
+                 const mm_map_params* params, mm_map_summary* summary);
+/* Device-resident ASCII reads (offsets on the host). */
+int mm_map_batch_dev(mm_ctx* ctx, const mm_index* idx, const void* reads_dev, const int64_t* offsets_host,
+                     int32_t n_reads, const mm_map_params* params, mm_map_summary* summary);
+
+/* Per-read: sketch size s (0 for skipped reads), minimumHits, offsets into the candidate arrays (n_reads+1).
+ * Any pointer may be NULL. */
+int mm_map_fetch_reads(mm_ctx* ctx, int32_t* sketch_size, int32_t* minimum_hits, int64_t* cand_offsets);
+/* Per L1 candidate, in the reference's order (read order, then (seqId,wpos) order): contig id, candidate range,
+ * L2 result: meanOptimalPos, sharedSketchSize, strand votes (sum strandQ*strandR), accepted flag (identity
+ * upper bound >= pi), valid flag (0 when no window had a shared element; the reference leaves the position
+ * uninitialised there), and the optimal window [opt_start,opt_end) as minimizerIndex positions. */
+int mm_map_fetch_candidates(mm_ctx* ctx, int32_t* seq_id, int32_t* range_start, int32_t* range_end,
+                            int32_t* mean_optimal_pos, int32_t* shared, int32_t* strand_votes,
+                            int32_t* accepted, int32_t* valid, int64_t* opt_start, int64_t* opt_end);
+/* Stage outputs for parity tests: the read sketch (sorted unique hashes + strand of the surviving minimizer). */
+int mm_map_fetch_sketch(mm_ctx* ctx, int64_t* offsets /*n_reads+1*/, uint32_t* hash, int32_t* strand, int64_t cap);
+
+/* ---- statistics tables the host needs for text output (replace Stat::*, map_stats.hpp) ------------ */
+int mm_stat_min_hits_relaxed(int s, int k, float perc_identity);          /* estimateMinimumHitsRelaxed :142 */
+int mm_stat_recommended_window(double pvalue, int k, int alphabet, float perc_identity, int len_query,
+                               uint64_t len_reference);                    /* recommendedWindowSize :226 */
+double mm_stat_estimate_pvalue(int s, int k, int alphabet, float perc_identity, int len_query, uint64_t len_reference);
+void mm_stat_identity(int shared, int s, int k, float* nuc_identity, float* nuc_identity_upper); /* computeMap.hpp:405-411 */
+
+/* ---- K6: mapping qualities  (replaces mapWrap::addMappingQualities, mapWrap.h:215-323) ------------- */
+/* identity[m] = column 10 / 100; reads delimited by read_offsets (n_reads+1); read_len per read.
+ * mapq[m] = binomial likelihood normalised per read.  status[r] = 0, or 1 when the likelihood sum is 0
+ * (the reference asserts, mapWrap.h:298). */
+int mm_mapq_batch(mm_ctx* ctx, const double* identity, const int32_t* shared, const int32_t* sketch,
+                  const int32_t* read_len, const int64_t* read_offsets, int64_t n_reads, int k,
+                  double* mapq, int32_t* status);
+
+/* ---- K7/K8: EM  (replaces the loop of meta::doEM, fEM.h:491-661, and its final pass :693-716) ------ */
+/* taxon[m] in [0,T); mapq[m] = column 14; nloc[m] = possible mapping locations of that taxon for that read
+ * (fEM.h:324-348).  max_iter <= 0: run to the reference's stopping rule (fEM.h:636); max_iter > 0: run exactly
+ * max_iter rounds (the reference has no iteration cap; used to benchmark a fixed round count).
+ * Outputs: f[T]; posterior[m]; best[r] = index of the first maximal posterior of read r (getBestMapping :217);
+ * ll_hist[0..min(n_iter,ll_cap)) log-likelihood per round; *n_iter rounds run. */
+int mm_em_run(mm_ctx* ctx, const int32_t* taxon, const double* mapq, const double* nloc,
+              const int64_t* read_offsets, int64_t n_reads, int32_t T, int32_t max_iter,
+              double* f, double* posterior, int64_t* best, double* ll_hist, int32_t ll_cap, int32_t* n_iter);
+
+/* Multi-GPU EM: reads are partitioned over ranks; each rank passes its own mappings and the per-round
+ * taxon sums + log-likelihood are all-reduced over NCCL.  id_bytes: 128-byte ncclUniqueId from
+ * mm_comm_unique_id on rank 0, distributed by the caller (e.g. torch.distributed broadcast). */
+int mm_comm_unique_id(void* id_bytes_128);
+int mm_comm_init(mm_ctx* ctx, int n_ranks, int rank, const void* id_bytes_128);
+int mm_comm_destroy(mm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METAMAPS_B200_H */

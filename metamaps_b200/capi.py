@@ -1,0 +1,257 @@
+"""ctypes binding of the C ABI in include/metamaps_b200.h.
+
+`load()` binds metamaps_b200/libmetamaps_b200.so (the nvcc sm_100a build).  There is no Python or CPU
+implementation behind it: if the shared library is missing, or no CUDA device is usable, the calls fail.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmetamaps_b200.so")
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+class MapParams(C.Structure):
+    _fields_ = [("perc_identity", C.c_float), ("min_read_len", C.c_int32), ("report_all", C.c_int32), ("reserved", C.c_int32)]
+
+
+class MapSummary(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_too_short", C.c_int64), ("n_candidates", C.c_int64), ("n_mappings", C.c_int64),
+                ("n_reads_mapped", C.c_int64), ("total_bases_mapped_reads", C.c_int64)]
+
+
+# every symbol include/metamaps_b200.h declares: (restype, argtypes); None = opaque/void pointers
+SYMBOLS = {
+    "mm_last_error": (C.c_char_p, []),
+    "mm_version": (C.c_char_p, []),
+    "mm_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "mm_ctx_destroy": (None, [C.c_void_p]),
+    "mm_ctx_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "mm_ctx_last_map_stats": (C.c_int, [C.c_void_p, _f64p, _i64p]),
+    "mm_sketch_batch": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
+    "mm_sketch_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mm_index_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mm_index_add": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, C.c_int32]),
+    "mm_index_add_dev": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int32]),
+    "mm_index_finalize": (C.c_int, [C.c_void_p]),
+    "mm_index_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "mm_index_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mm_index_lookup": (C.c_int, [C.c_void_p, _u32p, C.c_int64, _i32p]),
+    "mm_index_destroy": (None, [C.c_void_p]),
+    "mm_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, _i64p, C.c_int32, C.POINTER(MapParams), C.POINTER(MapSummary)]),
+    "mm_map_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _i64p, C.c_int32, C.POINTER(MapParams), C.POINTER(MapSummary)]),
+    "mm_map_fetch_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mm_map_fetch_candidates": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
+    "mm_map_fetch_sketch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "mm_stat_min_hits_relaxed": (C.c_int, [C.c_int, C.c_int, C.c_float]),
+    "mm_stat_recommended_window": (C.c_int, [C.c_double, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64]),
+    "mm_stat_estimate_pvalue": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64]),
+    "mm_stat_identity": (None, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "mm_mapq_batch": (C.c_int, [C.c_void_p, _f64p, _i32p, _i32p, _i32p, _i64p, C.c_int64, C.c_int, _f64p, _i32p]),
+    "mm_em_run": (C.c_int, [C.c_void_p, _i32p, _f64p, _f64p, _i64p, C.c_int64, C.c_int32, C.c_int32, _f64p, _f64p, _i64p, _f64p, C.c_int32, C.POINTER(C.c_int32)]),
+    "mm_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mm_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mm_comm_destroy": (C.c_int, [C.c_void_p]),
+}
+
+
+class MMError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"metamaps_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """dlopen the C-ABI library and declare every prototype.  Raises if the library is absent."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _ascii_batch(seqs):
+    """list of bytes -> (joined bytes, int64 offsets)."""
+    offs = np.zeros(len(seqs) + 1, np.int64)
+    if len(seqs):
+        offs[1:] = np.cumsum([len(s) for s in seqs])
+    return b"".join(seqs), offs
+
+
+class Context:
+    """One per GPU (mm_ctx)."""
+
+    def __init__(self, device: int = 0, lib: C.CDLL | None = None):
+        self.lib = lib or load()
+        h = C.c_void_p()
+        self._check(self.lib.mm_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise MMError(rc, (self.lib.mm_last_error() or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mm_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_timing(self):
+        ms = C.c_double(); n = C.c_int64()
+        self.lib.mm_ctx_last_timing(self.h, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
+    def last_map_stats(self):
+        ms = np.zeros(8); ct = np.zeros(8, np.int64)
+        self.lib.mm_ctx_last_map_stats(self.h, ms, ct)
+        return {"sketch_ms": ms[0], "read_sketch_ms": ms[1], "l1_ms": ms[2], "l2_setup_ms": ms[3], "l2_classify_ms": ms[4],
+                "l2_sweep_ms": ms[5], "l2_strand_ms": ms[6],
+                "sketch_elems": int(ct[0]), "hits": int(ct[1]), "candidates": int(ct[2]), "span_elems": int(ct[3]),
+                "mappings": int(ct[4]), "read_minimizers": int(ct[5]), "bases": int(ct[6]), "exceptions": int(ct[7])}
+
+    # K1
+    def sketch(self, seqs, k: int, w: int):
+        """CommonFunc::addMinimizers over a list of ASCII sequences -> (offsets, hash, wpos, strand)."""
+        data, offs = _ascii_batch(seqs)
+        n = C.c_int64()
+        self._check(self.lib.mm_sketch_batch(self.h, data, offs, len(seqs), k, w, C.byref(n)))
+        counts = np.zeros(len(seqs) + 1, np.int64)
+        hs = np.zeros(n.value, np.uint32); wp = np.zeros(n.value, np.int32); st = np.zeros(n.value, np.int32)
+        self._check(self.lib.mm_sketch_fetch(self.h, _ptr(counts), _ptr(hs), _ptr(wp), _ptr(st)))
+        return counts, hs, wp, st
+
+    # K6
+    def mapq(self, identity, shared, sketch, read_len, read_off, k: int):
+        identity = np.ascontiguousarray(identity, np.float64)
+        out = np.zeros(len(identity)); status = np.zeros(len(read_off) - 1, np.int32)
+        self._check(self.lib.mm_mapq_batch(self.h, identity, np.ascontiguousarray(shared, np.int32),
+                                           np.ascontiguousarray(sketch, np.int32), np.ascontiguousarray(read_len, np.int32),
+                                           np.ascontiguousarray(read_off, np.int64), len(read_off) - 1, k, out, status))
+        return out, status
+
+    # K7/K8
+    def em(self, taxon, mapq, nloc, read_off, T: int, max_iter: int = 0):
+        taxon = np.ascontiguousarray(taxon, np.int32); mapq = np.ascontiguousarray(mapq, np.float64)
+        nloc = np.ascontiguousarray(nloc, np.float64); read_off = np.ascontiguousarray(read_off, np.int64)
+        nr = len(read_off) - 1
+        f = np.zeros(T); post = np.zeros(len(taxon)); best = np.zeros(max(nr, 1), np.int64); ll = np.zeros(4096)
+        it = C.c_int32()
+        self._check(self.lib.mm_em_run(self.h, taxon, mapq, nloc, read_off, nr, T, max_iter, f, post, best, ll, len(ll), C.byref(it)))
+        return {"f": f, "posterior": post, "best": best[:nr], "ll": ll[:min(it.value, len(ll))].copy(), "iters": it.value}
+
+    def comm_init(self, n_ranks: int, rank: int, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        self._check(self.lib.mm_comm_init(self.h, n_ranks, rank, buf))
+
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.mm_comm_unique_id(buf))
+        return buf.raw
+
+
+class Index:
+    """skch::Sketch on the GPU (mm_index)."""
+
+    def __init__(self, ctx: Context, k: int, w: int):
+        self.ctx = ctx; self.lib = ctx.lib; self.k = k; self.w = w
+        h = C.c_void_p()
+        ctx._check(self.lib.mm_index_create(ctx.h, k, w, C.byref(h)))
+        self.h = h
+
+    def add(self, contigs):
+        data, offs = _ascii_batch(contigs)
+        self.ctx._check(self.lib.mm_index_add(self.h, data, offs, len(contigs)))
+
+    def add_dev(self, dev_ptr: int, offsets):
+        offs = np.ascontiguousarray(offsets, np.int64)
+        self.ctx._check(self.lib.mm_index_add_dev(self.h, C.c_void_p(dev_ptr), offs, len(offs) - 1))
+
+    def finalize(self):
+        self.ctx._check(self.lib.mm_index_finalize(self.h))
+
+    def stats(self):
+        a = C.c_int64(); b = C.c_int64(); c = C.c_int32(); d = C.c_int32(); e = C.c_int64()
+        self.ctx._check(self.lib.mm_index_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)))
+        return {"n_minimizers": a.value, "n_unique": b.value, "freq_threshold": c.value, "n_contigs": d.value, "device_bytes": e.value}
+
+    def fetch(self):
+        n = self.stats()["n_minimizers"]
+        hs = np.zeros(n, np.uint32); sq = np.zeros(n, np.int32); wp = np.zeros(n, np.int32); st = np.zeros(n, np.int32)
+        self.ctx._check(self.lib.mm_index_fetch(self.h, _ptr(hs), _ptr(sq), _ptr(wp), _ptr(st)))
+        return hs, sq, wp, st
+
+    def lookup(self, hashes):
+        hashes = np.ascontiguousarray(hashes, np.uint32)
+        out = np.zeros(len(hashes), np.int32)
+        self.ctx._check(self.lib.mm_index_lookup(self.h, hashes, len(hashes), out))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mm_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def map_reads(ctx: Context, index: Index, reads=None, perc_identity: float = 80.0, min_read_len: int = 1000,
+              dev_ptr: int | None = None, offsets=None, fetch: bool = True, fetch_sketch: bool = False):
+    """skch::Map over a batch.  reads: list of ASCII bytes (host) or dev_ptr+offsets (device-resident ASCII)."""
+    p = MapParams(perc_identity, min_read_len, 1, 0)
+    s = MapSummary()
+    if dev_ptr is None:
+        data, offs = _ascii_batch(reads)
+        ctx._check(ctx.lib.mm_map_batch(ctx.h, index.h, data, offs, len(reads), C.byref(p), C.byref(s)))
+    else:
+        offs = np.ascontiguousarray(offsets, np.int64)
+        ctx._check(ctx.lib.mm_map_batch_dev(ctx.h, index.h, C.c_void_p(dev_ptr), offs, len(offs) - 1, C.byref(p), C.byref(s)))
+    n = len(offs) - 1
+    out = {"summary": {f[0]: getattr(s, f[0]) for f in MapSummary._fields_}}
+    if not fetch:
+        return out
+    sk = np.zeros(n, np.int32); mh = np.zeros(n, np.int32); co = np.zeros(n + 1, np.int64)
+    ctx._check(ctx.lib.mm_map_fetch_reads(ctx.h, _ptr(sk), _ptr(mh), _ptr(co)))
+    nc = int(s.n_candidates)
+    names = ["seq", "start", "end", "pos", "shared", "votes", "accepted", "valid"]
+    arrs = [np.zeros(nc, np.int32) for _ in names]
+    o1 = np.zeros(nc, np.int64); o2 = np.zeros(nc, np.int64)
+    ctx._check(ctx.lib.mm_map_fetch_candidates(ctx.h, *[_ptr(a) for a in arrs], _ptr(o1), _ptr(o2)))
+    out.update({"s": sk, "minimumHits": mh, "cand_off": co, "optStart": o1, "optEnd": o2})
+    out.update(dict(zip(names, arrs)))
+    if fetch_sketch:
+        qo = np.zeros(n + 1, np.int64)
+        ctx._check(ctx.lib.mm_map_fetch_sketch(ctx.h, _ptr(qo), None, None, 0))
+        nq = int(qo[-1])
+        qh = np.zeros(nq, np.uint32); qs = np.zeros(nq, np.int32)
+        ctx._check(ctx.lib.mm_map_fetch_sketch(ctx.h, _ptr(qo), _ptr(qh), _ptr(qs), nq))
+        out.update({"q_off": qo, "q_hash": qh, "q_strand": qs})
+    return out

@@ -1,0 +1,202 @@
+// mm_index.h -- K2: the GPU-resident reference index.
+//
+// Replaces skch::Sketch (reference src/map/include/winSketch.hpp):
+//   minimizerIndex           (:129)  -> miHash[] / miWs[]  SoA in (seqId,wpos) order, 8 B per minimizer,
+//                                       + contigStart[] (first entry of each contig)
+//   minimizerPosLookupIndex  (:119)  -> open-addressed table of 16-byte slots {hash, count, start} over
+//                                       posKey[] (CSR, entries of one hash contiguous, (seqId,wpos) order)
+//   computeFreqHist          (:452-495) -> freqThreshold
+//   searchIndex              (:506-517) -> contigStart[seq] + lower_bound over the contig's wpos
+//
+// Extra, not in the reference: a "dup" side structure.  SlideMapper (slidingMap.hpp:139-219) keeps ONE
+// entry per hash, so when the same hash occurs twice inside a contig the L2 window must treat it with set
+// semantics.  dupBits marks minimizers that share their hash with another minimizer of the same contig and
+// dupIdx/dupPrev/dupNext give the distance (in index entries) to the previous/next such occurrence.
+#pragma once
+#include "mm_sketch.h"
+
+namespace mm {
+
+struct Slot { uint32_t key, count, startLo, startHi; };
+
+// minimizer hashes are biased towards small values (they are window minima), so spread them first
+MM_HD uint32_t slot_of(uint32_t h, uint32_t mask) { return (uint32_t)(((uint64_t)h * 0x9E3779B97F4A7C15ull) >> 32) & mask; }
+
+// probe one hash: returns count (0 = absent) and the CSR start
+MM_HD uint32_t table_find(const Slot* table, uint32_t mask, uint32_t h, int64_t* start) {
+  uint32_t s = slot_of(h, mask);
+  for (;;) {
+#if defined(__CUDA_ARCH__)
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(table + s));
+    uint32_t key = v.x, cnt = v.y, lo = v.z, hi = v.w;
+#else
+    uint32_t key = table[s].key, cnt = table[s].count, lo = table[s].startLo, hi = table[s].startHi;
+#endif
+    if (cnt == 0) return 0;
+    if (key == h) { *start = (int64_t)(((uint64_t)hi << 32) | lo); return cnt; }
+    s = (s + 1) & mask;
+  }
+}
+
+struct IotaFn { uint32_t* v; MM_HD void operator()(int64_t i) const { v[i] = (uint32_t)i; } };
+
+struct TableInsertFn {
+  Slot* table; uint32_t mask; const uint32_t* uniq; const int32_t* counts; const int64_t* starts;
+  MM_HD void operator()(int64_t u) const {
+    uint32_t h = ldg(uniq + u); uint32_t c = (uint32_t)ldg(counts + u); int64_t st = ldg(starts + u);
+    uint32_t s = slot_of(h, mask);
+    for (;;) {
+      uint32_t old = atomic_cas_u32(&table[s].count, 0u, c);   // hashes are unique: claiming a slot is enough
+      if (old == 0) { table[s].key = h; table[s].startLo = (uint32_t)st; table[s].startHi = (uint32_t)((uint64_t)st >> 32); return; }
+      s = (s + 1) & mask;
+    }
+  }
+};
+
+// CSR entry e (hash order, then index order) -> (seqId << 32) | (wpos << 1 | strandbit): sorts like the
+// reference's MinimizerMetaData::operator< (base_types.hpp:100-103; REV = -1 < FWD = 1)
+struct PosKeyFn {
+  const uint32_t* sortedPos; const uint32_t* miWs; const int64_t* contigStart; int32_t n_contigs; uint64_t* posKey;
+  MM_HD void operator()(int64_t e) const {
+    uint32_t p = ldg(sortedPos + e);
+    int64_t sq = upper_bound_idx(contigStart, (int64_t)n_contigs + 1, (int64_t)p) - 1;
+    posKey[e] = ((uint64_t)sq << 32) | ldg(miWs + p);
+  }
+};
+
+// pass 0: mark + count dups; pass 1: also append (p, prev, next)
+struct DupFn {
+  const uint32_t* sortedHash; const uint32_t* sortedPos; const uint64_t* posKey; int64_t n;
+  uint32_t* dupBits; unsigned long long* count; int pass;
+  uint32_t* outIdx; uint64_t* outLinks;
+  MM_HD void operator()(int64_t e) const {
+    uint32_t h = ldg(sortedHash + e); uint32_t sq = (uint32_t)(ldg(posKey + e) >> 32); uint32_t p = ldg(sortedPos + e);
+    uint32_t prev = 0, next = 0;
+    if (e > 0 && ldg(sortedHash + e - 1) == h && (uint32_t)(ldg(posKey + e - 1) >> 32) == sq) prev = p - ldg(sortedPos + e - 1);
+    if (e + 1 < n && ldg(sortedHash + e + 1) == h && (uint32_t)(ldg(posKey + e + 1) >> 32) == sq) next = ldg(sortedPos + e + 1) - p;
+    if (prev | next) {
+      unsigned long long s = atomic_add_u64(count, 1ull);
+      if (pass == 0) atomic_or_u32(dupBits + (p >> 5), 1u << (p & 31));
+      else { outIdx[s] = p; outLinks[s] = ((uint64_t)prev << 32) | next; }
+    }
+  }
+};
+
+struct LookupFn {
+  const Slot* table; uint32_t mask; const uint32_t* hashes; int32_t* counts;
+  MM_HD void operator()(int64_t i) const { int64_t st; counts[i] = (int32_t)table_find(table, mask, ldg(hashes + i), &st); }
+};
+
+struct Index {
+  Runtime& rt; Prims& pr; Sketcher& sk;
+  int k, w;
+  bool finalized = false;
+  // positional arrays
+  DevBuf<uint32_t> miHash, miWs; int64_t n = 0;
+  std::vector<int64_t> h_contigStart{0}; std::vector<int32_t> h_contigLen;
+  DevBuf<int64_t> contigStart; DevBuf<int32_t> contigLen; int32_t n_contigs = 0;
+  // lookup
+  DevBuf<Slot> table; uint32_t tableMask = 0;
+  DevBuf<uint64_t> posKey;
+  int64_t n_unique = 0; int32_t freqThreshold = 0x7fffffff;
+  // dups
+  DevBuf<uint32_t> dupBits, dupIdx; DevBuf<uint64_t> dupLinks; int64_t n_dup = 0;
+  int64_t total_bases = 0;
+
+  Index(Runtime& r, Prims& p, Sketcher& s, int k_, int w_) : rt(r), pr(p), sk(s), k(k_), w(w_) {}
+
+  void add(SeqBatch& B) {
+    if (finalized) throw Error(-22, "index already finalized");
+    SketchOut out;
+    sk.run(B, k, w, out);
+    if ((uint64_t)(n + out.n_total) >= 0xFFFFFFF0ull) throw Error(-34, "index shard exceeds 2^32 minimizers: split the reference into shards");
+    miHash.grow(rt, (size_t)(n + out.n_total), (size_t)n); miWs.grow(rt, (size_t)(n + out.n_total), (size_t)n);
+    d2d(rt, miHash.p + n, out.hash.p, sizeof(uint32_t) * (size_t)out.n_total);
+    d2d(rt, miWs.p + n, out.ws.p, sizeof(uint32_t) * (size_t)out.n_total);
+    std::vector<int64_t> off((size_t)B.n_seqs + 1);
+    d2h(rt, off.data(), out.seqOff.p, sizeof(int64_t) * off.size());
+    off[B.n_seqs] = out.n_total;
+    for (int32_t i = 0; i < B.n_seqs; i++) {
+      h_contigLen.push_back(B.h_len[i]);
+      h_contigStart.push_back(n + off[i + 1]);
+    }
+    n += out.n_total; n_contigs += B.n_seqs; total_bases += B.total_bases;
+    rt.sync();
+  }
+
+  void finalize() {
+    if (finalized) return;
+    contigStart.ensure(h_contigStart.size()); h2d(rt, contigStart.p, h_contigStart.data(), sizeof(int64_t) * h_contigStart.size());
+    contigLen.ensure(h_contigLen.size() + 1); h2d(rt, contigLen.p, h_contigLen.data(), sizeof(int32_t) * h_contigLen.size());
+    finalized = true;
+    if (n == 0) { table.ensure(1024); dev_memset(rt, table.p, 0, sizeof(Slot) * 1024); tableMask = 1023; return; }
+    DevBuf<uint32_t> iota, sortedHash, sortedPos, uniq, cntSorted, cntUniq;
+    DevBuf<int32_t> counts, cntRuns; DevBuf<int64_t> starts, nRuns;
+    iota.ensure((size_t)n); sortedHash.ensure((size_t)n); sortedPos.ensure((size_t)n);
+    foreach(rt, n, IotaFn{iota.p});
+    pr.sort_pairs<uint32_t, uint32_t>(miHash.p, sortedHash.p, iota.p, sortedPos.p, n);
+    iota.release();
+    uniq.ensure((size_t)n); counts.ensure((size_t)n + 1); nRuns.ensure(2);
+    pr.rle<uint32_t>(sortedHash.p, uniq.p, counts.p, nRuns.p, n);
+    d2h(rt, &n_unique, nRuns.p, sizeof(int64_t));
+    starts.ensure((size_t)n_unique + 1);
+    dev_memset(rt, counts.p + n_unique, 0, sizeof(int32_t));
+    pr.exclusive_sum<int32_t, int64_t>(counts.p, starts.p, n_unique + 1);
+
+    // frequency threshold (computeFreqHist, winSketch.hpp:452-495): histogram of occurrences-per-hash,
+    // walked from the most frequent bucket while the cumulative count stays within 0.001 % of the hashes
+    {
+      cntSorted.ensure((size_t)n_unique); cntUniq.ensure((size_t)n_unique); cntRuns.ensure((size_t)n_unique + 1);
+      pr.sort_keys<uint32_t>((const uint32_t*)counts.p, cntSorted.p, n_unique);
+      pr.rle<uint32_t>(cntSorted.p, cntUniq.p, cntRuns.p, nRuns.p, n_unique);
+      int64_t nb = 0; d2h(rt, &nb, nRuns.p, sizeof(int64_t));
+      std::vector<uint32_t> hv((size_t)nb); std::vector<int32_t> hc((size_t)nb);
+      d2h(rt, hv.data(), cntUniq.p, sizeof(uint32_t) * (size_t)nb);
+      d2h(rt, hc.data(), cntRuns.p, sizeof(int32_t) * (size_t)nb);
+      float percentageThreshold = 0.001f;
+      int64_t toIgnore = (int64_t)(n_unique * percentageThreshold / 100);
+      int64_t sum = 0;
+      freqThreshold = 0x7fffffff;
+      for (int64_t b = nb - 1; b >= 0; b--) {
+        sum += hc[(size_t)b];
+        if (sum < toIgnore) freqThreshold = (int32_t)hv[(size_t)b];
+        else if (sum == toIgnore) { freqThreshold = (int32_t)hv[(size_t)b]; break; }
+        else break;
+      }
+      cntSorted.release(); cntUniq.release(); cntRuns.release();
+    }
+
+    uint64_t slots = 1024; while (slots < (uint64_t)n_unique * 2) slots <<= 1;
+    if (slots > (1ull << 32)) throw Error(-34, "hash table too large");
+    table.ensure((size_t)slots); dev_memset(rt, table.p, 0, sizeof(Slot) * (size_t)slots);
+    tableMask = (uint32_t)(slots - 1);
+    foreach(rt, n_unique, TableInsertFn{table.p, tableMask, uniq.p, counts.p, starts.p});
+    uniq.release(); counts.release(); starts.release();
+
+    posKey.ensure((size_t)n);
+    foreach(rt, n, PosKeyFn{sortedPos.p, miWs.p, contigStart.p, n_contigs, posKey.p});
+
+    dupBits.ensure((size_t)(n / 32 + 2)); dev_memset(rt, dupBits.p, 0, sizeof(uint32_t) * (size_t)(n / 32 + 2));
+    DevBuf<unsigned long long> cnt; cnt.ensure(1); dev_memset(rt, cnt.p, 0, sizeof(unsigned long long));
+    foreach(rt, n, DupFn{sortedHash.p, sortedPos.p, posKey.p, n, dupBits.p, cnt.p, 0, nullptr, nullptr});
+    unsigned long long nd = 0; d2h(rt, &nd, cnt.p, sizeof(nd));
+    n_dup = (int64_t)nd;
+    if (n_dup) {
+      DevBuf<uint32_t> tIdx; DevBuf<uint64_t> tLinks;
+      tIdx.ensure((size_t)n_dup); tLinks.ensure((size_t)n_dup);
+      dev_memset(rt, cnt.p, 0, sizeof(unsigned long long));
+      foreach(rt, n, DupFn{sortedHash.p, sortedPos.p, posKey.p, n, dupBits.p, cnt.p, 1, tIdx.p, tLinks.p});
+      dupIdx.ensure((size_t)n_dup); dupLinks.ensure((size_t)n_dup);
+      pr.sort_pairs<uint32_t, uint64_t>(tIdx.p, dupIdx.p, tLinks.p, dupLinks.p, n_dup);
+      rt.sync();
+    }
+    rt.sync();
+  }
+
+  int64_t device_bytes() const {
+    return (int64_t)(miHash.bytes() + miWs.bytes() + table.bytes() + posKey.bytes() + dupBits.bytes() + dupIdx.bytes() +
+                     dupLinks.bytes() + contigStart.bytes() + contigLen.bytes());
+  }
+};
+
+}  // namespace mm

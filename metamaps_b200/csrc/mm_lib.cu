@@ -1,0 +1,449 @@
+// mm_lib.cu -- the C ABI declared in include/metamaps_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -> libmetamaps_b200.so (see metamaps_b200/build.py).
+// (tests/_emu compiles this same file with g++ -DMM_HOST_EMU to check kernel logic without a GPU;
+//  that library is test infrastructure and is never loaded by the product.)
+#include "../../include/metamaps_b200.h"
+
+#include "mm_em.h"
+#include "mm_index.h"
+#include "mm_map.h"
+#include "mm_mapq.h"
+
+#ifndef MM_HOST_EMU
+#include <dlfcn.h>
+#endif
+
+using namespace mm;
+
+static thread_local std::string g_err;
+
+struct mm_ctx {
+  Runtime rt;
+  Prims pr;
+  Sketcher sk;
+  Mapper mp;
+  SeqBatch sketchBatch;
+  SketchOut sketchOut;
+  double last_ms = 0;
+  int64_t last_launches = 0;
+  // NCCL (multi-GPU EM), bound at run time
+  void* ncclLib = nullptr; void* comm = nullptr; int nRanks = 1, rank = 0;
+  mm_ctx() : pr(rt), sk(rt, pr), mp(rt, pr, sk) {}
+};
+struct mm_index {
+  mm_ctx* ctx;
+  Index ix;
+  mm_index(mm_ctx* c, int k, int w) : ctx(c), ix(c->rt, c->pr, c->sk, k, w) {}
+};
+
+#define MM_TRY try {
+#define MM_CATCH                                                   \
+  }                                                                \
+  catch (const mm::Error& e) { g_err = e.what(); return e.code; }  \
+  catch (const std::bad_alloc&) { g_err = "out of host memory"; return MM_ENOMEM; } \
+  catch (const std::exception& e) { g_err = e.what(); return MM_EINVAL; }           \
+  return MM_OK;
+
+static void begin_call(mm_ctx* c) {
+#ifndef MM_HOST_EMU
+  MM_CUDA(cudaSetDevice(c->rt.device));
+#endif
+  c->rt.launches = 0; c->last_ms = 0;
+}
+static void end_call(mm_ctx* c) { c->rt.sync(); c->rt.resolve_timers(); c->last_launches = c->rt.launches; }
+
+extern "C" {
+
+const char* mm_last_error(void) { return g_err.c_str(); }
+const char* mm_version(void) {
+#ifdef MM_HOST_EMU
+  return "metamaps_b200 0.1 (HOST EMULATION - test build, not a product path)";
+#else
+  return "metamaps_b200 0.1 (sm_100a)";
+#endif
+}
+
+int mm_ctx_create(int device, mm_ctx** out) {
+  MM_TRY
+  if (!out) throw Error(MM_EINVAL, "mm_ctx_create: out is NULL");
+#ifndef MM_HOST_EMU
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { cudaGetLastError(); throw Error(MM_ENODEV, "no CUDA device available: this library has no CPU path"); }
+  if (device < 0 || device >= n) throw Error(MM_EINVAL, "device ordinal out of range");
+  MM_CUDA(cudaSetDevice(device));
+#endif
+  mm_ctx* c = new mm_ctx();
+  c->rt.device = device;
+#ifndef MM_HOST_EMU
+  cudaDeviceProp prop; MM_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->rt.sm_count = prop.multiProcessorCount;
+  MM_CUDA(cudaStreamCreateWithFlags(&c->rt.stream, cudaStreamNonBlocking));
+#endif
+  *out = c;
+  MM_CATCH
+}
+void mm_ctx_destroy(mm_ctx* c) {
+  if (!c) return;
+#ifndef MM_HOST_EMU
+  cudaSetDevice(c->rt.device);
+  cudaStreamSynchronize(c->rt.stream);
+#endif
+  mm_comm_destroy(c);
+#ifndef MM_HOST_EMU
+  cudaStream_t s = c->rt.stream;
+  delete c;
+  cudaStreamDestroy(s);
+#else
+  delete c;
+#endif
+}
+int mm_ctx_last_timing(mm_ctx* c, double* total_ms, int64_t* n_launches) {
+  if (!c) return MM_EINVAL;
+  if (total_ms) *total_ms = c->last_ms;
+  if (n_launches) *n_launches = c->last_launches;
+  return MM_OK;
+}
+int mm_ctx_last_map_stats(mm_ctx* c, double* stage_ms, int64_t* counters) {
+  if (!c) return MM_EINVAL;
+  for (int i = 0; i < 8; i++) { if (stage_ms) stage_ms[i] = c->mp.st.ms[i]; if (counters) counters[i] = c->mp.st.counters[i]; }
+  return MM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+int mm_sketch_batch(mm_ctx* c, const char* seqs, const int64_t* offsets, int32_t n, int k, int w, int64_t* n_total) {
+  MM_TRY
+  if (!c || !offsets || n < 0 || (!seqs && n > 0)) throw Error(MM_EINVAL, "mm_sketch_batch: bad arguments");
+  if (k < 1 || k > 16) throw Error(MM_EINVAL, "k-mer size must be in [1,16] (parseCmdArgs.hpp:62)");
+  if (w < 1) throw Error(MM_EINVAL, "window size must be >= 1");
+  begin_call(c);
+  c->sk.load(c->sketchBatch, seqs, nullptr, offsets, n);
+  { StageTimer t(c->rt, &c->last_ms); c->sk.run(c->sketchBatch, k, w, c->sketchOut); }
+  end_call(c);
+  if (n_total) *n_total = c->sketchOut.n_total;
+  MM_CATCH
+}
+struct UnpackWsFn {
+  const uint32_t* ws; int32_t* wpos; int32_t* strand;
+  MM_HD void operator()(int64_t i) const { uint32_t v = ldg(ws + i); wpos[i] = (int32_t)(v >> 1); strand[i] = (v & 1u) ? 1 : -1; }
+};
+int mm_sketch_fetch(mm_ctx* c, int64_t* counts, uint32_t* hash, int32_t* wpos, int32_t* strand) {
+  MM_TRY
+  if (!c) throw Error(MM_EINVAL, "null ctx");
+  begin_call(c);
+  SketchOut& o = c->sketchOut;
+  if (counts) { d2h(c->rt, counts, o.seqOff.p, sizeof(int64_t) * ((size_t)o.n_seqs + 1)); }
+  if (hash) d2h(c->rt, hash, o.hash.p, sizeof(uint32_t) * (size_t)o.n_total);
+  if ((wpos || strand) && o.n_total) {
+    DevBuf<int32_t> a, b; a.ensure((size_t)o.n_total); b.ensure((size_t)o.n_total);
+    foreach(c->rt, o.n_total, UnpackWsFn{o.ws.p, a.p, b.p});
+    if (wpos) d2h(c->rt, wpos, a.p, sizeof(int32_t) * (size_t)o.n_total);
+    if (strand) d2h(c->rt, strand, b.p, sizeof(int32_t) * (size_t)o.n_total);
+    c->rt.sync();
+  }
+  MM_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+int mm_index_create(mm_ctx* c, int k, int w, mm_index** out) {
+  MM_TRY
+  if (!c || !out) throw Error(MM_EINVAL, "mm_index_create: bad arguments");
+  if (k < 1 || k > 16) throw Error(MM_EINVAL, "k-mer size must be in [1,16] (parseCmdArgs.hpp:62)");
+  if (w < 1) throw Error(MM_EINVAL, "window size must be >= 1");
+  *out = new mm_index(c, k, w);
+  MM_CATCH
+}
+static int index_add_impl(mm_index* idx, const char* seqs, const void* dev, const int64_t* offsets, int32_t n) {
+  MM_TRY
+  if (!idx || !offsets || n < 0) throw Error(MM_EINVAL, "mm_index_add: bad arguments");
+  mm_ctx* c = idx->ctx;
+  begin_call(c);
+  c->sk.load(c->sketchBatch, seqs, dev, offsets, n);
+  { StageTimer t(c->rt, &c->last_ms); idx->ix.add(c->sketchBatch); }
+  end_call(c);
+  MM_CATCH
+}
+int mm_index_add(mm_index* idx, const char* seqs, const int64_t* offsets, int32_t n) { return index_add_impl(idx, seqs, nullptr, offsets, n); }
+int mm_index_add_dev(mm_index* idx, const void* dev, const int64_t* offsets, int32_t n) {
+  if (!dev) { g_err = "mm_index_add_dev: null device pointer"; return MM_EINVAL; }
+  return index_add_impl(idx, nullptr, dev, offsets, n);
+}
+int mm_index_finalize(mm_index* idx) {
+  MM_TRY
+  if (!idx) throw Error(MM_EINVAL, "null index");
+  begin_call(idx->ctx);
+  { StageTimer t(idx->ctx->rt, &idx->ctx->last_ms); idx->ix.finalize(); }
+  end_call(idx->ctx);
+  MM_CATCH
+}
+int mm_index_stats(const mm_index* idx, int64_t* n_min, int64_t* n_unique, int32_t* freq, int32_t* n_contigs, int64_t* bytes) {
+  if (!idx) { g_err = "null index"; return MM_EINVAL; }
+  if (n_min) *n_min = idx->ix.n;
+  if (n_unique) *n_unique = idx->ix.n_unique;
+  if (freq) *freq = idx->ix.freqThreshold;
+  if (n_contigs) *n_contigs = idx->ix.n_contigs;
+  if (bytes) *bytes = idx->ix.device_bytes();
+  return MM_OK;
+}
+int mm_index_fetch(const mm_index* idx, uint32_t* hash, int32_t* seq_id, int32_t* wpos, int32_t* strand) {
+  MM_TRY
+  if (!idx) throw Error(MM_EINVAL, "null index");
+  mm_ctx* c = idx->ctx; const Index& ix = idx->ix;
+  begin_call(c);
+  if (hash) d2h(c->rt, hash, ix.miHash.p, sizeof(uint32_t) * (size_t)ix.n);
+  if ((wpos || strand) && ix.n) {
+    DevBuf<int32_t> a, b; a.ensure((size_t)ix.n); b.ensure((size_t)ix.n);
+    foreach(c->rt, ix.n, UnpackWsFn{ix.miWs.p, a.p, b.p});
+    if (wpos) d2h(c->rt, wpos, a.p, sizeof(int32_t) * (size_t)ix.n);
+    if (strand) d2h(c->rt, strand, b.p, sizeof(int32_t) * (size_t)ix.n);
+    c->rt.sync();
+  }
+  if (seq_id)
+    for (int32_t s = 0; s < ix.n_contigs; s++)
+      for (int64_t i = ix.h_contigStart[(size_t)s]; i < ix.h_contigStart[(size_t)s + 1]; i++) seq_id[i] = s;
+  MM_CATCH
+}
+int mm_index_lookup(const mm_index* idx, const uint32_t* hashes, int64_t n, int32_t* counts) {
+  MM_TRY
+  if (!idx || !idx->ix.finalized) throw Error(MM_EINVAL, "index not finalized");
+  mm_ctx* c = idx->ctx;
+  begin_call(c);
+  DevBuf<uint32_t> h; DevBuf<int32_t> o; h.ensure((size_t)n); o.ensure((size_t)n);
+  h2d(c->rt, h.p, hashes, sizeof(uint32_t) * (size_t)n);
+  foreach(c->rt, n, LookupFn{idx->ix.table.p, idx->ix.tableMask, h.p, o.p});
+  d2h(c->rt, counts, o.p, sizeof(int32_t) * (size_t)n);
+  end_call(c);
+  MM_CATCH
+}
+void mm_index_destroy(mm_index* idx) {
+  if (!idx) return;
+#ifndef MM_HOST_EMU
+  cudaSetDevice(idx->ctx->rt.device);
+#endif
+  delete idx;
+}
+
+// ------------------------------------------------------------------------------------------------ K3-K5
+static int map_impl(mm_ctx* c, const mm_index* idx, const char* reads, const void* dev, const int64_t* offsets, int32_t n,
+                    const mm_map_params* p, mm_map_summary* out) {
+  MM_TRY
+  if (!c || !idx || !offsets || !p || n < 0) throw Error(MM_EINVAL, "mm_map_batch: bad arguments");
+  if (idx->ctx != c) throw Error(MM_EINVAL, "index belongs to another context");
+  if (!idx->ix.finalized) throw Error(MM_EINVAL, "index not finalized");
+  begin_call(c);
+  c->sk.load(c->mp.batch, reads, dev, offsets, n);
+  int64_t s[6];
+  { StageTimer t(c->rt, &c->last_ms); c->mp.run(idx->ix, p->perc_identity, p->min_read_len, s); }
+  end_call(c);
+  if (out) { out->n_reads = s[0]; out->n_too_short = s[1]; out->n_candidates = s[2]; out->n_mappings = s[3]; out->n_reads_mapped = s[4]; out->total_bases_mapped_reads = s[5]; }
+  MM_CATCH
+}
+int mm_map_batch(mm_ctx* c, const mm_index* idx, const char* reads, const int64_t* offsets, int32_t n, const mm_map_params* p, mm_map_summary* out) {
+  if (!reads && n > 0) { g_err = "mm_map_batch: null reads"; return MM_EINVAL; }
+  return map_impl(c, idx, reads, nullptr, offsets, n, p, out);
+}
+int mm_map_batch_dev(mm_ctx* c, const mm_index* idx, const void* dev, const int64_t* offsets, int32_t n, const mm_map_params* p, mm_map_summary* out) {
+  if (!dev) { g_err = "mm_map_batch_dev: null device pointer"; return MM_EINVAL; }
+  return map_impl(c, idx, nullptr, dev, offsets, n, p, out);
+}
+struct MinHitsOfFn {
+  const int32_t* sOf; const int32_t* tab; int32_t* out;
+  MM_HD void operator()(int64_t r) const { int32_t s = ldg(sOf + r); out[r] = s > 0 ? ldg(tab + s) : 0; }
+};
+int mm_map_fetch_reads(mm_ctx* c, int32_t* sketch_size, int32_t* minimum_hits, int64_t* cand_offsets) {
+  MM_TRY
+  if (!c) throw Error(MM_EINVAL, "null ctx");
+  Mapper& m = c->mp;
+  begin_call(c);
+  if (sketch_size) d2h(c->rt, sketch_size, m.sOf.p, sizeof(int32_t) * (size_t)m.n_reads);
+  if (minimum_hits && m.n_reads) {
+    DevBuf<int32_t> t; t.ensure((size_t)m.n_reads);
+    foreach(c->rt, m.n_reads, MinHitsOfFn{m.sOf.p, m.dMinHits.p, t.p});
+    d2h(c->rt, minimum_hits, t.p, sizeof(int32_t) * (size_t)m.n_reads);
+  }
+  if (cand_offsets) d2h(c->rt, cand_offsets, m.candOff.p, sizeof(int64_t) * ((size_t)m.n_reads + 1));
+  c->rt.sync();
+  MM_CATCH
+}
+int mm_map_fetch_candidates(mm_ctx* c, int32_t* seq_id, int32_t* range_start, int32_t* range_end, int32_t* pos, int32_t* shared,
+                            int32_t* votes, int32_t* accepted, int32_t* valid, int64_t* opt_start, int64_t* opt_end) {
+  MM_TRY
+  if (!c) throw Error(MM_EINVAL, "null ctx");
+  Mapper& m = c->mp; size_t n = (size_t)m.n_cand;
+  begin_call(c);
+  if (seq_id) d2h(c->rt, seq_id, m.cSeq.p, 4 * n);
+  if (range_start) d2h(c->rt, range_start, m.cStart.p, 4 * n);
+  if (range_end) d2h(c->rt, range_end, m.cEnd.p, 4 * n);
+  if (pos) d2h(c->rt, pos, m.oPos.p, 4 * n);
+  if (shared) d2h(c->rt, shared, m.oShared.p, 4 * n);
+  if (votes) d2h(c->rt, votes, m.oVotes.p, 4 * n);
+  if (accepted) d2h(c->rt, accepted, m.oAccept.p, 4 * n);
+  if (valid) d2h(c->rt, valid, m.oValid.p, 4 * n);
+  if (opt_start) d2h(c->rt, opt_start, m.oOptS.p, 8 * n);
+  if (opt_end) d2h(c->rt, opt_end, m.oOptE.p, 8 * n);
+  c->rt.sync();
+  MM_CATCH
+}
+struct StrandOfFn { const uint8_t* q; int32_t* out; MM_HD void operator()(int64_t i) const { out[i] = ldg(q + i) ? 1 : -1; } };
+int mm_map_fetch_sketch(mm_ctx* c, int64_t* offsets, uint32_t* hash, int32_t* strand, int64_t cap) {
+  MM_TRY
+  if (!c) throw Error(MM_EINVAL, "null ctx");
+  Mapper& m = c->mp;
+  begin_call(c);
+  if (offsets) d2h(c->rt, offsets, m.qOff.p, sizeof(int64_t) * ((size_t)m.n_reads + 1));
+  if (cap < m.n_q && (hash || strand)) throw Error(MM_ERANGE, "mm_map_fetch_sketch: capacity too small");
+  if (hash) d2h(c->rt, hash, m.qHash.p, sizeof(uint32_t) * (size_t)m.n_q);
+  if (strand && m.n_q) {
+    DevBuf<int32_t> t; t.ensure((size_t)m.n_q);
+    foreach(c->rt, m.n_q, StrandOfFn{m.qStrand.p, t.p});
+    d2h(c->rt, strand, t.p, sizeof(int32_t) * (size_t)m.n_q);
+  }
+  c->rt.sync();
+  MM_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------ host statistics
+int mm_stat_min_hits_relaxed(int s, int k, float pi) { return stats::estimateMinimumHitsRelaxed(s, k, pi); }
+int mm_stat_recommended_window(double p, int k, int alphabet, float pi, int lenQ, uint64_t lenR) { return stats::recommendedWindowSize(p, k, alphabet, pi, lenQ, lenR); }
+double mm_stat_estimate_pvalue(int s, int k, int alphabet, float pi, int lenQ, uint64_t lenR) { return stats::estimate_pvalue(s, k, alphabet, pi, lenQ, lenR); }
+void mm_stat_identity(int shared, int s, int k, float* a, float* b) { stats::identity(shared, s, k, a, b); }
+
+// ------------------------------------------------------------------------------------------------ K6
+int mm_mapq_batch(mm_ctx* c, const double* identity, const int32_t* shared, const int32_t* sketch, const int32_t* read_len,
+                  const int64_t* read_off, int64_t n_reads, int k, double* mapq, int32_t* status) {
+  MM_TRY
+  if (!c || !read_off || n_reads < 0) throw Error(MM_EINVAL, "mm_mapq_batch: bad arguments");
+  begin_call(c);
+  int64_t M = read_off[n_reads];
+  DevBuf<double> dId, dQ; DevBuf<int32_t> dSh, dSk, dLen, dSt; DevBuf<int64_t> dOff;
+  dId.ensure((size_t)M); dQ.ensure((size_t)M); dSh.ensure((size_t)M); dSk.ensure((size_t)M);
+  dLen.ensure((size_t)n_reads); dSt.ensure((size_t)n_reads); dOff.ensure((size_t)n_reads + 1);
+  h2d(c->rt, dId.p, identity, 8 * (size_t)M); h2d(c->rt, dSh.p, shared, 4 * (size_t)M); h2d(c->rt, dSk.p, sketch, 4 * (size_t)M);
+  h2d(c->rt, dLen.p, read_len, 4 * (size_t)n_reads); h2d(c->rt, dOff.p, read_off, 8 * ((size_t)n_reads + 1));
+  { StageTimer t(c->rt, &c->last_ms); foreach(c->rt, n_reads, MapqFn{dId.p, dSh.p, dSk.p, dLen.p, dOff.p, k, dQ.p, dSt.p}); }
+  d2h(c->rt, mapq, dQ.p, 8 * (size_t)M);
+  if (status) d2h(c->rt, status, dSt.p, 4 * (size_t)n_reads);
+  end_call(c);
+  MM_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL binding
+struct NcclUid { char b[128]; };
+typedef int (*fn_ncclGetUniqueId)(NcclUid*);
+typedef int (*fn_ncclCommInitRank)(void**, int, NcclUid, int);
+typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(void*);
+static void* nccl_open() {
+#ifdef MM_HOST_EMU
+  throw Error(MM_ENODEV, "NCCL is not available in the host-emulation test build");
+#else
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) throw Error(MM_ENODEV, std::string("cannot load libnccl.so.2: ") + dlerror());
+  return h;
+#endif
+}
+static void* nccl_sym(void* h, const char* n) {
+#ifdef MM_HOST_EMU
+  (void)h; (void)n; return nullptr;
+#else
+  void* p = dlsym(h, n);
+  if (!p) throw Error(MM_ENODEV, std::string("libnccl is missing ") + n);
+  return p;
+#endif
+}
+int mm_comm_unique_id(void* id) {
+  MM_TRY
+  if (!id) throw Error(MM_EINVAL, "null id buffer");
+  void* h = nccl_open();
+  int rc = ((fn_ncclGetUniqueId)nccl_sym(h, "ncclGetUniqueId"))((NcclUid*)id);
+  if (rc != 0) throw Error(MM_ECUDA, "ncclGetUniqueId failed: " + std::to_string(rc));
+  MM_CATCH
+}
+int mm_comm_init(mm_ctx* c, int n_ranks, int rank, const void* id) {
+  MM_TRY
+  if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) throw Error(MM_EINVAL, "mm_comm_init: bad arguments");
+  begin_call(c);
+  c->ncclLib = nccl_open();
+  NcclUid u; memcpy(&u, id, sizeof(u));
+  int rc = ((fn_ncclCommInitRank)nccl_sym(c->ncclLib, "ncclCommInitRank"))(&c->comm, n_ranks, u, rank);
+  if (rc != 0) { c->comm = nullptr; throw Error(MM_ECUDA, "ncclCommInitRank failed: " + std::to_string(rc)); }
+  c->nRanks = n_ranks; c->rank = rank;
+  MM_CATCH
+}
+int mm_comm_destroy(mm_ctx* c) {
+  if (!c) return MM_EINVAL;
+  if (c->comm && c->ncclLib) {
+    try { ((fn_ncclCommDestroy)nccl_sym(c->ncclLib, "ncclCommDestroy"))(c->comm); } catch (...) {}
+  }
+  c->comm = nullptr; c->nRanks = 1; c->rank = 0;
+  return MM_OK;
+}
+static void allreduce_sum_f64(mm_ctx* c, double* buf, size_t n) {
+  if (!c->comm || c->nRanks == 1) return;
+  int rc = ((fn_ncclAllReduce)nccl_sym(c->ncclLib, "ncclAllReduce"))(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->rt.stream);
+  if (rc != 0) throw Error(MM_ECUDA, "ncclAllReduce failed: " + std::to_string(rc));
+  c->rt.launches++;
+}
+
+// ------------------------------------------------------------------------------------------------ K7/K8
+int mm_em_run(mm_ctx* c, const int32_t* taxon, const double* mapq, const double* nloc, const int64_t* read_off, int64_t n_reads,
+              int32_t T, int32_t max_iter, double* f_out, double* posterior, int64_t* best, double* ll_hist, int32_t ll_cap, int32_t* n_iter) {
+  MM_TRY
+  if (!c || !read_off || n_reads < 0 || T < 1) throw Error(MM_EINVAL, "mm_em_run: bad arguments");
+  begin_call(c);
+  Runtime& rt = c->rt; Prims& pr = c->pr;
+  int64_t M = read_off[n_reads];
+  if (M >= ((int64_t)1 << 32)) throw Error(MM_ERANGE, "more than 2^32 mappings on one rank: partition the reads");
+  DevBuf<int32_t> dTax, dReadOf, dReadT; DevBuf<double> dMq, dNl, dW, dWT, dF, dAcc, dRsum, dLog, dPost, dTot; DevBuf<int64_t> dOff, dBest;
+  DevBuf<uint32_t> dIota, dPerm, dTaxKey, dTaxT;
+  dTax.ensure((size_t)M); dReadOf.ensure((size_t)M); dReadT.ensure((size_t)M); dMq.ensure((size_t)M); dNl.ensure((size_t)M);
+  dW.ensure((size_t)M); dWT.ensure((size_t)M); dIota.ensure((size_t)M); dPerm.ensure((size_t)M); dTaxT.ensure((size_t)M);
+  dF.ensure((size_t)T); dAcc.ensure((size_t)T + 1); dRsum.ensure((size_t)n_reads + 1); dLog.ensure((size_t)n_reads + 1);
+  dPost.ensure((size_t)M); dTot.ensure(2); dOff.ensure((size_t)n_reads + 1); dBest.ensure((size_t)n_reads + 1);
+  h2d(rt, dTax.p, taxon, 4 * (size_t)M); h2d(rt, dMq.p, mapq, 8 * (size_t)M); h2d(rt, dNl.p, nloc, 8 * (size_t)M);
+  h2d(rt, dOff.p, read_off, 8 * ((size_t)n_reads + 1));
+  int iters = 0;
+  {
+    StageTimer tm(rt, &c->last_ms);
+    foreach(rt, M, EmPrepFn{dMq.p, dNl.p, dOff.p, n_reads, dW.p, dReadOf.p, dIota.p});
+    int bits = 1; while (bits < 32 && ((int64_t)1 << bits) < T) bits++;
+    pr.sort_pairs<uint32_t, uint32_t>((const uint32_t*)dTax.p, dTaxT.p, dIota.p, dPerm.p, M, bits);
+    foreach(rt, M, EmPermuteFn{dPerm.p, dW.p, dReadOf.p, dWT.p, dReadT.p});
+    foreach(rt, T, EmFillFn{dF.p, 1.0 / (double)T});                       // fEM.h:491-495
+    double ll_last = 0; bool cont = true;
+    int64_t tiles = (M + EM_TILE - 1) / EM_TILE;
+    while (cont) {
+      foreach(rt, n_reads, EmReadSumFn{dTax.p, dW.p, dOff.p, dF.p, dRsum.p, dLog.p});
+      dev_memset(rt, dAcc.p, 0, sizeof(double) * ((size_t)T + 1));
+      if (M > 0) foreach(rt, tiles, EmTaxonSumFn{dTaxT.p, dWT.p, dReadT.p, dRsum.p, dAcc.p, M});
+      foreach(rt, T, EmScaleFn{dF.p, dAcc.p});
+      if (n_reads > 0) pr.reduce_sum<double>(dLog.p, dAcc.p + T, n_reads);   // ll rides in slot T of the all-reduce buffer
+      allreduce_sum_f64(c, dAcc.p, (size_t)T + 1);
+      pr.reduce_sum<double>(dAcc.p, dTot.p, T);
+      foreach(rt, T, EmNormFn{dAcc.p, dTot.p, dF.p});                       // fEM.h:606-615
+      double ll = 0; d2h(rt, &ll, dAcc.p + T, sizeof(double));
+      if (iters < ll_cap && ll_hist) ll_hist[iters] = ll;
+      if (iters > 0 && max_iter <= 0) {                                     // fEM.h:624-640
+        double diff = ll - ll_last, rel = ll / ll_last;
+        if (diff <= 1 && (1 - rel) < 0.0001) cont = false;
+      }
+      iters++; ll_last = ll;
+      if (max_iter > 0 && iters >= max_iter) cont = false;
+    }
+    foreach(rt, n_reads, EmFinalFn{dTax.p, dW.p, dOff.p, dF.p, dPost.p, dBest.p});
+  }
+  if (f_out) d2h(rt, f_out, dF.p, 8 * (size_t)T);
+  if (posterior) d2h(rt, posterior, dPost.p, 8 * (size_t)M);
+  if (best) d2h(rt, best, dBest.p, 8 * (size_t)n_reads);
+  if (n_iter) *n_iter = iters;
+  end_call(c);
+  MM_CATCH
+}
+
+#ifdef MM_HOST_EMU
+// test hook (host-emulation build only): the std::sort replay, checked against the real std::sort by tests
+void mm_emu_stdsort(uint64_t* a, int64_t n) { mm::stdsort::sort(a, n); }
+#endif
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// mm_platform.h -- device plumbing: memory, launches, timing, error handling.
+//
+// Every kernel in this library is written as a functor with `MM_HD void operator()(int64_t item)`
+// (or a block-cooperative __global__ kernel in the .cu files) and launched through mm::foreach().
+// Defining MM_HOST_EMU compiles the same functors for the host and runs them in a loop; that build
+// (tests/_emu) exists ONLY so the kernel logic can be checked against the oracle on a machine without
+// a GPU.  It is never shipped, never loaded by the product, and is not a fallback: the product library
+// is the nvcc build and mm_ctx_create fails without a CUDA device.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef MM_HOST_EMU
+#define MM_HD inline
+#define MM_DEV inline
+typedef int cudaStream_t;
+struct uint2 { unsigned int x, y; };
+struct uint4 { unsigned int x, y, z, w; };
+inline uint2 make_uint2(unsigned int x, unsigned int y) { uint2 v; v.x = x; v.y = y; return v; }
+#else
+#include <cuda_runtime.h>
+#define MM_HD __host__ __device__ __forceinline__
+#define MM_DEV __device__ __forceinline__
+#endif
+
+namespace mm {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#ifndef MM_HOST_EMU
+#define MM_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      throw mm::Error(-5, std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + __FILE__ + \
+                              ":" + std::to_string(__LINE__));                                     \
+  } while (0)
+#endif
+
+// ---- per-context launch bookkeeping -------------------------------------------------------------
+struct Runtime {
+  int device = 0;
+  cudaStream_t stream = 0;
+  int sm_count = 148;
+  int64_t launches = 0;          // kernels launched since reset()
+  double total_ms = 0;           // filled by StageTimer users
+#ifndef MM_HOST_EMU
+  struct Pending { cudaEvent_t a = nullptr, b = nullptr; double* acc = nullptr; bool closed = false; };
+  std::vector<Pending> pending;
+#endif
+  void sync() {
+#ifndef MM_HOST_EMU
+    MM_CUDA(cudaStreamSynchronize(stream));
+#endif
+  }
+  // call after sync(): folds every closed StageTimer into its accumulator
+  void resolve_timers() {
+#ifndef MM_HOST_EMU
+    for (auto& p : pending) {
+      if (p.closed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess && p.acc) *p.acc += ms;
+      }
+      cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    pending.clear();
+#endif
+  }
+};
+
+// ---- memory --------------------------------------------------------------------------------------
+inline void* dev_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 16;
+#ifdef MM_HOST_EMU
+  void* p = malloc(bytes);
+  if (!p) throw Error(-12, "host-emu alloc failed");
+  return p;
+#else
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(-12, "cudaMalloc(" + std::to_string(bytes) + " B) failed: " + cudaGetErrorString(e));
+  }
+  return p;
+#endif
+}
+inline void dev_free(void* p) {
+  if (!p) return;
+#ifdef MM_HOST_EMU
+  free(p);
+#else
+  cudaFree(p);
+#endif
+}
+inline void h2d(Runtime& rt, void* d, const void* h, size_t bytes) {
+  if (!bytes) return;
+#ifdef MM_HOST_EMU
+  memcpy(d, h, bytes);
+#else
+  MM_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, rt.stream));
+#endif
+}
+inline void d2h(Runtime& rt, void* h, const void* d, size_t bytes) {
+  if (!bytes) return;
+#ifdef MM_HOST_EMU
+  memcpy(h, d, bytes);
+#else
+  MM_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, rt.stream));
+  MM_CUDA(cudaStreamSynchronize(rt.stream));
+#endif
+}
+inline void d2d(Runtime& rt, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+#ifdef MM_HOST_EMU
+  memmove(dst, src, bytes);
+#else
+  MM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, rt.stream));
+#endif
+}
+inline void dev_memset(Runtime& rt, void* d, int v, size_t bytes) {
+  if (!bytes) return;
+#ifdef MM_HOST_EMU
+  memset(d, v, bytes);
+#else
+  MM_CUDA(cudaMemsetAsync(d, v, bytes, rt.stream));
+#endif
+}
+
+// Growable device array.  Not copyable; freed on destruction.
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;   // elements
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { dev_free(p); }
+  void release() { dev_free(p); p = nullptr; cap = 0; }
+  // contents are NOT preserved
+  T* ensure(size_t n) {
+    if (n > cap) {
+      dev_free(p); p = nullptr; cap = 0;
+      size_t want = n + n / 8 + 64;
+      p = (T*)dev_alloc(want * sizeof(T));
+      cap = want;
+    }
+    return p;
+  }
+  // contents [0,keep) preserved
+  T* grow(Runtime& rt, size_t n, size_t keep) {
+    if (n > cap) {
+      size_t want = n + n / 2 + 64;
+      T* q = (T*)dev_alloc(want * sizeof(T));
+      if (keep) d2d(rt, q, p, keep * sizeof(T));
+#ifndef MM_HOST_EMU
+      if (keep) MM_CUDA(cudaStreamSynchronize(rt.stream));
+#endif
+      dev_free(p);
+      p = q; cap = want;
+    }
+    return p;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+// ---- launches ------------------------------------------------------------------------------------
+#ifndef MM_HOST_EMU
+template <class F>
+__global__ void __launch_bounds__(256) foreach_kernel(int64_t n, F f) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+template <class F>
+__global__ void __launch_bounds__(128) foreach_kernel128(int64_t n, F f) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+#endif
+
+// One logical thread per item.  Grid = a multiple of the SM count (grid-stride loop), so the last wave
+// is never a sliver (148 SMs, see DESIGN.md "grid sizing").
+template <class F>
+inline void foreach(Runtime& rt, int64_t n, const F& f, int block = 256, int ctas_per_sm = 8) {
+  if (n <= 0) return;
+#ifdef MM_HOST_EMU
+  for (int64_t i = 0; i < n; i++) f(i);
+  rt.launches++;
+#else
+  int64_t need = (n + block - 1) / block;
+  int64_t maxg = (int64_t)rt.sm_count * ctas_per_sm;
+  int grid = (int)(need < maxg ? need : maxg);
+  if (block == 128) foreach_kernel128<F><<<grid, 128, 0, rt.stream>>>(n, f);
+  else foreach_kernel<F><<<grid, 256, 0, rt.stream>>>(n, f);
+  MM_CUDA(cudaGetLastError());
+  rt.launches++;
+#endif
+}
+
+// ---- atomics / intrinsics usable from functors -----------------------------------------------------
+template <class T>
+MM_HD T atomic_add(T* p, T v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  T o = *p; *p = o + v; return o;
+#endif
+}
+MM_HD unsigned long long atomic_add_u64(unsigned long long* p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  unsigned long long o = *p; *p = o + v; return o;
+#endif
+}
+MM_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
+#if defined(__CUDA_ARCH__)
+  return atomicCAS(p, cmp, val);
+#else
+  uint32_t o = *p; if (o == cmp) *p = val; return o;
+#endif
+}
+MM_HD uint32_t atomic_or_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return atomicOr(p, v);
+#else
+  uint32_t o = *p; *p = o | v; return o;
+#endif
+}
+template <class T>
+MM_HD T ldg(const T* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// ---- stage timing ----------------------------------------------------------------------------------
+// Events are recorded on the context stream without synchronising; Runtime::resolve_timers() (called once
+// the entry point has synchronised anyway) turns them into milliseconds.
+struct StageTimer {
+  Runtime& rt;
+  int slot;
+  StageTimer(Runtime& r, double* accum) : rt(r), slot(-1) {
+#ifndef MM_HOST_EMU
+    Runtime::Pending p; p.acc = accum;
+    MM_CUDA(cudaEventCreate(&p.a)); MM_CUDA(cudaEventCreate(&p.b));
+    MM_CUDA(cudaEventRecord(p.a, rt.stream));
+    rt.pending.push_back(p); slot = (int)rt.pending.size() - 1;
+#else
+    (void)accum;
+#endif
+  }
+  void stop() {
+#ifndef MM_HOST_EMU
+    if (slot < 0) return;
+    MM_CUDA(cudaEventRecord(rt.pending[slot].b, rt.stream));
+    rt.pending[slot].closed = true;
+    slot = -1;
+#endif
+  }
+  ~StageTimer() {
+#ifndef MM_HOST_EMU
+    try { stop(); } catch (...) {}
+#endif
+  }
+};
+
+}  // namespace mm

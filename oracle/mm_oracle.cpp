@@ -416,7 +416,8 @@ int mmo_mapq(const double* identity, const int32_t* shared, const int32_t* sketc
 // fEM.h:491-661 (EM loop) + :234-373 (per-read posterior) + :693-716 (final pass) on arrays:
 //   taxon[m]  index into f, mapq[m] = column 14, nloc[m] = mappingLocations_per_taxonID for that read/taxon,
 //   read_off[r..r+1] delimits the mappings of read r (reads with >= 1 mapping only).
-// max_iter <= 0: run to the reference's stopping rule (:636).  Returns the number of EM rounds run.
+// max_iter <= 0: run to the reference's stopping rule (:636); max_iter > 0: exactly max_iter rounds (the
+// reference has no cap; BASELINE config 4 benchmarks a fixed round count).  Returns the rounds run.
 int mmo_em(const int32_t* taxon, const double* mapq, const double* nloc, const int64_t* read_off, int64_t n_reads, int T,
            int max_iter, double* f, double* posterior, int64_t* best, double* ll_hist, int ll_cap) {
   std::vector<double> fcur(T, 1.0 / (double)T), fn(T);
@@ -433,7 +434,7 @@ int mmo_em(const int32_t* taxon, const double* mapq, const double* nloc, const i
     double sum = 0; for (double v : fn) sum += v;
     for (double& v : fn) v /= sum;
     if (it < ll_cap) ll_hist[it] = ll;
-    if (it > 0) {
+    if (it > 0 && max_iter <= 0) {
       double diff = ll - ll_last, rel = ll / ll_last;
       if (diff <= 1 && (1 - rel) < 0.0001) cont = false;
     }

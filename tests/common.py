@@ -1,0 +1,165 @@
+"""Parity assertions shared by the host-emulation tests (CPU) and the GPU tests: every function takes a
+metamaps_b200.capi.Context and compares what comes out of the C ABI with the oracle / golden fixtures."""
+import numpy as np
+
+from metamaps_b200 import capi, synth
+
+ODD_PARAMS = ((16, 13), (16, 1), (11, 5), (8, 40), (5, 200))
+
+
+def check_sketch_vs_golden(ctx, golden):
+    odd = [s.encode() for s in golden["odd_seqs"]]
+    for (k, w) in ODD_PARAMS:
+        counts, hs, wp, st = ctx.sketch(odd, k, w)
+        for i in range(len(odd)):
+            a, b = counts[i], counts[i + 1]
+            assert np.array_equal(hs[a:b], golden[f"odd{i}_k{k}_w{w}_hash"]), (i, k, w)
+            assert np.array_equal(wp[a:b], golden[f"odd{i}_k{k}_w{w}_wpos"]), (i, k, w)
+            assert np.array_equal(st[a:b], golden[f"odd{i}_k{k}_w{w}_strand"]), (i, k, w)
+
+
+def check_sketch_vs_oracle(ctx, oracle, seqs, k, w):
+    counts, hs, wp, st = ctx.sketch(seqs, k, w)
+    assert counts[0] == 0 and counts[-1] == len(hs)
+    for i, s in enumerate(seqs):
+        oh, ow, os_ = oracle.minimizers(s, k, w)
+        a, b = counts[i], counts[i + 1]
+        assert np.array_equal(hs[a:b], oh), f"hash stream differs for sequence {i} (k={k}, w={w})"
+        assert np.array_equal(wp[a:b], ow), f"wpos stream differs for sequence {i} (k={k}, w={w})"
+        assert np.array_equal(st[a:b], os_), f"strand stream differs for sequence {i} (k={k}, w={w})"
+
+
+def build_index(ctx, contigs, k, w, batches=2):
+    ix = capi.Index(ctx, k, w)
+    step = max(1, (len(contigs) + batches - 1) // batches)
+    for i in range(0, len(contigs), step):
+        ix.add(contigs[i:i + step])
+    ix.finalize()
+    return ix
+
+
+def check_index_vs_golden(ctx, golden, small):
+    contigs = [synth.codes_to_ascii(c) for c in small["db"].contig_codes]
+    ix = build_index(ctx, contigs, int(golden["k"]), int(golden["w"]))
+    hs, sq, wp, st = ix.fetch()
+    assert np.array_equal(hs, golden["index_hash"])
+    assert np.array_equal(sq, golden["index_seq"])
+    assert np.array_equal(wp, golden["index_wpos"])
+    assert np.array_equal(st, golden["index_strand"])
+    s = ix.stats()
+    assert s["n_unique"] == int(golden["index_unique"])
+    assert s["freq_threshold"] == int(golden["freq_threshold"])
+    # lookup table: every present hash reports its multiplicity, absent hashes 0
+    uniq, cnt = np.unique(golden["index_hash"], return_counts=True)
+    assert np.array_equal(ix.lookup(uniq), cnt.astype(np.int32))
+    absent = np.setdiff1d(np.arange(1, 200000, 7, dtype=np.uint32), uniq)
+    assert not ix.lookup(absent).any()
+    return ix
+
+
+def check_map_vs_golden(ctx, golden, small, ix=None):
+    if ix is None:
+        contigs = [synth.codes_to_ascii(c) for c in small["db"].contig_codes]
+        ix = build_index(ctx, contigs, int(golden["k"]), int(golden["w"]))
+    reads = [synth.codes_to_ascii(r) for r in small["reads"]]
+    res = capi.map_reads(ctx, ix, reads, 80.0, 1000, fetch_sketch=True)
+    assert np.array_equal(res["s"], golden["read_s"])
+    assert np.array_equal(res["minimumHits"], golden["read_minhits"])
+    assert np.array_equal(res["cand_off"], golden["cand_off"])
+    assert np.array_equal(res["q_off"], golden["q_off"])
+    assert np.array_equal(res["q_hash"], golden["q_hash"])
+    assert np.array_equal(res["q_strand"], golden["q_strand"])
+    for key in ("seq", "start", "end", "shared", "valid", "votes", "optStart", "optEnd"):
+        assert np.array_equal(res[key], golden["cand_" + key]), key
+    v = golden["cand_valid"].astype(bool)       # position is undefined in the reference when nothing was shared
+    assert np.array_equal(res["pos"][v], golden["cand_pos"][v])
+    return res
+
+
+def check_map_vs_oracle(ctx, oracle, contigs, reads, k, w, pi=80.0, min_len=1000, batches=2):
+    ho = oracle.index_build(contigs, k, w)
+    ix = build_index(ctx, contigs, k, w, batches)
+    a = oracle.index_get(ho); b = ix.fetch()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert ix.stats()["freq_threshold"] == oracle.index_freq_threshold(ho)
+    res = capi.map_reads(ctx, ix, reads, pi, min_len, fetch_sketch=True)
+    n_acc = 0
+    for i, s in enumerate(reads):
+        c0, c1 = res["cand_off"][i], res["cand_off"][i + 1]
+        if len(s) < max(w, k, min_len):
+            assert res["s"][i] == 0 and c0 == c1
+            continue
+        mo = oracle.map_read(ho, s, pi)
+        assert mo["s"] == res["s"][i], i
+        if mo["s"] == 0:
+            assert c0 == c1
+            continue
+        assert mo["minimumHits"] == res["minimumHits"][i], i
+        qh, qw, qs = oracle.read_sketch(s, k, w)
+        q0, q1 = res["q_off"][i], res["q_off"][i + 1]
+        assert np.array_equal(qh, res["q_hash"][q0:q1]), i
+        assert np.array_equal(qs, res["q_strand"][q0:q1]), f"read {i}: surviving duplicate differs from std::sort+unique"
+        for key in ("seq", "start", "end", "shared", "valid", "votes", "optStart", "optEnd"):
+            assert np.array_equal(mo[key], res[key][c0:c1]), (i, key, mo[key], res[key][c0:c1])
+        v = mo["valid"].astype(bool)
+        assert np.array_equal(mo["pos"][v], res["pos"][c0:c1][v]), i
+        for j in range(c1 - c0):
+            nuc, up = oracle.identity(int(mo["shared"][j]), mo["s"], k)
+            acc = int(bool(mo["valid"][j]) and up >= pi)
+            assert acc == res["accepted"][c0 + j], (i, j)
+            n_acc += acc
+    assert n_acc == res["summary"]["n_mappings"]
+    oracle.index_free(ho)
+    return res
+
+
+def random_mapq_case(seed, nr=400):
+    rng = np.random.default_rng(seed)
+    cnt = rng.integers(1, 12, nr); off = np.zeros(nr + 1, np.int64); off[1:] = np.cumsum(cnt); M = int(off[-1])
+    sk = np.repeat(rng.integers(200, 1500, nr), cnt).astype(np.int32)
+    sh = (sk * rng.uniform(0.02, 0.3, M)).astype(np.int32)
+    ident = rng.uniform(0.78, 0.95, M).round(6)
+    rl = rng.integers(1000, 20000, nr).astype(np.int32)
+    return ident, sh, sk, rl, off
+
+
+def check_mapq_vs_oracle(ctx, oracle, seed=3):
+    ident, sh, sk, rl, off = random_mapq_case(seed)
+    q, st = ctx.mapq(ident, sh, sk, rl, off, 16)
+    for r in range(len(rl)):
+        a, b = off[r], off[r + 1]
+        rc, qo = oracle.mapq(ident[a:b], sh[a:b], sk[a:b], int(rl[r]), 16)
+        if rc == 0:
+            assert st[r] == 0
+            assert np.abs(qo - q[a:b]).max() <= 1e-6        # north_star tolerance for mapping qualities
+            assert abs(q[a:b].sum() - 1) < 1e-9
+        else:
+            assert st[r] == 1
+
+
+def random_em_case(seed, nr=3000, T=40, maxc=12):
+    rng = np.random.default_rng(seed)
+    cnt = rng.integers(1, maxc, nr); off = np.zeros(nr + 1, np.int64); off[1:] = np.cumsum(cnt); M = int(off[-1])
+    ab = rng.dirichlet(np.ones(T) * 0.3)
+    tax = rng.choice(T, size=M, p=ab).astype(np.int32)
+    mq = np.concatenate([(lambda v: v / v.sum())(rng.random(c)) for c in cnt])
+    nloc = rng.integers(1000, 5_000_000, M).astype(np.float64)
+    return tax, mq, nloc, off, T
+
+
+def check_em_vs_oracle(ctx, oracle, seed=5, max_iter=0, **kw):
+    tax, mq, nloc, off, T = random_em_case(seed, **kw)
+    a = oracle.em(tax, mq, nloc, off, T, max_iter)
+    b = ctx.em(tax, mq, nloc, off, T, max_iter)
+    assert a["iters"] == b["iters"]
+    assert np.abs(a["f"] - b["f"]).max() <= 1e-6             # north_star tolerance for EM frequencies
+    assert abs(b["f"].sum() - 1) < 1e-9
+    assert np.abs(a["posterior"] - b["posterior"]).max() <= 1e-6
+    assert np.abs(a["ll"] - b["ll"]).max() <= 1e-6 * np.abs(a["ll"]).max()
+    # read -> taxon assignment: bit-exact wherever the oracle's best posterior is not a near-tie
+    diff = a["best"] != b["best"]
+    for r in np.nonzero(diff)[0]:
+        pa = a["posterior"][a["best"][r]]; pb = a["posterior"][b["best"][r]]
+        assert abs(pa - pb) < 1e-12, r
+    return a, b

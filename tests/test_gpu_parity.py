@@ -1,0 +1,122 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the golden fixtures."""
+import numpy as np
+import pytest
+
+from metamaps_b200 import capi, synth
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sketch_golden(gpu_ctx, golden):
+    common.check_sketch_vs_golden(gpu_ctx, golden)
+
+
+def test_sketch_edge_cases(gpu_ctx, oracle):
+    rng = np.random.default_rng(11)
+    seqs = [b"", b"A", b"ACGTACGTACGTACG", b"ACGTACGTACGTACGT", b"N" * 300, b"ACGT" * 100 + b"N" * 64 + b"TTGACC" * 50,
+            bytes(rng.choice(list(b"ACGT"), size=20001).astype(np.uint8)),
+            bytes(rng.choice(list(b"acgtRYKM"), size=777).astype(np.uint8)), b"GATTACA" * 300]
+    for (k, w) in ((16, 16), (16, 13), (16, 1), (15, 8), (9, 33), (4, 100), (16, 500), (16, 2000)):
+        common.check_sketch_vs_oracle(gpu_ctx, oracle, seqs, k, w)
+
+
+def test_sketch_large_batch_properties(gpu_ctx, oracle):
+    """2000 reads x ~8 kb: spot-check 40 against the oracle; window property on all (every window of w
+    consecutive k-mers contains a sampled minimizer position => wpos gaps <= w)."""
+    rng = np.random.default_rng(3)
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(1200, 16000))).astype(np.uint8)) for _ in range(2000)]
+    counts, hs, wp, st = gpu_ctx.sketch(seqs, 16, 16)
+    for i in rng.choice(len(seqs), 40, replace=False):
+        oh, ow, os_ = oracle.minimizers(seqs[i], 16, 16)
+        a, b = counts[i], counts[i + 1]
+        assert np.array_equal(hs[a:b], oh) and np.array_equal(wp[a:b], ow) and np.array_equal(st[a:b], os_)
+    for i in range(len(seqs)):
+        w_ = wp[counts[i]:counts[i + 1]]
+        assert w_[0] == 0 and (np.diff(w_) > 0).all() and (np.diff(w_) <= 16).all()
+        assert w_[-1] <= len(seqs[i]) - 16 - 16 + 1
+
+
+def test_index_golden(gpu_ctx, golden, small_workload):
+    common.check_index_vs_golden(gpu_ctx, golden, small_workload)
+
+
+def test_map_golden(gpu_ctx, golden, small_workload):
+    res = common.check_map_vs_golden(gpu_ctx, golden, small_workload)
+    assert res["summary"]["n_too_short"] == 4 and res["summary"]["n_reads_mapped"] == 194
+
+
+def test_map_config1(gpu_ctx, oracle, tmp_path):
+    """BASELINE config 1 (the reference's own CPU-runnable case): 10-genome mini DB, 1000 reads of 5 kb."""
+    db, fa, fq, (names, reads, truth) = synth.config1(str(tmp_path), n_reads=1000)
+    contigs = [synth.codes_to_ascii(c) for c in db.contig_codes]
+    res = common.check_map_vs_oracle(gpu_ctx, oracle, contigs, [synth.codes_to_ascii(r) for r in reads], 16, 13)
+    assert res["summary"]["n_reads_mapped"] == 967 and res["summary"]["n_too_short"] == 21   # reference .meta
+
+
+def test_map_repetitive_reference(gpu_ctx, oracle):
+    rng = np.random.default_rng(77)
+    unit = rng.integers(0, 4, 700, dtype=np.uint8)
+    parts = [rng.integers(0, 4, 5000, dtype=np.uint8), unit, unit, unit, rng.integers(0, 4, 3000, dtype=np.uint8), unit,
+             rng.integers(0, 4, 4000, dtype=np.uint8)]
+    c0 = np.concatenate(parts)
+    c1 = np.concatenate([c0[2000:9000], rng.integers(0, 4, 2000, dtype=np.uint8), c0[2000:6000]])
+    db = synth.SynthDB(["C0|kraken:taxid|1|x", "C1|kraken:taxid|2|x"], ["1", "2"], [c0, c1])
+    _, reads, _ = synth.make_reads(db, 5, 60, 2500, err=0.06)
+    contigs = [synth.codes_to_ascii(c) for c in db.contig_codes]
+    common.check_map_vs_oracle(gpu_ctx, oracle, contigs, [synth.codes_to_ascii(r) for r in reads], 16, 5, 80.0, 1000)
+
+
+def test_map_low_complexity_reads(gpu_ctx, oracle):
+    rng = np.random.default_rng(9)
+    genome = rng.integers(0, 4, 40000, dtype=np.uint8)
+    pal = rng.integers(0, 4, 300, dtype=np.uint8)
+    rc = (3 - pal[::-1]).astype(np.uint8)
+    genome[10000:10300] = pal; genome[10300:10600] = rc; genome[12000:12300] = pal
+    reads = [synth.codes_to_ascii(genome[9000:13500]), synth.codes_to_ascii(genome[9500:12800]),
+             synth.codes_to_ascii((3 - genome[9000:13500][::-1]).astype(np.uint8))]
+    common.check_map_vs_oracle(gpu_ctx, oracle, [synth.codes_to_ascii(genome)], reads, 16, 4, 80.0, 1000, batches=1)
+
+
+def test_map_ragged_and_empty(gpu_ctx, oracle, small_workload):
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"][:12]]
+    ragged = [b"", reads[0], b"ACGT", reads[1][:999], reads[2], b"N" * 1500, reads[3] + reads[4], reads[5][:1000]]
+    common.check_map_vs_oracle(gpu_ctx, oracle, contigs + [b"ACGT", b""], ragged, 16, 13)
+    ix = common.build_index(gpu_ctx, contigs, 16, 13)
+    res = capi.map_reads(gpu_ctx, ix, [], 80.0, 1000)
+    assert res["summary"]["n_reads"] == 0 and res["summary"]["n_candidates"] == 0
+
+
+def test_map_is_deterministic_and_batch_invariant(gpu_ctx, small_workload):
+    """Idempotence: mapping the same reads twice, or split into two batches, gives identical candidates."""
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"]]
+    ix = common.build_index(gpu_ctx, contigs, 16, 13, batches=3)
+    a = capi.map_reads(gpu_ctx, ix, reads)
+    b = capi.map_reads(gpu_ctx, ix, reads)
+    h1 = capi.map_reads(gpu_ctx, ix, reads[:77]); h2 = capi.map_reads(gpu_ctx, ix, reads[77:])
+    for key in ("seq", "start", "end", "pos", "shared", "votes", "accepted"):
+        assert np.array_equal(a[key], b[key])
+        assert np.array_equal(a[key], np.concatenate([h1[key], h2[key]]))
+
+
+def test_mapq(gpu_ctx, oracle):
+    common.check_mapq_vs_oracle(gpu_ctx, oracle)
+
+
+def test_em(gpu_ctx, oracle):
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=5)
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=6, max_iter=50, nr=500, T=7, maxc=30)
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=8, nr=20000, T=300, maxc=40)
+
+
+def test_em_properties_large(gpu_ctx):
+    """Size-independent properties at scale: f sums to 1, posteriors sum to 1 per read, log-likelihood is monotone."""
+    tax, mq, nloc, off, T = common.random_em_case(21, nr=200_000, T=2000, maxc=20)
+    r = gpu_ctx.em(tax, mq, nloc, off, T, 12)
+    assert abs(r["f"].sum() - 1) < 1e-9
+    sums = np.add.reduceat(r["posterior"], off[:-1])
+    assert np.abs(sums - 1).max() < 1e-9
+    assert (np.diff(r["ll"]) >= -1e-6).all()
+    assert ((r["best"] >= off[:-1]) & (r["best"] < off[1:])).all()

@@ -1,0 +1,93 @@
+"""Kernel logic on the CPU: the same functors the GPU runs, compiled with -DMM_HOST_EMU and executed in a
+loop (tests/_emu/libmm_emu.so, test infrastructure only), checked against the oracle and the golden
+fixtures.  This is what lets the build container (no GPU) catch logic errors; the parity tests proper are
+in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from metamaps_b200 import capi, synth
+from tests import common
+
+
+def test_sketch_golden(emu_ctx, golden):
+    common.check_sketch_vs_golden(emu_ctx, golden)
+
+
+def test_sketch_edge_cases(emu_ctx, oracle):
+    rng = np.random.default_rng(11)
+    seqs = [b"", b"A", b"ACGTACGTACGTACG", b"ACGTACGTACGTACGT", b"N" * 300, b"ACGT" * 100 + b"N" * 64 + b"TTGACC" * 50,
+            bytes(rng.choice(list(b"ACGT"), size=20001).astype(np.uint8)),
+            bytes(rng.choice(list(b"acgtRYKM"), size=777).astype(np.uint8)), b"GATTACA" * 300]
+    for (k, w) in ((16, 16), (16, 13), (16, 1), (15, 8), (9, 33), (4, 100), (16, 500)):
+        common.check_sketch_vs_oracle(emu_ctx, oracle, seqs, k, w)
+
+
+def test_sketch_long_monotone_window(emu_ctx, oracle):
+    # w larger than the 32-entry register deque: exercises the global-memory replay of overflowing chunks
+    rng = np.random.default_rng(5)
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=30000).astype(np.uint8))]
+    common.check_sketch_vs_oracle(emu_ctx, oracle, seqs, 16, 2000)
+
+
+def test_index_golden(emu_ctx, golden, small_workload):
+    common.check_index_vs_golden(emu_ctx, golden, small_workload)
+
+
+def test_map_golden(emu_ctx, golden, small_workload):
+    res = common.check_map_vs_golden(emu_ctx, golden, small_workload)
+    assert res["summary"]["n_too_short"] == 4            # ref_small/ref.meta: ReadsTooShort 4
+    assert res["summary"]["n_reads_mapped"] == 194       # ReadsMapped 194
+
+
+def test_map_repetitive_reference(emu_ctx, oracle):
+    """Tandem repeats and duplicated segments inside one contig: duplicate hashes inside L2 windows."""
+    rng = np.random.default_rng(77)
+    unit = rng.integers(0, 4, 700, dtype=np.uint8)
+    parts = [rng.integers(0, 4, 5000, dtype=np.uint8), unit, unit, unit, rng.integers(0, 4, 3000, dtype=np.uint8), unit,
+             rng.integers(0, 4, 4000, dtype=np.uint8)]
+    c0 = np.concatenate(parts)
+    c1 = np.concatenate([c0[2000:9000], rng.integers(0, 4, 2000, dtype=np.uint8), c0[2000:6000]])
+    db = synth.SynthDB(["C0|kraken:taxid|1|x", "C1|kraken:taxid|2|x"], ["1", "2"], [c0, c1])
+    _, reads, _ = synth.make_reads(db, 5, 60, 2500, err=0.06)
+    contigs = [synth.codes_to_ascii(c) for c in db.contig_codes]
+    res = common.check_map_vs_oracle(emu_ctx, oracle, contigs, [synth.codes_to_ascii(r) for r in reads], 16, 5, 80.0, 1000)
+    assert res["summary"]["n_mappings"] > 0
+
+
+def test_map_low_complexity_reads(emu_ctx, oracle):
+    """Reads with repeated k-mers on both strands: the surviving duplicate must follow std::sort + std::unique."""
+    rng = np.random.default_rng(9)
+    genome = rng.integers(0, 4, 40000, dtype=np.uint8)
+    pal = rng.integers(0, 4, 300, dtype=np.uint8)
+    rc = (3 - pal[::-1]).astype(np.uint8)      # synth codes: A=0 C=1 G=2 T=3 -> complement = 3 - x
+    genome[10000:10300] = pal; genome[10300:10600] = rc; genome[12000:12300] = pal
+    db = synth.SynthDB(["C0|kraken:taxid|1|x"], ["1"], [genome])
+    reads = [synth.codes_to_ascii(genome[9000:13500]), synth.codes_to_ascii(genome[9500:12800]),
+             synth.codes_to_ascii((3 - genome[9000:13500][::-1]).astype(np.uint8))]
+    common.check_map_vs_oracle(emu_ctx, oracle, [synth.codes_to_ascii(genome)], reads, 16, 4, 80.0, 1000, batches=1)
+
+
+def test_map_ragged_and_empty(emu_ctx, oracle, small_workload):
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"][:12]]
+    ragged = [b"", reads[0], b"ACGT", reads[1][:999], reads[2], b"N" * 1500, reads[3] + reads[4], reads[5][:1000]]
+    common.check_map_vs_oracle(emu_ctx, oracle, contigs + [b"ACGT", b""], ragged, 16, 13)
+    ix = common.build_index(emu_ctx, contigs, 16, 13)
+    res = capi.map_reads(emu_ctx, ix, [], 80.0, 1000)
+    assert res["summary"]["n_reads"] == 0 and res["summary"]["n_candidates"] == 0
+
+
+def test_mapq(emu_ctx, oracle):
+    common.check_mapq_vs_oracle(emu_ctx, oracle)
+
+
+def test_em(emu_ctx, oracle):
+    common.check_em_vs_oracle(emu_ctx, oracle, seed=5)
+    common.check_em_vs_oracle(emu_ctx, oracle, seed=6, max_iter=50, nr=500, T=7, maxc=30)
+
+
+def test_api_errors(emu_ctx):
+    with pytest.raises(capi.MMError):
+        emu_ctx.sketch([b"ACGT"], 17, 5)          # k > 16 (parseCmdArgs.hpp:62)
+    with pytest.raises(capi.MMError):
+        capi.Index(emu_ctx, 16, 0)
