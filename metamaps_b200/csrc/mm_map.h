@@ -500,7 +500,7 @@ struct Mapper {
       pr.reduce_sum<int32_t>(readMapped.p, red.p + 1, n_reads);
       int32_t h[2]; d2h(rt, h, red.p, sizeof(h)); nMap = h[0]; nReadsMapped = h[1];
     }
-    rt.sync(); rt.resolve_timers();
+    rt.sync();
     st.counters[0] = n_q; st.counters[1] = n_hits; st.counters[2] = n_cand; st.counters[3] = totalEv; st.counters[4] = nMap;
     st.counters[5] = rs.n_total; st.counters[6] = basesOk; st.counters[7] = batch.n_exc;
     summary[0] = n_reads; summary[1] = nShort; summary[2] = n_cand; summary[3] = nMap; summary[4] = nReadsMapped; summary[5] = basesOk;

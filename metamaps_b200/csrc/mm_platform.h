@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <list>
 
 #ifdef MM_HOST_EMU
 #define MM_HD inline
@@ -55,24 +56,25 @@ struct Runtime {
   double total_ms = 0;           // filled by StageTimer users
 #ifndef MM_HOST_EMU
   struct Pending { cudaEvent_t a = nullptr, b = nullptr; double* acc = nullptr; bool closed = false; };
-  std::vector<Pending> pending;
+  std::list<Pending> pending;     // list: StageTimer keeps a pointer to its entry
 #endif
   void sync() {
 #ifndef MM_HOST_EMU
     MM_CUDA(cudaStreamSynchronize(stream));
 #endif
   }
-  // call after sync(): folds every closed StageTimer into its accumulator
+  // call after sync(): folds every closed StageTimer into its accumulator (open ones are left alone)
   void resolve_timers() {
 #ifndef MM_HOST_EMU
-    for (auto& p : pending) {
-      if (p.closed) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess && p.acc) *p.acc += ms;
-      }
-      cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    for (auto it = pending.begin(); it != pending.end();) {
+      if (!it->closed) { ++it; continue; }
+      float ms = 0;
+      cudaError_t e = cudaEventElapsedTime(&ms, it->a, it->b);
+      if (e == cudaSuccess) { if (it->acc) *it->acc += ms; }
+      else { fprintf(stderr, "[metamaps_b200] cudaEventElapsedTime failed: %s\n", cudaGetErrorString(e)); cudaGetLastError(); }
+      cudaEventDestroy(it->a); cudaEventDestroy(it->b);
+      it = pending.erase(it);
     }
-    pending.clear();
 #endif
   }
 };
@@ -99,7 +101,8 @@ inline void dev_free(void* p) {
 #ifdef MM_HOST_EMU
   free(p);
 #else
-  cudaFree(p);
+  cudaError_t e = cudaFree(p);
+  if (e != cudaSuccess) { fprintf(stderr, "[metamaps_b200] cudaFree(%p) failed: %s\n", p, cudaGetErrorString(e)); cudaGetLastError(); }
 #endif
 }
 inline void h2d(Runtime& rt, void* d, const void* h, size_t bytes) {
@@ -250,23 +253,27 @@ MM_HD T ldg(const T* p) {
 // the entry point has synchronised anyway) turns them into milliseconds.
 struct StageTimer {
   Runtime& rt;
-  int slot;
-  StageTimer(Runtime& r, double* accum) : rt(r), slot(-1) {
 #ifndef MM_HOST_EMU
-    Runtime::Pending p; p.acc = accum;
+  Runtime::Pending* slot = nullptr;
+#endif
+  StageTimer(Runtime& r, double* accum) : rt(r) {
+#ifndef MM_HOST_EMU
+    rt.pending.emplace_back();
+    Runtime::Pending& p = rt.pending.back();
+    p.acc = accum;
     MM_CUDA(cudaEventCreate(&p.a)); MM_CUDA(cudaEventCreate(&p.b));
     MM_CUDA(cudaEventRecord(p.a, rt.stream));
-    rt.pending.push_back(p); slot = (int)rt.pending.size() - 1;
+    slot = &p;
 #else
     (void)accum;
 #endif
   }
   void stop() {
 #ifndef MM_HOST_EMU
-    if (slot < 0) return;
-    MM_CUDA(cudaEventRecord(rt.pending[slot].b, rt.stream));
-    rt.pending[slot].closed = true;
-    slot = -1;
+    if (!slot) return;
+    Runtime::Pending* p = slot; slot = nullptr;
+    MM_CUDA(cudaEventRecord(p->b, rt.stream));
+    p->closed = true;
 #endif
   }
   ~StageTimer() {
