@@ -224,18 +224,25 @@ class Index:
 
 
 def map_reads(ctx: Context, index: Index, reads=None, perc_identity: float = 80.0, min_read_len: int = 1000,
-              dev_ptr: int | None = None, offsets=None, fetch: bool = True, fetch_sketch: bool = False):
-    """skch::Map over a batch.  reads: list of ASCII bytes (host) or dev_ptr+offsets (device-resident ASCII)."""
+              dev_ptr: int | None = None, host_ptr: int | None = None, offsets=None, fetch: bool = True,
+              fetch_sketch: bool = False):
+    """skch::Map over a batch.  reads: list of ASCII bytes (host); or host_ptr+offsets (one host buffer, e.g.
+    pinned); or dev_ptr+offsets (device-resident ASCII)."""
     p = MapParams(perc_identity, min_read_len, 1, 0)
     s = MapSummary()
-    if dev_ptr is None:
+    if host_ptr is not None:
+        offs = np.ascontiguousarray(offsets, np.int64)
+        ctx._check(ctx.lib.mm_map_batch(ctx.h, index.h, C.cast(host_ptr, C.c_char_p), offs, len(offs) - 1, C.byref(p), C.byref(s)))
+    elif dev_ptr is None:
         data, offs = _ascii_batch(reads)
         ctx._check(ctx.lib.mm_map_batch(ctx.h, index.h, data, offs, len(reads), C.byref(p), C.byref(s)))
     else:
         offs = np.ascontiguousarray(offsets, np.int64)
         ctx._check(ctx.lib.mm_map_batch_dev(ctx.h, index.h, C.c_void_p(dev_ptr), offs, len(offs) - 1, C.byref(p), C.byref(s)))
     n = len(offs) - 1
-    out = {"summary": {f[0]: getattr(s, f[0]) for f in MapSummary._fields_}}
+    gpu_ms, launches = ctx.last_timing()          # of the map call itself (the fetches below are separate calls)
+    out = {"summary": {f[0]: getattr(s, f[0]) for f in MapSummary._fields_}, "gpu_ms": gpu_ms, "launches": launches,
+           "stats": ctx.last_map_stats()}
     if not fetch:
         return out
     sk = np.zeros(n, np.int32); mh = np.zeros(n, np.int32); co = np.zeros(n + 1, np.int64)
@@ -247,6 +254,7 @@ def map_reads(ctx: Context, index: Index, reads=None, perc_identity: float = 80.
     ctx._check(ctx.lib.mm_map_fetch_candidates(ctx.h, *[_ptr(a) for a in arrs], _ptr(o1), _ptr(o2)))
     out.update({"s": sk, "minimumHits": mh, "cand_off": co, "optStart": o1, "optEnd": o2})
     out.update(dict(zip(names, arrs)))
+    out["d2h_bytes"] = int(sk.nbytes + mh.nbytes + co.nbytes + sum(a.nbytes for a in arrs) + o1.nbytes + o2.nbytes)
     if fetch_sketch:
         qo = np.zeros(n + 1, np.int64)
         ctx._check(ctx.lib.mm_map_fetch_sketch(ctx.h, _ptr(qo), None, None, 0))

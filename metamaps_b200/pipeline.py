@@ -1,0 +1,129 @@
+"""Host-side mirror of the reference's mapDirectly -> classify data flow on arrays (no files).
+
+`map_and_classify` strings the C-ABI calls together the way `metamaps mapDirectly` + `metamaps classify` do:
+  skch::Map (K1,K3,K4,K5)  ->  identity + filter (computeMap.hpp:405-415)  ->  addMappingQualities (K6)
+  ->  getMappingLocations nloc (fEM.h:324-348)  ->  doEM (K7/K8).
+The float arithmetic that fixes the printed identity (and therefore what `classify` re-parses from the text
+file, mapWrap.h:229, fEM.h:297) is done here on the host, vectorised, exactly as the reference does it.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+
+
+def nuc_identity(shared: np.ndarray, s: np.ndarray, k: int) -> np.ndarray:
+    """float nucIdentity = 100 * (1 - j2md(1.0*shared/s, k))   (map_stats.hpp:44-54, computeMap.hpp:403-408)."""
+    j = (shared.astype(np.float64) / s.astype(np.float64)).astype(np.float32)
+    jd = j.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        # `2.0 * j/(1+j)`: (1+j) is evaluated in float (int + float), the rest in double
+        md = ((-1.0 / k) * np.log(2.0 * jd / (np.float32(1) + j).astype(np.float64))).astype(np.float32)
+    md = np.where(j == 0, np.float32(1.0), np.where(j == 1, np.float32(0.0), md)).astype(np.float32)
+    return (np.float32(100) * (np.float32(1) - md)).astype(np.float32)
+
+
+def round_6_significant(x32: np.ndarray) -> np.ndarray:
+    """The double obtained by printing a float with the default ostream precision (6 significant digits) and
+    parsing it back (what mapWrap.h:229 / fEM.h:297 see).  x*10^d has at most 24+14 significant bits, so the
+    scaling is exact in double and rint()/division give the correctly rounded decimal."""
+    x = x32.astype(np.float64)
+    out = np.zeros_like(x)
+    nz = x != 0
+    e = np.floor(np.log10(np.abs(x[nz])))
+    e = np.where(np.abs(x[nz]) >= 10.0 ** (e + 1), e + 1, e)
+    e = np.where(np.abs(x[nz]) < 10.0 ** e, e - 1, e)
+    d = (5 - e).astype(np.int64)
+    scale = 10.0 ** np.abs(d)
+    scaled = np.where(d >= 0, x[nz] * scale, x[nz] / scale)
+    r = np.rint(scaled)
+    out[nz] = np.where(d >= 0, r / scale, r * scale)
+    return out
+
+
+def map_and_classify(ctx: capi.Context, index: capi.Index, *, reads=None, dev_ptr=None, host_ptr=None, offsets=None, read_len=None,
+                     contig_len: np.ndarray, contig_taxon: np.ndarray, n_taxa: int, perc_identity: float = 80.0,
+                     min_read_len: int = 1000, em_max_iter: int = 0, stats: dict | None = None):
+    """One pass of the hot path over one batch of reads.  Returns per-mapping arrays + EM result."""
+    k = index.k
+    res = capi.map_reads(ctx, index, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets)
+    launches = res["launches"]
+    gpu_ms = res["gpu_ms"]
+    if stats is not None:
+        stats["map"] = res["stats"]
+    n_reads = len(res["s"])
+    if read_len is None:
+        read_len = np.array([len(r) for r in reads], np.int32) if reads is not None else np.diff(offsets).astype(np.int32)
+    cand_read = np.repeat(np.arange(n_reads, dtype=np.int64), np.diff(res["cand_off"]))
+    acc = res["accepted"].astype(bool)
+    m_read = cand_read[acc]
+    m_seq = res["seq"][acc]; m_shared = res["shared"][acc]; m_pos = res["pos"][acc]; m_votes = res["votes"][acc]
+    m_s = res["s"][m_read]
+    ident32 = nuc_identity(m_shared, m_s, k)
+    ident = round_6_significant(ident32) / 100.0
+    # reads with >= 1 mapping, in read order (the mappings file has no lines for the others)
+    counts = np.bincount(m_read, minlength=n_reads)
+    mapped = np.nonzero(counts)[0]
+    read_off = np.zeros(len(mapped) + 1, np.int64); read_off[1:] = np.cumsum(counts[mapped])
+    out = {"summary": res["summary"], "read": m_read, "seq": m_seq, "pos": m_pos, "shared": m_shared, "sketch": m_s,
+           "strand": np.where(m_votes > 0, 1, -1), "identity": ident32, "mapped_reads": mapped, "read_off": read_off}
+    d2h = res["d2h_bytes"]
+    if len(m_read) == 0:
+        out.update({"mapq": np.zeros(0), "em": None, "gpu_ms": gpu_ms, "launches": launches, "d2h_bytes": d2h})
+        return out
+    mapq, status = ctx.mapq(ident, m_shared, m_s, read_len[mapped], read_off, k)
+    launches += ctx.last_timing()[1]; gpu_ms += ctx.last_timing()[0]
+    out["mapq"] = mapq; out["mapq_status"] = status
+    # fEM.h:324-348: possible mapping locations of the mapping's taxon for this read length
+    L = read_len[m_read].astype(np.int64)
+    tax = contig_taxon[m_seq]
+    nloc = _nloc(tax, m_seq, m_read, L, contig_len, contig_taxon, n_taxa)
+    em = ctx.em(tax, mapq, nloc, read_off, n_taxa, em_max_iter)
+    launches += ctx.last_timing()[1]; gpu_ms += ctx.last_timing()[0]
+    d2h += mapq.nbytes + status.nbytes + em["f"].nbytes + em["posterior"].nbytes + em["best"].nbytes
+    out["taxon"] = tax; out["nloc"] = nloc; out["em"] = em; out["gpu_ms"] = gpu_ms; out["launches"] = launches; out["d2h_bytes"] = int(d2h)
+    return out
+
+
+_TAXON_CACHE: dict = {}
+
+
+def _nloc(tax, m_seq, m_read, L, contig_len, contig_taxon, n_taxa):
+    """sum over the taxon's contigs of (len >= L ? len-L+1 : [contig seen among this read's mappings])."""
+    key = (id(contig_len), id(contig_taxon))
+    if key not in _TAXON_CACHE:
+        order = np.lexsort((contig_len, contig_taxon))
+        lens = contig_len[order].astype(np.int64); tx = contig_taxon[order]
+        start = np.searchsorted(tx, np.arange(n_taxa + 1))
+        csum = np.concatenate([[0], np.cumsum(lens)])
+        _TAXON_CACHE.clear(); _TAXON_CACHE[key] = (lens, start, csum)
+    lens, start, csum = _TAXON_CACHE[key]
+    # contigs of taxon t are lens[start[t]:start[t+1]] ascending; those >= L start at p
+    # vectorised per-mapping binary search inside the taxon's slice
+    lo = start[tax].copy(); hi = start[tax + 1].copy()
+    while True:
+        act = lo < hi
+        if not act.any():
+            break
+        mid = (lo + hi) // 2
+        less = act & (lens[np.minimum(mid, len(lens) - 1)] < L)
+        lo = np.where(less, mid + 1, lo); hi = np.where(act & ~less, mid, hi)
+    p = lo
+    n_big = start[tax + 1] - p
+    big = (csum[start[tax + 1]] - csum[p]) - n_big * (L - 1)
+    # short contigs (len < L) count once if this read maps to them; distinct (read, contig) pairs of the taxon
+    short = contig_len[m_seq] < L
+    seen = np.zeros(len(tax), np.int64)
+    if short.any():
+        idx = np.nonzero(short)[0]
+        keyrc = m_read[idx].astype(np.int64) * (int(contig_len.shape[0]) + 1) + m_seq[idx]
+        _, first = np.unique(keyrc, return_index=True)
+        uniq_idx = idx[first]
+        keyrt = m_read[uniq_idx].astype(np.int64) * (n_taxa + 1) + tax[uniq_idx]
+        u, cnt = np.unique(keyrt, return_counts=True)
+        allkey = m_read.astype(np.int64) * (n_taxa + 1) + tax
+        pos = np.searchsorted(u, allkey)
+        pos = np.minimum(pos, len(u) - 1)
+        seen = np.where(u[pos] == allkey, cnt[pos], 0)
+    return (big + seen).astype(np.float64)

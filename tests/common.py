@@ -163,3 +163,47 @@ def check_em_vs_oracle(ctx, oracle, seed=5, max_iter=0, **kw):
         pa = a["posterior"][a["best"][r]]; pb = a["posterior"][b["best"][r]]
         assert abs(pa - pb) < 1e-12, r
     return a, b
+
+
+def check_pipeline_vs_reference_files(ctx, small, golden_dir):
+    """mapDirectly + classify on arrays vs the text files the unmodified reference wrote for the same inputs."""
+    import os
+    import re
+    from metamaps_b200 import pipeline
+    db = small["db"]
+    contigs = [synth.codes_to_ascii(c) for c in db.contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small["reads"]]
+    ix = build_index(ctx, contigs, 16, 13)
+    taxa = sorted(set(db.contig_taxon))
+    tidx = {t: i for i, t in enumerate(taxa)}
+    contig_taxon = np.array([tidx[t] for t in db.contig_taxon], np.int32)
+    contig_len = np.array([len(c) for c in db.contig_codes], np.int64)
+    out = pipeline.map_and_classify(ctx, ix, reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=len(taxa))
+    ref_lines = open(os.path.join(golden_dir, "ref_small", "ref")).read().splitlines()
+    assert len(ref_lines) == len(out["read"])
+    for m, line in enumerate(ref_lines):
+        f = line.split(" ")
+        r = out["read"][m]
+        assert f[0] == small["names"][r] and int(f[1]) == len(reads[r])
+        assert f[4] == ("+" if out["strand"][m] > 0 else "-")
+        assert f[5] == db.contig_names[out["seq"][m]] and int(f[6]) == contig_len[out["seq"][m]]
+        assert int(f[7]) == out["pos"][m] and int(f[8]) == out["pos"][m] + len(reads[r]) - 1      # mapping coordinates: bit-exact
+        assert f[9] == "%g" % out["identity"][m]
+        assert int(f[10]) == out["shared"][m] and int(f[11]) == out["sketch"][m]                  # MinHash counts: bit-exact
+        assert abs(float(f[13]) - out["mapq"][m]) <= 1e-6 + 2e-6 * float(f[13])                    # 6 significant digits in the file
+    meta = dict(l.split() for l in open(os.path.join(golden_dir, "ref_small", "ref.meta")))
+    assert int(meta["ReadsTooShort"]) == out["summary"]["n_too_short"]
+    assert int(meta["ReadsMapped"]) == len(out["mapped_reads"])
+    em = out["em"]
+    log = open(os.path.join(golden_dir, "ref_small", "classify.log")).read()
+    assert em["iters"] == len(re.findall(r"^EM round", log, re.M))
+    for m, line in enumerate(open(os.path.join(golden_dir, "ref_small", "ref.EM")).read().splitlines()):
+        assert abs(float(line.split(" ")[13]) - em["posterior"][m]) <= 1e-6
+    r2t = dict(l.rstrip("\n").split("\t") for l in open(os.path.join(golden_dir, "ref_small", "ref.EM.reads2Taxon")))
+    for i, r in enumerate(out["mapped_reads"]):
+        assert r2t[small["names"][r]] == taxa[out["taxon"][em["best"][i]]]                          # read -> taxon: exact
+    for line in open(os.path.join(golden_dir, "ref_small", "ref.EM.WIMP")):
+        c = line.rstrip("\n").split("\t")
+        if c[0] == "definedGenomes" and c[1] in tidx:
+            assert abs(float(c[4]) - em["f"][tidx[c[1]]]) <= 1e-6
+    return out

@@ -121,3 +121,9 @@ def test_em_properties_large(gpu_ctx):
     assert np.abs(sums - 1).max() < 1e-9
     assert (np.diff(r["ll"]) >= -1e-6).all()
     assert ((r["best"] >= off[:-1]) & (r["best"] < off[1:])).all()
+
+
+def test_pipeline_matches_reference_files(gpu_ctx, small_workload):
+    """End to end on arrays against the files written by the unmodified reference binary for the same inputs."""
+    from tests.conftest import GOLDEN
+    common.check_pipeline_vs_reference_files(gpu_ctx, small_workload, GOLDEN)

@@ -91,3 +91,8 @@ def test_api_errors(emu_ctx):
         emu_ctx.sketch([b"ACGT"], 17, 5)          # k > 16 (parseCmdArgs.hpp:62)
     with pytest.raises(capi.MMError):
         capi.Index(emu_ctx, 16, 0)
+
+
+def test_pipeline_matches_reference_files(emu_ctx, small_workload):
+    from tests.conftest import GOLDEN
+    common.check_pipeline_vs_reference_files(emu_ctx, small_workload, GOLDEN)
