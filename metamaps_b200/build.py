@@ -32,5 +32,20 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+HOST_SRC = os.path.join(HERE, "csrc", "host", "metamaps_main.cpp")
+HOST_BIN = os.path.join(HERE, "metamaps")
+
+
+def build_host(lib_dir: str = HERE, lib_name: str = "metamaps_b200", out: str = HOST_BIN, force: bool = False) -> str:
+    """The C++ host (`metamaps mapDirectly|classify`) linked against the C-ABI library."""
+    deps = [HOST_SRC, os.path.join(HERE, "csrc", "host", "mm_fastx.hpp"), os.path.join(ROOT, "include", "metamaps_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", HOST_SRC, "-o", out, "-L" + lib_dir, "-l" + lib_name,
+                    "-Wl,-rpath," + lib_dir + ":$ORIGIN", "-lz"], check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build_cuda(force=True, verbose=True))
+    print(build_host(force=True))

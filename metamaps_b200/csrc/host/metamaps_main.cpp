@@ -1,0 +1,565 @@
+// metamaps_main.cpp -- C++ host of the B200 compute core: a `metamaps` command with the reference's
+// sub-commands `mapDirectly` and `classify`, the same options and the same output files
+// (reference src/map/mash_map.cpp:257-326, parseCmdArgs.hpp:33-117,255-460, mapWrap.h:34-213,407-441,
+//  src/meta/fEM.h:466-1133).  All array work goes through the C ABI (include/metamaps_b200.h); this file only
+// parses files, prints text with the reference's formatting, and keeps the taxonomy book-keeping.
+//
+// Not supported (out of scope): `index` / `mapAgainstIndex` (Boost archives), `classifyU`.
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../../include/metamaps_b200.h"
+#include "mm_fastx.hpp"
+
+namespace {
+
+[[noreturn]] void die(const std::string& m) { std::cerr << m << std::endl; exit(1); }
+void ck(int rc, const char* what) { if (rc != 0) die(std::string(what) + ": " + mm_last_error()); }
+
+std::vector<std::string> split(const std::string& s, const std::string& d) {     // util.h:80 semantics
+  std::vector<std::string> out; size_t p = 0;
+  for (;;) { size_t q = s.find(d, p); if (q == std::string::npos) { out.push_back(s.substr(p)); break; } out.push_back(s.substr(p, q - p)); p = q + d.size(); }
+  return out;
+}
+void erase_nl(std::string& s) { while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back(); }
+template <class T> std::string g6(T v) { std::ostringstream o; o << v; return o.str(); }     // default ostream formatting
+
+// ------------------------------------------------------------------------------------------------ options
+struct Options {
+  std::map<std::string, std::string> kv; std::set<std::string> flags;
+  bool has(const std::string& k) const { return kv.count(k) || flags.count(k); }
+  std::string get(const std::string& k) const { return kv.at(k); }
+};
+// `--opt v`, `--opt=v`, `-o v`; long/short aliases folded to the long name (argvparser.hpp grammar)
+Options parse_args(int argc, char** argv, int first, const std::map<std::string, std::string>& alias, const std::set<std::string>& valueless) {
+  Options o;
+  for (int i = first; i < argc; i++) {
+    std::string a = argv[i];
+    if (a.size() < 2 || a[0] != '-') die("Unknown argument: " + a);
+    a = a.substr(a[1] == '-' ? 2 : 1);
+    std::string val; bool hasVal = false;
+    size_t eq = a.find('=');
+    if (eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); hasVal = true; }
+    auto it = alias.find(a);
+    if (it == alias.end()) die("Unknown option: " + a);
+    std::string key = it->second;
+    if (valueless.count(key)) { o.flags.insert(key); continue; }
+    if (!hasVal) { if (i + 1 >= argc) die("Option " + a + " requires a value"); val = argv[++i]; }
+    o.kv[key] = val;
+  }
+  return o;
+}
+
+struct Params {          // skch::Parameters (map_parameters.hpp:57-76)
+  int kmerSize = 16, windowSize = 0, minReadLength = 1000, alphabetSize = 4, threads = 1;
+  uint64_t referenceSize = 0; float percentageIdentity = 80; double p_value = 1e-3;
+  std::string ref, query, out; bool reportAll = false; uint64_t maximumMemory = 0;
+};
+
+uint64_t file_size(const std::string& f) {
+  struct stat st; if (stat(f.c_str(), &st) != 0) die("Cannot open " + f + " for size determination.");
+  return (uint64_t)st.st_size;
+}
+
+// ------------------------------------------------------------------------------------------------ mapDirectly
+struct Contig { std::string name; int len; };
+
+int run_mapDirectly(int argc, char** argv) {
+  const std::map<std::string, std::string> alias = {
+      {"reference", "reference"}, {"r", "reference"}, {"kmer", "kmer"}, {"k", "kmer"}, {"pval", "pval"}, {"p", "pval"},
+      {"maxmemory", "maxmemory"}, {"mm", "maxmemory"}, {"window", "window"}, {"w", "window"}, {"minReadLen", "minReadLen"}, {"m", "minReadLen"},
+      {"perc_identity", "perc_identity"}, {"pi", "perc_identity"}, {"threads", "threads"}, {"t", "threads"}, {"query", "query"}, {"q", "query"},
+      {"all", "all"}, {"output", "output"}, {"o", "output"}, {"device", "device"}};
+  Options o = parse_args(argc, argv, 2, alias, {"all"});
+  Params P;
+  if (!o.has("reference")) die("Provide reference file (s)");
+  P.ref = o.get("reference");
+  P.referenceSize = file_size(P.ref);                                   // commonFunc.hpp:211
+  if (o.has("maxmemory")) P.maximumMemory = (uint64_t)(std::pow(1024, 3) * strtoull(o.get("maxmemory").c_str(), nullptr, 10));
+  if (o.has("kmer")) P.kmerSize = atoi(o.get("kmer").c_str());
+  if (o.has("pval")) P.p_value = atof(o.get("pval").c_str());
+  if (o.has("minReadLen")) P.minReadLength = atoi(o.get("minReadLen").c_str());
+  if (o.has("perc_identity")) P.percentageIdentity = (float)atof(o.get("perc_identity").c_str());
+  if (o.has("window")) {                                                // parseCmdArgs.hpp:363-374
+    P.windowSize = atoi(o.get("window").c_str());
+    int s = P.minReadLength * 2 / P.windowSize;
+    P.p_value = mm_stat_estimate_pvalue(s, P.kmerSize, P.alphabetSize, P.percentageIdentity, P.minReadLength, P.referenceSize);
+  } else {
+    P.windowSize = mm_stat_recommended_window(P.p_value, P.kmerSize, P.alphabetSize, P.percentageIdentity, P.minReadLength, P.referenceSize);
+  }
+  if (!o.has("query")) die("Provide query file (s)");
+  P.query = o.get("query");
+  P.reportAll = o.has("all");
+  if (o.has("threads")) P.threads = atoi(o.get("threads").c_str());
+  if (!o.has("output")) die("Provide output file");
+  P.out = o.get("output");
+  std::vector<std::string> queries = split(P.query, ","), prefixes = split(P.out, ",");
+  if (queries.size() != prefixes.size()) die("Please specify an equal number of input and output files (as comma-separated lists)");
+  int device = o.has("device") ? atoi(o.get("device").c_str()) : 0;
+
+  std::cout << "Parameters used:\n\t- alphabetSize: " << P.alphabetSize << "\n\t- kmerSize: " << P.kmerSize << "\n\t- minReadLength: " << P.minReadLength
+            << "\n\t- p_value: " << P.p_value << "\n\t- percentageIdentity: " << P.percentageIdentity << "\n\t- windowSize: " << P.windowSize
+            << "\n\t- maximumMemory: ~" << P.maximumMemory / std::pow(1024, 3) << " GB (GPU build: the index is device-resident, no chunking)\n\n" << std::flush;
+
+  mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
+  mm_index* idx = nullptr; ck(mm_index_create(ctx, P.kmerSize, P.windowSize, &idx), "mm_index_create");
+  std::vector<Contig> meta;
+  {
+    mmhost::FastxReader rd(P.ref);
+    if (!rd.ok()) die("Cannot open " + P.ref);
+    std::string buf; std::vector<int64_t> off{0};
+    auto flush = [&]() {
+      if (off.size() > 1) ck(mm_index_add(idx, buf.data(), off.data(), (int32_t)off.size() - 1), "mm_index_add");
+      buf.clear(); off.assign(1, 0);
+    };
+    long len;
+    while ((len = rd.read()) >= 0) {
+      meta.push_back(Contig{rd.name, (int)len});
+      buf += rd.seq; off.push_back((int64_t)buf.size());
+      if (buf.size() >= ((size_t)256 << 20)) flush();
+    }
+    flush();
+    ck(mm_index_finalize(idx), "mm_index_finalize");
+  }
+  int64_t nMin = 0, nUniq = 0; int32_t freq = 0, nCont = 0; int64_t bytes = 0;
+  mm_index_stats(idx, &nMin, &nUniq, &freq, &nCont, &bytes);
+  std::cout << "INFO, skch::Sketch::build, minimizers picked from reference = " << nMin << std::endl;
+  if (freq != 0x7fffffff) std::cout << "INFO, skch::Sketch::computeFreqHist, With threshold 0.001%, ignore minimizers occurring >= " << freq << " times during lookup." << std::endl;
+  else std::cout << "INFO, skch::Sketch::computeFreqHist, With threshold 0.001%, consider all minimizers during lookup." << std::endl;
+
+  for (size_t fi = 0; fi < queries.size(); fi++) {
+    const std::string prefix = prefixes[fi];
+    std::ofstream out(prefix);
+    if (!out.is_open()) die("Cannot open output file " + prefix);
+    std::ofstream metaLengths(prefix + ".meta.unmappedReadsLengths");
+    size_t total = 0, tooShort = 0, mapped = 0, notMapped = 0;
+    std::set<std::string> seenIDs;
+    mmhost::FastxReader rd(queries[fi]);
+    if (!rd.ok()) die("Cannot open " + queries[fi]);
+    std::string buf; std::vector<int64_t> off{0}; std::vector<std::string> names;
+
+    auto flush = [&]() {
+      int32_t n = (int32_t)names.size();
+      if (n == 0) return;
+      mm_map_params mp{P.percentageIdentity, P.minReadLength, P.reportAll ? 1 : 0, 0};
+      mm_map_summary sum;
+      ck(mm_map_batch(ctx, idx, buf.data(), off.data(), n, &mp, &sum), "mm_map_batch");
+      std::vector<int32_t> sk((size_t)n); std::vector<int64_t> co((size_t)n + 1);
+      ck(mm_map_fetch_reads(ctx, sk.data(), nullptr, co.data()), "mm_map_fetch_reads");
+      size_t C = (size_t)sum.n_candidates;
+      std::vector<int32_t> seq(C), pos(C), shared(C), votes(C), acc(C);
+      ck(mm_map_fetch_candidates(ctx, seq.data(), nullptr, nullptr, pos.data(), shared.data(), votes.data(), acc.data(), nullptr, nullptr, nullptr), "mm_map_fetch_candidates");
+      // reportReadMappings (computeMap.hpp:546-588) -> 12 columns per kept mapping
+      struct Line { std::string text; double identity; int shared, sketch; };
+      std::vector<Line> lines; std::vector<int64_t> roff{0}; std::vector<int32_t> rlen; std::vector<int32_t> ridx;
+      for (int32_t r = 0; r < n; r++) {
+        int len = (int)(off[(size_t)r + 1] - off[(size_t)r]);
+        total++;
+        if (len < P.windowSize || len < P.kmerSize || len < P.minReadLength) { tooShort++; continue; }
+        std::vector<size_t> keep; std::vector<float> nuc;
+        float best = 0;
+        for (int64_t c = co[(size_t)r]; c < co[(size_t)r + 1]; c++) if (acc[(size_t)c]) {
+          float a, b; mm_stat_identity(shared[(size_t)c], sk[(size_t)r], P.kmerSize, &a, &b);
+          keep.push_back((size_t)c); nuc.push_back(a); if (a > best) best = a;
+        }
+        size_t before = lines.size();
+        for (size_t j = 0; j < keep.size(); j++) {
+          if (!(P.reportAll || nuc[j] >= best - 1.0)) continue;
+          size_t c = keep[j];
+          std::ostringstream l;
+          l << names[(size_t)r] << " " << len << " 0 " << len - 1 << " " << (votes[c] > 0 ? "+" : "-") << " " << meta[(size_t)seq[c]].name << " "
+            << meta[(size_t)seq[c]].len << " " << pos[c] << " " << pos[c] + len - 1 << " " << nuc[j] << " " << shared[c] << " " << sk[(size_t)r];
+          // addMappingQualities re-parses the printed identity (mapWrap.h:229)
+          lines.push_back(Line{l.str(), std::stod(g6(nuc[j])) / 100.0, shared[c], sk[(size_t)r]});
+        }
+        if (lines.size() == before) { notMapped++; metaLengths << len << "\t" << names[(size_t)r] << "\n"; }
+        else {
+          mapped++;
+          if (!seenIDs.insert(names[(size_t)r]).second) die("Seems that read ID " + names[(size_t)r] + " has already been processed - this target ID " + names[(size_t)r] + "\n");
+          roff.push_back((int64_t)lines.size()); rlen.push_back(len); ridx.push_back(r);
+        }
+      }
+      if (!lines.empty()) {                                            // mapWrap.h:215-323
+        std::vector<double> id(lines.size()), mq(lines.size()); std::vector<int32_t> sh(lines.size()), ss(lines.size()), st(rlen.size());
+        for (size_t i = 0; i < lines.size(); i++) { id[i] = lines[i].identity; sh[i] = lines[i].shared; ss[i] = lines[i].sketch; }
+        ck(mm_mapq_batch(ctx, id.data(), sh.data(), ss.data(), rlen.data(), roff.data(), (int64_t)rlen.size(), P.kmerSize, mq.data(), st.data()), "mm_mapq_batch");
+        for (size_t r = 0; r < rlen.size(); r++) if (st[r]) die("WARNING!\n\tlikelihood_sum: 0\n\treadID: " + names[(size_t)ridx[r]] + "\n========= END ==========");
+        for (size_t i = 0; i < lines.size(); i++) {
+          float corrected = exp(-(1 - id[i]));
+          out << lines[i].text << " " << corrected * 100 << " " << mq[i] << "\n";
+        }
+      }
+      buf.clear(); off.assign(1, 0); names.clear();
+    };
+    long len;
+    while ((len = rd.read()) >= 0) {
+      names.push_back(rd.name); buf += rd.seq; off.push_back((int64_t)buf.size());
+      if (buf.size() >= ((size_t)512 << 20) || names.size() >= (1u << 20)) flush();
+    }
+    flush();
+    out.close(); metaLengths.close();
+    std::ofstream m(prefix + ".meta");
+    m << "TotalReads " << total << "\nReadsTooShort " << tooShort << "\nReadsMapped " << mapped << "\nReadsNotMapped " << notMapped << "\n";
+    m.close();
+    std::ofstream ps(prefix + ".parameters");                          // mapWrap.h:196-211
+    ps << "kmerSize " << P.kmerSize << "\nwindowSize " << P.windowSize << "\nminReadLength " << P.minReadLength << "\nalphabetSize " << P.alphabetSize
+       << "\nreferenceSize " << P.referenceSize << "\npercentageIdentity " << P.percentageIdentity << "\np_value " << P.p_value
+       << "\nrefSequences [" << P.ref << "]\nquerySequences [" << queries[fi] << "]\noutFileName " << prefix << "\nreportAll " << (P.reportAll ? 1 : 0)
+       << "\nindex \nmaximumMemory " << P.maximumMemory << "\n";
+    std::cout << "INFO, skch::Map::mapQuery, [count of mapped reads, reads qualified for mapping, total input reads] = [" << mapped << ", "
+              << total - tooShort << ", " << total << "]" << std::endl;
+  }
+  mm_index_destroy(idx); mm_ctx_destroy(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ classify
+struct TaxNode { std::string parent, rank, name; };
+struct Taxonomy {                                                       // taxonomy.h:137-246
+  std::map<std::string, TaxNode> T;
+  static std::vector<std::string> dmp_fields(std::string line) {
+    std::vector<std::string> f = split(line, "|");
+    for (auto& x : f) { size_t a = x.find_first_not_of(" \t"); size_t b = x.find_last_not_of(" \t"); x = (a == std::string::npos) ? "" : x.substr(a, b - a + 1); }
+    return f;
+  }
+  explicit Taxonomy(const std::string& dir) {
+    std::map<std::string, std::string> names;
+    std::ifstream n(dir + "/names.dmp");
+    if (!n.is_open()) die("Cannot open file " + dir + "/names.dmp -- is '" + dir + "' a valid NCBI taxonomy?");
+    std::string line;
+    while (std::getline(n, line)) { erase_nl(line); if (line.empty()) continue; auto f = dmp_fields(line); if (f.size() > 3 && f[3] == "scientific name") names[f[0]] = f[1]; }
+    std::ifstream d(dir + "/nodes.dmp");
+    if (!d.is_open()) die("Cannot open file " + dir + "/nodes.dmp -- is '" + dir + "' a valid NCBI taxonomy?");
+    while (std::getline(d, line)) {
+      erase_nl(line); if (line.empty()) continue; auto f = dmp_fields(line);
+      if (!names.count(f[0])) die("No name for taxon ID " + f[0] + " in taxonomy directory " + dir);
+      T[f[0]] = TaxNode{f[1], f[2], names[f[0]]};
+    }
+    std::cout << "Read taxonomy from " << dir << " -- have " << T.size() << " nodes." << std::endl;
+  }
+  std::vector<std::string> upward(std::string id) const { std::vector<std::string> u{id}; while (id != "1") { id = T.at(id).parent; u.push_back(id); } return u; }
+  std::map<std::string, std::string> upward_by_ranks(const std::string& id, const std::set<std::string>& ranks) const {      // taxonomy.h:76-110
+    std::map<std::string, std::string> r;
+    for (auto& n : upward(id)) {
+      const std::string& rank = T.at(n).rank;
+      if (!ranks.empty() && !ranks.count(rank)) continue;
+      if (rank != "no rank") { if (r.count(rank)) die("Node " + id + " has multiple entries for rank " + rank); r[rank] = n; }
+    }
+    for (auto& t : ranks) if (!r.count(t)) r[t] = "Undefined";
+    return r;
+  }
+  std::string first_non_x(std::string id) const { while (id.find("x") != std::string::npos) id = T.at(id).parent; return id; }
+};
+
+std::string extract_taxon(const std::string& contig) {                  // fEM.h:1396-1414, regex kraken:taxid\|(x?\d+)
+  size_t p = 0; const std::string tag = "kraken:taxid|";
+  while ((p = contig.find(tag, p)) != std::string::npos) {
+    size_t q = p + tag.size(), s = q;
+    if (q < contig.size() && contig[q] == 'x') q++;
+    size_t dstart = q;
+    while (q < contig.size() && isdigit((unsigned char)contig[q])) q++;
+    if (q > dstart) return contig.substr(s, q - s);
+    p += 1;
+  }
+  die("Could not extract taxon ID from contig identifier '" + contig + "' - did you use the MetMaps build scripts to construct your database?");
+}
+
+size_t overlap(size_t a1, size_t a2, size_t b1, size_t b2) {            // util.h:150: closed intervals
+  size_t lo = std::max(a1, b1), hi = std::min(a2, b2);
+  return hi >= lo ? hi - lo + 1 : 0;
+}
+
+// tail sums for the evidence file (fEM.h:1101-1108): Poisson pmf at 0 and binomial cdf
+double binom_cdf_host(long k, long n, double p) {
+  if (k < 0) return 0; if (k >= n) return 1;
+  double s = 0;
+  for (long j = 0; j <= k; j++) s += std::exp(std::lgamma(n + 1.0) - std::lgamma(j + 1.0) - std::lgamma(n - j + 1.0) + j * std::log(p) + (n - j) * std::log1p(-p));
+  return std::min(1.0, s);
+}
+
+void classify_one(const std::string& DB, const std::string& mapped, int device, size_t minReadsPerBest) {
+  // ---- read the mappings file, grouped by consecutive read id (fEM.h:1167-1214)
+  std::vector<std::vector<std::string>> fields; std::vector<int64_t> readOff{0}; std::vector<std::string> lines;
+  {
+    std::ifstream in(mapped);
+    if (!in.is_open()) die("Cannot open mappings file " + mapped);
+    std::string line, running;
+    while (std::getline(in, line)) {
+      erase_nl(line); if (line.empty()) continue;
+      std::vector<std::string> f = split(line, " ");
+      if (f.size() < 14) die("File " + mapped + " has weird format - is this a mappings file generated by MetaMap?");
+      if (f[0] != running) { if (!fields.empty()) readOff.push_back((int64_t)fields.size()); running = f[0]; }
+      fields.push_back(f); lines.push_back(line);
+    }
+    if (!fields.empty()) readOff.push_back((int64_t)fields.size());
+  }
+  size_t M = fields.size(); int64_t nReads = (int64_t)readOff.size() - 1;
+  std::vector<std::string> mTaxon(M);
+  std::set<std::string> relevant;
+  for (size_t m = 0; m < M; m++) { mTaxon[m] = extract_taxon(fields[m][5]); relevant.insert(mTaxon[m]); }
+  if (relevant.empty()) die("No relevant taxon IDs found in your mappings file - is it possible that none of your reads are mapped?");
+  std::map<std::string, size_t> stats;
+  {
+    std::ifstream s(mapped + ".meta");
+    if (!s.is_open()) die("The file " + mapped + ".meta is not present or could not be opened - this file is generated automatically as part of the mapping process, so please check whether the mapping process finished successfully.");
+    std::string line; while (std::getline(s, line)) { erase_nl(line); if (line.empty()) continue; auto f = split(line, " "); stats[f[0]] = strtoull(f[1].c_str(), nullptr, 10); }
+  }
+  size_t nUnmapped = stats.at("ReadsNotMapped"), nTooShort = stats.at("ReadsTooShort"), nTotal = stats.at("TotalReads"), nMapped = stats.at("ReadsMapped");
+  // ---- taxonInfo.txt (fEM.h:1320-1364)
+  std::map<std::string, std::map<std::string, size_t>> taxonInfo;
+  {
+    std::ifstream t(DB + "/taxonInfo.txt");
+    if (!t.is_open()) die("Could not open file " + DB + "/taxonInfo.txt -- perhaps you have specified an incomplete DB?");
+    std::string line;
+    while (std::getline(t, line)) {
+      erase_nl(line); if (line.empty()) continue;
+      auto f = split(line, " ");
+      if (f.size() != 2) die("Weird format in " + DB + "/taxonInfo.txt -- wrong number of fields.");
+      if (!relevant.count(f[0])) continue;
+      for (auto& c : split(f[1], ";")) { auto kv = split(c, "="); taxonInfo[f[0]][kv[0]] = strtoull(kv[1].c_str(), nullptr, 10); }
+    }
+  }
+  Taxonomy T(DB + "/taxonomy");
+  std::vector<std::string> taxa(relevant.begin(), relevant.end());       // std::map order of the reference's f
+  std::map<std::string, int32_t> tIdx; for (size_t i = 0; i < taxa.size(); i++) tIdx[taxa[i]] = (int32_t)i;
+  // ---- per mapping: taxon index, mapq, nloc (fEM.h:246-348)
+  std::vector<int32_t> taxon(M); std::vector<double> mapq(M), nloc(M), identity(M); std::vector<long long> rlen((size_t)nReads);
+  for (int64_t r = 0; r < nReads; r++) {
+    long long L = std::stoi(fields[(size_t)readOff[(size_t)r]][1]); rlen[(size_t)r] = L;
+    std::set<std::string> sawContigs; std::map<std::string, double> perTaxon;
+    for (int64_t m = readOff[(size_t)r]; m < readOff[(size_t)r + 1]; m++) sawContigs.insert(fields[(size_t)m][5]);
+    for (int64_t m = readOff[(size_t)r]; m < readOff[(size_t)r + 1]; m++) {
+      const std::string& t = mTaxon[(size_t)m];
+      if (!taxonInfo.count(t)) die("Unknown taxonID '" + t + "'; please check that your mappings file was mapped against the database now specified.");
+      if (!perTaxon.count(t)) {
+        size_t n = 0;
+        for (auto& c : taxonInfo.at(t)) { if ((long long)c.second >= L) n += (c.second - L + 1); else if (sawContigs.count(c.first)) n++; }
+        perTaxon[t] = (double)n;
+      }
+      taxon[(size_t)m] = tIdx.at(t); nloc[(size_t)m] = perTaxon[t];
+      double q; try { q = std::stod(fields[(size_t)m][13]); } catch (const std::out_of_range&) { q = 0; }
+      mapq[(size_t)m] = q; identity[(size_t)m] = std::stod(fields[(size_t)m][9]) / 100.0;
+    }
+  }
+  // ---- EM on the GPU (fEM.h:491-661)
+  std::cout << "Starting EM..." << std::endl;
+  mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
+  int32_t Tn = (int32_t)taxa.size(), iters = 0;
+  std::vector<double> f((size_t)Tn), post(M), ll(4096); std::vector<int64_t> best((size_t)std::max<int64_t>(nReads, 1));
+  ck(mm_em_run(ctx, taxon.data(), mapq.data(), nloc.data(), readOff.data(), nReads, Tn, 0, f.data(), post.data(), best.data(), ll.data(), 4096, &iters), "mm_em_run");
+  mm_ctx_destroy(ctx);
+  for (int i = 0; i < iters && i < 4096; i++) {
+    std::cout << "EM round " << i << "\n\n\tLog likelihood: " << ll[(size_t)i] << std::endl;
+    if (i > 0) std::cout << "\tImprovement: " << ll[(size_t)i] - ll[(size_t)i - 1] << "\n\tRelative   : " << ll[(size_t)i] / ll[(size_t)i - 1] << std::endl;
+  }
+  // ---- final pass (fEM.h:663-782)
+  std::ofstream oId(mapped + ".EM.lengthAndIdentitiesPerMappingUnit"), oEM(mapped + ".EM"), oR2T(mapped + ".EM.reads2Taxon"), oKrona(mapped + ".EM.reads2Taxon.krona");
+  oId << "AnalysisLevel\tID\treadI\tIdentity\tLength\n";
+  const size_t W = 1000;
+  std::map<std::string, std::map<std::string, std::vector<size_t>>> cov, covReads; std::map<std::string, std::map<std::string, size_t>> lastWin;
+  std::map<std::string, size_t> readsPerTaxon; std::map<std::string, std::vector<double>> idPerTaxon; long long maxReadLen = -1;
+  std::cout << "Outputting mappings with adjusted alignment qualities." << std::endl;
+  for (int64_t r = 0; r < nReads; r++) {
+    for (int64_t m = readOff[(size_t)r]; m < readOff[(size_t)r + 1]; m++) {
+      std::vector<std::string> f2 = fields[(size_t)m]; f2[13] = std::to_string(post[(size_t)m]);
+      for (size_t i = 0; i < f2.size(); i++) oEM << (i ? " " : "") << f2[i];
+      oEM << "\n";
+    }
+    size_t b = (size_t)best[(size_t)r];
+    const std::string& bt = mTaxon[b]; const std::string& bc = fields[b][5];
+    const std::string& readID = fields[b][0];
+    oId << "EqualCoverageUnit\t" << bc << "\t" << r << "\t" << identity[b] << "\t" << rlen[(size_t)r] << "\n";
+    oR2T << readID << "\t" << bt << "\n";
+    oKrona << readID << "\t" << T.first_non_x(bt) << "\t" << post[b] << "\n";
+    idPerTaxon[bt].push_back(identity[b]);
+    if (rlen[(size_t)r] > maxReadLen) maxReadLen = rlen[(size_t)r];
+    readsPerTaxon[bt]++;
+    size_t clen = taxonInfo.at(bt).at(bc);
+    if (!cov[bt].count(bc)) {                                            // fEM.h:730-752
+      size_t nw = clen / W;
+      if (nw == 0) { nw++; lastWin[bt][bc] = clen; }
+      else if (nw * W != clen) { nw++; lastWin[bt][bc] = clen - (nw * W); }
+      else lastWin[bt][bc] = W;
+      cov[bt][bc].assign(nw, 0); covReads[bt][bc].assign(nw, 0);
+    }
+    size_t start = strtoull(fields[b][7].c_str(), nullptr, 10), stop = strtoull(fields[b][8].c_str(), nullptr, 10);
+    size_t stopPos = stop >= clen ? clen - 1 : stop;
+    for (size_t p = start; p <= stopPos; p += W) {                        // fEM.h:755-776
+      size_t wi = p / W, ws = wi * W, we = (wi + 1) * W - 1;
+      if (we > clen) we = clen - 1;
+      cov[bt][bc].at(wi) += overlap(ws, we, start, stopPos);
+      covReads[bt][bc].at(wi)++;
+    }
+  }
+  {
+    std::ifstream u(mapped + ".meta.unmappedReadsLengths"); std::string line;   // fEM.h:785-790
+    while (std::getline(u, line)) { erase_nl(line); if (line.empty()) continue; auto f2 = split(line, "\t"); oR2T << f2[1] << "\t0\n"; oKrona << f2[1] << "\t0\t0\n"; }
+  }
+  oId.close(); oEM.close(); oR2T.close(); oKrona.close();
+  // ---- cleanF (fEM.h:1135-1163)
+  std::map<std::string, double> fm; for (size_t i = 0; i < taxa.size(); i++) fm[taxa[i]] = f[i];
+  {
+    double minFreq = 0.9 * (1.0 / (double)nMapped);
+    std::set<std::string> del; for (auto& e : fm) if (e.second < minFreq && !readsPerTaxon.count(e.first)) del.insert(e.first);
+    for (auto& d : del) fm.erase(d);
+    double s = 0; for (auto& e : fm) s += e.second;
+    for (auto& e : fm) e.second /= s;
+  }
+  // ---- producePotFile (fEM.h:52-215)
+  {
+    const std::set<std::string> levels = {"species", "genus", "family", "order", "phylum", "superkingdom"};
+    std::map<std::string, std::set<std::string>> keys; std::map<std::string, std::map<std::string, double>> fl; std::map<std::string, std::map<std::string, size_t>> rc;
+    for (auto& e : fm) {
+      auto up = T.upward_by_ranks(e.first, levels); up["definedGenomes"] = e.first;
+      for (auto& u : up) { fl[u.first][u.second] += e.second; keys[u.first].insert(u.second); if (fl[u.first][u.second] > 1) fl[u.first][u.second] = 1; }
+    }
+    for (auto& e : readsPerTaxon) {
+      auto up = T.upward_by_ranks(e.first, levels); up["definedGenomes"] = e.first;
+      for (auto& u : up) {
+        if (fl[u.first].count(u.second) == 0) rc[u.first][u.second] = 0;       // (sic) fEM.h:105-106
+        rc[u.first][u.second] += e.second; keys[u.first].insert(u.second);
+      }
+    }
+    long long nMappable = (long long)nTotal - (long long)nTooShort, nMap2 = nMappable - (long long)nUnmapped;
+    std::ofstream o(mapped + ".EM.WIMP");
+    o << "AnalysisLevel\ttaxonID\tName\tAbsolute\tEMFrequency\tPotFrequency\n";
+    for (auto& l : keys) {
+      const std::string& lv = l.first; std::map<std::string, double> orig; double sumAssigned = 0;
+      for (auto& t : l.second) { double v = fl[lv].count(t) ? fl[lv][t] : 0; size_t c = rc[lv].count(t) ? rc[lv][t] : 0; sumAssigned += v; fl[lv][t] = v; rc[lv][t] = c; }
+      for (auto& t : l.second) { fl[lv][t] /= sumAssigned; orig[t] = fl[lv][t]; }
+      double propMapped = (double)nMap2 / nMappable, propNot = (double)nUnmapped / nMappable;
+      for (auto& t : l.second) fl[lv][t] *= propMapped;
+      double emUnm = 0; size_t nUnd = nUnmapped;
+      for (auto& t : l.second) {
+        if (t != "Undefined") o << lv << "\t" << t << "\t" << T.T.at(t).name << "\t" << rc[lv][t] << "\t" << orig[t] << "\t" << fl[lv][t] << "\n";
+        else { nUnd += rc[lv][t]; emUnm += orig[t]; propNot += fl[lv][t]; }
+      }
+      o << lv << "\t0\tUnclassified\t" << nUnd << "\t" << emUnm << "\t" << propNot << "\n";
+      o << lv << "\t-3\ttotalReads\t" << nTotal << "\t0\t0\n" << lv << "\t-3\treadsLongEnough\t" << nMappable << "\t0\t0\n" << lv << "\t-3\treadsLongEnough_unmapped\t" << nUnmapped << "\t0\t0\n";
+    }
+  }
+  // ---- contig coverage (fEM.h:805-844)
+  std::map<std::string, std::string> contig2taxon;
+  {
+    std::ofstream o(mapped + ".EM.contigCoverage");
+    o << "taxonID\tequalCoverageUnitLabel\tcontigID\tstart\tstop\tnBases\treadCoverage\n";
+    for (auto& t : cov) for (auto& c : t.second) {
+      for (size_t wi = 0; wi < c.second.size(); wi++) {
+        size_t wl = (wi == c.second.size() - 1) ? lastWin.at(t.first).at(c.first) : W;
+        size_t nb = c.second[wi];
+        o << t.first << "\t" << T.T.at(t.first).name << "\t" << c.first << "\t" << wi * W << "\t" << (wi + 1) * W - 1 << "\t" << nb << "\t" << (double)nb / (double)wl << "\n";
+      }
+      contig2taxon[c.first] = t.first;
+    }
+  }
+  // ---- evidence for unknown species (fEM.h:846-1132)
+  {
+    std::string bestTaxon; double bestMedian = 0, oneThird = 0, oneThirdP = 0;
+    for (auto e : idPerTaxon) {
+      auto ids = e.second;
+      if (ids.size() >= 3 && ids.size() >= minReadsPerBest) {
+        std::sort(ids.begin(), ids.end());
+        double med = ids.at(ids.size() / 2);
+        if (bestTaxon.empty() || med > bestMedian) {
+          bestMedian = med; bestTaxon = e.first; oneThird = ids.at((size_t)(ids.size() * (1.0 / 3.0)));
+          size_t n = 0; for (double v : ids) if (v <= oneThird) n++;
+          oneThirdP = (double)n / (double)ids.size();
+        }
+      }
+    }
+    std::map<std::string, std::vector<size_t>> Ns;
+    {
+      std::ifstream w(DB + "/contigNstats_windowSize_1000.txt"); std::string line;
+      while (std::getline(w, line)) {
+        erase_nl(line); if (line.empty()) continue; auto f2 = split(line, "\t");
+        if (f2.size() != 3) continue;
+        if (cov.count(f2[0]) && cov.at(f2[0]).count(f2[1])) { std::vector<size_t> v; for (auto& x : split(f2[2], ";")) v.push_back(strtoull(x.c_str(), nullptr, 10)); Ns[f2[1]] = v; }
+      }
+      for (auto& t : cov) for (auto& c : t.second) if (!Ns.count(c.first)) die("\nMissing entry " + c.first + " in " + DB + "/contigNstats_windowSize_1000.txt\n");
+    }
+    std::map<std::string, size_t> gw, gwUse, gwReads; std::map<std::string, double> gwZero;
+    size_t need = (size_t)maxReadLen;
+    for (auto& cd : Ns) {
+      const std::string& t = contig2taxon.at(cd.first); size_t n = cd.second.size();
+      std::vector<size_t> fw(n, 0), bw(n, 0); size_t run = 0;
+      auto wlen = [&](size_t wi) { return wi == n - 1 ? lastWin.at(t).at(cd.first) : W; };
+      for (size_t wi = 0; wi < n; wi++) { fw[wi] = run; if ((double)cd.second[wi] / (double)wlen(wi) <= 0.02) run += wlen(wi); else run = 0; }
+      run = 0;
+      for (long long wi = (long long)n - 1; wi >= 0; wi--) { bw[(size_t)wi] = run; if ((double)cd.second[(size_t)wi] / (double)wlen((size_t)wi) <= 0.02) run += wlen((size_t)wi); else run = 0; }
+      size_t use = 0, useReads = 0, useZero = 0;
+      for (size_t wi = 0; wi < n; wi++) if (fw[wi] >= need && bw[wi] >= need) { use++; size_t c = covReads.at(t).at(cd.first).at(wi); useReads += c; if (c == 0) useZero++; }
+      gw[t] += n; gwUse[t] += use; gwReads[t] += useReads; gwZero[t] += useZero;
+    }
+    std::ofstream o(mapped + ".EM.evidenceUnknownSpecies");
+    o << "taxonID\tspecies\tgenus\tnReads\tpropBottomThirdReadIdentities\texpectedPropBottomThirdReadIdentities\tpValue_BottomThirdReadIdentities\tcoverageWindows_totalGenome"
+         "\tcoverageWindows_usable\tcoverageWindows_usable_averageCoverage\tcoverageWindows_usable_coverageIsZero\tcoverageWindows_usable_coverageIsZero_expected"
+         "\tcoverageWindows_usable_coverageIsZero_P\n";
+    for (auto& e : idPerTaxon) {
+      const std::string& t = e.first; const auto& ids = e.second;
+      std::string sProp = "NA", sP = "NA", sExp = "NA";
+      if (!bestTaxon.empty()) {
+        size_t obs = 0; for (double v : ids) if (v <= oneThird) obs++;
+        size_t obsNon = ids.size() - obs; double ex = oneThirdP * ids.size(), exNon = ids.size() - ex;
+        sExp = std::to_string(oneThirdP);
+        double stat = std::pow(obs - ex, 2) / ex + std::pow(obsNon - exNon, 2) / exNon;
+        sProp = std::to_string((double)obs / (double)ids.size());
+        sP = std::to_string(1 - std::erf(std::sqrt(stat / 2.0)));          // chi-squared, 1 d.f.
+      }
+      std::string sAvg = "NA", sZeroExp = "NA", sZeroP = "NA";
+      if (gwUse.at(t) > 0) {
+        double avg = (double)gwReads.at(t) / (double)gwUse.at(t); sAvg = std::to_string(avg);
+        if (avg == 0) { sZeroExp = std::to_string(gwUse.at(t)); sZeroP = std::to_string(1); }
+        else {
+          double p0 = std::exp(-avg); sZeroExp = std::to_string(gwUse.at(t) * p0);
+          double pv = 1;
+          if (gwZero.at(t) > 0) pv = 1 - binom_cdf_host((long)gwZero.at(t) - 1, (long)gwUse.at(t), p0);
+          sZeroP = std::to_string(pv);
+        }
+      }
+      auto up = T.upward_by_ranks(t, {"species", "genus"});
+      o << t << "\t" << up.at("species") << "\t" << up.at("genus") << "\t" << ids.size() << "\t" << sProp << "\t" << sExp << "\t" << sP << "\t" << gw.at(t) << "\t"
+        << gwUse.at(t) << "\t" << sAvg << "\t" << gwZero.at(t) << "\t" << sZeroExp << "\t" << sZeroP << "\n";
+    }
+  }
+}
+
+int run_classify(int argc, char** argv) {
+  const std::map<std::string, std::string> alias = {{"DB", "DB"}, {"mappings", "mappings"}, {"minreads", "minreads"}, {"threads", "threads"}, {"t", "threads"}, {"device", "device"}};
+  Options o = parse_args(argc, argv, 2, alias, {});
+  if (!o.has("DB") || !o.has("mappings")) die("classify needs --DB and --mappings");
+  int device = o.has("device") ? atoi(o.get("device").c_str()) : 0;
+  size_t minReads = o.has("minreads") ? strtoull(o.get("minreads").c_str(), nullptr, 10) : 10000;      // parseCmdArgs.hpp:462-471
+  for (auto& m : split(o.get("mappings"), ",")) classify_one(o.get("DB"), m, device, minReads);
+  return 0;
+}
+
+void usage() {
+  std::cout << "\nMetaMaps (metamaps_b200: B200 compute core) \n\n  Simultaneous metagenomic classification and mapping.\n\nUsage:\n\n  ./metamaps mapDirectly|classify\n\n"
+               "  mapDirectly -r <ref.fa[.gz]> -q <reads.fq[,..]> -o <prefix[,..]> [--all] [-k 16] [-w W | -p 1e-3] [-m 1000] [--pi 80] [-t N] [--maxmemory GB] [--device 0]\n"
+               "  classify --DB <dir> --mappings <prefix[,..]> [-t N] [--device 0]\n\n";
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 2) { usage(); return 1; }
+  std::string cmd = argv[1];
+  if (cmd == "mapDirectly") return run_mapDirectly(argc, argv);
+  if (cmd == "classify") return run_classify(argc, argv);
+  if (cmd == "index" || cmd == "mapAgainstIndex" || cmd == "classifyU") die("sub-command '" + cmd + "' is not part of the GPU hot path (see DESIGN.md, out of scope)");
+  usage();
+  return 1;
+}

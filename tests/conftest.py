@@ -61,6 +61,16 @@ def build_emu():
     return EMU_SO
 
 
+EMU_HOST = os.path.join(ROOT, "tests", "_emu", "metamaps_emu")
+
+
+def build_emu_host():
+    """The C++ host linked against the host-emulation library (CPU test tier only)."""
+    from metamaps_b200 import build as b
+    build_emu()
+    return b.build_host(os.path.dirname(EMU_SO), "mm_emu", EMU_HOST)
+
+
 @pytest.fixture(scope="session")
 def emu_ctx():
     from metamaps_b200 import capi

@@ -1,0 +1,55 @@
+"""The C++ host linked against the host-emulation library writes the same files as the reference CLI."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from metamaps_b200 import synth
+from tests import cli_common
+from tests.conftest import GOLDEN, build_emu_host
+
+
+def test_cli_matches_golden_reference_files(small_workload):
+    binary = build_emu_host()
+    got = cli_common.run_cli(binary, small_workload["dir"], out="out_emu")
+    n_identical = cli_common.compare_dirs(os.path.join(GOLDEN, "ref_small"), got)
+    assert n_identical >= 8      # byte-identical in practice; float columns may differ in the last printed digit
+
+
+def test_cli_matches_live_reference_with_options(tmp_path):
+    from oracle import pyoracle
+    if not pyoracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    binary = build_emu_host()
+    d = str(tmp_path)
+    db = synth.make_db(5, 3, 2, 50_000, 0.03)
+    synth.write_db(db, os.path.join(d, "db"))
+    names, reads, _ = synth.make_reads(db, 6, 150, 2500, lognormal_sigma=0.4, clip=(600, 9000), frac_random=0.03)
+    synth.write_fastq(os.path.join(d, "reads.fq"), names, reads)
+    for extra, tag in ((("-m", "800", "--pi", "85"), "a"), (("-w", "7", "-k", "15"), "b")):
+        os.makedirs(os.path.join(d, "out_ref" + tag), exist_ok=True)
+        subprocess.run([pyoracle.REF_BIN, "mapDirectly", "--all", "-r", "db/DB.fa", "-q", "reads.fq", "-o", f"out_ref{tag}/ref", *extra], cwd=d, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.run([pyoracle.REF_BIN, "classify", "--DB", "db", "--mappings", f"out_ref{tag}/ref"], cwd=d, check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        got = cli_common.run_cli(binary, d, extra, out="out_emu" + tag)
+        cli_common.compare_dirs(os.path.join(d, "out_ref" + tag), got)
+
+
+def test_cli_without_all_keeps_top_mappings(tmp_path):
+    """Default (no --all): only mappings within 1 % identity of the best are reported (computeMap.hpp:561-563)."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    binary = build_emu_host()
+    d = str(tmp_path)
+    db = synth.make_db(9, 2, 3, 40_000, 0.02)
+    synth.write_db(db, os.path.join(d, "db"))
+    names, reads, _ = synth.make_reads(db, 10, 80, 3000)
+    synth.write_fastq(os.path.join(d, "reads.fq"), names, reads)
+    os.makedirs(os.path.join(d, "o1")); os.makedirs(os.path.join(d, "o2"))
+    subprocess.run([pyoracle.REF_BIN, "mapDirectly", "-r", "db/DB.fa", "-q", "reads.fq", "-o", "o1/ref"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([binary, "mapDirectly", "-r", "db/DB.fa", "-q", "reads.fq", "-o", "o2/ref"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert open(os.path.join(d, "o1", "ref")).read() == open(os.path.join(d, "o2", "ref")).read()
+    assert open(os.path.join(d, "o1", "ref.meta")).read() == open(os.path.join(d, "o2", "ref.meta")).read()

@@ -127,3 +127,14 @@ def test_pipeline_matches_reference_files(gpu_ctx, small_workload):
     """End to end on arrays against the files written by the unmodified reference binary for the same inputs."""
     from tests.conftest import GOLDEN
     common.check_pipeline_vs_reference_files(gpu_ctx, small_workload, GOLDEN)
+
+
+def test_cli_matches_golden_reference_files(small_workload):
+    """`metamaps mapDirectly` + `classify` (C++ host over the CUDA library) vs the files of the unmodified reference."""
+    import os
+    from metamaps_b200 import build
+    from tests import cli_common
+    from tests.conftest import GOLDEN
+    assert os.path.exists(build.HOST_BIN), "metamaps_b200/metamaps not built"
+    got = cli_common.run_cli(build.HOST_BIN, small_workload["dir"], out="out_gpu")
+    assert cli_common.compare_dirs(os.path.join(GOLDEN, "ref_small"), got) >= 8
