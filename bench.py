@@ -315,15 +315,20 @@ def main():
 
     ms = stats["map"]
     # dominant kernel group and its algorithmic bytes (SURVEY.md 8d / DESIGN.md "algorithmic bytes")
-    stage_ms = {k_: ms[k_] for k_ in ("sketch_ms", "read_sketch_ms", "l1_ms", "l2_setup_ms", "l2_classify_ms", "l2_sweep_ms", "l2_strand_ms")}
+    stage_keys = ("sketch_ms", "read_sketch_ms", "l1_probe_ms", "l1_sort_ms", "l1_candidates_ms", "l2_setup_ms", "l2_classify_ms",
+                  "l2_sweep_ms", "l2_strand_ms", "accept_ms")
+    stage_ms = {k_: ms[k_] for k_ in stage_keys}
     dom = max(stage_ms, key=stage_ms.get)
     alg = {"sketch_ms": ms["bases"] / 4 + 8 * ms["read_minimizers"],
            "read_sketch_ms": 2 * 8 * ms["read_minimizers"],
-           "l1_ms": 16 * ms["sketch_elems"] + 8 * ms["hits"] + 12 * ms["candidates"],
+           "l1_probe_ms": 16 * ms["sketch_elems"] + 8 * ms["hits"],
+           "l1_sort_ms": 2 * 8 * ms["hits"],
+           "l1_candidates_ms": 8 * ms["hits"] + 12 * ms["candidates"],
            "l2_setup_ms": 12 * ms["candidates"],
            "l2_classify_ms": 8 * ms["span_elems"] + 8 * ms["span_elems"],
            "l2_sweep_ms": 2 * 8 * ms["span_elems"] + 20 * ms["candidates"],
-           "l2_strand_ms": 8 * ms["span_elems"] / 2.8}
+           "l2_strand_ms": 8 * ms["span_elems"] / 2.8,
+           "accept_ms": 12 * ms["candidates"]}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -340,7 +345,8 @@ def main():
                    "l2_flush": "inputs (index %.1f GB + reads) larger than L2" % (istats["device_bytes"] / 1e9),
                    "index_minimizers": istats["n_minimizers"], "index_build_s": index_s, "setup_s": setup_s,
                    "mappings_per_step": int(out["summary"]["n_mappings"]), "candidates_per_step": int(out["summary"]["n_candidates"]),
-                   "em_iters": int(out["em"]["iters"]) if out["em"] else 0},
+                   "em_iters": int(out["em"]["iters"]) if out["em"] else 0, "smem_swept": ms["smem_swept"], "ambiguous_reads": ms["ambiguous_reads"],
+                   "span_elems": ms["span_elems"], "hits": ms["hits"], "sketch_elems": ms["sketch_elems"]},
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(r_host.numel() + r_off.nbytes),
                 "d2h_bytes_per_step": int(o2["d2h_bytes"])},

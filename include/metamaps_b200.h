@@ -55,9 +55,14 @@ void mm_ctx_destroy(mm_ctx* ctx);
 /* Device-time (ms, CUDA events on the context stream) and launch count of the kernels issued by the last
  * mm_* call on this context; bench.py uses these for `gpu_launches` and the roofline block. */
 int mm_ctx_last_timing(mm_ctx* ctx, double* total_ms, int64_t* n_launches);
-/* Per-stage device time of the last mm_map_* call: K1 sketch, K3 read sketch, K4 L1, K5 L2 (classify, sweep,
- * strand), plus algorithmic byte counters: s_total, hits, candidates, span elements. */
-int mm_ctx_last_map_stats(mm_ctx* ctx, double* stage_ms /*[8]*/, int64_t* counters /*[8]*/);
+/* Per-stage device time (ms, CUDA events) of the last mm_map_* call:
+ *   [0] K1 sketch  [1] K3 read sketch  [2] K4 probe+gather  [3] K4 hit sort  [4] K4 candidate regions  [5] K5 setup
+ *   [6] K5a classify  [7] K5b sweep  [8] K5c strand  [9] accept + summary
+ * and the algorithmic unit counters: [0] sketch elements s_total  [1] seed hits H  [2] candidates C
+ *   [3] span minimizers sum N_c  [4] accepted mappings  [5] read minimizers  [6] bases of eligible reads
+ *   [7] non-ACGT bases  [8] reads whose duplicate survivor needed the std::sort replay  [9] candidates swept in
+ *   shared memory. */
+int mm_ctx_last_map_stats(mm_ctx* ctx, double* stage_ms /*[16]*/, int64_t* counters /*[16]*/);
 
 /* ---- K1: winnowed minimizers  (replaces CommonFunc::addMinimizers, commonFunc.hpp:92-175) --------- */
 /* Sketches n_seqs sequences; results stay on the device until fetched.  *n_total = number of minimizers. */

@@ -127,12 +127,13 @@ class Context:
         return ms.value, n.value
 
     def last_map_stats(self):
-        ms = np.zeros(8); ct = np.zeros(8, np.int64)
+        ms = np.zeros(16); ct = np.zeros(16, np.int64)
         self.lib.mm_ctx_last_map_stats(self.h, ms, ct)
-        return {"sketch_ms": ms[0], "read_sketch_ms": ms[1], "l1_ms": ms[2], "l2_setup_ms": ms[3], "l2_classify_ms": ms[4],
-                "l2_sweep_ms": ms[5], "l2_strand_ms": ms[6],
+        return {"sketch_ms": ms[0], "read_sketch_ms": ms[1], "l1_probe_ms": ms[2], "l1_sort_ms": ms[3], "l1_candidates_ms": ms[4],
+                "l2_setup_ms": ms[5], "l2_classify_ms": ms[6], "l2_sweep_ms": ms[7], "l2_strand_ms": ms[8], "accept_ms": ms[9],
                 "sketch_elems": int(ct[0]), "hits": int(ct[1]), "candidates": int(ct[2]), "span_elems": int(ct[3]),
-                "mappings": int(ct[4]), "read_minimizers": int(ct[5]), "bases": int(ct[6]), "exceptions": int(ct[7])}
+                "mappings": int(ct[4]), "read_minimizers": int(ct[5]), "bases": int(ct[6]), "exceptions": int(ct[7]),
+                "ambiguous_reads": int(ct[8]), "smem_swept": int(ct[9])}
 
     # K1
     def sketch(self, seqs, k: int, w: int):

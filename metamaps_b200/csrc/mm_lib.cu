@@ -26,6 +26,13 @@ struct mm_ctx {
   SketchOut sketchOut;
   double last_ms = 0;
   int64_t last_launches = 0;
+  // grow-only scratch of the mapq / EM / fetch entry points (cudaMalloc + cudaFree per call would cost more than the kernels)
+  struct {
+    DevBuf<double> dId, dQ, dMq, dNl, dW, dWT, dF, dAcc, dRsum, dLog, dPost, dTot;
+    DevBuf<int32_t> dSh, dSk, dLen, dSt, dTax, dReadOf, dReadT, tmpA, tmpB;
+    DevBuf<int64_t> dOff, dBest;
+    DevBuf<uint32_t> dIota, dPerm, dTaxT;
+  } scr;
   // NCCL (multi-GPU EM), bound at run time
   void* ncclLib = nullptr; void* comm = nullptr; int nRanks = 1, rank = 0;
   mm_ctx() : pr(rt), sk(rt, pr), mp(rt, pr, sk) {}
@@ -79,6 +86,7 @@ int mm_ctx_create(int device, mm_ctx** out) {
   cudaDeviceProp prop; MM_CUDA(cudaGetDeviceProperties(&prop, device));
   c->rt.sm_count = prop.multiProcessorCount;
   MM_CUDA(cudaStreamCreateWithFlags(&c->rt.stream, cudaStreamNonBlocking));
+  MM_CUDA(cudaStreamCreateWithFlags(&c->rt.side, cudaStreamNonBlocking));
 #endif
   *out = c;
   MM_CATCH
@@ -91,9 +99,10 @@ void mm_ctx_destroy(mm_ctx* c) {
 #endif
   mm_comm_destroy(c);
 #ifndef MM_HOST_EMU
-  cudaStream_t s = c->rt.stream;
+  cudaStream_t s = c->rt.stream, s2 = c->rt.side;
+  cudaStreamSynchronize(s2);
   delete c;
-  cudaStreamDestroy(s);
+  cudaStreamDestroy(s); cudaStreamDestroy(s2);
 #else
   delete c;
 #endif
@@ -106,7 +115,7 @@ int mm_ctx_last_timing(mm_ctx* c, double* total_ms, int64_t* n_launches) {
 }
 int mm_ctx_last_map_stats(mm_ctx* c, double* stage_ms, int64_t* counters) {
   if (!c) return MM_EINVAL;
-  for (int i = 0; i < 8; i++) { if (stage_ms) stage_ms[i] = c->mp.st.ms[i]; if (counters) counters[i] = c->mp.st.counters[i]; }
+  for (int i = 0; i < 16; i++) { if (stage_ms) stage_ms[i] = c->mp.st.ms[i]; if (counters) counters[i] = c->mp.st.counters[i]; }
   return MM_OK;
 }
 
@@ -257,7 +266,7 @@ int mm_map_fetch_reads(mm_ctx* c, int32_t* sketch_size, int32_t* minimum_hits, i
   begin_call(c);
   if (sketch_size) d2h(c->rt, sketch_size, m.sOf.p, sizeof(int32_t) * (size_t)m.n_reads);
   if (minimum_hits && m.n_reads) {
-    DevBuf<int32_t> t; t.ensure((size_t)m.n_reads);
+    auto& t = c->scr.tmpA; t.ensure((size_t)m.n_reads);
     foreach(c->rt, m.n_reads, MinHitsOfFn{m.sOf.p, m.dMinHits.p, t.p});
     d2h(c->rt, minimum_hits, t.p, sizeof(int32_t) * (size_t)m.n_reads);
   }
@@ -315,7 +324,7 @@ int mm_mapq_batch(mm_ctx* c, const double* identity, const int32_t* shared, cons
   if (!c || !read_off || n_reads < 0) throw Error(MM_EINVAL, "mm_mapq_batch: bad arguments");
   begin_call(c);
   int64_t M = read_off[n_reads];
-  DevBuf<double> dId, dQ; DevBuf<int32_t> dSh, dSk, dLen, dSt; DevBuf<int64_t> dOff;
+  auto& dId = c->scr.dId; auto& dQ = c->scr.dQ; auto& dSh = c->scr.dSh; auto& dSk = c->scr.dSk; auto& dLen = c->scr.dLen; auto& dSt = c->scr.dSt; auto& dOff = c->scr.dOff;
   dId.ensure((size_t)M); dQ.ensure((size_t)M); dSh.ensure((size_t)M); dSk.ensure((size_t)M);
   dLen.ensure((size_t)n_reads); dSt.ensure((size_t)n_reads); dOff.ensure((size_t)n_reads + 1);
   h2d(c->rt, dId.p, identity, 8 * (size_t)M); h2d(c->rt, dSh.p, shared, 4 * (size_t)M); h2d(c->rt, dSk.p, sketch, 4 * (size_t)M);
@@ -395,8 +404,10 @@ int mm_em_run(mm_ctx* c, const int32_t* taxon, const double* mapq, const double*
   Runtime& rt = c->rt; Prims& pr = c->pr;
   int64_t M = read_off[n_reads];
   if (M >= ((int64_t)1 << 32)) throw Error(MM_ERANGE, "more than 2^32 mappings on one rank: partition the reads");
-  DevBuf<int32_t> dTax, dReadOf, dReadT; DevBuf<double> dMq, dNl, dW, dWT, dF, dAcc, dRsum, dLog, dPost, dTot; DevBuf<int64_t> dOff, dBest;
-  DevBuf<uint32_t> dIota, dPerm, dTaxKey, dTaxT;
+  auto& dTax = c->scr.dTax; auto& dReadOf = c->scr.dReadOf; auto& dReadT = c->scr.dReadT; auto& dMq = c->scr.dMq; auto& dNl = c->scr.dNl;
+  auto& dW = c->scr.dW; auto& dWT = c->scr.dWT; auto& dF = c->scr.dF; auto& dAcc = c->scr.dAcc; auto& dRsum = c->scr.dRsum; auto& dLog = c->scr.dLog;
+  auto& dPost = c->scr.dPost; auto& dTot = c->scr.dTot; auto& dOff = c->scr.dOff; auto& dBest = c->scr.dBest;
+  auto& dIota = c->scr.dIota; auto& dPerm = c->scr.dPerm; auto& dTaxT = c->scr.dTaxT;
   dTax.ensure((size_t)M); dReadOf.ensure((size_t)M); dReadT.ensure((size_t)M); dMq.ensure((size_t)M); dNl.ensure((size_t)M);
   dW.ensure((size_t)M); dWT.ensure((size_t)M); dIota.ensure((size_t)M); dPerm.ensure((size_t)M); dTaxT.ensure((size_t)M);
   dF.ensure((size_t)T); dAcc.ensure((size_t)T + 1); dRsum.ensure((size_t)n_reads + 1); dLog.ensure((size_t)n_reads + 1);

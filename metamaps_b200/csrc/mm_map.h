@@ -24,6 +24,9 @@
 namespace mm {
 
 static const uint32_t CODE_MATCH = 0x80000000u, CODE_DUP = 0x40000000u, CODE_IDX = 0x3FFFFFFFu;
+// K5b state of one candidate: s+1 gap counters (cntBytes each) + s match bits + one spare word, in 32-bit words
+MM_HD int32_t sweep_cnt_words(int32_t s, int32_t cntBytes) { return ((s + 1) * cntBytes + 3) / 4; }
+MM_HD int32_t sweep_state_words(int32_t s, int32_t cntBytes) { return sweep_cnt_words(s, cntBytes) + (s + 31) / 32 + 1; }
 
 // ---------------------------------------------------------------------------------------------- K3
 struct ReadKeyFn {          // entry e of the batch sketch -> (read << 32 | hash)
@@ -38,9 +41,12 @@ struct HeadFlagFn {
   MM_HD void operator()(int64_t e) const { head[e] = (e < n && (e == 0 || ldg(key + e) != ldg(key + e - 1))) ? 1 : 0; }
 };
 struct UniqueScatterFn {    // std::unique keeps the first element of every equal-hash run (computeMap.hpp:295)
-  const uint64_t* key; const uint32_t* ws; const int32_t* head; const int64_t* idx; uint32_t* qHash; uint8_t* qStrand;
+  const uint64_t* key; const uint32_t* ws; const int32_t* head; const int64_t* idx; uint32_t* qHash; uint8_t* qStrand; int32_t* qRead;
   MM_HD void operator()(int64_t e) const {
-    if (ldg(head + e)) { int64_t d = ldg(idx + e); qHash[d] = (uint32_t)ldg(key + e); qStrand[d] = (uint8_t)(ldg(ws + e) & 1u); }
+    if (ldg(head + e)) {
+      int64_t d = ldg(idx + e); uint64_t k = ldg(key + e);
+      qHash[d] = (uint32_t)k; qStrand[d] = (uint8_t)(ldg(ws + e) & 1u); qRead[d] = (int32_t)(k >> 32);
+    }
   }
 };
 struct ReadSketchOffFn {    // sorting is within reads, so read r still owns [seqOff[r], seqOff[r+1])
@@ -94,13 +100,21 @@ struct ProbeFn {            // computeMap.hpp:307-321
     else hitCnt[i] = 0;
   }
 };
+// Hits are written as ONE 64-bit sort key  read << (seqBits+wsBits) | seqId << wsBits | (wpos<<1|strand), so that a
+// single radix sort over the used bits orders them per read by (seqId, wpos, strand) -- the order std::sort gives
+// the reference (computeMap.hpp:352).
+struct HitKeyLayout { int seqBits, wsBits; };
 struct GatherHitsFn {
-  const int32_t* hitCnt; const int64_t* hitStart; const int64_t* hitOff; const uint64_t* posKey; uint64_t* hits;
+  const int32_t* hitCnt; const int64_t* hitStart; const int64_t* hitOff; const int32_t* qRead; const uint64_t* posKey; uint64_t* hits; HitKeyLayout lay;
   MM_HD void operator()(int64_t i) const {
     int32_t c = ldg(hitCnt + i);
     if (!c) return;
     int64_t s = ldg(hitStart + i), d = ldg(hitOff + i);
-    for (int32_t j = 0; j < c; j++) hits[d + j] = ldg(posKey + s + j);
+    uint64_t hi = (uint64_t)ldg(qRead + i) << (lay.seqBits + lay.wsBits);
+    for (int32_t j = 0; j < c; j++) {
+      uint64_t pk = ldg(posKey + s + j);
+      hits[d + j] = hi | ((pk >> 32) << lay.wsBits) | (pk & 0xFFFFFFFFull);
+    }
   }
 };
 struct ReadHitOffFn {
@@ -108,37 +122,131 @@ struct ReadHitOffFn {
   MM_HD void operator()(int64_t r) const { readHitOff[r] = ldg(hitOff + ldg(qOff + r)); }
 };
 
-// computeL1CandidateRegions (computeMap.hpp:346-386) over the read's sorted hits.  pass 0 counts, pass 1 writes.
-struct CandidateFn {
-  const uint64_t* hits; const int64_t* readHitOff; const int32_t* sOf; const int32_t* readLen;
-  const int32_t* minHitsTab; int pass;
-  int32_t* candCnt; const int64_t* candOff;
-  int32_t* cRead; int32_t* cSeq; int32_t* cStart; int32_t* cEnd;
-  MM_HD void operator()(int64_t r) const {
-    int32_t s = ldg(sOf + r);
-    int32_t n = 0;
-    if (s > 0) {
-      int64_t b = ldg(readHitOff + r), e = ldg(readHitOff + r + 1);
-      int32_t mh = ldg(minHitsTab + s); if (mh < 1) mh = 1;
-      int32_t len = ldg(readLen + r);
-      int64_t out = pass ? ldg(candOff + r) : 0;
-      int32_t lastSeq = -1, lastStart = 0, lastEnd = 0;
-      for (int64_t i = b; i + mh - 1 < e; i++) {
-        uint64_t ka = ldg(hits + i), kb = ldg(hits + i + mh - 1);
-        int32_t sa = (int32_t)(ka >> 32), sb = (int32_t)(kb >> 32);
-        int32_t wa = (int32_t)((uint32_t)ka >> 1), wb = (int32_t)((uint32_t)kb >> 1);
-        if (sa == sb && wb - wa < len) {
-          int32_t st = wb - len + 1; if (st < 0) st = 0;
-          if (n > 0 && sa == lastSeq && lastEnd >= st) { if (wa > lastEnd) lastEnd = wa; }
-          else {
-            if (n > 0 && pass) { cRead[out + n - 1] = (int32_t)r; cSeq[out + n - 1] = lastSeq; cStart[out + n - 1] = lastStart; cEnd[out + n - 1] = lastEnd; }
-            n++; lastSeq = sa; lastStart = st; lastEnd = wa;
-          }
+#ifndef MM_HOST_EMU
+// Device fast path of the gather: one CTA per read.  Pass 1 counts the read's seed hits per contig in shared memory
+// (16-bit counters, contig id folded into HF bins); pass 2 keeps only the hits on contigs that collected at least
+// minimumHits of them -- fewer can never satisfy computeMap.hpp:358-362, so dropping them changes nothing downstream
+// but shrinks the sort by the spurious 32-bit-hash collisions (7000 -> ~900 hits per read on the 12 Gbp DB).
+// Survivors are appended as composite sort keys at a global cursor; the radix sort restores read order.
+__global__ void __launch_bounds__(256) l1_filter_gather_kernel(const int32_t* hitCnt, const int64_t* hitStart, const int64_t* qOff, const int32_t* sOf,
+                                                               const int32_t* minHitsTab, const uint64_t* posKey, HitKeyLayout lay, int32_t n_reads,
+                                                               uint32_t binMask, unsigned long long* cursor, uint64_t* hitsOut, int32_t* keptPerRead) {
+  extern __shared__ uint32_t bins[];            // (binMask+1)/2 words, two 16-bit counters per word
+  __shared__ unsigned int smTotal, smPos; __shared__ unsigned long long smBase;
+  for (int32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+    const int32_t s = sOf[r];
+    const int64_t q0 = qOff[r], q1 = qOff[r + 1];
+    if (s == 0 || q1 <= q0) { if (threadIdx.x == 0) keptPerRead[r] = 0; continue; }
+    int32_t mh = minHitsTab[s]; if (mh < 1) mh = 1;
+    for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) bins[i] = 0;
+    if (threadIdx.x == 0) { smTotal = 0; smPos = 0; }
+    __syncthreads();
+    bool saturated = false;
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+      const int32_t c = hitCnt[q]; const int64_t st = hitStart[q];
+      for (int32_t j = 0; j < c; j++) {
+        const uint32_t b = (uint32_t)(__ldg(posKey + st + j) >> 32) & binMask;
+        const uint32_t old = atomicAdd(&bins[b >> 1], (b & 1u) ? 0x10000u : 1u);
+        if ((((b & 1u) ? (old >> 16) : (old & 0xFFFFu)) & 0xFFFFu) >= 0xFFF0u) saturated = true;
+      }
+    }
+    const int anySat = __syncthreads_or(saturated ? 1 : 0);      // absurdly deep pile-up: keep everything for this read
+    unsigned int local = 0;
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+      const int32_t c = hitCnt[q]; const int64_t st = hitStart[q];
+      for (int32_t j = 0; j < c; j++) {
+        const uint32_t b = (uint32_t)(__ldg(posKey + st + j) >> 32) & binMask;
+        const uint32_t v = (bins[b >> 1] >> ((b & 1u) * 16)) & 0xFFFFu;
+        local += (anySat || v >= (uint32_t)mh) ? 1u : 0u;
+      }
+    }
+    if (local) atomicAdd(&smTotal, local);
+    __syncthreads();
+    if (threadIdx.x == 0) { smBase = atomicAdd(cursor, (unsigned long long)smTotal); keptPerRead[r] = (int32_t)smTotal; }
+    __syncthreads();
+    const uint64_t hi = (uint64_t)r << (lay.seqBits + lay.wsBits);
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+      const int32_t c = hitCnt[q]; const int64_t st = hitStart[q];
+      for (int32_t j = 0; j < c; j++) {
+        const uint64_t pk = __ldg(posKey + st + j);
+        const uint32_t b = (uint32_t)(pk >> 32) & binMask;
+        const uint32_t v = (bins[b >> 1] >> ((b & 1u) * 16)) & 0xFFFFu;
+        if (anySat || v >= (uint32_t)mh) {
+          const unsigned int p = atomicAdd(&smPos, 1u);
+          hitsOut[smBase + p] = hi | ((pk >> 32) << lay.wsBits) | (pk & 0xFFFFFFFFull);
         }
       }
-      if (n > 0 && pass) { cRead[out + n - 1] = (int32_t)r; cSeq[out + n - 1] = lastSeq; cStart[out + n - 1] = lastStart; cEnd[out + n - 1] = lastEnd; }
     }
-    if (!pass) candCnt[r] = n;
+    __syncthreads();
+  }
+}
+#endif
+
+// computeL1CandidateRegions (computeMap.hpp:346-386), one item per sorted hit:
+//   hit i opens a candidate iff hits i and i+minimumHits-1 lie on the same contig less than a read length apart;
+//   consecutive such candidates are merged while prev.end >= start (ends are non-decreasing, so "prev" is simply
+//   the previous flagged hit).
+struct HitDecode {
+  HitKeyLayout lay;
+  MM_HD int32_t read(uint64_t k) const { return (int32_t)(k >> (lay.seqBits + lay.wsBits)); }
+  MM_HD int32_t seq(uint64_t k) const { return (int32_t)((k >> lay.wsBits) & ((1ull << lay.seqBits) - 1)); }
+  MM_HD int32_t wpos(uint64_t k) const { return (int32_t)((k & ((1ull << lay.wsBits) - 1)) >> 1); }
+};
+struct HitFlagFn {
+  const uint64_t* hits; const int64_t* readHitOff; const int32_t* sOf; const int32_t* readLen; const int32_t* minHitsTab; HitDecode dec;
+  int32_t* flag; int64_t n;
+  MM_HD void operator()(int64_t i) const {
+    int32_t f = 0;
+    if (i < n) {
+      uint64_t ka = ldg(hits + i);
+      int32_t r = dec.read(ka);
+      int32_t mh = ldg(minHitsTab + ldg(sOf + r)); if (mh < 1) mh = 1;
+      int64_t j = i + mh - 1;
+      if (j < ldg(readHitOff + r + 1)) {
+        uint64_t kb = ldg(hits + j);
+        if (dec.seq(ka) == dec.seq(kb) && dec.wpos(kb) - dec.wpos(ka) < ldg(readLen + r)) f = 1;
+      }
+    }
+    flag[i] = f;
+  }
+};
+struct HitCompactFn {
+  const int32_t* flag; const int64_t* fidx; int64_t* flagged;
+  MM_HD void operator()(int64_t i) const { if (ldg(flag + i)) flagged[ldg(fidx + i)] = i; }
+};
+MM_HD void hit_candidate(const uint64_t* hits, const int32_t* sOf, const int32_t* readLen, const int32_t* minHitsTab, const HitDecode& dec, int64_t i,
+                         int32_t* r, int32_t* seq, int32_t* start, int32_t* end) {
+  uint64_t ka = ldg(hits + i);
+  *r = dec.read(ka); *seq = dec.seq(ka); *end = dec.wpos(ka);
+  int32_t mh = ldg(minHitsTab + ldg(sOf + *r)); if (mh < 1) mh = 1;
+  int32_t st = dec.wpos(ldg(hits + i + mh - 1)) - ldg(readLen + *r) + 1;
+  *start = st < 0 ? 0 : st;
+}
+struct LocusHeadFn {
+  const uint64_t* hits; const int64_t* flagged; const int32_t* sOf; const int32_t* readLen; const int32_t* minHitsTab; HitDecode dec;
+  int32_t* head; int64_t n;
+  MM_HD void operator()(int64_t f) const {
+    int32_t h = 0;
+    if (f < n) {
+      int32_t r, sq, st, en; hit_candidate(hits, sOf, readLen, minHitsTab, dec, ldg(flagged + f), &r, &sq, &st, &en);
+      h = 1;
+      if (f > 0) {
+        int32_t r2, sq2, st2, en2; hit_candidate(hits, sOf, readLen, minHitsTab, dec, ldg(flagged + f - 1), &r2, &sq2, &st2, &en2);
+        if (r2 == r && sq2 == sq && en2 >= st) h = 0;
+      }
+    }
+    head[f] = h;
+  }
+};
+struct LocusWriteFn {
+  const uint64_t* hits; const int64_t* flagged; const int32_t* sOf; const int32_t* readLen; const int32_t* minHitsTab; HitDecode dec;
+  const int32_t* head; const int64_t* lidx; int64_t n;
+  int32_t* cRead; int32_t* cSeq; int32_t* cStart; int32_t* cEnd; int32_t* candCnt;
+  MM_HD void operator()(int64_t f) const {
+    int32_t r, sq, st, en; hit_candidate(hits, sOf, readLen, minHitsTab, dec, ldg(flagged + f), &r, &sq, &st, &en);
+    int64_t l = ldg(lidx + f) + (ldg(head + f) ? 0 : -1);      // lidx = exclusive scan of head
+    if (ldg(head + f)) { cRead[l] = r; cSeq[l] = sq; cStart[l] = st; atomic_add(candCnt + r, 1); }
+    if (f + 1 == n || ldg(head + f + 1)) cEnd[l] = en;          // last flagged hit of the group carries the largest end
   }
 };
 
@@ -169,7 +277,7 @@ struct StWordsFn {
   MM_HD void operator()(int64_t c) const {
     if (c >= n) { stWords[c] = 0; return; }
     int32_t s = ldg(sOf + ldg(cRead + c));
-    stWords[c] = ((s + 1) * cntBytes + 3) / 4 + (s + 31) / 32;
+    stWords[c] = sweep_state_words(s, cntBytes);
   }
 };
 
@@ -193,101 +301,196 @@ struct L2ClassifyFn {
   }
 };
 
+#ifndef MM_HOST_EMU
+// Device fast path of phase A: one CTA per candidate; the read sketch is staged in shared memory once and the span's
+// reference minimizers are classified with coalesced loads / stores (same codes as L2ClassifyFn).
+__global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a) {
+  extern __shared__ uint32_t smq[];
+  for (int64_t ci = blockIdx.x; ci < a.nCand; ci += gridDim.x) {
+    const int64_t c = a.cand0 + ci;
+    const int32_t r = a.cRead[c], s = a.sOf[r];
+    const uint32_t* q = a.qHash + a.qOff[r];
+    for (int32_t i = threadIdx.x; i < s; i += blockDim.x) smq[i] = __ldg(q + i);
+    __syncthreads();
+    const int64_t b0 = a.beg0[c];
+    const int64_t e0 = a.evOff[c] - a.evBase; const int32_t n = (int32_t)(a.evOff[c + 1] - a.evOff[c]);
+    for (int32_t t = threadIdx.x; t < n; t += blockDim.x) {
+      const int64_t j = b0 + t;
+      const uint32_t h = __ldg(a.miHash + j);
+      int32_t lo = 0, hi = s;
+      while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (smq[m] < h) lo = m + 1; else hi = m; }
+      uint32_t code = (lo < s && smq[lo] == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
+      if ((__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u) code |= CODE_DUP;
+      a.ev[e0 + t] = make_uint2(code, __ldg(a.miWs + j));
+    }
+    __syncthreads();
+  }
+}
+#endif
+
 MM_HD uint64_t dup_links(const uint32_t* dupIdx, const uint64_t* dupLinks, int64_t n_dup, int64_t j) {
   int64_t p = lower_bound_idx(dupIdx, n_dup, (uint32_t)j);
   return (p < n_dup && ldg(dupIdx + p) == (uint32_t)j) ? ldg(dupLinks + p) : 0ull;
 }
 
 // phase B: the evaluate-then-advance loop of computeL2MappedRegions (computeMap.hpp:482-533).
-// CntT = uint16_t when every span of the pass has fewer than 65535 minimizers (a gap count can never
-// exceed the span size), uint32_t otherwise.
-template <class CntT>
-struct L2SweepFn {
-  const uint2* ev; const int64_t* evOff; int64_t evBase; uint32_t* state; const int64_t* stOff; int64_t stBase; int64_t cand0;
+// The gap counters cnt[] and the match bits mb[] live wherever the caller puts them:
+//   * L2SweepFn<uint16_t|uint32_t>  -- global memory (any sketch size; also what the host-emulation tests run);
+//   * l2_sweep_smem_kernel          -- shared memory, 8-bit counters (device fast path; a counter that would
+//                                      pass 255 sends the candidate back to the global-memory functor).
+// Both call l2_sweep_one, so the logic that is checked against the oracle on the CPU is the logic the GPU runs.
+struct L2SweepArgs {
+  const uint2* ev; const int64_t* evOff; int64_t evBase; int64_t cand0;
   const int64_t* beg0; const int64_t* fe; const int64_t* le; const int32_t* cRead; const int32_t* sOf; const int32_t* readLen;
   const uint32_t* dupIdx; const uint64_t* dupLinks; int64_t n_dup; int k, w;
   int32_t* oShared; int32_t* oPos; int32_t* oValid; int64_t* oOptS; int64_t* oOptE; int32_t* oIstar;
+};
 
-  struct St { CntT* cnt; uint32_t* mb; int32_t s, istar, C, shared; };
-  MM_HD static void ins(St& z, uint32_t code) {
-    if (code & CODE_MATCH) {
-      int32_t i = (int32_t)(code & CODE_IDX);
-      z.mb[(i - 1) >> 5] |= 1u << ((i - 1) & 31);
-      if (i <= z.istar) z.shared++;
-    } else {
-      int32_t g = (int32_t)(code & CODE_IDX);
-      if (g >= z.s) return;                   // above the largest query hash: can never enter the bottom-s
-      z.cnt[g]++;
-      if (g < z.istar) {
-        z.C++;
-        if (z.istar + z.C > z.s) {            // q_istar drops out of the bottom-s
-          z.C -= z.cnt[z.istar - 1];
-          if ((z.mb[(z.istar - 1) >> 5] >> ((z.istar - 1) & 31)) & 1u) z.shared--;
-          z.istar--;
-        }
-      }
-    }
+// Branch-free updates: every lane of a warp runs the same instruction stream whatever the event is.  cnt[] has
+// s+1 counters; slot s ("above the largest query hash", never consulted) doubles as the dummy target of events
+// that do not move a counter.  mb[] has one spare word after the s match bits for the same purpose.
+template <class CntT, bool CHECK_OVF>
+struct SweepState {
+  CntT* cnt; uint32_t* mb; int32_t s, istar, C, shared, junkBit; bool ovf;
+  MM_HD uint32_t bit(int32_t i0) const { return (mb[i0 >> 5] >> (i0 & 31)) & 1u; }      // i0 = 0-based query index
+  MM_HD void ins(uint32_t code) {
+    const int32_t isM = (int32_t)(code >> 31), idx = (int32_t)(code & CODE_IDX);
+    const bool gv = !isM && idx < s;                       // a gap counter really moves
+    const int32_t gi = gv ? idx : s;
+    const CntT v = cnt[gi];
+    if (CHECK_OVF) ovf = ovf || (gv && v == (CntT)~(CntT)0);
+    cnt[gi] = (CntT)(v + 1);
+    const int32_t below = (gv && idx < istar) ? 1 : 0;
+    C += below;
+    const int32_t im1 = istar > 0 ? istar - 1 : 0;
+    const int32_t cprev = (int32_t)cnt[im1];               // after the increment above (g may be istar-1)
+    const int32_t mprev = (int32_t)bit(im1);
+    const int32_t dec = (below && istar + C > s) ? 1 : 0;  // q_istar drops out of the bottom-s
+    C -= dec ? cprev : 0;
+    shared -= dec & mprev;
+    istar -= dec;
+    const int32_t mi = isM ? idx - 1 : junkBit;
+    mb[mi >> 5] |= (uint32_t)isM << (mi & 31);
+    shared += (isM && idx <= istar) ? 1 : 0;
   }
-  MM_HD static void del(St& z, uint32_t code) {
-    if (code & CODE_MATCH) {
-      int32_t i = (int32_t)(code & CODE_IDX);
-      z.mb[(i - 1) >> 5] &= ~(1u << ((i - 1) & 31));
-      if (i <= z.istar) z.shared--;
-    } else {
-      int32_t g = (int32_t)(code & CODE_IDX);
-      if (g >= z.s) return;
-      z.cnt[g]--;
-      if (g < z.istar) z.C--;
-      if (z.istar < z.s && z.istar + 1 + z.C + (int32_t)z.cnt[z.istar] <= z.s) {   // q_{istar+1} enters
-        z.C += z.cnt[z.istar];
-        z.istar++;
-        if ((z.mb[(z.istar - 1) >> 5] >> ((z.istar - 1) & 31)) & 1u) z.shared++;
-      }
-    }
-  }
-  MM_HD void operator()(int64_t ci) const {
-    int64_t c = cand0 + ci;
-    int32_t r = ldg(cRead + c); int32_t s = ldg(sOf + r); int32_t len = ldg(readLen + r);
-    int64_t b0 = ldg(beg0 + c);
-    const uint2* e = ev + (ldg(evOff + c) - evBase) - b0;        // e[j] for index position j
-    uint32_t* stp = state + (ldg(stOff + c) - stBase);
-    St z; z.cnt = (CntT*)stp; z.mb = stp + ((s + 1) * (int32_t)sizeof(CntT) + 3) / 4; z.s = s; z.istar = s; z.C = 0; z.shared = 0;
-    int64_t beg = b0, end = ldg(fe + c), last = ldg(le + c);
-    int32_t cmw = len - (w - 1) - (k - 1);
-    // slidemap.insert_ref(sw_beg, sw_end) (computeMap.hpp:488); a hash already present is only revised
-    for (int64_t j = beg; j < end; j++) {
-      uint32_t code = e[j].x;
-      if (code & CODE_DUP) { uint64_t l = dup_links(dupIdx, dupLinks, n_dup, j); uint32_t pd = (uint32_t)(l >> 32); if (pd && j - (int64_t)pd >= beg) continue; }
-      ins(z, code);
-    }
-    int32_t best = 0, bpos = 0, lpos = 0, valid = 0, bistar = s; int64_t optS = 0, optE = 0;
-    int64_t pb = beg, pe = end;
-    int32_t sw_pos = (int32_t)(e[beg].y >> 1);
-    while (end < last) {
-      if (pb != beg) {                                   // delete_ref(prev_beg) (slidingMap.hpp:170-219)
-        uint32_t code = e[pb].x; bool noop = false;
-        if (code & CODE_DUP) { uint64_t l = dup_links(dupIdx, dupLinks, n_dup, pb); uint32_t nd = (uint32_t)l; if (nd && pb + (int64_t)nd < pe) noop = true; }
-        if (!noop) del(z, code);
-      }
-      if (pe != end) {                                   // insert_ref(prev_end) (slidingMap.hpp:139-164)
-        uint32_t code = e[pe].x; bool noop = false;
-        if (code & CODE_DUP) { uint64_t l = dup_links(dupIdx, dupLinks, n_dup, pe); uint32_t pd = (uint32_t)(l >> 32); if (pd && pe - (int64_t)pd >= beg) noop = true; }
-        if (!noop) ins(z, code);
-      }
-      int32_t wb = (int32_t)(e[beg].y >> 1);
-      if (z.shared > best) { best = z.shared; optS = beg; optE = end; bpos = lpos = wb; valid = 1; bistar = z.istar; }
-      else if (z.shared == best) lpos = wb;
-      pb = beg; pe = end;
-      int32_t nb = (int32_t)(e[beg + 1].y >> 1) - sw_pos;            // MIIteratorL2::next (MIIteratorL2.hpp:74-96)
-      int32_t ne = (int32_t)(e[end].y >> 1) - (sw_pos + cmw - 1);
-      int32_t adv = nb < ne ? nb : ne;
-      sw_pos += adv;
-      if (adv == nb) beg++;
-      if (adv == ne) end++;
-    }
-    oShared[c] = best; oPos[c] = (bpos + lpos) / 2; oValid[c] = valid; oOptS[c] = optS; oOptE[c] = optE; oIstar[c] = bistar;
+  MM_HD void del(uint32_t code) {
+    const int32_t isM = (int32_t)(code >> 31), idx = (int32_t)(code & CODE_IDX);
+    const bool gv = !isM && idx < s;
+    const int32_t gi = gv ? idx : s;
+    cnt[gi] = (CntT)(cnt[gi] - 1);
+    C -= (gv && idx < istar) ? 1 : 0;
+    const int32_t ccur = (int32_t)cnt[istar];              // istar <= s: always a valid slot
+    const int32_t adv = (gv && istar < s && istar + 1 + C + ccur <= s) ? 1 : 0;   // q_{istar+1} enters
+    C += adv ? ccur : 0;
+    istar += adv;
+    const int32_t im1 = istar > 0 ? istar - 1 : 0;
+    shared += adv & (int32_t)bit(im1);
+    const int32_t mi = isM ? idx - 1 : junkBit;
+    mb[mi >> 5] &= ~((uint32_t)isM << (mi & 31));
+    shared -= (isM && idx <= istar) ? 1 : 0;
   }
 };
+
+// one candidate; cnt/mb must be zero on entry.  Returns false if an 8-bit counter overflowed (CHECK_OVF only).
+template <class CntT, bool CHECK_OVF>
+MM_HD bool l2_sweep_one(const L2SweepArgs& a, int64_t c, CntT* cnt, uint32_t* mb) {
+  const int32_t r = ldg(a.cRead + c), s = ldg(a.sOf + r), len = ldg(a.readLen + r);
+  const int64_t b0 = ldg(a.beg0 + c);
+  const uint2* e = a.ev + (ldg(a.evOff + c) - a.evBase);             // e[j]: index position b0 + j
+  SweepState<CntT, CHECK_OVF> z; z.cnt = cnt; z.mb = mb; z.s = s; z.istar = s; z.C = 0; z.shared = 0; z.ovf = false;
+  z.junkBit = 32 * ((s + 31) / 32);
+  const uint32_t NOP = (uint32_t)s;                                  // "gap s": touches only the dummy slots
+  int32_t beg = 0, end = (int32_t)(ldg(a.fe + c) - b0); const int32_t last = (int32_t)(ldg(a.le + c) - b0);
+  const int32_t cmw = len - (a.w - 1) - (a.k - 1);
+  // slidemap.insert_ref(sw_beg, sw_end) (computeMap.hpp:488); a hash already present is only revised
+  for (int32_t j = 0; j < end; j++) {
+    uint32_t code = ldg(&e[j].x);
+    if (code & CODE_DUP) { uint64_t l = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0 + j); uint32_t pd = (uint32_t)(l >> 32); if (pd && j - (int64_t)pd >= 0) code = NOP; }
+    z.ins(code & ~CODE_DUP);
+  }
+  int32_t best = 0, bpos = 0, lpos = 0, valid = 0, bistar = s, optS = 0, optE = 0;
+  // the two event streams are kept one element ahead in registers
+  uint2 evBeg = ldg(e + beg), evBeg1 = ldg(e + beg + 1), evEnd = ldg(e + end), evEnd1 = ldg(e + end + 1);
+  int32_t sw_pos = (int32_t)(evBeg.y >> 1);
+  uint32_t delCode = NOP, insCode = NOP; int32_t oldEnd = end;
+  while (end < last) {
+    if (delCode & CODE_DUP) {                            // delete_ref(prev_beg) (slidingMap.hpp:170-219): a later copy keeps the hash
+      uint64_t l = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0 + beg - 1); uint32_t nd = (uint32_t)l;
+      delCode = (nd && (int64_t)(beg - 1) + nd < oldEnd) ? NOP : (delCode & ~CODE_DUP);
+    }
+    z.del(delCode);
+    if (insCode & CODE_DUP) {                            // insert_ref(prev_end) (slidingMap.hpp:139-164): an earlier copy already holds it
+      uint64_t l = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0 + end - 1); uint32_t pd = (uint32_t)(l >> 32);
+      insCode = (pd && (int64_t)(end - 1) - pd >= beg) ? NOP : (insCode & ~CODE_DUP);
+    }
+    z.ins(insCode);
+    if (CHECK_OVF && z.ovf) return false;
+    const int32_t wb = (int32_t)(evBeg.y >> 1);
+    const bool better = z.shared > best;
+    lpos = (z.shared >= best) ? wb : lpos;
+    if (better) { best = z.shared; optS = beg; optE = end; bpos = wb; valid = 1; bistar = z.istar; }
+    const int32_t nb = (int32_t)(evBeg1.y >> 1) - sw_pos;            // MIIteratorL2::next (MIIteratorL2.hpp:74-96)
+    const int32_t ne = (int32_t)(evEnd.y >> 1) - (sw_pos + cmw - 1);
+    const int32_t adv = nb < ne ? nb : ne;
+    sw_pos += adv;
+    oldEnd = end;
+    delCode = NOP; insCode = NOP;
+    if (adv == nb) { delCode = evBeg.x; evBeg = evBeg1; beg++; evBeg1 = ldg(e + beg + 1); }
+    if (adv == ne) { insCode = evEnd.x; evEnd = evEnd1; end++; evEnd1 = ldg(e + end + 1); }
+  }
+  a.oShared[c] = best; a.oPos[c] = (bpos + lpos) / 2; a.oValid[c] = valid; a.oOptS[c] = b0 + optS; a.oOptE[c] = b0 + optE; a.oIstar[c] = bistar;
+  return true;
+}
+
+// global-memory state; item ci -> candidate cand0 + (list ? list[ci] : ci)
+template <class CntT>
+struct L2SweepFn {
+  L2SweepArgs a; uint32_t* state; const int64_t* stOff; int64_t stBase; const int32_t* list;
+  MM_HD void operator()(int64_t ci) const {
+    int64_t c = a.cand0 + (list ? (int64_t)ldg(list + ci) : ci);
+    int32_t s = ldg(a.sOf + ldg(a.cRead + c));
+    uint32_t* stp = state + (ldg(stOff + c) - stBase);
+    l2_sweep_one<CntT, false>(a, c, (CntT*)stp, stp + sweep_cnt_words(s, (int32_t)sizeof(CntT)));
+  }
+};
+struct SweepKeyFn {     // sort key: descending sketch size (similar work inside a warp, longest first)
+  const int32_t* cRead; const int32_t* sOf; int64_t cand0; uint32_t* key; uint32_t* val;
+  MM_HD void operator()(int64_t ci) const { key[ci] = 0xFFFFFFFFu - (uint32_t)ldg(sOf + ldg(cRead + cand0 + ci)); val[ci] = (uint32_t)ci; }
+};
+
+#ifndef MM_HOST_EMU
+// Shared-memory fast path.  Each WARP owns a fixed slice of the CTA's shared memory and pulls "tiles" from a global
+// counter: a tile = up to 32 consecutive candidates (in descending-sketch-size order) whose gap counters + match bits
+// fit the slice; lane t sweeps candidate order[tileStart+t].  No block-level barrier: a slow candidate only delays its
+// own warp.  Per-candidate word counts are odd, so the lanes' regions start on different banks.
+static const int SWEEP_WARPS = 6;                    // warps per CTA (1 CTA per SM)
+static const int SWEEP_SLICE_WORDS = 8704;           // 34 KB per warp -> 204 KB per CTA
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) l2_sweep_smem_kernel(L2SweepArgs a, const uint32_t* order, const int32_t* tileStart, int32_t nTiles,
+                                                                         const int32_t* localOff, unsigned int* tileCounter, int32_t* redo,
+                                                                         unsigned long long* redoCount) {
+  extern __shared__ uint32_t sm[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t* slice = sm + wid * SWEEP_SLICE_WORDS;
+  for (;;) {
+    int32_t tile = 0;
+    if (lane == 0) tile = (int32_t)atomicAdd(tileCounter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= nTiles) break;
+    const int32_t t0 = tileStart[tile], t1 = tileStart[tile + 1];
+    const int32_t i = t0 + lane;
+    if (i < t1) {
+      const int64_t c = a.cand0 + (int64_t)order[i];
+      const int32_t s = a.sOf[a.cRead[c]];
+      uint32_t* my = slice + localOff[i];
+      const int32_t cw = sweep_cnt_words(s, 1), words = sweep_state_words(s, 1);
+      for (int32_t j = 0; j < words; j++) my[j] = 0;
+      const bool ok = l2_sweep_one<uint8_t, true>(a, c, (uint8_t*)my, my + cw);
+      if (!ok) { unsigned long long slot = atomicAdd(redoCount, 1ull); redo[slot] = (int32_t)order[i]; }
+    }
+    __syncwarp();
+  }
+}
+#endif
 
 // phase C: strand vote of the optimal window (computeMap.hpp:431-438, slidingMap.hpp:232-254)
 struct L2StrandFn {
@@ -327,7 +530,7 @@ struct AcceptFn {           // computeMap.hpp:415 through the per-s threshold ta
   }
 };
 
-struct MapStats { double ms[8]; int64_t counters[8]; };
+struct MapStats { double ms[16]; int64_t counters[16]; };
 
 struct Mapper {
   Runtime& rt; Prims& pr; Sketcher& sk;
@@ -338,10 +541,13 @@ struct Mapper {
   int32_t n_reads = 0; int64_t n_q = 0, n_hits = 0, n_cand = 0;
   DevBuf<int32_t> readLen, sOf, head, hitCnt, candCnt, cRead, cSeq, cStart, cEnd, spanN, stWords;
   DevBuf<int32_t> oShared, oPos, oValid, oIstar, oVotes, oAccept, readMapped;
-  DevBuf<int64_t> qOff, idx, hitStart, hitOff, readHitOff, candOff, beg0, fe, le, evOff, stOff, oOptS, oOptE, scalar;
+  DevBuf<int64_t> qOff, idx, hitStart, hitOff, readHitOff, candOff, beg0, fe, le, evOff, stOff, oOptS, oOptE;
   DevBuf<uint64_t> key, key2, hits, hits2;
   DevBuf<uint32_t> ws2, qHash, state; DevBuf<uint8_t> qStrand; DevBuf<uint2> ev;
-  DevBuf<int32_t> ambig, ambigList; DevBuf<unsigned long long> ambigCount; int64_t n_ambig = 0;
+  DevBuf<int32_t> ambig, ambigList, red, swTile, swLocal, swRedo; DevBuf<unsigned long long> scal; int64_t n_ambig = 0;
+  DevBuf<uint32_t> swKey, swKey2, swVal, swOrder; int32_t maxSketch = 0;
+  DevBuf<int32_t> qRead, hflag, lhead, keptPerRead; DevBuf<int64_t> hfidx, flagged, lidx; int64_t n_hits_all = 0;
+  std::vector<uint32_t> hk; std::vector<int32_t> tileStartH, localOffH;
   std::vector<int32_t> h_effLen;
   MapStats st;
   int64_t evBudget = (int64_t)1 << 28;       // span elements classified per L2 pass (8 B each)
@@ -368,12 +574,12 @@ struct Mapper {
     n_reads = batch.n_seqs;
     // reads shorter than w, k or -m are skipped (computeMap.hpp:137): hide them from K1 by zeroing their length
     h_effLen.assign((size_t)n_reads, 0);
-    int64_t nShort = 0, basesOk = 0; int32_t maxLen = 0;
+    int64_t nShort = 0, basesOk = 0;
     std::vector<int32_t> saveLen = batch.h_len;
     for (int32_t i = 0; i < n_reads; i++) {
       int32_t L = batch.h_len[i];
       if (L < w || L < k || L < minReadLen) { nShort++; batch.h_len[i] = 0; }
-      else { h_effLen[i] = L; basesOk += L; if (L > maxLen) maxLen = L; }
+      else { h_effLen[i] = L; basesOk += L; }
     }
     readLen.ensure((size_t)n_reads + 1); h2d(rt, readLen.p, h_effLen.data(), sizeof(int32_t) * (size_t)n_reads);
     {
@@ -384,6 +590,7 @@ struct Mapper {
     // ---- K3: sort by (read, hash), unique
     int64_t nm = rs.n_total;
     sOf.ensure((size_t)n_reads + 1); qOff.ensure((size_t)n_reads + 2);
+    bool ambigPending = false;
     {
       StageTimer t(rt, &st.ms[1]);
       key.ensure((size_t)nm + 1); key2.ensure((size_t)nm + 1); ws2.ensure((size_t)nm + 1); head.ensure((size_t)nm + 2); idx.ensure((size_t)nm + 2);
@@ -393,52 +600,114 @@ struct Mapper {
       foreach(rt, nm + 1, HeadFlagFn{key2.p, head.p, nm});
       pr.exclusive_sum<int32_t, int64_t>(head.p, idx.p, nm + 1);
       d2h(rt, &n_q, idx.p + nm, sizeof(int64_t));
-      qHash.ensure((size_t)n_q + 1); qStrand.ensure((size_t)n_q + 1);
-      foreach(rt, nm, UniqueScatterFn{key2.p, ws2.p, head.p, idx.p, qHash.p, qStrand.p});
+      qHash.ensure((size_t)n_q + 1); qStrand.ensure((size_t)n_q + 1); qRead.ensure((size_t)n_q + 1);
+      foreach(rt, nm, UniqueScatterFn{key2.p, ws2.p, head.p, idx.p, qHash.p, qStrand.p, qRead.p});
       foreach(rt, (int64_t)n_reads + 1, ReadSketchOffFn{rs.seqOff.p, idx.p, qOff.p, sOf.p, n_reads});
       {   // duplicate hashes with both strands: settle the survivor like std::sort + std::unique would
-        ambig.ensure((size_t)n_reads + 1); ambigList.ensure(4096); ambigCount.ensure(1);
+        ambig.ensure((size_t)n_reads + 1); ambigList.ensure(4096); scal.ensure(4);
         dev_memset(rt, ambig.p, 0, sizeof(int32_t) * ((size_t)n_reads + 1));
-        dev_memset(rt, ambigCount.p, 0, sizeof(unsigned long long));
-        foreach(rt, nm, AmbigDetectFn{key2.p, ws2.p, head.p, ambig.p, ambigCount.p, ambigList.p, 4096});
-        unsigned long long na = 0; d2h(rt, &na, ambigCount.p, sizeof(na));
+        dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);
+        foreach(rt, nm, AmbigDetectFn{key2.p, ws2.p, head.p, ambig.p, scal.p, ambigList.p, 4096});
+        if (n_reads > 0) pr.reduce_max<int32_t>(sOf.p, (int32_t*)(scal.p + 1), n_reads);
+        unsigned long long hs[2] = {0, 0}; d2h(rt, hs, scal.p, sizeof(hs));
+        unsigned long long na = hs[0]; int32_t maxS = (int32_t)(hs[1] & 0xffffffffu);
         if (na > 4096) {
           ambigList.ensure((size_t)na);
           dev_memset(rt, ambig.p, 0, sizeof(int32_t) * ((size_t)n_reads + 1));
-          dev_memset(rt, ambigCount.p, 0, sizeof(unsigned long long));
-          foreach(rt, nm, AmbigDetectFn{key2.p, ws2.p, head.p, ambig.p, ambigCount.p, ambigList.p, (int64_t)na});
+          dev_memset(rt, scal.p, 0, sizeof(unsigned long long));
+          foreach(rt, nm, AmbigDetectFn{key2.p, ws2.p, head.p, ambig.p, scal.p, ambigList.p, (int64_t)na});
         }
         n_ambig = (int64_t)na;
-        if (na) foreach(rt, (int64_t)na, AmbigResolveFn{ambigList.p, rs.hash.p, rs.ws.p, rs.seqOff.p, key.p, qOff.p, qHash.p, qStrand.p}, 128, 16);
+        if (na) {
+          // The replay is one slow sequential thread per read and only the strand vote (K5c) needs its result:
+          // run it on the side stream, rejoin before K5c.
+#ifndef MM_HOST_EMU
+          MM_CUDA(cudaEventRecord(evFork(), rt.stream));
+          MM_CUDA(cudaStreamWaitEvent(rt.side, evFork(), 0));
+#endif
+          foreach(rt, (int64_t)na, AmbigResolveFn{ambigList.p, rs.hash.p, rs.ws.p, rs.seqOff.p, key.p, qOff.p, qHash.p, qStrand.p}, 128, 16, true);
+#ifndef MM_HOST_EMU
+          MM_CUDA(cudaEventRecord(evJoin(), rt.side));
+#endif
+          ambigPending = true;
+        }
+        // minimumHits[s] / acceptMin[s] tables up to the largest sketch of the batch (host, map_stats.hpp)
+        ensure_tables(k, pi, maxS);
+        maxSketch = maxS;
       }
-      // minimumHits[s] / acceptMin[s] tables up to the largest sketch of the batch (host, map_stats.hpp)
-      int32_t maxS = 0;
-      if (n_reads > 0) { DevBuf<int32_t> m; m.ensure(1); pr.reduce_max<int32_t>(sOf.p, m.p, n_reads); d2h(rt, &maxS, m.p, sizeof(int32_t)); }
-      ensure_tables(k, pi, maxS);
     }
     // ---- K4: probe, gather, sort, candidate regions
     candOff.ensure((size_t)n_reads + 2); candCnt.ensure((size_t)n_reads + 2);
+    HitKeyLayout lay; lay.seqBits = 1; lay.wsBits = 2;
+    { int64_t nc_ = ix.n_contigs > 1 ? ix.n_contigs : 2; while (((int64_t)1 << lay.seqBits) < nc_) lay.seqBits++;
+      int64_t ml = 2; for (int32_t l : ix.h_contigLen) if (l > ml) ml = l;
+      while (((int64_t)1 << (lay.wsBits - 1)) < ml) lay.wsBits++; }
+    int readBits = 1; while (((int64_t)1 << readBits) < (n_reads > 1 ? n_reads : 2)) readBits++;
+    if (readBits + lay.seqBits + lay.wsBits > 64) throw Error(-34, "read batch too large for the 64-bit hit key: map fewer reads per call");
+    HitDecode dec{lay};
     {
       StageTimer t(rt, &st.ms[2]);
       hitCnt.ensure((size_t)n_q + 2); hitStart.ensure((size_t)n_q + 2); hitOff.ensure((size_t)n_q + 2);
       foreach(rt, n_q + 1, ProbeFn{ix.table.p, ix.tableMask, qHash.p, ix.freqThreshold, hitCnt.p, hitStart.p, n_q});
       pr.exclusive_sum<int32_t, int64_t>(hitCnt.p, hitOff.p, n_q + 1);
       d2h(rt, &n_hits, hitOff.p + n_q, sizeof(int64_t));
-      hits.ensure((size_t)n_hits + 1); hits2.ensure((size_t)n_hits + 1); readHitOff.ensure((size_t)n_reads + 2);
-      foreach(rt, n_q, GatherHitsFn{hitCnt.p, hitStart.p, hitOff.p, ix.posKey.p, hits.p});
-      foreach(rt, (int64_t)n_reads + 1, ReadHitOffFn{qOff.p, hitOff.p, readHitOff.p});
-      pr.segmented_sort_keys<uint64_t>(hits.p, hits2.p, n_hits, n_reads, readHitOff.p);
-      CandidateFn cf{hits2.p, readHitOff.p, sOf.p, readLen.p, dMinHits.p, 0, candCnt.p, candOff.p, nullptr, nullptr, nullptr, nullptr};
-      foreach(rt, n_reads, cf);
-      dev_memset(rt, candCnt.p + n_reads, 0, sizeof(int32_t));
+      readHitOff.ensure((size_t)n_reads + 2);
+      n_hits_all = n_hits;
+#ifndef MM_HOST_EMU
+      if (n_hits > 0 && n_reads > 0) {
+        // filtered gather (see l1_filter_gather_kernel): survivors only, unordered by read
+        uint32_t binsN = 64; while (binsN < (uint32_t)ix.n_contigs && binsN < 32768u) binsN <<= 1;
+        hits.ensure((size_t)n_hits + 1); keptPerRead.ensure((size_t)n_reads + 2); scal.ensure(4);
+        dev_memset(rt, scal.p, 0, sizeof(unsigned long long));
+        static bool attrF = false;
+        if (!attrF) { MM_CUDA(cudaFuncSetAttribute(l1_filter_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); attrF = true; }
+        int grid = n_reads < rt.sm_count * 8 ? n_reads : rt.sm_count * 8;
+        l1_filter_gather_kernel<<<grid, 256, binsN * 2, rt.stream>>>(hitCnt.p, hitStart.p, qOff.p, sOf.p, dMinHits.p, ix.posKey.p, lay, n_reads, binsN - 1,
+                                                                     scal.p, hits.p, keptPerRead.p);
+        MM_CUDA(cudaGetLastError());
+        rt.launches++;
+        unsigned long long kept = 0; d2h(rt, &kept, scal.p, sizeof(kept));
+        n_hits = (int64_t)kept;
+        dev_memset(rt, keptPerRead.p + n_reads, 0, sizeof(int32_t));
+        pr.exclusive_sum<int32_t, int64_t>(keptPerRead.p, readHitOff.p, (int64_t)n_reads + 1);
+        hits2.ensure((size_t)n_hits + 1);
+      } else
+#endif
+      {
+        hits.ensure((size_t)n_hits + 1); hits2.ensure((size_t)n_hits + 1);
+        foreach(rt, n_q, GatherHitsFn{hitCnt.p, hitStart.p, hitOff.p, qRead.p, ix.posKey.p, hits.p, lay});
+        foreach(rt, (int64_t)n_reads + 1, ReadHitOffFn{qOff.p, hitOff.p, readHitOff.p});
+      }
+    }
+    {
+      StageTimer t(rt, &st.ms[3]);
+      pr.sort_keys<uint64_t>(hits.p, hits2.p, n_hits, readBits + lay.seqBits + lay.wsBits);
+    }
+    {
+      StageTimer t(rt, &st.ms[4]);
+      n_cand = 0;
+      dev_memset(rt, candCnt.p, 0, sizeof(int32_t) * ((size_t)n_reads + 1));
+      if (n_hits > 0) {
+        hflag.ensure((size_t)n_hits + 2); hfidx.ensure((size_t)n_hits + 2);
+        foreach(rt, n_hits + 1, HitFlagFn{hits2.p, readHitOff.p, sOf.p, readLen.p, dMinHits.p, dec, hflag.p, n_hits});
+        pr.exclusive_sum<int32_t, int64_t>(hflag.p, hfidx.p, n_hits + 1);
+        int64_t nFlag = 0; d2h(rt, &nFlag, hfidx.p + n_hits, sizeof(int64_t));
+        if (nFlag > 0) {
+          flagged.ensure((size_t)nFlag + 1); lhead.ensure((size_t)nFlag + 2); lidx.ensure((size_t)nFlag + 2);
+          foreach(rt, n_hits, HitCompactFn{hflag.p, hfidx.p, flagged.p});
+          foreach(rt, nFlag + 1, LocusHeadFn{hits2.p, flagged.p, sOf.p, readLen.p, dMinHits.p, dec, lhead.p, nFlag});
+          pr.exclusive_sum<int32_t, int64_t>(lhead.p, lidx.p, nFlag + 1);
+          d2h(rt, &n_cand, lidx.p + nFlag, sizeof(int64_t));
+          cRead.ensure((size_t)n_cand + 1); cSeq.ensure((size_t)n_cand + 1); cStart.ensure((size_t)n_cand + 1); cEnd.ensure((size_t)n_cand + 1);
+          foreach(rt, nFlag, LocusWriteFn{hits2.p, flagged.p, sOf.p, readLen.p, dMinHits.p, dec, lhead.p, lidx.p, nFlag,
+                                          cRead.p, cSeq.p, cStart.p, cEnd.p, candCnt.p});
+        }
+      }
       pr.exclusive_sum<int32_t, int64_t>(candCnt.p, candOff.p, (int64_t)n_reads + 1);
-      d2h(rt, &n_cand, candOff.p + n_reads, sizeof(int64_t));
       cRead.ensure((size_t)n_cand + 1); cSeq.ensure((size_t)n_cand + 1); cStart.ensure((size_t)n_cand + 1); cEnd.ensure((size_t)n_cand + 1);
-      cf.pass = 1; cf.cRead = cRead.p; cf.cSeq = cSeq.p; cf.cStart = cStart.p; cf.cEnd = cEnd.p;
-      foreach(rt, n_reads, cf);
     }
     // ---- K5
-    int64_t totalEv = 0;
+    int64_t totalEv = 0, smemSwept = 0;
     int32_t cntBytes = 2;
     oShared.ensure((size_t)n_cand + 1); oPos.ensure((size_t)n_cand + 1); oValid.ensure((size_t)n_cand + 1); oIstar.ensure((size_t)n_cand + 1);
     oVotes.ensure((size_t)n_cand + 1); oAccept.ensure((size_t)n_cand + 1); oOptS.ensure((size_t)n_cand + 1); oOptE.ensure((size_t)n_cand + 1);
@@ -447,64 +716,155 @@ struct Mapper {
       beg0.ensure((size_t)n_cand + 1); fe.ensure((size_t)n_cand + 1); le.ensure((size_t)n_cand + 1);
       spanN.ensure((size_t)n_cand + 2); stWords.ensure((size_t)n_cand + 2); evOff.ensure((size_t)n_cand + 2); stOff.ensure((size_t)n_cand + 2);
       {
-        StageTimer t(rt, &st.ms[3]);
+        StageTimer t(rt, &st.ms[5]);
         foreach(rt, n_cand + 1, L2SetupFn{ix.miWs.p, ix.contigStart.p, cRead.p, cSeq.p, cStart.p, cEnd.p, readLen.p, sOf.p, k, w,
                                            beg0.p, fe.p, le.p, spanN.p, n_cand});
         pr.exclusive_sum<int32_t, int64_t>(spanN.p, evOff.p, n_cand + 1);
       }
-      std::vector<int64_t> hEv((size_t)n_cand + 1), hSt((size_t)n_cand + 1);
+      std::vector<int64_t> hEv((size_t)n_cand + 1);
       d2h(rt, hEv.data(), evOff.p, sizeof(int64_t) * hEv.size());
       totalEv = hEv[(size_t)n_cand];
       // a gap counter never exceeds the number of minimizers in the span: 16 bits unless some span is huge
       for (int64_t c = 0; c < n_cand; c++) if (hEv[(size_t)c + 1] - hEv[(size_t)c] >= 65535) { cntBytes = 4; break; }
-      foreach(rt, n_cand + 1, StWordsFn{cRead.p, sOf.p, stWords.p, n_cand, cntBytes});
-      pr.exclusive_sum<int32_t, int64_t>(stWords.p, stOff.p, n_cand + 1);
-      d2h(rt, hSt.data(), stOff.p, sizeof(int64_t) * hSt.size());
       int64_t c0 = 0;
       while (c0 < n_cand) {          // passes bounded by the event budget
         int64_t c1 = c0 + 1;
         while (c1 < n_cand && hEv[(size_t)c1 + 1] - hEv[(size_t)c0] <= evBudget) c1++;
-        int64_t nEv = hEv[(size_t)c1] - hEv[(size_t)c0], nSt = hSt[(size_t)c1] - hSt[(size_t)c0], nc = c1 - c0;
-        ev.ensure((size_t)nEv + 1); state.ensure((size_t)nSt + 1);
-        dev_memset(rt, state.p, 0, sizeof(uint32_t) * (size_t)nSt);
-        {
-          StageTimer t(rt, &st.ms[4]);
-          foreach(rt, nEv, L2ClassifyFn{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p,
-                                        qHash.p, qOff.p, sOf.p, ev.p});
-        }
-        {
-          StageTimer t(rt, &st.ms[5]);
-          if (cntBytes == 2)
-            foreach(rt, nc, L2SweepFn<uint16_t>{ev.p, evOff.p, hEv[(size_t)c0], state.p, stOff.p, hSt[(size_t)c0], c0, beg0.p, fe.p, le.p, cRead.p, sOf.p,
-                                                readLen.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, k, w, oShared.p, oPos.p, oValid.p, oOptS.p, oOptE.p, oIstar.p},
-                    128, 16);
-          else
-            foreach(rt, nc, L2SweepFn<uint32_t>{ev.p, evOff.p, hEv[(size_t)c0], state.p, stOff.p, hSt[(size_t)c0], c0, beg0.p, fe.p, le.p, cRead.p, sOf.p,
-                                                readLen.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, k, w, oShared.p, oPos.p, oValid.p, oOptS.p, oOptE.p, oIstar.p},
-                    128, 16);
-        }
+        int64_t nEv = hEv[(size_t)c1] - hEv[(size_t)c0], nc = c1 - c0;
+        ev.ensure((size_t)nEv + 8);
         {
           StageTimer t(rt, &st.ms[6]);
+          L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p};
+#ifndef MM_HOST_EMU
+          if ((int64_t)maxSketch * 4 <= 200 * 1024) {
+            static bool attrC = false;
+            if (!attrC) { MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attrC = true; }
+            int64_t g = nc < (int64_t)rt.sm_count * 16 ? nc : (int64_t)rt.sm_count * 16;
+            l2_classify_smem_kernel<<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf);
+            MM_CUDA(cudaGetLastError());
+            rt.launches++;
+          } else
+#endif
+            foreach(rt, nEv, cf);
+        }
+        L2SweepArgs sa{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, le.p, cRead.p, sOf.p, readLen.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, k, w,
+                       oShared.p, oPos.p, oValid.p, oOptS.p, oOptE.p, oIstar.p};
+        {
+          StageTimer t(rt, &st.ms[7]);
+          smemSwept += sweep_pass(sa, nc, cntBytes);
+        }
+        if (ambigPending) {
+#ifndef MM_HOST_EMU
+          MM_CUDA(cudaStreamWaitEvent(rt.stream, evJoin(), 0));
+#endif
+          ambigPending = false;
+        }
+        {
+          StageTimer t(rt, &st.ms[8]);
           foreach(rt, nc, L2StrandFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, cRead.p, qOff.p, qStrand.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup,
                                      oValid.p, oOptS.p, oOptE.p, oIstar.p, oVotes.p}, 128, 16);
         }
         c0 = c1;
       }
-      foreach(rt, n_cand, AcceptFn{cRead.p, sOf.p, dAccept.p, oShared.p, oValid.p, oAccept.p, readMapped.p});
     }
-    scalar.ensure(4);
+    if (ambigPending) {
+#ifndef MM_HOST_EMU
+      MM_CUDA(cudaStreamWaitEvent(rt.stream, evJoin(), 0));
+#endif
+    }
     int64_t nMap = 0, nReadsMapped = 0;
-    if (n_cand > 0) {
-      DevBuf<int32_t> red; red.ensure(2);
-      pr.reduce_sum<int32_t>(oAccept.p, red.p, n_cand);
-      pr.reduce_sum<int32_t>(readMapped.p, red.p + 1, n_reads);
-      int32_t h[2]; d2h(rt, h, red.p, sizeof(h)); nMap = h[0]; nReadsMapped = h[1];
+    {
+      StageTimer t(rt, &st.ms[9]);
+      if (n_cand > 0) {
+        foreach(rt, n_cand, AcceptFn{cRead.p, sOf.p, dAccept.p, oShared.p, oValid.p, oAccept.p, readMapped.p});
+        red.ensure(2);
+        pr.reduce_sum<int32_t>(oAccept.p, red.p, n_cand);
+        pr.reduce_sum<int32_t>(readMapped.p, red.p + 1, n_reads);
+        int32_t h[2]; d2h(rt, h, red.p, sizeof(h)); nMap = h[0]; nReadsMapped = h[1];
+      }
     }
     rt.sync();
-    st.counters[0] = n_q; st.counters[1] = n_hits; st.counters[2] = n_cand; st.counters[3] = totalEv; st.counters[4] = nMap;
-    st.counters[5] = rs.n_total; st.counters[6] = basesOk; st.counters[7] = batch.n_exc;
+    st.counters[0] = n_q; st.counters[1] = n_hits_all; st.counters[10] = n_hits; st.counters[2] = n_cand; st.counters[3] = totalEv; st.counters[4] = nMap;
+    st.counters[5] = rs.n_total; st.counters[6] = basesOk; st.counters[7] = batch.n_exc; st.counters[8] = n_ambig; st.counters[9] = smemSwept;
     summary[0] = n_reads; summary[1] = nShort; summary[2] = n_cand; summary[3] = nMap; summary[4] = nReadsMapped; summary[5] = basesOk;
   }
+
+  // K5b over the candidates [sa.cand0, sa.cand0+nc) of one pass.  Returns how many were swept in shared memory.
+  int64_t sweep_pass(const L2SweepArgs& sa, int64_t nc, int32_t cntBytes) {
+    int64_t done_smem = 0;
+    const int32_t* redoList = nullptr; int64_t nRedo = nc;        // default: everything through the global-memory functor
+#ifndef MM_HOST_EMU
+    const int32_t SLICE = SWEEP_SLICE_WORDS;
+    if (nc >= 64 && nc < ((int64_t)1 << 31) && maxSketch < (1 << 20)) {
+      swKey.ensure((size_t)nc); swKey2.ensure((size_t)nc); swVal.ensure((size_t)nc); swOrder.ensure((size_t)nc);
+      foreach(rt, nc, SweepKeyFn{cRead.p, sOf.p, sa.cand0, swKey.p, swVal.p});
+      pr.sort_pairs<uint32_t, uint32_t>(swKey.p, swKey2.p, swVal.p, swOrder.p, nc, 20);
+      hk.resize((size_t)nc);
+      d2h(rt, hk.data(), swKey2.p, sizeof(uint32_t) * (size_t)nc);
+      // tiles over the descending-s order; candidates whose state does not fit a warp slice go to the global path
+      tileStartH.clear(); localOffH.assign((size_t)nc, 0);
+      int64_t firstFit = 0;
+      auto wordsOf = [](uint32_t s_) { return sweep_state_words((int32_t)s_, 1) | 1; };
+      while (firstFit < nc && wordsOf(0xFFFFFu - (hk[(size_t)firstFit] & 0xFFFFFu)) > SLICE) firstFit++;
+      int64_t i = firstFit;
+      while (i < nc) {
+        tileStartH.push_back((int32_t)i);
+        int32_t used = 0, cnt = 0;
+        while (i < nc && cnt < 32) {
+          int32_t wds = wordsOf(0xFFFFFu - (hk[(size_t)i] & 0xFFFFFu));
+          if (used + wds > SLICE) break;
+          localOffH[(size_t)i] = used; used += wds; cnt++; i++;
+        }
+      }
+      tileStartH.push_back((int32_t)nc);
+      int32_t nTiles = (int32_t)tileStartH.size() - 1;
+      swRedo.ensure((size_t)nc + 1); scal.ensure(4);
+      if (nTiles > 0) {
+        swTile.ensure(tileStartH.size()); swLocal.ensure((size_t)nc);
+        h2d(rt, swTile.p, tileStartH.data(), sizeof(int32_t) * tileStartH.size());
+        h2d(rt, swLocal.p, localOffH.data(), sizeof(int32_t) * (size_t)nc);
+        // scal[0] = redo count, scal[1] = tile counter.  Candidates that fit no slice (the first `firstFit` of the order)
+        // are pre-loaded into the redo list.
+        dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 2);
+        if (firstFit > 0) {
+          d2d(rt, swRedo.p, swOrder.p, sizeof(int32_t) * (size_t)firstFit);
+          unsigned long long ff = (unsigned long long)firstFit; h2d(rt, scal.p, &ff, sizeof(ff));
+        }
+        static bool attr = false;
+        if (!attr) { MM_CUDA(cudaFuncSetAttribute(l2_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_WARPS * SLICE * 4)); attr = true; }
+        int grid = (nTiles + SWEEP_WARPS - 1) / SWEEP_WARPS; if (grid > rt.sm_count) grid = rt.sm_count;
+        l2_sweep_smem_kernel<<<grid, SWEEP_WARPS * 32, SWEEP_WARPS * SLICE * 4, rt.stream>>>(sa, swOrder.p, swTile.p, nTiles, swLocal.p,
+                                                                                             (unsigned int*)(scal.p + 1), swRedo.p, scal.p);
+        MM_CUDA(cudaGetLastError());
+        rt.launches++;
+        unsigned long long nr = 0; d2h(rt, &nr, scal.p, sizeof(nr));
+        nRedo = (int64_t)nr; redoList = swRedo.p;
+        done_smem = nc - nRedo;
+      }
+    }
+#endif
+    if (nRedo > 0) {
+      // global-memory state for the rest (host-emulation build: for everything)
+      stWords.ensure((size_t)n_cand + 2); stOff.ensure((size_t)n_cand + 2);
+      foreach(rt, n_cand + 1, StWordsFn{cRead.p, sOf.p, stWords.p, n_cand, cntBytes});
+      pr.exclusive_sum<int32_t, int64_t>(stWords.p, stOff.p, n_cand + 1);
+      int64_t stRange[2];
+      d2h(rt, &stRange[0], stOff.p + sa.cand0, sizeof(int64_t));
+      d2h(rt, &stRange[1], stOff.p + sa.cand0 + nc, sizeof(int64_t));
+      int64_t nSt = stRange[1] - stRange[0];
+      state.ensure((size_t)nSt + 1);
+      dev_memset(rt, state.p, 0, sizeof(uint32_t) * (size_t)nSt);
+      if (cntBytes == 2) foreach(rt, nRedo, L2SweepFn<uint16_t>{sa, state.p, stOff.p, stRange[0], redoList}, 128, 16);
+      else foreach(rt, nRedo, L2SweepFn<uint32_t>{sa, state.p, stOff.p, stRange[0], redoList}, 128, 16);
+    }
+    return done_smem;
+  }
+
+#ifndef MM_HOST_EMU
+  cudaEvent_t evF = nullptr, evJ = nullptr;
+  cudaEvent_t evFork() { if (!evF) MM_CUDA(cudaEventCreateWithFlags(&evF, cudaEventDisableTiming)); return evF; }
+  cudaEvent_t evJoin() { if (!evJ) MM_CUDA(cudaEventCreateWithFlags(&evJ, cudaEventDisableTiming)); return evJ; }
+#endif
 };
 
 }  // namespace mm

@@ -51,6 +51,7 @@ struct Error : std::runtime_error {
 struct Runtime {
   int device = 0;
   cudaStream_t stream = 0;
+  cudaStream_t side = 0;         // side stream: work that is off the critical path (joined with events)
   int sm_count = 148;
   int64_t launches = 0;          // kernels launched since reset()
   double total_ms = 0;           // filled by StageTimer users
@@ -193,17 +194,19 @@ __global__ void __launch_bounds__(128) foreach_kernel128(int64_t n, F f) {
 // One logical thread per item.  Grid = a multiple of the SM count (grid-stride loop), so the last wave
 // is never a sliver (148 SMs, see DESIGN.md "grid sizing").
 template <class F>
-inline void foreach(Runtime& rt, int64_t n, const F& f, int block = 256, int ctas_per_sm = 8) {
+inline void foreach(Runtime& rt, int64_t n, const F& f, int block = 256, int ctas_per_sm = 8, bool on_side_stream = false) {
   if (n <= 0) return;
 #ifdef MM_HOST_EMU
+  (void)on_side_stream;
   for (int64_t i = 0; i < n; i++) f(i);
   rt.launches++;
 #else
   int64_t need = (n + block - 1) / block;
   int64_t maxg = (int64_t)rt.sm_count * ctas_per_sm;
   int grid = (int)(need < maxg ? need : maxg);
-  if (block == 128) foreach_kernel128<F><<<grid, 128, 0, rt.stream>>>(n, f);
-  else foreach_kernel<F><<<grid, 256, 0, rt.stream>>>(n, f);
+  cudaStream_t st = on_side_stream ? rt.side : rt.stream;
+  if (block == 128) foreach_kernel128<F><<<grid, 128, 0, st>>>(n, f);
+  else foreach_kernel<F><<<grid, 256, 0, st>>>(n, f);
   MM_CUDA(cudaGetLastError());
   rt.launches++;
 #endif
