@@ -156,6 +156,12 @@ int mm_em_run(mm_ctx* ctx, const int32_t* taxon, const double* mapq, const doubl
 int mm_comm_unique_id(void* id_bytes_128);
 int mm_comm_init(mm_ctx* ctx, int n_ranks, int rank, const void* id_bytes_128);
 int mm_comm_destroy(mm_ctx* ctx);
+/* Alternative transport for the same exchange: a caller-supplied sum-all-reduce over a HOST buffer of n doubles
+ * (e.g. MPI_Allreduce or torch.distributed/gloo).  The (T+1)-double buffer is staged through the host each EM round.
+ * Used when NCCL is not wanted and by the world-size-2 gloo tests; pass fn = NULL to remove it.  NCCL takes
+ * precedence when both are set.  The callback returns 0 on success. */
+typedef int (*mm_allreduce_fn)(double* buf, int64_t n, void* user);
+int mm_comm_set_allreduce(mm_ctx* ctx, mm_allreduce_fn fn, void* user);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,9 @@ SYMBOLS = {
     "mm_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mm_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mm_comm_destroy": (C.c_int, [C.c_void_p]),
+    "mm_comm_set_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int64, C.c_void_p)
 
 
 class MMError(RuntimeError):
@@ -168,6 +170,22 @@ class Context:
     def comm_init(self, n_ranks: int, rank: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         self._check(self.lib.mm_comm_init(self.h, n_ranks, rank, buf))
+
+    def set_allreduce(self, fn):
+        """fn(numpy float64 array) -> None must sum-all-reduce the array in place across ranks (host transport)."""
+        if fn is None:
+            self._ar = None
+            self._check(self.lib.mm_comm_set_allreduce(self.h, None, None))
+            return
+
+        def tramp(ptr, n, user):
+            try:
+                fn(np.ctypeslib.as_array(ptr, shape=(n,)))
+                return 0
+            except Exception:
+                return 1
+        self._ar = ALLREDUCE_FN(tramp)        # keep the trampoline alive
+        self._check(self.lib.mm_comm_set_allreduce(self.h, C.cast(self._ar, C.c_void_p), None))
 
     def comm_unique_id(self) -> bytes:
         buf = C.create_string_buffer(128)

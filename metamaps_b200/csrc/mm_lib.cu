@@ -35,6 +35,7 @@ struct mm_ctx {
   } scr;
   // NCCL (multi-GPU EM), bound at run time
   void* ncclLib = nullptr; void* comm = nullptr; int nRanks = 1, rank = 0;
+  mm_allreduce_fn hostAllreduce = nullptr; void* hostAllreduceUser = nullptr; std::vector<double> hostBuf;
   mm_ctx() : pr(rt), sk(rt, pr), mp(rt, pr, sk) {}
 };
 struct mm_index {
@@ -388,7 +389,19 @@ int mm_comm_destroy(mm_ctx* c) {
   c->comm = nullptr; c->nRanks = 1; c->rank = 0;
   return MM_OK;
 }
+int mm_comm_set_allreduce(mm_ctx* c, mm_allreduce_fn fn, void* user) {
+  if (!c) { g_err = "null ctx"; return MM_EINVAL; }
+  c->hostAllreduce = fn; c->hostAllreduceUser = user;
+  return MM_OK;
+}
 static void allreduce_sum_f64(mm_ctx* c, double* buf, size_t n) {
+  if (!c->comm && c->hostAllreduce) {        // host-staged transport
+    c->hostBuf.resize(n);
+    d2h(c->rt, c->hostBuf.data(), buf, sizeof(double) * n);
+    if (c->hostAllreduce(c->hostBuf.data(), (int64_t)n, c->hostAllreduceUser) != 0) throw Error(MM_ECUDA, "host all-reduce callback failed");
+    h2d(c->rt, buf, c->hostBuf.data(), sizeof(double) * n);
+    return;
+  }
   if (!c->comm || c->nRanks == 1) return;
   int rc = ((fn_ncclAllReduce)nccl_sym(c->ncclLib, "ncclAllReduce"))(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->rt.stream);
   if (rc != 0) throw Error(MM_ECUDA, "ncclAllReduce failed: " + std::to_string(rc));

@@ -1,0 +1,55 @@
+"""World-size-2 (gloo, CPU) test of the multi-rank EM path: reads are partitioned over ranks, each rank runs mm_em_run
+on its share and the per-round taxon sums are all-reduced through the host transport (mm_comm_set_allreduce).  The
+result must equal the single-rank EM over all reads (the oracle)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from metamaps_b200 import capi
+    from tests import common
+    from tests.conftest import build_emu
+    lib = capi.load(build_emu())
+    ctx = capi.Context(0, lib)
+
+    def allreduce(a):
+        t = torch.from_numpy(a)
+        dist.all_reduce(t)          # in place on the shared buffer
+    ctx.set_allreduce(allreduce)
+    tax, mq, nloc, off, T = common.random_em_case(31, nr=4000, T=60, maxc=15)
+    # contiguous partition of the reads, like the bench shards read batches
+    nr = len(off) - 1
+    lo, hi = rank * nr // world, (rank + 1) * nr // world
+    m0, m1 = off[lo], off[hi]
+    res = ctx.em(tax[m0:m1], mq[m0:m1], nloc[m0:m1], off[lo:hi + 1] - m0, T)
+    np.savez(os.path.join(tmp, f"rank{rank}.npz"), f=res["f"], post=res["posterior"], best=res["best"] + m0, iters=res["iters"], ll=res["ll"], lo=lo, hi=hi, m0=m0, m1=m1)
+    dist.destroy_process_group()
+
+
+def test_em_two_ranks_equals_single_rank(oracle, tmp_path):
+    from tests import common
+    from tests.conftest import build_emu
+    build_emu()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    tax, mq, nloc, off, T = common.random_em_case(31, nr=4000, T=60, maxc=15)
+    ref = oracle.em(tax, mq, nloc, off, T)
+    parts = [np.load(os.path.join(str(tmp_path), f"rank{r}.npz")) for r in range(2)]
+    for p in parts:
+        assert int(p["iters"]) == ref["iters"]                        # same stopping round on every rank
+        assert np.abs(p["f"] - ref["f"]).max() <= 1e-6                # identical global frequencies
+        assert np.abs(p["ll"] - ref["ll"]).max() <= 1e-6 * np.abs(ref["ll"]).max()
+        assert np.abs(p["post"] - ref["posterior"][int(p["m0"]):int(p["m1"])]).max() <= 1e-6
+        assert np.array_equal(p["best"], ref["best"][int(p["lo"]):int(p["hi"])])
+    assert np.array_equal(parts[0]["f"], parts[1]["f"])
