@@ -29,6 +29,8 @@ def round_6_significant(x32: np.ndarray) -> np.ndarray:
     parsing it back (what mapWrap.h:229 / fEM.h:297 see).  x*10^d has at most 24+14 significant bits, so the
     scaling is exact in double and rint()/division give the correctly rounded decimal."""
     x = x32.astype(np.float64)
+    if x.size and x.min() >= 10.0 and x.max() < 99.99995:      # the usual case: identities in [10,100) -> 4 decimals
+        return np.rint(x * 1e4) / 1e4
     out = np.zeros_like(x)
     nz = x != 0
     e = np.floor(np.log10(np.abs(x[nz])))
@@ -94,22 +96,21 @@ def _nloc(tax, m_seq, m_read, L, contig_len, contig_taxon, n_taxa):
     key = (id(contig_len), id(contig_taxon))
     if key not in _TAXON_CACHE:
         order = np.lexsort((contig_len, contig_taxon))
-        lens = contig_len[order].astype(np.int64); tx = contig_taxon[order]
+        lens = contig_len[order].astype(np.int64); tx = contig_taxon[order].astype(np.int64)
         start = np.searchsorted(tx, np.arange(n_taxa + 1))
         csum = np.concatenate([[0], np.cumsum(lens)])
-        _TAXON_CACHE.clear(); _TAXON_CACHE[key] = (lens, start, csum)
-    lens, start, csum = _TAXON_CACHE[key]
-    # contigs of taxon t are lens[start[t]:start[t+1]] ascending; those >= L start at p
-    # vectorised per-mapping binary search inside the taxon's slice
-    lo = start[tax].copy(); hi = start[tax + 1].copy()
-    while True:
-        act = lo < hi
-        if not act.any():
-            break
-        mid = (lo + hi) // 2
-        less = act & (lens[np.minimum(mid, len(lens) - 1)] < L)
-        lo = np.where(less, mid + 1, lo); hi = np.where(act & ~less, mid, hi)
-    p = lo
+        big = int(lens.max()) + 2 if len(lens) else 2
+        tsum = np.bincount(contig_taxon, weights=contig_len.astype(np.float64), minlength=n_taxa).astype(np.int64)
+        tcnt = np.bincount(contig_taxon, minlength=n_taxa).astype(np.int64)
+        _TAXON_CACHE.clear(); _TAXON_CACHE[key] = (lens, start, csum, tx * big + lens, big, tsum, tcnt, int(lens.min()) if len(lens) else 0)
+    lens, start, csum, skey, big, tsum, tcnt, min_len = _TAXON_CACHE[key]
+    if len(L) and int(L.max()) <= min_len:          # every contig is at least as long as every read: closed form
+        return (tsum[tax] - tcnt[tax] * (L - 1)).astype(np.float64)
+    # contigs of taxon t are lens[start[t]:start[t+1]] ascending; p = first of them with len >= L: one global
+    # searchsorted over (taxon, len) keys
+    tax = tax.astype(np.int64)
+    p = np.searchsorted(skey, tax * big + np.minimum(L, big - 1), side="left")
+    p = np.clip(p, start[tax], start[tax + 1])
     n_big = start[tax + 1] - p
     big = (csum[start[tax + 1]] - csum[p]) - n_big * (L - 1)
     # short contigs (len < L) count once if this read maps to them; distinct (read, contig) pairs of the taxon
