@@ -100,6 +100,81 @@ struct ProbeFn {            // computeMap.hpp:307-321
     else hitCnt[i] = 0;
   }
 };
+#ifndef MM_HOST_EMU
+// Device fast path of the probe: persistent CTAs; batches of 2048 probe keys are staged into shared memory by the
+// TMA engine (cp.async.bulk global -> shared, completion on an mbarrier), double-buffered, so the next batch lands
+// while the current one is being probed.  The probes themselves are independent random 16-byte slot reads; each thread
+// keeps four of them in flight.
+MM_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+MM_DEV void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+MM_DEV void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src), "r"(bytes),
+               "r"(smem_addr(bar))
+               : "memory");
+}
+MM_DEV void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MM_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MM_DONE_%=;\n"
+      "bra MM_WAIT_%=;\n"
+      "MM_DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+static const int PROBE_TILE = 2048;
+__global__ void __launch_bounds__(256) l1_probe_tma_kernel(const Slot* table, uint32_t mask, const uint32_t* qHash, int32_t freqThreshold, int32_t* hitCnt,
+                                                           int64_t* hitStart, int64_t n) {
+  __shared__ __align__(128) uint32_t keys[2][PROBE_TILE];
+  __shared__ __align__(8) unsigned long long bar[2];
+  const int64_t nTiles = (n + PROBE_TILE - 1) / PROBE_TILE;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto tileBytes = [&](int64_t tile) { int64_t c = n - tile * PROBE_TILE; if (c > PROBE_TILE) c = PROBE_TILE; return (uint32_t)(((c * 4 + 15) / 16) * 16); };
+  int64_t tile = blockIdx.x; int stage = 0; uint32_t phase0 = 0, phase1 = 0;
+  if (tile < nTiles && threadIdx.x == 0) tma_load_1d(keys[0], qHash + tile * PROBE_TILE, tileBytes(tile), &bar[0]);
+  for (; tile < nTiles; tile += gridDim.x) {
+    const int64_t next = tile + gridDim.x;
+    if (next < nTiles && threadIdx.x == 0) tma_load_1d(keys[stage ^ 1], qHash + next * PROBE_TILE, tileBytes(next), &bar[stage ^ 1]);
+    if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+    const int64_t base = tile * PROBE_TILE;
+    const int32_t cnt = (int32_t)((n - base) < PROBE_TILE ? (n - base) : PROBE_TILE);
+    for (int32_t i0 = threadIdx.x; i0 < cnt; i0 += 4 * blockDim.x) {
+      uint32_t h[4]; uint4 v[4]; uint32_t sl[4]; bool act[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int32_t i = i0 + u * (int32_t)blockDim.x;
+        act[u] = i < cnt;
+        h[u] = act[u] ? keys[stage][i] : 0u;
+        sl[u] = slot_of(h[u], mask);
+        if (act[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(table + sl[u]));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (!act[u]) continue;
+        const int32_t i = i0 + u * (int32_t)blockDim.x;
+        uint4 w = v[u]; uint32_t s_ = sl[u];
+        while (w.y != 0 && w.x != h[u]) { s_ = (s_ + 1) & mask; w = __ldg(reinterpret_cast<const uint4*>(table + s_)); }
+        int32_t c = 0;
+        if (w.y != 0 && (int64_t)w.y < (int64_t)freqThreshold) { c = (int32_t)w.y; hitStart[base + i] = (int64_t)(((uint64_t)w.w << 32) | w.z); }
+        hitCnt[base + i] = c;
+      }
+    }
+    __syncthreads();          // the whole CTA is done with this stage before it is refilled
+    stage ^= 1;
+  }
+}
+#endif
+
 // Hits are written as ONE 64-bit sort key  read << (seqBits+wsBits) | seqId << wsBits | (wpos<<1|strand), so that a
 // single radix sort over the used bits orders them per read by (seqId, wpos, strand) -- the order std::sort gives
 // the reference (computeMap.hpp:352).
@@ -409,8 +484,9 @@ MM_HD bool l2_sweep_one(const L2SweepArgs& a, int64_t c, CntT* cnt, uint32_t* mb
     z.ins(code & ~CODE_DUP);
   }
   int32_t best = 0, bpos = 0, lpos = 0, valid = 0, bistar = s, optS = 0, optE = 0;
-  // the two event streams are kept one element ahead in registers
-  uint2 evBeg = ldg(e + beg), evBeg1 = ldg(e + beg + 1), evEnd = ldg(e + end), evEnd1 = ldg(e + end + 1);
+  // the two event streams are kept two elements ahead in registers (the loads have two iterations to land)
+  uint2 evBeg = ldg(e + beg), evBeg1 = ldg(e + beg + 1), evBeg2 = ldg(e + beg + 2);
+  uint2 evEnd = ldg(e + end), evEnd1 = ldg(e + end + 1), evEnd2 = ldg(e + end + 2);
   int32_t sw_pos = (int32_t)(evBeg.y >> 1);
   uint32_t delCode = NOP, insCode = NOP; int32_t oldEnd = end;
   while (end < last) {
@@ -435,8 +511,8 @@ MM_HD bool l2_sweep_one(const L2SweepArgs& a, int64_t c, CntT* cnt, uint32_t* mb
     sw_pos += adv;
     oldEnd = end;
     delCode = NOP; insCode = NOP;
-    if (adv == nb) { delCode = evBeg.x; evBeg = evBeg1; beg++; evBeg1 = ldg(e + beg + 1); }
-    if (adv == ne) { insCode = evEnd.x; evEnd = evEnd1; end++; evEnd1 = ldg(e + end + 1); }
+    if (adv == nb) { delCode = evBeg.x; evBeg = evBeg1; evBeg1 = evBeg2; beg++; evBeg2 = ldg(e + beg + 2); }
+    if (adv == ne) { insCode = evEnd.x; evEnd = evEnd1; evEnd1 = evEnd2; end++; evEnd2 = ldg(e + end + 2); }
   }
   a.oShared[c] = best; a.oPos[c] = (bpos + lpos) / 2; a.oValid[c] = valid; a.oOptS[c] = b0 + optS; a.oOptE[c] = b0 + optE; a.oIstar[c] = bistar;
   return true;
@@ -648,7 +724,18 @@ struct Mapper {
     {
       StageTimer t(rt, &st.ms[2]);
       hitCnt.ensure((size_t)n_q + 2); hitStart.ensure((size_t)n_q + 2); hitOff.ensure((size_t)n_q + 2);
+#ifndef MM_HOST_EMU
+      if (n_q > 0) {
+        int64_t tiles = (n_q + PROBE_TILE - 1) / PROBE_TILE;
+        int grid = (int)(tiles < (int64_t)rt.sm_count * 4 ? tiles : (int64_t)rt.sm_count * 4);
+        l1_probe_tma_kernel<<<grid, 256, 0, rt.stream>>>(ix.table.p, ix.tableMask, qHash.p, ix.freqThreshold, hitCnt.p, hitStart.p, n_q);
+        MM_CUDA(cudaGetLastError());
+        rt.launches++;
+      }
+      dev_memset(rt, hitCnt.p + n_q, 0, sizeof(int32_t));
+#else
       foreach(rt, n_q + 1, ProbeFn{ix.table.p, ix.tableMask, qHash.p, ix.freqThreshold, hitCnt.p, hitStart.p, n_q});
+#endif
       pr.exclusive_sum<int32_t, int64_t>(hitCnt.p, hitOff.p, n_q + 1);
       d2h(rt, &n_hits, hitOff.p + n_q, sizeof(int64_t));
       readHitOff.ensure((size_t)n_reads + 2);
