@@ -226,14 +226,12 @@ __global__ void __launch_bounds__(256) l1_filter_gather_kernel(const int32_t* hi
       }
     }
     const int anySat = __syncthreads_or(saturated ? 1 : 0);      // absurdly deep pile-up: keep everything for this read
+    // survivors = sum of the bins that reached minimumHits (no second pass over the position lists)
     unsigned int local = 0;
-    for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-      const int32_t c = hitCnt[q]; const int64_t st = hitStart[q];
-      for (int32_t j = 0; j < c; j++) {
-        const uint32_t b = (uint32_t)(__ldg(posKey + st + j) >> 32) & binMask;
-        const uint32_t v = (bins[b >> 1] >> ((b & 1u) * 16)) & 0xFFFFu;
-        local += (anySat || v >= (uint32_t)mh) ? 1u : 0u;
-      }
+    for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) {
+      const uint32_t w = bins[i], lo = w & 0xFFFFu, hi = w >> 16;
+      local += (anySat || lo >= (uint32_t)mh) ? lo : 0u;
+      local += (anySat || hi >= (uint32_t)mh) ? hi : 0u;
     }
     if (local) atomicAdd(&smTotal, local);
     __syncthreads();
