@@ -23,7 +23,10 @@
 
 namespace mm {
 
-static const uint32_t CODE_MATCH = 0x80000000u, CODE_DUP = 0x40000000u, CODE_IDX = 0x3FFFFFFFu;
+// event code of one reference minimizer of a span: bit 31 = its hash is in the read sketch (idx = 1-based query rank),
+// else idx = gap (number of query hashes below it); bits 30/29 = its insertion / deletion does not change the window's
+// hash SET because another copy of the same hash is inside the window at that moment (SlideMapper keeps one entry per hash)
+static const uint32_t CODE_MATCH = 0x80000000u, CODE_INS_NOP = 0x40000000u, CODE_DEL_NOP = 0x20000000u, CODE_IDX = 0x1FFFFFFFu;
 // K5b state of one candidate: s+1 gap counters (cntBytes each) + s match bits + one spare word, in 32-bit words
 MM_HD int32_t sweep_cnt_words(int32_t s, int32_t cntBytes) { return ((s + 1) * cntBytes + 3) / 4; }
 MM_HD int32_t sweep_state_words(int32_t s, int32_t cntBytes) { return sweep_cnt_words(s, cntBytes) + (s + 31) / 32 + 1; }
@@ -354,12 +357,37 @@ struct StWordsFn {
   }
 };
 
+MM_HD uint64_t dup_links(const uint32_t* dupIdx, const uint64_t* dupLinks, int64_t n_dup, int64_t j) {
+  int64_t p = lower_bound_idx(dupIdx, n_dup, (uint32_t)j);
+  return (p < n_dup && ldg(dupIdx + p) == (uint32_t)j) ? ldg(dupLinks + p) : 0ull;
+}
+// Which of a duplicated minimizer's two events are no-ops.  Element j enters the window at the step where
+// sw_pos = wpos[j]-cmw+1 (or at once if j < fe) and leaves at the step where sw_pos = wpos[j+1]; inside one step the
+// reference deletes before it inserts (computeMap.hpp:500-505).
+MM_HD uint32_t dup_event_flags(const uint32_t* miWs, const uint32_t* dupIdx, const uint64_t* dupLinks, int64_t n_dup, int64_t j, int64_t b0, int64_t fe,
+                               int64_t last, int32_t cmw) {
+  const uint64_t l = dup_links(dupIdx, dupLinks, n_dup, j);
+  const uint32_t pd = (uint32_t)(l >> 32), nd = (uint32_t)l;
+  uint32_t f = 0;
+  const int64_t wj = (int64_t)(ldg(miWs + j) >> 1);
+  if (pd) {
+    const int64_t p = j - (int64_t)pd;
+    if (p >= b0 && (j < fe || (int64_t)(ldg(miWs + p + 1) >> 1) > wj - cmw + 1)) f |= CODE_INS_NOP;      // the earlier copy is still inside
+  }
+  if (nd) {
+    const int64_t q = j + (int64_t)nd;
+    if (q < last && (q < fe || (int64_t)(ldg(miWs + q) >> 1) - cmw + 1 < (int64_t)(ldg(miWs + j + 1) >> 1))) f |= CODE_DEL_NOP;   // a later copy already entered
+  }
+  return f;
+}
+
 // phase A: one item per reference minimizer of a candidate span
 struct L2ClassifyFn {
   const uint32_t* miHash; const uint32_t* miWs; const uint32_t* dupBits;
   const int64_t* evOff; int64_t cand0, nCand; int64_t evBase;   // candidates [cand0, cand0+nCand), events relative to evBase
   const int64_t* beg0; const int32_t* cRead; const uint32_t* qHash; const int64_t* qOff; const int32_t* sOf;
   uint2* ev;
+  const int64_t* fe; const int64_t* le; const int32_t* readLen; const uint32_t* dupIdx; const uint64_t* dupLinks; int64_t n_dup; int k, w;
   MM_HD void operator()(int64_t t) const {
     int64_t c = cand0 + upper_bound_idx(evOff + cand0, nCand + 1, t + evBase) - 1;
     int64_t j = ldg(beg0 + c) + (t + evBase - ldg(evOff + c));
@@ -369,7 +397,8 @@ struct L2ClassifyFn {
     int32_t lo = 0, hi = s;
     while (lo < hi) { int32_t m = (lo + hi) >> 1; if (ldg(q + m) < h) lo = m + 1; else hi = m; }
     uint32_t code = (lo < s && ldg(q + lo) == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
-    if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u) code |= CODE_DUP;
+    if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u)
+      code |= dup_event_flags(miWs, dupIdx, dupLinks, n_dup, j, ldg(beg0 + c), ldg(fe + c), ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1));
     ev[t] = make_uint2(code, ldg(miWs + j));
   }
 };
@@ -393,7 +422,8 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a) {
       int32_t lo = 0, hi = s;
       while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (smq[m] < h) lo = m + 1; else hi = m; }
       uint32_t code = (lo < s && smq[lo] == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
-      if ((__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u) code |= CODE_DUP;
+      if ((__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u)
+        code |= dup_event_flags(a.miWs, a.dupIdx, a.dupLinks, a.n_dup, j, b0, a.fe[c], a.le[c], a.readLen[r] - (a.w - 1) - (a.k - 1));
       a.ev[e0 + t] = make_uint2(code, __ldg(a.miWs + j));
     }
     __syncthreads();
@@ -401,10 +431,6 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a) {
 }
 #endif
 
-MM_HD uint64_t dup_links(const uint32_t* dupIdx, const uint64_t* dupLinks, int64_t n_dup, int64_t j) {
-  int64_t p = lower_bound_idx(dupIdx, n_dup, (uint32_t)j);
-  return (p < n_dup && ldg(dupIdx + p) == (uint32_t)j) ? ldg(dupLinks + p) : 0ull;
-}
 
 // phase B: the evaluate-then-advance loop of computeL2MappedRegions (computeMap.hpp:482-533).
 // The gap counters cnt[] and the match bits mb[] live wherever the caller puts them:
@@ -477,27 +503,18 @@ MM_HD bool l2_sweep_one(const L2SweepArgs& a, int64_t c, CntT* cnt, uint32_t* mb
   const int32_t cmw = len - (a.w - 1) - (a.k - 1);
   // slidemap.insert_ref(sw_beg, sw_end) (computeMap.hpp:488); a hash already present is only revised
   for (int32_t j = 0; j < end; j++) {
-    uint32_t code = ldg(&e[j].x);
-    if (code & CODE_DUP) { uint64_t l = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0 + j); uint32_t pd = (uint32_t)(l >> 32); if (pd && j - (int64_t)pd >= 0) code = NOP; }
-    z.ins(code & ~CODE_DUP);
+    const uint32_t code = ldg(&e[j].x);
+    z.ins((code & CODE_INS_NOP) ? NOP : (code & (CODE_MATCH | CODE_IDX)));
   }
   int32_t best = 0, bpos = 0, lpos = 0, valid = 0, bistar = s, optS = 0, optE = 0;
   // the two event streams are kept two elements ahead in registers (the loads have two iterations to land)
   uint2 evBeg = ldg(e + beg), evBeg1 = ldg(e + beg + 1), evBeg2 = ldg(e + beg + 2);
   uint2 evEnd = ldg(e + end), evEnd1 = ldg(e + end + 1), evEnd2 = ldg(e + end + 2);
   int32_t sw_pos = (int32_t)(evBeg.y >> 1);
-  uint32_t delCode = NOP, insCode = NOP; int32_t oldEnd = end;
+  uint32_t delCode = NOP, insCode = NOP;
   while (end < last) {
-    if (delCode & CODE_DUP) {                            // delete_ref(prev_beg) (slidingMap.hpp:170-219): a later copy keeps the hash
-      uint64_t l = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0 + beg - 1); uint32_t nd = (uint32_t)l;
-      delCode = (nd && (int64_t)(beg - 1) + nd < oldEnd) ? NOP : (delCode & ~CODE_DUP);
-    }
-    z.del(delCode);
-    if (insCode & CODE_DUP) {                            // insert_ref(prev_end) (slidingMap.hpp:139-164): an earlier copy already holds it
-      uint64_t l = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0 + end - 1); uint32_t pd = (uint32_t)(l >> 32);
-      insCode = (pd && (int64_t)(end - 1) - pd >= beg) ? NOP : (insCode & ~CODE_DUP);
-    }
-    z.ins(insCode);
+    z.del((delCode & CODE_DEL_NOP) ? NOP : (delCode & (CODE_MATCH | CODE_IDX)));      // delete_ref(prev_beg) (slidingMap.hpp:170-219)
+    z.ins((insCode & CODE_INS_NOP) ? NOP : (insCode & (CODE_MATCH | CODE_IDX)));      // insert_ref(prev_end) (slidingMap.hpp:139-164)
     if (CHECK_OVF && z.ovf) return false;
     const int32_t wb = (int32_t)(evBeg.y >> 1);
     const bool better = z.shared > best;
@@ -507,7 +524,6 @@ MM_HD bool l2_sweep_one(const L2SweepArgs& a, int64_t c, CntT* cnt, uint32_t* mb
     const int32_t ne = (int32_t)(evEnd.y >> 1) - (sw_pos + cmw - 1);
     const int32_t adv = nb < ne ? nb : ne;
     sw_pos += adv;
-    oldEnd = end;
     delCode = NOP; insCode = NOP;
     if (adv == nb) { delCode = evBeg.x; evBeg = evBeg1; evBeg1 = evBeg2; beg++; evBeg2 = ldg(e + beg + 2); }
     if (adv == ne) { insCode = evEnd.x; evEnd = evEnd1; evEnd1 = evEnd2; end++; evEnd2 = ldg(e + end + 2); }
@@ -537,14 +553,14 @@ struct SweepKeyFn {     // sort key: descending sketch size (similar work inside
 // counter: a tile = up to 32 consecutive candidates (in descending-sketch-size order) whose gap counters + match bits
 // fit the slice; lane t sweeps candidate order[tileStart+t].  No block-level barrier: a slow candidate only delays its
 // own warp.  Per-candidate word counts are odd, so the lanes' regions start on different banks.
-static const int SWEEP_WARPS = 6;                    // warps per CTA (1 CTA per SM)
-static const int SWEEP_SLICE_WORDS = 8704;           // 34 KB per warp -> 204 KB per CTA
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) l2_sweep_smem_kernel(L2SweepArgs a, const uint32_t* order, const int32_t* tileStart, int32_t nTiles,
+static const int SWEEP_WARPS_MAX = 8;                // warps per CTA (1 CTA per SM); MM_SWEEP_WARPS overrides
+static const int SWEEP_SMEM_WORDS = 56 * 1024;       // 224 KB of the SM's 227 KB, split evenly between the warps
+__global__ void __launch_bounds__(SWEEP_WARPS_MAX * 32) l2_sweep_smem_kernel(L2SweepArgs a, const uint32_t* order, const int32_t* tileStart, int32_t nTiles,
                                                                          const int32_t* localOff, unsigned int* tileCounter, int32_t* redo,
-                                                                         unsigned long long* redoCount) {
+                                                                         unsigned long long* redoCount, int32_t sliceWords) {
   extern __shared__ uint32_t sm[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t* slice = sm + wid * SWEEP_SLICE_WORDS;
+  uint32_t* slice = sm + wid * sliceWords;
   for (;;) {
     int32_t tile = 0;
     if (lane == 0) tile = (int32_t)atomicAdd(tileCounter, 1u);
@@ -570,7 +586,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) l2_sweep_smem_kernel(L2Sweep
 struct L2StrandFn {
   const uint2* ev; const int64_t* evOff; int64_t evBase; int64_t cand0; const int64_t* beg0;
   const int32_t* cRead; const int64_t* qOff; const uint8_t* qStrand;
-  const uint32_t* dupIdx; const uint64_t* dupLinks; int64_t n_dup;
+  const uint32_t* dupIdx; const uint64_t* dupLinks; int64_t n_dup; const uint32_t* dupBits;
   const int32_t* oValid; const int64_t* oOptS; const int64_t* oOptE; const int32_t* oIstar; int32_t* oVotes;
   MM_HD void operator()(int64_t ci) const {
     int64_t c = cand0 + ci;
@@ -585,7 +601,7 @@ struct L2StrandFn {
         int32_t i = (int32_t)(v.x & CODE_IDX);
         if (i > istar) continue;
         // the map keeps the strand of the LAST inserted occurrence of a hash
-        if (v.x & CODE_DUP) { uint64_t l = dup_links(dupIdx, dupLinks, n_dup, j); uint32_t nd = (uint32_t)l; if (nd && j + (int64_t)nd < b) continue; }
+        if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u) { uint64_t l = dup_links(dupIdx, dupLinks, n_dup, j); uint32_t nd = (uint32_t)l; if (nd && j + (int64_t)nd < b) continue; }
         int32_t sq = ldg(qs + i - 1) ? 1 : -1, sr = (v.y & 1u) ? 1 : -1;
         votes += sq * sr;
       }
@@ -819,7 +835,8 @@ struct Mapper {
         ev.ensure((size_t)nEv + 8);
         {
           StageTimer t(rt, &st.ms[6]);
-          L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p};
+          L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p,
+                          fe.p, le.p, readLen.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, k, w};
 #ifndef MM_HOST_EMU
           if ((int64_t)maxSketch * 4 <= 200 * 1024) {
             static bool attrC = false;
@@ -846,7 +863,7 @@ struct Mapper {
         }
         {
           StageTimer t(rt, &st.ms[8]);
-          foreach(rt, nc, L2StrandFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, cRead.p, qOff.p, qStrand.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup,
+          foreach(rt, nc, L2StrandFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, cRead.p, qOff.p, qStrand.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, ix.dupBits.p,
                                      oValid.p, oOptS.p, oOptE.p, oIstar.p, oVotes.p}, 128, 16);
         }
         c0 = c1;
@@ -879,7 +896,14 @@ struct Mapper {
     int64_t done_smem = 0;
     const int32_t* redoList = nullptr; int64_t nRedo = nc;        // default: everything through the global-memory functor
 #ifndef MM_HOST_EMU
-    const int32_t SLICE = SWEEP_SLICE_WORDS;
+    static int SWEEP_WARPS = 0;
+    if (!SWEEP_WARPS) {
+      const char* ev_ = getenv("MM_SWEEP_WARPS");
+      SWEEP_WARPS = ev_ ? atoi(ev_) : 8;
+      if (SWEEP_WARPS < 1 || SWEEP_WARPS > SWEEP_WARPS_MAX) SWEEP_WARPS = 8;
+      MM_CUDA(cudaFuncSetAttribute(l2_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_WORDS * 4));
+    }
+    const int32_t SLICE = SWEEP_SMEM_WORDS / SWEEP_WARPS;
     if (nc >= 64 && nc < ((int64_t)1 << 31) && maxSketch < (1 << 20)) {
       swKey.ensure((size_t)nc); swKey2.ensure((size_t)nc); swVal.ensure((size_t)nc); swOrder.ensure((size_t)nc);
       foreach(rt, nc, SweepKeyFn{cRead.p, sOf.p, sa.cand0, swKey.p, swVal.p});
@@ -915,11 +939,9 @@ struct Mapper {
           d2d(rt, swRedo.p, swOrder.p, sizeof(int32_t) * (size_t)firstFit);
           unsigned long long ff = (unsigned long long)firstFit; h2d(rt, scal.p, &ff, sizeof(ff));
         }
-        static bool attr = false;
-        if (!attr) { MM_CUDA(cudaFuncSetAttribute(l2_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_WARPS * SLICE * 4)); attr = true; }
         int grid = (nTiles + SWEEP_WARPS - 1) / SWEEP_WARPS; if (grid > rt.sm_count) grid = rt.sm_count;
         l2_sweep_smem_kernel<<<grid, SWEEP_WARPS * 32, SWEEP_WARPS * SLICE * 4, rt.stream>>>(sa, swOrder.p, swTile.p, nTiles, swLocal.p,
-                                                                                             (unsigned int*)(scal.p + 1), swRedo.p, scal.p);
+                                                                                             (unsigned int*)(scal.p + 1), swRedo.p, scal.p, SLICE);
         MM_CUDA(cudaGetLastError());
         rt.launches++;
         unsigned long long nr = 0; d2h(rt, &nr, scal.p, sizeof(nr));
