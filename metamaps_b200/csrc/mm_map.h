@@ -231,10 +231,14 @@ __global__ void __launch_bounds__(256) l1_filter_gather_kernel(const int32_t* hi
     const int anySat = __syncthreads_or(saturated ? 1 : 0);      // absurdly deep pile-up: keep everything for this read
     // survivors = sum of the bins that reached minimumHits (no second pass over the position lists)
     unsigned int local = 0;
-    for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) {
-      const uint32_t w = bins[i], lo = w & 0xFFFFu, hi = w >> 16;
-      local += (anySat || lo >= (uint32_t)mh) ? lo : 0u;
-      local += (anySat || hi >= (uint32_t)mh) ? hi : 0u;
+    if (anySat) {              // counters wrapped: everything is kept, so the total is simply the read's hit count
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) local += (unsigned int)hitCnt[q];
+    } else {
+      for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) {
+        const uint32_t w = bins[i], lo = w & 0xFFFFu, hi = w >> 16;
+        local += (lo >= (uint32_t)mh) ? lo : 0u;
+        local += (hi >= (uint32_t)mh) ? hi : 0u;
+      }
     }
     if (local) atomicAdd(&smTotal, local);
     __syncthreads();
@@ -642,7 +646,10 @@ struct Mapper {
   MapStats st;
   int64_t evBudget = (int64_t)1 << 28;       // span elements classified per L2 pass (8 B each)
 
-  Mapper(Runtime& r, Prims& p, Sketcher& s) : rt(r), pr(p), sk(s) { memset(&st, 0, sizeof(st)); }
+  Mapper(Runtime& r, Prims& p, Sketcher& s) : rt(r), pr(p), sk(s) {
+    memset(&st, 0, sizeof(st));
+    if (const char* e = getenv("MM_EV_BUDGET")) { long long v = atoll(e); if (v > 0) evBudget = v; }   // tests: force several L2 passes
+  }
 
   void ensure_tables(int k, float pi, int smax) {
     if (smax < 16) smax = 16;

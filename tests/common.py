@@ -207,3 +207,32 @@ def check_pipeline_vs_reference_files(ctx, small, golden_dir):
         if c[0] == "definedGenomes" and c[1] in tidx:
             assert abs(float(c[4]) - em["f"][tidx[c[1]]]) <= 1e-6
     return out
+
+
+def fallback_workloads():
+    """Inputs that push the device fast paths into their fallbacks (each returns contigs, reads, k, w, min_len)."""
+    rng = np.random.default_rng(123)
+    out = {}
+    # (a) more contigs than the 32768 per-read contig bins of the filtered gather (bins are then hashed)
+    big = [rng.integers(0, 4, 30000, dtype=np.uint8) for _ in range(3)]
+    tiny = [rng.integers(0, 4, 40, dtype=np.uint8) for _ in range(33000)]
+    contigs = tiny[:20000] + [big[0]] + tiny[20000:] + big[1:]
+    db = synth.SynthDB([f"C{i}|kraken:taxid|{i}|x" for i in range(len(contigs))], [str(i) for i in range(len(contigs))], contigs)
+    sub = synth.SynthDB(["a", "b", "c"], ["1", "2", "3"], big)
+    _, reads, _ = synth.make_reads(sub, 7, 40, 2500, err=0.08)
+    out["many_contigs"] = ([synth.codes_to_ascii(c) for c in db.contig_codes], [synth.codes_to_ascii(r) for r in reads], 16, 8, 1000)
+    # (b) one very long read: sketch larger than a sweep slice / the classify staging buffer -> global-memory paths
+    g = rng.integers(0, 4, 900_000, dtype=np.uint8)
+    sub = synth.SynthDB(["g"], ["1"], [g])
+    _, rl, _ = synth.make_reads(sub, 9, 3, 600_000, err=0.05)
+    _, rs, _ = synth.make_reads(sub, 10, 20, 3000, err=0.08)
+    out["long_read"] = ([synth.codes_to_ascii(g)], [synth.codes_to_ascii(r) for r in rl + rs], 16, 5, 1000)
+    # (c) low-complexity read: a handful of distinct minimizers, so hundreds of reference-only hashes share one gap
+    #     (8-bit gap counters overflow -> the candidate is replayed with 16-bit counters in global memory)
+    unit = rng.integers(0, 4, 23, dtype=np.uint8)
+    rep = np.tile(unit, 400)                                   # 9.2 kb tandem repeat
+    flankL = rng.integers(0, 4, 20000, dtype=np.uint8); flankR = rng.integers(0, 4, 20000, dtype=np.uint8)
+    c0 = np.concatenate([flankL, rep, flankR])
+    reads = [np.concatenate([flankL[-1500:], rep[:3000]]), rep[100:5100].copy(), np.concatenate([rep[-2500:], flankR[:2500]])]
+    out["low_complexity"] = ([synth.codes_to_ascii(c0)], [synth.codes_to_ascii(r) for r in reads], 16, 6, 1000)
+    return out

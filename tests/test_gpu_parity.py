@@ -138,3 +138,20 @@ def test_cli_matches_golden_reference_files(small_workload):
     assert os.path.exists(build.HOST_BIN), "metamaps_b200/metamaps not built"
     got = cli_common.run_cli(build.HOST_BIN, small_workload["dir"], out="out_gpu")
     assert cli_common.compare_dirs(os.path.join(GOLDEN, "ref_small"), got) >= 8
+
+
+@pytest.mark.parametrize("name", ["many_contigs", "long_read", "low_complexity"])
+def test_fast_path_fallbacks(gpu_ctx, oracle, name):
+    """Hashed contig bins, sketches too large for shared memory, 8-bit counter overflow: same results as the oracle."""
+    contigs, reads, k, w, min_len = common.fallback_workloads()[name]
+    common.check_map_vs_oracle(gpu_ctx, oracle, contigs, reads, k, w, 80.0, min_len, batches=1)
+
+
+def test_multiple_l2_passes(oracle, small_workload, monkeypatch):
+    """A tiny event budget forces the L2 stage through several passes; results must not change."""
+    monkeypatch.setenv("MM_EV_BUDGET", "20000")
+    ctx = capi.Context(0)
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"]]
+    common.check_map_vs_oracle(ctx, oracle, contigs, reads, 16, 13)
+    ctx.close()

@@ -96,3 +96,9 @@ def test_api_errors(emu_ctx):
 def test_pipeline_matches_reference_files(emu_ctx, small_workload):
     from tests.conftest import GOLDEN
     common.check_pipeline_vs_reference_files(emu_ctx, small_workload, GOLDEN)
+
+
+@pytest.mark.parametrize("name", ["many_contigs", "low_complexity"])
+def test_fallback_workloads(emu_ctx, oracle, name):
+    contigs, reads, k, w, min_len = common.fallback_workloads()[name]
+    common.check_map_vs_oracle(emu_ctx, oracle, contigs, reads, k, w, 80.0, min_len, batches=1)
