@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--ref-contigs", type=int, default=12, help="reference arm: DB sample size in contigs")
     ap.add_argument("--ref-reads", type=int, default=1500, help="reference arm: reads in the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.reads:
@@ -273,6 +275,13 @@ def main():
 
     for _ in range(args.warmup):
         out = step_dev()
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_dev()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local); sampler.start()
     stats = {}
     gpu_ms = 0.0; launches = 0
