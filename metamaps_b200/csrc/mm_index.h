@@ -57,10 +57,12 @@ struct TableInsertFn {
 // reference's MinimizerMetaData::operator< (base_types.hpp:100-103; REV = -1 < FWD = 1)
 struct PosKeyFn {
   const uint32_t* sortedPos; const uint32_t* miWs; const int64_t* contigStart; int32_t n_contigs; uint64_t* posKey;
+  uint16_t* posSeq16;      // optional 2-byte copy of the contig id (the L1 contig filter streams this instead of posKey)
   MM_HD void operator()(int64_t e) const {
     uint32_t p = ldg(sortedPos + e);
     int64_t sq = upper_bound_idx(contigStart, (int64_t)n_contigs + 1, (int64_t)p) - 1;
     posKey[e] = ((uint64_t)sq << 32) | ldg(miWs + p);
+    if (posSeq16) posSeq16[e] = (uint16_t)sq;
   }
 };
 
@@ -98,6 +100,7 @@ struct Index {
   // lookup
   DevBuf<Slot> table; uint32_t tableMask = 0;
   DevBuf<uint64_t> posKey;
+  DevBuf<uint16_t> posSeq16; bool hasSeq16 = false;     // contig id of every CSR entry when n_contigs <= 65536
   int64_t n_unique = 0; int32_t freqThreshold = 0x7fffffff;
   // dups
   DevBuf<uint32_t> dupBits, dupIdx; DevBuf<uint64_t> dupLinks; int64_t n_dup = 0;
@@ -174,7 +177,9 @@ struct Index {
     uniq.release(); counts.release(); starts.release();
 
     posKey.ensure((size_t)n);
-    foreach(rt, n, PosKeyFn{sortedPos.p, miWs.p, contigStart.p, n_contigs, posKey.p});
+    hasSeq16 = n_contigs <= 65536;
+    if (hasSeq16) posSeq16.ensure((size_t)n + 8);
+    foreach(rt, n, PosKeyFn{sortedPos.p, miWs.p, contigStart.p, n_contigs, posKey.p, hasSeq16 ? posSeq16.p : nullptr});
 
     dupBits.ensure((size_t)(n / 32 + 2)); dev_memset(rt, dupBits.p, 0, sizeof(uint32_t) * (size_t)(n / 32 + 2));
     DevBuf<unsigned long long> cnt; cnt.ensure(1); dev_memset(rt, cnt.p, 0, sizeof(unsigned long long));
@@ -194,7 +199,7 @@ struct Index {
   }
 
   int64_t device_bytes() const {
-    return (int64_t)(miHash.bytes() + miWs.bytes() + table.bytes() + posKey.bytes() + dupBits.bytes() + dupIdx.bytes() +
+    return (int64_t)(miHash.bytes() + miWs.bytes() + table.bytes() + posKey.bytes() + posSeq16.bytes() + dupBits.bytes() + dupIdx.bytes() +
                      dupLinks.bytes() + contigStart.bytes() + contigLen.bytes());
   }
 };

@@ -26,7 +26,9 @@ namespace mm {
 // event code of one reference minimizer of a span: bit 31 = its hash is in the read sketch (idx = 1-based query rank),
 // else idx = gap (number of query hashes below it); bits 30/29 = its insertion / deletion does not change the window's
 // hash SET because another copy of the same hash is inside the window at that moment (SlideMapper keeps one entry per hash)
-static const uint32_t CODE_MATCH = 0x80000000u, CODE_INS_NOP = 0x40000000u, CODE_DEL_NOP = 0x20000000u, CODE_IDX = 0x1FFFFFFFu;
+static const uint32_t CODE_MATCH = 0x80000000u, CODE_INS_NOP = 0x40000000u, CODE_DEL_NOP = 0x20000000u, CODE_DUP = 0x10000000u, CODE_IDX = 0x0FFFFFFFu;
+// (CODE_DUP: the minimizer shares its hash with another one of the same contig; the banded sweep then consults the dup links
+//  when it has to rebuild its state from a window)
 // K5b state of one candidate: s+1 gap counters (cntBytes each) + s match bits + one spare word, in 32-bit words
 MM_HD int32_t sweep_cnt_words(int32_t s, int32_t cntBytes) { return ((s + 1) * cntBytes + 3) / 4; }
 MM_HD int32_t sweep_state_words(int32_t s, int32_t cntBytes) { return sweep_cnt_words(s, cntBytes) + (s + 31) / 32 + 1; }
@@ -262,6 +264,80 @@ __global__ void __launch_bounds__(256) l1_filter_gather_kernel(const int32_t* hi
 }
 #endif
 
+#ifndef MM_HOST_EMU
+// Same filter, streaming the index's 2-byte contig-id side array (Index::posSeq16) instead of the 8-byte position keys:
+// pass 1 reads the contig id of every hit once (a 7-entry list is 14 B, one sector), counts it into the bins and parks it in
+// a shared-memory cache at the hit's rank within the read (hitOff, the prefix sum of the per-query hit counts); pass 2
+// re-reads the ids from that cache and fetches the 8-byte position key of the survivors only.
+__global__ void __launch_bounds__(256) l1_filter_gather16_kernel(const int32_t* hitCnt, const int64_t* hitStart, const int64_t* hitOff, const int64_t* qOff,
+                                                                 const int32_t* sOf, const int32_t* minHitsTab, const uint16_t* posSeq16, const uint64_t* posKey,
+                                                                 HitKeyLayout lay, int32_t n_reads, uint32_t binMask, unsigned long long* cursor,
+                                                                 uint64_t* hitsOut, int32_t* keptPerRead, uint32_t cacheCap) {
+  extern __shared__ uint32_t bins[];            // (binMask+1)/2 words of 16-bit counters, then cacheCap 16-bit contig ids
+  uint16_t* cache = reinterpret_cast<uint16_t*>(bins + (binMask + 1) / 2);
+  __shared__ unsigned int smTotal, smPos; __shared__ unsigned long long smBase;
+  for (int32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+    const int32_t s = sOf[r];
+    const int64_t q0 = qOff[r], q1 = qOff[r + 1];
+    if (s == 0 || q1 <= q0) { if (threadIdx.x == 0) keptPerRead[r] = 0; continue; }
+    int32_t mh = minHitsTab[s]; if (mh < 1) mh = 1;
+    const int64_t h0 = hitOff[q0]; const int64_t nHits = hitOff[q1] - h0;
+    if (nHits == 0) { if (threadIdx.x == 0) keptPerRead[r] = 0; continue; }
+    const bool anySat = nHits >= 0xFFF0;        // a 16-bit bin could wrap: keep everything for this read
+    for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) bins[i] = 0;
+    if (threadIdx.x == 0) { smTotal = 0; smPos = 0; }
+    __syncthreads();
+    unsigned int local = 0;
+    if (!anySat) {
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const int32_t c = hitCnt[q];
+        if (!c) continue;
+        const int64_t st = hitStart[q]; const uint32_t base = (uint32_t)(hitOff[q] - h0);
+        for (int32_t j = 0; j < c; j++) {
+          const uint32_t sq = __ldg(posSeq16 + st + j);
+          if (base + j < cacheCap) cache[base + j] = (uint16_t)sq;
+          const uint32_t b = sq & binMask;
+          atomicAdd(&bins[b >> 1], (b & 1u) ? 0x10000u : 1u);
+        }
+      }
+      __syncthreads();
+      // survivors = sum of the bins that reached minimumHits
+      for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) {
+        const uint32_t w = bins[i], lo = w & 0xFFFFu, hi = w >> 16;
+        local += (lo >= (uint32_t)mh) ? lo : 0u;
+        local += (hi >= (uint32_t)mh) ? hi : 0u;
+      }
+    } else if (threadIdx.x == 0) local = (unsigned int)nHits;
+    if (local) atomicAdd(&smTotal, local);
+    __syncthreads();
+    if (threadIdx.x == 0) { smBase = atomicAdd(cursor, (unsigned long long)smTotal); keptPerRead[r] = (int32_t)smTotal; }
+    __syncthreads();
+    if (smTotal != 0) {
+      const uint64_t hi = (uint64_t)r << (lay.seqBits + lay.wsBits);
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const int32_t c = hitCnt[q];
+        if (!c) continue;
+        const int64_t st = hitStart[q]; const uint32_t base = (uint32_t)(hitOff[q] - h0);
+        for (int32_t j = 0; j < c; j++) {
+          bool keep = anySat;
+          if (!anySat) {
+            const uint32_t sq = (base + j < cacheCap) ? (uint32_t)cache[base + j] : (uint32_t)__ldg(posSeq16 + st + j);
+            const uint32_t b = sq & binMask;
+            keep = ((bins[b >> 1] >> ((b & 1u) * 16)) & 0xFFFFu) >= (uint32_t)mh;
+          }
+          if (keep) {
+            const uint64_t pk = __ldg(posKey + st + j);
+            const unsigned int p = atomicAdd(&smPos, 1u);
+            hitsOut[smBase + p] = hi | ((pk >> 32) << lay.wsBits) | (pk & 0xFFFFFFFFull);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+#endif
+
 // computeL1CandidateRegions (computeMap.hpp:346-386), one item per sorted hit:
 //   hit i opens a candidate iff hits i and i+minimumHits-1 lie on the same contig less than a read length apart;
 //   consecutive such candidates are merged while prev.end >= start (ends are non-decreasing, so "prev" is simply
@@ -402,35 +478,52 @@ struct L2ClassifyFn {
     while (lo < hi) { int32_t m = (lo + hi) >> 1; if (ldg(q + m) < h) lo = m + 1; else hi = m; }
     uint32_t code = (lo < s && ldg(q + lo) == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
     if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u)
-      code |= dup_event_flags(miWs, dupIdx, dupLinks, n_dup, j, ldg(beg0 + c), ldg(fe + c), ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1));
+      code |= CODE_DUP | dup_event_flags(miWs, dupIdx, dupLinks, n_dup, j, ldg(beg0 + c), ldg(fe + c), ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1));
     ev[t] = make_uint2(code, ldg(miWs + j));
   }
 };
 
 #ifndef MM_HOST_EMU
-// Device fast path of phase A: one CTA per candidate; the read sketch is staged in shared memory once and the span's
-// reference minimizers are classified with coalesced loads / stores (same codes as L2ClassifyFn).
-__global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a) {
+// Device fast path of phase A: each CTA takes a contiguous run of candidates (candidates are ordered by read, so the read
+// sketch staged in shared memory is reused by the read's other candidates).  Next to the sketch sits a 2048-bucket index
+// on the top 11 hash bits (first sketch rank of every bucket), so the rank search of a reference minimizer is a lookup
+// plus a short binary search inside one bucket instead of log2(s) steps.  Same codes as L2ClassifyFn.
+static const int CLS_BUCKET_BITS = 11, CLS_BUCKETS = 1 << CLS_BUCKET_BITS;
+__global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, int32_t perCta) {
   extern __shared__ uint32_t smq[];
-  for (int64_t ci = blockIdx.x; ci < a.nCand; ci += gridDim.x) {
+  __shared__ uint16_t bstart[CLS_BUCKETS + 2];
+  int32_t curRead = -1, s = 0;
+  const int64_t ciEnd = ((int64_t)blockIdx.x + 1) * perCta < a.nCand ? ((int64_t)blockIdx.x + 1) * perCta : a.nCand;
+  for (int64_t ci = (int64_t)blockIdx.x * perCta; ci < ciEnd; ci++) {
     const int64_t c = a.cand0 + ci;
-    const int32_t r = a.cRead[c], s = a.sOf[r];
-    const uint32_t* q = a.qHash + a.qOff[r];
-    for (int32_t i = threadIdx.x; i < s; i += blockDim.x) smq[i] = __ldg(q + i);
-    __syncthreads();
+    const int32_t r = a.cRead[c];
+    if (r != curRead) {
+      __syncthreads();                                   // everyone is done with the previous sketch
+      curRead = r; s = a.sOf[r];
+      const uint32_t* q = a.qHash + a.qOff[r];
+      for (int32_t i = threadIdx.x; i < s; i += blockDim.x) smq[i] = __ldg(q + i);
+      __syncthreads();
+      for (int32_t i = threadIdx.x; i <= s; i += blockDim.x) {      // bucket b starts at the first rank whose hash is in bucket >= b
+        const int32_t bPrev = i > 0 ? (int32_t)(smq[i - 1] >> (32 - CLS_BUCKET_BITS)) : -1;
+        const int32_t bCur = i < s ? (int32_t)(smq[i] >> (32 - CLS_BUCKET_BITS)) : CLS_BUCKETS;
+        for (int32_t bb = bPrev + 1; bb <= bCur; bb++) bstart[bb] = (uint16_t)i;
+      }
+      __syncthreads();
+    }
     const int64_t b0 = a.beg0[c];
     const int64_t e0 = a.evOff[c] - a.evBase; const int32_t n = (int32_t)(a.evOff[c + 1] - a.evOff[c]);
+    const int64_t fe = a.fe[c], le = a.le[c]; const int32_t cmw = a.readLen[r] - (a.w - 1) - (a.k - 1);
     for (int32_t t = threadIdx.x; t < n; t += blockDim.x) {
       const int64_t j = b0 + t;
       const uint32_t h = __ldg(a.miHash + j);
-      int32_t lo = 0, hi = s;
+      const uint32_t bk = h >> (32 - CLS_BUCKET_BITS);
+      int32_t lo = bstart[bk], hi = bstart[bk + 1];
       while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (smq[m] < h) lo = m + 1; else hi = m; }
       uint32_t code = (lo < s && smq[lo] == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
       if ((__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u)
-        code |= dup_event_flags(a.miWs, a.dupIdx, a.dupLinks, a.n_dup, j, b0, a.fe[c], a.le[c], a.readLen[r] - (a.w - 1) - (a.k - 1));
+        code |= CODE_DUP | dup_event_flags(a.miWs, a.dupIdx, a.dupLinks, a.n_dup, j, b0, fe, le, cmw);
       a.ev[e0 + t] = make_uint2(code, __ldg(a.miWs + j));
     }
-    __syncthreads();
   }
 }
 #endif
@@ -547,9 +640,12 @@ struct L2SweepFn {
     l2_sweep_one<CntT, false>(a, c, (CntT*)stp, stp + sweep_cnt_words(s, (int32_t)sizeof(CntT)));
   }
 };
-struct SweepKeyFn {     // sort key: descending sketch size (similar work inside a warp, longest first)
-  const int32_t* cRead; const int32_t* sOf; int64_t cand0; uint32_t* key; uint32_t* val;
-  MM_HD void operator()(int64_t ci) const { key[ci] = 0xFFFFFFFFu - (uint32_t)ldg(sOf + ldg(cRead + cand0 + ci)); val[ci] = (uint32_t)ci; }
+struct SweepKeyFn {     // sort key: descending span length (spanN given) or sketch size: similar work inside a warp, longest first
+  const int32_t* cRead; const int32_t* sOf; const int32_t* spanN; int64_t cand0; uint32_t* key; uint32_t* val;
+  MM_HD void operator()(int64_t ci) const {
+    const uint32_t v = spanN ? (uint32_t)ldg(spanN + cand0 + ci) : (uint32_t)ldg(sOf + ldg(cRead + cand0 + ci));
+    key[ci] = 0xFFFFFFFFu - v; val[ci] = (uint32_t)ci;
+  }
 };
 
 #ifndef MM_HOST_EMU
@@ -586,12 +682,349 @@ __global__ void __launch_bounds__(SWEEP_WARPS_MAX * 32) l2_sweep_smem_kernel(L2S
 }
 #endif
 
+
+// ---- banded sweep ---------------------------------------------------------------------------------------------------
+// The state of SlideMapper at any moment is a function of the window's CONTENT alone:
+//     istar = max{ i : i + #{distinct W-only hashes with gap < i} <= s },   shared = #{ matches with rank <= istar }
+// and one event moves istar by at most one.  So the sweep only ever consults the gap counters / match bits next to istar.
+// l2_sweep_band keeps them for a BAND of BW consecutive gaps [lo, lo+BW) around istar; W-only events below the band
+// only move C (the number of W-only hashes below q_istar), matches below it only move `shared`, events above it are
+// ignored.  When istar reaches the edge of the band the state is REBUILT from the window's events around the new istar
+// (two simple scans of the ~s events currently in the window).  The first window is built the same way, after a
+// 64-bin histogram of the gap indices has located istar.  Per-candidate state: BW + BW/8 + 8 bytes whatever the sketch
+// size (the full-state sweep above needs s + s/8), which is what lets 3-4x more candidates be resident per SM.
+//
+// The loop applies ONE event per iteration (the reference's step "delete prev_beg, insert prev_end, evaluate" becomes
+// delete -> [insert] -> evaluate, with the evaluation skipped between the two halves of a step that does both).
+// Events come through an EvSrc: DirectEv reads the global array (host emulation, tests); RingEv (device) streams both
+// event cursors through per-lane shared-memory rings filled by cp.async, several iterations ahead of their use.
+MM_HD int32_t band_bins(int32_t BW) { return BW >= 128 ? 64 : BW / 2; }
+struct DirectEv {
+  const uint2* e;
+  MM_HD void init(int32_t, int32_t) {}
+  MM_HD uint2 fetch(int32_t /*stream: 0 = beg cursor, 1 = end cursor*/, int32_t j) { return ldg(e + j); }
+};
+
+template <class Ev>
+struct BandSweep {
+  const L2SweepArgs& a; const uint2* e; Ev& ev;
+  uint8_t* cnt; uint32_t* mb; int32_t BW;                  // cnt[BW+1], mb[BW/32+1]: the last entries are write-only dummies
+  int64_t b0; int32_t s, sh, lo, istar, C, shared; bool fail, bad;
+
+  MM_HD uint32_t bit(int32_t rel) const { return (mb[rel >> 5] >> (rel & 31)) & 1u; }
+  // element j of the span counts for a window starting at `beg` iff no earlier copy of its hash is inside that window
+  MM_HD bool first_copy(uint32_t code, int32_t j, int32_t beg) const {
+    if (!(code & CODE_DUP)) return true;
+    const uint64_t l = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0 + j);
+    const int64_t pd = (int64_t)(l >> 32);
+    return !(pd && (int64_t)j - pd >= (int64_t)beg);
+  }
+  // State of the window [beg, end) with the band placed around `center` (center < 0: locate istar first with a coarse
+  // histogram of the gap indices).  Sets `bad` when istar turns out to lie outside the band (only possible when the
+  // caller guessed the center).  Event codes are fetched eight at a time so that the loads overlap.
+  MM_HD void rebuild(int32_t beg, int32_t end, int32_t center, int32_t bias) {
+    bad = false;
+    const uint32_t SKIP = (uint32_t)s;                       // "W-only hash in gap s": ignored everywhere
+    if (center < 0) {
+      uint16_t* H = reinterpret_cast<uint16_t*>(cnt);       // NB coarse bins of 2^sh gaps (2*NB bytes <= BW)
+      const int32_t NB = band_bins(BW);
+      for (int32_t b = 0; b < NB; b++) H[b] = 0;
+      for (int32_t j0 = beg; j0 < end; j0 += 8) {
+        uint32_t cd[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) cd[u] = (j0 + u < end) ? ldg(&e[j0 + u].x) : SKIP;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const uint32_t code = cd[u];
+          if ((code & CODE_MATCH) || !first_copy(code, j0 + u, beg)) continue;
+          const int32_t g = (int32_t)(code & CODE_IDX);
+          if (g < s) H[g >> sh]++;
+        }
+      }
+      int32_t acc = 0, bb = 0;
+      for (int32_t b = 0; b < NB; b++) {                     // F(b << sh) = (b << sh) + #{gaps below}: increasing in b
+        const int32_t ib = b << sh;
+        if (ib > s || ib + acc > s) break;
+        bb = b; acc += (int32_t)H[b];
+      }
+      center = (bb << sh) + (1 << sh) / 2; bias = 0;
+    }
+    int32_t l0 = center - BW / 2 + bias;
+    if (l0 > s + 1 - BW) l0 = s + 1 - BW;
+    if (l0 < 0) l0 = 0;
+    lo = l0;
+    for (int32_t i = 0; i < (BW + 4) / 4; i++) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
+    for (int32_t i = 0; i <= BW / 32; i++) mb[i] = 0;
+    int32_t Cb = 0, Sb = 0;
+    for (int32_t j0 = beg; j0 < end; j0 += 8) {
+      uint32_t cd[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) cd[u] = (j0 + u < end) ? ldg(&e[j0 + u].x) : SKIP;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t code = cd[u];
+        const bool cntd = first_copy(code, j0 + u, beg);
+        const int32_t isM = (int32_t)(code >> 31), idx = (int32_t)(code & CODE_IDX);
+        const int32_t rel = idx - isM - lo;                  // match of rank idx -> bit idx-1; W-only hash -> gap idx
+        const bool below = cntd && rel < 0;
+        Sb += (below && isM) ? 1 : 0; Cb += (below && !isM) ? 1 : 0;
+        const bool inb = cntd && (uint32_t)rel < (uint32_t)BW;
+        // straight-line: the update that does not apply lands in the dummy slot
+        const int32_t cslot = (inb && !isM && idx < s) ? rel : BW;
+        const uint32_t v = cnt[cslot];
+        if (cslot != BW && v == 255) fail = true;
+        cnt[cslot] = (uint8_t)(v + 1);
+        const int32_t mslot = (inb && isM) ? rel : BW;
+        mb[mslot >> 5] |= 1u << (mslot & 31);
+      }
+    }
+    int32_t i = lo; C = Cb; shared = Sb;
+    if (lo > 0 && lo + Cb > s) bad = true;                   // istar is below the band
+    while (i < s && i - lo < BW && i + 1 + C + (int32_t)cnt[i - lo] <= s) { C += (int32_t)cnt[i - lo]; i++; shared += (int32_t)bit(i - 1 - lo); }
+    if (i < s && i - lo >= BW) bad = true;                   // istar is above the band
+    istar = i;
+  }
+  // one insertion (isDel = 0) or deletion (isDel = 1) of the reference minimizer with event code `code`
+  // (SlideMapper::insert_ref / delete_ref, slidingMap.hpp:139-219).  Straight-line: an update that does not apply
+  // lands in the dummy slots.  An insertion can push q_istar out of the bottom-s, a deletion can let q_{istar+1} in;
+  // both consult one gap counter and one match bit: rank istar-1 for the insertion, rank istar for the deletion.
+  MM_HD void apply(uint32_t code, int32_t isDel) {
+    const bool live = (code & (isDel ? CODE_DEL_NOP : CODE_INS_NOP)) == 0;
+    const bool isM = (int32_t)code < 0;
+    const int32_t idx = (int32_t)(code & CODE_IDX);
+    const int32_t d = 1 - 2 * isDel;
+    const bool gv = live && !isM && idx < s;                 // a W-only hash in gap idx
+    const uint32_t grel = (uint32_t)(idx - lo);
+    const bool gin = gv && grel < (uint32_t)BW;
+    const int32_t gslot = gin ? (int32_t)grel : BW;
+    const int32_t v = (int32_t)cnt[gslot];
+    if (gin && !isDel && v == 255) fail = true;
+    cnt[gslot] = (uint8_t)(v + d);
+    const bool below = gv && idx < istar;
+    C += below ? d : 0;
+    int32_t t = istar - 1 + isDel; t = t < 0 ? 0 : t;
+    const int32_t trel = t - lo;                             // inside the band by the out_of_band() invariant
+    const int32_t cX = (int32_t)cnt[trel];                   // after the update above (the gap may be the consulted one)
+    const int32_t mX = (int32_t)bit(trel);
+    const bool move = isDel ? (gv && istar < s && istar + 1 + C + cX <= s) : (below && istar + C > s);
+    C -= move ? d * cX : 0; shared -= move ? d * mX : 0; istar -= move ? d : 0;
+    const bool mv = live && isM;                             // a hash of the read sketch, rank idx
+    const int32_t mrel = idx - 1 - lo;
+    const bool min_ = mv && (uint32_t)mrel < (uint32_t)BW;
+    const int32_t mslot = min_ ? mrel : BW;
+    const uint32_t mbit = 1u << (mslot & 31);
+    const uint32_t word = mb[mslot >> 5];
+    mb[mslot >> 5] = isDel ? (word & ~mbit) : (word | mbit);
+    shared += (mv && (mrel < 0 || (min_ && idx <= istar))) ? d : 0;
+  }
+  MM_HD bool out_of_band() const { return (istar <= lo && lo > 0) || (istar >= lo + BW - 1 && lo + BW <= s); }
+};
+
+// Result of one SEGMENT of a candidate's sweep.  Because the state is a function of the window alone, a long candidate
+// is cut into segments by the window's first element ("beg" in [B0, B1)); every segment rebuilds its first window and
+// sweeps on its own, and L2BandMergeFn combines them: the optimum is the FIRST window with the maximal count, the
+// reported last position the LAST window with that count (computeMap.hpp:510-533), whichever segments they fall in.
+struct BandPart { int32_t shared, bpos, lpos, optS, optE, istar, any, fail; };
+static const int BAND_SEG_DEFAULT = 2048;
+
+// one segment; cnt: BW+1 (+3 pad) bytes, mb: BW/32+1 words.  part.fail: the candidate must go through the full-state
+// sweep instead (sketch too large for the band, a gap counter passing 255, a span beyond 65534 elements).
+template <class Ev>
+MM_HD void l2_sweep_band(const L2SweepArgs& a, int64_t c, int32_t B0, int32_t B1, uint8_t* cnt, uint32_t* mb, int32_t BW, Ev& ev, BandPart& out) {
+  const int32_t r = ldg(a.cRead + c), s = ldg(a.sOf + r), len = ldg(a.readLen + r);
+  const int64_t b0 = ldg(a.beg0 + c);
+  const uint2* e = a.ev + (ldg(a.evOff + c) - a.evBase);
+  const int32_t last = (int32_t)(ldg(a.le + c) - b0);
+  const int32_t cmw = len - (a.w - 1) - (a.k - 1);
+  out.shared = 0; out.bpos = 0; out.lpos = 0; out.optS = 0; out.optE = 0; out.istar = s; out.any = 0; out.fail = 1;
+  int32_t sh = 0; while ((band_bins(BW) << sh) < s + 1) sh++;
+  if ((2 << sh) > BW && s + 1 > BW) return;                  // a coarse bin must fit the band with margins
+  if (last >= 65535) return;
+  out.fail = 0;
+  // The window whose first element is B0, after every event of that step: all elements below wpos[B0] + cmw are inside
+  // (for B0 = 0 this is the reference's first window, computeMap.hpp:465-480).
+  int32_t beg = B0, end;
+  if (B0 == 0) end = (int32_t)(ldg(a.fe + c) - b0);
+  else {
+    if (B0 >= last) return;
+    const int32_t lim = (int32_t)(ldg(&e[B0].y) >> 1) + cmw;
+    int32_t l = B0, h = last;
+    while (l < h) { const int32_t m = (l + h) >> 1; if ((int32_t)(ldg(&e[m].y) >> 1) < lim) l = m + 1; else h = m; }
+    end = l;
+  }
+  if (end >= last) return;                                   // the reference's loop is over before this window is evaluated
+  BandSweep<Ev> z{a, e, ev, cnt, mb, BW, b0, s, sh, 0, 0, 0, 0, false, false};
+  // slidemap.insert_ref(sw_beg, sw_end) (computeMap.hpp:488).  With every window minimizer W-only, F(i) ~ i*(1 + nW/s):
+  // try the band around that istar first (one scan); if the guess misses, locate istar with the histogram (two scans).
+  z.rebuild(beg, end, (int32_t)(((int64_t)s * s) / (s + (end - beg) + 1)), 0);
+  if (z.bad || z.out_of_band()) z.rebuild(beg, end, -1, 0);
+  if (z.fail || z.bad) { out.fail = 1; return; }
+  int32_t best = 0, bpos = 0, lpos = 0, bistar = s, optS = 0, optE = 0, any = 0;
+  ev.init(beg + 1, end);
+  uint2 evBeg = ldg(e + beg), evBeg1 = ev.fetch(0, beg + 1), evEnd = ev.fetch(1, end);
+  int32_t sw_pos = (int32_t)(evBeg.y >> 1);
+  bool doEval = true;
+  while (end < last && beg < B1) {
+    if (doEval) {
+      const int32_t wb = (int32_t)(evBeg.y >> 1);
+      const bool better = z.shared > best;
+      lpos = (z.shared >= best) ? wb : lpos;
+      if (better) { best = z.shared; optS = beg; optE = end; bpos = wb; bistar = z.istar; }
+      any = 1;
+    }
+    const int32_t nb = (int32_t)(evBeg1.y >> 1) - sw_pos;    // MIIteratorL2::next (MIIteratorL2.hpp:74-96)
+    const int32_t ne = (int32_t)(evEnd.y >> 1) - (sw_pos + cmw - 1);
+    const int32_t isDel = nb <= ne ? 1 : 0;
+    doEval = nb != ne;                                        // a step that deletes AND inserts is evaluated after the insert
+    sw_pos += isDel ? nb : ne;
+    z.apply(isDel ? evBeg.x : evEnd.x, isDel);
+    beg += isDel; end += 1 - isDel;
+    const uint2 nx = ev.fetch(1 - isDel, isDel ? beg + 1 : end);
+    evBeg = isDel ? evBeg1 : evBeg; evBeg1 = isDel ? nx : evBeg1; evEnd = isDel ? evEnd : nx;
+    if (z.out_of_band() || z.fail) {
+      if (z.fail) break;
+      z.rebuild(beg, end, z.istar, z.istar <= z.lo ? -BW / 4 : BW / 4);   // keep drifting room on the side it left
+      if (z.bad) { z.fail = true; break; }
+    }
+  }
+  out.shared = best; out.bpos = bpos; out.lpos = lpos; out.optS = optS; out.optE = optE; out.istar = bistar; out.any = any; out.fail = z.fail ? 1 : 0;
+}
+MM_HD int32_t band_state_words(int32_t BW) { return (BW + 4) / 4 + BW / 32 + 1; }
+
+// work items: candidate ci of the pass has max(1, ceil(span / seg)) segments; itemOff = prefix sum over the pass
+struct BandItemFn {         // item -> (candidate, segment) + sort key (descending work)
+  const int64_t* itemOff; int64_t nCand; const int32_t* spanN; const int64_t* beg0; const int64_t* fe; int64_t cand0; int32_t seg;
+  uint32_t* key; uint32_t* val; int32_t* itemCand; int32_t* itemSeg;
+  MM_HD void operator()(int64_t i) const {
+    const int64_t ci = upper_bound_idx(itemOff, nCand + 1, i) - 1;
+    const int32_t sg = (int32_t)(i - ldg(itemOff + ci));
+    const int64_t c = cand0 + ci;
+    itemCand[i] = (int32_t)ci; itemSeg[i] = sg;
+    int32_t span = ldg(spanN + c), rest = span - sg * seg; if (rest > seg) rest = seg; if (rest < 0) rest = 0;
+    const int32_t win = (int32_t)(ldg(fe + c) - ldg(beg0 + c));
+    key[i] = 0xFFFFFFFFu - (uint32_t)(2 * rest + win / 4); val[i] = (uint32_t)i;
+  }
+};
+struct L2BandMergeFn {      // candidate ci: combine its segments (in time order) into the final outputs
+  L2SweepArgs a; const BandPart* parts; const int64_t* itemOff; int32_t* redo; unsigned long long* redoCount;
+  MM_HD void operator()(int64_t ci) const {
+    const int64_t c = a.cand0 + ci;
+    const int32_t s = ldg(a.sOf + ldg(a.cRead + c));
+    const int64_t b0 = ldg(a.beg0 + c);
+    int32_t best = 0, bpos = 0, lpos = 0, valid = 0, bistar = s, optS = 0, optE = 0, fail = 0;
+    for (int64_t i = ldg(itemOff + ci); i < ldg(itemOff + ci + 1); i++) {
+      const BandPart p = parts[i];
+      fail |= p.fail;
+      if (!p.any) continue;
+      if (p.shared > best) { best = p.shared; bpos = p.bpos; optS = p.optS; optE = p.optE; bistar = p.istar; valid = 1; }
+      if (p.shared >= best) lpos = p.lpos;
+    }
+    if (fail) { unsigned long long slot = atomic_add_u64(redoCount, 1ull); redo[slot] = (int32_t)ci; return; }
+    a.oShared[c] = best; a.oPos[c] = (bpos + lpos) / 2; a.oValid[c] = valid; a.oOptS[c] = b0 + optS; a.oOptE[c] = b0 + optE; a.oIstar[c] = bistar;
+  }
+};
+
+// global-memory band state (host emulation and tests): item i of the pass
+struct L2SweepBandFn {
+  L2SweepArgs a; uint32_t* state; int32_t BW; int32_t seg; const int32_t* itemCand; const int32_t* itemSeg; BandPart* parts;
+  MM_HD void operator()(int64_t i) const {
+    const int64_t c = a.cand0 + ldg(itemCand + i);
+    const int32_t sg = ldg(itemSeg + i);
+    uint32_t* stp = state + i * band_state_words(BW);
+    DirectEv ev{a.ev + (ldg(a.evOff + c) - a.evBase)};
+    BandPart p;
+    l2_sweep_band(a, c, sg * seg, (sg + 1) * seg, (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
+    parts[i] = p;
+  }
+};
+
+#ifndef MM_HOST_EMU
+// Device event source: two per-lane rings of R 16-byte pairs (2 events each) in shared memory, laid out [stream][pair][lane].
+// A pair is refilled by cp.async the moment the cursor leaves it, i.e. 2R-2 events ahead of its use.
+template <int R>
+struct RingEv {
+  const uint2* gbase;       // candidate's events, rounded down to a 16-byte boundary
+  int32_t par;              // 0/1: the candidate's first event is the second half of its pair
+  uint32_t sb;              // shared-memory byte address of this lane's slot 0 of stream 0
+  MM_DEV RingEv(const uint2* evArray, int64_t off, uint4* ring) : gbase(evArray + (off & ~(int64_t)1)), par((int32_t)(off & 1)), sb((uint32_t)__cvta_generic_to_shared(ring)) {}
+  MM_DEV void load_pair(int32_t stream, int32_t pair) {
+    const uint32_t dst = sb + (uint32_t)((stream * R + (pair & (R - 1))) * 512);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gbase + 2 * (int64_t)pair) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  MM_DEV void init(int32_t jb, int32_t je) {
+    const int32_t pb = (jb + par) >> 1, pe = (je + par) >> 1;
+#pragma unroll
+    for (int i = 0; i < R; i++) load_pair(0, pb + i);
+#pragma unroll
+    for (int i = 0; i < R; i++) load_pair(1, pe + i);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  // the frontier of a stream moved to element j (one past the previous one)
+  MM_DEV uint2 fetch(int32_t stream, int32_t j) {
+    const int32_t jj = j + par;
+    if ((jj & 1) == 0) {                      // entered a new pair: the one behind it is dead, reuse its slot
+      load_pair(stream, (jj >> 1) + R - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(R - 1) : "memory");
+    }
+    const uint32_t addr = sb + (uint32_t)((stream * R + ((jj >> 1) & (R - 1))) * 512 + (jj & 1) * 8);
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+  }
+};
+
+// Each warp owns WARP_WORDS of shared memory (32 band states + the rings) and pulls tiles of 32 consecutive work items
+// of `order` (descending work: lanes of a tile run loops of similar length) from a global counter.
+template <int BW, int R>
+__global__ void __launch_bounds__(512, 1) l2_sweep_band_kernel(L2SweepArgs a, const uint32_t* order, int64_t nItems, const int32_t* itemCand,
+                                                               const int32_t* itemSeg, int32_t seg, BandPart* parts, unsigned int* tileCounter) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  constexpr int ST = ((BW + 4) / 4 + BW / 32 + 1) | 1;       // odd word count: lanes start on different banks
+  constexpr int WARP_WORDS = 2 * R * 32 * 4 + 32 * ST;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t* wbase = sm + (size_t)wid * WARP_WORDS;
+  uint4* ring = reinterpret_cast<uint4*>(wbase) + lane;
+  uint32_t* my = wbase + 2 * R * 32 * 4 + lane * ST;
+  const int64_t nTiles = (nItems + 31) / 32;
+  for (;;) {
+    int64_t tile = 0;
+    if (lane == 0) tile = (int64_t)atomicAdd(tileCounter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= nTiles) break;
+    const int64_t t = tile * 32 + lane;
+    if (t < nItems) {
+      const int64_t i = (int64_t)order[t];
+      const int64_t c = a.cand0 + itemCand[i];
+      const int32_t sg = itemSeg[i];
+      RingEv<R> ev(a.ev, a.evOff[c] - a.evBase, ring);
+      BandPart p;
+      l2_sweep_band(a, c, sg * seg, (sg + 1) * seg, (uint8_t*)my, my + (BW + 4) / 4, BW, ev, p);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      parts[i] = p;
+    }
+    __syncwarp();
+  }
+}
+#endif
+
 // phase C: strand vote of the optimal window (computeMap.hpp:431-438, slidingMap.hpp:232-254)
 struct L2StrandFn {
   const uint2* ev; const int64_t* evOff; int64_t evBase; int64_t cand0; const int64_t* beg0;
   const int32_t* cRead; const int64_t* qOff; const uint8_t* qStrand;
   const uint32_t* dupIdx; const uint64_t* dupLinks; int64_t n_dup; const uint32_t* dupBits;
   const int32_t* oValid; const int64_t* oOptS; const int64_t* oOptE; const int32_t* oIstar; int32_t* oVotes;
+  // contribution of index position j to the vote of a window [.., b) whose bottom-s holds query ranks <= istar
+  MM_HD int32_t vote_of(const uint2* e, const uint8_t* qs, int64_t j, int64_t b, int32_t istar) const {
+    uint2 v = e[j];
+    if (!(v.x & CODE_MATCH)) return 0;
+    int32_t i = (int32_t)(v.x & CODE_IDX);
+    if (i > istar) return 0;
+    // the map keeps the strand of the LAST inserted occurrence of a hash
+    if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u) { uint64_t l = dup_links(dupIdx, dupLinks, n_dup, j); uint32_t nd = (uint32_t)l; if (nd && j + (int64_t)nd < b) return 0; }
+    int32_t sq = ldg(qs + i - 1) ? 1 : -1, sr = (v.y & 1u) ? 1 : -1;
+    return sq * sr;
+  }
   MM_HD void operator()(int64_t ci) const {
     int64_t c = cand0 + ci;
     int32_t votes = 0;
@@ -599,20 +1032,31 @@ struct L2StrandFn {
       const uint2* e = ev + (ldg(evOff + c) - evBase) - ldg(beg0 + c);
       const uint8_t* qs = qStrand + ldg(qOff + ldg(cRead + c));
       int64_t a = ldg(oOptS + c), b = ldg(oOptE + c); int32_t istar = ldg(oIstar + c);
-      for (int64_t j = a; j < b; j++) {
-        uint2 v = e[j];
-        if (!(v.x & CODE_MATCH)) continue;
-        int32_t i = (int32_t)(v.x & CODE_IDX);
-        if (i > istar) continue;
-        // the map keeps the strand of the LAST inserted occurrence of a hash
-        if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u) { uint64_t l = dup_links(dupIdx, dupLinks, n_dup, j); uint32_t nd = (uint32_t)l; if (nd && j + (int64_t)nd < b) continue; }
-        int32_t sq = ldg(qs + i - 1) ? 1 : -1, sr = (v.y & 1u) ? 1 : -1;
-        votes += sq * sr;
-      }
+      for (int64_t j = a; j < b; j++) votes += vote_of(e, qs, j, b, istar);
     }
     oVotes[c] = votes;
   }
 };
+#ifndef MM_HOST_EMU
+// Device fast path of phase C: one warp per candidate, lanes stride over the optimal window (coalesced 8-byte events).
+__global__ void __launch_bounds__(256) l2_strand_warp_kernel(L2StrandFn f, int64_t nc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t ci = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < nc; ci += nw) {
+    const int64_t c = f.cand0 + ci;
+    int32_t votes = 0;
+    if (f.oValid[c]) {
+      const uint2* e = f.ev + (f.evOff[c] - f.evBase) - f.beg0[c];
+      const uint8_t* qs = f.qStrand + f.qOff[f.cRead[c]];
+      const int64_t a = f.oOptS[c], b = f.oOptE[c]; const int32_t istar = f.oIstar[c];
+      for (int64_t j = a + lane; j < b; j += 32) votes += f.vote_of(e, qs, j, b, istar);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) votes += __shfl_xor_sync(0xffffffffu, votes, o);
+    if (lane == 0) f.oVotes[c] = votes;
+  }
+}
+#endif
 struct AcceptFn {           // computeMap.hpp:415 through the per-s threshold table
   const int32_t* cRead; const int32_t* sOf; const int32_t* acceptTab; const int32_t* oShared; const int32_t* oValid;
   int32_t* oAccept; int32_t* readMapped;
@@ -644,11 +1088,18 @@ struct Mapper {
   std::vector<uint32_t> hk; std::vector<int32_t> tileStartH, localOffH;
   std::vector<int32_t> h_effLen;
   MapStats st;
-  int64_t evBudget = (int64_t)1 << 28;       // span elements classified per L2 pass (8 B each)
+  int sweepBand = 256, sweepRing = 8, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT;
+  DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemSeg; DevBuf<BandPart> bandParts; std::vector<int64_t> hItemOff, hEvSpan;
+  int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
   Mapper(Runtime& r, Prims& p, Sketcher& s) : rt(r), pr(p), sk(s) {
     memset(&st, 0, sizeof(st));
     if (const char* e = getenv("MM_EV_BUDGET")) { long long v = atoll(e); if (v > 0) evBudget = v; }   // tests: force several L2 passes
+    // K5b variants (tests and A/B measurements): band width, event-ring depth, and which sweep runs first
+    if (const char* e = getenv("MM_SWEEP_BAND")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) sweepBand = v; }
+    if (const char* e = getenv("MM_SWEEP_RING")) { int v = atoi(e); if (v == 4 || v == 8) sweepRing = v; }
+    if (const char* e = getenv("MM_SWEEP_SEG")) { int v = atoi(e); if (v >= 64) sweepSeg = v; }
+    if (const char* e = getenv("MM_SWEEP")) sweepMode = !strcmp(e, "full") ? 1 : !strcmp(e, "global") ? 2 : 0;
   }
 
   void ensure_tables(int k, float pi, int smax) {
@@ -769,9 +1220,22 @@ struct Mapper {
         dev_memset(rt, scal.p, 0, sizeof(unsigned long long));
         static bool attrF = false;
         if (!attrF) { MM_CUDA(cudaFuncSetAttribute(l1_filter_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); attrF = true; }
-        int grid = n_reads < rt.sm_count * 8 ? n_reads : rt.sm_count * 8;
-        l1_filter_gather_kernel<<<grid, 256, binsN * 2, rt.stream>>>(hitCnt.p, hitStart.p, qOff.p, sOf.p, dMinHits.p, ix.posKey.p, lay, n_reads, binsN - 1,
-                                                                     scal.p, hits.p, keptPerRead.p);
+        const char* lf = getenv("MM_L1_FILTER"); const bool legacy = lf && !strcmp(lf, "legacy");
+        if (ix.hasSeq16 && !legacy) {
+          static bool attrG = false;
+          if (!attrG) { MM_CUDA(cudaFuncSetAttribute(l1_filter_gather16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attrG = true; }
+          static int cacheCap = 0;
+          if (!cacheCap) { const char* e = getenv("MM_L1_CACHE"); cacheCap = e ? atoi(e) : 12288; if (cacheCap < 0 || cacheCap > 14336) cacheCap = 12288; }
+          size_t smem = (size_t)binsN * 2 + (size_t)cacheCap * 2;
+          int perSm = (int)((220 * 1024) / (smem + 1024)); if (perSm > 8) perSm = 8; if (perSm < 1) perSm = 1;
+          int grid = n_reads < rt.sm_count * perSm ? n_reads : rt.sm_count * perSm;
+          l1_filter_gather16_kernel<<<grid, 256, smem, rt.stream>>>(hitCnt.p, hitStart.p, hitOff.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p, ix.posKey.p, lay, n_reads,
+                                                                    binsN - 1, scal.p, hits.p, keptPerRead.p, (uint32_t)cacheCap);
+        } else {
+          int grid = n_reads < rt.sm_count * 8 ? n_reads : rt.sm_count * 8;
+          l1_filter_gather_kernel<<<grid, 256, binsN * 2, rt.stream>>>(hitCnt.p, hitStart.p, qOff.p, sOf.p, dMinHits.p, ix.posKey.p, lay, n_reads, binsN - 1,
+                                                                       scal.p, hits.p, keptPerRead.p);
+        }
         MM_CUDA(cudaGetLastError());
         rt.launches++;
         unsigned long long kept = 0; d2h(rt, &kept, scal.p, sizeof(kept));
@@ -829,7 +1293,7 @@ struct Mapper {
                                            beg0.p, fe.p, le.p, spanN.p, n_cand});
         pr.exclusive_sum<int32_t, int64_t>(spanN.p, evOff.p, n_cand + 1);
       }
-      std::vector<int64_t> hEv((size_t)n_cand + 1);
+      std::vector<int64_t>& hEv = hEvSpan; hEv.resize((size_t)n_cand + 1);
       d2h(rt, hEv.data(), evOff.p, sizeof(int64_t) * hEv.size());
       totalEv = hEv[(size_t)n_cand];
       // a gap counter never exceeds the number of minimizers in the span: 16 bits unless some span is huge
@@ -839,17 +1303,19 @@ struct Mapper {
         int64_t c1 = c0 + 1;
         while (c1 < n_cand && hEv[(size_t)c1 + 1] - hEv[(size_t)c0] <= evBudget) c1++;
         int64_t nEv = hEv[(size_t)c1] - hEv[(size_t)c0], nc = c1 - c0;
-        ev.ensure((size_t)nEv + 8);
+        ev.ensure((size_t)nEv + 64);      // the sweeps prefetch a few events past the end of a span
         {
           StageTimer t(rt, &st.ms[6]);
           L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p,
                           fe.p, le.p, readLen.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, k, w};
 #ifndef MM_HOST_EMU
-          if ((int64_t)maxSketch * 4 <= 200 * 1024) {
+          if ((int64_t)maxSketch * 4 <= 200 * 1024 && maxSketch < 65535) {      // bucket starts are 16-bit ranks
             static bool attrC = false;
             if (!attrC) { MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attrC = true; }
-            int64_t g = nc < (int64_t)rt.sm_count * 16 ? nc : (int64_t)rt.sm_count * 16;
-            l2_classify_smem_kernel<<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf);
+            // contiguous runs of candidates per CTA, ~8 waves of CTAs so that uneven runs average out
+            int64_t g = (int64_t)rt.sm_count * 64; if (g > nc) g = nc;
+            int32_t perCta = (int32_t)((nc + g - 1) / g); g = (nc + perCta - 1) / perCta;
+            l2_classify_smem_kernel<<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
             MM_CUDA(cudaGetLastError());
             rt.launches++;
           } else
@@ -870,8 +1336,18 @@ struct Mapper {
         }
         {
           StageTimer t(rt, &st.ms[8]);
-          foreach(rt, nc, L2StrandFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, cRead.p, qOff.p, qStrand.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, ix.dupBits.p,
-                                     oValid.p, oOptS.p, oOptE.p, oIstar.p, oVotes.p}, 128, 16);
+          L2StrandFn sf{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, cRead.p, qOff.p, qStrand.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, ix.dupBits.p,
+                        oValid.p, oOptS.p, oOptE.p, oIstar.p, oVotes.p};
+#ifndef MM_HOST_EMU
+          {
+            int64_t g = (nc + 7) / 8; if (g > (int64_t)rt.sm_count * 8) g = (int64_t)rt.sm_count * 8;
+            l2_strand_warp_kernel<<<(int)g, 256, 0, rt.stream>>>(sf, nc);
+            MM_CUDA(cudaGetLastError());
+            rt.launches++;
+          }
+#else
+          foreach(rt, nc, sf, 128, 16);
+#endif
         }
         c0 = c1;
       }
@@ -898,67 +1374,98 @@ struct Mapper {
     summary[0] = n_reads; summary[1] = nShort; summary[2] = n_cand; summary[3] = nMap; summary[4] = nReadsMapped; summary[5] = basesOk;
   }
 
-  // K5b over the candidates [sa.cand0, sa.cand0+nc) of one pass.  Returns how many were swept in shared memory.
+  // K5b over the candidates [sa.cand0, sa.cand0+nc) of one pass.  Returns how many were swept by the fast path.
+  //   device: banded sweep in shared memory (l2_sweep_band_kernel); MM_SWEEP=full selects the older full-state
+  //           shared-memory kernel instead, MM_SWEEP=global sends everything through the global-memory functor;
+  //   host emulation: the same banded logic with its state in global memory (L2SweepBandFn).
+  // Whatever a fast path declines (oversize sketches, counter overflow) goes through L2SweepFn (full state, global memory).
   int64_t sweep_pass(const L2SweepArgs& sa, int64_t nc, int32_t cntBytes) {
-    int64_t done_smem = 0;
+    int64_t done_fast = 0;
     const int32_t* redoList = nullptr; int64_t nRedo = nc;        // default: everything through the global-memory functor
-#ifndef MM_HOST_EMU
-    static int SWEEP_WARPS = 0;
-    if (!SWEEP_WARPS) {
-      const char* ev_ = getenv("MM_SWEEP_WARPS");
-      SWEEP_WARPS = ev_ ? atoi(ev_) : 8;
-      if (SWEEP_WARPS < 1 || SWEEP_WARPS > SWEEP_WARPS_MAX) SWEEP_WARPS = 8;
-      MM_CUDA(cudaFuncSetAttribute(l2_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_WORDS * 4));
-    }
-    const int32_t SLICE = SWEEP_SMEM_WORDS / SWEEP_WARPS;
-    if (nc >= 64 && nc < ((int64_t)1 << 31) && maxSketch < (1 << 20)) {
-      swKey.ensure((size_t)nc); swKey2.ensure((size_t)nc); swVal.ensure((size_t)nc); swOrder.ensure((size_t)nc);
-      foreach(rt, nc, SweepKeyFn{cRead.p, sOf.p, sa.cand0, swKey.p, swVal.p});
-      pr.sort_pairs<uint32_t, uint32_t>(swKey.p, swKey2.p, swVal.p, swOrder.p, nc, 20);
-      hk.resize((size_t)nc);
-      d2h(rt, hk.data(), swKey2.p, sizeof(uint32_t) * (size_t)nc);
-      // tiles over the descending-s order; candidates whose state does not fit a warp slice go to the global path
-      tileStartH.clear(); localOffH.assign((size_t)nc, 0);
-      int64_t firstFit = 0;
-      auto wordsOf = [](uint32_t s_) { return sweep_state_words((int32_t)s_, 1) | 1; };
-      while (firstFit < nc && wordsOf(0xFFFFFu - (hk[(size_t)firstFit] & 0xFFFFFu)) > SLICE) firstFit++;
-      int64_t i = firstFit;
-      while (i < nc) {
-        tileStartH.push_back((int32_t)i);
-        int32_t used = 0, cnt = 0;
-        while (i < nc && cnt < 32) {
-          int32_t wds = wordsOf(0xFFFFFu - (hk[(size_t)i] & 0xFFFFFu));
-          if (used + wds > SLICE) break;
-          localOffH[(size_t)i] = used; used += wds; cnt++; i++;
-        }
+    const int BAND = sweepBand, MODE = sweepMode;                 // MODE 0 band, 1 full-state smem, 2 global only
+    swRedo.ensure((size_t)nc + 1); scal.ensure(4);
+    if (MODE == 0 && nc > 0 && nc < ((int64_t)1 << 31) && maxSketch < (1 << 20)) {
+      // work items = segments of candidates (spans are known on the host: hEvSpan)
+      hItemOff.resize((size_t)nc + 1); hItemOff[0] = 0;
+      for (int64_t ci = 0; ci < nc; ci++) {
+        int64_t span = hEvSpan[(size_t)(sa.cand0 + ci) + 1] - hEvSpan[(size_t)(sa.cand0 + ci)];
+        int64_t ns = (span + sweepSeg - 1) / sweepSeg; if (ns < 1) ns = 1;
+        hItemOff[(size_t)ci + 1] = hItemOff[(size_t)ci] + ns;
       }
-      tileStartH.push_back((int32_t)nc);
-      int32_t nTiles = (int32_t)tileStartH.size() - 1;
-      swRedo.ensure((size_t)nc + 1); scal.ensure(4);
-      if (nTiles > 0) {
-        swTile.ensure(tileStartH.size()); swLocal.ensure((size_t)nc);
-        h2d(rt, swTile.p, tileStartH.data(), sizeof(int32_t) * tileStartH.size());
-        h2d(rt, swLocal.p, localOffH.data(), sizeof(int32_t) * (size_t)nc);
-        // scal[0] = redo count, scal[1] = tile counter.  Candidates that fit no slice (the first `firstFit` of the order)
-        // are pre-loaded into the redo list.
-        dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 2);
-        if (firstFit > 0) {
-          d2d(rt, swRedo.p, swOrder.p, sizeof(int32_t) * (size_t)firstFit);
-          unsigned long long ff = (unsigned long long)firstFit; h2d(rt, scal.p, &ff, sizeof(ff));
+      const int64_t nItems = hItemOff[(size_t)nc];
+      itemOff.ensure((size_t)nc + 1); h2d(rt, itemOff.p, hItemOff.data(), sizeof(int64_t) * ((size_t)nc + 1));
+      itemCand.ensure((size_t)nItems); itemSeg.ensure((size_t)nItems); bandParts.ensure((size_t)nItems);
+      swKey.ensure((size_t)nItems); swKey2.ensure((size_t)nItems); swVal.ensure((size_t)nItems); swOrder.ensure((size_t)nItems);
+      foreach(rt, nItems, BandItemFn{itemOff.p, nc, spanN.p, beg0.p, fe.p, sa.cand0, sweepSeg, swKey.p, swVal.p, itemCand.p, itemSeg.p});
+      dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 2);          // scal[0] = redo count, scal[1] = tile counter
+#ifdef MM_HOST_EMU
+      state.ensure((size_t)nItems * band_state_words(BAND) + 1);
+      foreach(rt, nItems, L2SweepBandFn{sa, state.p, BAND, sweepSeg, itemCand.p, itemSeg.p, bandParts.p});
+#else
+      pr.sort_pairs<uint32_t, uint32_t>(swKey.p, swKey2.p, swVal.p, swOrder.p, nItems, 32);
+      launch_band(sa, nItems);
+#endif
+      foreach(rt, nc, L2BandMergeFn{sa, bandParts.p, itemOff.p, swRedo.p, scal.p});
+      unsigned long long nr = 0; d2h(rt, &nr, scal.p, sizeof(nr));
+      nRedo = (int64_t)nr; redoList = swRedo.p; done_fast = nc - nRedo;
+    }
+#ifndef MM_HOST_EMU
+    if (MODE == 1 && nc >= 1 && nc < ((int64_t)1 << 31) && maxSketch < (1 << 20)) {
+      // order: descending sketch size, so that the lanes of a warp run similar loops
+      swKey.ensure((size_t)nc); swKey2.ensure((size_t)nc); swVal.ensure((size_t)nc); swOrder.ensure((size_t)nc);
+      foreach(rt, nc, SweepKeyFn{cRead.p, sOf.p, nullptr, sa.cand0, swKey.p, swVal.p});
+      pr.sort_pairs<uint32_t, uint32_t>(swKey.p, swKey2.p, swVal.p, swOrder.p, nc, 32);
+      dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 2);          // scal[0] = redo count, scal[1] = tile counter
+      {
+        static int SWEEP_WARPS = 0;
+        if (!SWEEP_WARPS) {
+          const char* ev_ = getenv("MM_SWEEP_WARPS");
+          SWEEP_WARPS = ev_ ? atoi(ev_) : 8;
+          if (SWEEP_WARPS < 1 || SWEEP_WARPS > SWEEP_WARPS_MAX) SWEEP_WARPS = 8;
+          MM_CUDA(cudaFuncSetAttribute(l2_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_WORDS * 4));
         }
-        int grid = (nTiles + SWEEP_WARPS - 1) / SWEEP_WARPS; if (grid > rt.sm_count) grid = rt.sm_count;
-        l2_sweep_smem_kernel<<<grid, SWEEP_WARPS * 32, SWEEP_WARPS * SLICE * 4, rt.stream>>>(sa, swOrder.p, swTile.p, nTiles, swLocal.p,
-                                                                                             (unsigned int*)(scal.p + 1), swRedo.p, scal.p, SLICE);
-        MM_CUDA(cudaGetLastError());
-        rt.launches++;
-        unsigned long long nr = 0; d2h(rt, &nr, scal.p, sizeof(nr));
-        nRedo = (int64_t)nr; redoList = swRedo.p;
-        done_smem = nc - nRedo;
+        const int32_t SLICE = SWEEP_SMEM_WORDS / SWEEP_WARPS;
+        hk.resize((size_t)nc);
+        d2h(rt, hk.data(), swKey2.p, sizeof(uint32_t) * (size_t)nc);
+        // tiles over the descending-s order; candidates whose state does not fit a warp slice go to the global path
+        tileStartH.clear(); localOffH.assign((size_t)nc, 0);
+        int64_t firstFit = 0;
+        auto wordsOf = [](uint32_t s_) { return sweep_state_words((int32_t)s_, 1) | 1; };
+        while (firstFit < nc && wordsOf(0xFFFFFFFFu - hk[(size_t)firstFit]) > SLICE) firstFit++;
+        int64_t i = firstFit;
+        while (i < nc) {
+          tileStartH.push_back((int32_t)i);
+          int32_t used = 0, cnt = 0;
+          while (i < nc && cnt < 32) {
+            int32_t wds = wordsOf(0xFFFFFFFFu - hk[(size_t)i]);
+            if (used + wds > SLICE) break;
+            localOffH[(size_t)i] = used; used += wds; cnt++; i++;
+          }
+        }
+        tileStartH.push_back((int32_t)nc);
+        int32_t nTiles = (int32_t)tileStartH.size() - 1;
+        if (nTiles > 0) {
+          swTile.ensure(tileStartH.size()); swLocal.ensure((size_t)nc);
+          h2d(rt, swTile.p, tileStartH.data(), sizeof(int32_t) * tileStartH.size());
+          h2d(rt, swLocal.p, localOffH.data(), sizeof(int32_t) * (size_t)nc);
+          if (firstFit > 0) {          // candidates that fit no slice are pre-loaded into the redo list
+            d2d(rt, swRedo.p, swOrder.p, sizeof(int32_t) * (size_t)firstFit);
+            unsigned long long ff = (unsigned long long)firstFit; h2d(rt, scal.p, &ff, sizeof(ff));
+          }
+          int grid = (nTiles + SWEEP_WARPS - 1) / SWEEP_WARPS; if (grid > rt.sm_count) grid = rt.sm_count;
+          l2_sweep_smem_kernel<<<grid, SWEEP_WARPS * 32, SWEEP_WARPS * SLICE * 4, rt.stream>>>(sa, swOrder.p, swTile.p, nTiles, swLocal.p,
+                                                                                               (unsigned int*)(scal.p + 1), swRedo.p, scal.p, SLICE);
+          MM_CUDA(cudaGetLastError());
+          rt.launches++;
+          unsigned long long nr = 0; d2h(rt, &nr, scal.p, sizeof(nr));
+          nRedo = (int64_t)nr; redoList = swRedo.p;
+          done_fast = nc - nRedo;
+        }
       }
     }
 #endif
     if (nRedo > 0) {
-      // global-memory state for the rest (host-emulation build: for everything)
+      // full state in global memory for the rest
       stWords.ensure((size_t)n_cand + 2); stOff.ensure((size_t)n_cand + 2);
       foreach(rt, n_cand + 1, StWordsFn{cRead.p, sOf.p, stWords.p, n_cand, cntBytes});
       pr.exclusive_sum<int32_t, int64_t>(stWords.p, stOff.p, n_cand + 1);
@@ -971,8 +1478,39 @@ struct Mapper {
       if (cntBytes == 2) foreach(rt, nRedo, L2SweepFn<uint16_t>{sa, state.p, stOff.p, stRange[0], redoList}, 128, 16);
       else foreach(rt, nRedo, L2SweepFn<uint32_t>{sa, state.p, stOff.p, stRange[0], redoList}, 128, 16);
     }
-    return done_smem;
+    return done_fast;
   }
+
+#ifndef MM_HOST_EMU
+  template <int BW, int R>
+  void launch_band_t(const L2SweepArgs& sa, int64_t nc) {
+    constexpr int ST = ((BW + 4) / 4 + BW / 32 + 1) | 1;
+    constexpr int WARP_BYTES = (2 * R * 32 * 4 + 32 * ST) * 4;
+    static int warps = 0, ctasPerSm = 1;
+    if (!warps) {
+      int total = (220 * 1024) / WARP_BYTES;                 // warps that fit one SM's shared memory
+      if (total > 32) total = 32;
+      ctasPerSm = total > 16 ? 2 : 1;
+      warps = total / ctasPerSm;
+      if (const char* e = getenv("MM_SWEEP_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 16) warps = v; }
+      MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
+    }
+    int64_t tiles = (nc + 31) / 32;
+    int64_t g = (tiles + warps - 1) / warps; if (g > (int64_t)rt.sm_count * ctasPerSm) g = (int64_t)rt.sm_count * ctasPerSm;
+    l2_sweep_band_kernel<BW, R><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, swOrder.p, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,
+                                                                                               (unsigned int*)(scal.p + 1));
+    MM_CUDA(cudaGetLastError());
+    rt.launches++;
+  }
+  void launch_band(const L2SweepArgs& sa, int64_t nc) {
+    const int BAND = sweepBand, RING = sweepRing;
+    if (BAND == 64) launch_band_t<64, 4>(sa, nc);
+    else if (BAND == 128 && RING == 4) launch_band_t<128, 4>(sa, nc);
+    else if (BAND == 128) launch_band_t<128, 8>(sa, nc);
+    else if (RING == 4) launch_band_t<256, 4>(sa, nc);
+    else launch_band_t<256, 8>(sa, nc);
+  }
+#endif
 
 #ifndef MM_HOST_EMU
   cudaEvent_t evF = nullptr, evJ = nullptr;

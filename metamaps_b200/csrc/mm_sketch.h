@@ -280,7 +280,8 @@ struct Sketcher {
 
   // K1 over a packed batch.  Sequences with len < w or len < k get no minimizers (winSketch.hpp:258).
   void run(const SeqBatch& B, int k, int w, SketchOut& out) {
-    const int CH = 128;
+    static int CH = 0;
+    if (!CH) { const char* e = getenv("MM_SKETCH_CH"); CH = e ? atoi(e) : 128; if (CH < 32 || CH > 4096) CH = 128; }
     int32_t n = B.n_seqs;
     std::vector<int64_t> hChunk((size_t)n + 1), hPos((size_t)n + 1);
     int64_t chunks = 0, pos = 0;

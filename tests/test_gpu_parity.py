@@ -155,3 +155,18 @@ def test_multiple_l2_passes(oracle, small_workload, monkeypatch):
     reads = [synth.codes_to_ascii(r) for r in small_workload["reads"]]
     common.check_map_vs_oracle(ctx, oracle, contigs, reads, 16, 13)
     ctx.close()
+
+
+@pytest.mark.parametrize("env", [{"MM_SWEEP_BAND": "64"}, {"MM_SWEEP_BAND": "128", "MM_SWEEP_RING": "4", "MM_SWEEP_SEG": "100"},
+                                 {"MM_SWEEP_SEG": "64"}, {"MM_SWEEP": "full"},
+                                 {"MM_SWEEP": "global"}, {"MM_L1_FILTER": "legacy"}])
+def test_kernel_variants(oracle, small_workload, monkeypatch, env):
+    """Every selectable variant of K4/K5b (band width / ring depth of the banded sweep, the full-state shared-memory
+    sweep, the global-memory sweep, the 8-byte L1 filter) gives the oracle's results."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    ctx = capi.Context(0)
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"]]
+    common.check_map_vs_oracle(ctx, oracle, contigs, reads, 16, 13)
+    ctx.close()

@@ -102,3 +102,36 @@ def test_pipeline_matches_reference_files(emu_ctx, small_workload):
 def test_fallback_workloads(emu_ctx, oracle, name):
     contigs, reads, k, w, min_len = common.fallback_workloads()[name]
     common.check_map_vs_oracle(emu_ctx, oracle, contigs, reads, k, w, 80.0, min_len, batches=1)
+
+
+def _repetitive_workload():
+    rng = np.random.default_rng(77)
+    unit = rng.integers(0, 4, 700, dtype=np.uint8)
+    parts = [rng.integers(0, 4, 5000, dtype=np.uint8), unit, unit, unit, rng.integers(0, 4, 3000, dtype=np.uint8), unit,
+             rng.integers(0, 4, 4000, dtype=np.uint8)]
+    c0 = np.concatenate(parts)
+    c1 = np.concatenate([c0[2000:9000], rng.integers(0, 4, 2000, dtype=np.uint8), c0[2000:6000]])
+    db = synth.SynthDB(["C0|kraken:taxid|1|x", "C1|kraken:taxid|2|x"], ["1", "2"], [c0, c1])
+    _, reads, _ = synth.make_reads(db, 5, 40, 2500, err=0.06)
+    return [synth.codes_to_ascii(c) for c in db.contig_codes], [synth.codes_to_ascii(r) for r in reads]
+
+
+@pytest.mark.parametrize("env", [{"MM_SWEEP_BAND": "64"}, {"MM_SWEEP_BAND": "128", "MM_SWEEP_SEG": "100"}, {"MM_SWEEP_SEG": "64"},
+                                 {"MM_SWEEP": "global"}])
+def test_sweep_variants(oracle, small_workload, monkeypatch, env):
+    """K5b: a narrow band (the state is rebuilt from the window again and again) and the full-state sweep must both
+    reproduce the reference's std::map sliding window, on plain and on repetitive references."""
+    from metamaps_b200 import capi
+    from tests.conftest import build_emu
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    ctx = capi.Context(0, capi.load(build_emu()))
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"][:60]]
+    common.check_map_vs_oracle(ctx, oracle, contigs, reads, 16, 13)
+    rc, rr = _repetitive_workload()
+    common.check_map_vs_oracle(ctx, oracle, rc, rr, 16, 5, 80.0, 1000)
+    st = ctx.last_map_stats()
+    if "MM_SWEEP" not in env:
+        assert st["smem_swept"] > 0          # the banded path really ran
+    ctx.close()
