@@ -355,7 +355,8 @@ def main():
                    "index_minimizers": istats["n_minimizers"], "index_build_s": index_s, "setup_s": setup_s,
                    "mappings_per_step": int(out["summary"]["n_mappings"]), "candidates_per_step": int(out["summary"]["n_candidates"]),
                    "em_iters": int(out["em"]["iters"]) if out["em"] else 0, "smem_swept": ms["smem_swept"], "ambiguous_reads": ms["ambiguous_reads"],
-                   "span_elems": ms["span_elems"], "hits": ms["hits"], "sketch_elems": ms["sketch_elems"]},
+                   "span_elems": ms["span_elems"], "hits": ms["hits"], "sketch_elems": ms["sketch_elems"],
+                   "wall_ms_last_step": {k_: round(v, 2) for k_, v in stats.get("wall_ms", {}).items()}},
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(r_host.numel() + r_off.nbytes),
                 "d2h_bytes_per_step": int(o2["d2h_bytes"])},

@@ -125,6 +125,27 @@ int mm_map_fetch_candidates(mm_ctx* ctx, int32_t* seq_id, int32_t* range_start, 
 /* Stage outputs for parity tests: the read sketch (sorted unique hashes + strand of the surviving minimizer). */
 int mm_map_fetch_sketch(mm_ctx* ctx, int64_t* offsets /*n_reads+1*/, uint32_t* hash, int32_t* strand, int64_t cap);
 
+/* The accepted mappings of the batch (what mapDirectly writes, computeMap.hpp:546-588 with --all), compacted on the device,
+ * in the reference's order (read order, then (seqId, wpos)).  Per mapping: read index in the batch, contig id,
+ * meanOptimalPos (refStart), sharedSketchSize, sketch size s, strand (+1/-1), nucIdentity (float, computeMap.hpp:405-408,
+ * computed on the host through glibc like the reference) and identity_parsed = the double that `classify` re-reads from
+ * the 6-significant-digit text of column 10 (mapWrap.h:229, fEM.h:297).  Any output pointer may be NULL; cap = capacity
+ * of the arrays (>= summary.n_mappings). */
+int mm_map_fetch_mappings(mm_ctx* ctx, int32_t* read_idx, int32_t* seq_id, int32_t* ref_start, int32_t* shared,
+                          int32_t* sketch, int32_t* strand, float* identity, double* identity_parsed, int64_t cap,
+                          int64_t* n_mappings);
+
+/* ---- host helpers of the classify stage (C++/OpenMP, no device work) -------------------------------- */
+/* nucIdentity and its 6-significant-digit round trip for n (shared, s) pairs. */
+int mm_stat_identity_batch(const int32_t* shared, const int32_t* sketch, int64_t n, int k, float* identity,
+                           double* identity_parsed);
+/* getMappingLocations' nLoc (fEM.h:324-348): mappings of read r are [read_off[r], read_off[r+1]); read_len[r] its length;
+ * taxon[m] := contig_taxon[seq_id[m]];  nloc[m] = sum over the contigs c of that taxon of
+ * (len_c >= read_len ? len_c - read_len + 1 : [c is among this read's mapped contigs]). */
+int mm_nloc_batch(const int32_t* seq_id, const int64_t* read_off, const int32_t* read_len, int64_t n_reads,
+                  const int64_t* contig_len, const int32_t* contig_taxon, int32_t n_contigs, int32_t n_taxa,
+                  int32_t* taxon, double* nloc);
+
 /* ---- statistics tables the host needs for text output (replace Stat::*, map_stats.hpp) ------------ */
 int mm_stat_min_hits_relaxed(int s, int k, float perc_identity);          /* estimateMinimumHitsRelaxed :142 */
 int mm_stat_recommended_window(double pvalue, int k, int alphabet, float perc_identity, int len_query,

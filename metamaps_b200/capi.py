@@ -51,6 +51,9 @@ SYMBOLS = {
     "mm_map_fetch_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mm_map_fetch_candidates": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
     "mm_map_fetch_sketch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "mm_map_fetch_mappings": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int64, C.POINTER(C.c_int64)]),
+    "mm_stat_identity_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "mm_nloc_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mm_stat_min_hits_relaxed": (C.c_int, [C.c_int, C.c_int, C.c_float]),
     "mm_stat_recommended_window": (C.c_int, [C.c_double, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64]),
     "mm_stat_estimate_pvalue": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_uint64]),
@@ -242,6 +245,56 @@ class Index:
             pass
 
 
+def fetch_map_results(ctx: Context, out: dict) -> dict:
+    """D2H of the per-read and per-candidate results of the last map call (mm_map_fetch_reads / _candidates)."""
+    n, nc = out["_n"], out["_nc"]
+    sk = np.zeros(n, np.int32); mh = np.zeros(n, np.int32); co = np.zeros(n + 1, np.int64)
+    ctx._check(ctx.lib.mm_map_fetch_reads(ctx.h, _ptr(sk), _ptr(mh), _ptr(co)))
+    names = ["seq", "start", "end", "pos", "shared", "votes", "accepted", "valid"]
+    arrs = [np.zeros(nc, np.int32) for _ in names]
+    o1 = np.zeros(nc, np.int64); o2 = np.zeros(nc, np.int64)
+    ctx._check(ctx.lib.mm_map_fetch_candidates(ctx.h, *[_ptr(a) for a in arrs], _ptr(o1), _ptr(o2)))
+    out.update({"s": sk, "minimumHits": mh, "cand_off": co, "optStart": o1, "optEnd": o2})
+    out.update(dict(zip(names, arrs)))
+    out["d2h_bytes"] = int(sk.nbytes + mh.nbytes + co.nbytes + sum(a.nbytes for a in arrs) + o1.nbytes + o2.nbytes)
+    return out
+
+
+def fetch_mappings(ctx: Context, n_mappings: int) -> dict:
+    """The accepted mappings of the last map call, compacted on the device (mm_map_fetch_mappings)."""
+    n = int(n_mappings)
+    i32 = lambda: np.zeros(n, np.int32)
+    out = {"read": i32(), "seq": i32(), "pos": i32(), "shared": i32(), "sketch": i32(), "strand": i32(),
+           "identity": np.zeros(n, np.float32), "identity_parsed": np.zeros(n, np.float64)}
+    got = C.c_int64()
+    ctx._check(ctx.lib.mm_map_fetch_mappings(ctx.h, *[_ptr(out[k_]) for k_ in ("read", "seq", "pos", "shared", "sketch", "strand", "identity",
+                                                                                "identity_parsed")], n, C.byref(got)))
+    assert got.value == n, (got.value, n)
+    out["d2h_bytes"] = int(6 * 4 * n)
+    return out
+
+
+def identity_batch(lib, shared, sketch, k: int):
+    shared = np.ascontiguousarray(shared, np.int32); sketch = np.ascontiguousarray(sketch, np.int32)
+    a = np.zeros(len(shared), np.float32); b = np.zeros(len(shared), np.float64)
+    rc = lib.mm_stat_identity_batch(_ptr(shared), _ptr(sketch), len(shared), k, _ptr(a), _ptr(b))
+    if rc != 0:
+        raise MMError(rc, (lib.mm_last_error() or b"").decode())
+    return a, b
+
+
+def nloc_batch(lib, seq, read_off, read_len, contig_len, contig_taxon, n_taxa: int):
+    seq = np.ascontiguousarray(seq, np.int32); read_off = np.ascontiguousarray(read_off, np.int64)
+    read_len = np.ascontiguousarray(read_len, np.int32); contig_len = np.ascontiguousarray(contig_len, np.int64)
+    contig_taxon = np.ascontiguousarray(contig_taxon, np.int32)
+    tax = np.zeros(len(seq), np.int32); nloc = np.zeros(len(seq), np.float64)
+    rc = lib.mm_nloc_batch(_ptr(seq), _ptr(read_off), _ptr(read_len), len(read_off) - 1, _ptr(contig_len), _ptr(contig_taxon), len(contig_len),
+                           int(n_taxa), _ptr(tax), _ptr(nloc))
+    if rc != 0:
+        raise MMError(rc, (lib.mm_last_error() or b"").decode())
+    return tax, nloc
+
+
 def map_reads(ctx: Context, index: Index, reads=None, perc_identity: float = 80.0, min_read_len: int = 1000,
               dev_ptr: int | None = None, host_ptr: int | None = None, offsets=None, fetch: bool = True,
               fetch_sketch: bool = False):
@@ -262,18 +315,10 @@ def map_reads(ctx: Context, index: Index, reads=None, perc_identity: float = 80.
     gpu_ms, launches = ctx.last_timing()          # of the map call itself (the fetches below are separate calls)
     out = {"summary": {f[0]: getattr(s, f[0]) for f in MapSummary._fields_}, "gpu_ms": gpu_ms, "launches": launches,
            "stats": ctx.last_map_stats()}
+    out["_n"] = n; out["_nc"] = int(s.n_candidates)
     if not fetch:
         return out
-    sk = np.zeros(n, np.int32); mh = np.zeros(n, np.int32); co = np.zeros(n + 1, np.int64)
-    ctx._check(ctx.lib.mm_map_fetch_reads(ctx.h, _ptr(sk), _ptr(mh), _ptr(co)))
-    nc = int(s.n_candidates)
-    names = ["seq", "start", "end", "pos", "shared", "votes", "accepted", "valid"]
-    arrs = [np.zeros(nc, np.int32) for _ in names]
-    o1 = np.zeros(nc, np.int64); o2 = np.zeros(nc, np.int64)
-    ctx._check(ctx.lib.mm_map_fetch_candidates(ctx.h, *[_ptr(a) for a in arrs], _ptr(o1), _ptr(o2)))
-    out.update({"s": sk, "minimumHits": mh, "cand_off": co, "optStart": o1, "optEnd": o2})
-    out.update(dict(zip(names, arrs)))
-    out["d2h_bytes"] = int(sk.nbytes + mh.nbytes + co.nbytes + sum(a.nbytes for a in arrs) + o1.nbytes + o2.nbytes)
+    out = fetch_map_results(ctx, out)
     if fetch_sketch:
         qo = np.zeros(n + 1, np.int64)
         ctx._check(ctx.lib.mm_map_fetch_sketch(ctx.h, _ptr(qo), None, None, 0))

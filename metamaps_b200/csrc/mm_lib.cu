@@ -312,6 +312,119 @@ int mm_map_fetch_sketch(mm_ctx* c, int64_t* offsets, uint32_t* hash, int32_t* st
   MM_CATCH
 }
 
+struct MapCompactFn {
+  const int32_t* oAccept; const int64_t* accIdx; const int32_t* cRead; const int32_t* cSeq; const int32_t* oPos; const int32_t* oShared;
+  const int32_t* oVotes; const int32_t* sOf;
+  int32_t* mRead; int32_t* mSeq; int32_t* mPos; int32_t* mShared; int32_t* mSketch; int32_t* mStrand;
+  MM_HD void operator()(int64_t c) const {
+    if (!ldg(oAccept + c)) return;
+    const int64_t d = ldg(accIdx + c); const int32_t r = ldg(cRead + c);
+    mRead[d] = r; mSeq[d] = ldg(cSeq + c); mPos[d] = ldg(oPos + c); mShared[d] = ldg(oShared + c); mSketch[d] = ldg(sOf + r);
+    mStrand[d] = ldg(oVotes + c) > 0 ? 1 : -1;                         // computeMap.hpp:438
+  }
+};
+// the double obtained by printing a float with 6 significant digits and parsing it back
+static inline double round6(float x32) {
+  const double x = (double)x32;
+  if (x >= 10.0 && x < 99.99995) return rint(x * 1e4) / 1e4;       // x*1e4 < 2^24 * 2^14: exact in double
+  char buf[64]; snprintf(buf, sizeof buf, "%.6g", x); return strtod(buf, nullptr);
+}
+int mm_stat_identity_batch(const int32_t* shared, const int32_t* sketch, int64_t n, int k, float* identity, double* parsed) {
+  MM_TRY
+  if (n < 0 || (n > 0 && (!shared || !sketch))) throw Error(MM_EINVAL, "mm_stat_identity_batch: bad arguments");
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; i++) {
+    float a, b; stats::identity_only(shared[i], sketch[i], k, &a); (void)b;
+    if (identity) identity[i] = a;
+    if (parsed) parsed[i] = round6(a);
+  }
+  MM_CATCH
+}
+int mm_map_fetch_mappings(mm_ctx* c, int32_t* read_idx, int32_t* seq_id, int32_t* ref_start, int32_t* shared, int32_t* sketch, int32_t* strand,
+                          float* identity, double* parsed, int64_t cap, int64_t* n_out) {
+  MM_TRY
+  if (!c) throw Error(MM_EINVAL, "null ctx");
+  Mapper& m = c->mp; const int64_t nc = m.n_cand;
+  begin_call(c);
+  int64_t nm = 0;
+  auto& idx = c->scr.dOff; auto& a = c->scr.tmpA; auto& b = c->scr.tmpB; auto& d0 = c->scr.dSh; auto& d1 = c->scr.dSk; auto& d2 = c->scr.dLen; auto& d3 = c->scr.dSt;
+  if (nc > 0) {
+    idx.ensure((size_t)nc + 2);
+    dev_memset(c->rt, m.oAccept.p + nc, 0, sizeof(int32_t));
+    c->pr.exclusive_sum<int32_t, int64_t>(m.oAccept.p, idx.p, nc + 1);
+    d2h(c->rt, &nm, idx.p + nc, sizeof(int64_t));
+  }
+  if (n_out) *n_out = nm;
+  if (nm > cap && (read_idx || seq_id || ref_start || shared || sketch || strand || identity || parsed)) throw Error(MM_ERANGE, "mm_map_fetch_mappings: capacity too small");
+  if (nm > 0) {
+    a.ensure((size_t)nm); b.ensure((size_t)nm); d0.ensure((size_t)nm); d1.ensure((size_t)nm); d2.ensure((size_t)nm); d3.ensure((size_t)nm);
+    foreach(c->rt, nc, MapCompactFn{m.oAccept.p, idx.p, m.cRead.p, m.cSeq.p, m.oPos.p, m.oShared.p, m.oVotes.p, m.sOf.p, a.p, b.p, d0.p, d1.p, d2.p, d3.p});
+    std::vector<int32_t> hs, hk;
+    const bool needId = identity || parsed;
+    if (needId && !shared) hs.resize((size_t)nm);
+    if (needId && !sketch) hk.resize((size_t)nm);
+    int32_t* pShared = shared ? shared : (needId ? hs.data() : nullptr);
+    int32_t* pSketch = sketch ? sketch : (needId ? hk.data() : nullptr);
+    if (read_idx) d2h(c->rt, read_idx, a.p, 4 * (size_t)nm);
+    if (seq_id) d2h(c->rt, seq_id, b.p, 4 * (size_t)nm);
+    if (ref_start) d2h(c->rt, ref_start, d0.p, 4 * (size_t)nm);
+    if (pShared) d2h(c->rt, pShared, d1.p, 4 * (size_t)nm);
+    if (pSketch) d2h(c->rt, pSketch, d2.p, 4 * (size_t)nm);
+    if (strand) d2h(c->rt, strand, d3.p, 4 * (size_t)nm);
+    c->rt.sync();
+    if (needId) { int rc = mm_stat_identity_batch(pShared, pSketch, nm, m.lastK, identity, parsed); if (rc != MM_OK) return rc; }
+  }
+  end_call(c);
+  MM_CATCH
+}
+int mm_nloc_batch(const int32_t* seq_id, const int64_t* read_off, const int32_t* read_len, int64_t n_reads, const int64_t* contig_len,
+                  const int32_t* contig_taxon, int32_t n_contigs, int32_t T, int32_t* taxon, double* nloc) {
+  MM_TRY
+  if (n_reads < 0 || !read_off || !contig_len || !contig_taxon || n_contigs < 0 || T < 1) throw Error(MM_EINVAL, "mm_nloc_batch: bad arguments");
+  // contigs of each taxon sorted by length, with prefix sums of the lengths
+  std::vector<int64_t> start((size_t)T + 1, 0);
+  for (int32_t c_ = 0; c_ < n_contigs; c_++) {
+    if (contig_taxon[c_] < 0 || contig_taxon[c_] >= T) throw Error(MM_EINVAL, "mm_nloc_batch: contig taxon out of range");
+    start[(size_t)contig_taxon[c_] + 1]++;
+  }
+  for (int32_t t = 0; t < T; t++) start[(size_t)t + 1] += start[(size_t)t];
+  std::vector<int64_t> lens((size_t)n_contigs), fill(start.begin(), start.end() - 1), csum((size_t)n_contigs + 1, 0);
+  for (int32_t c_ = 0; c_ < n_contigs; c_++) lens[(size_t)fill[(size_t)contig_taxon[c_]]++] = contig_len[c_];
+  for (int32_t t = 0; t < T; t++) std::sort(lens.begin() + start[(size_t)t], lens.begin() + start[(size_t)t + 1]);
+  for (int32_t c_ = 0; c_ < n_contigs; c_++) csum[(size_t)c_ + 1] = csum[(size_t)c_] + lens[(size_t)c_];
+  const int64_t M = read_off[n_reads];
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t r = 0; r < n_reads; r++) {
+    const int64_t L = read_len[r];
+    const int64_t m0 = read_off[r], m1 = read_off[r + 1];
+    for (int64_t m = m0; m < m1; m++) {
+      const int32_t sq = seq_id[m];
+      if (sq < 0 || sq >= n_contigs) { bad = 1; continue; }
+      const int32_t t = contig_taxon[sq];
+      if (taxon) taxon[m] = t;
+      if (!nloc) continue;
+      const int64_t* b = lens.data() + start[(size_t)t]; const int64_t* e = lens.data() + start[(size_t)t + 1];
+      const int64_t* p = std::lower_bound(b, e, L);                       // contigs at least as long as the read
+      const int64_t nBig = e - p;
+      int64_t v = (csum[(size_t)(e - lens.data())] - csum[(size_t)(p - lens.data())]) - nBig * (L - 1);
+      if (p != b) {           // shorter contigs of the taxon count once each if this read maps to them (fEM.h:337-345)
+        for (int64_t x = m0; x < m1; x++) {
+          const int32_t sx = seq_id[x];
+          if (sx < 0 || sx >= n_contigs || contig_taxon[sx] != t || contig_len[sx] >= L) continue;
+          bool first = true;
+          for (int64_t y = m0; y < x; y++) if (seq_id[y] == sx) { first = false; break; }
+          if (first) v++;
+        }
+      }
+      nloc[m] = (double)v;
+    }
+  }
+  (void)M;
+  if (bad) throw Error(MM_EINVAL, "mm_nloc_batch: contig id out of range");
+  MM_CATCH
+}
+
 // ------------------------------------------------------------------------------------------------ host statistics
 int mm_stat_min_hits_relaxed(int s, int k, float pi) { return stats::estimateMinimumHitsRelaxed(s, k, pi); }
 int mm_stat_recommended_window(double p, int k, int alphabet, float pi, int lenQ, uint64_t lenR) { return stats::recommendedWindowSize(p, k, alphabet, pi, lenQ, lenR); }

@@ -1076,7 +1076,7 @@ struct Mapper {
   DevBuf<int32_t> dMinHits, dAccept; int tabUploaded = 0; int tabK = 0; float tabPi = 0;
   // per batch (kept until the next batch for the fetch calls)
   SeqBatch batch; SketchOut rs;
-  int32_t n_reads = 0; int64_t n_q = 0, n_hits = 0, n_cand = 0;
+  int32_t n_reads = 0; int64_t n_q = 0, n_hits = 0, n_cand = 0; int lastK = 16;
   DevBuf<int32_t> readLen, sOf, head, hitCnt, candCnt, cRead, cSeq, cStart, cEnd, spanN, stWords;
   DevBuf<int32_t> oShared, oPos, oValid, oIstar, oVotes, oAccept, readMapped;
   DevBuf<int64_t> qOff, idx, hitStart, hitOff, readHitOff, candOff, beg0, fe, le, evOff, stOff, oOptS, oOptE;
@@ -1119,6 +1119,7 @@ struct Mapper {
   void run(const Index& ix, float pi, int32_t minReadLen, int64_t* summary /*6*/) {
     memset(&st, 0, sizeof(st));
     const int k = ix.k, w = ix.w;
+    lastK = k;
     n_reads = batch.n_seqs;
     // reads shorter than w, k or -m are skipped (computeMap.hpp:137): hide them from K1 by zeroing their length
     h_effLen.assign((size_t)n_reads, 0);

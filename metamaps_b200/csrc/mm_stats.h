@@ -138,6 +138,10 @@ inline void identity(int shared, int s, int k, float* nuc, float* upper) {      
   *nuc = 100 * (1 - md);
   *upper = 100 * (1 - lb);
 }
+inline void identity_only(int shared, int s, int k, float* nuc) {                             // computeMap.hpp:403-408
+  float md = j2md(1.0 * shared / s, k);
+  *nuc = 100 * (1 - md);
+}
 inline double estimate_pvalue(int s, int k, int alphabet, float identity_, int lenQ, uint64_t lenR) {  // :179-213
   double kmerSpace = pow(alphabet, k);
   double pX, pY; pX = pY = 1. / (1. + kmerSpace / lenQ);

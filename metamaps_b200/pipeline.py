@@ -47,41 +47,49 @@ def round_6_significant(x32: np.ndarray) -> np.ndarray:
 def map_and_classify(ctx: capi.Context, index: capi.Index, *, reads=None, dev_ptr=None, host_ptr=None, offsets=None, read_len=None,
                      contig_len: np.ndarray, contig_taxon: np.ndarray, n_taxa: int, perc_identity: float = 80.0,
                      min_read_len: int = 1000, em_max_iter: int = 0, stats: dict | None = None):
-    """One pass of the hot path over one batch of reads.  Returns per-mapping arrays + EM result."""
+    """One pass of the hot path over one batch of reads.  Returns per-mapping arrays + EM result.
+
+    mm_map_batch (K1,K3-K5) -> mm_map_fetch_mappings (accepted mappings compacted on the device, identities on the host
+    through glibc) -> mm_mapq_batch (K6) -> mm_nloc_batch (host) -> mm_em_run (K7/K8)."""
+    import time
     k = index.k
-    res = capi.map_reads(ctx, index, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets)
+    t0 = time.perf_counter()
+    res = capi.map_reads(ctx, index, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets, fetch=False)
+    t1 = time.perf_counter()
     launches = res["launches"]
     gpu_ms = res["gpu_ms"]
     if stats is not None:
         stats["map"] = res["stats"]
-    n_reads = len(res["s"])
+    n_reads = res["_n"]
+    m = capi.fetch_mappings(ctx, res["summary"]["n_mappings"])
+    t2 = time.perf_counter()
     if read_len is None:
         read_len = np.array([len(r) for r in reads], np.int32) if reads is not None else np.diff(offsets).astype(np.int32)
-    cand_read = np.repeat(np.arange(n_reads, dtype=np.int64), np.diff(res["cand_off"]))
-    acc = res["accepted"].astype(bool)
-    m_read = cand_read[acc]
-    m_seq = res["seq"][acc]; m_shared = res["shared"][acc]; m_pos = res["pos"][acc]; m_votes = res["votes"][acc]
-    m_s = res["s"][m_read]
-    ident32 = nuc_identity(m_shared, m_s, k)
-    ident = round_6_significant(ident32) / 100.0
+    m_read = m["read"]
     # reads with >= 1 mapping, in read order (the mappings file has no lines for the others)
     counts = np.bincount(m_read, minlength=n_reads)
     mapped = np.nonzero(counts)[0]
     read_off = np.zeros(len(mapped) + 1, np.int64); read_off[1:] = np.cumsum(counts[mapped])
-    out = {"summary": res["summary"], "read": m_read, "seq": m_seq, "pos": m_pos, "shared": m_shared, "sketch": m_s,
-           "strand": np.where(m_votes > 0, 1, -1), "identity": ident32, "mapped_reads": mapped, "read_off": read_off}
-    d2h = res["d2h_bytes"]
+    out = {"summary": res["summary"], "read": m_read, "seq": m["seq"], "pos": m["pos"], "shared": m["shared"], "sketch": m["sketch"],
+           "strand": m["strand"], "identity": m["identity"], "mapped_reads": mapped, "read_off": read_off}
+    d2h = m["d2h_bytes"]
     if len(m_read) == 0:
         out.update({"mapq": np.zeros(0), "em": None, "gpu_ms": gpu_ms, "launches": launches, "d2h_bytes": d2h})
         return out
-    mapq, status = ctx.mapq(ident, m_shared, m_s, read_len[mapped], read_off, k)
+    t3 = time.perf_counter()
+    rl_mapped = np.ascontiguousarray(read_len[mapped], np.int32)
+    mapq, status = ctx.mapq(m["identity_parsed"] / 100.0, m["shared"], m["sketch"], rl_mapped, read_off, k)
+    t4 = time.perf_counter()
     launches += ctx.last_timing()[1]; gpu_ms += ctx.last_timing()[0]
     out["mapq"] = mapq; out["mapq_status"] = status
     # fEM.h:324-348: possible mapping locations of the mapping's taxon for this read length
-    L = read_len[m_read].astype(np.int64)
-    tax = contig_taxon[m_seq]
-    nloc = _nloc(tax, m_seq, m_read, L, contig_len, contig_taxon, n_taxa)
+    tax, nloc = capi.nloc_batch(ctx.lib, m["seq"], read_off, rl_mapped, contig_len, contig_taxon, n_taxa)
+    t5 = time.perf_counter()
     em = ctx.em(tax, mapq, nloc, read_off, n_taxa, em_max_iter)
+    t6 = time.perf_counter()
+    if stats is not None:       # wall-clock split of one step (ms): the C-ABI calls and the glue between them
+        stats["wall_ms"] = {"map_call": (t1 - t0) * 1e3, "fetch_mappings": (t2 - t1) * 1e3, "read_offsets": (t3 - t2) * 1e3, "mapq_call": (t4 - t3) * 1e3,
+                            "nloc": (t5 - t4) * 1e3, "em_call": (t6 - t5) * 1e3}
     launches += ctx.last_timing()[1]; gpu_ms += ctx.last_timing()[0]
     d2h += mapq.nbytes + status.nbytes + em["f"].nbytes + em["posterior"].nbytes + em["best"].nbytes
     out["taxon"] = tax; out["nloc"] = nloc; out["em"] = em; out["gpu_ms"] = gpu_ms; out["launches"] = launches; out["d2h_bytes"] = int(d2h)
@@ -92,7 +100,8 @@ _TAXON_CACHE: dict = {}
 
 
 def _nloc(tax, m_seq, m_read, L, contig_len, contig_taxon, n_taxa):
-    """sum over the taxon's contigs of (len >= L ? len-L+1 : [contig seen among this read's mappings])."""
+    """numpy restatement of mm_nloc_batch (kept as the cross-check in tests/test_host_stats.py):
+    sum over the taxon's contigs of (len >= L ? len-L+1 : [contig seen among this read's mappings])."""
     key = (id(contig_len), id(contig_taxon))
     if key not in _TAXON_CACHE:
         order = np.lexsort((contig_len, contig_taxon))
