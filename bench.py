@@ -216,6 +216,9 @@ def main():
     ap.add_argument("--ref-contigs", type=int, default=12, help="reference arm: DB sample size in contigs")
     ap.add_argument("--ref-reads", type=int, default=1500, help="reference arm: reads in the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="reads", choices=["reads", "contigs"],
+                    help="N > 1: 'reads' = index replicated, every rank maps its own reads (no mapping exchange); 'contigs' = the "
+                         "index is split into contig ranges, every rank maps ALL reads against its shard, mappings are exchanged")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -247,14 +250,28 @@ def main():
     n_contigs = len(offsets) - 1
     step_c = max(1, (256_000_000 // wl["contig_len"]))
     t_ix = time.time()
-    for c0 in range(0, n_contigs, step_c):
-        c1 = min(n_contigs, c0 + step_c)
+    by_contigs = args.shard == "contigs" and world > 1
+    own0, own1 = (rank * n_contigs // world, (rank + 1) * n_contigs // world) if by_contigs else (0, n_contigs)
+    if by_contigs:
+        ix.set_shard(own0, keep_counts=True)
+    for c0 in range(own0, own1, step_c):
+        c1 = min(own1, c0 + step_c)
         ix.add_dev(asc.data_ptr(), offsets[c0:c1 + 1])
     del asc
     ix.finalize()
+    if by_contigs:
+        ix.sync_threshold()                        # collective: occurrence threshold of the whole reference
     index_s = time.time() - t_ix
     istats = ix.stats()
-    r_asc, r_off = gen_reads(torch, dev, wl, codes, rank)
+    if by_contigs:                                 # every rank needs every read: blocks 0..N-1 of the read recipe
+        blocks = [gen_reads(torch, dev, wl, codes, b) for b in range(world)]
+        r_asc = torch.cat([b[0] for b in blocks])
+        r_off = np.concatenate([[0]] + [b[1][1:] + sum(int(x[1][-1]) for x in blocks[:i]) for i, b in enumerate(blocks)]).astype(np.int64)
+        blk = np.cumsum([0] + [len(b[1]) - 1 for b in blocks])
+        my_reads = (int(blk[rank]), int(blk[rank + 1]))
+        del blocks
+    else:
+        r_asc, r_off = gen_reads(torch, dev, wl, codes, rank)
     del codes
     torch.cuda.empty_cache()
     n_taxa = int(contig_taxon.max()) + 1
@@ -264,7 +281,38 @@ def main():
     r_host.copy_(r_asc); torch.cuda.synchronize()
     setup_s = time.time() - t_setup
 
+    MKEYS = (("read", np.int32), ("seq", np.int32), ("pos", np.int32), ("shared", np.int32), ("sketch", np.int32), ("strand", np.int32),
+             ("identity", np.float32), ("identity_parsed", np.float64))
+
+    def exchange(parts):
+        """all-gather of this rank's accepted mappings (one shard per rank): sizes first, then one padded byte tensor over NCCL."""
+        m = parts[0]
+        n = len(m["read"])
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev); sizes[rank] = n
+        dist.all_reduce(sizes)
+        sizes = sizes.cpu().numpy(); cap = int(sizes.max())
+        rec = sum(np.dtype(t).itemsize for _, t in MKEYS)
+        buf = np.zeros(cap * rec, np.uint8); o = 0
+        for k_, t in MKEYS:
+            b = np.ascontiguousarray(m[k_], t).view(np.uint8); buf[o:o + b.size] = b; o += cap * np.dtype(t).itemsize
+        send = torch.from_numpy(buf).to(dev)
+        recv = torch.empty(world * cap * rec, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send)
+        allb = recv.cpu().numpy().reshape(world, cap * rec)
+        out = []
+        for r in range(world):
+            d = {}; o = 0
+            for k_, t in MKEYS:
+                isz = np.dtype(t).itemsize
+                d[k_] = allb[r, o:o + int(sizes[r]) * isz].view(t).copy(); o += cap * isz
+            out.append([d])
+        return out
+
     def step_dev(stats=None):
+        if by_contigs:
+            return pipeline.map_and_classify_sharded(ctx, [ix], dev_ptr=r_asc.data_ptr(), offsets=r_off, read_len=read_len, contig_len=contig_len,
+                                                     contig_taxon=contig_taxon, n_taxa=n_taxa, perc_identity=PI, min_read_len=wl["min_read_len"],
+                                                     exchange=exchange, read_range=my_reads, stats=stats)
         return pipeline.map_and_classify(ctx, ix, dev_ptr=r_asc.data_ptr(), offsets=r_off, read_len=read_len, contig_len=contig_len,
                                          contig_taxon=contig_taxon, n_taxa=n_taxa, perc_identity=PI, min_read_len=wl["min_read_len"], stats=stats)
 
@@ -298,13 +346,17 @@ def main():
     wall = float(tt.item())
     bases = int(out["summary"]["total_bases_mapped_reads"])
     tb = torch.tensor([bases], device=dev, dtype=torch.float64)
-    if world > 1:
+    if world > 1 and not by_contigs:               # contig shards: every rank already counts all reads
         dist.all_reduce(tb)
     total_bases = float(tb.item())
     value = total_bases * args.steps / 1e6 / wall
 
     # e2e leg: host-buffer C-ABI calls (H2D of the pinned reads + D2H of every result array inside the timed region)
     def e2e_step_direct():
+        if by_contigs:
+            return pipeline.map_and_classify_sharded(ctx, [ix], host_ptr=r_host.data_ptr(), offsets=r_off, read_len=read_len, contig_len=contig_len,
+                                                     contig_taxon=contig_taxon, n_taxa=n_taxa, perc_identity=PI, min_read_len=wl["min_read_len"],
+                                                     exchange=exchange, read_range=my_reads)
         return pipeline.map_and_classify(ctx, ix, host_ptr=r_host.data_ptr(), offsets=r_off, read_len=read_len, contig_len=contig_len,
                                          contig_taxon=contig_taxon, n_taxa=n_taxa, perc_identity=PI, min_read_len=wl["min_read_len"])
     for _ in range(2):
@@ -350,7 +402,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32/int64 (mapping), f64 (mapq, EM)", "data": "synthetic",
         "config": {"workload": args.workload, "reads_per_gpu": wl["n_reads"], "db_gbp": istats["n_contigs"] * wl["contig_len"] / 1e9,
-                   "k": K, "w": wl["w"], "min_read_len": wl["min_read_len"], "perc_identity": PI, "parallelism": f"reads sharded x{world}, index replicated",
+                   "k": K, "w": wl["w"], "min_read_len": wl["min_read_len"], "perc_identity": PI, "parallelism": (f"index sharded by contig range x{world}, every rank maps all {world}x{wl['n_reads']} reads, mappings all-gathered"
+                                   if by_contigs else f"reads sharded x{world}, index replicated"),
                    "l2_flush": "inputs (index %.1f GB + reads) larger than L2" % (istats["device_bytes"] / 1e9),
                    "index_minimizers": istats["n_minimizers"], "index_build_s": index_s, "setup_s": setup_s,
                    "mappings_per_step": int(out["summary"]["n_mappings"]), "candidates_per_step": int(out["summary"]["n_candidates"]),

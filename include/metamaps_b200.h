@@ -82,6 +82,18 @@ int mm_index_add_dev(mm_index* idx, const void* seqs_dev, const int64_t* offsets
 int mm_index_finalize(mm_index* idx);
 int mm_index_stats(const mm_index* idx, int64_t* n_minimizers, int64_t* n_unique, int32_t* freq_threshold,
                    int32_t* n_contigs, int64_t* device_bytes);
+/* Contig-range shards.  A reference too large for one GPU (or spread over the GPUs of a node) is indexed as shards of
+ * consecutive contigs, one mm_index each -- the reference's own chunking (winSketch.hpp:284-329), where chunk N's
+ * sequence ids restart at 0 (:308,315): results carry shard-local contig ids, the caller adds first_contig_id.
+ * L1/L2 work per contig, so a read's mappings against the whole reference are the concatenation, in shard order, of its
+ * mappings against every shard -- provided the shards agree on which hashes are over-frequent.  Two choices:
+ *   - per-shard thresholds (nothing to call): the reference's behaviour under --maxmemory, chunk by chunk;
+ *   - the threshold of the UNCHUNKED reference: call mm_index_set_shard(.., keep_counts = 1) before mm_index_finalize
+ *     on every shard, then mm_index_sync_threshold on every rank (collective over the context's communicator:
+ *     mm_comm_init, or mm_comm_set_allreduce + mm_comm_set_rank).  The shards' (hash, count) lists are exchanged by
+ *     hash range, merged, the global histogram gives the threshold and the over-frequent hashes are flagged locally. */
+int mm_index_set_shard(mm_index* idx, int32_t first_contig_id, int32_t keep_counts);
+int mm_index_sync_threshold(mm_index* idx, int32_t* global_threshold, int64_t* global_unique);
 /* minimizerIndex in (seqId,wpos) order, for parity tests. */
 int mm_index_fetch(const mm_index* idx, uint32_t* hash, int32_t* seq_id, int32_t* wpos, int32_t* strand);
 /* minimizerPosLookupIndex probe, for parity tests: count (0 = absent) of each hash. */
@@ -183,6 +195,8 @@ int mm_comm_destroy(mm_ctx* ctx);
  * precedence when both are set.  The callback returns 0 on success. */
 typedef int (*mm_allreduce_fn)(double* buf, int64_t n, void* user);
 int mm_comm_set_allreduce(mm_ctx* ctx, mm_allreduce_fn fn, void* user);
+/* rank / size of the host transport (NCCL contexts get theirs from mm_comm_init) */
+int mm_comm_set_rank(mm_ctx* ctx, int n_ranks, int rank);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,9 @@ SYMBOLS = {
     "mm_index_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mm_index_add": (C.c_int, [C.c_void_p, C.c_char_p, _i64p, C.c_int32]),
     "mm_index_add_dev": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int32]),
+    "mm_index_set_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "mm_index_sync_threshold": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "mm_comm_set_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mm_index_finalize": (C.c_int, [C.c_void_p]),
     "mm_index_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "mm_index_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -173,6 +176,7 @@ class Context:
     def comm_init(self, n_ranks: int, rank: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         self._check(self.lib.mm_comm_init(self.h, n_ranks, rank, buf))
+        self.n_ranks_hint = n_ranks
 
     def set_allreduce(self, fn):
         """fn(numpy float64 array) -> None must sum-all-reduce the array in place across ranks (host transport)."""
@@ -189,6 +193,12 @@ class Context:
                 return 1
         self._ar = ALLREDUCE_FN(tramp)        # keep the trampoline alive
         self._check(self.lib.mm_comm_set_allreduce(self.h, C.cast(self._ar, C.c_void_p), None))
+
+    n_ranks_hint = 1       # > 1 once a communicator / host transport is attached: collective calls must not be skipped
+
+    def set_rank(self, n_ranks: int, rank: int):
+        self._check(self.lib.mm_comm_set_rank(self.h, n_ranks, rank))
+        self.n_ranks_hint = n_ranks
 
     def comm_unique_id(self) -> bytes:
         buf = C.create_string_buffer(128)
@@ -215,6 +225,17 @@ class Index:
 
     def finalize(self):
         self.ctx._check(self.lib.mm_index_finalize(self.h))
+
+    def set_shard(self, first_contig_id: int, keep_counts: bool = True):
+        """This index holds the contigs [first_contig_id, ...) of a larger reference (call before finalize)."""
+        self.first_contig = int(first_contig_id)
+        self.ctx._check(self.lib.mm_index_set_shard(self.h, int(first_contig_id), 1 if keep_counts else 0))
+
+    def sync_threshold(self):
+        """Collective: occurrence threshold of the whole (sharded) reference; flags the over-frequent hashes locally."""
+        t = C.c_int32(); u = C.c_int64()
+        self.ctx._check(self.lib.mm_index_sync_threshold(self.h, C.byref(t), C.byref(u)))
+        return t.value, u.value
 
     def stats(self):
         a = C.c_int64(); b = C.c_int64(); c = C.c_int32(); d = C.c_int32(); e = C.c_int64()

@@ -84,9 +84,46 @@ struct DupFn {
   }
 };
 
+// bit 31 of a slot's count: the hash is over-frequent in the WHOLE (sharded) reference, see Index::keepUnique; such a
+// count compares above every threshold, so the L1 probe skips the hash without knowing about the flag
+static const uint32_t SLOT_GLOBAL_FREQ = 0x80000000u;
 struct LookupFn {
   const Slot* table; uint32_t mask; const uint32_t* hashes; int32_t* counts;
-  MM_HD void operator()(int64_t i) const { int64_t st; counts[i] = (int32_t)table_find(table, mask, ldg(hashes + i), &st); }
+  MM_HD void operator()(int64_t i) const { int64_t st; counts[i] = (int32_t)(table_find(table, mask, ldg(hashes + i), &st) & ~SLOT_GLOBAL_FREQ); }
+};
+struct GatherStrideFn {     // out[j] = in[j * step]
+  const uint32_t* in; int64_t step; uint32_t* out;
+  MM_HD void operator()(int64_t j) const { out[j] = ldg(in + j * step); }
+};
+struct LowerBoundFn {       // out[j] = first index of the sorted array with a[i] >= key[j]
+  const uint32_t* a; int64_t n; const uint32_t* key; int64_t* out;
+  MM_HD void operator()(int64_t j) const { out[j] = lower_bound_idx(a, n, ldg(key + j)); }
+};
+struct RunSumFn {           // gc[u] = sum of the values of run u
+  const uint32_t* val; const int64_t* runStart; const int32_t* runLen; uint32_t* gc;
+  MM_HD void operator()(int64_t u) const {
+    int64_t b = ldg(runStart + u); uint64_t acc = 0;
+    for (int32_t i = 0; i < ldg(runLen + u); i++) acc += ldg(val + b + i);
+    gc[u] = acc > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)acc;
+  }
+};
+struct GlobalCountFn {      // local unique hash lo+i -> its count in the merged (all shards) list of this hash range
+  const uint32_t* uHash; int64_t lo; const uint32_t* mergedHash; const uint32_t* mergedCount; int64_t nMerged; uint32_t* out;
+  MM_HD void operator()(int64_t i) const {
+    const uint32_t h = ldg(uHash + lo + i);
+    const int64_t p = lower_bound_idx(mergedHash, nMerged, h);
+    out[lo + i] = ldg(mergedCount + p);           // present by construction
+  }
+};
+struct FlagFreqFn {         // mark the slots of the hashes whose global count reaches the threshold
+  Slot* table; uint32_t mask; const uint32_t* uHash; const uint32_t* gCount; uint32_t threshold;
+  MM_HD void operator()(int64_t i) const {
+    if (ldg(gCount + i) < threshold) return;
+    const uint32_t h = ldg(uHash + i);
+    uint32_t s = slot_of(h, mask);
+    while (table[s].key != h || table[s].count == 0) s = (s + 1) & mask;
+    table[s].count |= SLOT_GLOBAL_FREQ;
+  }
 };
 
 struct Index {
@@ -102,6 +139,10 @@ struct Index {
   DevBuf<uint64_t> posKey;
   DevBuf<uint16_t> posSeq16; bool hasSeq16 = false;     // contig id of every CSR entry when n_contigs <= 65536
   int64_t n_unique = 0; int32_t freqThreshold = 0x7fffffff;
+  // contig-range shard of a larger reference: the sorted unique hashes and their local counts are kept after finalize() so
+  // that mm_index_sync_threshold can derive the occurrence threshold of the WHOLE reference (winSketch.hpp:452-495)
+  bool keepUnique = false; int32_t firstContig = 0; bool globalSynced = false; int32_t globalThreshold = 0x7fffffff;
+  DevBuf<uint32_t> uHash; DevBuf<int32_t> uCnt;
   // dups
   DevBuf<uint32_t> dupBits, dupIdx; DevBuf<uint64_t> dupLinks; int64_t n_dup = 0;
   int64_t total_bases = 0;
@@ -174,6 +215,7 @@ struct Index {
     table.ensure((size_t)slots); dev_memset(rt, table.p, 0, sizeof(Slot) * (size_t)slots);
     tableMask = (uint32_t)(slots - 1);
     foreach(rt, n_unique, TableInsertFn{table.p, tableMask, uniq.p, counts.p, starts.p});
+    if (keepUnique) { std::swap(uHash.p, uniq.p); std::swap(uHash.cap, uniq.cap); std::swap(uCnt.p, counts.p); std::swap(uCnt.cap, counts.cap); }
     uniq.release(); counts.release(); starts.release();
 
     posKey.ensure((size_t)n);
@@ -200,7 +242,7 @@ struct Index {
 
   int64_t device_bytes() const {
     return (int64_t)(miHash.bytes() + miWs.bytes() + table.bytes() + posKey.bytes() + posSeq16.bytes() + dupBits.bytes() + dupIdx.bytes() +
-                     dupLinks.bytes() + contigStart.bytes() + contigLen.bytes());
+                     dupLinks.bytes() + contigStart.bytes() + contigLen.bytes() + uHash.bytes() + uCnt.bytes());
   }
 };
 

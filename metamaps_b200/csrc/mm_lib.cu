@@ -190,7 +190,7 @@ int mm_index_stats(const mm_index* idx, int64_t* n_min, int64_t* n_unique, int32
   if (!idx) { g_err = "null index"; return MM_EINVAL; }
   if (n_min) *n_min = idx->ix.n;
   if (n_unique) *n_unique = idx->ix.n_unique;
-  if (freq) *freq = idx->ix.freqThreshold;
+  if (freq) *freq = idx->ix.globalSynced ? idx->ix.globalThreshold : idx->ix.freqThreshold;
   if (n_contigs) *n_contigs = idx->ix.n_contigs;
   if (bytes) *bytes = idx->ix.device_bytes();
   return MM_OK;
@@ -456,6 +456,7 @@ typedef int (*fn_ncclGetUniqueId)(NcclUid*);
 typedef int (*fn_ncclCommInitRank)(void**, int, NcclUid, int);
 typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_ncclCommDestroy)(void*);
+typedef int (*fn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
 static void* nccl_open() {
 #ifdef MM_HOST_EMU
   throw Error(MM_ENODEV, "NCCL is not available in the host-emulation test build");
@@ -519,6 +520,134 @@ static void allreduce_sum_f64(mm_ctx* c, double* buf, size_t n) {
   int rc = ((fn_ncclAllReduce)nccl_sym(c->ncclLib, "ncclAllReduce"))(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->rt.stream);
   if (rc != 0) throw Error(MM_ECUDA, "ncclAllReduce failed: " + std::to_string(rc));
   c->rt.launches++;
+}
+
+int mm_comm_set_rank(mm_ctx* c, int n_ranks, int rank) {
+  if (!c || n_ranks < 1 || rank < 0 || rank >= n_ranks) { g_err = "mm_comm_set_rank: bad arguments"; return MM_EINVAL; }
+  if (c->comm) { g_err = "mm_comm_set_rank: the context has an NCCL communicator"; return MM_EINVAL; }
+  c->nRanks = n_ranks; c->rank = rank;
+  return MM_OK;
+}
+// all-gather of `count` 32-bit words per rank (device buffers); recv holds nRanks * count words in rank order
+static void allgather_u32(mm_ctx* c, const uint32_t* send, uint32_t* recv, size_t count) {
+  if (count == 0) return;
+  if (c->comm && c->nRanks > 1) {
+    int rc = ((fn_ncclAllGather)nccl_sym(c->ncclLib, "ncclAllGather"))(send, recv, count, /*ncclUint32*/ 3, c->comm, c->rt.stream);
+    if (rc != 0) throw Error(MM_ECUDA, "ncclAllGather failed: " + std::to_string(rc));
+    c->rt.launches++;
+    return;
+  }
+  if (c->nRanks > 1 && c->hostAllreduce) {      // host transport: every rank fills its own slot of a zero buffer, then sum
+    std::vector<uint32_t> mine(count);
+    d2h(c->rt, mine.data(), send, 4 * count);
+    c->hostBuf.assign(count * (size_t)c->nRanks, 0.0);
+    for (size_t i = 0; i < count; i++) c->hostBuf[(size_t)c->rank * count + i] = (double)mine[i];
+    if (c->hostAllreduce(c->hostBuf.data(), (int64_t)c->hostBuf.size(), c->hostAllreduceUser) != 0) throw Error(MM_ECUDA, "host all-reduce callback failed");
+    std::vector<uint32_t> all(c->hostBuf.size());
+    for (size_t i = 0; i < all.size(); i++) all[i] = (uint32_t)c->hostBuf[i];
+    h2d(c->rt, recv, all.data(), 4 * all.size());
+    c->rt.sync();
+    return;
+  }
+  if (c->nRanks > 1) throw Error(MM_EINVAL, "multi-rank context without a transport (mm_comm_init or mm_comm_set_allreduce)");
+  d2d(c->rt, recv, send, 4 * count);
+}
+
+int mm_index_set_shard(mm_index* idx, int32_t first_contig_id, int32_t keep_counts) {
+  if (!idx || first_contig_id < 0) { g_err = "mm_index_set_shard: bad arguments"; return MM_EINVAL; }
+  if (idx->ix.finalized) { g_err = "mm_index_set_shard: call before mm_index_finalize"; return MM_EINVAL; }
+  idx->ix.firstContig = first_contig_id; idx->ix.keepUnique = keep_counts != 0;
+  return MM_OK;
+}
+int mm_index_sync_threshold(mm_index* idx, int32_t* global_threshold, int64_t* global_unique) {
+  MM_TRY
+  if (!idx || !idx->ix.finalized) throw Error(MM_EINVAL, "mm_index_sync_threshold: index not finalized");
+  Index& ix = idx->ix; mm_ctx* c = idx->ctx; Runtime& rt = c->rt; Prims& pr = c->pr;
+  if (!ix.keepUnique) throw Error(MM_EINVAL, "mm_index_sync_threshold: mm_index_set_shard(.., keep_counts = 1) was not called before finalize");
+  begin_call(c);
+  const int R = c->nRanks; const int64_t nu = ix.n_unique;
+  int64_t STEP = (int64_t)1 << 23;
+  if (const char* e = getenv("MM_SYNC_STEP")) { long long v = atoll(e); if (v >= 4) STEP = v; }
+  // 1. hash ranges: every STEP-th unique hash of rank 0 (the shards are statistically alike)
+  DevBuf<uint32_t> one, oneAll; one.ensure(1); oneAll.ensure((size_t)R);
+  uint32_t nRmine = (uint32_t)std::max<int64_t>(1, (nu + STEP - 1) / STEP);
+  h2d(rt, one.p, &nRmine, 4); allgather_u32(c, one.p, oneAll.p, 1);
+  uint32_t nR = 0; d2h(rt, &nR, oneAll.p, 4);                               // rank 0's value
+  DevBuf<uint32_t> bnd, bndAll; bnd.ensure(nR + 1); bndAll.ensure((size_t)R * (nR + 1));
+  dev_memset(rt, bnd.p, 0, 4 * ((size_t)nR + 1));
+  if (c->rank == 0 && nR > 1) foreach(rt, (int64_t)nR - 1, GatherStrideFn{ix.uHash.p + STEP, STEP, bnd.p + 1});
+  allgather_u32(c, bnd.p, bndAll.p, nR + 1);                                // slot 0 = rank 0's boundaries; [0] = 0
+  // 2. local offsets of the ranges
+  DevBuf<int64_t> dLo; dLo.ensure((size_t)nR + 1);
+  foreach(rt, (int64_t)nR, LowerBoundFn{ix.uHash.p, nu, bndAll.p, dLo.p});
+  std::vector<int64_t> lo((size_t)nR + 1);
+  d2h(rt, lo.data(), dLo.p, 8 * (size_t)nR); lo[0] = 0; lo[nR] = nu;
+  // 3. every rank's entry count per range
+  std::vector<uint32_t> cntMine(nR);
+  for (uint32_t j = 0; j < nR; j++) cntMine[j] = (uint32_t)(lo[j + 1] - lo[j]);
+  DevBuf<uint32_t> dCnt, dCntAll; dCnt.ensure(nR); dCntAll.ensure((size_t)R * nR);
+  h2d(rt, dCnt.p, cntMine.data(), 4 * (size_t)nR); allgather_u32(c, dCnt.p, dCntAll.p, nR);
+  std::vector<uint32_t> cntAll((size_t)R * nR); d2h(rt, cntAll.data(), dCntAll.p, 4 * cntAll.size());
+  // 4. per range: gather, merge, histogram, look the local hashes up
+  DevBuf<uint32_t> gLocal; gLocal.ensure((size_t)nu + 1);
+  DevBuf<uint32_t> sendH, sendC, recvH, recvC, catH, catC, srtH, srtC, uh, gc, gcs, hv; DevBuf<int32_t> runLen, hc; DevBuf<int64_t> runStart, nRuns;
+  nRuns.ensure(2);
+  std::vector<std::pair<uint32_t, int64_t>> hist;          // (count value, number of hashes), unsorted, merged below
+  int64_t uniqueGlobal = 0;
+  for (uint32_t j = 0; j < nR; j++) {
+    uint32_t maxc = 0; int64_t tot = 0;
+    for (int r = 0; r < R; r++) { maxc = std::max(maxc, cntAll[(size_t)r * nR + j]); tot += cntAll[(size_t)r * nR + j]; }
+    if (tot == 0) continue;
+    sendH.ensure(maxc); sendC.ensure(maxc); recvH.ensure((size_t)R * maxc); recvC.ensure((size_t)R * maxc);
+    dev_memset(rt, sendH.p, 0, 4 * (size_t)maxc); dev_memset(rt, sendC.p, 0, 4 * (size_t)maxc);
+    d2d(rt, sendH.p, ix.uHash.p + lo[j], 4 * (size_t)cntMine[j]); d2d(rt, sendC.p, ix.uCnt.p + lo[j], 4 * (size_t)cntMine[j]);
+    allgather_u32(c, sendH.p, recvH.p, maxc); allgather_u32(c, sendC.p, recvC.p, maxc);
+    catH.ensure((size_t)tot); catC.ensure((size_t)tot); srtH.ensure((size_t)tot); srtC.ensure((size_t)tot);
+    int64_t pos = 0;
+    for (int r = 0; r < R; r++) {
+      const size_t n_ = cntAll[(size_t)r * nR + j];
+      d2d(rt, catH.p + pos, recvH.p + (size_t)r * maxc, 4 * n_); d2d(rt, catC.p + pos, recvC.p + (size_t)r * maxc, 4 * n_);
+      pos += (int64_t)n_;
+    }
+    pr.sort_pairs<uint32_t, uint32_t>(catH.p, srtH.p, catC.p, srtC.p, tot);
+    uh.ensure((size_t)tot); runLen.ensure((size_t)tot + 1); runStart.ensure((size_t)tot + 1); gc.ensure((size_t)tot); gcs.ensure((size_t)tot);
+    pr.rle<uint32_t>(srtH.p, uh.p, runLen.p, nRuns.p, tot);
+    int64_t nuj = 0; d2h(rt, &nuj, nRuns.p, 8);
+    pr.exclusive_sum<int32_t, int64_t>(runLen.p, runStart.p, nuj);
+    foreach(rt, nuj, RunSumFn{srtC.p, runStart.p, runLen.p, gc.p});
+    uniqueGlobal += nuj;
+    // histogram of the global counts of this range
+    pr.sort_keys<uint32_t>(gc.p, gcs.p, nuj);
+    hv.ensure((size_t)nuj); hc.ensure((size_t)nuj + 1);
+    pr.rle<uint32_t>(gcs.p, hv.p, hc.p, nRuns.p, nuj);
+    int64_t nb = 0; d2h(rt, &nb, nRuns.p, 8);
+    std::vector<uint32_t> v((size_t)nb); std::vector<int32_t> k_((size_t)nb);
+    d2h(rt, v.data(), hv.p, 4 * (size_t)nb); d2h(rt, k_.data(), hc.p, 4 * (size_t)nb);
+    for (int64_t b = 0; b < nb; b++) hist.emplace_back(v[(size_t)b], (int64_t)k_[(size_t)b]);
+    if (cntMine[j]) foreach(rt, (int64_t)cntMine[j], GlobalCountFn{ix.uHash.p, lo[j], uh.p, gc.p, nuj, gLocal.p});
+    rt.sync();
+  }
+  // 5. the threshold of the whole reference (computeFreqHist, winSketch.hpp:452-495) and the local flags
+  std::sort(hist.begin(), hist.end());
+  std::vector<std::pair<uint32_t, int64_t>> hm;
+  for (auto& p : hist) { if (!hm.empty() && hm.back().first == p.first) hm.back().second += p.second; else hm.push_back(p); }
+  float percentageThreshold = 0.001f;
+  int64_t toIgnore = (int64_t)(uniqueGlobal * percentageThreshold / 100);
+  int64_t sum = 0; int32_t T = 0x7fffffff;
+  for (int64_t b = (int64_t)hm.size() - 1; b >= 0; b--) {
+    sum += hm[(size_t)b].second;
+    if (sum < toIgnore) T = (int32_t)hm[(size_t)b].first;
+    else if (sum == toIgnore) { T = (int32_t)hm[(size_t)b].first; break; }
+    else break;
+  }
+  if (nu > 0 && T != 0x7fffffff) foreach(rt, nu, FlagFreqFn{ix.table.p, ix.tableMask, ix.uHash.p, gLocal.p, (uint32_t)T});
+  ix.freqThreshold = 0x7fffffff;            // from now on only the flags decide (flagged counts compare above everything)
+  ix.globalSynced = true; ix.globalThreshold = T;
+  ix.uHash.release(); ix.uCnt.release();
+  end_call(c);
+  if (global_threshold) *global_threshold = T;
+  if (global_unique) *global_unique = uniqueGlobal;
+  MM_CATCH
 }
 
 // ------------------------------------------------------------------------------------------------ K7/K8

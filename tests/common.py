@@ -236,3 +236,44 @@ def fallback_workloads():
     reads = [np.concatenate([flankL[-1500:], rep[:3000]]), rep[100:5100].copy(), np.concatenate([rep[-2500:], flankR[:2500]])]
     out["low_complexity"] = ([synth.codes_to_ascii(c0)], [synth.codes_to_ascii(r) for r in reads], 16, 6, 1000)
     return out
+
+
+def sharded_case(seed=5, n_contigs=6, L=200_000, w=10, n_reads=60):
+    """A reference whose global occurrence threshold is finite (70) although no half of it reaches it: five 25-base units
+    (one full window of w = 10 k-mers, so their smallest k-mer is a minimizer in every copy) planted 90/70/55/41/33 times
+    over all contigs.  Returns (db, contig ASCII list, read ASCII list, w, contig_taxon, contig_len, n_taxa)."""
+    rng = np.random.default_rng(seed)
+    contigs = [rng.integers(0, 4, L, dtype=np.uint8) for _ in range(n_contigs)]
+    for copies in (90, 70, 55, 41, 33):
+        unit = rng.integers(0, 4, 25, dtype=np.uint8)
+        for _ in range(copies):
+            ci = int(rng.integers(0, n_contigs)); pos = int(rng.integers(0, L - 50))
+            contigs[ci][pos:pos + 25] = unit
+    names = [f"C{i}|kraken:taxid|{i + 1}|x" for i in range(n_contigs)]
+    db = synth.SynthDB(names, [str(i + 1) for i in range(n_contigs)], contigs)
+    _, reads, _ = synth.make_reads(db, seed + 1, n_reads, 3000, err=0.08)
+    contig_taxon = np.arange(n_contigs, dtype=np.int32)
+    contig_len = np.full(n_contigs, L, np.int64)
+    return db, [synth.codes_to_ascii(c) for c in contigs], [synth.codes_to_ascii(r) for r in reads], w, contig_taxon, contig_len, n_contigs
+
+
+MAPPING_KEYS = ("read", "seq", "pos", "shared", "sketch", "strand", "identity", "mapq")
+
+
+def check_shard_walk_equals_full(ctx, contigs, reads, k, w, contig_taxon, contig_len, n_taxa, cuts, min_len=1000):
+    """Single process: the reference cut into contig-range shards walked one after the other (per-shard thresholds, the
+    reference's --maxmemory behaviour) gives the unsharded result whenever no hash is over-frequent."""
+    from metamaps_b200 import capi, pipeline
+    full = build_index(ctx, contigs, k, w)
+    a = pipeline.map_and_classify(ctx, full, reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa, min_read_len=min_len)
+    shards = []
+    bounds = [0] + list(cuts) + [len(contigs)]
+    for c0, c1 in zip(bounds[:-1], bounds[1:]):
+        ix = capi.Index(ctx, k, w); ix.set_shard(c0, keep_counts=False); ix.add(contigs[c0:c1]); ix.finalize(); shards.append(ix)
+    b = pipeline.map_and_classify_sharded(ctx, shards, reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa, min_read_len=min_len)
+    assert len(a["read"]) > 0
+    for key in MAPPING_KEYS:
+        assert np.array_equal(a[key], b[key]), key
+    assert a["em"]["iters"] == b["em"]["iters"]
+    assert np.array_equal(a["em"]["f"], b["em"]["f"]) and np.array_equal(a["em"]["best"], b["em"]["best"])
+    return a

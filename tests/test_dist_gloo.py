@@ -53,3 +53,67 @@ def test_em_two_ranks_equals_single_rank(oracle, tmp_path):
         assert np.abs(p["post"] - ref["posterior"][int(p["m0"]):int(p["m1"])]).max() <= 1e-6
         assert np.array_equal(p["best"], ref["best"][int(p["lo"]):int(p["hi"])])
     assert np.array_equal(parts[0]["f"], parts[1]["f"])
+
+
+# ---------------------------------------------------------------------------------------------- contig-range shards
+def _shard_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ["MM_SYNC_STEP"] = "50000"            # several hash ranges even on this small reference
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from metamaps_b200 import capi, pipeline
+    from tests import common
+    from tests.conftest import build_emu
+    lib = capi.load(build_emu())
+    ctx = capi.Context(0, lib)
+
+    def allreduce(a):
+        dist.all_reduce(torch.from_numpy(a))
+    ctx.set_allreduce(allreduce); ctx.set_rank(world, rank)
+    db, contigs, reads, w, contig_taxon, contig_len, T = common.sharded_case()
+    per = len(contigs) // world
+    c0, c1 = rank * per, (rank + 1) * per if rank + 1 < world else len(contigs)
+    ix = capi.Index(ctx, 16, w); ix.set_shard(c0, keep_counts=True); ix.add(contigs[c0:c1]); ix.finalize()
+    local_thr = ix.stats()["freq_threshold"]
+    thr, uniq = ix.sync_threshold()
+
+    def exchange(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    n = len(reads); lo, hi = rank * n // world, (rank + 1) * n // world
+    res = pipeline.map_and_classify_sharded(ctx, [ix], reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=T,
+                                            exchange=exchange, read_range=(lo, hi))
+    np.savez(os.path.join(tmp, f"shard{rank}.npz"), thr=thr, uniq=uniq, local_thr=local_thr, lo=lo, hi=hi, f=res["em"]["f"], iters=res["em"]["iters"],
+             post=res["em"]["posterior"], **{k_: res[k_] for k_ in common.MAPPING_KEYS})
+    dist.destroy_process_group()
+
+
+def test_contig_shards_two_ranks_equal_unsharded_reference(tmp_path):
+    """World size 2 (gloo): each rank indexes half of the contigs, the occurrence threshold of the WHOLE reference is
+    agreed through mm_index_sync_threshold, every rank maps all reads against its shard, mappings are exchanged, each
+    rank finalises its block of reads and the EM sums are all-reduced.  Everything must equal the one-index run."""
+    from metamaps_b200 import capi, pipeline
+    from tests import common
+    from tests.conftest import build_emu
+    lib = capi.load(build_emu())
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ctx = capi.Context(0, lib)
+    db, contigs, reads, w, contig_taxon, contig_len, T = common.sharded_case()
+    full = common.build_index(ctx, contigs, 16, w)
+    st = full.stats()
+    assert st["freq_threshold"] == 70                    # finite: over-frequent hashes exist ...
+    ref = pipeline.map_and_classify(ctx, full, reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=T)
+    parts = [np.load(os.path.join(str(tmp_path), f"shard{r}.npz")) for r in range(2)]
+    for p in parts:
+        assert int(p["thr"]) == st["freq_threshold"] and int(p["uniq"]) == st["n_unique"]
+        assert int(p["local_thr"]) != st["freq_threshold"]          # ... which no shard can see on its own
+        sel = (ref["read"] >= int(p["lo"])) & (ref["read"] < int(p["hi"]))
+        for key in common.MAPPING_KEYS:
+            assert np.array_equal(p[key], ref[key][sel]), key          # coordinates, counts, identities, mapq: identical
+        assert int(p["iters"]) == ref["em"]["iters"]
+        assert np.abs(p["f"] - ref["em"]["f"]).max() <= 1e-6
+        assert np.abs(p["post"] - ref["em"]["posterior"][sel]).max() <= 1e-6
+    assert np.array_equal(parts[0]["f"], parts[1]["f"])
+    assert sum(len(p["read"]) for p in parts) == len(ref["read"])

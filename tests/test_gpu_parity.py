@@ -170,3 +170,13 @@ def test_kernel_variants(oracle, small_workload, monkeypatch, env):
     reads = [synth.codes_to_ascii(r) for r in small_workload["reads"]]
     common.check_map_vs_oracle(ctx, oracle, contigs, reads, 16, 13)
     ctx.close()
+
+
+def test_contig_shards_walked_in_one_process(gpu_ctx, small_workload):
+    db = small_workload["db"]
+    contigs = [synth.codes_to_ascii(c) for c in db.contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"]]
+    taxa = sorted(set(db.contig_taxon)); tidx = {t: i for i, t in enumerate(taxa)}
+    contig_taxon = np.array([tidx[t] for t in db.contig_taxon], np.int32)
+    contig_len = np.array([len(c) for c in db.contig_codes], np.int64)
+    common.check_shard_walk_equals_full(gpu_ctx, contigs, reads, 16, 13, contig_taxon, contig_len, len(taxa), cuts=[2, 5, 6])

@@ -135,3 +135,13 @@ def test_sweep_variants(oracle, small_workload, monkeypatch, env):
     if "MM_SWEEP" not in env:
         assert st["smem_swept"] > 0          # the banded path really ran
     ctx.close()
+
+
+def test_contig_shards_walked_in_one_process(emu_ctx, small_workload):
+    db = small_workload["db"]
+    contigs = [synth.codes_to_ascii(c) for c in db.contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"][:80]]
+    taxa = sorted(set(db.contig_taxon)); tidx = {t: i for i, t in enumerate(taxa)}
+    contig_taxon = np.array([tidx[t] for t in db.contig_taxon], np.int32)
+    contig_len = np.array([len(c) for c in db.contig_codes], np.int64)
+    common.check_shard_walk_equals_full(emu_ctx, contigs, reads, 16, 13, contig_taxon, contig_len, len(taxa), cuts=[3, 7])
