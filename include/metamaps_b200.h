@@ -124,6 +124,13 @@ int mm_map_batch(mm_ctx* ctx, const mm_index* idx, const char* reads, const int6
 int mm_map_batch_dev(mm_ctx* ctx, const mm_index* idx, const void* reads_dev, const int64_t* offsets_host,
                      int32_t n_reads, const mm_map_params* params, mm_map_summary* summary);
 
+/* Double-buffered input staging (the pinned, double-buffered H2D of a streaming host).  mm_stage_reads_async copies a
+ * batch of reads host->device on the context's copy stream and returns at once (reads_host should be pinned memory for a
+ * truly asynchronous copy; offsets are copied); mm_map_batch_staged maps the batch staged in `slot` (0 or 1) -- the copy
+ * is awaited on the device, so staging batch i+1 before mapping batch i overlaps the transfer with the kernels. */
+int mm_stage_reads_async(mm_ctx* ctx, int slot, const char* reads_host, const int64_t* offsets, int32_t n_reads);
+int mm_map_batch_staged(mm_ctx* ctx, const mm_index* idx, int slot, const mm_map_params* params, mm_map_summary* summary);
+
 /* Per-read: sketch size s (0 for skipped reads), minimumHits, offsets into the candidate arrays (n_reads+1).
  * Any pointer may be NULL. */
 int mm_map_fetch_reads(mm_ctx* ctx, int32_t* sketch_size, int32_t* minimum_hits, int64_t* cand_offsets);

@@ -51,6 +51,8 @@ SYMBOLS = {
     "mm_index_destroy": (None, [C.c_void_p]),
     "mm_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, _i64p, C.c_int32, C.POINTER(MapParams), C.POINTER(MapSummary)]),
     "mm_map_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _i64p, C.c_int32, C.POINTER(MapParams), C.POINTER(MapSummary)]),
+    "mm_stage_reads_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _i64p, C.c_int32]),
+    "mm_map_batch_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(MapParams), C.POINTER(MapSummary)]),
     "mm_map_fetch_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mm_map_fetch_candidates": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
     "mm_map_fetch_sketch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
@@ -194,6 +196,11 @@ class Context:
         self._ar = ALLREDUCE_FN(tramp)        # keep the trampoline alive
         self._check(self.lib.mm_comm_set_allreduce(self.h, C.cast(self._ar, C.c_void_p), None))
 
+    def stage_reads(self, slot: int, host_ptr: int, offsets):
+        """Start the H2D copy of a batch (one host buffer, ideally pinned) into staging slot 0/1; returns at once."""
+        offs = np.ascontiguousarray(offsets, np.int64)
+        self._check(self.lib.mm_stage_reads_async(self.h, slot, C.c_void_p(host_ptr), offs, len(offs) - 1))
+
     n_ranks_hint = 1       # > 1 once a communicator / host transport is attached: collective calls must not be skipped
 
     def set_rank(self, n_ranks: int, rank: int):
@@ -318,12 +325,15 @@ def nloc_batch(lib, seq, read_off, read_len, contig_len, contig_taxon, n_taxa: i
 
 def map_reads(ctx: Context, index: Index, reads=None, perc_identity: float = 80.0, min_read_len: int = 1000,
               dev_ptr: int | None = None, host_ptr: int | None = None, offsets=None, fetch: bool = True,
-              fetch_sketch: bool = False):
+              fetch_sketch: bool = False, staged_slot: int | None = None):
     """skch::Map over a batch.  reads: list of ASCII bytes (host); or host_ptr+offsets (one host buffer, e.g.
     pinned); or dev_ptr+offsets (device-resident ASCII)."""
     p = MapParams(perc_identity, min_read_len, 1, 0)
     s = MapSummary()
-    if host_ptr is not None:
+    if staged_slot is not None:
+        offs = np.ascontiguousarray(offsets, np.int64)
+        ctx._check(ctx.lib.mm_map_batch_staged(ctx.h, index.h, staged_slot, C.byref(p), C.byref(s)))
+    elif host_ptr is not None:
         offs = np.ascontiguousarray(offsets, np.int64)
         ctx._check(ctx.lib.mm_map_batch(ctx.h, index.h, C.cast(host_ptr, C.c_char_p), offs, len(offs) - 1, C.byref(p), C.byref(s)))
     elif dev_ptr is None:

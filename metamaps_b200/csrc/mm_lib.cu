@@ -11,6 +11,7 @@
 
 #ifndef MM_HOST_EMU
 #include <dlfcn.h>
+#include <thread>
 #endif
 
 using namespace mm;
@@ -33,6 +34,15 @@ struct mm_ctx {
     DevBuf<int64_t> dOff, dBest;
     DevBuf<uint32_t> dIota, dPerm, dTaxT;
   } scr;
+  // double-buffered input staging (mm_stage_reads_async)
+  struct Stage { DevBuf<uint8_t> asc; std::vector<int64_t> off; int32_t n = -1;
+#ifndef MM_HOST_EMU
+                 cudaEvent_t ready = nullptr; std::thread feeder; int feedErr = 0;
+                 void join() { if (feeder.joinable()) feeder.join(); }
+#else
+                 void join() {}
+#endif
+  } stage[2];
   // NCCL (multi-GPU EM), bound at run time
   void* ncclLib = nullptr; void* comm = nullptr; int nRanks = 1, rank = 0;
   mm_allreduce_fn hostAllreduce = nullptr; void* hostAllreduceUser = nullptr; std::vector<double> hostBuf;
@@ -88,6 +98,7 @@ int mm_ctx_create(int device, mm_ctx** out) {
   c->rt.sm_count = prop.multiProcessorCount;
   MM_CUDA(cudaStreamCreateWithFlags(&c->rt.stream, cudaStreamNonBlocking));
   MM_CUDA(cudaStreamCreateWithFlags(&c->rt.side, cudaStreamNonBlocking));
+  MM_CUDA(cudaStreamCreateWithFlags(&c->rt.copy, cudaStreamNonBlocking));
 #endif
   *out = c;
   MM_CATCH
@@ -100,10 +111,11 @@ void mm_ctx_destroy(mm_ctx* c) {
 #endif
   mm_comm_destroy(c);
 #ifndef MM_HOST_EMU
-  cudaStream_t s = c->rt.stream, s2 = c->rt.side;
-  cudaStreamSynchronize(s2);
+  cudaStream_t s = c->rt.stream, s2 = c->rt.side, s3 = c->rt.copy;
+  cudaStreamSynchronize(s2); cudaStreamSynchronize(s3);
+  for (auto& st : c->stage) { st.join(); if (st.ready) cudaEventDestroy(st.ready); }
   delete c;
-  cudaStreamDestroy(s); cudaStreamDestroy(s2);
+  cudaStreamDestroy(s); cudaStreamDestroy(s2); cudaStreamDestroy(s3);
 #else
   delete c;
 #endif
@@ -255,6 +267,54 @@ int mm_map_batch(mm_ctx* c, const mm_index* idx, const char* reads, const int64_
 int mm_map_batch_dev(mm_ctx* c, const mm_index* idx, const void* dev, const int64_t* offsets, int32_t n, const mm_map_params* p, mm_map_summary* out) {
   if (!dev) { g_err = "mm_map_batch_dev: null device pointer"; return MM_EINVAL; }
   return map_impl(c, idx, nullptr, dev, offsets, n, p, out);
+}
+int mm_stage_reads_async(mm_ctx* c, int slot, const char* reads, const int64_t* offsets, int32_t n) {
+  MM_TRY
+  if (!c || slot < 0 || slot > 1 || !offsets || n < 0 || (!reads && n > 0)) throw Error(MM_EINVAL, "mm_stage_reads_async: bad arguments");
+  auto& st = c->stage[slot];
+  const int64_t bytes = offsets[n] - offsets[0];
+  if (bytes < 0) throw Error(MM_EINVAL, "mm_stage_reads_async: offsets not ascending");
+  st.off.assign(offsets, offsets + n + 1);
+  for (auto& o : st.off) o -= offsets[0];
+  st.n = n;
+#ifndef MM_HOST_EMU
+  MM_CUDA(cudaSetDevice(c->rt.device));
+  st.asc.ensure((size_t)bytes + 16);
+  if (!st.ready) MM_CUDA(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
+  // The DMA queue is first-in first-out across streams: if the whole batch were queued at once, the small host->device
+  // copies of the batch being mapped meanwhile would wait behind 100s of MB.  A feeder thread therefore hands the copy
+  // to the engine 8 MB at a time (one piece in flight), and records the slot's event when the last piece is done.
+  st.join();
+  st.feedErr = 0;
+  {
+    const int dev = c->rt.device; cudaStream_t cs = c->rt.copy; uint8_t* dst = st.asc.p; const char* src = reads + offsets[0];
+    cudaEvent_t ev = st.ready; int* err = &st.feedErr;
+    st.feeder = std::thread([=]() {
+      if (cudaSetDevice(dev) != cudaSuccess) { *err = 1; return; }
+      for (int64_t o = 0; o < bytes; o += (int64_t)8 << 20) {
+        const int64_t nb = std::min<int64_t>((int64_t)8 << 20, bytes - o);
+        if (cudaMemcpyAsync(dst + o, src + o, (size_t)nb, cudaMemcpyHostToDevice, cs) != cudaSuccess || cudaStreamSynchronize(cs) != cudaSuccess) { *err = 1; return; }
+      }
+      if (cudaEventRecord(ev, cs) != cudaSuccess) *err = 1;
+    });
+  }
+#else
+  st.asc.ensure((size_t)bytes + 16);
+  if (bytes) memcpy(st.asc.p, reads + offsets[0], (size_t)bytes);
+#endif
+  MM_CATCH
+}
+int mm_map_batch_staged(mm_ctx* c, const mm_index* idx, int slot, const mm_map_params* p, mm_map_summary* out) {
+  if (!c || slot < 0 || slot > 1 || c->stage[slot].n < 0) { g_err = "mm_map_batch_staged: nothing staged in this slot"; return MM_EINVAL; }
+  auto& st = c->stage[slot];
+#ifndef MM_HOST_EMU
+  st.join();                                    // the last piece has been handed over and the event recorded
+  if (st.feedErr) { g_err = "mm_stage_reads_async: the host->device copy failed"; return MM_ECUDA; }
+  cudaSetDevice(c->rt.device);
+  cudaError_t e = cudaStreamWaitEvent(c->rt.stream, st.ready, 0);
+  if (e != cudaSuccess) { g_err = std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e); return MM_ECUDA; }
+#endif
+  return map_impl(c, idx, nullptr, st.asc.p, st.off.data(), st.n, p, out);
 }
 struct MinHitsOfFn {
   const int32_t* sOf; const int32_t* tab; int32_t* out;

@@ -52,6 +52,7 @@ struct Runtime {
   int device = 0;
   cudaStream_t stream = 0;
   cudaStream_t side = 0;         // side stream: work that is off the critical path (joined with events)
+  cudaStream_t copy = 0;         // copy stream: input staging for the NEXT batch (mm_stage_reads_async)
   int sm_count = 148;
   int64_t launches = 0;          // kernels launched since reset()
   double total_ms = 0;           // filled by StageTimer users

@@ -81,14 +81,15 @@ def classify_mappings(ctx: capi.Context, m: dict, n_reads: int, read_len: np.nda
 
 def map_and_classify(ctx: capi.Context, index: capi.Index, *, reads=None, dev_ptr=None, host_ptr=None, offsets=None, read_len=None,
                      contig_len: np.ndarray, contig_taxon: np.ndarray, n_taxa: int, perc_identity: float = 80.0,
-                     min_read_len: int = 1000, em_max_iter: int = 0, stats: dict | None = None):
+                     min_read_len: int = 1000, em_max_iter: int = 0, stats: dict | None = None, staged_slot: int | None = None):
     """One pass of the hot path over one batch of reads.  Returns per-mapping arrays + EM result.
 
     mm_map_batch (K1,K3-K5) -> mm_map_fetch_mappings (accepted mappings compacted on the device, identities on the host
     through glibc) -> mm_mapq_batch (K6) -> mm_nloc_batch (host) -> mm_em_run (K7/K8)."""
     import time
     t0 = time.perf_counter()
-    res = capi.map_reads(ctx, index, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets, fetch=False)
+    res = capi.map_reads(ctx, index, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets, fetch=False,
+                         staged_slot=staged_slot)
     t1 = time.perf_counter()
     if stats is not None:
         stats["map"] = res["stats"]

@@ -277,3 +277,23 @@ def check_shard_walk_equals_full(ctx, contigs, reads, k, w, contig_taxon, contig
     assert a["em"]["iters"] == b["em"]["iters"]
     assert np.array_equal(a["em"]["f"], b["em"]["f"]) and np.array_equal(a["em"]["best"], b["em"]["best"])
     return a
+
+
+def check_staged_equals_direct(ctx, contigs, reads, k, w):
+    """mm_stage_reads_async + mm_map_batch_staged (both slots, staged ahead) give what mm_map_batch gives."""
+    from metamaps_b200 import capi
+    ix = build_index(ctx, contigs, k, w)
+    half = len(reads) // 2
+    batches = [reads[:half], reads[half:]]
+    direct = [capi.map_reads(ctx, ix, b, 80.0, 1000) for b in batches]
+    bufs = []
+    for b in batches:
+        data = np.frombuffer(b"".join(b), np.uint8).copy()
+        off = np.zeros(len(b) + 1, np.int64); off[1:] = np.cumsum([len(x) for x in b])
+        bufs.append((data, off))
+    ctx.stage_reads(0, bufs[0][0].ctypes.data, bufs[0][1])
+    ctx.stage_reads(1, bufs[1][0].ctypes.data, bufs[1][1])          # staged before batch 0 is mapped
+    for slot in (0, 1):
+        got = capi.map_reads(ctx, ix, None, 80.0, 1000, offsets=bufs[slot][1], staged_slot=slot)
+        for key in ("s", "cand_off", "seq", "pos", "shared", "votes", "accepted", "valid"):
+            assert np.array_equal(got[key], direct[slot][key]), (slot, key)

@@ -145,3 +145,8 @@ def test_contig_shards_walked_in_one_process(emu_ctx, small_workload):
     contig_taxon = np.array([tidx[t] for t in db.contig_taxon], np.int32)
     contig_len = np.array([len(c) for c in db.contig_codes], np.int64)
     common.check_shard_walk_equals_full(emu_ctx, contigs, reads, 16, 13, contig_taxon, contig_len, len(taxa), cuts=[3, 7])
+
+
+def test_staged_reads(emu_ctx, small_workload):
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    common.check_staged_equals_direct(emu_ctx, contigs, [synth.codes_to_ascii(r) for r in small_workload["reads"][:60]], 16, 13)
