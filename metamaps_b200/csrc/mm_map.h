@@ -94,6 +94,86 @@ struct AmbigResolveFn {
   }
 };
 
+#ifndef MM_HOST_EMU
+// Device fast path of K3: one CTA per read.  The read's minimizers (hash, wpos|strand) are radix-sorted by hash in shared
+// memory (stable, like the global sort it replaces), equal-hash runs are reduced to their first element (std::unique,
+// computeMap.hpp:295) and written, compacted, to the read's own slice of tHash/tStrand; reads with a hash that occurs
+// on both strands are listed for the std::sort replay (AmbigResolveFn).  Three instantiations cover reads of up to
+// 1024 / 2048 / 6144 minimizers; a longer read sends the whole batch through the global-sort path.
+template <int ITEMS>
+struct K3Block {
+  typedef cub::BlockLoad<uint32_t, 256, ITEMS, cub::BLOCK_LOAD_WARP_TRANSPOSE> Load;
+  typedef cub::BlockRadixSort<uint32_t, 256, ITEMS, uint32_t> Sort;
+  union Temp { typename Load::TempStorage load; typename Sort::TempStorage sort; };
+};
+template <int ITEMS>
+__global__ void __launch_bounds__(256) read_sketch_block_kernel(const uint32_t* hash, const uint32_t* ws, const int64_t* seqOff, int32_t n_reads, int32_t nLo,
+                                                                int32_t nHi, uint32_t* tHash, uint8_t* tStrand, int32_t* sOf, unsigned long long* ambCount,
+                                                                int32_t* ambList, int64_t ambCap) {
+  typedef K3Block<ITEMS> B;
+  typedef cub::BlockScan<int32_t, 256> Scan;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  typename B::Temp& tmp = *reinterpret_cast<typename B::Temp*>(dyn);
+  __shared__ typename Scan::TempStorage scanTmp;
+  __shared__ uint32_t lastKey[256], lastVal[256];
+  for (int32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+    const int64_t b = seqOff[r]; const int32_t n = (int32_t)(seqOff[r + 1] - b);
+    if (n <= nLo || n > nHi) continue;
+    uint32_t keys[ITEMS], vals[ITEMS];
+    typename B::Load(tmp.load).Load(hash + b, keys, n, 0xFFFFFFFFu);      // blocked arrangement, emission order; padding sorts last
+    __syncthreads();
+    typename B::Load(tmp.load).Load(ws + b, vals, n, 0xFFFFFFFFu);
+    __syncthreads();
+    typename B::Sort(tmp.sort).Sort(keys, vals);                            // stable LSD radix sort by hash
+    lastKey[threadIdx.x] = keys[ITEMS - 1]; lastVal[threadIdx.x] = vals[ITEMS - 1];
+    __syncthreads();
+    uint32_t pk = threadIdx.x > 0 ? lastKey[threadIdx.x - 1] : 0u, pv = threadIdx.x > 0 ? lastVal[threadIdx.x - 1] : 0u;
+    const int32_t i0 = (int32_t)threadIdx.x * ITEMS;
+    uint32_t headMask = 0; int32_t cnt = 0; int amb = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const int32_t i = i0 + j;
+      const bool real = i < n;
+      const bool head = real && (i == 0 || keys[j] != pk);
+      amb |= (real && !head && ((vals[j] ^ pv) & 1u)) ? 1 : 0;             // same hash, other strand (AmbigDetectFn)
+      headMask |= head ? (1u << j) : 0u; cnt += head ? 1 : 0;
+      pk = keys[j]; pv = vals[j];
+    }
+    int32_t base = 0, total = 0;
+    Scan(scanTmp).ExclusiveSum(cnt, base, total);
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      if (headMask & (1u << j)) { tHash[b + base] = keys[j]; tStrand[b + base] = (uint8_t)(vals[j] & 1u); base++; }
+    }
+    const int anyAmb = __syncthreads_or(amb);
+    if (threadIdx.x == 0) {
+      sOf[r] = total;
+      if (anyAmb) { const unsigned long long slot = atomicAdd(ambCount, 1ull); if ((int64_t)slot < ambCap) ambList[slot] = r; }
+    }
+    __syncthreads();
+  }
+}
+// reads outside every class: sketch size 0 for empty reads, overflow flag for oversize ones
+struct K3EdgeFn {
+  const int64_t* seqOff; int32_t nMax; int32_t* sOf; unsigned long long* overflow;
+  MM_HD void operator()(int64_t r) const {
+    const int64_t n = ldg(seqOff + r + 1) - ldg(seqOff + r);
+    if (n == 0) sOf[r] = 0;
+    else if (n > nMax) { sOf[r] = 0; atomic_add_u64(overflow, 1ull); }
+  }
+};
+// the reads' compacted sketches -> one dense array (qOff = prefix sum of the sketch sizes)
+__global__ void __launch_bounds__(256) read_sketch_gather_kernel(const uint32_t* tHash, const uint8_t* tStrand, const int64_t* seqOff, const int64_t* qOff,
+                                                                 const int32_t* sOf, int32_t n_reads, uint32_t* qHash, uint8_t* qStrand, int32_t* qRead) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += nw) {
+    const int64_t src = seqOff[r], dst = qOff[r]; const int32_t s = sOf[r];
+    for (int32_t i = lane; i < s; i += 32) { qHash[dst + i] = tHash[src + i]; qStrand[dst + i] = tStrand[src + i]; qRead[dst + i] = (int32_t)r; }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------- K4
 struct ProbeFn {            // computeMap.hpp:307-321
   const Slot* table; uint32_t mask; const uint32_t* qHash; int32_t freqThreshold; int32_t* hitCnt; int64_t* hitStart; int64_t n;
@@ -1081,7 +1161,7 @@ struct Mapper {
   DevBuf<int32_t> oShared, oPos, oValid, oIstar, oVotes, oAccept, readMapped;
   DevBuf<int64_t> qOff, idx, hitStart, hitOff, readHitOff, candOff, beg0, fe, le, evOff, stOff, oOptS, oOptE;
   DevBuf<uint64_t> key, key2, hits, hits2;
-  DevBuf<uint32_t> ws2, qHash, state; DevBuf<uint8_t> qStrand; DevBuf<uint2> ev;
+  DevBuf<uint32_t> ws2, qHash, state; DevBuf<uint8_t> qStrand, tStrand; DevBuf<uint2> ev;
   DevBuf<int32_t> ambig, ambigList, red, swTile, swLocal, swRedo; DevBuf<unsigned long long> scal; int64_t n_ambig = 0;
   DevBuf<uint32_t> swKey, swKey2, swVal, swOrder; int32_t maxSketch = 0;
   DevBuf<int32_t> qRead, hflag, lhead, keptPerRead; DevBuf<int64_t> hfidx, flagged, lidx; int64_t n_hits_all = 0;
@@ -1142,30 +1222,73 @@ struct Mapper {
     bool ambigPending = false;
     {
       StageTimer t(rt, &st.ms[1]);
-      key.ensure((size_t)nm + 1); key2.ensure((size_t)nm + 1); ws2.ensure((size_t)nm + 1); head.ensure((size_t)nm + 2); idx.ensure((size_t)nm + 2);
-      foreach(rt, nm, ReadKeyFn{rs.hash.p, rs.seqOff.p, n_reads, key.p});
-      int bits = 33; while (bits < 64 && ((int64_t)1 << (bits - 32)) < n_reads) bits++;
-      pr.sort_pairs<uint64_t, uint32_t>(key.p, key2.p, rs.ws.p, ws2.p, nm, bits);
-      foreach(rt, nm + 1, HeadFlagFn{key2.p, head.p, nm});
-      pr.exclusive_sum<int32_t, int64_t>(head.p, idx.p, nm + 1);
-      d2h(rt, &n_q, idx.p + nm, sizeof(int64_t));
-      qHash.ensure((size_t)n_q + 1); qStrand.ensure((size_t)n_q + 1); qRead.ensure((size_t)n_q + 1);
-      foreach(rt, nm, UniqueScatterFn{key2.p, ws2.p, head.p, idx.p, qHash.p, qStrand.p, qRead.p});
-      foreach(rt, (int64_t)n_reads + 1, ReadSketchOffFn{rs.seqOff.p, idx.p, qOff.p, sOf.p, n_reads});
-      {   // duplicate hashes with both strands: settle the survivor like std::sort + std::unique would
-        ambig.ensure((size_t)n_reads + 1); ambigList.ensure(4096); scal.ensure(4);
+      bool blockPath = false;
+      unsigned long long na = 0; int32_t maxS = 0;
+      ambig.ensure((size_t)n_reads + 1); ambigList.ensure(4096); scal.ensure(4);
+      key.ensure((size_t)nm + 1);                     // scratch of the std::sort replay
+#ifndef MM_HOST_EMU
+      if (!getenv("MM_K3_GLOBAL") && nm > 0) {
+        // per-read block sort (read_sketch_block_kernel); scal[0] = ambiguous reads, [1] = max sketch, [2] = oversize reads, [3] = n_q
+        ws2.ensure((size_t)nm + 1); tStrand.ensure((size_t)nm + 1);
+        dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);
+        static bool attrK3 = false;
+        if (!attrK3) {
+          MM_CUDA(cudaFuncSetAttribute(read_sketch_block_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Block<24>::Temp)));
+          attrK3 = true;
+        }
+        int ambCap = (int)ambigList.cap;
+        int grid = n_reads < rt.sm_count * 8 ? n_reads : rt.sm_count * 8;
+        read_sketch_block_kernel<4><<<grid, 256, sizeof(K3Block<4>::Temp), rt.stream>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 0, 1024, ws2.p, tStrand.p, sOf.p,
+                                                                                        scal.p, ambigList.p, ambCap);
+        read_sketch_block_kernel<8><<<grid, 256, sizeof(K3Block<8>::Temp), rt.stream>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 1024, 2048, ws2.p, tStrand.p, sOf.p,
+                                                                                        scal.p, ambigList.p, ambCap);
+        read_sketch_block_kernel<24><<<grid, 256, sizeof(K3Block<24>::Temp), rt.stream>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 2048, 6144, ws2.p, tStrand.p,
+                                                                                          sOf.p, scal.p, ambigList.p, ambCap);
+        MM_CUDA(cudaGetLastError());
+        rt.launches += 3;
+        foreach(rt, n_reads, K3EdgeFn{rs.seqOff.p, 6144, sOf.p, scal.p + 2});
+        dev_memset(rt, sOf.p + n_reads, 0, sizeof(int32_t));
+        pr.exclusive_sum<int32_t, int64_t>(sOf.p, qOff.p, (int64_t)n_reads + 1);
+        pr.reduce_max<int32_t>(sOf.p, (int32_t*)(scal.p + 1), n_reads);
+        d2d(rt, scal.p + 3, qOff.p + n_reads, sizeof(int64_t));
+        unsigned long long hs[4] = {0, 0, 0, 0}; d2h(rt, hs, scal.p, sizeof(hs));
+        if (hs[2] == 0 && hs[0] <= (unsigned long long)ambCap) {
+          blockPath = true;
+          na = hs[0]; maxS = (int32_t)(hs[1] & 0xffffffffu); n_q = (int64_t)hs[3];
+          qHash.ensure((size_t)n_q + 1); qStrand.ensure((size_t)n_q + 1); qRead.ensure((size_t)n_q + 1);
+          int g2 = (int)(((int64_t)n_reads + 7) / 8); if (g2 > rt.sm_count * 8) g2 = rt.sm_count * 8;
+          read_sketch_gather_kernel<<<g2, 256, 0, rt.stream>>>(ws2.p, tStrand.p, rs.seqOff.p, qOff.p, sOf.p, n_reads, qHash.p, qStrand.p, qRead.p);
+          MM_CUDA(cudaGetLastError());
+          rt.launches++;
+        }
+      }
+#endif
+      if (!blockPath) {       // global sort by (read, hash): host emulation, oversize reads, MM_K3_GLOBAL
+        key2.ensure((size_t)nm + 1); ws2.ensure((size_t)nm + 1); head.ensure((size_t)nm + 2); idx.ensure((size_t)nm + 2);
+        foreach(rt, nm, ReadKeyFn{rs.hash.p, rs.seqOff.p, n_reads, key.p});
+        int bits = 33; while (bits < 64 && ((int64_t)1 << (bits - 32)) < n_reads) bits++;
+        pr.sort_pairs<uint64_t, uint32_t>(key.p, key2.p, rs.ws.p, ws2.p, nm, bits);
+        foreach(rt, nm + 1, HeadFlagFn{key2.p, head.p, nm});
+        pr.exclusive_sum<int32_t, int64_t>(head.p, idx.p, nm + 1);
+        d2h(rt, &n_q, idx.p + nm, sizeof(int64_t));
+        qHash.ensure((size_t)n_q + 1); qStrand.ensure((size_t)n_q + 1); qRead.ensure((size_t)n_q + 1);
+        foreach(rt, nm, UniqueScatterFn{key2.p, ws2.p, head.p, idx.p, qHash.p, qStrand.p, qRead.p});
+        foreach(rt, (int64_t)n_reads + 1, ReadSketchOffFn{rs.seqOff.p, idx.p, qOff.p, sOf.p, n_reads});
+        // duplicate hashes with both strands: settle the survivor like std::sort + std::unique would
         dev_memset(rt, ambig.p, 0, sizeof(int32_t) * ((size_t)n_reads + 1));
         dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);
         foreach(rt, nm, AmbigDetectFn{key2.p, ws2.p, head.p, ambig.p, scal.p, ambigList.p, 4096});
         if (n_reads > 0) pr.reduce_max<int32_t>(sOf.p, (int32_t*)(scal.p + 1), n_reads);
         unsigned long long hs[2] = {0, 0}; d2h(rt, hs, scal.p, sizeof(hs));
-        unsigned long long na = hs[0]; int32_t maxS = (int32_t)(hs[1] & 0xffffffffu);
+        na = hs[0]; maxS = (int32_t)(hs[1] & 0xffffffffu);
         if (na > 4096) {
           ambigList.ensure((size_t)na);
           dev_memset(rt, ambig.p, 0, sizeof(int32_t) * ((size_t)n_reads + 1));
           dev_memset(rt, scal.p, 0, sizeof(unsigned long long));
           foreach(rt, nm, AmbigDetectFn{key2.p, ws2.p, head.p, ambig.p, scal.p, ambigList.p, (int64_t)na});
         }
+      }
+      {
         n_ambig = (int64_t)na;
         if (na) {
           // The replay is one slow sequential thread per read and only the strand vote (K5c) needs its result:
