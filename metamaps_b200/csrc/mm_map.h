@@ -593,16 +593,29 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
     const int64_t b0 = a.beg0[c];
     const int64_t e0 = a.evOff[c] - a.evBase; const int32_t n = (int32_t)(a.evOff[c + 1] - a.evOff[c]);
     const int64_t fe = a.fe[c], le = a.le[c]; const int32_t cmw = a.readLen[r] - (a.w - 1) - (a.k - 1);
-    for (int32_t t = threadIdx.x; t < n; t += blockDim.x) {
-      const int64_t j = b0 + t;
-      const uint32_t h = __ldg(a.miHash + j);
+    auto rank_code = [&](uint32_t h) -> uint32_t {
       const uint32_t bk = h >> (32 - CLS_BUCKET_BITS);
       int32_t lo = bstart[bk], hi = bstart[bk + 1];
       while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (smq[m] < h) lo = m + 1; else hi = m; }
-      uint32_t code = (lo < s && smq[lo] == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
-      if ((__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u)
-        code |= CODE_DUP | dup_event_flags(a.miWs, a.dupIdx, a.dupLinks, a.n_dup, j, b0, fe, le, cmw);
-      a.ev[e0 + t] = make_uint2(code, __ldg(a.miWs + j));
+      return (lo < s && smq[lo] == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
+    };
+    // four elements per thread and trip: the twelve global loads are issued before the first search needs one
+    for (int32_t t0 = threadIdx.x; t0 < n; t0 += 4 * blockDim.x) {
+      uint32_t h[4], wsv[4], db[4]; bool on[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int32_t t = t0 + u * (int32_t)blockDim.x; on[u] = t < n;
+        const int64_t j = b0 + (on[u] ? t : 0);
+        h[u] = __ldg(a.miHash + j); wsv[u] = __ldg(a.miWs + j); db[u] = (__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (!on[u]) continue;
+        const int32_t t = t0 + u * (int32_t)blockDim.x;
+        uint32_t code = rank_code(h[u]);
+        if (db[u]) code |= CODE_DUP | dup_event_flags(a.miWs, a.dupIdx, a.dupLinks, a.n_dup, b0 + t, b0, fe, le, cmw);
+        a.ev[e0 + t] = make_uint2(code, wsv[u]);
+      }
     }
   }
 }
@@ -906,83 +919,139 @@ struct BandSweep {
 // reported last position the LAST window with that count (computeMap.hpp:510-533), whichever segments they fall in.
 struct BandPart { int32_t shared, bpos, lpos, optS, optE, istar, any, fail; };
 static const int BAND_SEG_DEFAULT = 2048;
+static const int32_t BAND_LAST_SEG = 1 << 30;
 
 // one segment; cnt: BW+1 (+3 pad) bytes, mb: BW/32+1 words.  part.fail: the candidate must go through the full-state
 // sweep instead (sketch too large for the band, a gap counter passing 255, a span beyond 65534 elements).
+// On the device the 32 lanes of a warp sweep 32 items in lock step: every lane of the warp must call this function
+// (`valid` = the lane has an item), and the loop's continuation test is a warp vote, which re-converges the lanes after
+// every iteration (without it, lanes that part ways in one of the data-dependent branches keep looping in separate groups
+// and every group pays the full instruction stream).
+#if defined(__CUDA_ARCH__)
+#define MM_WARP_ANY(x) __any_sync(0xffffffffu, (x))
+#else
+#define MM_WARP_ANY(x) (x)
+#endif
 template <class Ev>
-MM_HD void l2_sweep_band(const L2SweepArgs& a, int64_t c, int32_t B0, int32_t B1, uint8_t* cnt, uint32_t* mb, int32_t BW, Ev& ev, BandPart& out) {
+MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0, int32_t B1, uint8_t* cnt, uint32_t* mb, int32_t BW, Ev& ev, BandPart& out) {
+  out.shared = 0; out.bpos = 0; out.lpos = 0; out.optS = 0; out.optE = 0; out.istar = 0; out.any = 0; out.fail = 0;
+  if (!valid) c = a.cand0;                                   // harmless loads; the lane never becomes active
   const int32_t r = ldg(a.cRead + c), s = ldg(a.sOf + r), len = ldg(a.readLen + r);
   const int64_t b0 = ldg(a.beg0 + c);
   const uint2* e = a.ev + (ldg(a.evOff + c) - a.evBase);
   const int32_t last = (int32_t)(ldg(a.le + c) - b0);
   const int32_t cmw = len - (a.w - 1) - (a.k - 1);
-  out.shared = 0; out.bpos = 0; out.lpos = 0; out.optS = 0; out.optE = 0; out.istar = s; out.any = 0; out.fail = 1;
+  out.istar = s;
   int32_t sh = 0; while ((band_bins(BW) << sh) < s + 1) sh++;
-  if ((2 << sh) > BW && s + 1 > BW) return;                  // a coarse bin must fit the band with margins
-  if (last >= 65535) return;
-  out.fail = 0;
+  bool fail = valid && (((2 << sh) > BW && s + 1 > BW) || last >= 65535);   // a coarse bin must fit the band with margins
+  bool active = valid && !fail;
   // The window whose first element is B0, after every event of that step: all elements below wpos[B0] + cmw are inside
   // (for B0 = 0 this is the reference's first window, computeMap.hpp:465-480).
-  int32_t beg = B0, end;
-  if (B0 == 0) end = (int32_t)(ldg(a.fe + c) - b0);
-  else {
-    if (B0 >= last) return;
-    const int32_t lim = (int32_t)(ldg(&e[B0].y) >> 1) + cmw;
-    int32_t l = B0, h = last;
-    while (l < h) { const int32_t m = (l + h) >> 1; if ((int32_t)(ldg(&e[m].y) >> 1) < lim) l = m + 1; else h = m; }
-    end = l;
+  int32_t beg = B0, end = last;
+  if (active) {
+    if (B0 == 0) end = (int32_t)(ldg(a.fe + c) - b0);
+    else if (B0 < last) {
+      const int32_t lim = (int32_t)(ldg(&e[B0].y) >> 1) + cmw;
+      int32_t l = B0, h = last;
+      while (l < h) { const int32_t m = (l + h) >> 1; if ((int32_t)(ldg(&e[m].y) >> 1) < lim) l = m + 1; else h = m; }
+      end = l;
+    }
+    active = end < last;                                     // else the reference's loop is over before this window is evaluated
   }
-  if (end >= last) return;                                   // the reference's loop is over before this window is evaluated
   BandSweep<Ev> z{a, e, ev, cnt, mb, BW, b0, s, sh, 0, 0, 0, 0, false, false};
-  // slidemap.insert_ref(sw_beg, sw_end) (computeMap.hpp:488).  With every window minimizer W-only, F(i) ~ i*(1 + nW/s):
-  // try the band around that istar first (one scan); if the guess misses, locate istar with the histogram (two scans).
-  z.rebuild(beg, end, (int32_t)(((int64_t)s * s) / (s + (end - beg) + 1)), 0);
-  if (z.bad || z.out_of_band()) z.rebuild(beg, end, -1, 0);
-  if (z.fail || z.bad) { out.fail = 1; return; }
+  if (active) {
+    // slidemap.insert_ref(sw_beg, sw_end) (computeMap.hpp:488).  With every window minimizer W-only, F(i) ~ i*(1 + nW/s):
+    // try the band around that istar first (one scan); if the guess misses, locate istar with the histogram (two scans).
+    z.rebuild(beg, end, (int32_t)(((int64_t)s * s) / (s + (end - beg) + 1)), 0);
+    if (z.bad || z.out_of_band()) z.rebuild(beg, end, -1, 0);
+    if (z.fail || z.bad) { fail = true; active = false; }
+  }
   int32_t best = 0, bpos = 0, lpos = 0, bistar = s, optS = 0, optE = 0, any = 0;
-  ev.init(beg + 1, end);
-  uint2 evBeg = ldg(e + beg), evBeg1 = ev.fetch(0, beg + 1), evEnd = ev.fetch(1, end);
+  uint2 evBeg = make_uint2(0, 0), evBeg1 = evBeg, evEnd = evBeg;
+  if (active) {
+    ev.init(beg + 1, end);
+    evBeg = ldg(e + beg); evBeg1 = ev.fetch(0, beg + 1); evEnd = ev.fetch(1, end);
+  }
   int32_t sw_pos = (int32_t)(evBeg.y >> 1);
   bool doEval = true;
-  while (end < last && beg < B1) {
-    if (doEval) {
-      const int32_t wb = (int32_t)(evBeg.y >> 1);
-      const bool better = z.shared > best;
-      lpos = (z.shared >= best) ? wb : lpos;
-      if (better) { best = z.shared; optS = beg; optE = end; bpos = wb; bistar = z.istar; }
-      any = 1;
-    }
-    const int32_t nb = (int32_t)(evBeg1.y >> 1) - sw_pos;    // MIIteratorL2::next (MIIteratorL2.hpp:74-96)
-    const int32_t ne = (int32_t)(evEnd.y >> 1) - (sw_pos + cmw - 1);
-    const int32_t isDel = nb <= ne ? 1 : 0;
-    doEval = nb != ne;                                        // a step that deletes AND inserts is evaluated after the insert
-    sw_pos += isDel ? nb : ne;
-    z.apply(isDel ? evBeg.x : evEnd.x, isDel);
-    beg += isDel; end += 1 - isDel;
-    const uint2 nx = ev.fetch(1 - isDel, isDel ? beg + 1 : end);
-    evBeg = isDel ? evBeg1 : evBeg; evBeg1 = isDel ? nx : evBeg1; evEnd = isDel ? evEnd : nx;
-    if (z.out_of_band() || z.fail) {
-      if (z.fail) break;
-      z.rebuild(beg, end, z.istar, z.istar <= z.lo ? -BW / 4 : BW / 4);   // keep drifting room on the side it left
-      if (z.bad) { z.fail = true; break; }
+#ifdef MM_BAND_DEBUG
+  int dbgIters = 0, dbgWin = end - beg, dbgReb = 0;
+#endif
+  while (MM_WARP_ANY(active)) {
+    if (active) {
+#ifdef MM_BAND_DEBUG
+      dbgIters++;
+#endif
+      if (doEval) {
+        const int32_t wb = (int32_t)(evBeg.y >> 1);
+        const bool better = z.shared > best;
+        lpos = (z.shared >= best) ? wb : lpos;
+        if (better) { best = z.shared; optS = beg; optE = end; bpos = wb; bistar = z.istar; }
+        any = 1;
+      }
+      const int32_t nb = (int32_t)(evBeg1.y >> 1) - sw_pos;    // MIIteratorL2::next (MIIteratorL2.hpp:74-96)
+      const int32_t ne = (int32_t)(evEnd.y >> 1) - (sw_pos + cmw - 1);
+      const int32_t isDel = nb <= ne ? 1 : 0;
+      doEval = nb != ne;                                        // a step that deletes AND inserts is evaluated after the insert
+      sw_pos += isDel ? nb : ne;
+      z.apply(isDel ? evBeg.x : evEnd.x, isDel);
+      beg += isDel; end += 1 - isDel;
+      const uint2 nx = ev.fetch(1 - isDel, isDel ? beg + 1 : end);
+      evBeg = isDel ? evBeg1 : evBeg; evBeg1 = isDel ? nx : evBeg1; evEnd = isDel ? evEnd : nx;
+      if (z.out_of_band() || z.fail) {
+        if (!z.fail) {
+#ifdef MM_BAND_DEBUG
+          dbgReb += end - beg;
+#endif
+          z.rebuild(beg, end, z.istar, z.istar <= z.lo ? -BW / 4 : BW / 4);   // keep drifting room on the side it left
+          if (z.bad) z.fail = true;
+        }
+      }
+      active = !z.fail && end < last && beg < B1;
     }
   }
-  out.shared = best; out.bpos = bpos; out.lpos = lpos; out.optS = optS; out.optE = optE; out.istar = bistar; out.any = any; out.fail = z.fail ? 1 : 0;
+  fail = fail || z.fail;
+  out.shared = best; out.bpos = bpos; out.lpos = lpos; out.optS = optS; out.optE = optE; out.istar = bistar; out.any = any; out.fail = fail ? 1 : 0;
+#ifdef MM_BAND_DEBUG
+  { ::g_band_dbg_cur[0] = dbgIters; ::g_band_dbg_cur[1] = dbgWin; ::g_band_dbg_cur[2] = dbgReb; }
+#endif
 }
 MM_HD int32_t band_state_words(int32_t BW) { return (BW + 4) / 4 + BW / 32 + 1; }
 
-// work items: candidate ci of the pass has max(1, ceil(span / seg)) segments; itemOff = prefix sum over the pass
-struct BandItemFn {         // item -> (candidate, segment) + sort key (descending work)
+// work items: a candidate's window start ("beg") runs over [0, span - window) (the loop ends when the window's end reaches the
+// end of the span), cut into segments of `seg`; itemOff = prefix sum of the segment counts over the pass
+MM_HD int32_t band_beg_range(int32_t span, int32_t win) { const int32_t v = span - win; return v > 0 ? v : 0; }
+struct BandSegCountFn {
+  const int32_t* spanN; const int64_t* beg0; const int64_t* fe; int64_t cand0, nCand; int32_t seg; int32_t* nSeg;
+  MM_HD void operator()(int64_t ci) const {
+    if (ci >= nCand) { nSeg[ci] = 0; return; }
+    const int64_t c = cand0 + ci;
+    const int32_t range = band_beg_range(ldg(spanN + c), (int32_t)(ldg(fe + c) - ldg(beg0 + c)));
+    const int32_t n = (range + seg - 1) / seg;
+    nSeg[ci] = n < 1 ? 1 : n;
+  }
+};
+struct BandItemFn {         // item -> (candidate, segment) + sort key (wide-band class first, then descending work)
   const int64_t* itemOff; int64_t nCand; const int32_t* spanN; const int64_t* beg0; const int64_t* fe; int64_t cand0; int32_t seg;
   uint32_t* key; uint32_t* val; int32_t* itemCand; int32_t* itemSeg;
+  const int32_t* cRead; const int32_t* sOf; int32_t wideFrom; unsigned long long* nWide;
   MM_HD void operator()(int64_t i) const {
     const int64_t ci = upper_bound_idx(itemOff, nCand + 1, i) - 1;
     const int32_t sg = (int32_t)(i - ldg(itemOff + ci));
     const int64_t c = cand0 + ci;
-    itemCand[i] = (int32_t)ci; itemSeg[i] = sg;
-    int32_t span = ldg(spanN + c), rest = span - sg * seg; if (rest > seg) rest = seg; if (rest < 0) rest = 0;
+    // the candidate's last segment is open-ended (the window may shrink towards the end of the span)
+    itemCand[i] = (int32_t)ci; itemSeg[i] = sg | ((i + 1 == ldg(itemOff + ci + 1)) ? BAND_LAST_SEG : 0);
     const int32_t win = (int32_t)(ldg(fe + c) - ldg(beg0 + c));
-    key[i] = 0xFFFFFFFFu - (uint32_t)(2 * rest + win / 4); val[i] = (uint32_t)i;
+    int32_t rest = band_beg_range(ldg(spanN + c), win) - sg * seg; if (rest > seg) rest = seg; if (rest < 0) rest = 0;
+    // ~2 loop iterations per window start (one delete, one insert), and a rebuild scan of the window (cheaper per element)
+    // large sketches drift further than the narrow band tolerates: they run in the wide-band instantiation, sorted first
+    const bool wide = ldg(sOf + ldg(cRead + c)) >= wideFrom;
+    if (wide) atomic_add_u64(nWide, 1ull);
+    uint32_t work = (uint32_t)(2 * rest + win / 4); if (work > 0x7FFFFFFFu) work = 0x7FFFFFFFu;
+    key[i] = (wide ? 0u : 0x80000000u) | (0x7FFFFFFFu - work); val[i] = (uint32_t)i;
+#ifdef MM_BAND_DEBUG
+    if (i < 1000000) ::g_band_dbg_key[i] = (int)work;
+#endif
   }
 };
 struct L2BandMergeFn {      // candidate ci: combine its segments (in time order) into the final outputs
@@ -1009,11 +1078,17 @@ struct L2SweepBandFn {
   L2SweepArgs a; uint32_t* state; int32_t BW; int32_t seg; const int32_t* itemCand; const int32_t* itemSeg; BandPart* parts;
   MM_HD void operator()(int64_t i) const {
     const int64_t c = a.cand0 + ldg(itemCand + i);
-    const int32_t sg = ldg(itemSeg + i);
+    const int32_t sgl = ldg(itemSeg + i), sg = sgl & ~BAND_LAST_SEG;
     uint32_t* stp = state + i * band_state_words(BW);
     DirectEv ev{a.ev + (ldg(a.evOff + c) - a.evBase)};
     BandPart p;
-    l2_sweep_band(a, c, sg * seg, (sg + 1) * seg, (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
+#ifdef MM_BAND_DEBUG
+    ::g_band_dbg_cur[0] = ::g_band_dbg_cur[1] = ::g_band_dbg_cur[2] = 0;
+#endif
+    l2_sweep_band(a, true, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
+#ifdef MM_BAND_DEBUG
+    if (i < 1000000) { ::g_band_dbg_n = i; ::g_band_dbg_it[i] = ::g_band_dbg_cur[0]; ::g_band_dbg_win[i] = ::g_band_dbg_cur[1]; ::g_band_dbg_reb[i] = ::g_band_dbg_cur[2]; }
+#endif
     parts[i] = p;
   }
 };
@@ -1073,16 +1148,15 @@ __global__ void __launch_bounds__(512, 1) l2_sweep_band_kernel(L2SweepArgs a, co
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= nTiles) break;
     const int64_t t = tile * 32 + lane;
-    if (t < nItems) {
-      const int64_t i = (int64_t)order[t];
-      const int64_t c = a.cand0 + itemCand[i];
-      const int32_t sg = itemSeg[i];
-      RingEv<R> ev(a.ev, a.evOff[c] - a.evBase, ring);
-      BandPart p;
-      l2_sweep_band(a, c, sg * seg, (sg + 1) * seg, (uint8_t*)my, my + (BW + 4) / 4, BW, ev, p);
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      parts[i] = p;
-    }
+    const bool valid = t < nItems;
+    const int64_t i = valid ? (int64_t)order[t] : 0;
+    const int64_t c = a.cand0 + (valid ? itemCand[i] : 0);
+    const int32_t sgl = valid ? itemSeg[i] : 0, sg = sgl & ~BAND_LAST_SEG;
+    RingEv<R> ev(a.ev, a.evOff[c] - a.evBase, ring);
+    BandPart p;
+    l2_sweep_band(a, valid, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)my, my + (BW + 4) / 4, BW, ev, p);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (valid) parts[i] = p;
     __syncwarp();
   }
 }
@@ -1168,8 +1242,8 @@ struct Mapper {
   std::vector<uint32_t> hk; std::vector<int32_t> tileStartH, localOffH;
   std::vector<int32_t> h_effLen;
   MapStats st;
-  int sweepBand = 256, sweepRing = 8, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT;
-  DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemSeg; DevBuf<BandPart> bandParts; std::vector<int64_t> hItemOff, hEvSpan;
+  int sweepBand = 256, sweepRing = 8, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT, sweepWideFrom = 0x7fffffff;   // wide-band class: measured neutral on config 2, off unless MM_SWEEP_WIDE_FROM is set
+  DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemSeg, segCnt; DevBuf<BandPart> bandParts; std::vector<int64_t> hItemOff, hEvSpan;
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
   Mapper(Runtime& r, Prims& p, Sketcher& s) : rt(r), pr(p), sk(s) {
@@ -1178,6 +1252,7 @@ struct Mapper {
     // K5b variants (tests and A/B measurements): band width, event-ring depth, and which sweep runs first
     if (const char* e = getenv("MM_SWEEP_BAND")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) sweepBand = v; }
     if (const char* e = getenv("MM_SWEEP_RING")) { int v = atoi(e); if (v == 4 || v == 8) sweepRing = v; }
+    if (const char* e = getenv("MM_SWEEP_WIDE_FROM")) { int v = atoi(e); if (v >= 1) sweepWideFrom = v; }
     if (const char* e = getenv("MM_SWEEP_SEG")) { int v = atoi(e); if (v >= 64) sweepSeg = v; }
     if (const char* e = getenv("MM_SWEEP")) sweepMode = !strcmp(e, "full") ? 1 : !strcmp(e, "global") ? 2 : 0;
   }
@@ -1509,25 +1584,28 @@ struct Mapper {
     const int BAND = sweepBand, MODE = sweepMode;                 // MODE 0 band, 1 full-state smem, 2 global only
     swRedo.ensure((size_t)nc + 1); scal.ensure(4);
     if (MODE == 0 && nc > 0 && nc < ((int64_t)1 << 31) && maxSketch < (1 << 20)) {
-      // work items = segments of candidates (spans are known on the host: hEvSpan)
-      hItemOff.resize((size_t)nc + 1); hItemOff[0] = 0;
-      for (int64_t ci = 0; ci < nc; ci++) {
-        int64_t span = hEvSpan[(size_t)(sa.cand0 + ci) + 1] - hEvSpan[(size_t)(sa.cand0 + ci)];
-        int64_t ns = (span + sweepSeg - 1) / sweepSeg; if (ns < 1) ns = 1;
-        hItemOff[(size_t)ci + 1] = hItemOff[(size_t)ci] + ns;
-      }
-      const int64_t nItems = hItemOff[(size_t)nc];
-      itemOff.ensure((size_t)nc + 1); h2d(rt, itemOff.p, hItemOff.data(), sizeof(int64_t) * ((size_t)nc + 1));
+      // work items = segments of candidates
+      segCnt.ensure((size_t)nc + 2); itemOff.ensure((size_t)nc + 2);
+      foreach(rt, nc + 1, BandSegCountFn{spanN.p, beg0.p, fe.p, sa.cand0, nc, sweepSeg, segCnt.p});
+      pr.exclusive_sum<int32_t, int64_t>(segCnt.p, itemOff.p, nc + 1);
+      int64_t nItems = 0; d2h(rt, &nItems, itemOff.p + nc, sizeof(int64_t));
       itemCand.ensure((size_t)nItems); itemSeg.ensure((size_t)nItems); bandParts.ensure((size_t)nItems);
       swKey.ensure((size_t)nItems); swKey2.ensure((size_t)nItems); swVal.ensure((size_t)nItems); swOrder.ensure((size_t)nItems);
-      foreach(rt, nItems, BandItemFn{itemOff.p, nc, spanN.p, beg0.p, fe.p, sa.cand0, sweepSeg, swKey.p, swVal.p, itemCand.p, itemSeg.p});
-      dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 2);          // scal[0] = redo count, scal[1] = tile counter
+      dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);          // scal[0] = redo count, [1] = tile counter, [2] = wide-band items
+      foreach(rt, nItems, BandItemFn{itemOff.p, nc, spanN.p, beg0.p, fe.p, sa.cand0, sweepSeg, swKey.p, swVal.p, itemCand.p, itemSeg.p,
+                                     cRead.p, sOf.p, sweepWideFrom, scal.p + 2});
 #ifdef MM_HOST_EMU
       state.ensure((size_t)nItems * band_state_words(BAND) + 1);
       foreach(rt, nItems, L2SweepBandFn{sa, state.p, BAND, sweepSeg, itemCand.p, itemSeg.p, bandParts.p});
 #else
       pr.sort_pairs<uint32_t, uint32_t>(swKey.p, swKey2.p, swVal.p, swOrder.p, nItems, 32);
-      launch_band(sa, nItems);
+      unsigned long long nWide = 0; d2h(rt, &nWide, scal.p + 2, sizeof(nWide));
+      if (BAND != 256) nWide = 0;                                           // test widths: one instantiation for everything
+      if (nWide > 0) launch_band_t<512, 8>(sa, swOrder.p, (int64_t)nWide);
+      if ((int64_t)nWide < nItems) {
+        if (nWide > 0) dev_memset(rt, scal.p + 1, 0, sizeof(unsigned long long));       // fresh tile counter
+        launch_band(sa, swOrder.p + nWide, nItems - (int64_t)nWide);
+      }
 #endif
       foreach(rt, nc, L2BandMergeFn{sa, bandParts.p, itemOff.p, swRedo.p, scal.p});
       unsigned long long nr = 0; d2h(rt, &nr, scal.p, sizeof(nr));
@@ -1607,7 +1685,7 @@ struct Mapper {
 
 #ifndef MM_HOST_EMU
   template <int BW, int R>
-  void launch_band_t(const L2SweepArgs& sa, int64_t nc) {
+  void launch_band_t(const L2SweepArgs& sa, const uint32_t* order, int64_t nc) {
     constexpr int ST = ((BW + 4) / 4 + BW / 32 + 1) | 1;
     constexpr int WARP_BYTES = (2 * R * 32 * 4 + 32 * ST) * 4;
     static int warps = 0, ctasPerSm = 1;
@@ -1621,18 +1699,18 @@ struct Mapper {
     }
     int64_t tiles = (nc + 31) / 32;
     int64_t g = (tiles + warps - 1) / warps; if (g > (int64_t)rt.sm_count * ctasPerSm) g = (int64_t)rt.sm_count * ctasPerSm;
-    l2_sweep_band_kernel<BW, R><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, swOrder.p, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,
+    l2_sweep_band_kernel<BW, R><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, order, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,
                                                                                                (unsigned int*)(scal.p + 1));
     MM_CUDA(cudaGetLastError());
     rt.launches++;
   }
-  void launch_band(const L2SweepArgs& sa, int64_t nc) {
+  void launch_band(const L2SweepArgs& sa, const uint32_t* order, int64_t nc) {
     const int BAND = sweepBand, RING = sweepRing;
-    if (BAND == 64) launch_band_t<64, 4>(sa, nc);
-    else if (BAND == 128 && RING == 4) launch_band_t<128, 4>(sa, nc);
-    else if (BAND == 128) launch_band_t<128, 8>(sa, nc);
-    else if (RING == 4) launch_band_t<256, 4>(sa, nc);
-    else launch_band_t<256, 8>(sa, nc);
+    if (BAND == 64) launch_band_t<64, 4>(sa, order, nc);
+    else if (BAND == 128 && RING == 4) launch_band_t<128, 4>(sa, order, nc);
+    else if (BAND == 128) launch_band_t<128, 8>(sa, order, nc);
+    else if (RING == 4) launch_band_t<256, 4>(sa, order, nc);
+    else launch_band_t<256, 8>(sa, order, nc);
   }
 #endif
 
