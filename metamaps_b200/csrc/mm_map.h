@@ -174,6 +174,31 @@ __global__ void __launch_bounds__(256) read_sketch_gather_kernel(const uint32_t*
 }
 #endif
 
+struct AmbigResolveBigFn {  // items beyond *count are empty
+  AmbigResolveFn f; const unsigned long long* count;
+  MM_HD void operator()(int64_t i) const { if ((unsigned long long)i < *count) f(i); }
+};
+#ifndef MM_HOST_EMU
+// Device fast path of the std::sort replay: one CTA per ambiguous read, the read's minimizers staged in shared memory by
+// the whole warp, the replay itself run by lane 0 (it is a sequential algorithm; what matters is that its ~10^5 dependent
+// loads and stores hit shared memory instead of L2).  Reads beyond the shared-memory budget use AmbigResolveFn.
+__global__ void __launch_bounds__(32) ambig_resolve_smem_kernel(AmbigResolveFn f, int32_t maxN, int32_t* big, unsigned long long* bigCount) {
+  extern __shared__ __align__(8) uint64_t sa[];
+  const int32_t r = f.list[blockIdx.x];
+  const int64_t b = f.seqOff[r]; const int64_t n = f.seqOff[r + 1] - b;
+  if (n > maxN) { if (threadIdx.x == 0) { const unsigned long long s_ = atomicAdd(bigCount, 1ull); big[s_] = r; } return; }
+  for (int64_t j = threadIdx.x; j < n; j += 32) sa[j] = ((uint64_t)__ldg(f.hash + b + j) << 32) | __ldg(f.ws + b + j);
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    stdsort::sort(sa, n);
+    int64_t q = f.qOff[r];
+    for (int64_t j = 0; j < n; j++) {
+      if (j == 0 || (uint32_t)(sa[j] >> 32) != (uint32_t)(sa[j - 1] >> 32)) { f.qStrand[q] = (uint8_t)(sa[j] & 1u); q++; }
+    }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------- K4
 struct ProbeFn {            // computeMap.hpp:307-321
   const Slot* table; uint32_t mask; const uint32_t* qHash; int32_t freqThreshold; int32_t* hitCnt; int64_t* hitStart; int64_t n;
@@ -1236,7 +1261,7 @@ struct Mapper {
   DevBuf<int64_t> qOff, idx, hitStart, hitOff, readHitOff, candOff, beg0, fe, le, evOff, stOff, oOptS, oOptE;
   DevBuf<uint64_t> key, key2, hits, hits2;
   DevBuf<uint32_t> ws2, qHash, state; DevBuf<uint8_t> qStrand, tStrand; DevBuf<uint2> ev;
-  DevBuf<int32_t> ambig, ambigList, red, swTile, swLocal, swRedo; DevBuf<unsigned long long> scal; int64_t n_ambig = 0;
+  DevBuf<int32_t> ambig, ambigList, ambigBig, red, swTile, swLocal, swRedo; DevBuf<unsigned long long> scal, scal2; int64_t n_ambig = 0;
   DevBuf<uint32_t> swKey, swKey2, swVal, swOrder; int32_t maxSketch = 0;
   DevBuf<int32_t> qRead, hflag, lhead, keptPerRead; DevBuf<int64_t> hfidx, flagged, lidx; int64_t n_hits_all = 0;
   std::vector<uint32_t> hk; std::vector<int32_t> tileStartH, localOffH;
@@ -1372,7 +1397,22 @@ struct Mapper {
           MM_CUDA(cudaEventRecord(evFork(), rt.stream));
           MM_CUDA(cudaStreamWaitEvent(rt.side, evFork(), 0));
 #endif
-          foreach(rt, (int64_t)na, AmbigResolveFn{ambigList.p, rs.hash.p, rs.ws.p, rs.seqOff.p, key.p, qOff.p, qHash.p, qStrand.p}, 128, 16, true);
+          AmbigResolveFn rf{ambigList.p, rs.hash.p, rs.ws.p, rs.seqOff.p, key.p, qOff.p, qHash.p, qStrand.p};
+#ifndef MM_HOST_EMU
+          {   // shared-memory replay for reads of up to 6000 minimizers; the (rare) longer ones through the global-memory functor
+            static bool attrA = false;
+            if (!attrA) { MM_CUDA(cudaFuncSetAttribute(ambig_resolve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48000)); attrA = true; }
+            ambigBig.ensure((size_t)na + 1); scal2.ensure(2);
+            MM_CUDA(cudaMemsetAsync(scal2.p, 0, sizeof(unsigned long long), rt.side));
+            ambig_resolve_smem_kernel<<<(unsigned)na, 32, 48000, rt.side>>>(rf, 6000, ambigBig.p, scal2.p);
+            MM_CUDA(cudaGetLastError());
+            rt.launches++;
+            rf.list = ambigBig.p;                                   // no host round trip: the functor checks the device-side count
+            foreach(rt, (int64_t)na, AmbigResolveBigFn{rf, scal2.p}, 128, 16, true);
+          }
+#else
+          foreach(rt, (int64_t)na, rf, 128, 16, true);
+#endif
 #ifndef MM_HOST_EMU
           MM_CUDA(cudaEventRecord(evJoin(), rt.side));
 #endif
