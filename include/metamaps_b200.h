@@ -58,10 +58,11 @@ int mm_ctx_last_timing(mm_ctx* ctx, double* total_ms, int64_t* n_launches);
 /* Per-stage device time (ms, CUDA events) of the last mm_map_* call:
  *   [0] K1 sketch  [1] K3 read sketch  [2] K4 probe+gather  [3] K4 hit sort  [4] K4 candidate regions  [5] K5 setup
  *   [6] K5a classify  [7] K5b sweep  [8] K5c strand  [9] accept + summary
+ *   [10] the K1 kernel alone (SketchChunkFn, inside [0])  [11] the K5b sweep kernel alone (l2_sweep_band_kernel, inside [7])
  * and the algorithmic unit counters: [0] sketch elements s_total  [1] seed hits H  [2] candidates C
  *   [3] span minimizers sum N_c  [4] accepted mappings  [5] read minimizers  [6] bases of eligible reads
- *   [7] non-ACGT bases  [8] reads whose duplicate survivor needed the std::sort replay  [9] candidates swept in
- *   shared memory. */
+ *   [7] non-ACGT bases  [8] reads whose duplicate survivor needed the std::sort replay  [9] candidates swept by the
+ *   fast (shared-memory) sweep  [10] seed hits kept by the L1 contig filter  [11] K5b work items (candidate segments). */
 int mm_ctx_last_map_stats(mm_ctx* ctx, double* stage_ms /*[16]*/, int64_t* counters /*[16]*/);
 
 /* ---- K1: winnowed minimizers  (replaces CommonFunc::addMinimizers, commonFunc.hpp:92-175) --------- */

@@ -143,7 +143,8 @@ class Context:
                 "l2_setup_ms": ms[5], "l2_classify_ms": ms[6], "l2_sweep_ms": ms[7], "l2_strand_ms": ms[8], "accept_ms": ms[9],
                 "sketch_elems": int(ct[0]), "hits": int(ct[1]), "candidates": int(ct[2]), "span_elems": int(ct[3]),
                 "mappings": int(ct[4]), "read_minimizers": int(ct[5]), "bases": int(ct[6]), "exceptions": int(ct[7]),
-                "ambiguous_reads": int(ct[8]), "smem_swept": int(ct[9])}
+                "ambiguous_reads": int(ct[8]), "smem_swept": int(ct[9]), "hits_kept": int(ct[10]), "sweep_items": int(ct[11]),
+                "k1_kernel_ms": ms[10], "sweep_kernel_ms": ms[11]}
 
     # K1
     def sketch(self, seqs, k: int, w: int):

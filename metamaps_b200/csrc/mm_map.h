@@ -1313,7 +1313,9 @@ struct Mapper {
     readLen.ensure((size_t)n_reads + 1); h2d(rt, readLen.p, h_effLen.data(), sizeof(int32_t) * (size_t)n_reads);
     {
       StageTimer t(rt, &st.ms[0]);
+      sk.chunkMs = &st.ms[10];
       sk.run(batch, k, w, rs);
+      sk.chunkMs = nullptr;
     }
     batch.h_len = saveLen;
     // ---- K3: sort by (read, hash), unique
@@ -1641,11 +1643,15 @@ struct Mapper {
       pr.sort_pairs<uint32_t, uint32_t>(swKey.p, swKey2.p, swVal.p, swOrder.p, nItems, 32);
       unsigned long long nWide = 0; d2h(rt, &nWide, scal.p + 2, sizeof(nWide));
       if (BAND != 256) nWide = 0;                                           // test widths: one instantiation for everything
-      if (nWide > 0) launch_band_t<512, 8>(sa, swOrder.p, (int64_t)nWide);
-      if ((int64_t)nWide < nItems) {
-        if (nWide > 0) dev_memset(rt, scal.p + 1, 0, sizeof(unsigned long long));       // fresh tile counter
-        launch_band(sa, swOrder.p + nWide, nItems - (int64_t)nWide);
+      {
+        StageTimer tb(rt, &st.ms[11]);                                      // the sweep kernel proper
+        if (nWide > 0) launch_band_t<512, 8>(sa, swOrder.p, (int64_t)nWide);
+        if ((int64_t)nWide < nItems) {
+          if (nWide > 0) dev_memset(rt, scal.p + 1, 0, sizeof(unsigned long long));       // fresh tile counter
+          launch_band(sa, swOrder.p + nWide, nItems - (int64_t)nWide);
+        }
       }
+      st.counters[11] += nItems;
 #endif
       foreach(rt, nc, L2BandMergeFn{sa, bandParts.p, itemOff.p, swRedo.p, scal.p});
       unsigned long long nr = 0; d2h(rt, &nr, scal.p, sizeof(nr));

@@ -235,6 +235,7 @@ struct Sketcher {
   DevBuf<int32_t> chunkCount, keep;
   DevBuf<uint32_t> slabHash, slabWs, tmpHash, tmpWs, gdq, flag;
   DevBuf<unsigned long long> ovfCount;
+  double* chunkMs = nullptr;      // optional accumulator: device time of the K1 kernel proper (SketchChunkFn)
   Sketcher(Runtime& r, Prims& p) : rt(r), pr(p) {}
 
   // ASCII (host or device) -> packed batch.  asc_dev != nullptr: data already on the device.
@@ -303,7 +304,7 @@ struct Sketcher {
     int64_t ovfCap = 1 << 16; ovfList.ensure((size_t)ovfCap);
     SketchArgs a{B.packed.p, B.wordOff.p, B.len.p, n, chunkOff.p, posOff.p, B.excPos.p, B.excByte.p, B.n_exc,
                  k, w, CH, slabHash.p, slabWs.p, chunkCount.p, ovfCount.p, ovfList.p, ovfCap, nullptr, nullptr, 0};
-    foreach(rt, chunks, SketchChunkFn<false>{a}, 128, 16);
+    { StageTimer t(rt, chunkMs); foreach(rt, chunks, SketchChunkFn<false>{a}, 128, 16); }
     unsigned long long novf = 0; d2h(rt, &novf, ovfCount.p, sizeof(novf));
     if (novf) {   // deque longer than 32 entries: replay those chunks with a w-entry deque in global memory
       if ((int64_t)novf > ovfCap) throw Error(-34, "too many deque overflows in one batch");
