@@ -392,48 +392,72 @@ __global__ void __launch_bounds__(256) l1_filter_gather16_kernel(const int32_t* 
     for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) bins[i] = 0;
     if (threadIdx.x == 0) { smTotal = 0; smPos = 0; }
     __syncthreads();
+    // Warp-cooperative walk over the position lists: each warp takes 32 queries at a time (lane i holds query i's list start and
+    // length), then the lanes stride over the FLATTENED hits of those 32 lists; a lane finds the list its hit belongs to with a
+    // 5-step search over the warp's prefix sums (shuffles).  Every lane does the same number of trips whatever the list
+    // lengths, and consecutive lanes read consecutive entries of a list.
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
     unsigned int local = 0;
-    if (!anySat) {
-      for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-        const int32_t c = hitCnt[q];
-        if (!c) continue;
-        const int64_t st = hitStart[q]; const uint32_t base = (uint32_t)(hitOff[q] - h0);
-        for (int32_t j = 0; j < c; j++) {
-          const uint32_t sq = __ldg(posSeq16 + st + j);
-          if (base + j < cacheCap) cache[base + j] = (uint16_t)sq;
-          const uint32_t b = sq & binMask;
-          atomicAdd(&bins[b >> 1], (b & 1u) ? 0x10000u : 1u);
-        }
-      }
-      __syncthreads();
-      // survivors = sum of the bins that reached minimumHits
-      for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) {
-        const uint32_t w = bins[i], lo = w & 0xFFFFu, hi = w >> 16;
-        local += (lo >= (uint32_t)mh) ? lo : 0u;
-        local += (hi >= (uint32_t)mh) ? hi : 0u;
-      }
-    } else if (threadIdx.x == 0) local = (unsigned int)nHits;
-    if (local) atomicAdd(&smTotal, local);
-    __syncthreads();
-    if (threadIdx.x == 0) { smBase = atomicAdd(cursor, (unsigned long long)smTotal); keptPerRead[r] = (int32_t)smTotal; }
-    __syncthreads();
-    if (smTotal != 0) {
-      const uint64_t hi = (uint64_t)r << (lay.seqBits + lay.wsBits);
-      for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-        const int32_t c = hitCnt[q];
-        if (!c) continue;
-        const int64_t st = hitStart[q]; const uint32_t base = (uint32_t)(hitOff[q] - h0);
-        for (int32_t j = 0; j < c; j++) {
-          bool keep = anySat;
-          if (!anySat) {
-            const uint32_t sq = (base + j < cacheCap) ? (uint32_t)cache[base + j] : (uint32_t)__ldg(posSeq16 + st + j);
-            const uint32_t b = sq & binMask;
-            keep = ((bins[b >> 1] >> ((b & 1u) * 16)) & 0xFFFFu) >= (uint32_t)mh;
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1) {
+        if (!anySat) {
+          __syncthreads();
+          // survivors = sum of the bins that reached minimumHits
+          for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) {
+            const uint32_t w = bins[i], lo = w & 0xFFFFu, hi = w >> 16;
+            local += (lo >= (uint32_t)mh) ? lo : 0u;
+            local += (hi >= (uint32_t)mh) ? hi : 0u;
           }
-          if (keep) {
-            const uint64_t pk = __ldg(posKey + st + j);
-            const unsigned int p = atomicAdd(&smPos, 1u);
-            hitsOut[smBase + p] = hi | ((pk >> 32) << lay.wsBits) | (pk & 0xFFFFFFFFull);
+        } else if (threadIdx.x == 0) local = (unsigned int)nHits;
+        if (local) atomicAdd(&smTotal, local);
+        __syncthreads();
+        if (threadIdx.x == 0) { smBase = atomicAdd(cursor, (unsigned long long)smTotal); keptPerRead[r] = (int32_t)smTotal; }
+        __syncthreads();
+        if (smTotal == 0) break;
+      } else if (anySat) continue;                         // counters could wrap: no counting pass, everything is kept
+      const uint64_t hiKey = (uint64_t)r << (lay.seqBits + lay.wsBits);
+      for (int64_t qb = q0 + (int64_t)wid * 32; qb < q1; qb += (int64_t)nWarps * 32) {
+        const int64_t q = qb + lane;
+        const int32_t c = q < q1 ? hitCnt[q] : 0;
+        const int64_t st = c ? hitStart[q] : 0;
+        int32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int32_t ex = incl - c;
+        const int32_t T = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t rankBase = (uint32_t)(hitOff[qb] - h0);
+        for (int32_t t0 = 0; t0 < T; t0 += 32) {
+          const int32_t t = t0 + lane;
+          int32_t j = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const int32_t cand = j + step;
+            const int32_t v = __shfl_sync(0xffffffffu, ex, cand & 31);
+            if (cand < 32 && v <= t) j = cand;
+          }
+          const int64_t stj = __shfl_sync(0xffffffffu, st, j);
+          const int32_t exj = __shfl_sync(0xffffffffu, ex, j);
+          if (t < T) {
+            const int64_t idx = stj + (t - exj);
+            const uint32_t rank = rankBase + (uint32_t)t;
+            if (pass == 0) {
+              const uint32_t sq = __ldg(posSeq16 + idx);
+              if (rank < cacheCap) cache[rank] = (uint16_t)sq;
+              const uint32_t b_ = sq & binMask;
+              atomicAdd(&bins[b_ >> 1], (b_ & 1u) ? 0x10000u : 1u);
+            } else {
+              bool keep = anySat;
+              if (!anySat) {
+                const uint32_t sq = (rank < cacheCap) ? (uint32_t)cache[rank] : (uint32_t)__ldg(posSeq16 + idx);
+                const uint32_t b_ = sq & binMask;
+                keep = ((bins[b_ >> 1] >> ((b_ & 1u) * 16)) & 0xFFFFu) >= (uint32_t)mh;
+              }
+              if (keep) {
+                const uint64_t pk = __ldg(posKey + idx);
+                const unsigned int p = atomicAdd(&smPos, 1u);
+                hitsOut[smBase + p] = hiKey | ((pk >> 32) << lay.wsBits) | (pk & 0xFFFFFFFFull);
+              }
+            }
           }
         }
       }
