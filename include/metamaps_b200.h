@@ -95,6 +95,15 @@ int mm_index_stats(const mm_index* idx, int64_t* n_minimizers, int64_t* n_unique
  *     hash range, merged, the global histogram gives the threshold and the over-frequent hashes are flagged locally. */
 int mm_index_set_shard(mm_index* idx, int32_t first_contig_id, int32_t keep_counts);
 int mm_index_sync_threshold(mm_index* idx, int32_t* global_threshold, int64_t* global_unique);
+/* Persistent index (replaces the Boost binary archive of skch::Sketch written by `metamaps index`, mapWrap.h:358-405).
+ * A GPU-native dump: fixed header + the device arrays as they lie in HBM, so loading is a sequence of plain reads and
+ * host->device copies (no re-sort, no re-hash).  Not byte-compatible with the reference's archives by design; the
+ * `<prefix>.index` manifest contract (first line 1 = complete, then the chunk files) is kept by the host.
+ * The file records k, w and the occurrence threshold; contig names are host metadata and are not stored here. */
+int mm_index_save(const mm_index* idx, const char* path);
+int mm_index_load(mm_ctx* ctx, const char* path, mm_index** out);
+/* k / w of an index (e.g. after mm_index_load), contig lengths in id order (n_contigs entries, may be NULL). */
+int mm_index_params(const mm_index* idx, int32_t* k, int32_t* w, int32_t* contig_len);
 /* minimizerIndex in (seqId,wpos) order, for parity tests. */
 int mm_index_fetch(const mm_index* idx, uint32_t* hash, int32_t* seq_id, int32_t* wpos, int32_t* strand);
 /* minimizerPosLookupIndex probe, for parity tests: count (0 = absent) of each hash. */

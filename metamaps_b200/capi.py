@@ -44,6 +44,9 @@ SYMBOLS = {
     "mm_index_set_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "mm_index_sync_threshold": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "mm_comm_set_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mm_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mm_index_load": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mm_index_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
     "mm_index_finalize": (C.c_int, [C.c_void_p]),
     "mm_index_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "mm_index_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -233,6 +236,23 @@ class Index:
 
     def finalize(self):
         self.ctx._check(self.lib.mm_index_finalize(self.h))
+
+    def save(self, path: str):
+        """GPU-native dump of the finalized index (mm_index_save)."""
+        self.ctx._check(self.lib.mm_index_save(self.h, path.encode()))
+
+    @classmethod
+    def load(cls, ctx: "Context", path: str) -> "Index":
+        """mm_index_load: the arrays go straight back to the device."""
+        self = cls.__new__(cls)
+        self.ctx = ctx; self.lib = ctx.lib
+        h = C.c_void_p()
+        ctx._check(ctx.lib.mm_index_load(ctx.h, path.encode(), C.byref(h)))
+        self.h = h
+        k = C.c_int32(); w = C.c_int32()
+        ctx._check(ctx.lib.mm_index_params(h, C.byref(k), C.byref(w), None))
+        self.k, self.w = k.value, w.value
+        return self
 
     def set_shard(self, first_contig_id: int, keep_counts: bool = True):
         """This index holds the contigs [first_contig_id, ...) of a larger reference (call before finalize)."""

@@ -4,7 +4,8 @@
 //  src/meta/fEM.h:466-1133).  All array work goes through the C ABI (include/metamaps_b200.h); this file only
 // parses files, prints text with the reference's formatting, and keeps the taxonomy book-keeping.
 //
-// Not supported (out of scope): `index` / `mapAgainstIndex` (Boost archives), `classifyU`.
+// `index` / `mapAgainstIndex` keep the <prefix>.index manifest contract with a GPU-native index file (mm_index_save) instead
+// of Boost archives.  Not supported: `classifyU` (disabled in the reference itself).
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -66,7 +67,7 @@ Options parse_args(int argc, char** argv, int first, const std::map<std::string,
 struct Params {          // skch::Parameters (map_parameters.hpp:57-76)
   int kmerSize = 16, windowSize = 0, minReadLength = 1000, alphabetSize = 4, threads = 1;
   uint64_t referenceSize = 0; float percentageIdentity = 80; double p_value = 1e-3;
-  std::string ref, query, out; bool reportAll = false; uint64_t maximumMemory = 0;
+  std::string ref, query, out, index; bool reportAll = false; uint64_t maximumMemory = 0;
 };
 
 uint64_t file_size(const std::string& f) {
@@ -77,46 +78,63 @@ uint64_t file_size(const std::string& f) {
 // ------------------------------------------------------------------------------------------------ mapDirectly
 struct Contig { std::string name; int len; };
 
-int run_mapDirectly(int argc, char** argv) {
+// mode: 0 = mapDirectly, 1 = index (no queries), 2 = mapAgainstIndex (no reference; parameters come from the index)
+static Params parse_map_options(int argc, char** argv, int mode, int* device) {
   const std::map<std::string, std::string> alias = {
       {"reference", "reference"}, {"r", "reference"}, {"kmer", "kmer"}, {"k", "kmer"}, {"pval", "pval"}, {"p", "pval"},
       {"maxmemory", "maxmemory"}, {"mm", "maxmemory"}, {"window", "window"}, {"w", "window"}, {"minReadLen", "minReadLen"}, {"m", "minReadLen"},
       {"perc_identity", "perc_identity"}, {"pi", "perc_identity"}, {"threads", "threads"}, {"t", "threads"}, {"query", "query"}, {"q", "query"},
-      {"all", "all"}, {"output", "output"}, {"o", "output"}, {"device", "device"}};
+      {"all", "all"}, {"output", "output"}, {"o", "output"}, {"device", "device"}, {"index", "index"}, {"i", "index"}};
   Options o = parse_args(argc, argv, 2, alias, {"all"});
   Params P;
-  if (!o.has("reference")) die("Provide reference file (s)");
-  P.ref = o.get("reference");
-  P.referenceSize = file_size(P.ref);                                   // commonFunc.hpp:211
-  if (o.has("maxmemory")) P.maximumMemory = (uint64_t)(std::pow(1024, 3) * strtoull(o.get("maxmemory").c_str(), nullptr, 10));
-  if (o.has("kmer")) P.kmerSize = atoi(o.get("kmer").c_str());
-  if (o.has("pval")) P.p_value = atof(o.get("pval").c_str());
-  if (o.has("minReadLen")) P.minReadLength = atoi(o.get("minReadLen").c_str());
-  if (o.has("perc_identity")) P.percentageIdentity = (float)atof(o.get("perc_identity").c_str());
-  if (o.has("window")) {                                                // parseCmdArgs.hpp:363-374
-    P.windowSize = atoi(o.get("window").c_str());
-    int s = P.minReadLength * 2 / P.windowSize;
-    P.p_value = mm_stat_estimate_pvalue(s, P.kmerSize, P.alphabetSize, P.percentageIdentity, P.minReadLength, P.referenceSize);
-  } else {
-    P.windowSize = mm_stat_recommended_window(P.p_value, P.kmerSize, P.alphabetSize, P.percentageIdentity, P.minReadLength, P.referenceSize);
+  if (mode != 0) {                                                       // parseCmdArgs.hpp:266-281
+    if (!o.has("index")) die("Please provide index");
+    P.index = o.get("index");
   }
-  if (!o.has("query")) die("Provide query file (s)");
-  P.query = o.get("query");
-  P.reportAll = o.has("all");
+  if (mode != 2) {
+    if (!o.has("reference")) die("Provide reference file (s)");
+    P.ref = o.get("reference");
+    P.referenceSize = file_size(P.ref);                                   // commonFunc.hpp:211
+    if (o.has("maxmemory")) P.maximumMemory = (uint64_t)(std::pow(1024, 3) * strtoull(o.get("maxmemory").c_str(), nullptr, 10));
+    if (o.has("kmer")) P.kmerSize = atoi(o.get("kmer").c_str());
+    if (o.has("pval")) P.p_value = atof(o.get("pval").c_str());
+    if (o.has("minReadLen")) P.minReadLength = atoi(o.get("minReadLen").c_str());
+    if (o.has("perc_identity")) P.percentageIdentity = (float)atof(o.get("perc_identity").c_str());
+    if (o.has("window")) {                                                // parseCmdArgs.hpp:363-374
+      P.windowSize = atoi(o.get("window").c_str());
+      int s = P.minReadLength * 2 / P.windowSize;
+      P.p_value = mm_stat_estimate_pvalue(s, P.kmerSize, P.alphabetSize, P.percentageIdentity, P.minReadLength, P.referenceSize);
+    } else {
+      P.windowSize = mm_stat_recommended_window(P.p_value, P.kmerSize, P.alphabetSize, P.percentageIdentity, P.minReadLength, P.referenceSize);
+    }
+  }
+  if (mode != 1) {
+    if (!o.has("query")) die("Provide query file (s)");
+    P.query = o.get("query");
+    P.reportAll = o.has("all");
+    if (!o.has("output")) die("Provide output file");
+    P.out = o.get("output");
+  }
   if (o.has("threads")) P.threads = atoi(o.get("threads").c_str());
-  if (!o.has("output")) die("Provide output file");
-  P.out = o.get("output");
-  std::vector<std::string> queries = split(P.query, ","), prefixes = split(P.out, ",");
-  if (queries.size() != prefixes.size()) die("Please specify an equal number of input and output files (as comma-separated lists)");
-  int device = o.has("device") ? atoi(o.get("device").c_str()) : 0;
-
+  *device = o.has("device") ? atoi(o.get("device").c_str()) : 0;
+  return P;
+}
+static void print_params(const Params& P) {
   std::cout << "Parameters used:\n\t- alphabetSize: " << P.alphabetSize << "\n\t- kmerSize: " << P.kmerSize << "\n\t- minReadLength: " << P.minReadLength
             << "\n\t- p_value: " << P.p_value << "\n\t- percentageIdentity: " << P.percentageIdentity << "\n\t- windowSize: " << P.windowSize
             << "\n\t- maximumMemory: ~" << P.maximumMemory / std::pow(1024, 3) << " GB (GPU build: the index is device-resident, no chunking)\n\n" << std::flush;
+}
+static void print_index_info(mm_index* idx) {
+  int64_t nMin = 0, nUniq = 0; int32_t freq = 0, nCont = 0; int64_t bytes = 0;
+  mm_index_stats(idx, &nMin, &nUniq, &freq, &nCont, &bytes);
+  std::cout << "INFO, skch::Sketch::build, minimizers picked from reference = " << nMin << std::endl;
+  if (freq != 0x7fffffff) std::cout << "INFO, skch::Sketch::computeFreqHist, With threshold 0.001%, ignore minimizers occurring >= " << freq << " times during lookup." << std::endl;
+  else std::cout << "INFO, skch::Sketch::computeFreqHist, With threshold 0.001%, consider all minimizers during lookup." << std::endl;
 
-  mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
+}
+// skch::Sketch over the reference FASTA (winSketch.hpp:180-365) on the device
+static mm_index* build_reference_index(mm_ctx* ctx, const Params& P, std::vector<Contig>& meta) {
   mm_index* idx = nullptr; ck(mm_index_create(ctx, P.kmerSize, P.windowSize, &idx), "mm_index_create");
-  std::vector<Contig> meta;
   {
     mmhost::FastxReader rd(P.ref);
     if (!rd.ok()) die("Cannot open " + P.ref);
@@ -134,12 +152,12 @@ int run_mapDirectly(int argc, char** argv) {
     flush();
     ck(mm_index_finalize(idx), "mm_index_finalize");
   }
-  int64_t nMin = 0, nUniq = 0; int32_t freq = 0, nCont = 0; int64_t bytes = 0;
-  mm_index_stats(idx, &nMin, &nUniq, &freq, &nCont, &bytes);
-  std::cout << "INFO, skch::Sketch::build, minimizers picked from reference = " << nMin << std::endl;
-  if (freq != 0x7fffffff) std::cout << "INFO, skch::Sketch::computeFreqHist, With threshold 0.001%, ignore minimizers occurring >= " << freq << " times during lookup." << std::endl;
-  else std::cout << "INFO, skch::Sketch::computeFreqHist, With threshold 0.001%, consider all minimizers during lookup." << std::endl;
-
+  return idx;
+}
+// skch::Map over every query file + unifyFiles + addMappingQualities (computeMap.hpp:104-172, mapWrap.h:34-323)
+static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& meta, const Params& P) {
+  std::vector<std::string> queries = split(P.query, ","), prefixes = split(P.out, ",");
+  if (queries.size() != prefixes.size()) die("Please specify an equal number of input and output files (as comma-separated lists)");
   for (size_t fi = 0; fi < queries.size(); fi++) {
     const std::string prefix = prefixes[fi];
     std::ofstream out(prefix);
@@ -222,6 +240,101 @@ int run_mapDirectly(int argc, char** argv) {
     std::cout << "INFO, skch::Map::mapQuery, [count of mapped reads, reads qualified for mapping, total input reads] = [" << mapped << ", "
               << total - tooShort << ", " << total << "]" << std::endl;
   }
+}
+
+int run_mapDirectly(int argc, char** argv) {
+  int device = 0;
+  Params P = parse_map_options(argc, argv, 0, &device);
+  print_params(P);
+  mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
+  std::vector<Contig> meta;
+  mm_index* idx = build_reference_index(ctx, P, meta);
+  print_index_info(idx);
+  map_queries(ctx, idx, meta, P);
+  mm_index_destroy(idx); mm_ctx_destroy(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ index / mapAgainstIndex
+// mapWrap::createIndex (mapWrap.h:358-405): <prefix>.index (0 while building, then 1 + the chunk files), <prefix>.arguments
+// (the parameters), <prefix>.0 (the index; here the GPU-native dump of mm_index_save plus <prefix>.0.contigs with the
+// contig names and lengths).  The index is device-resident and written as ONE chunk.
+int run_index(int argc, char** argv) {
+  int device = 0;
+  Params P = parse_map_options(argc, argv, 1, &device);
+  print_params(P);
+  { std::ofstream st(P.index + ".index"); if (!st.is_open()) die("Cannot open file " + P.index + ".index"); st << 0 << "\n"; }
+  {
+    std::ofstream a(P.index + ".arguments");
+    if (!a.is_open()) die("Cannot open file " + P.index + ".arguments for serialization.");
+    a.precision(17);
+    a << "alphabetSize " << P.alphabetSize << "\nkmerSize " << P.kmerSize << "\nminReadLength " << P.minReadLength << "\np_value " << P.p_value
+      << "\npercentageIdentity " << P.percentageIdentity << "\nwindowSize " << P.windowSize << "\nreferenceSize " << P.referenceSize
+      << "\nrefSequences " << P.ref << "\n";
+  }
+  mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
+  std::vector<Contig> meta;
+  mm_index* idx = build_reference_index(ctx, P, meta);
+  print_index_info(idx);
+  const std::string chunk = P.index + ".0";
+  ck(mm_index_save(idx, chunk.c_str()), "mm_index_save");
+  {
+    std::ofstream c(chunk + ".contigs");
+    if (!c.is_open()) die("Cannot open file " + chunk + ".contigs for serialization.");
+    for (const Contig& m : meta) c << m.len << "\t" << m.name << "\n";
+  }
+  std::cout << "Stored state in file " << chunk << "\n" << std::flush;
+  { std::ofstream st(P.index + ".index"); st << 1 << "\n" << chunk << "\n"; }
+  mm_index_destroy(idx); mm_ctx_destroy(ctx);
+  return 0;
+}
+// mapWrap::mapAgainstIndex (mapWrap.h:443-554)
+int run_mapAgainstIndex(int argc, char** argv) {
+  int device = 0;
+  Params P = parse_map_options(argc, argv, 2, &device);
+  std::vector<std::string> lines;
+  {
+    std::ifstream st(P.index + ".index");
+    std::string l;
+    while (st.is_open() && std::getline(st, l)) { erase_nl(l); if (!l.empty()) lines.push_back(l); }
+  }
+  if (lines.empty() || lines[0] != "1") die("The file " + P.index + ".index does not indicate that index " + P.index + " was built successfully, abort.");
+  if (lines.size() < 2) die("Index " + P.index + " was built successfully, but no index files present?");
+  if (lines.size() > 2) die("Index " + P.index + " lists several chunk files; this build writes and reads single-chunk (device-resident) indices");
+  {
+    std::ifstream a(P.index + ".arguments");
+    if (!a.is_open()) die("Expected file " + P.index + ".arguments not found - have you supplied a valid index?");
+    std::string key, val;
+    while (a >> key >> val) {
+      if (key == "alphabetSize") P.alphabetSize = atoi(val.c_str());
+      else if (key == "kmerSize") P.kmerSize = atoi(val.c_str());
+      else if (key == "minReadLength") P.minReadLength = atoi(val.c_str());
+      else if (key == "p_value") P.p_value = atof(val.c_str());
+      else if (key == "percentageIdentity") P.percentageIdentity = (float)atof(val.c_str());
+      else if (key == "windowSize") P.windowSize = atoi(val.c_str());
+      else if (key == "referenceSize") P.referenceSize = strtoull(val.c_str(), nullptr, 10);
+      else if (key == "refSequences") P.ref = val;
+    }
+  }
+  std::cout << "Parameters restored from index " << P.index << ".arguments\n\t- alphabetSize: " << P.alphabetSize << "\n\t- kmerSize: " << P.kmerSize
+            << "\n\t- minReadLength: " << P.minReadLength << "\n\t- p_value: " << P.p_value << "\n\t- percentageIdentity: " << P.percentageIdentity
+            << "\n\t- windowSize: " << P.windowSize << "\n\n" << std::flush;
+  mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
+  mm_index* idx = nullptr;
+  ck(mm_index_load(ctx, lines[1].c_str(), &idx), "mm_index_load");
+  int32_t k = 0, w = 0; mm_index_params(idx, &k, &w, nullptr);
+  if (k != P.kmerSize || w != P.windowSize) die("Index file " + lines[1] + " does not match " + P.index + ".arguments");
+  std::vector<Contig> meta;
+  {
+    std::ifstream c(lines[1] + ".contigs");
+    if (!c.is_open()) die("Cannot open file " + lines[1] + ".contigs for reading -- invalid index " + P.index);
+    std::string l;
+    while (std::getline(c, l)) { erase_nl(l); size_t t = l.find('\t'); if (t == std::string::npos) continue; meta.push_back(Contig{l.substr(t + 1), atoi(l.substr(0, t).c_str())}); }
+  }
+  int32_t nCont = 0; mm_index_stats(idx, nullptr, nullptr, nullptr, &nCont, nullptr);
+  if ((size_t)nCont != meta.size()) die("Index file " + lines[1] + " and its .contigs file disagree");
+  print_index_info(idx);
+  map_queries(ctx, idx, meta, P);
   mm_index_destroy(idx); mm_ctx_destroy(ctx);
   return 0;
 }
@@ -547,7 +660,7 @@ int run_classify(int argc, char** argv) {
 }
 
 void usage() {
-  std::cout << "\nMetaMaps (metamaps_b200: B200 compute core) \n\n  Simultaneous metagenomic classification and mapping.\n\nUsage:\n\n  ./metamaps mapDirectly|classify\n\n"
+  std::cout << "\nMetaMaps (metamaps_b200: B200 compute core) \n\n  Simultaneous metagenomic classification and mapping.\n\nUsage:\n\n  ./metamaps mapDirectly|classify|index|mapAgainstIndex\n\n"
                "  mapDirectly -r <ref.fa[.gz]> -q <reads.fq[,..]> -o <prefix[,..]> [--all] [-k 16] [-w W | -p 1e-3] [-m 1000] [--pi 80] [-t N] [--maxmemory GB] [--device 0]\n"
                "  classify --DB <dir> --mappings <prefix[,..]> [-t N] [--device 0]\n\n";
 }
@@ -559,7 +672,9 @@ int main(int argc, char** argv) {
   std::string cmd = argv[1];
   if (cmd == "mapDirectly") return run_mapDirectly(argc, argv);
   if (cmd == "classify") return run_classify(argc, argv);
-  if (cmd == "index" || cmd == "mapAgainstIndex" || cmd == "classifyU") die("sub-command '" + cmd + "' is not part of the GPU hot path (see DESIGN.md, out of scope)");
+  if (cmd == "index") return run_index(argc, argv);
+  if (cmd == "mapAgainstIndex") return run_mapAgainstIndex(argc, argv);
+  if (cmd == "classifyU") die("sub-command 'classifyU' is disabled in the reference (mash_map.cpp:323) and not part of the GPU hot path");
   usage();
   return 1;
 }

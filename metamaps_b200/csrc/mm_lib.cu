@@ -225,6 +225,98 @@ int mm_index_fetch(const mm_index* idx, uint32_t* hash, int32_t* seq_id, int32_t
       for (int64_t i = ix.h_contigStart[(size_t)s]; i < ix.h_contigStart[(size_t)s + 1]; i++) seq_id[i] = s;
   MM_CATCH
 }
+// ---- persistent index ------------------------------------------------------------------------------------------
+namespace {
+struct IndexFileHeader {
+  char magic[8]; uint32_t version, k, w, hasSeq16; int64_t n, n_unique, n_dup, total_bases, tableSlots; int32_t n_contigs, freqThreshold, firstContig,
+      globalSynced, globalThreshold, reserved[7];
+};
+const char INDEX_MAGIC[8] = {'M', 'M', 'B', '2', '0', '0', 'I', 'X'};
+void put(FILE* f, const void* p, size_t bytes) { if (bytes && fwrite(p, 1, bytes, f) != bytes) throw Error(MM_EINVAL, "mm_index_save: short write"); }
+void get(FILE* f, void* p, size_t bytes) { if (bytes && fread(p, 1, bytes, f) != bytes) throw Error(MM_EINVAL, "mm_index_load: truncated index file"); }
+// device array <-> file through a host bounce buffer
+void put_dev(Runtime& rt, FILE* f, const void* d, size_t bytes, std::vector<char>& bounce) {
+  for (size_t o = 0; o < bytes; o += bounce.size()) {
+    const size_t nb = std::min(bounce.size(), bytes - o);
+    d2h(rt, bounce.data(), (const char*)d + o, nb); put(f, bounce.data(), nb);
+  }
+}
+void get_dev(Runtime& rt, FILE* f, void* d, size_t bytes, std::vector<char>& bounce) {
+  for (size_t o = 0; o < bytes; o += bounce.size()) {
+    const size_t nb = std::min(bounce.size(), bytes - o);
+    get(f, bounce.data(), nb); h2d(rt, (char*)d + o, bounce.data(), nb); rt.sync();
+  }
+}
+}  // namespace
+int mm_index_save(const mm_index* idx, const char* path) {
+  MM_TRY
+  if (!idx || !path || !idx->ix.finalized) throw Error(MM_EINVAL, "mm_index_save: index not finalized");
+  const Index& ix = idx->ix; mm_ctx* c = idx->ctx;
+  begin_call(c);
+  FILE* f = fopen(path, "wb");
+  if (!f) throw Error(MM_EINVAL, std::string("mm_index_save: cannot open ") + path);
+  try {
+    IndexFileHeader h; memset(&h, 0, sizeof h); memcpy(h.magic, INDEX_MAGIC, 8);
+    h.version = 1; h.k = (uint32_t)ix.k; h.w = (uint32_t)ix.w; h.hasSeq16 = ix.hasSeq16 ? 1 : 0; h.n = ix.n; h.n_unique = ix.n_unique; h.n_dup = ix.n_dup;
+    h.total_bases = ix.total_bases; h.tableSlots = (int64_t)ix.tableMask + 1; h.n_contigs = ix.n_contigs; h.freqThreshold = ix.freqThreshold;
+    h.firstContig = ix.firstContig; h.globalSynced = ix.globalSynced ? 1 : 0; h.globalThreshold = ix.globalThreshold;
+    put(f, &h, sizeof h);
+    put(f, ix.h_contigLen.data(), sizeof(int32_t) * ix.h_contigLen.size());
+    put(f, ix.h_contigStart.data(), sizeof(int64_t) * ix.h_contigStart.size());
+    std::vector<char> bounce((size_t)64 << 20);
+    put_dev(c->rt, f, ix.miHash.p, 4 * (size_t)ix.n, bounce); put_dev(c->rt, f, ix.miWs.p, 4 * (size_t)ix.n, bounce);
+    put_dev(c->rt, f, ix.table.p, sizeof(Slot) * (size_t)h.tableSlots, bounce);
+    put_dev(c->rt, f, ix.posKey.p, 8 * (size_t)ix.n, bounce);
+    if (ix.hasSeq16) put_dev(c->rt, f, ix.posSeq16.p, 2 * (size_t)ix.n, bounce);
+    put_dev(c->rt, f, ix.dupBits.p, 4 * (size_t)(ix.n / 32 + 2), bounce);
+    put_dev(c->rt, f, ix.dupIdx.p, 4 * (size_t)ix.n_dup, bounce); put_dev(c->rt, f, ix.dupLinks.p, 8 * (size_t)ix.n_dup, bounce);
+  } catch (...) { fclose(f); throw; }
+  if (fclose(f) != 0) throw Error(MM_EINVAL, "mm_index_save: close failed");
+  MM_CATCH
+}
+int mm_index_load(mm_ctx* c, const char* path, mm_index** out) {
+  MM_TRY
+  if (!c || !path || !out) throw Error(MM_EINVAL, "mm_index_load: bad arguments");
+  begin_call(c);
+  FILE* f = fopen(path, "rb");
+  if (!f) throw Error(MM_EINVAL, std::string("mm_index_load: cannot open ") + path);
+  mm_index* idx = nullptr;
+  try {
+    IndexFileHeader h; get(f, &h, sizeof h);
+    if (memcmp(h.magic, INDEX_MAGIC, 8) != 0 || h.version != 1) throw Error(MM_EINVAL, "mm_index_load: not a metamaps_b200 index file (or another version)");
+    if (h.k < 1 || h.k > 16 || h.w < 1 || h.n < 0 || h.n_contigs < 0 || h.tableSlots < 1 || (h.tableSlots & (h.tableSlots - 1))) throw Error(MM_EINVAL, "mm_index_load: corrupt header");
+    idx = new mm_index(c, (int)h.k, (int)h.w);
+    Index& ix = idx->ix;
+    ix.n = h.n; ix.n_unique = h.n_unique; ix.n_dup = h.n_dup; ix.total_bases = h.total_bases; ix.tableMask = (uint32_t)(h.tableSlots - 1); ix.n_contigs = h.n_contigs;
+    ix.freqThreshold = h.freqThreshold; ix.firstContig = h.firstContig; ix.globalSynced = h.globalSynced != 0; ix.globalThreshold = h.globalThreshold; ix.hasSeq16 = h.hasSeq16 != 0;
+    ix.h_contigLen.resize((size_t)h.n_contigs); ix.h_contigStart.resize((size_t)h.n_contigs + 1);
+    get(f, ix.h_contigLen.data(), sizeof(int32_t) * ix.h_contigLen.size());
+    get(f, ix.h_contigStart.data(), sizeof(int64_t) * ix.h_contigStart.size());
+    ix.contigStart.ensure(ix.h_contigStart.size()); h2d(c->rt, ix.contigStart.p, ix.h_contigStart.data(), sizeof(int64_t) * ix.h_contigStart.size());
+    ix.contigLen.ensure(ix.h_contigLen.size() + 1); h2d(c->rt, ix.contigLen.p, ix.h_contigLen.data(), sizeof(int32_t) * ix.h_contigLen.size());
+    c->rt.sync();
+    std::vector<char> bounce((size_t)64 << 20);
+    ix.miHash.ensure((size_t)ix.n + 1); ix.miWs.ensure((size_t)ix.n + 1);
+    get_dev(c->rt, f, ix.miHash.p, 4 * (size_t)ix.n, bounce); get_dev(c->rt, f, ix.miWs.p, 4 * (size_t)ix.n, bounce);
+    ix.table.ensure((size_t)h.tableSlots); get_dev(c->rt, f, ix.table.p, sizeof(Slot) * (size_t)h.tableSlots, bounce);
+    ix.posKey.ensure((size_t)ix.n + 1); get_dev(c->rt, f, ix.posKey.p, 8 * (size_t)ix.n, bounce);
+    if (ix.hasSeq16) { ix.posSeq16.ensure((size_t)ix.n + 8); get_dev(c->rt, f, ix.posSeq16.p, 2 * (size_t)ix.n, bounce); }
+    ix.dupBits.ensure((size_t)(ix.n / 32 + 2)); get_dev(c->rt, f, ix.dupBits.p, 4 * (size_t)(ix.n / 32 + 2), bounce);
+    ix.dupIdx.ensure((size_t)ix.n_dup + 1); ix.dupLinks.ensure((size_t)ix.n_dup + 1);
+    get_dev(c->rt, f, ix.dupIdx.p, 4 * (size_t)ix.n_dup, bounce); get_dev(c->rt, f, ix.dupLinks.p, 8 * (size_t)ix.n_dup, bounce);
+    ix.finalized = true;
+  } catch (...) { fclose(f); delete idx; throw; }
+  fclose(f);
+  *out = idx;
+  MM_CATCH
+}
+int mm_index_params(const mm_index* idx, int32_t* k, int32_t* w, int32_t* contig_len) {
+  if (!idx) { g_err = "null index"; return MM_EINVAL; }
+  if (k) *k = idx->ix.k;
+  if (w) *w = idx->ix.w;
+  if (contig_len) for (int32_t i = 0; i < idx->ix.n_contigs; i++) contig_len[i] = idx->ix.h_contigLen[(size_t)i];
+  return MM_OK;
+}
 int mm_index_lookup(const mm_index* idx, const uint32_t* hashes, int64_t n, int32_t* counts) {
   MM_TRY
   if (!idx || !idx->ix.finalized) throw Error(MM_EINVAL, "index not finalized");

@@ -52,3 +52,21 @@ def compare_dirs(ref_dir, got_dir):
         if k != "outFileName":
             assert pa[k] == pb[k], k
     return identical
+
+
+def run_cli_via_index(binary, workdir, out="out_ix"):
+    """`metamaps index` then `metamaps mapAgainstIndex` (+ classify): the persistent-index route to the same files."""
+    os.makedirs(os.path.join(workdir, out), exist_ok=True)
+    subprocess.run([binary, "index", "-r", "db/DB.fa", "-i", f"{out}/idx"], cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    manifest = open(os.path.join(workdir, out, "idx.index")).read().split()
+    assert manifest[0] == "1" and len(manifest) == 2 and os.path.exists(os.path.join(workdir, manifest[1]))     # mapWrap.h:395-403
+    subprocess.run([binary, "mapAgainstIndex", "--all", "-i", f"{out}/idx", "-q", "reads.fq", "-o", f"{out}/ref"], cwd=workdir, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    subprocess.run([binary, "classify", "--DB", "db", "--mappings", f"{out}/ref"], cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    return os.path.join(workdir, out)
+
+
+def compare_mapping_files(dir_a, dir_b):
+    """Every output of the index route equals the mapDirectly route byte for byte (same library, same arrays)."""
+    for fn in OUTPUTS:
+        assert open(os.path.join(dir_a, fn)).read() == open(os.path.join(dir_b, fn)).read(), fn

@@ -297,3 +297,27 @@ def check_staged_equals_direct(ctx, contigs, reads, k, w):
         got = capi.map_reads(ctx, ix, None, 80.0, 1000, offsets=bufs[slot][1], staged_slot=slot)
         for key in ("s", "cand_off", "seq", "pos", "shared", "votes", "accepted", "valid"):
             assert np.array_equal(got[key], direct[slot][key]), (slot, key)
+
+
+def check_index_save_load(ctx, contigs, reads, k, w, path):
+    """mm_index_save -> mm_index_load: identical arrays and identical mapping results."""
+    from metamaps_b200 import capi
+    ix = build_index(ctx, contigs, k, w)
+    ix.save(path)
+    ix2 = capi.Index.load(ctx, path)
+    sa, sb = ix.stats(), ix2.stats()
+    sa.pop("device_bytes"); sb.pop("device_bytes")          # allocation sizes, not content
+    assert (ix2.k, ix2.w) == (k, w) and sa == sb, (sa, sb)
+    for a, b in zip(ix.fetch(), ix2.fetch()):
+        assert np.array_equal(a, b)
+    probe = np.concatenate([ix.fetch()[0][:2000], np.arange(1000, dtype=np.uint32) * 7919])
+    assert np.array_equal(ix.lookup(probe), ix2.lookup(probe))
+    r1 = capi.map_reads(ctx, ix, reads, 80.0, 1000); r2 = capi.map_reads(ctx, ix2, reads, 80.0, 1000)
+    for key in ("s", "cand_off", "seq", "start", "end", "pos", "shared", "votes", "accepted", "valid", "optStart", "optEnd"):
+        assert np.array_equal(r1[key], r2[key]), key
+    assert r1["summary"]["n_mappings"] > 0
+    with open(path, "r+b") as f:          # a damaged file is refused, not loaded
+        f.write(b"XXXX")
+    import pytest
+    with pytest.raises(capi.MMError):
+        capi.Index.load(ctx, path)

@@ -53,3 +53,12 @@ def test_cli_without_all_keeps_top_mappings(tmp_path):
     subprocess.run([binary, "mapDirectly", "-r", "db/DB.fa", "-q", "reads.fq", "-o", "o2/ref"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     assert open(os.path.join(d, "o1", "ref")).read() == open(os.path.join(d, "o2", "ref")).read()
     assert open(os.path.join(d, "o1", "ref.meta")).read() == open(os.path.join(d, "o2", "ref.meta")).read()
+
+
+def test_cli_index_then_mapAgainstIndex(small_workload):
+    """`index` + `mapAgainstIndex` (GPU-native index file behind the reference's <prefix>.index manifest) = `mapDirectly`."""
+    binary = build_emu_host()
+    direct = cli_common.run_cli(binary, small_workload["dir"], out="out_emu_d")
+    via = cli_common.run_cli_via_index(binary, small_workload["dir"], out="out_emu_ix")
+    cli_common.compare_mapping_files(direct, via)
+    assert cli_common.compare_dirs(os.path.join(GOLDEN, "ref_small"), via) >= 8

@@ -138,6 +138,8 @@ def test_cli_matches_golden_reference_files(small_workload):
     assert os.path.exists(build.HOST_BIN), "metamaps_b200/metamaps not built"
     got = cli_common.run_cli(build.HOST_BIN, small_workload["dir"], out="out_gpu")
     assert cli_common.compare_dirs(os.path.join(GOLDEN, "ref_small"), got) >= 8
+    via = cli_common.run_cli_via_index(build.HOST_BIN, small_workload["dir"], out="out_gpu_ix")      # index + mapAgainstIndex
+    cli_common.compare_mapping_files(got, via)
 
 
 @pytest.mark.parametrize("name", ["many_contigs", "long_read", "low_complexity"])
@@ -185,3 +187,8 @@ def test_contig_shards_walked_in_one_process(gpu_ctx, small_workload):
 def test_staged_reads(gpu_ctx, small_workload):
     contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
     common.check_staged_equals_direct(gpu_ctx, contigs, [synth.codes_to_ascii(r) for r in small_workload["reads"]], 16, 13)
+
+
+def test_index_save_load(gpu_ctx, small_workload, tmp_path):
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    common.check_index_save_load(gpu_ctx, contigs, [synth.codes_to_ascii(r) for r in small_workload["reads"]], 16, 13, str(tmp_path / "ix.0"))

@@ -150,3 +150,8 @@ def test_contig_shards_walked_in_one_process(emu_ctx, small_workload):
 def test_staged_reads(emu_ctx, small_workload):
     contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
     common.check_staged_equals_direct(emu_ctx, contigs, [synth.codes_to_ascii(r) for r in small_workload["reads"][:60]], 16, 13)
+
+
+def test_index_save_load(emu_ctx, small_workload, tmp_path):
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    common.check_index_save_load(emu_ctx, contigs, [synth.codes_to_ascii(r) for r in small_workload["reads"][:40]], 16, 13, str(tmp_path / "ix.0"))
