@@ -47,13 +47,29 @@ struct PackFn {
     int32_t L = ldg(len + sq);
     const uint8_t* src = asc + ldg(ascOff + sq) + lw * 16;
     int32_t nb = L - (int32_t)(lw * 16); if (nb > 16) nb = 16;
+    // the 16 bytes are fetched as the (at most five) aligned 32-bit words that hold them -- every such word contains at least
+    // one byte of the sequence, so the loads stay inside the caller's allocation -- and realigned with funnel shifts
+    const uintptr_t addr = (uintptr_t)src; const int mis = (int)(addr & 3);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr - mis);
+    const int nWords = (mis + nb + 3) / 4;
+    uint32_t wv[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) wv[i] = i < nWords ? ldg(wp + i) : 0u;
     uint32_t word = 0;
-    for (int b = 0; b < nb; b++) {
-      uint32_t u = upper_ascii(ldg(src + b));
-      word |= ((u >> 1) & 3u) << (2 * b);
-      if (!is_acgt_upper(u)) {
-        unsigned long long slot = atomic_add_u64(excCount, 1ull);
-        if ((int64_t)slot < excCap) { excPos[slot] = (uint64_t)t * 16 + b; excByte[slot] = (uint8_t)u; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint32_t four = mis ? ((wv[q] >> (8 * mis)) | (wv[q + 1] << (32 - 8 * mis))) : wv[q];
+#pragma unroll
+      for (int b4 = 0; b4 < 4; b4++) {
+        const int b = 4 * q + b4;
+        if (b < nb) {
+          uint32_t u = upper_ascii((four >> (8 * b4)) & 0xffu);
+          word |= ((u >> 1) & 3u) << (2 * b);
+          if (!is_acgt_upper(u)) {
+            unsigned long long slot = atomic_add_u64(excCount, 1ull);
+            if ((int64_t)slot < excCap) { excPos[slot] = (uint64_t)t * 16 + b; excByte[slot] = (uint8_t)u; }
+          }
+        }
       }
     }
     packed[t] = word;
@@ -304,7 +320,9 @@ struct Sketcher {
     int64_t ovfCap = 1 << 16; ovfList.ensure((size_t)ovfCap);
     SketchArgs a{B.packed.p, B.wordOff.p, B.len.p, n, chunkOff.p, posOff.p, B.excPos.p, B.excByte.p, B.n_exc,
                  k, w, CH, slabHash.p, slabWs.p, chunkCount.p, ovfCount.p, ovfList.p, ovfCap, nullptr, nullptr, 0};
-    { StageTimer t(rt, chunkMs); foreach(rt, chunks, SketchChunkFn<false>{a}, 128, 16); }
+    static int gridCap = 0;
+    if (!gridCap) { const char* e = getenv("MM_SKETCH_CTAS"); gridCap = e ? atoi(e) : (1 << 20); if (gridCap < 1) gridCap = 16; }   // one chunk per thread: the hardware block scheduler balances the tail
+    { StageTimer t(rt, chunkMs); foreach(rt, chunks, SketchChunkFn<false>{a}, 128, gridCap); }
     unsigned long long novf = 0; d2h(rt, &novf, ovfCount.p, sizeof(novf));
     if (novf) {   // deque longer than 32 entries: replay those chunks with a w-entry deque in global memory
       if ((int64_t)novf > ovfCap) throw Error(-34, "too many deque overflows in one batch");
