@@ -381,10 +381,12 @@ int mm_stage_reads_async(mm_ctx* c, int slot, const char* reads, const int64_t* 
   {
     const int dev = c->rt.device; cudaStream_t cs = c->rt.copy; uint8_t* dst = st.asc.p; const char* src = reads + offsets[0];
     cudaEvent_t ev = st.ready; int* err = &st.feedErr;
+    int64_t piece = (int64_t)8 << 20;
+    if (const char* e = getenv("MM_STAGE_PIECE_KB")) { long long v = atoll(e); if (v >= 64) piece = v << 10; }
     st.feeder = std::thread([=]() {
       if (cudaSetDevice(dev) != cudaSuccess) { *err = 1; return; }
-      for (int64_t o = 0; o < bytes; o += (int64_t)8 << 20) {
-        const int64_t nb = std::min<int64_t>((int64_t)8 << 20, bytes - o);
+      for (int64_t o = 0; o < bytes; o += piece) {
+        const int64_t nb = std::min<int64_t>(piece, bytes - o);
         if (cudaMemcpyAsync(dst + o, src + o, (size_t)nb, cudaMemcpyHostToDevice, cs) != cudaSuccess || cudaStreamSynchronize(cs) != cudaSuccess) { *err = 1; return; }
       }
       if (cudaEventRecord(ev, cs) != cudaSuccess) *err = 1;
