@@ -192,3 +192,58 @@ def test_staged_reads(gpu_ctx, small_workload):
 def test_index_save_load(gpu_ctx, small_workload, tmp_path):
     contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
     common.check_index_save_load(gpu_ctx, contigs, [synth.codes_to_ascii(r) for r in small_workload["reads"]], 16, 13, str(tmp_path / "ix.0"))
+
+
+def test_map_at_scale_independent_paths_agree(oracle, monkeypatch):
+    """Config-2-shaped workload at a size the oracle cannot finish (360 Mbp, 4 000 log-normal reads up to 40 kb, w = 16):
+    the fast kernel chain (block-sort K3, 16-bit contig filter, banded + segmented sweep) and the independent general chain
+    (global sort, 8-byte filter, full-state sweep in global memory) must agree on every candidate; size-independent
+    properties hold; a random subsample is checked against the oracle."""
+    import torch
+    import bench
+    dev = torch.device("cuda", 0)
+    wl = dict(n_species=60, n_strains=3, contig_len=2_000_000, div=0.01, n_reads=4000, mean_len=8000, sigma=0.5, min_read_len=2000, w=16, seed=17)
+    asc, codes, offsets, _, _ = bench.gen_db(torch, dev, wl)
+    r_asc, r_off = bench.gen_reads(torch, dev, wl, codes, 0)
+    torch.cuda.synchronize()
+    results = []
+    for env in ({}, {"MM_SWEEP": "global", "MM_K3_GLOBAL": "1", "MM_L1_FILTER": "legacy"}):
+        for k_, v in env.items():
+            monkeypatch.setenv(k_, v)
+        ctx = capi.Context(0)
+        ix = capi.Index(ctx, 16, wl["w"])
+        ix.add_dev(asc.data_ptr(), offsets); ix.finalize()
+        res = capi.map_reads(ctx, ix, None, 80.0, wl["min_read_len"], dev_ptr=r_asc.data_ptr(), offsets=r_off, fetch_sketch=True)
+        results.append(res)
+        if env:
+            assert res["stats"]["smem_swept"] == 0
+        else:
+            assert res["stats"]["smem_swept"] == len(res["shared"]) and res["stats"]["sweep_items"] > len(res["shared"])   # segments were cut
+        ix.close(); ctx.close()
+    a, b = results
+    assert len(a["shared"]) > 8000
+    for key in ("s", "minimumHits", "cand_off", "seq", "start", "end", "pos", "shared", "votes", "accepted", "valid", "optStart", "optEnd", "q_off", "q_hash",
+                "q_strand"):
+        assert np.array_equal(a[key], b[key]), key
+    # properties
+    cand_read = np.repeat(np.arange(len(a["s"])), np.diff(a["cand_off"]))
+    assert (a["shared"] <= a["s"][cand_read]).all() and (a["shared"] >= 0).all()
+    assert (np.abs(a["votes"]) <= a["shared"]).all()
+    assert (a["start"] <= a["end"]).all()
+    same = cand_read[1:] == cand_read[:-1]
+    key2 = a["seq"].astype(np.int64) * (1 << 32) + a["start"]
+    assert (key2[1:][same] > key2[:-1][same]).all()                       # per read: (seqId, position) order, disjoint loci
+    assert (np.diff(a["q_off"]) == a["s"]).all()
+    for r in range(0, len(a["s"]), 97):                                   # sketches sorted and unique
+        q = a["q_hash"][a["q_off"][r]:a["q_off"][r + 1]]
+        assert (np.diff(q.astype(np.int64)) > 0).all()
+    # oracle on a subsample (it needs the contigs the reads map to: use whole contigs of the first candidates)
+    host_reads = r_asc.cpu().numpy()
+    contig_ids = sorted(set(int(x) for x in a["seq"][:60]))[:6]
+    L = wl["contig_len"]
+    sub_contigs = [bytes(asc[c * L:(c + 1) * L].cpu().numpy()) for c in contig_ids]
+    pick = [r for r in range(len(a["s"])) if a["cand_off"][r + 1] > a["cand_off"][r] and int(a["seq"][a["cand_off"][r]]) in contig_ids][:25]
+    sub_reads = [bytes(host_reads[r_off[r]:r_off[r + 1]]) for r in pick]
+    ctx = capi.Context(0)
+    common.check_map_vs_oracle(ctx, oracle, sub_contigs, sub_reads, 16, wl["w"], 80.0, wl["min_read_len"], batches=1)
+    ctx.close()
