@@ -229,10 +229,12 @@ def main():
         reference_arm(args, wl)
         return
 
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:       # the host helpers (identities, nLoc) are OpenMP loops: share the cores between the ranks of the node
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     import torch
     import torch.distributed as dist
     from metamaps_b200 import capi, pipeline
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
