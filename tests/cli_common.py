@@ -70,3 +70,58 @@ def compare_mapping_files(dir_a, dir_b):
     """Every output of the index route equals the mapDirectly route byte for byte (same library, same arrays)."""
     for fn in OUTPUTS:
         assert open(os.path.join(dir_a, fn)).read() == open(os.path.join(dir_b, fn)).read(), fn
+
+
+def check_db_with_N_runs_lowercase_and_iupac(binary, tmp_path):
+    """A DB directory as buildDB.pl leaves it for real genomes: N runs, soft-masked lower case, IUPAC codes in
+    contigs and reads, and non-zero contigNstats.  Non-ACGT bytes are hashed verbatim by the reference (commonFunc.hpp:44-51)
+    -> the packed-sequence exception path of K0/K1 -- and N windows enter the coverage statistics of classify."""
+    import pytest
+    from metamaps_b200 import synth
+    from oracle import pyoracle
+    if not pyoracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    d = str(tmp_path)
+    db = synth.make_db(9, 3, 2, 60_000, 0.02)
+    synth.write_db(db, os.path.join(d, "db"))
+    import numpy as np
+    rng = np.random.default_rng(4)
+    contigs = []
+    for c in db.contig_codes:
+        a = bytearray(synth.codes_to_ascii(c))
+        for _ in range(3):                                   # N runs (some longer than a window of k-mers, some short)
+            p = int(rng.integers(0, len(a) - 400)); n = int(rng.choice([1, 7, 40, 350]))
+            a[p:p + n] = b"N" * n
+        for _ in range(4):                                   # soft-masked repeats
+            p = int(rng.integers(0, len(a) - 600)); a[p:p + 500] = bytes(a[p:p + 500]).lower()
+        for _ in range(6):                                   # IUPAC ambiguity codes
+            a[int(rng.integers(0, len(a)))] = int(rng.choice(list(b"RYKMSWn")))
+        contigs.append(bytes(a))
+    with open(os.path.join(d, "db", "DB.fa"), "wb") as f:
+        for name, a in zip(db.contig_names, contigs):
+            f.write(b">" + name.encode() + b"\n")
+            for i in range(0, len(a), 80):
+                f.write(a[i:i + 80] + b"\n")
+    with open(os.path.join(d, "db", "contigNstats_windowSize_1000.txt"), "w") as f:
+        for name, t, a in zip(db.contig_names, db.contig_taxon, contigs):
+            up = a.upper()
+            f.write(f"{t}\t{name}\t" + ";".join(str(up[i:i + 1000].count(b"N")) for i in range(0, len(a), 1000)) + "\n")
+    names, reads, _ = synth.make_reads(db, 10, 120, 2500, lognormal_sigma=0.3, clip=(900, 6000))
+    reads_asc = []
+    for r in reads:
+        a = bytearray(synth.codes_to_ascii(r))
+        if rng.random() < 0.3:
+            p = int(rng.integers(0, max(1, len(a) - 60))); a[p:p + 30] = b"N" * min(30, len(a) - p)
+        if rng.random() < 0.3:
+            a[:] = bytes(a).lower()
+        reads_asc.append(bytes(a))
+    with open(os.path.join(d, "reads.fq"), "wb") as f:
+        for nme, a in zip(names, reads_asc):
+            f.write(b"@" + nme.encode() + b"\n" + a + b"\n+\n" + b"I" * len(a) + b"\n")
+    os.makedirs(os.path.join(d, "out_ref"), exist_ok=True)
+    subprocess.run([pyoracle.REF_BIN, "mapDirectly", "--all", "-r", "db/DB.fa", "-q", "reads.fq", "-o", "out_ref/ref"], cwd=d, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([pyoracle.REF_BIN, "classify", "--DB", "db", "--mappings", "out_ref/ref"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    got = run_cli(binary, d, out="out_emu")
+    compare_dirs(os.path.join(d, "out_ref"), got)
+    assert sum(1 for _ in open(os.path.join(d, "out_ref", "ref"))) > 100

@@ -62,3 +62,7 @@ def test_cli_index_then_mapAgainstIndex(small_workload):
     via = cli_common.run_cli_via_index(binary, small_workload["dir"], out="out_emu_ix")
     cli_common.compare_mapping_files(direct, via)
     assert cli_common.compare_dirs(os.path.join(GOLDEN, "ref_small"), via) >= 8
+
+
+def test_cli_db_with_N_runs_lowercase_and_iupac(tmp_path):
+    cli_common.check_db_with_N_runs_lowercase_and_iupac(build_emu_host(), tmp_path)

@@ -247,3 +247,10 @@ def test_map_at_scale_independent_paths_agree(oracle, monkeypatch):
     ctx = capi.Context(0)
     common.check_map_vs_oracle(ctx, oracle, sub_contigs, sub_reads, 16, wl["w"], 80.0, wl["min_read_len"], batches=1)
     ctx.close()
+
+
+def test_cli_db_with_N_runs_lowercase_and_iupac(tmp_path):
+    """The CUDA host binary against the unmodified reference on a DB with N runs, soft-masking and IUPAC codes."""
+    from metamaps_b200 import build
+    from tests import cli_common
+    cli_common.check_db_with_N_runs_lowercase_and_iupac(build.HOST_BIN, tmp_path)
