@@ -20,8 +20,10 @@
  *   - plain pointers + sizes; the caller owns every buffer it passes; the library owns handles until the
  *     matching *_destroy;  "host" pointers are ordinary host memory, "_dev" entry points take CUDA
  *     device pointers on the context's device;
- *   - one mm_ctx per GPU, used by one host thread at a time; work is issued on the context's CUDA stream
- *     and every entry point returns after its results are complete unless stated otherwise;
+ *   - an mm_ctx is used by one host thread at a time; work is issued on the context's CUDA stream and every entry
+ *     point returns after its results are complete unless stated otherwise.  Several contexts may exist per GPU
+ *     (e.g. two host threads, one context each, keeping two batches in flight); a finalized mm_index is read-only
+ *     and may be mapped against from any context of its device;
  *   - there is no CPU implementation: if no CUDA device is usable, mm_ctx_create fails.
  *
  * Sequences are ASCII (any case, any byte; non-ACGT bytes are hashed verbatim like the reference does,

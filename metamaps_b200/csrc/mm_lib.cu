@@ -342,7 +342,9 @@ static int map_impl(mm_ctx* c, const mm_index* idx, const char* reads, const voi
                     const mm_map_params* p, mm_map_summary* out) {
   MM_TRY
   if (!c || !idx || !offsets || !p || n < 0) throw Error(MM_EINVAL, "mm_map_batch: bad arguments");
-  if (idx->ctx != c) throw Error(MM_EINVAL, "index belongs to another context");
+  // a finalized index is read-only: any context of the same device may map against it (two host threads with one
+  // context each keep two batches in flight and fill each other's synchronisation bubbles)
+  if (idx->ctx->rt.device != c->rt.device) throw Error(MM_EINVAL, "index lives on another device");
   if (!idx->ix.finalized) throw Error(MM_EINVAL, "index not finalized");
   begin_call(c);
   c->sk.load(c->mp.batch, reads, dev, offsets, n);
