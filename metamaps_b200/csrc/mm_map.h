@@ -926,6 +926,63 @@ struct BandSweep {
     if (i < s && i - lo >= BW) bad = true;                   // istar is above the band
     istar = i;
   }
+#if defined(__CUDA_ARCH__)
+  // Warp-cooperative form of rebuild(beg, end, center, bias) for lane `l` of a converged warp (all 32 lanes call it): the
+  // lanes stride over lane l's window (coalesced 8-byte events) and update ITS band with shared-memory atomics; lane l then
+  // walks to istar.  30 strides instead of one lane scanning ~s events while 31 lanes wait.
+  MM_DEV void rebuild_coop(int l, int32_t beg_, int32_t end_, int32_t center, int32_t bias) {
+    const int lane = threadIdx.x & 31;
+    int32_t l0 = center - BW / 2 + bias;
+    if (l0 > s + 1 - BW) l0 = s + 1 - BW;
+    if (l0 < 0) l0 = 0;
+    // lane l's view, broadcast
+    const int32_t lo_l = __shfl_sync(0xffffffffu, l0, l), s_l = __shfl_sync(0xffffffffu, s, l);
+    const int32_t beg_l = __shfl_sync(0xffffffffu, beg_, l), end_l = __shfl_sync(0xffffffffu, end_, l);
+    const unsigned long long e_l = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)e, l);
+    const unsigned long long cnt_l = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)cnt, l);
+    const unsigned long long mb_l = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)mb, l);
+    const long long b0_l = __shfl_sync(0xffffffffu, (long long)b0, l);
+    const uint2* el = reinterpret_cast<const uint2*>((uintptr_t)e_l);
+    uint32_t* cw = reinterpret_cast<uint32_t*>((uintptr_t)cnt_l);
+    uint32_t* mw = reinterpret_cast<uint32_t*>((uintptr_t)mb_l);
+    for (int32_t i = lane; i < (BW + 4) / 4; i += 32) cw[i] = 0;
+    for (int32_t i = lane; i <= BW / 32; i += 32) mw[i] = 0;
+    __syncwarp();
+    int32_t Cb = 0, Sb = 0, ovf = 0;
+    for (int32_t j = beg_l + lane; j < end_l; j += 32) {
+      const uint32_t code = __ldg(&el[j].x);
+      bool cntd = true;
+      if (code & CODE_DUP) {
+        const uint64_t lk = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0_l + j);
+        const int64_t pd = (int64_t)(lk >> 32);
+        cntd = !(pd && (int64_t)j - pd >= (int64_t)beg_l);
+      }
+      const int32_t isM = (int32_t)(code >> 31), idx = (int32_t)(code & CODE_IDX);
+      const int32_t rel = idx - isM - lo_l;
+      const bool below = cntd && rel < 0;
+      Sb += (below && isM) ? 1 : 0; Cb += (below && !isM) ? 1 : 0;
+      const bool inb = cntd && (uint32_t)rel < (uint32_t)BW;
+      if (inb && !isM && idx < s_l) {
+        const uint32_t old = atomicAdd(cw + (rel >> 2), 1u << (8 * (rel & 3)));
+        if (((old >> (8 * (rel & 3))) & 0xffu) == 255u) ovf = 1;
+      }
+      if (inb && isM) atomicOr(mw + (rel >> 5), 1u << (rel & 31));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { Cb += __shfl_xor_sync(0xffffffffu, Cb, o); Sb += __shfl_xor_sync(0xffffffffu, Sb, o); ovf |= __shfl_xor_sync(0xffffffffu, ovf, o); }
+    __syncwarp();
+    if (lane == l) {
+      bad = false; lo = l0;
+      if (ovf) fail = true;
+      int32_t i = lo; C = Cb; shared = Sb;
+      if (lo > 0 && lo + Cb > s) bad = true;
+      while (i < s && i - lo < BW && i + 1 + C + (int32_t)cnt[i - lo] <= s) { C += (int32_t)cnt[i - lo]; i++; shared += (int32_t)bit(i - 1 - lo); }
+      if (i < s && i - lo >= BW) bad = true;
+      istar = i;
+    }
+    __syncwarp();
+  }
+#endif
   // one insertion (isDel = 0) or deletion (isDel = 1) of the reference minimizer with event code `code`
   // (SlideMapper::insert_ref / delete_ref, slidingMap.hpp:139-219).  Straight-line: an update that does not apply
   // lands in the dummy slots.  An insertion can push q_istar out of the bottom-s, a deletion can let q_{istar+1} in;
@@ -1047,17 +1104,26 @@ MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0
       beg += isDel; end += 1 - isDel;
       const uint2 nx = ev.fetch(1 - isDel, isDel ? beg + 1 : end);
       evBeg = isDel ? evBeg1 : evBeg; evBeg1 = isDel ? nx : evBeg1; evEnd = isDel ? evEnd : nx;
-      if (z.out_of_band() || z.fail) {
-        if (!z.fail) {
+#if !defined(__CUDA_ARCH__)
+      if (z.out_of_band() && !z.fail) {
 #ifdef MM_BAND_DEBUG
-          dbgReb += end - beg;
+        dbgReb += end - beg;
 #endif
-          z.rebuild(beg, end, z.istar, z.istar <= z.lo ? -BW / 4 : BW / 4);   // keep drifting room on the side it left
-          if (z.bad) z.fail = true;
-        }
+        z.rebuild(beg, end, z.istar, z.istar <= z.lo ? -BW / 4 : BW / 4);   // keep drifting room on the side it left
+        if (z.bad) z.fail = true;
       }
+#endif
       active = !z.fail && end < last && beg < B1;
     }
+#if defined(__CUDA_ARCH__)
+    // istar left the band on some lanes: the whole warp rebuilds their states one after the other
+    unsigned need = __ballot_sync(0xffffffffu, active && z.out_of_band());
+    while (need) {
+      const int l = __ffs(need) - 1; need &= need - 1;
+      z.rebuild_coop(l, beg, end, z.istar, z.istar <= z.lo ? -BW / 4 : BW / 4);
+      if ((int)(threadIdx.x & 31) == l && (z.bad || z.fail)) { z.fail = true; active = false; }
+    }
+#endif
   }
   fail = fail || z.fail;
   out.shared = best; out.bpos = bpos; out.lpos = lpos; out.optS = optS; out.optE = optE; out.istar = bistar; out.any = any; out.fail = fail ? 1 : 0;
@@ -1666,10 +1732,9 @@ struct Mapper {
 #else
       pr.sort_pairs<uint32_t, uint32_t>(swKey.p, swKey2.p, swVal.p, swOrder.p, nItems, 32);
       unsigned long long nWide = 0; d2h(rt, &nWide, scal.p + 2, sizeof(nWide));
-      if (BAND != 256) nWide = 0;                                           // test widths: one instantiation for everything
       {
         StageTimer tb(rt, &st.ms[11]);                                      // the sweep kernel proper
-        if (nWide > 0) launch_band_t<512, 8>(sa, swOrder.p, (int64_t)nWide);
+        if (nWide > 0) { if (BAND == 256) launch_band_t<512, 8>(sa, swOrder.p, (int64_t)nWide); else launch_band_t<256, 8>(sa, swOrder.p, (int64_t)nWide); }
         if ((int64_t)nWide < nItems) {
           if (nWide > 0) dev_memset(rt, scal.p + 1, 0, sizeof(unsigned long long));       // fresh tile counter
           launch_band(sa, swOrder.p + nWide, nItems - (int64_t)nWide);
