@@ -321,3 +321,39 @@ def check_index_save_load(ctx, contigs, reads, k, w, path):
     import pytest
     with pytest.raises(capi.MMError):
         capi.Index.load(ctx, path)
+
+
+def check_api_errors(ctx, tmp_path):
+    """Misuse of the session-2 entry points fails loudly with an MM_E* code and a message, never silently."""
+    import ctypes as C
+    import pytest
+    from metamaps_b200 import capi
+    lib = ctx.lib
+    contigs = [synth.codes_to_ascii(np.random.default_rng(1).integers(0, 4, 30_000, dtype=np.uint8))]
+    ix = build_index(ctx, contigs, 16, 13)
+    with pytest.raises(capi.MMError) as e:
+        ix.set_shard(3)                                   # after finalize
+    assert e.value.code == -22
+    with pytest.raises(capi.MMError):
+        ix.sync_threshold()                               # shard counts were not kept
+    with pytest.raises(capi.MMError):
+        capi.Index.load(ctx, str(tmp_path / "does_not_exist.0"))
+    with pytest.raises(capi.MMError):
+        ix.save(str(tmp_path / "no_such_dir" / "ix.0"))
+    fresh = capi.Context(0, lib)
+    p = capi.MapParams(80.0, 1000, 1, 0); s = capi.MapSummary()
+    assert lib.mm_map_batch_staged(fresh.h, ix.h, 0, C.byref(p), C.byref(s)) == -22      # nothing staged in that slot
+    assert b"staged" in lib.mm_last_error()
+    fresh.close()
+    reads = [contigs[0][1000:4000], contigs[0][8000:12000]]
+    res = capi.map_reads(ctx, ix, reads, 80.0, 1000, fetch=False)
+    assert res["summary"]["n_mappings"] >= 2
+    got = C.c_int64(); buf = np.zeros(1, np.int32)
+    rc = lib.mm_map_fetch_mappings(ctx.h, buf.ctypes.data, None, None, None, None, None, None, None, 1, C.byref(got))
+    assert rc == -34 and got.value == res["summary"]["n_mappings"]                        # capacity too small, count still reported
+    with pytest.raises(capi.MMError):
+        capi.nloc_batch(lib, np.array([5], np.int32), np.array([0, 1], np.int64), np.array([100], np.int32), np.array([1000], np.int64),
+                        np.array([0], np.int32), 1)                                       # contig id out of range
+    with pytest.raises(capi.MMError):
+        capi.nloc_batch(lib, np.array([0], np.int32), np.array([0, 1], np.int64), np.array([100], np.int32), np.array([1000], np.int64),
+                        np.array([7], np.int32), 1)                                       # taxon out of range

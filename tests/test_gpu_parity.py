@@ -254,3 +254,7 @@ def test_cli_db_with_N_runs_lowercase_and_iupac(tmp_path):
     from metamaps_b200 import build
     from tests import cli_common
     cli_common.check_db_with_N_runs_lowercase_and_iupac(build.HOST_BIN, tmp_path)
+
+
+def test_api_errors(gpu_ctx, tmp_path):
+    common.check_api_errors(gpu_ctx, tmp_path)

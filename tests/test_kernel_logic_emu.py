@@ -86,11 +86,12 @@ def test_em(emu_ctx, oracle):
     common.check_em_vs_oracle(emu_ctx, oracle, seed=6, max_iter=50, nr=500, T=7, maxc=30)
 
 
-def test_api_errors(emu_ctx):
+def test_api_errors(emu_ctx, tmp_path):
     with pytest.raises(capi.MMError):
         emu_ctx.sketch([b"ACGT"], 17, 5)          # k > 16 (parseCmdArgs.hpp:62)
     with pytest.raises(capi.MMError):
         capi.Index(emu_ctx, 16, 0)
+    common.check_api_errors(emu_ctx, tmp_path)
 
 
 def test_pipeline_matches_reference_files(emu_ctx, small_workload):
