@@ -57,6 +57,8 @@ void mm_ctx_destroy(mm_ctx* ctx);
 /* Device-time (ms, CUDA events on the context stream) and launch count of the kernels issued by the last
  * mm_* call on this context; bench.py uses these for `gpu_launches` and the roofline block. */
 int mm_ctx_last_timing(mm_ctx* ctx, double* total_ms, int64_t* n_launches);
+/* Free / total device memory in bytes (a host sizes its index chunks with it, like the reference's --maxmemory estimate). */
+int mm_ctx_mem_info(mm_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
 /* Per-stage device time (ms, CUDA events) of the last mm_map_* call:
  *   [0] K1 sketch  [1] K3 read sketch  [2] K4 probe+gather  [3] K4 hit sort  [4] K4 candidate regions  [5] K5 setup
  *   [6] K5a classify  [7] K5b sweep  [8] K5c strand  [9] accept + summary

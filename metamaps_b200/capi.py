@@ -44,6 +44,7 @@ SYMBOLS = {
     "mm_index_set_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "mm_index_sync_threshold": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "mm_comm_set_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mm_ctx_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mm_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mm_index_load": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "mm_index_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),

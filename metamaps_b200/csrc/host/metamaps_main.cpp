@@ -122,7 +122,7 @@ static Params parse_map_options(int argc, char** argv, int mode, int* device) {
 static void print_params(const Params& P) {
   std::cout << "Parameters used:\n\t- alphabetSize: " << P.alphabetSize << "\n\t- kmerSize: " << P.kmerSize << "\n\t- minReadLength: " << P.minReadLength
             << "\n\t- p_value: " << P.p_value << "\n\t- percentageIdentity: " << P.percentageIdentity << "\n\t- windowSize: " << P.windowSize
-            << "\n\t- maximumMemory: ~" << P.maximumMemory / std::pow(1024, 3) << " GB (GPU build: the index is device-resident, no chunking)\n\n" << std::flush;
+            << "\n\t- maximumMemory: ~" << P.maximumMemory / std::pow(1024, 3) << " GB (GPU build: caps the device-memory budget of one index chunk)\n\n" << std::flush;
 }
 static void print_index_info(mm_index* idx) {
   int64_t nMin = 0, nUniq = 0; int32_t freq = 0, nCont = 0; int64_t bytes = 0;
@@ -133,6 +133,27 @@ static void print_index_info(mm_index* idx) {
 
 }
 // skch::Sketch over the reference FASTA (winSketch.hpp:180-365) on the device
+// next chunk of the reference (contigs until `budgetBases` bases are in, like winSketch.hpp:284-329 cuts at a memory estimate);
+// returns null when the FASTA is exhausted
+static mm_index* build_index_chunk(mm_ctx* ctx, const Params& P, mmhost::FastxReader& rd, uint64_t budgetBases, std::vector<Contig>& meta) {
+  mm_index* idx = nullptr; ck(mm_index_create(ctx, P.kmerSize, P.windowSize, &idx), "mm_index_create");
+  meta.clear();
+  std::string buf; std::vector<int64_t> off{0}; uint64_t bases = 0;
+  auto flush = [&]() {
+    if (off.size() > 1) ck(mm_index_add(idx, buf.data(), off.data(), (int32_t)off.size() - 1), "mm_index_add");
+    buf.clear(); off.assign(1, 0);
+  };
+  long len;
+  while (bases < budgetBases && (len = rd.read()) >= 0) {
+    meta.push_back(Contig{rd.name, (int)len});
+    buf += rd.seq; off.push_back((int64_t)buf.size()); bases += (uint64_t)len;
+    if (buf.size() >= ((size_t)256 << 20)) flush();
+  }
+  flush();
+  if (meta.empty()) { mm_index_destroy(idx); return nullptr; }
+  ck(mm_index_finalize(idx), "mm_index_finalize");
+  return idx;
+}
 static mm_index* build_reference_index(mm_ctx* ctx, const Params& P, std::vector<Contig>& meta) {
   mm_index* idx = nullptr; ck(mm_index_create(ctx, P.kmerSize, P.windowSize, &idx), "mm_index_create");
   {
@@ -154,15 +175,29 @@ static mm_index* build_reference_index(mm_ctx* ctx, const Params& P, std::vector
   }
   return idx;
 }
+static void write_meta_and_parameters(const std::string& prefix, const Params& P, const std::string& query, size_t total, size_t tooShort, size_t mapped, size_t notMapped) {
+  std::ofstream m(prefix + ".meta");                                  // mapWrap.h:180-183
+  m << "TotalReads " << total << "\nReadsTooShort " << tooShort << "\nReadsMapped " << mapped << "\nReadsNotMapped " << notMapped << "\n";
+  m.close();
+  std::ofstream ps(prefix + ".parameters");                          // mapWrap.h:196-211
+  ps << "kmerSize " << P.kmerSize << "\nwindowSize " << P.windowSize << "\nminReadLength " << P.minReadLength << "\nalphabetSize " << P.alphabetSize
+     << "\nreferenceSize " << P.referenceSize << "\npercentageIdentity " << P.percentageIdentity << "\np_value " << P.p_value
+     << "\nrefSequences [" << P.ref << "]\nquerySequences [" << query << "]\noutFileName " << prefix << "\nreportAll " << (P.reportAll ? 1 : 0)
+     << "\nindex \nmaximumMemory " << P.maximumMemory << "\n";
+  std::cout << "INFO, skch::Map::mapQuery, [count of mapped reads, reads qualified for mapping, total input reads] = [" << mapped << ", "
+            << total - tooShort << ", " << total << "]" << std::endl;
+}
 // skch::Map over every query file + unifyFiles + addMappingQualities (computeMap.hpp:104-172, mapWrap.h:34-323)
-static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& meta, const Params& P) {
+// chunk < 0: the whole reference is in `idx` -> final files.  chunk >= 0: `idx` is chunk N of the reference -> only the
+// 12-column lines of this chunk go to <prefix>.<N> (skch::Map per chunk, mapWrap.h:425-432); unify_files finishes the job.
+static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& meta, const Params& P, int chunk = -1) {
   std::vector<std::string> queries = split(P.query, ","), prefixes = split(P.out, ",");
   if (queries.size() != prefixes.size()) die("Please specify an equal number of input and output files (as comma-separated lists)");
   for (size_t fi = 0; fi < queries.size(); fi++) {
-    const std::string prefix = prefixes[fi];
+    const std::string prefix = chunk < 0 ? prefixes[fi] : prefixes[fi] + "." + std::to_string(chunk);
     std::ofstream out(prefix);
     if (!out.is_open()) die("Cannot open output file " + prefix);
-    std::ofstream metaLengths(prefix + ".meta.unmappedReadsLengths");
+    std::ofstream metaLengths(chunk < 0 ? prefix + ".meta.unmappedReadsLengths" : std::string("/dev/null"));
     size_t total = 0, tooShort = 0, mapped = 0, notMapped = 0;
     std::set<std::string> seenIDs;
     mmhost::FastxReader rd(queries[fi]);
@@ -210,7 +245,9 @@ static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& m
           roff.push_back((int64_t)lines.size()); rlen.push_back(len); ridx.push_back(r);
         }
       }
-      if (!lines.empty()) {                                            // mapWrap.h:215-323
+      if (chunk >= 0) {
+        for (const Line& l : lines) out << l.text << "\n";
+      } else if (!lines.empty()) {                                     // mapWrap.h:215-323
         std::vector<double> id(lines.size()), mq(lines.size()); std::vector<int32_t> sh(lines.size()), ss(lines.size()), st(rlen.size());
         for (size_t i = 0; i < lines.size(); i++) { id[i] = lines[i].identity; sh[i] = lines[i].shared; ss[i] = lines[i].sketch; }
         ck(mm_mapq_batch(ctx, id.data(), sh.data(), ss.data(), rlen.data(), roff.data(), (int64_t)rlen.size(), P.kmerSize, mq.data(), st.data()), "mm_mapq_batch");
@@ -229,17 +266,69 @@ static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& m
     }
     flush();
     out.close(); metaLengths.close();
-    std::ofstream m(prefix + ".meta");
-    m << "TotalReads " << total << "\nReadsTooShort " << tooShort << "\nReadsMapped " << mapped << "\nReadsNotMapped " << notMapped << "\n";
-    m.close();
-    std::ofstream ps(prefix + ".parameters");                          // mapWrap.h:196-211
-    ps << "kmerSize " << P.kmerSize << "\nwindowSize " << P.windowSize << "\nminReadLength " << P.minReadLength << "\nalphabetSize " << P.alphabetSize
-       << "\nreferenceSize " << P.referenceSize << "\npercentageIdentity " << P.percentageIdentity << "\np_value " << P.p_value
-       << "\nrefSequences [" << P.ref << "]\nquerySequences [" << queries[fi] << "]\noutFileName " << prefix << "\nreportAll " << (P.reportAll ? 1 : 0)
-       << "\nindex \nmaximumMemory " << P.maximumMemory << "\n";
-    std::cout << "INFO, skch::Map::mapQuery, [count of mapped reads, reads qualified for mapping, total input reads] = [" << mapped << ", "
-              << total - tooShort << ", " << total << "]" << std::endl;
+    if (chunk < 0) write_meta_and_parameters(prefix, P, queries[fi], total, tooShort, mapped, notMapped);
   }
+}
+
+// mapWrap::unifyFiles (mapWrap.h:34-213): per read, in FASTQ order, the lines of every chunk file in chunk order; mapping
+// qualities over the union (addMappingQualities, mapWrap.h:215-323); counters; the chunk files are removed.
+static void unify_files(mm_ctx* ctx, const std::string& prefix, const Params& P, const std::vector<std::string>& chunkFiles, const std::string& query) {
+  std::ofstream out(prefix);
+  if (!out.is_open()) die("Cannot open output file " + prefix);
+  std::ofstream metaLengths(prefix + ".meta.unmappedReadsLengths");
+  std::vector<std::ifstream> files;
+  for (const auto& f : chunkFiles) { files.emplace_back(f); if (!files.back().is_open()) die("Cannot open " + f); }
+  std::vector<std::string> pending(files.size()); std::vector<bool> has(files.size(), false);
+  auto peek = [&](size_t fI) -> const std::string* {              // next line of chunk file fI, or null at its end
+    if (!has[fI]) { if (!std::getline(files[fI], pending[fI])) return nullptr; has[fI] = true; }
+    return &pending[fI];
+  };
+  size_t total = 0, tooShort = 0, mapped = 0, notMapped = 0;
+  std::set<std::string> processed;
+  struct L { std::string text; double identity; int shared, sketch; };
+  std::vector<L> lines; std::vector<int64_t> roff{0}; std::vector<int32_t> rlen; std::vector<std::string> rname;
+  auto flush = [&]() {
+    if (lines.empty()) { roff.assign(1, 0); rlen.clear(); rname.clear(); return; }
+    std::vector<double> id(lines.size()), mq(lines.size()); std::vector<int32_t> sh(lines.size()), ss(lines.size()), st(rlen.size());
+    for (size_t i = 0; i < lines.size(); i++) { id[i] = lines[i].identity; sh[i] = lines[i].shared; ss[i] = lines[i].sketch; }
+    ck(mm_mapq_batch(ctx, id.data(), sh.data(), ss.data(), rlen.data(), roff.data(), (int64_t)rlen.size(), P.kmerSize, mq.data(), st.data()), "mm_mapq_batch");
+    for (size_t r = 0; r < rlen.size(); r++) if (st[r]) die("WARNING!\n\tlikelihood_sum: 0\n\treadID: " + rname[r] + "\n========= END ==========");
+    for (size_t i = 0; i < lines.size(); i++) { float corrected = exp(-(1 - id[i])); out << lines[i].text << " " << corrected * 100 << " " << mq[i] << "\n"; }
+    lines.clear(); roff.assign(1, 0); rlen.clear(); rname.clear();
+  };
+  mmhost::FastxReader rd(query);
+  if (!rd.ok()) die("Cannot open " + query);
+  long len;
+  while ((len = rd.read()) >= 0) {
+    total++;
+    if (len < P.windowSize || len < P.kmerSize || len < P.minReadLength) { tooShort++; continue; }
+    const size_t before = lines.size();
+    for (size_t fI = 0; fI < files.size(); fI++) {
+      const std::string* l;
+      while ((l = peek(fI)) != nullptr) {
+        size_t sp = l->find(' ');
+        if (sp == std::string::npos) { has[fI] = false; continue; }
+        const std::string id = l->substr(0, sp);
+        if (processed.count(id)) die("Seems that read ID " + id + " has already been processed - this target ID " + rd.name + "\n");
+        if (id != rd.name) break;
+        std::vector<std::string> f = split(*l, " ");
+        if (f.size() != 12) die("Unexpected line in " + chunkFiles[fI] + ": " + *l);
+        lines.push_back(L{*l, std::stod(f[9]) / 100.0, atoi(f[10].c_str()), atoi(f[11].c_str())});
+        has[fI] = false;
+      }
+    }
+    if (lines.size() == before) { notMapped++; metaLengths << (int)len << "\t" << rd.name << "\n"; }
+    else { mapped++; roff.push_back((int64_t)lines.size()); rlen.push_back((int32_t)len); rname.push_back(rd.name); }
+    processed.insert(rd.name);
+    if (lines.size() >= (1u << 20)) flush();
+  }
+  flush();
+  if (total - tooShort != 0)
+    for (size_t fI = 0; fI < files.size(); fI++) if (peek(fI)) die("Error: output file " + std::to_string(fI) + " / " + std::to_string(files.size()) + " not completely processed.\n\tFile: " + chunkFiles[fI]);
+  out.close(); metaLengths.close();
+  for (auto& f : files) f.close();
+  for (const auto& f : chunkFiles) std::remove(f.c_str());
+  write_meta_and_parameters(prefix, P, query, total, tooShort, mapped, notMapped);
 }
 
 int run_mapDirectly(int argc, char** argv) {
@@ -247,11 +336,36 @@ int run_mapDirectly(int argc, char** argv) {
   Params P = parse_map_options(argc, argv, 0, &device);
   print_params(P);
   mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
+  // Does the index fit the device?  ~75 bytes per minimizer while it is being built (8 + 8 + 2 resident, 32 of table at load
+  // 0.5, sort temporaries), 2/(w+1) minimizers per base; --maxmemory (GB) caps the budget like in the reference.
+  int64_t freeB = 0, totalB = 0; ck(mm_ctx_mem_info(ctx, &freeB, &totalB), "mm_ctx_mem_info");
+  double budget = 0.6 * (double)freeB;
+  if (P.maximumMemory > 0 && (double)P.maximumMemory < budget) budget = (double)P.maximumMemory;
+  uint64_t chunkBases = (uint64_t)(budget / (75.0 * 2.0 / (P.windowSize + 1)));
+  if (const char* e = getenv("MM_HOST_CHUNK_BASES")) chunkBases = strtoull(e, nullptr, 10);       // tests: force chunking
   std::vector<Contig> meta;
-  mm_index* idx = build_reference_index(ctx, P, meta);
-  print_index_info(idx);
-  map_queries(ctx, idx, meta, P);
-  mm_index_destroy(idx); mm_ctx_destroy(ctx);
+  if (P.referenceSize <= chunkBases) {                               // the usual case: one device-resident index
+    mm_index* idx = build_reference_index(ctx, P, meta);
+    print_index_info(idx);
+    map_queries(ctx, idx, meta, P);
+    mm_index_destroy(idx);
+  } else {                                                           // the reference's chunk loop (winSketch.hpp:284-329, mapWrap.h:407-441)
+    std::vector<std::string> queries = split(P.query, ","), prefixes = split(P.out, ",");
+    if (queries.size() != prefixes.size()) die("Please specify an equal number of input and output files (as comma-separated lists)");
+    mmhost::FastxReader rd(P.ref);
+    if (!rd.ok()) die("Cannot open " + P.ref);
+    std::vector<std::vector<std::string>> chunkFiles(prefixes.size());
+    int N = 0;
+    for (mm_index* idx; (idx = build_index_chunk(ctx, P, rd, chunkBases, meta)) != nullptr; N++) {
+      std::cout << "Index chunk " << N << ": " << meta.size() << " contigs\n";
+      print_index_info(idx);
+      map_queries(ctx, idx, meta, P, N);
+      for (size_t fi = 0; fi < prefixes.size(); fi++) chunkFiles[fi].push_back(prefixes[fi] + "." + std::to_string(N));
+      mm_index_destroy(idx);
+    }
+    for (size_t fi = 0; fi < prefixes.size(); fi++) unify_files(ctx, prefixes[fi], P, chunkFiles[fi], queries[fi]);
+  }
+  mm_ctx_destroy(ctx);
   return 0;
 }
 

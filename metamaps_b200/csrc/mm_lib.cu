@@ -126,6 +126,20 @@ int mm_ctx_last_timing(mm_ctx* c, double* total_ms, int64_t* n_launches) {
   if (n_launches) *n_launches = c->last_launches;
   return MM_OK;
 }
+int mm_ctx_mem_info(mm_ctx* c, int64_t* free_bytes, int64_t* total_bytes) {
+  MM_TRY
+  if (!c) throw Error(MM_EINVAL, "null ctx");
+#ifndef MM_HOST_EMU
+  MM_CUDA(cudaSetDevice(c->rt.device));
+  size_t f = 0, t = 0; MM_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+#else
+  if (free_bytes) *free_bytes = (int64_t)8 << 30;       // the emulation build pretends to be an 8 GB device
+  if (total_bytes) *total_bytes = (int64_t)8 << 30;
+#endif
+  MM_CATCH
+}
 int mm_ctx_last_map_stats(mm_ctx* c, double* stage_ms, int64_t* counters) {
   if (!c) return MM_EINVAL;
   for (int i = 0; i < 16; i++) { if (stage_ms) stage_ms[i] = c->mp.st.ms[i]; if (counters) counters[i] = c->mp.st.counters[i]; }

@@ -125,3 +125,20 @@ def check_db_with_N_runs_lowercase_and_iupac(binary, tmp_path):
     got = run_cli(binary, d, out="out_emu")
     compare_dirs(os.path.join(d, "out_ref"), got)
     assert sum(1 for _ in open(os.path.join(d, "out_ref", "ref"))) > 100
+
+
+def check_chunked_equals_direct(binary, workdir, chunk_bases=150_000):
+    """`mapDirectly` with the reference cut into index chunks (the --maxmemory loop: chunk files <prefix>.N, then unifyFiles)
+    writes the same files as the single-index run whenever no hash is over-frequent."""
+    direct = run_cli(binary, workdir, out="out_direct")
+    out = "out_chunked"
+    os.makedirs(os.path.join(workdir, out), exist_ok=True)
+    env = dict(os.environ, MM_HOST_CHUNK_BASES=str(chunk_bases))
+    p = subprocess.run([binary, "mapDirectly", "--all", "-r", "db/DB.fa", "-q", "reads.fq", "-o", f"{out}/ref"], cwd=workdir, check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, text=True)
+    n_chunks = p.stdout.count("Index chunk ")
+    assert n_chunks >= 3, p.stdout[-500:]
+    assert not any(fn.startswith("ref.") and fn[4:].isdigit() for fn in os.listdir(os.path.join(workdir, out)))      # chunk files removed
+    subprocess.run([binary, "classify", "--DB", "db", "--mappings", f"{out}/ref"], cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    compare_mapping_files(direct, os.path.join(workdir, out))
+    return n_chunks

@@ -66,3 +66,8 @@ def test_cli_index_then_mapAgainstIndex(small_workload):
 
 def test_cli_db_with_N_runs_lowercase_and_iupac(tmp_path):
     cli_common.check_db_with_N_runs_lowercase_and_iupac(build_emu_host(), tmp_path)
+
+
+def test_cli_chunked_reference_equals_single_index(small_workload):
+    binary = build_emu_host()
+    assert cli_common.check_chunked_equals_direct(binary, small_workload["dir"]) >= 3

@@ -140,6 +140,7 @@ def test_cli_matches_golden_reference_files(small_workload):
     assert cli_common.compare_dirs(os.path.join(GOLDEN, "ref_small"), got) >= 8
     via = cli_common.run_cli_via_index(build.HOST_BIN, small_workload["dir"], out="out_gpu_ix")      # index + mapAgainstIndex
     cli_common.compare_mapping_files(got, via)
+    assert cli_common.check_chunked_equals_direct(build.HOST_BIN, small_workload["dir"]) >= 3          # the --maxmemory chunk loop
 
 
 @pytest.mark.parametrize("name", ["many_contigs", "long_read", "low_complexity"])
