@@ -1358,7 +1358,7 @@ struct Mapper {
   std::vector<int32_t> h_effLen;
   MapStats st;
   int sweepBand = 256, sweepRing = 8, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT, sweepWideFrom = 0x7fffffff;   // wide-band class: measured neutral on config 2, off unless MM_SWEEP_WIDE_FROM is set
-  DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemSeg, segCnt; DevBuf<BandPart> bandParts; std::vector<int64_t> hItemOff, hEvSpan;
+  DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemSeg, segCnt; DevBuf<BandPart> bandParts; std::vector<int64_t> hEvSpan;
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
   Mapper(Runtime& r, Prims& p, Sketcher& s) : rt(r), pr(p), sk(s) {
