@@ -138,10 +138,12 @@ int mm_map_batch(mm_ctx* ctx, const mm_index* idx, const char* reads, const int6
 int mm_map_batch_dev(mm_ctx* ctx, const mm_index* idx, const void* reads_dev, const int64_t* offsets_host,
                      int32_t n_reads, const mm_map_params* params, mm_map_summary* summary);
 
-/* Double-buffered input staging (the pinned, double-buffered H2D of a streaming host).  mm_stage_reads_async copies a
- * batch of reads host->device on the context's copy stream and returns at once (reads_host should be pinned memory for a
- * truly asynchronous copy; offsets are copied); mm_map_batch_staged maps the batch staged in `slot` (0 or 1) -- the copy
- * is awaited on the device, so staging batch i+1 before mapping batch i overlaps the transfer with the kernels. */
+/* Double-buffered input staging (the pinned, double-buffered H2D of a streaming host).  mm_stage_reads_async starts the
+ * upload of a batch of reads on the context's copy stream and returns at once; mm_map_batch_staged maps the batch staged
+ * in `slot` (0 or 1) -- the upload is awaited on the device, so staging batch i+1 before mapping batch i overlaps the
+ * transfer with the kernels.  reads_host in pinned (mapped) memory: no DMA at all, the 2-bit packing kernel reads the
+ * bytes over PCIe itself; pageable memory: a feeder thread copies in pieces.  Either way reads_host must stay valid and
+ * unchanged until mm_map_batch_staged has returned; offsets are copied. */
 int mm_stage_reads_async(mm_ctx* ctx, int slot, const char* reads_host, const int64_t* offsets, int32_t n_reads);
 int mm_map_batch_staged(mm_ctx* ctx, const mm_index* idx, int slot, const mm_map_params* params, mm_map_summary* summary);
 

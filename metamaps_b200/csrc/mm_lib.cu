@@ -36,6 +36,7 @@ struct mm_ctx {
   } scr;
   // double-buffered input staging (mm_stage_reads_async)
   struct Stage { DevBuf<uint8_t> asc; std::vector<int64_t> off; int32_t n = -1;
+                 SeqBatch batch; bool packed = false; const uint8_t* hostAsc = nullptr;     // zero-copy mode: packed straight from pinned host memory
 #ifndef MM_HOST_EMU
                  cudaEvent_t ready = nullptr; std::thread feeder; int feedErr = 0;
                  void join() { if (feeder.joinable()) feeder.join(); }
@@ -352,20 +353,27 @@ void mm_index_destroy(mm_index* idx) {
 }
 
 // ------------------------------------------------------------------------------------------------ K3-K5
-static int map_impl(mm_ctx* c, const mm_index* idx, const char* reads, const void* dev, const int64_t* offsets, int32_t n,
-                    const mm_map_params* p, mm_map_summary* out) {
-  MM_TRY
-  if (!c || !idx || !offsets || !p || n < 0) throw Error(MM_EINVAL, "mm_map_batch: bad arguments");
+static void check_map_args(mm_ctx* c, const mm_index* idx, const mm_map_params* p) {
+  if (!c || !idx || !p) throw Error(MM_EINVAL, "mm_map_batch: bad arguments");
   // a finalized index is read-only: any context of the same device may map against it (two host threads with one
   // context each keep two batches in flight and fill each other's synchronisation bubbles)
   if (idx->ctx->rt.device != c->rt.device) throw Error(MM_EINVAL, "index lives on another device");
   if (!idx->ix.finalized) throw Error(MM_EINVAL, "index not finalized");
+}
+static void fill_summary(mm_map_summary* out, const int64_t* s) {
+  if (out) { out->n_reads = s[0]; out->n_too_short = s[1]; out->n_candidates = s[2]; out->n_mappings = s[3]; out->n_reads_mapped = s[4]; out->total_bases_mapped_reads = s[5]; }
+}
+static int map_impl(mm_ctx* c, const mm_index* idx, const char* reads, const void* dev, const int64_t* offsets, int32_t n,
+                    const mm_map_params* p, mm_map_summary* out) {
+  MM_TRY
+  if (!offsets || n < 0) throw Error(MM_EINVAL, "mm_map_batch: bad arguments");
+  check_map_args(c, idx, p);
   begin_call(c);
   c->sk.load(c->mp.batch, reads, dev, offsets, n);
   int64_t s[6];
-  { StageTimer t(c->rt, &c->last_ms); c->mp.run(idx->ix, p->perc_identity, p->min_read_len, s); }
+  { StageTimer t(c->rt, &c->last_ms); c->mp.run(idx->ix, c->mp.batch, p->perc_identity, p->min_read_len, s); }
   end_call(c);
-  if (out) { out->n_reads = s[0]; out->n_too_short = s[1]; out->n_candidates = s[2]; out->n_mappings = s[3]; out->n_reads_mapped = s[4]; out->total_bases_mapped_reads = s[5]; }
+  fill_summary(out, s);
   MM_CATCH
 }
 int mm_map_batch(mm_ctx* c, const mm_index* idx, const char* reads, const int64_t* offsets, int32_t n, const mm_map_params* p, mm_map_summary* out) {
@@ -387,8 +395,29 @@ int mm_stage_reads_async(mm_ctx* c, int slot, const char* reads, const int64_t* 
   st.n = n;
 #ifndef MM_HOST_EMU
   MM_CUDA(cudaSetDevice(c->rt.device));
-  st.asc.ensure((size_t)bytes + 16);
   if (!st.ready) MM_CUDA(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
+  st.join();
+  st.feedErr = 0; st.packed = false;
+  // Pinned (mapped) host memory: no DMA at all -- K0 itself pulls the bytes over PCIe on the copy stream and writes the
+  // 2-bit words, so the upload of the next batch neither queues in front of the small copies of the batch being mapped
+  // nor leaves K0 on that batch's critical path.  MM_STAGE=copy (or pageable memory) selects the DMA path below.
+  cudaPointerAttributes attr; memset(&attr, 0, sizeof attr);
+  const bool mapped = bytes > 0 && cudaPointerGetAttributes(&attr, reads + offsets[0]) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer;
+  cudaGetLastError();
+  const char* mode = getenv("MM_STAGE");
+  if (mapped && !(mode && !strcmp(mode, "copy"))) {
+    const uint8_t* dp = (const uint8_t*)attr.devicePointer - offsets[0];       // PackFn indexes with the caller's offsets
+    std::swap(c->rt.stream, c->rt.copy);                                         // issue on the copy stream
+    try {
+      c->sk.prepare(st.batch, offsets, n);
+      c->sk.pack_async(st.batch, dp, 1);                                         // 148 CTAs keep PCIe busy without crowding the SMs
+    } catch (...) { std::swap(c->rt.stream, c->rt.copy); throw; }
+    std::swap(c->rt.stream, c->rt.copy);
+    st.packed = true; st.hostAsc = dp;
+    MM_CUDA(cudaEventRecord(st.ready, c->rt.copy));
+    return MM_OK;
+  }
+  st.asc.ensure((size_t)bytes + 16);
   // The DMA queue is first-in first-out across streams: if the whole batch were queued at once, the small host->device
   // copies of the batch being mapped meanwhile would wait behind 100s of MB.  A feeder thread therefore hands the copy
   // to the engine 8 MB at a time (one piece in flight), and records the slot's event when the last piece is done.
@@ -424,6 +453,17 @@ int mm_map_batch_staged(mm_ctx* c, const mm_index* idx, int slot, const mm_map_p
   cudaError_t e = cudaStreamWaitEvent(c->rt.stream, st.ready, 0);
   if (e != cudaSuccess) { g_err = std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e); return MM_ECUDA; }
 #endif
+  if (st.packed) {
+    MM_TRY
+    check_map_args(c, idx, p);
+    begin_call(c);
+    c->sk.finish_pack(st.batch, st.hostAsc);                 // on the main stream, after the event
+    int64_t s[6];
+    { StageTimer t(c->rt, &c->last_ms); c->mp.run(idx->ix, st.batch, p->perc_identity, p->min_read_len, s); }
+    end_call(c);
+    fill_summary(out, s);
+    MM_CATCH
+  }
   return map_impl(c, idx, nullptr, st.asc.p, st.off.data(), st.n, p, out);
 }
 struct MinHitsOfFn {

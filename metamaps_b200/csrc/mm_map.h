@@ -1344,7 +1344,7 @@ struct Mapper {
   stats::Tables tabs;
   DevBuf<int32_t> dMinHits, dAccept; int tabUploaded = 0; int tabK = 0; float tabPi = 0;
   // per batch (kept until the next batch for the fetch calls)
-  SeqBatch batch; SketchOut rs;
+  SeqBatch batch; SketchOut rs;          // `batch`: the default input slot (mm_map_batch); run() takes any loaded batch
   int32_t n_reads = 0; int64_t n_q = 0, n_hits = 0, n_cand = 0; int lastK = 16;
   DevBuf<int32_t> readLen, sOf, head, hitCnt, candCnt, cRead, cSeq, cStart, cEnd, spanN, stWords;
   DevBuf<int32_t> oShared, oPos, oValid, oIstar, oVotes, oAccept, readMapped;
@@ -1385,8 +1385,8 @@ struct Mapper {
     }
   }
 
-  // `batch` must already be loaded (Sketcher::load)
-  void run(const Index& ix, float pi, int32_t minReadLen, int64_t* summary /*6*/) {
+  // `batch` must already be loaded (Sketcher::load, or prepare + pack_async + finish_pack)
+  void run(const Index& ix, SeqBatch& batch, float pi, int32_t minReadLen, int64_t* summary /*6*/) {
     memset(&st, 0, sizeof(st));
     const int k = ix.k, w = ix.w;
     lastK = k;

@@ -256,6 +256,18 @@ struct Sketcher {
 
   // ASCII (host or device) -> packed batch.  asc_dev != nullptr: data already on the device.
   void load(SeqBatch& B, const char* seqs_host, const void* asc_dev, const int64_t* offsets, int32_t n) {
+    prepare(B, offsets, n);
+    const uint8_t* asc = (const uint8_t*)asc_dev;
+    if (!asc) {
+      B.asc.ensure((size_t)B.total_bases + 16);
+      h2d(rt, B.asc.p, seqs_host + offsets[0], (size_t)B.total_bases);
+      asc = B.asc.p - offsets[0];
+    }
+    pack_async(B, asc);
+    finish_pack(B, asc);
+  }
+  // host-side layout of the batch + the small offset tables on the device (issued on rt.stream)
+  void prepare(SeqBatch& B, const int64_t* offsets, int32_t n) {
     B.n_seqs = n;
     B.h_wordOff.assign((size_t)n + 1, 0); B.h_len.assign((size_t)n, 0);
     int64_t words = 0;
@@ -265,27 +277,30 @@ struct Sketcher {
       B.h_len[i] = (int32_t)L; B.h_wordOff[i] = words; words += (L + 15) / 16;
     }
     B.h_wordOff[n] = words; B.total_words = words; B.total_bases = offsets[n] - offsets[0];
-    const uint8_t* asc = (const uint8_t*)asc_dev;
-    if (!asc) {
-      B.asc.ensure((size_t)B.total_bases + 16);
-      h2d(rt, B.asc.p, seqs_host + offsets[0], (size_t)B.total_bases);
-      asc = B.asc.p - offsets[0];
-    }
     B.ascOff.ensure((size_t)n + 1); h2d(rt, B.ascOff.p, offsets, sizeof(int64_t) * ((size_t)n + 1));
     B.wordOff.ensure((size_t)n + 1); h2d(rt, B.wordOff.p, B.h_wordOff.data(), sizeof(int64_t) * ((size_t)n + 1));
     B.len.ensure((size_t)n + 1); h2d(rt, B.len.p, B.h_len.data(), sizeof(int32_t) * (size_t)n);
     B.packed.ensure((size_t)words + 4);
     B.excCount.ensure(1);
-    int64_t cap = (int64_t)B.excPos.cap; if (cap < 4096) cap = 4096;
-    for (int pass = 0; pass < 2; pass++) {
-      B.excPos.ensure((size_t)cap); B.excByte.ensure((size_t)cap);
-      dev_memset(rt, B.excCount.p, 0, sizeof(unsigned long long));
-      PackFn f{asc, B.ascOff.p, B.wordOff.p, B.len.p, n, B.packed.p, B.excCount.p, B.excPos.p, B.excByte.p, cap};
-      foreach(rt, words, f);
-      unsigned long long c = 0; d2h(rt, &c, B.excCount.p, sizeof(c));
+    size_t cap = B.excPos.cap; if (cap < 4096) cap = 4096;
+    B.excPos.ensure(cap); B.excByte.ensure(cap);
+  }
+  // K0 on rt.stream; `asc` (indexed with the caller's offsets) may be device memory or mapped pinned host memory, in which
+  // case the kernel pulls the bytes over PCIe itself.  No host synchronisation.
+  void pack_async(SeqBatch& B, const uint8_t* asc, int ctas_per_sm = 8) {
+    dev_memset(rt, B.excCount.p, 0, sizeof(unsigned long long));
+    PackFn f{asc, B.ascOff.p, B.wordOff.p, B.len.p, B.n_seqs, B.packed.p, B.excCount.p, B.excPos.p, B.excByte.p, (int64_t)B.excPos.cap};
+    foreach(rt, B.total_words, f, 256, ctas_per_sm);
+  }
+  // the non-ACGT side list: count it (host sync on rt.stream), re-pack with a larger list if it overflowed, sort by position
+  void finish_pack(SeqBatch& B, const uint8_t* asc) {
+    unsigned long long c = 0; d2h(rt, &c, B.excCount.p, sizeof(c));
+    B.n_exc = (int64_t)c;
+    if (B.n_exc > (int64_t)B.excPos.cap) {      // list overflowed: rerun with room for all of them
+      B.excPos.ensure((size_t)B.n_exc + 64); B.excByte.ensure((size_t)B.n_exc + 64);
+      pack_async(B, asc);
+      d2h(rt, &c, B.excCount.p, sizeof(c));
       B.n_exc = (int64_t)c;
-      if (B.n_exc <= cap) break;
-      cap = B.n_exc + 64;     // list overflowed: rerun with room for all of them
     }
     if (B.n_exc > 1) {        // atomics fill the list in arbitrary order: sort by position
       B.excPos2.ensure((size_t)B.n_exc); B.excByte2.ensure((size_t)B.n_exc);

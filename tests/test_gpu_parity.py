@@ -259,3 +259,27 @@ def test_cli_db_with_N_runs_lowercase_and_iupac(tmp_path):
 
 def test_api_errors(gpu_ctx, tmp_path):
     common.check_api_errors(gpu_ctx, tmp_path)
+
+
+def test_staged_reads_pinned_zero_copy(gpu_ctx, small_workload, monkeypatch):
+    """Pinned host memory: mm_stage_reads_async packs straight from host memory over PCIe (no DMA); same results as the direct
+    call, including reads with non-ACGT bytes (the exception side list is settled at map time); MM_STAGE=copy too."""
+    import torch
+    contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"][:120]]
+    reads[3] = reads[3][:500] + b"N" * 40 + reads[3][540:]; reads[7] = reads[7].lower(); reads[11] = reads[11][:100] + b"RYK" + reads[11][103:]
+    ix = common.build_index(gpu_ctx, contigs, 16, 13)
+    direct = capi.map_reads(gpu_ctx, ix, reads, 80.0, 1000)
+    off = np.zeros(len(reads) + 1, np.int64); off[1:] = np.cumsum([len(x) for x in reads])
+    pinned = torch.empty(int(off[-1]) + 64, dtype=torch.uint8, pin_memory=True)
+    pinned[:int(off[-1])] = torch.frombuffer(bytearray(b"".join(reads)), dtype=torch.uint8)
+    for mode in (None, "copy"):
+        if mode:
+            monkeypatch.setenv("MM_STAGE", mode)
+        for slot in (0, 1):
+            gpu_ctx.stage_reads(slot, pinned.data_ptr(), off)
+        for slot in (0, 1):
+            got = capi.map_reads(gpu_ctx, ix, None, 80.0, 1000, offsets=off, staged_slot=slot)
+            for key in ("s", "cand_off", "seq", "pos", "shared", "votes", "accepted", "valid"):
+                assert np.array_equal(got[key], direct[key]), (mode, slot, key)
+            assert got["stats"]["exceptions"] == direct["stats"]["exceptions"] > 0
