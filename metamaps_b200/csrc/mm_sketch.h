@@ -91,7 +91,8 @@ struct SketchArgs {
   uint32_t* gdq; int gdqCap;   // global deque storage, 2*gdqCap words per item
 };
 
-template <bool GLOBALDQ>
+// K16: compile-time k = 16 (the reference's default and maximum): constant shifts and masks, one full Murmur3 block
+template <bool GLOBALDQ, bool K16 = false>
 struct SketchChunkFn {
   SketchArgs a;
   MM_HD void operator()(int64_t item) const {
@@ -104,10 +105,10 @@ struct SketchChunkFn {
 
     int64_t sq = upper_bound_idx(a.chunkOff, (int64_t)a.n_seqs + 1, chunk) - 1;
     int32_t L = ldg(a.len + sq);
-    int32_t npos = L - a.k + 1;
+    int32_t npos = L - (K16 ? 16 : a.k) + 1;
     int32_t c0 = (int32_t)(chunk - ldg(a.chunkOff + sq)) * a.CH;
     int32_t c1 = c0 + a.CH; if (c1 > npos) c1 = npos;
-    const int k = a.k, w = a.w;
+    const int k = K16 ? 16 : a.k, w = a.w;
     int32_t start = c0 - 2 * (w - 1); if (start < 0) start = 0;
     int32_t shadow = c0 - (w - 1);            // steps >= shadow have an exact deque front
     const uint32_t* pw = a.packed + ldg(a.wordOff + sq);
@@ -337,7 +338,11 @@ struct Sketcher {
                  k, w, CH, slabHash.p, slabWs.p, chunkCount.p, ovfCount.p, ovfList.p, ovfCap, nullptr, nullptr, 0};
     static int gridCap = 0;
     if (!gridCap) { const char* e = getenv("MM_SKETCH_CTAS"); gridCap = e ? atoi(e) : (1 << 20); if (gridCap < 1) gridCap = 16; }   // one chunk per thread: the hardware block scheduler balances the tail
-    { StageTimer t(rt, chunkMs); foreach(rt, chunks, SketchChunkFn<false>{a}, 128, gridCap); }
+    {
+      StageTimer t(rt, chunkMs);
+      if (k == 16) foreach(rt, chunks, SketchChunkFn<false, true>{a}, 128, gridCap);
+      else foreach(rt, chunks, SketchChunkFn<false>{a}, 128, gridCap);
+    }
     unsigned long long novf = 0; d2h(rt, &novf, ovfCount.p, sizeof(novf));
     if (novf) {   // deque longer than 32 entries: replay those chunks with a w-entry deque in global memory
       if ((int64_t)novf > ovfCap) throw Error(-34, "too many deque overflows in one batch");
