@@ -243,6 +243,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = capi.Context(local)                       # raises if the CUDA library / device is missing: no fallback
+    capi.use_pinned_results(True)                   # like a streaming host: result arrays live in reused pinned buffers
     if world > 1:
         uid = [ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

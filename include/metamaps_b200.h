@@ -171,6 +171,9 @@ int mm_map_fetch_mappings(mm_ctx* ctx, int32_t* read_idx, int32_t* seq_id, int32
                           int64_t* n_mappings);
 
 /* ---- host helpers of the classify stage (C++/OpenMP, no device work) -------------------------------- */
+/* Runs of equal values in a non-decreasing array (the mappings' read indices): group_value[g], group_off[g..g+1]; arrays of
+ * capacity n and n+1.  These are the reads that have lines in the mappings file, and their line ranges. */
+int mm_group_sorted(const int32_t* values, int64_t n, int32_t* group_value, int64_t* group_off, int64_t* n_groups);
 /* nucIdentity and its 6-significant-digit round trip for n (shared, s) pairs. */
 int mm_stat_identity_batch(const int32_t* shared, const int32_t* sketch, int64_t n, int k, float* identity,
                            double* identity_parsed);

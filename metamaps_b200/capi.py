@@ -61,6 +61,7 @@ SYMBOLS = {
     "mm_map_fetch_candidates": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
     "mm_map_fetch_sketch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "mm_map_fetch_mappings": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int64, C.POINTER(C.c_int64)]),
+    "mm_group_sorted": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "mm_stat_identity_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "mm_nloc_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mm_stat_min_hits_relaxed": (C.c_int, [C.c_int, C.c_int, C.c_float]),
@@ -164,7 +165,7 @@ class Context:
     # K6
     def mapq(self, identity, shared, sketch, read_len, read_off, k: int):
         identity = np.ascontiguousarray(identity, np.float64)
-        out = np.zeros(len(identity)); status = np.zeros(len(read_off) - 1, np.int32)
+        out = _out("mapq", len(identity), np.float64); status = _out("mapq_status", len(read_off) - 1, np.int32)
         self._check(self.lib.mm_mapq_batch(self.h, identity, np.ascontiguousarray(shared, np.int32),
                                            np.ascontiguousarray(sketch, np.int32), np.ascontiguousarray(read_len, np.int32),
                                            np.ascontiguousarray(read_off, np.int64), len(read_off) - 1, k, out, status))
@@ -175,7 +176,7 @@ class Context:
         taxon = np.ascontiguousarray(taxon, np.int32); mapq = np.ascontiguousarray(mapq, np.float64)
         nloc = np.ascontiguousarray(nloc, np.float64); read_off = np.ascontiguousarray(read_off, np.int64)
         nr = len(read_off) - 1
-        f = np.zeros(T); post = np.zeros(len(taxon)); best = np.zeros(max(nr, 1), np.int64); ll = np.zeros(4096)
+        f = _out("em_f", T, np.float64); post = _out("em_post", len(taxon), np.float64); best = _out("em_best", max(nr, 1), np.int64); ll = np.zeros(4096)
         it = C.c_int32()
         self._check(self.lib.mm_em_run(self.h, taxon, mapq, nloc, read_off, nr, T, max_iter, f, post, best, ll, len(ll), C.byref(it)))
         return {"f": f, "posterior": post, "best": best[:nr], "ll": ll[:min(it.value, len(ll))].copy(), "iters": it.value}
@@ -310,18 +311,62 @@ def fetch_map_results(ctx: Context, out: dict) -> dict:
     return out
 
 
+class _PinnedPool:
+    """Grow-only pinned host buffers for result arrays, one per (thread, name): a streaming host reuses its result buffers
+    from batch to batch, and device<->host copies to pinned memory run at full PCIe speed instead of being staged."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.bufs = {}
+
+    def get(self, name: str, n: int, dtype):
+        import threading
+        key = (threading.get_ident(), name)
+        need = max(int(n) * np.dtype(dtype).itemsize, 8)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < need:
+            buf = self.torch.empty(max(need + need // 4, 1 << 16), dtype=self.torch.uint8, pin_memory=True)
+            self.bufs[key] = buf
+        return buf.numpy()[:int(n) * np.dtype(dtype).itemsize].view(dtype)
+
+
+_POOL = None
+
+
+def use_pinned_results(flag: bool = True):
+    """Result arrays of fetch_mappings / mapq / nloc_batch / em come from reused pinned buffers (valid until the same
+    thread's next call of the same function) instead of fresh numpy arrays."""
+    global _POOL
+    _POOL = _PinnedPool() if flag else None
+
+
+def _out(name: str, n: int, dtype):
+    return _POOL.get(name, n, dtype) if _POOL is not None else np.zeros(int(n), dtype)
+
+
 def fetch_mappings(ctx: Context, n_mappings: int) -> dict:
     """The accepted mappings of the last map call, compacted on the device (mm_map_fetch_mappings)."""
     n = int(n_mappings)
-    i32 = lambda: np.zeros(n, np.int32)
-    out = {"read": i32(), "seq": i32(), "pos": i32(), "shared": i32(), "sketch": i32(), "strand": i32(),
-           "identity": np.zeros(n, np.float32), "identity_parsed": np.zeros(n, np.float64)}
+    out = {k_: _out("m_" + k_, n, np.int32) for k_ in ("read", "seq", "pos", "shared", "sketch", "strand")}
+    out["identity"] = _out("m_identity", n, np.float32); out["identity_parsed"] = _out("m_identity_parsed", n, np.float64)
     got = C.c_int64()
     ctx._check(ctx.lib.mm_map_fetch_mappings(ctx.h, *[_ptr(out[k_]) for k_ in ("read", "seq", "pos", "shared", "sketch", "strand", "identity",
                                                                                 "identity_parsed")], n, C.byref(got)))
     assert got.value == n, (got.value, n)
     out["d2h_bytes"] = int(6 * 4 * n)
     return out
+
+
+def group_sorted(lib, values):
+    """(distinct values, offsets) of the runs of a non-decreasing int32 array (mm_group_sorted)."""
+    values = np.ascontiguousarray(values, np.int32)
+    gv = _out("grp_value", len(values), np.int32); go = _out("grp_off", len(values) + 1, np.int64)
+    ng = C.c_int64()
+    rc = lib.mm_group_sorted(_ptr(values), len(values), _ptr(gv), _ptr(go), C.byref(ng))
+    if rc != 0:
+        raise MMError(rc, (lib.mm_last_error() or b"").decode())
+    return gv[:ng.value], go[:ng.value + 1]
 
 
 def identity_batch(lib, shared, sketch, k: int):
@@ -337,7 +382,7 @@ def nloc_batch(lib, seq, read_off, read_len, contig_len, contig_taxon, n_taxa: i
     seq = np.ascontiguousarray(seq, np.int32); read_off = np.ascontiguousarray(read_off, np.int64)
     read_len = np.ascontiguousarray(read_len, np.int32); contig_len = np.ascontiguousarray(contig_len, np.int64)
     contig_taxon = np.ascontiguousarray(contig_taxon, np.int32)
-    tax = np.zeros(len(seq), np.int32); nloc = np.zeros(len(seq), np.float64)
+    tax = _out("nloc_tax", len(seq), np.int32); nloc = _out("nloc", len(seq), np.float64)
     rc = lib.mm_nloc_batch(_ptr(seq), _ptr(read_off), _ptr(read_len), len(read_off) - 1, _ptr(contig_len), _ptr(contig_taxon), len(contig_len),
                            int(n_taxa), _ptr(tax), _ptr(nloc))
     if rc != 0:

@@ -539,6 +539,20 @@ static inline double round6(float x32) {
   if (x >= 10.0 && x < 99.99995) return rint(x * 1e4) / 1e4;       // x*1e4 < 2^24 * 2^14: exact in double
   char buf[64]; snprintf(buf, sizeof buf, "%.6g", x); return strtod(buf, nullptr);
 }
+int mm_group_sorted(const int32_t* v, int64_t n, int32_t* gv, int64_t* go, int64_t* ng) {
+  MM_TRY
+  if (n < 0 || (n > 0 && (!v || !gv || !go)) || !ng) throw Error(MM_EINVAL, "mm_group_sorted: bad arguments");
+  int64_t g = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (i == 0 || v[i] != v[i - 1]) {
+      if (i > 0 && v[i] < v[i - 1]) throw Error(MM_EINVAL, "mm_group_sorted: values are not sorted");
+      gv[g] = v[i]; go[g] = i; g++;
+    }
+  }
+  if (go) go[g] = n;
+  *ng = g;
+  MM_CATCH
+}
 int mm_stat_identity_batch(const int32_t* shared, const int32_t* sketch, int64_t n, int k, float* identity, double* parsed) {
   MM_TRY
   if (n < 0 || (n > 0 && (!shared || !sketch))) throw Error(MM_EINVAL, "mm_stat_identity_batch: bad arguments");

@@ -1624,14 +1624,24 @@ struct Mapper {
                                            beg0.p, fe.p, le.p, spanN.p, n_cand});
         pr.exclusive_sum<int32_t, int64_t>(spanN.p, evOff.p, n_cand + 1);
       }
-      std::vector<int64_t>& hEv = hEvSpan; hEv.resize((size_t)n_cand + 1);
-      d2h(rt, hEv.data(), evOff.p, sizeof(int64_t) * hEv.size());
-      totalEv = hEv[(size_t)n_cand];
+      // the usual case is ONE pass over all candidates: only the total and the largest span come to the host then; the full
+      // offset array is fetched when the event budget forces several passes
+      std::vector<int64_t>& hEv = hEvSpan;
+      red.ensure(2);
+      pr.reduce_max<int32_t>(spanN.p, red.p, n_cand);
+      d2d(rt, scal.p, evOff.p + n_cand, sizeof(int64_t));
+      d2d(rt, scal.p + 1, red.p, sizeof(int32_t));
+      unsigned long long hs2[2] = {0, 0}; d2h(rt, hs2, scal.p, sizeof(hs2));
+      totalEv = (int64_t)hs2[0];
+      const int32_t maxSpan = (int32_t)(hs2[1] & 0xffffffffu);
+      if (totalEv <= evBudget) { hEv.assign((size_t)n_cand + 1, 0); hEv[(size_t)n_cand] = totalEv; if (maxSpan >= 65535) cntBytes = 4; }
+      else { hEv.resize((size_t)n_cand + 1); d2h(rt, hEv.data(), evOff.p, sizeof(int64_t) * hEv.size()); }
       // a gap counter never exceeds the number of minimizers in the span: 16 bits unless some span is huge
-      for (int64_t c = 0; c < n_cand; c++) if (hEv[(size_t)c + 1] - hEv[(size_t)c] >= 65535) { cntBytes = 4; break; }
+      if (totalEv > evBudget) for (int64_t c = 0; c < n_cand; c++) if (hEv[(size_t)c + 1] - hEv[(size_t)c] >= 65535) { cntBytes = 4; break; }
       int64_t c0 = 0;
       while (c0 < n_cand) {          // passes bounded by the event budget
         int64_t c1 = c0 + 1;
+        if (totalEv <= evBudget) c1 = n_cand;
         while (c1 < n_cand && hEv[(size_t)c1 + 1] - hEv[(size_t)c0] <= evBudget) c1++;
         int64_t nEv = hEv[(size_t)c1] - hEv[(size_t)c0], nc = c1 - c0;
         ev.ensure((size_t)nEv + 64);      // the sweeps prefetch a few events past the end of a span

@@ -52,9 +52,7 @@ def classify_mappings(ctx: capi.Context, m: dict, n_reads: int, read_len: np.nda
     t2 = time.perf_counter()
     m_read = m["read"]
     # reads with >= 1 mapping, in read order (the mappings file has no lines for the others)
-    counts = np.bincount(m_read, minlength=n_reads)
-    mapped = np.nonzero(counts)[0]
-    read_off = np.zeros(len(mapped) + 1, np.int64); read_off[1:] = np.cumsum(counts[mapped])
+    mapped, read_off = capi.group_sorted(ctx.lib, m_read)
     out = {"read": m_read, "seq": m["seq"], "pos": m["pos"], "shared": m["shared"], "sketch": m["sketch"],
            "strand": m["strand"], "identity": m["identity"], "mapped_reads": mapped, "read_off": read_off}
     if len(m_read) == 0 and ctx.n_ranks_hint <= 1:
@@ -62,7 +60,8 @@ def classify_mappings(ctx: capi.Context, m: dict, n_reads: int, read_len: np.nda
         return out
     t3 = time.perf_counter()
     rl_mapped = np.ascontiguousarray(read_len[mapped], np.int32)
-    mapq, status = ctx.mapq(m["identity_parsed"] / 100.0, m["shared"], m["sketch"], rl_mapped, read_off, k)
+    ident = np.divide(m["identity_parsed"], 100.0, out=capi._out("ident_frac", len(m_read), np.float64))    # column 10 / 100 (mapWrap.h:229)
+    mapq, status = ctx.mapq(ident, m["shared"], m["sketch"], rl_mapped, read_off, k)
     t4 = time.perf_counter()
     launches = ctx.last_timing()[1]; gpu_ms = ctx.last_timing()[0]
     out["mapq"] = mapq; out["mapq_status"] = status

@@ -283,3 +283,27 @@ def test_staged_reads_pinned_zero_copy(gpu_ctx, small_workload, monkeypatch):
             for key in ("s", "cand_off", "seq", "pos", "shared", "votes", "accepted", "valid"):
                 assert np.array_equal(got[key], direct[key]), (mode, slot, key)
             assert got["stats"]["exceptions"] == direct["stats"]["exceptions"] > 0
+
+
+def test_pinned_result_buffers(gpu_ctx, small_workload):
+    """capi.use_pinned_results: same pipeline results from the reused pinned buffers as from fresh arrays."""
+    from metamaps_b200 import pipeline
+    db = small_workload["db"]
+    contigs = [synth.codes_to_ascii(c) for c in db.contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small_workload["reads"]]
+    taxa = sorted(set(db.contig_taxon)); tidx = {t: i for i, t in enumerate(taxa)}
+    contig_taxon = np.array([tidx[t] for t in db.contig_taxon], np.int32)
+    contig_len = np.array([len(c) for c in db.contig_codes], np.int64)
+    ix = common.build_index(gpu_ctx, contigs, 16, 13)
+    a = pipeline.map_and_classify(gpu_ctx, ix, reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=len(taxa))
+    a = {k_: (np.array(v) if isinstance(v, np.ndarray) else v) for k_, v in a.items()}
+    fa, posta = a["em"]["f"].copy(), a["em"]["posterior"].copy()
+    capi.use_pinned_results(True)
+    try:
+        for _ in range(2):          # second pass reuses the buffers
+            b = pipeline.map_and_classify(gpu_ctx, ix, reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=len(taxa))
+            for key in common.MAPPING_KEYS:
+                assert np.array_equal(a[key], b[key]), key
+            assert np.array_equal(fa, b["em"]["f"]) and np.array_equal(posta, b["em"]["posterior"])
+    finally:
+        capi.use_pinned_results(False)
