@@ -235,6 +235,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:       # the host helpers (identities, nLoc) are OpenMP loops: share the cores between the ranks of the node
         os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")       # idle OpenMP workers must not spin on cores the other ranks need
     import torch
     import torch.distributed as dist
     from metamaps_b200 import capi, pipeline
