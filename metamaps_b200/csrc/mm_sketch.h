@@ -87,12 +87,14 @@ struct SketchArgs {
   int32_t* chunkCount;
   // overflow handling of the in-register deque (see SketchChunkFn)
   unsigned long long* ovfCount; int64_t* ovfList; int64_t ovfCap;
-  const int64_t* redoList;     // when non-null: item i processes chunk redoList[i] with the global deque
+  const int64_t* redoList;     // REDO instantiations: item i processes chunk redoList[i]
   uint32_t* gdq; int gdqCap;   // global deque storage, 2*gdqCap words per item
+  // chunks the block-minimum kernel (SketchBlockMinFn) hands back to the deque kernel
+  unsigned long long* bailCount; int64_t* bailList; int64_t bailCap;
 };
 
 // K16: compile-time k = 16 (the reference's default and maximum): constant shifts and masks, one full Murmur3 block
-template <bool GLOBALDQ, bool K16 = false>
+template <bool GLOBALDQ, bool K16 = false, bool REDO = GLOBALDQ>
 struct SketchChunkFn {
   SketchArgs a;
   MM_HD void operator()(int64_t item) const {
@@ -101,7 +103,7 @@ struct SketchChunkFn {
     uint32_t *dqh, *dqp; uint32_t dmask;
     if (GLOBALDQ) { dqh = a.gdq + item * 2 * (int64_t)a.gdqCap; dqp = dqh + a.gdqCap; dmask = (uint32_t)a.gdqCap - 1; }
     else { dqh = lh; dqp = lp; dmask = DQL - 1; }
-    int64_t chunk = GLOBALDQ ? ldg(a.redoList + item) : item;
+    int64_t chunk = REDO ? ldg(a.redoList + item) : item;
 
     int64_t sq = upper_bound_idx(a.chunkOff, (int64_t)a.n_seqs + 1, chunk) - 1;
     int32_t L = ldg(a.len + sq);
@@ -174,6 +176,105 @@ struct SketchChunkFn {
     a.chunkCount[chunk] = cnt;
   }
 };
+
+// K1, fast path.  The deque of commonFunc.hpp:139-147 only ever answers one question: which k-mer of the window
+// [i-w+1, i] has the smallest hash, the newest one on ties (`>=` pops equal hashes, :144).  Positions are cut into blocks
+// of w; with S[j] = minimum of block positions j..w-1 of the PREVIOUS block (one backward pass when a block completes) and
+// P = running minimum of the current block, the window ending at block position j is min(S[j+1], P) -- three compares per
+// k-mer, no data-dependent loops, and a halo of one block (w positions) instead of 2(w-1).  The thread's w {hash, pos<<1|strand}
+// pairs live in shared memory (A[j*stride], conflict-free).  A chunk that meets what this formulation does not cover -- a k-mer
+// with hashFwd == hashBwd (skipped without expiring the deque, :130) or a non-ACGT byte -- is handed to SketchChunkFn
+// through the bail list; that is 0.2 % of the chunks of a random sequence (palindromic 16-mers, 4^-8 per position).
+template <bool K16>
+struct SketchBlockMinFn {
+  SketchArgs a;
+  MM_HD void bail(int64_t chunk) const {
+    unsigned long long s = atomic_add_u64(a.bailCount, 1ull);
+    if ((int64_t)s < a.bailCap) a.bailList[s] = chunk;
+    a.chunkCount[chunk] = 0;
+  }
+  MM_HD void operator()(int64_t chunk, uint2* A, int stride) const {
+    int64_t sq = upper_bound_idx(a.chunkOff, (int64_t)a.n_seqs + 1, chunk) - 1;
+    const int k = K16 ? 16 : a.k, w = a.w;
+    int32_t npos = ldg(a.len + sq) - k + 1;
+    int32_t c0 = (int32_t)(chunk - ldg(a.chunkOff + sq)) * a.CH;      // CH >= w (host)
+    int32_t c1 = c0 + a.CH; if (c1 > npos) c1 = npos;
+    const int32_t start = c0 > 0 ? c0 - w : 0;
+    const int64_t wo = ldg(a.wordOff + sq);
+    const uint32_t* pw = a.packed + wo;
+    if (a.n_exc) {
+      uint64_t gbase = (uint64_t)wo * 16;
+      int64_t ec = lower_bound_idx(a.excPos, a.n_exc, gbase + (uint64_t)start);
+      if (ec < a.n_exc && ldg(a.excPos + ec) < gbase + (uint64_t)(c1 + k - 1)) { bail(chunk); return; }
+    }
+    uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;
+    const int insShift = ((k - 1) & 7) * 8; const bool insHi = (k - 1) >= 8;
+    const uint64_t rmask0 = k >= 8 ? ~0ull : ((1ull << (8 * k)) - 1);
+    const uint64_t rmask1 = k >= 16 ? ~0ull : (k <= 8 ? 0ull : ((1ull << (8 * (k - 8))) - 1));
+    const uint2 INF = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    bool halo = c0 > 0;
+    if (!halo) for (int j = 1; j < w; j++) A[j * stride] = INF;        // no previous block
+    uint2 P = INF;
+    uint32_t carry = 0xFFFFFFFFu;              // pos<<1|strand of the window minimum at the previous step
+    int jj = 0;
+    int32_t j = start;                         // next base to push
+    uint32_t word = 0;
+    if ((j & 15) != 0) word = ldg(pw + (j >> 4));
+    int32_t cnt = 0;
+    const int64_t slab0 = ldg(a.posOff + sq) + c0;
+    bool bailed = false;
+    for (int32_t i = start - (k - 1); i < c1; i++) {
+      if ((j & 15) == 0) word = ldg(pw + (j >> 4));
+      const uint32_t code = (word >> (2 * (j & 15))) & 3u;
+      const uint32_t u = code_to_ascii(code), cu = code_to_ascii(code ^ 2u);
+      j++;
+      f0 = (f0 >> 8) | (f1 << 56); f1 >>= 8;
+      if (insHi) f1 |= (uint64_t)u << insShift; else f0 |= (uint64_t)u << insShift;
+      r1 = ((r1 << 8) | (r0 >> 56)) & rmask1; r0 = ((r0 << 8) | cu) & rmask0;
+      if (i < start) continue;
+      const uint32_t hf = murmur_kmer(f0, f1, k), hb = murmur_kmer(r0, r1, k);
+      if (hf == hb) { bailed = true; break; }
+      const uint2 key = make_uint2(hf < hb ? hf : hb, ((uint32_t)i << 1) | (hf < hb ? 1u : 0u));
+      if (key.x <= P.x) P = key;
+      if (!halo && i >= w - 1) {
+        uint2 F = P;
+        if (jj + 1 < w) { const uint2 S = A[(jj + 1) * stride]; if (!(P.x <= S.x)) F = S; }
+        if (F.y != carry) {                    // commonFunc.hpp:157 (the wpos==0 quirk is fixed up later)
+          a.slabHash[slab0 + cnt] = F.x;
+          a.slabWs[slab0 + cnt] = ((uint32_t)(i - w + 1) << 1) | (F.y & 1u);
+          cnt++;
+        }
+        carry = F.y;
+      }
+      A[jj * stride] = key;
+      if (++jj == w) {                         // block complete: suffix minima in place, newest wins ties
+        jj = 0;
+        uint2 run = key;
+        for (int q = w - 2; q >= 0; q--) { const uint2 v = A[q * stride]; if (v.x < run.x) run = v; A[q * stride] = run; }
+        if (halo) { carry = run.y; halo = false; }
+        P = INF;
+      }
+    }
+    if (bailed) { bail(chunk); return; }
+    a.chunkCount[chunk] = cnt;
+  }
+};
+#ifndef MM_HOST_EMU
+template <bool K16>
+__global__ void __launch_bounds__(128) sketch_blockmin_kernel(int64_t n, SketchBlockMinFn<K16> f) {
+  extern __shared__ uint2 mm_k1_smem[];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, mm_k1_smem + threadIdx.x, 128);
+}
+// the same with the w pairs in local memory (MM_SKETCH_SCRATCH=local): no shared-memory carve-out to agree on with kernels
+// of other streams that are resident at the same time
+template <bool K16>
+__global__ void __launch_bounds__(128) sketch_blockmin_local_kernel(int64_t n, SketchBlockMinFn<K16> f) {
+  uint2 A[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, A, 1);
+}
+#endif
 
 // gather the per-chunk slab segments into dense arrays
 struct SketchCompactFn {
@@ -248,7 +349,7 @@ struct SketchOut {
 struct Sketcher {
   Runtime& rt; Prims& pr;
   // scratch
-  DevBuf<int64_t> chunkOff, posOff, chunkOutOff, ovfList, newIdx;
+  DevBuf<int64_t> chunkOff, posOff, chunkOutOff, ovfList, bailList, newIdx;
   DevBuf<int32_t> chunkCount, keep;
   DevBuf<uint32_t> slabHash, slabWs, tmpHash, tmpWs, gdq, flag;
   DevBuf<unsigned long long> ovfCount;
@@ -291,6 +392,16 @@ struct Sketcher {
   void pack_async(SeqBatch& B, const uint8_t* asc, int ctas_per_sm = 8) {
     dev_memset(rt, B.excCount.p, 0, sizeof(unsigned long long));
     PackFn f{asc, B.ascOff.p, B.wordOff.p, B.len.p, B.n_seqs, B.packed.p, B.excCount.p, B.excPos.p, B.excByte.p, (int64_t)B.excPos.cap};
+#ifndef MM_HOST_EMU
+    // K0 of the NEXT batch is resident (one CTA per SM, PCIe-bound) while this batch's kernels run; an SM keeps the L1 /
+    // shared-memory split it was given when it was last idle, so K0 asks for the all-shared split its co-residents need
+    static bool carve = false;
+    if (!carve) {
+      carve = true;
+      const char* e = getenv("MM_K0_CARVEOUT"); const int pct = e ? atoi(e) : 100;
+      if (pct >= 0) MM_CUDA(cudaFuncSetAttribute(foreach_kernel<PackFn>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+#endif
     foreach(rt, B.total_words, f, 256, ctas_per_sm);
   }
   // the non-ACGT side list: count it (host sync on rt.stream), re-pack with a larger list if it overflowed, sort by position
@@ -311,10 +422,28 @@ struct Sketcher {
     }
   }
 
+  template <class F>
+  void launch_blockmin(const F& f, int64_t chunks, int w, int gridCap) {
+#ifdef MM_HOST_EMU
+    (void)gridCap;
+    uint2 A[32];
+    for (int64_t c = 0; c < chunks; c++) { (void)w; f(c, A, 1); }
+    rt.launches++;
+#else
+    int64_t need = (chunks + 127) / 128, maxg = (int64_t)rt.sm_count * gridCap;
+    int grid = (int)(need < maxg ? need : maxg);
+    const char* scr = getenv("MM_SKETCH_SCRATCH");
+    if (scr && !strcmp(scr, "local")) sketch_blockmin_local_kernel<<<grid, 128, 0, rt.stream>>>(chunks, f);
+    else sketch_blockmin_kernel<<<grid, 128, (size_t)w * 128 * sizeof(uint2), rt.stream>>>(chunks, f);
+    MM_CUDA(cudaGetLastError());
+    rt.launches++;
+#endif
+  }
+
   // K1 over a packed batch.  Sequences with len < w or len < k get no minimizers (winSketch.hpp:258).
   void run(const SeqBatch& B, int k, int w, SketchOut& out) {
-    static int CH = 0;
-    if (!CH) { const char* e = getenv("MM_SKETCH_CH"); CH = e ? atoi(e) : 128; if (CH < 32 || CH > 4096) CH = 128; }
+    int CH = 128;                            // tunables are read per call so that tests can walk through them
+    { const char* e = getenv("MM_SKETCH_CH"); if (e) CH = atoi(e); if (CH < 32 || CH > 4096) CH = 128; }
     int32_t n = B.n_seqs;
     std::vector<int64_t> hChunk((size_t)n + 1), hPos((size_t)n + 1);
     int64_t chunks = 0, pos = 0;
@@ -332,18 +461,45 @@ struct Sketcher {
     h2d(rt, posOff.p, hPos.data(), sizeof(int64_t) * ((size_t)n + 1));
     slabHash.ensure((size_t)pos); slabWs.ensure((size_t)pos);
     chunkCount.ensure((size_t)chunks + 1); chunkOutOff.ensure((size_t)chunks + 1);
-    ovfCount.ensure(1); dev_memset(rt, ovfCount.p, 0, sizeof(unsigned long long));
+    ovfCount.ensure(2); dev_memset(rt, ovfCount.p, 0, 2 * sizeof(unsigned long long));      // [0] deque overflows, [1] bails
     int64_t ovfCap = 1 << 16; ovfList.ensure((size_t)ovfCap);
+    int fastPath = 1;
+    { const char* e = getenv("MM_SKETCH_BLOCKMIN"); if (e) fastPath = atoi(e); }
+    const bool fast = fastPath && w <= 32 && w <= CH;
+    int64_t bailCap = 0;
+    if (fast) {
+      bailCap = chunks / 16 + 4096;          // more bails than this (low-complexity input): one deque pass over everything
+      const char* e = getenv("MM_SKETCH_BAILCAP"); if (e && atoi(e) > 0) bailCap = atoi(e);
+      bailList.ensure((size_t)bailCap);
+    }
     SketchArgs a{B.packed.p, B.wordOff.p, B.len.p, n, chunkOff.p, posOff.p, B.excPos.p, B.excByte.p, B.n_exc,
-                 k, w, CH, slabHash.p, slabWs.p, chunkCount.p, ovfCount.p, ovfList.p, ovfCap, nullptr, nullptr, 0};
+                 k, w, CH, slabHash.p, slabWs.p, chunkCount.p, ovfCount.p, ovfList.p, ovfCap, nullptr, nullptr, 0,
+                 ovfCount.p + 1, bailList.p, bailCap};
     static int gridCap = 0;
     if (!gridCap) { const char* e = getenv("MM_SKETCH_CTAS"); gridCap = e ? atoi(e) : (1 << 20); if (gridCap < 1) gridCap = 16; }   // one chunk per thread: the hardware block scheduler balances the tail
-    {
-      StageTimer t(rt, chunkMs);
+    auto deque_pass = [&]() {
       if (k == 16) foreach(rt, chunks, SketchChunkFn<false, true>{a}, 128, gridCap);
       else foreach(rt, chunks, SketchChunkFn<false>{a}, 128, gridCap);
+    };
+    {
+      StageTimer t(rt, chunkMs);
+      if (fast) {
+        if (k == 16) launch_blockmin(SketchBlockMinFn<true>{a}, chunks, w, gridCap);
+        else launch_blockmin(SketchBlockMinFn<false>{a}, chunks, w, gridCap);
+      } else deque_pass();
     }
-    unsigned long long novf = 0; d2h(rt, &novf, ovfCount.p, sizeof(novf));
+    unsigned long long cnts[2] = {0, 0}; d2h(rt, cnts, ovfCount.p, sizeof(cnts));
+    if (getenv("MM_SKETCH_DEBUG")) fprintf(stderr, "[k1] fast=%d chunks=%lld bailed=%llu w=%d CH=%d\n", (int)fast, (long long)chunks, cnts[1], w, CH);
+    if (cnts[1]) {   // chunks with a skipped k-mer or a non-ACGT byte: the reference's deque, step by step
+      if ((int64_t)cnts[1] > bailCap) deque_pass();
+      else {
+        SketchArgs a1 = a; a1.redoList = bailList.p;
+        if (k == 16) foreach(rt, (int64_t)cnts[1], SketchChunkFn<false, true, true>{a1}, 128, gridCap);
+        else foreach(rt, (int64_t)cnts[1], SketchChunkFn<false, false, true>{a1}, 128, gridCap);
+      }
+      d2h(rt, cnts, ovfCount.p, sizeof(cnts));
+    }
+    unsigned long long novf = cnts[0];
     if (novf) {   // deque longer than 32 entries: replay those chunks with a w-entry deque in global memory
       if ((int64_t)novf > ovfCap) throw Error(-34, "too many deque overflows in one batch");
       int cap = 64; while (cap < w + 1) cap <<= 1;

@@ -29,6 +29,36 @@ def check_sketch_vs_oracle(ctx, oracle, seqs, k, w):
         assert np.array_equal(st[a:b], os_), f"strand stream differs for sequence {i} (k={k}, w={w})"
 
 
+def blockmin_stress_seqs(seed=3):
+    """Sequences for K1's block-minimum path: random bases with runs the path must hand back to the deque kernel
+    ((AT)n = k-mers with hashFwd == hashBwd, commonFunc.hpp:130; N runs and lower case, :44-51,106) placed on and
+    around chunk boundaries (multiples of 32 .. 256 k-mer positions), homopolymers (equal hashes: newest wins, :144),
+    and lengths around w, k and the chunk size."""
+    rng = np.random.default_rng(seed)
+    def rnd(n): return bytearray(rng.choice(list(b"ACGT"), size=n).astype(np.uint8).tobytes())
+    seqs = []
+    s = rnd(3000)
+    for at, ln in ((96, 40), (250, 17), (511, 2), (640, 64), (1020, 30), (1279, 18), (2040, 200)):
+        s[at:at + ln] = (b"AT" * ln)[:ln]
+    seqs.append(bytes(s))
+    s = rnd(2500)
+    for at, ln in ((30, 1), (127, 3), (256, 1), (300, 50), (1023, 2), (1500, 400)):
+        s[at:at + ln] = b"N" * ln
+    s[700:900] = bytes(s[700:900]).lower()
+    seqs.append(bytes(s))
+    s = rnd(1500); s[200:420] = b"A" * 220; s[600:700] = b"ACGT" * 25; s[900:1100] = b"GC" * 100
+    seqs.append(bytes(s))
+    for n in (15, 16, 17, 31, 32, 33, 47, 48, 127, 128, 129, 143, 144, 145, 159, 160, 271, 272, 273):
+        seqs.append(bytes(rnd(n)))
+    seqs.append(b"AT" * 400)                      # every k-mer skipped
+    seqs.append(bytes(rnd(20)) + b"AT" * 300 + bytes(rnd(500)))
+    seqs.append(bytes(rnd(9000)))
+    return seqs
+
+
+BLOCKMIN_PARAMS = ((16, 16), (16, 13), (16, 2), (16, 32), (16, 31), (12, 17), (7, 5), (16, 33))
+
+
 def build_index(ctx, contigs, k, w, batches=2):
     ix = capi.Index(ctx, k, w)
     step = max(1, (len(contigs) + batches - 1) // batches)

@@ -21,6 +21,16 @@ def test_sketch_edge_cases(gpu_ctx, oracle):
         common.check_sketch_vs_oracle(gpu_ctx, oracle, seqs, k, w)
 
 
+@pytest.mark.parametrize("env", [{}, {"MM_SKETCH_CH": "32"}, {"MM_SKETCH_CH": "48"}, {"MM_SKETCH_BLOCKMIN": "0"}])
+def test_sketch_blockmin(gpu_ctx, oracle, monkeypatch, env):
+    """K1 fast path (block prefix / suffix minima in shared memory) + bail list vs the oracle; see the emulation test."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    seqs = common.blockmin_stress_seqs()
+    for (k, w) in common.BLOCKMIN_PARAMS:
+        common.check_sketch_vs_oracle(gpu_ctx, oracle, seqs, k, w)
+
+
 def test_sketch_large_batch_properties(gpu_ctx, oracle):
     """2000 reads x ~8 kb: spot-check 40 against the oracle; window property on all (a minimizer stays the
     window minimum for at most w steps, so consecutive wpos differ by <= w, plus one step for every

@@ -29,6 +29,18 @@ def test_sketch_long_monotone_window(emu_ctx, oracle):
     common.check_sketch_vs_oracle(emu_ctx, oracle, seqs, 16, 2000)
 
 
+@pytest.mark.parametrize("env", [{}, {"MM_SKETCH_CH": "32"}, {"MM_SKETCH_CH": "48"}, {"MM_SKETCH_CH": "256"},
+                                 {"MM_SKETCH_BLOCKMIN": "0", "MM_SKETCH_CH": "32"}, {"MM_SKETCH_BAILCAP": "8", "MM_SKETCH_CH": "32"}])
+def test_sketch_blockmin(emu_ctx, oracle, monkeypatch, env):
+    """K1's block prefix / suffix minimum kernel and the chunks it hands back to the deque kernel, over chunk sizes that put
+    the engineered runs on, before and after chunk boundaries; and the deque kernel alone over the same inputs."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    seqs = common.blockmin_stress_seqs()
+    for (k, w) in common.BLOCKMIN_PARAMS:
+        common.check_sketch_vs_oracle(emu_ctx, oracle, seqs, k, w)
+
+
 def test_index_golden(emu_ctx, golden, small_workload):
     common.check_index_vs_golden(emu_ctx, golden, small_workload)
 
