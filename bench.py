@@ -222,6 +222,9 @@ def main():
     ap.add_argument("--shard", default="reads", choices=["reads", "contigs"],
                     help="N > 1: 'reads' = index replicated, every rank maps its own reads (no mapping exchange); 'contigs' = the "
                          "index is split into contig ranges, every rank maps ALL reads against its shard, mappings are exchanged")
+    ap.add_argument("--e2e-breakdown", action="store_true",
+                    help="after the timed runs: three more e2e steps with the per-stage CUDA-event times and the wall-clock split of each "
+                         "printed to stderr next to those of a device-resident step (what staging the next batch costs the current one)")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -452,6 +455,24 @@ def main():
     wall2 = float(tt.item())
     e2e_value = total_bases * args.steps / 1e6 / wall2
     sampler.stop_flag = True; sampler.join(timeout=2)
+
+    if args.e2e_breakdown and not by_contigs and n_flight == 1 and rank == 0:
+        sd = {}; step_dev(sd)
+        print("[breakdown] resident:", json.dumps({"stage_ms": {k_: round(v, 2) for k_, v in sd["map"].items() if k_.endswith("_ms")},
+                                                   "wall_ms": {k_: round(v, 2) for k_, v in sd["wall_ms"].items()}}), file=sys.stderr)
+        ctx.stage_reads(0, r_host.data_ptr(), r_off)
+        for i in range(3):
+            se = {}
+            ta = time.perf_counter()
+            ctx.stage_reads((i + 1) & 1, r_host.data_ptr(), r_off)
+            tb_ = time.perf_counter()
+            pipeline.map_and_classify(ctx, ix, staged_slot=i & 1, offsets=r_off, read_len=read_len, contig_len=contig_len, contig_taxon=contig_taxon,
+                                      n_taxa=n_taxa, perc_identity=PI, min_read_len=wl["min_read_len"], stats=se)
+            tc = time.perf_counter()
+            print("[breakdown] e2e step %d:" % i, json.dumps({"stage_call_ms": round((tb_ - ta) * 1e3, 2), "step_ms": round((tc - ta) * 1e3, 2),
+                  "stage_ms": {k_: round(v, 2) for k_, v in se["map"].items() if k_.endswith("_ms")},
+                  "wall_ms": {k_: round(v, 2) for k_, v in se["wall_ms"].items()}}), file=sys.stderr)
+        torch.cuda.synchronize()
 
     if n_flight > 1:        # per-kernel event times of overlapped steps include the other batch's kernels: time one step alone
         stats = {}

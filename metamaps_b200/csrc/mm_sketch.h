@@ -291,6 +291,38 @@ struct SketchCompactFn {
     for (int32_t i = 0; i < n; i++) { outHash[dst + i] = slabHash[src + i]; outWs[dst + i] = slabWs[src + i]; }
   }
 };
+#ifndef MM_HOST_EMU
+// the same gather, one warp per 32 consecutive chunks: their output range is contiguous, so lane l takes output o0 + l,
+// finds its chunk among the 32 with a shuffle search and copies one element -- coalesced writes, 60-byte runs of reads
+__global__ void __launch_bounds__(256) sketch_compact_warp_kernel(SketchCompactFn f, int64_t chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = ((((int64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5) * 32; base < chunks; base += nw * 32) {
+    const int64_t c = base + lane;
+    int32_t n = 0; int64_t src = 0;
+    const int64_t dst = ldg(f.chunkOutOff + (c < chunks ? c : chunks));
+    if (c < chunks) {
+      n = ldg(f.chunkCount + c);
+      if (n) {
+        int64_t sq = upper_bound_idx(f.chunkOff, (int64_t)f.n_seqs + 1, c) - 1;
+        src = ldg(f.posOff + sq) + (c - ldg(f.chunkOff + sq)) * f.CH;
+      }
+    }
+    const int64_t d0 = __shfl_sync(0xffffffffu, dst, 0);
+    const int32_t len = (int32_t)(__shfl_sync(0xffffffffu, dst + n, 31) - d0);
+    const int32_t rel = (int32_t)(dst - d0);
+    for (int32_t o0 = 0; o0 < len; o0 += 32) {
+      const int32_t o = o0 + lane;
+      int j = 0;                                   // last chunk of the group that starts at or before output o
+#pragma unroll
+      for (int step = 16; step; step >>= 1) { const int32_t r = __shfl_sync(0xffffffffu, rel, j + step); if (r <= o) j += step; }
+      const int64_t sj = __shfl_sync(0xffffffffu, src, j);
+      const int32_t rj = __shfl_sync(0xffffffffu, rel, j);
+      if (o < len) { f.outHash[d0 + o] = f.slabHash[sj + (o - rj)]; f.outWs[d0 + o] = f.slabWs[sj + (o - rj)]; }
+    }
+  }
+}
+#endif
 struct SeqOutOffFn {
   const int64_t* chunkOff; const int64_t* chunkOutOff; int64_t* seqOutOff;
   MM_HD void operator()(int64_t sq) const { seqOutOff[sq] = ldg(chunkOutOff + ldg(chunkOff + sq)); }
@@ -442,8 +474,8 @@ struct Sketcher {
 
   // K1 over a packed batch.  Sequences with len < w or len < k get no minimizers (winSketch.hpp:258).
   void run(const SeqBatch& B, int k, int w, SketchOut& out) {
-    int CH = 128;                            // tunables are read per call so that tests can walk through them
-    { const char* e = getenv("MM_SKETCH_CH"); if (e) CH = atoi(e); if (CH < 32 || CH > 4096) CH = 128; }
+    int CH = 256;                            // tunables are read per call so that tests can walk through them
+    { const char* e = getenv("MM_SKETCH_CH"); if (e) CH = atoi(e); if (CH < 32 || CH > 4096) CH = 256; }
     int32_t n = B.n_seqs;
     std::vector<int64_t> hChunk((size_t)n + 1), hPos((size_t)n + 1);
     int64_t chunks = 0, pos = 0;
@@ -511,8 +543,19 @@ struct Sketcher {
     pr.exclusive_sum<int32_t, int64_t>(chunkCount.p, chunkOutOff.p, chunks + 1);
     int64_t total = 0; d2h(rt, &total, chunkOutOff.p + chunks, sizeof(int64_t));
     out.hash.ensure((size_t)total + 1); out.ws.ensure((size_t)total + 1);
-    foreach(rt, chunks, SketchCompactFn{chunkOff.p, posOff.p, n, CH, chunkCount.p, chunkOutOff.p, slabHash.p, slabWs.p,
-                                         out.hash.p, out.ws.p});
+    {
+      SketchCompactFn cf{chunkOff.p, posOff.p, n, CH, chunkCount.p, chunkOutOff.p, slabHash.p, slabWs.p, out.hash.p, out.ws.p};
+#ifndef MM_HOST_EMU
+      const char* e = getenv("MM_SKETCH_COMPACT");
+      if (!(e && !strcmp(e, "thread"))) {
+        int64_t g = (chunks + 255) / 256; if (g > (int64_t)rt.sm_count * 16) g = (int64_t)rt.sm_count * 16;
+        sketch_compact_warp_kernel<<<(int)g, 256, 0, rt.stream>>>(cf, chunks);
+        MM_CUDA(cudaGetLastError());
+        rt.launches++;
+      } else
+#endif
+      foreach(rt, chunks, cf);
+    }
     foreach(rt, (int64_t)n + 1, SeqOutOffFn{chunkOff.p, chunkOutOff.p, out.seqOff.p});
     flag.ensure(1); dev_memset(rt, flag.p, 0, sizeof(uint32_t));
     foreach(rt, n, SketchQuirkFn{out.seqOff.p, out.hash.p, out.ws.p, flag.p});

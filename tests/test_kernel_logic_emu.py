@@ -29,7 +29,7 @@ def test_sketch_long_monotone_window(emu_ctx, oracle):
     common.check_sketch_vs_oracle(emu_ctx, oracle, seqs, 16, 2000)
 
 
-@pytest.mark.parametrize("env", [{}, {"MM_SKETCH_CH": "32"}, {"MM_SKETCH_CH": "48"}, {"MM_SKETCH_CH": "256"},
+@pytest.mark.parametrize("env", [{}, {"MM_SKETCH_CH": "32"}, {"MM_SKETCH_CH": "48"}, {"MM_SKETCH_CH": "128"},
                                  {"MM_SKETCH_BLOCKMIN": "0", "MM_SKETCH_CH": "32"}, {"MM_SKETCH_BAILCAP": "8", "MM_SKETCH_CH": "32"}])
 def test_sketch_blockmin(emu_ctx, oracle, monkeypatch, env):
     """K1's block prefix / suffix minimum kernel and the chunks it hands back to the deque kernel, over chunk sizes that put
