@@ -232,7 +232,7 @@ struct SketchBlockMinFn {
       if (insHi) f1 |= (uint64_t)u << insShift; else f0 |= (uint64_t)u << insShift;
       r1 = ((r1 << 8) | (r0 >> 56)) & rmask1; r0 = ((r0 << 8) | cu) & rmask0;
       if (i < start) continue;
-      const uint32_t hf = murmur_kmer(f0, f1, k), hb = murmur_kmer(r0, r1, k);
+      const uint32_t hf = K16 ? murmur_kmer16(f0, f1) : murmur_kmer(f0, f1, k), hb = K16 ? murmur_kmer16(r0, r1) : murmur_kmer(r0, r1, k);
       if (hf == hb) { bailed = true; break; }
       const uint2 key = make_uint2(hf < hb ? hf : hb, ((uint32_t)i << 1) | (hf < hb ? 1u : 0u));
       if (key.x <= P.x) P = key;
