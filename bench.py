@@ -483,7 +483,7 @@ def main():
     stage_keys = ("sketch_ms", "read_sketch_ms", "l1_probe_ms", "l1_sort_ms", "l1_candidates_ms", "l2_setup_ms", "l2_classify_ms",
                   "l2_sweep_ms", "l2_strand_ms", "accept_ms")
     stage_ms = {k_: ms[k_] for k_ in stage_keys}
-    kernels = {"SketchChunkFn (K1)": (ms["k1_kernel_ms"], ms["bases"] / 4 + 8 * ms["read_minimizers"]),
+    kernels = {"sketch_blockmin_kernel (K1)": (ms["k1_kernel_ms"], ms["bases"] / 4 + 8 * ms["read_minimizers"]),
                "l2_sweep_band_kernel (K5b)": (ms["sweep_kernel_ms"], 2 * 8 * ms["span_elems"] + 32 * ms["sweep_items"])}
     dom = max(kernels, key=lambda k_: kernels[k_][0])
     dom_ms, dom_bytes = kernels[dom]
