@@ -84,6 +84,22 @@ struct DupFn {
   }
 };
 
+// dupRB[i] = {dupBits word i, number of duplicate bits set before word i}: the link record of minimizer j is
+// dupLinks[rank + popc(bits below j)] -- two dependent loads where a binary search over dupIdx took ~17 (it was 22 % of the
+// instructions K5a issued, almost all with a single active lane)
+MM_HD uint32_t popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
+struct DupPopcFn { const uint32_t* bits; int32_t* out; MM_HD void operator()(int64_t i) const { out[i] = (int32_t)popc32(ldg(bits + i)); } };
+struct DupRBFn {
+  const uint32_t* bits; const int64_t* rank; uint2* out;
+  MM_HD void operator()(int64_t i) const { out[i] = make_uint2(ldg(bits + i), (uint32_t)ldg(rank + i)); }
+};
+
 // bit 31 of a slot's count: the hash is over-frequent in the WHOLE (sharded) reference, see Index::keepUnique; such a
 // count compares above every threshold, so the L1 probe skips the hash without knowing about the flag
 static const uint32_t SLOT_GLOBAL_FREQ = 0x80000000u;
@@ -144,7 +160,7 @@ struct Index {
   bool keepUnique = false; int32_t firstContig = 0; bool globalSynced = false; int32_t globalThreshold = 0x7fffffff;
   DevBuf<uint32_t> uHash; DevBuf<int32_t> uCnt;
   // dups
-  DevBuf<uint32_t> dupBits, dupIdx; DevBuf<uint64_t> dupLinks; int64_t n_dup = 0;
+  DevBuf<uint32_t> dupBits, dupIdx; DevBuf<uint64_t> dupLinks; DevBuf<uint2> dupRB; int64_t n_dup = 0;
   int64_t total_bases = 0;
 
   Index(Runtime& r, Prims& p, Sketcher& s, int k_, int w_) : rt(r), pr(p), sk(s), k(k_), w(w_) {}
@@ -237,11 +253,22 @@ struct Index {
       pr.sort_pairs<uint32_t, uint64_t>(tIdx.p, dupIdx.p, tLinks.p, dupLinks.p, n_dup);
       rt.sync();
     }
+    build_dup_rank();
+    rt.sync();
+  }
+  // dupRB from dupBits (finalize, and after mm_index_load: the file format keeps dupBits / dupIdx / dupLinks only)
+  void build_dup_rank() {
+    const int64_t nw = n / 32 + 2;
+    dupRB.ensure((size_t)nw);
+    DevBuf<int32_t> pc; DevBuf<int64_t> rk; pc.ensure((size_t)nw + 1); rk.ensure((size_t)nw + 1);
+    foreach(rt, nw, DupPopcFn{dupBits.p, pc.p});
+    pr.exclusive_sum<int32_t, int64_t>(pc.p, rk.p, nw);
+    foreach(rt, nw, DupRBFn{dupBits.p, rk.p, dupRB.p});
     rt.sync();
   }
 
   int64_t device_bytes() const {
-    return (int64_t)(miHash.bytes() + miWs.bytes() + table.bytes() + posKey.bytes() + posSeq16.bytes() + dupBits.bytes() + dupIdx.bytes() +
+    return (int64_t)(miHash.bytes() + miWs.bytes() + table.bytes() + posKey.bytes() + posSeq16.bytes() + dupBits.bytes() + dupRB.bytes() + dupIdx.bytes() +
                      dupLinks.bytes() + contigStart.bytes() + contigLen.bytes() + uHash.bytes() + uCnt.bytes());
   }
 };

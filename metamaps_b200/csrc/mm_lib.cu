@@ -319,6 +319,7 @@ int mm_index_load(mm_ctx* c, const char* path, mm_index** out) {
     ix.dupBits.ensure((size_t)(ix.n / 32 + 2)); get_dev(c->rt, f, ix.dupBits.p, 4 * (size_t)(ix.n / 32 + 2), bounce);
     ix.dupIdx.ensure((size_t)ix.n_dup + 1); ix.dupLinks.ensure((size_t)ix.n_dup + 1);
     get_dev(c->rt, f, ix.dupIdx.p, 4 * (size_t)ix.n_dup, bounce); get_dev(c->rt, f, ix.dupLinks.p, 8 * (size_t)ix.n_dup, bounce);
+    ix.build_dup_rank();
     ix.finalized = true;
   } catch (...) { fclose(f); delete idx; throw; }
   fclose(f);

@@ -586,16 +586,18 @@ struct StWordsFn {
   }
 };
 
-MM_HD uint64_t dup_links(const uint32_t* dupIdx, const uint64_t* dupLinks, int64_t n_dup, int64_t j) {
-  int64_t p = lower_bound_idx(dupIdx, n_dup, (uint32_t)j);
-  return (p < n_dup && ldg(dupIdx + p) == (uint32_t)j) ? ldg(dupLinks + p) : 0ull;
+MM_HD uint64_t dup_links(const uint2* dupRB, const uint64_t* dupLinks, int64_t n_dup, int64_t j) {
+  (void)n_dup;
+  const uint2 rb = ldg(dupRB + (j >> 5));                  // {dupBits word, duplicates before it}
+  if (!((rb.x >> (j & 31)) & 1u)) return 0ull;
+  return ldg(dupLinks + rb.y + popc32(rb.x & ((1u << (j & 31)) - 1u)));
 }
 // Which of a duplicated minimizer's two events are no-ops.  Element j enters the window at the step where
 // sw_pos = wpos[j]-cmw+1 (or at once if j < fe) and leaves at the step where sw_pos = wpos[j+1]; inside one step the
 // reference deletes before it inserts (computeMap.hpp:500-505).
-MM_HD uint32_t dup_event_flags(const uint32_t* miWs, const uint32_t* dupIdx, const uint64_t* dupLinks, int64_t n_dup, int64_t j, int64_t b0, int64_t fe,
+MM_HD uint32_t dup_event_flags(const uint32_t* miWs, const uint2* dupRB, const uint64_t* dupLinks, int64_t n_dup, int64_t j, int64_t b0, int64_t fe,
                                int64_t last, int32_t cmw) {
-  const uint64_t l = dup_links(dupIdx, dupLinks, n_dup, j);
+  const uint64_t l = dup_links(dupRB, dupLinks, n_dup, j);
   const uint32_t pd = (uint32_t)(l >> 32), nd = (uint32_t)l;
   uint32_t f = 0;
   const int64_t wj = (int64_t)(ldg(miWs + j) >> 1);
@@ -616,7 +618,7 @@ struct L2ClassifyFn {
   const int64_t* evOff; int64_t cand0, nCand; int64_t evBase;   // candidates [cand0, cand0+nCand), events relative to evBase
   const int64_t* beg0; const int32_t* cRead; const uint32_t* qHash; const int64_t* qOff; const int32_t* sOf;
   uint2* ev;
-  const int64_t* fe; const int64_t* le; const int32_t* readLen; const uint32_t* dupIdx; const uint64_t* dupLinks; int64_t n_dup; int k, w;
+  const int64_t* fe; const int64_t* le; const int32_t* readLen; const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; int k, w;
   MM_HD void operator()(int64_t t) const {
     int64_t c = cand0 + upper_bound_idx(evOff + cand0, nCand + 1, t + evBase) - 1;
     int64_t j = ldg(beg0 + c) + (t + evBase - ldg(evOff + c));
@@ -627,7 +629,7 @@ struct L2ClassifyFn {
     while (lo < hi) { int32_t m = (lo + hi) >> 1; if (ldg(q + m) < h) lo = m + 1; else hi = m; }
     uint32_t code = (lo < s && ldg(q + lo) == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
     if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u)
-      code |= CODE_DUP | dup_event_flags(miWs, dupIdx, dupLinks, n_dup, j, ldg(beg0 + c), ldg(fe + c), ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1));
+      code |= CODE_DUP | dup_event_flags(miWs, dupRB, dupLinks, n_dup, j, ldg(beg0 + c), ldg(fe + c), ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1));
     ev[t] = make_uint2(code, ldg(miWs + j));
   }
 };
@@ -682,7 +684,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
         if (!on[u]) continue;
         const int32_t t = t0 + u * (int32_t)blockDim.x;
         uint32_t code = rank_code(h[u]);
-        if (db[u]) code |= CODE_DUP | dup_event_flags(a.miWs, a.dupIdx, a.dupLinks, a.n_dup, b0 + t, b0, fe, le, cmw);
+        if (db[u]) code |= CODE_DUP | dup_event_flags(a.miWs, a.dupRB, a.dupLinks, a.n_dup, b0 + t, b0, fe, le, cmw);
         a.ev[e0 + t] = make_uint2(code, wsv[u]);
       }
     }
@@ -700,7 +702,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
 struct L2SweepArgs {
   const uint2* ev; const int64_t* evOff; int64_t evBase; int64_t cand0;
   const int64_t* beg0; const int64_t* fe; const int64_t* le; const int32_t* cRead; const int32_t* sOf; const int32_t* readLen;
-  const uint32_t* dupIdx; const uint64_t* dupLinks; int64_t n_dup; int k, w;
+  const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; int k, w;
   int32_t* oShared; int32_t* oPos; int32_t* oValid; int64_t* oOptS; int64_t* oOptE; int32_t* oIstar;
 };
 
@@ -877,7 +879,7 @@ struct BandSweep {
   // element j of the span counts for a window starting at `beg` iff no earlier copy of its hash is inside that window
   MM_HD bool first_copy(uint32_t code, int32_t j, int32_t beg) const {
     if (!(code & CODE_DUP)) return true;
-    const uint64_t l = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0 + j);
+    const uint64_t l = dup_links(a.dupRB, a.dupLinks, a.n_dup, b0 + j);
     const int64_t pd = (int64_t)(l >> 32);
     return !(pd && (int64_t)j - pd >= (int64_t)beg);
   }
@@ -973,7 +975,7 @@ struct BandSweep {
       const uint32_t code = __ldg(&el[j].x);
       bool cntd = true;
       if (code & CODE_DUP) {
-        const uint64_t lk = dup_links(a.dupIdx, a.dupLinks, a.n_dup, b0_l + j);
+        const uint64_t lk = dup_links(a.dupRB, a.dupLinks, a.n_dup, b0_l + j);
         const int64_t pd = (int64_t)(lk >> 32);
         cntd = !(pd && (int64_t)j - pd >= (int64_t)beg_l);
       }
@@ -1301,7 +1303,7 @@ __global__ void __launch_bounds__(512, 1) l2_sweep_band_kernel(L2SweepArgs a, co
 struct L2StrandFn {
   const uint2* ev; const int64_t* evOff; int64_t evBase; int64_t cand0; const int64_t* beg0;
   const int32_t* cRead; const int64_t* qOff; const uint8_t* qStrand;
-  const uint32_t* dupIdx; const uint64_t* dupLinks; int64_t n_dup; const uint32_t* dupBits;
+  const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; const uint32_t* dupBits;
   const int32_t* oValid; const int64_t* oOptS; const int64_t* oOptE; const int32_t* oIstar; int32_t* oVotes;
   // contribution of index position j to the vote of a window [.., b) whose bottom-s holds query ranks <= istar
   MM_HD int32_t vote_of(const uint2* e, const uint8_t* qs, int64_t j, int64_t b, int32_t istar) const {
@@ -1310,7 +1312,7 @@ struct L2StrandFn {
     int32_t i = (int32_t)(v.x & CODE_IDX);
     if (i > istar) return 0;
     // the map keeps the strand of the LAST inserted occurrence of a hash
-    if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u) { uint64_t l = dup_links(dupIdx, dupLinks, n_dup, j); uint32_t nd = (uint32_t)l; if (nd && j + (int64_t)nd < b) return 0; }
+    if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u) { uint64_t l = dup_links(dupRB, dupLinks, n_dup, j); uint32_t nd = (uint32_t)l; if (nd && j + (int64_t)nd < b) return 0; }
     int32_t sq = ldg(qs + i - 1) ? 1 : -1, sr = (v.y & 1u) ? 1 : -1;
     return sq * sr;
   }
@@ -1668,7 +1670,7 @@ struct Mapper {
         {
           StageTimer t(rt, &st.ms[6]);
           L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p,
-                          fe.p, le.p, readLen.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, k, w};
+                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w};
 #ifndef MM_HOST_EMU
           if ((int64_t)maxSketch * 4 <= 200 * 1024 && maxSketch < 65535) {      // bucket starts are 16-bit ranks
             static bool attrC = false;
@@ -1683,7 +1685,7 @@ struct Mapper {
 #endif
             foreach(rt, nEv, cf);
         }
-        L2SweepArgs sa{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, le.p, cRead.p, sOf.p, readLen.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, k, w,
+        L2SweepArgs sa{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, le.p, cRead.p, sOf.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w,
                        oShared.p, oPos.p, oValid.p, oOptS.p, oOptE.p, oIstar.p};
         {
           StageTimer t(rt, &st.ms[7]);
@@ -1697,7 +1699,7 @@ struct Mapper {
         }
         {
           StageTimer t(rt, &st.ms[8]);
-          L2StrandFn sf{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, cRead.p, qOff.p, qStrand.p, ix.dupIdx.p, ix.dupLinks.p, ix.n_dup, ix.dupBits.p,
+          L2StrandFn sf{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, cRead.p, qOff.p, qStrand.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, ix.dupBits.p,
                         oValid.p, oOptS.p, oOptE.p, oIstar.p, oVotes.p};
 #ifndef MM_HOST_EMU
           {
