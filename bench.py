@@ -28,6 +28,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries the one JSON line: the image's NCCL_DEBUG=VERSION makes NCCL print its banner there
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 WORKLOADS = {
     # BASELINE.json configs[1]: 100k reads (mean 8 kb, log-normal sigma 0.5) vs 1000 species x 3 strains x 4 Mbp = 12 Gbp
