@@ -1452,12 +1452,19 @@ struct Mapper {
         }
         int ambCap = (int)ambigList.cap;
         int grid = n_reads < rt.sm_count * 8 ? n_reads : rt.sm_count * 8;
+        // the three size classes touch disjoint reads: the two larger ones run on the side stream next to the small one
+        // (each alone leaves SMs idle in its tail; MM_K3_SERIAL=1 = one after the other on the main stream)
+        const bool fork = !getenv("MM_K3_SERIAL");
+        cudaStream_t s2 = fork ? rt.side : rt.stream;
+        if (fork) { MM_CUDA(cudaEventRecord(evFork(), rt.stream)); MM_CUDA(cudaStreamWaitEvent(s2, evFork(), 0)); }
+        read_sketch_block_kernel<24><<<grid, 256, sizeof(K3Block<24>::Temp), s2>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 2048, 6144, ws2.p, tStrand.p,
+                                                                                   sOf.p, scal.p, ambigList.p, ambCap);
+        read_sketch_block_kernel<8><<<grid, 256, sizeof(K3Block<8>::Temp), s2>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 1024, 2048, ws2.p, tStrand.p, sOf.p,
+                                                                                 scal.p, ambigList.p, ambCap);
+        if (fork) MM_CUDA(cudaEventRecord(evJoin(), s2));
         read_sketch_block_kernel<4><<<grid, 256, sizeof(K3Block<4>::Temp), rt.stream>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 0, 1024, ws2.p, tStrand.p, sOf.p,
                                                                                         scal.p, ambigList.p, ambCap);
-        read_sketch_block_kernel<8><<<grid, 256, sizeof(K3Block<8>::Temp), rt.stream>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 1024, 2048, ws2.p, tStrand.p, sOf.p,
-                                                                                        scal.p, ambigList.p, ambCap);
-        read_sketch_block_kernel<24><<<grid, 256, sizeof(K3Block<24>::Temp), rt.stream>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 2048, 6144, ws2.p, tStrand.p,
-                                                                                          sOf.p, scal.p, ambigList.p, ambCap);
+        if (fork) MM_CUDA(cudaStreamWaitEvent(rt.stream, evJoin(), 0));
         MM_CUDA(cudaGetLastError());
         rt.launches += 3;
         foreach(rt, n_reads, K3EdgeFn{rs.seqOff.p, 6144, sOf.p, scal.p + 2});
