@@ -203,6 +203,10 @@ def test_staged_reads(gpu_ctx, small_workload):
 def test_index_save_load(gpu_ctx, small_workload, tmp_path):
     contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
     common.check_index_save_load(gpu_ctx, contigs, [synth.codes_to_ascii(r) for r in small_workload["reads"]], 16, 13, str(tmp_path / "ix.0"))
+    # same-hash-same-contig minimizers: the loaded index rebuilds its duplicate rank table (Index::build_dup_rank)
+    from tests.test_kernel_logic_emu import _repetitive_workload
+    rc, rr = _repetitive_workload()
+    common.check_index_save_load(gpu_ctx, rc, rr, 16, 5, str(tmp_path / "ix.1"))
 
 
 def test_map_at_scale_independent_paths_agree(oracle, monkeypatch):

@@ -168,3 +168,6 @@ def test_staged_reads(emu_ctx, small_workload):
 def test_index_save_load(emu_ctx, small_workload, tmp_path):
     contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
     common.check_index_save_load(emu_ctx, contigs, [synth.codes_to_ascii(r) for r in small_workload["reads"][:40]], 16, 13, str(tmp_path / "ix.0"))
+    # a reference with same-hash-same-contig minimizers: the loaded index rebuilds its duplicate rank table (Index::build_dup_rank)
+    rc, rr = _repetitive_workload()
+    common.check_index_save_load(emu_ctx, rc, rr, 16, 5, str(tmp_path / "ix.1"))
