@@ -41,8 +41,20 @@ struct PackFn {
   const int64_t* wordOff; const int32_t* len; int32_t n_seqs;
   uint32_t* packed;
   unsigned long long* excCount; uint64_t* excPos; uint8_t* excByte; int64_t excCap;
-  MM_HD void operator()(int64_t t) const {
+  int64_t total_words;
+  // item = (group of 256 consecutive words, lane): the lane packs words lane, lane + 32, ... of the group, so a warp writes 32
+  // consecutive words per trip and the sequence a word belongs to is searched once per 8 words (then walked forward)
+  static constexpr int TRIPS = 8;
+  MM_HD void operator()(int64_t item) const {
+    int64_t t = (item >> 5) * (32 * TRIPS) + (item & 31);
+    if (t >= total_words) return;
     int64_t sq = upper_bound_idx(wordOff, (int64_t)n_seqs + 1, t) - 1;
+    for (int i = 0; i < TRIPS && t < total_words; i++, t += 32) {
+      while (ldg(wordOff + sq + 1) <= t) sq++;         // t < total_words = wordOff[n_seqs]: stops at the word's sequence
+      pack_word(t, sq);
+    }
+  }
+  MM_HD void pack_word(int64_t t, int64_t sq) const {
     int64_t lw = t - ldg(wordOff + sq);
     int32_t L = ldg(len + sq);
     const uint8_t* src = asc + ldg(ascOff + sq) + lw * 16;
@@ -59,6 +71,25 @@ struct PackFn {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const uint32_t four = mis ? ((wv[q] >> (8 * mis)) | (wv[q + 1] << (32 - 8 * mis))) : wv[q];
+      const int nbq = nb - 4 * q;                      // bytes of this group that belong to the sequence
+      if (nbq <= 0) break;
+      // four bytes at a time: upper-case, 2-bit codes and the A/C/G/T test as word operations; a group with any other byte
+      // (N, IUPAC codes, >= 0x80) takes the byte loop below, which also files the exceptions
+      const uint32_t vmask = nbq >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbq)) - 1u);
+      const uint32_t x = four & vmask;
+      const uint32_t lower = (x + 0x1f1f1f1fu) & ~(x + 0x05050505u) & 0x80808080u;      // bytes in 'a'..'z' (valid while no byte >= 0x80)
+      const uint32_t u4 = x - (lower >> 2);
+      const uint32_t cd = (u4 >> 1) & 0x03030303u;
+      uint32_t rec = 0;                                // the ASCII letters the codes stand for
+#if defined(__CUDA_ARCH__)
+      rec = __byte_perm(0x47544341u, 0u, (cd & 0x3u) | ((cd >> 4) & 0x30u) | ((cd >> 8) & 0x300u) | ((cd >> 12) & 0x3000u));
+#else
+      for (int b4 = 0; b4 < 4; b4++) rec |= code_to_ascii((cd >> (8 * b4)) & 3u) << (8 * b4);
+#endif
+      if (!(x & 0x80808080u) && ((rec ^ u4) & vmask) == 0) {
+        word |= ((cd | (cd >> 6) | (cd >> 12) | (cd >> 18)) & 0xFFu) << (8 * q);
+        continue;
+      }
 #pragma unroll
       for (int b4 = 0; b4 < 4; b4++) {
         const int b = 4 * q + b4;
@@ -423,7 +454,7 @@ struct Sketcher {
   // case the kernel pulls the bytes over PCIe itself.  No host synchronisation.
   void pack_async(SeqBatch& B, const uint8_t* asc, int ctas_per_sm = 8) {
     dev_memset(rt, B.excCount.p, 0, sizeof(unsigned long long));
-    PackFn f{asc, B.ascOff.p, B.wordOff.p, B.len.p, B.n_seqs, B.packed.p, B.excCount.p, B.excPos.p, B.excByte.p, (int64_t)B.excPos.cap};
+    PackFn f{asc, B.ascOff.p, B.wordOff.p, B.len.p, B.n_seqs, B.packed.p, B.excCount.p, B.excPos.p, B.excByte.p, (int64_t)B.excPos.cap, B.total_words};
 #ifndef MM_HOST_EMU
     // K0 of the NEXT batch is resident (one CTA per SM, PCIe-bound) while this batch's kernels run; an SM keeps the L1 /
     // shared-memory split it was given when it was last idle, so K0 asks for the all-shared split its co-residents need
@@ -434,7 +465,7 @@ struct Sketcher {
       if (pct >= 0) MM_CUDA(cudaFuncSetAttribute(foreach_kernel<PackFn>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
 #endif
-    foreach(rt, B.total_words, f, 256, ctas_per_sm);
+    foreach(rt, (B.total_words + 32 * PackFn::TRIPS - 1) / (32 * PackFn::TRIPS) * 32, f, 256, ctas_per_sm);
   }
   // the non-ACGT side list: count it (host sync on rt.stream), re-pack with a larger list if it overflowed, sort by position
   void finish_pack(SeqBatch& B, const uint8_t* asc) {
