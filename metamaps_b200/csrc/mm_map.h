@@ -871,6 +871,7 @@ struct DirectEv {
 
 template <class Ev>
 struct BandSweep {
+  static constexpr int RB_UNROLL = 16;                      // event codes in flight per lane in rebuild()'s scan (8: 10 % of K5b's stall samples sat on these loads)
   const L2SweepArgs& a; const uint2* e; Ev& ev;
   uint8_t* cnt; uint32_t* mb; int32_t BW;                  // cnt[BW+1], mb[BW/32+1]: the last entries are write-only dummies
   int64_t b0; int32_t s, sh, lo, istar, C, shared; bool fail, bad;
@@ -920,12 +921,12 @@ struct BandSweep {
     for (int32_t i = 0; i < (BW + 4) / 4; i++) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
     for (int32_t i = 0; i <= BW / 32; i++) mb[i] = 0;
     int32_t Cb = 0, Sb = 0;
-    for (int32_t j0 = beg; j0 < end; j0 += 8) {
-      uint32_t cd[8];
+    for (int32_t j0 = beg; j0 < end; j0 += RB_UNROLL) {
+      uint32_t cd[RB_UNROLL];
 #pragma unroll
-      for (int u = 0; u < 8; u++) cd[u] = (j0 + u < end) ? ldg(&e[j0 + u].x) : SKIP;
+      for (int u = 0; u < RB_UNROLL; u++) cd[u] = (j0 + u < end) ? ldg(&e[j0 + u].x) : SKIP;
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
+      for (int u = 0; u < RB_UNROLL; u++) {
         const uint32_t code = cd[u];
         const bool cntd = first_copy(code, j0 + u, beg);
         const int32_t isM = (int32_t)(code >> 31), idx = (int32_t)(code & CODE_IDX);
