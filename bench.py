@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=1,
                     help="batches in flight per GPU (host threads, one context each, sharing the index); measured on config 2: 2 in flight = "
-                         "+3 % value, -4 % e2e, so the default stays 1")
+                         "+3 % value, -4 % e2e with the session-2 kernels and -7 % / -15 % with the session-3 ones, so the default stays 1")
     ap.add_argument("--shard", default="reads", choices=["reads", "contigs"],
                     help="N > 1: 'reads' = index replicated, every rank maps its own reads (no mapping exchange); 'contigs' = the "
                          "index is split into contig ranges, every rank maps ALL reads against its shard, mappings are exchanged")
