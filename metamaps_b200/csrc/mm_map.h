@@ -1047,7 +1047,7 @@ struct BandSweep {
 // sweeps on its own, and L2BandMergeFn combines them: the optimum is the FIRST window with the maximal count, the
 // reported last position the LAST window with that count (computeMap.hpp:510-533), whichever segments they fall in.
 struct BandPart { int32_t shared, bpos, lpos, optS, optE, istar, any, fail; };
-static const int BAND_SEG_DEFAULT = 2048;
+static const int BAND_SEG_DEFAULT = 4096;   // window starts per segment: 2048 12.9 ms, 3072 12.5, 4096 12.2, 6144 13.2, 8192 15.3 (config 2)
 static const int32_t BAND_LAST_SEG = 1 << 30;
 
 // one segment; cnt: BW+1 (+3 pad) bytes, mb: BW/32+1 words.  part.fail: the candidate must go through the full-state
