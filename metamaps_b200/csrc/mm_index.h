@@ -189,7 +189,13 @@ struct Index {
     contigStart.ensure(h_contigStart.size()); h2d(rt, contigStart.p, h_contigStart.data(), sizeof(int64_t) * h_contigStart.size());
     contigLen.ensure(h_contigLen.size() + 1); h2d(rt, contigLen.p, h_contigLen.data(), sizeof(int32_t) * h_contigLen.size());
     finalized = true;
-    if (n == 0) { table.ensure(1024); dev_memset(rt, table.p, 0, sizeof(Slot) * 1024); tableMask = 1023; return; }
+    if (n == 0) {          // no minimizers (no contigs, or all shorter than w / k): every array exists, zeroed, so that save / load / map work
+      table.ensure(1024); dev_memset(rt, table.p, 0, sizeof(Slot) * 1024); tableMask = 1023;
+      miHash.ensure(1); miWs.ensure(1); posKey.ensure(1); hasSeq16 = n_contigs <= 65536; if (hasSeq16) posSeq16.ensure(8);
+      dupBits.ensure(2); dev_memset(rt, dupBits.p, 0, sizeof(uint32_t) * 2); dupIdx.ensure(1); dupLinks.ensure(1);
+      build_dup_rank();
+      return;
+    }
     DevBuf<uint32_t> iota, sortedHash, sortedPos, uniq, cntSorted, cntUniq;
     DevBuf<int32_t> counts, cntRuns; DevBuf<int64_t> starts, nRuns;
     iota.ensure((size_t)n); sortedHash.ensure((size_t)n); sortedPos.ensure((size_t)n);

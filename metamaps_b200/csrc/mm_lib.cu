@@ -45,7 +45,7 @@ struct mm_ctx {
 #endif
   } stage[2];
   // NCCL (multi-GPU EM), bound at run time
-  void* ncclLib = nullptr; void* comm = nullptr; int nRanks = 1, rank = 0;
+  void* comm = nullptr; int nRanks = 1, rank = 0;
   mm_allreduce_fn hostAllreduce = nullptr; void* hostAllreduceUser = nullptr; std::vector<double> hostBuf;
   mm_ctx() : pr(rt), sk(rt, pr), mp(rt, pr, sk) {}
 };
@@ -299,7 +299,18 @@ int mm_index_load(mm_ctx* c, const char* path, mm_index** out) {
   try {
     IndexFileHeader h; get(f, &h, sizeof h);
     if (memcmp(h.magic, INDEX_MAGIC, 8) != 0 || h.version != 1) throw Error(MM_EINVAL, "mm_index_load: not a metamaps_b200 index file (or another version)");
-    if (h.k < 1 || h.k > 16 || h.w < 1 || h.n < 0 || h.n_contigs < 0 || h.tableSlots < 1 || (h.tableSlots & (h.tableSlots - 1))) throw Error(MM_EINVAL, "mm_index_load: corrupt header");
+    if (h.k < 1 || h.k > 16 || h.w < 1 || h.n < 0 || h.n_contigs < 0 || h.n_dup < 0 || h.n_dup > h.n || h.n_unique < 0 || h.n_unique > h.n || h.tableSlots < 1 ||
+        h.tableSlots > ((int64_t)1 << 32) || (h.tableSlots & (h.tableSlots - 1)) || h.n >= 0xFFFFFFF0ll)
+      throw Error(MM_EINVAL, "mm_index_load: corrupt header");
+    {   // the header must agree with the file size before anything is allocated from it
+      const int64_t expect = (int64_t)sizeof h + 4 * (int64_t)h.n_contigs + 8 * ((int64_t)h.n_contigs + 1) + 8 * h.n + (int64_t)sizeof(Slot) * h.tableSlots + 8 * h.n +
+                             (h.hasSeq16 ? 2 * h.n : 0) + 4 * (h.n / 32 + 2) + 12 * h.n_dup;
+      const long at = ftell(f);
+      if (fseek(f, 0, SEEK_END) != 0) throw Error(MM_EINVAL, "mm_index_load: cannot seek");
+      const int64_t size = (int64_t)ftell(f);
+      if (fseek(f, at, SEEK_SET) != 0) throw Error(MM_EINVAL, "mm_index_load: cannot seek");
+      if (size != expect) throw Error(MM_EINVAL, "mm_index_load: file size does not match its header (truncated or corrupt index file)");
+    }
     idx = new mm_index(c, (int)h.k, (int)h.w);
     Index& ix = idx->ix;
     ix.n = h.n; ix.n_unique = h.n_unique; ix.n_dup = h.n_dup; ix.total_bases = h.total_bases; ix.tableMask = (uint32_t)(h.tableSlots - 1); ix.n_contigs = h.n_contigs;
@@ -682,48 +693,54 @@ typedef int (*fn_ncclCommInitRank)(void**, int, NcclUid, int);
 typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_ncclCommDestroy)(void*);
 typedef int (*fn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
-static void* nccl_open() {
+typedef int (*fn_ncclSend)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclGroup)(void);
+// libnccl is opened ONCE per process and its entry points resolved once (a magic static: thread-safe); the handle is never
+// closed -- communicators of any context may still be alive at exit.
+struct NcclApi {
+  void* lib = nullptr; std::string err;
+  fn_ncclGetUniqueId getUniqueId = nullptr; fn_ncclCommInitRank commInitRank = nullptr; fn_ncclAllReduce allReduce = nullptr;
+  fn_ncclCommDestroy commDestroy = nullptr; fn_ncclAllGather allGather = nullptr;
+  NcclApi() {
 #ifdef MM_HOST_EMU
-  throw Error(MM_ENODEV, "NCCL is not available in the host-emulation test build");
+    err = "NCCL is not available in the host-emulation test build";
 #else
-  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-  if (!h) throw Error(MM_ENODEV, std::string("cannot load libnccl.so.2: ") + dlerror());
-  return h;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+    auto sym = [&](const char* n) -> void* { void* p = dlsym(lib, n); if (!p && err.empty()) err = std::string("libnccl is missing ") + n; return p; };
+    getUniqueId = (fn_ncclGetUniqueId)sym("ncclGetUniqueId"); commInitRank = (fn_ncclCommInitRank)sym("ncclCommInitRank");
+    allReduce = (fn_ncclAllReduce)sym("ncclAllReduce"); commDestroy = (fn_ncclCommDestroy)sym("ncclCommDestroy"); allGather = (fn_ncclAllGather)sym("ncclAllGather");
 #endif
-}
-static void* nccl_sym(void* h, const char* n) {
-#ifdef MM_HOST_EMU
-  (void)h; (void)n; return nullptr;
-#else
-  void* p = dlsym(h, n);
-  if (!p) throw Error(MM_ENODEV, std::string("libnccl is missing ") + n);
-  return p;
-#endif
+  }
+};
+static const NcclApi& nccl() {
+  static NcclApi api;
+  if (!api.err.empty()) throw Error(MM_ENODEV, api.err);
+  return api;
 }
 int mm_comm_unique_id(void* id) {
   MM_TRY
   if (!id) throw Error(MM_EINVAL, "null id buffer");
-  void* h = nccl_open();
-  int rc = ((fn_ncclGetUniqueId)nccl_sym(h, "ncclGetUniqueId"))((NcclUid*)id);
+  int rc = nccl().getUniqueId((NcclUid*)id);
   if (rc != 0) throw Error(MM_ECUDA, "ncclGetUniqueId failed: " + std::to_string(rc));
   MM_CATCH
 }
 int mm_comm_init(mm_ctx* c, int n_ranks, int rank, const void* id) {
   MM_TRY
   if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) throw Error(MM_EINVAL, "mm_comm_init: bad arguments");
+  if (c->comm) throw Error(MM_EINVAL, "mm_comm_init: the context already has a communicator (mm_comm_destroy first)");
   begin_call(c);
-  c->ncclLib = nccl_open();
   NcclUid u; memcpy(&u, id, sizeof(u));
-  int rc = ((fn_ncclCommInitRank)nccl_sym(c->ncclLib, "ncclCommInitRank"))(&c->comm, n_ranks, u, rank);
+  int rc = nccl().commInitRank(&c->comm, n_ranks, u, rank);
   if (rc != 0) { c->comm = nullptr; throw Error(MM_ECUDA, "ncclCommInitRank failed: " + std::to_string(rc)); }
   c->nRanks = n_ranks; c->rank = rank;
   MM_CATCH
 }
 int mm_comm_destroy(mm_ctx* c) {
   if (!c) return MM_EINVAL;
-  if (c->comm && c->ncclLib) {
-    try { ((fn_ncclCommDestroy)nccl_sym(c->ncclLib, "ncclCommDestroy"))(c->comm); } catch (...) {}
+  if (c->comm) {
+    try { nccl().commDestroy(c->comm); } catch (...) {}
   }
   c->comm = nullptr; c->nRanks = 1; c->rank = 0;
   return MM_OK;
@@ -742,7 +759,7 @@ static void allreduce_sum_f64(mm_ctx* c, double* buf, size_t n) {
     return;
   }
   if (!c->comm || c->nRanks == 1) return;
-  int rc = ((fn_ncclAllReduce)nccl_sym(c->ncclLib, "ncclAllReduce"))(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->rt.stream);
+  int rc = nccl().allReduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->rt.stream);
   if (rc != 0) throw Error(MM_ECUDA, "ncclAllReduce failed: " + std::to_string(rc));
   c->rt.launches++;
 }
@@ -757,7 +774,7 @@ int mm_comm_set_rank(mm_ctx* c, int n_ranks, int rank) {
 static void allgather_u32(mm_ctx* c, const uint32_t* send, uint32_t* recv, size_t count) {
   if (count == 0) return;
   if (c->comm && c->nRanks > 1) {
-    int rc = ((fn_ncclAllGather)nccl_sym(c->ncclLib, "ncclAllGather"))(send, recv, count, /*ncclUint32*/ 3, c->comm, c->rt.stream);
+    int rc = nccl().allGather(send, recv, count, /*ncclUint32*/ 3, c->comm, c->rt.stream);
     if (rc != 0) throw Error(MM_ECUDA, "ncclAllGather failed: " + std::to_string(rc));
     c->rt.launches++;
     return;

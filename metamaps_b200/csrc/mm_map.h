@@ -1446,11 +1446,8 @@ struct Mapper {
         // per-read block sort (read_sketch_block_kernel); scal[0] = ambiguous reads, [1] = max sketch, [2] = oversize reads, [3] = n_q
         ws2.ensure((size_t)nm + 1); tStrand.ensure((size_t)nm + 1);
         dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);
-        static bool attrK3 = false;
-        if (!attrK3) {
+        if (rt.first((const void*)read_sketch_block_kernel<24>))
           MM_CUDA(cudaFuncSetAttribute(read_sketch_block_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Block<24>::Temp)));
-          attrK3 = true;
-        }
         int ambCap = (int)ambigList.cap;
         int grid = n_reads < rt.sm_count * 8 ? n_reads : rt.sm_count * 8;
         // the three size classes touch disjoint reads: the two larger ones run on the side stream next to the small one
@@ -1522,8 +1519,7 @@ struct Mapper {
           AmbigResolveFn rf{ambigList.p, rs.hash.p, rs.ws.p, rs.seqOff.p, key.p, qOff.p, qHash.p, qStrand.p};
 #ifndef MM_HOST_EMU
           {   // shared-memory replay for reads of up to 6000 minimizers; the (rare) longer ones through the global-memory functor
-            static bool attrA = false;
-            if (!attrA) { MM_CUDA(cudaFuncSetAttribute(ambig_resolve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48000)); attrA = true; }
+            if (rt.first((const void*)ambig_resolve_smem_kernel)) MM_CUDA(cudaFuncSetAttribute(ambig_resolve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48000));
             ambigBig.ensure((size_t)na + 1); scal2.ensure(2);
             MM_CUDA(cudaMemsetAsync(scal2.p, 0, sizeof(unsigned long long), rt.side));
             ambig_resolve_smem_kernel<<<(unsigned)na, 32, 48000, rt.side>>>(rf, 6000, ambigBig.p, scal2.p);
@@ -1579,12 +1575,10 @@ struct Mapper {
         uint32_t binsN = 64; while (binsN < (uint32_t)ix.n_contigs && binsN < 32768u) binsN <<= 1;
         hits.ensure((size_t)n_hits + 1); keptPerRead.ensure((size_t)n_reads + 2); scal.ensure(4);
         dev_memset(rt, scal.p, 0, sizeof(unsigned long long));
-        static bool attrF = false;
-        if (!attrF) { MM_CUDA(cudaFuncSetAttribute(l1_filter_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); attrF = true; }
+        if (rt.first((const void*)l1_filter_gather_kernel)) MM_CUDA(cudaFuncSetAttribute(l1_filter_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         const char* lf = getenv("MM_L1_FILTER"); const bool legacy = lf && !strcmp(lf, "legacy");
         if (ix.hasSeq16 && !legacy) {
-          static bool attrG = false;
-          if (!attrG) { MM_CUDA(cudaFuncSetAttribute(l1_filter_gather16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attrG = true; }
+          if (rt.first((const void*)l1_filter_gather16_kernel)) MM_CUDA(cudaFuncSetAttribute(l1_filter_gather16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
           static int cacheCap = 0;
           if (!cacheCap) { const char* e = getenv("MM_L1_CACHE"); cacheCap = e ? atoi(e) : 12288; if (cacheCap < 0 || cacheCap > 14336) cacheCap = 12288; }
           size_t smem = (size_t)binsN * 2 + (size_t)cacheCap * 2;
@@ -1681,8 +1675,7 @@ struct Mapper {
                           fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w};
 #ifndef MM_HOST_EMU
           if ((int64_t)maxSketch * 4 <= 200 * 1024 && maxSketch < 65535) {      // bucket starts are 16-bit ranks
-            static bool attrC = false;
-            if (!attrC) { MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attrC = true; }
+            if (rt.first((const void*)l2_classify_smem_kernel)) MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             // contiguous runs of candidates per CTA, ~8 waves of CTAs so that uneven runs average out
             int64_t g = (int64_t)rt.sm_count * 64; if (g > nc) g = nc;
             int32_t perCta = (int32_t)((nc + g - 1) / g); g = (nc + perCta - 1) / perCta;
@@ -1799,8 +1792,8 @@ struct Mapper {
           const char* ev_ = getenv("MM_SWEEP_WARPS");
           SWEEP_WARPS = ev_ ? atoi(ev_) : 8;
           if (SWEEP_WARPS < 1 || SWEEP_WARPS > SWEEP_WARPS_MAX) SWEEP_WARPS = 8;
-          MM_CUDA(cudaFuncSetAttribute(l2_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_WORDS * 4));
         }
+        if (rt.first((const void*)l2_sweep_smem_kernel)) MM_CUDA(cudaFuncSetAttribute(l2_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_WORDS * 4));
         const int32_t SLICE = SWEEP_SMEM_WORDS / SWEEP_WARPS;
         hk.resize((size_t)nc);
         d2h(rt, hk.data(), swKey2.p, sizeof(uint32_t) * (size_t)nc);
@@ -1870,8 +1863,8 @@ struct Mapper {
       ctasPerSm = total > 16 ? 2 : 1;
       warps = total / ctasPerSm;
       if (const char* e = getenv("MM_SWEEP_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 16) warps = v; }
-      MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
     }
+    if (rt.first((const void*)l2_sweep_band_kernel<BW, R>)) MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
     int64_t tiles = (nc + 31) / 32;
     int64_t g = (tiles + warps - 1) / warps; if (g > (int64_t)rt.sm_count * ctasPerSm) g = (int64_t)rt.sm_count * ctasPerSm;
     l2_sweep_band_kernel<BW, R><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, order, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,

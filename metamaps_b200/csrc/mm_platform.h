@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 #include <list>
+#include <set>
 
 #ifdef MM_HOST_EMU
 #define MM_HD inline
@@ -56,6 +57,10 @@ struct Runtime {
   int sm_count = 148;
   int64_t launches = 0;          // kernels launched since reset()
   double total_ms = 0;           // filled by StageTimer users
+  // cudaFuncSetAttribute is per DEVICE: the opt-ins are remembered per context (one device, one host thread at a time),
+  // not in function-local statics -- a process may hold contexts on several GPUs
+  std::set<const void*> attrDone;
+  bool first(const void* key) { return attrDone.insert(key).second; }
 #ifndef MM_HOST_EMU
   struct Pending { cudaEvent_t a = nullptr, b = nullptr; double* acc = nullptr; bool closed = false; };
   std::list<Pending> pending;     // list: StageTimer keeps a pointer to its entry

@@ -458,9 +458,7 @@ struct Sketcher {
 #ifndef MM_HOST_EMU
     // K0 of the NEXT batch is resident (one CTA per SM, PCIe-bound) while this batch's kernels run; an SM keeps the L1 /
     // shared-memory split it was given when it was last idle, so K0 asks for the all-shared split its co-residents need
-    static bool carve = false;
-    if (!carve) {
-      carve = true;
+    if (rt.first((const void*)foreach_kernel<PackFn>)) {
       const char* e = getenv("MM_K0_CARVEOUT"); const int pct = e ? atoi(e) : 100;
       if (pct >= 0) MM_CUDA(cudaFuncSetAttribute(foreach_kernel<PackFn>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }

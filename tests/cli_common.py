@@ -142,3 +142,28 @@ def check_chunked_equals_direct(binary, workdir, chunk_bases=150_000):
     subprocess.run([binary, "classify", "--DB", "db", "--mappings", f"{out}/ref"], cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     compare_mapping_files(direct, os.path.join(workdir, out))
     return n_chunks
+
+
+def check_config2_golden(binary, workdir):
+    """The C++ host on the config-2-shaped sample (408 Mbp, finite occurrence threshold) against the files the UNMODIFIED
+    reference wrote for it (tests/golden/ref_config2, generator make_golden_config2.py).  Returns (identical files, threshold line)."""
+    import gzip
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    import make_golden_config2 as g
+    g.config2_sample(workdir)
+    gold = os.path.join(workdir, "gold"); os.makedirs(gold, exist_ok=True)
+    src = os.path.join(root, "tests", "golden", "ref_config2")
+    for fn in os.listdir(src):
+        with gzip.open(os.path.join(src, fn), "rb") as f, open(os.path.join(gold, fn[:-3]), "wb") as o:
+            o.write(f.read())
+    thr = [l for l in open(os.path.join(gold, "map.log")) if "ignore minimizers occurring" in l]
+    assert thr and ">= 12 times" in thr[0], "the fixture must pin a FINITE occurrence threshold"
+    out = os.path.join(workdir, "out_b200"); os.makedirs(out, exist_ok=True)
+    p = subprocess.run([binary, "mapDirectly", *g.MAP_ARGS, "-r", "db/DB.fa", "-q", "reads.fq", "-o", "out_b200/ref"], cwd=workdir, check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    mine = [l for l in p.stdout.splitlines() if "ignore minimizers occurring" in l]
+    assert mine and mine[0].strip() == thr[0].strip(), (mine, thr)          # same computeFreqHist line as the reference
+    subprocess.run([binary, "classify", "--DB", "db", "--mappings", "out_b200/ref"], cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    return compare_dirs(gold, out), thr[0].strip()

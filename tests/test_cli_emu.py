@@ -71,3 +71,10 @@ def test_cli_db_with_N_runs_lowercase_and_iupac(tmp_path):
 def test_cli_chunked_reference_equals_single_index(small_workload):
     binary = build_emu_host()
     assert cli_common.check_chunked_equals_direct(binary, small_workload["dir"]) >= 3
+
+
+def test_cli_config2_shaped_sample_matches_reference_files(tmp_path):
+    """408 Mbp of the config-2 recipe: the reference's occurrence threshold is FINITE there (>= 12, its own INFO line), the
+    32-bit hash space starts to saturate, and all ten files must equal what the unmodified reference wrote (fixture)."""
+    identical, thr = cli_common.check_config2_golden(build_emu_host(), str(tmp_path))
+    assert identical == 10, identical

@@ -153,6 +153,19 @@ def test_cli_matches_golden_reference_files(small_workload):
     assert cli_common.check_chunked_equals_direct(build.HOST_BIN, small_workload["dir"]) >= 3          # the --maxmemory chunk loop
 
 
+def test_cli_config2_shaped_sample_matches_reference_files(tmp_path):
+    """Config-2-shaped data from the reference itself: 408 Mbp of bench.py's DB recipe, 1500 reads, -m 2000 -w 16.  The
+    reference's occurrence threshold is finite there (its own "ignore minimizers occurring >= 12 times" line, which the host
+    must print too), so the over-frequent-hash skip (computeMap.hpp:314) and the L1 contig filter on a saturating 32-bit hash
+    space are pinned by the unmodified reference's ten output files (tests/golden/ref_config2)."""
+    import os
+    from metamaps_b200 import build
+    from tests import cli_common
+    assert os.path.exists(build.HOST_BIN), "metamaps_b200/metamaps not built"
+    identical, thr = cli_common.check_config2_golden(build.HOST_BIN, str(tmp_path))
+    assert identical == 10, identical
+
+
 @pytest.mark.parametrize("name", ["many_contigs", "long_read", "low_complexity"])
 def test_fast_path_fallbacks(gpu_ctx, oracle, name):
     """Hashed contig bins, sketches too large for shared memory, 8-bit counter overflow: same results as the oracle."""
