@@ -118,7 +118,8 @@ void mm_index_destroy(mm_index* idx);
 typedef struct mm_map_params {
   float perc_identity;   /* --pi, default 80 (parseCmdArgs.hpp:345-354) */
   int32_t min_read_len;  /* -m; reads shorter than max(w,k,m) are skipped (computeMap.hpp:137) */
-  int32_t report_all;    /* --all: 1 keeps every accepted mapping; 0 keeps identity >= best-1 (computeMap.hpp:561-563) */
+  int32_t report_all;    /* --all: 1 keeps every accepted mapping; 0 keeps, per read, those with identity >= best - 1.0
+                            (reportReadMappings, computeMap.hpp:551-563): the others are dropped from the accepted set */
   int32_t reserved;
 } mm_map_params;
 
@@ -169,6 +170,44 @@ int mm_map_fetch_sketch(mm_ctx* ctx, int64_t* offsets /*n_reads+1*/, uint32_t* h
 int mm_map_fetch_mappings(mm_ctx* ctx, int32_t* read_idx, int32_t* seq_id, int32_t* ref_start, int32_t* shared,
                           int32_t* sketch, int32_t* strand, float* identity, double* identity_parsed, int64_t cap,
                           int64_t* n_mappings);
+
+/* ---- the classify stage on the device  (mapWrap::addMappingQualities + meta::doEM on arrays that stay in HBM) -------
+ * The accepted mappings of the last mm_map_* call(s) go through identity -> mapping quality (K6) -> nLoc -> EM (K7/K8)
+ * without leaving the device; the host reads the finished arrays once.  Sequence of calls per batch of reads:
+ *   mm_classify_setup          once per reference: contig lengths and taxa (GLOBAL contig ids), n_taxa
+ *   mm_classify_begin          empties the mapping table
+ *   mm_classify_add_mappings   after each mm_map_* call of the batch: appends its accepted mappings, contig ids shifted by
+ *                              first_contig_id (0 for an unsharded index; the shard's first contig otherwise).  Shards must be
+ *                              added in contig order: a read's lines are its mappings per chunk, in chunk order
+ *                              (unifyFiles, mapWrap.h:128-132).
+ *   mm_classify_exchange       contig-sharded multi-GPU only (collective over the context's communicator): all ranks mapped
+ *                              the same reads against their own shard; the tables are all-gathered (ncclAllGather of padded
+ *                              slabs) and merged on the device in shard (= rank) order; this rank keeps the reads
+ *                              [read_lo, read_hi) and finalises them (mapping quality needs a read's mappings from all shards,
+ *                              mapWrap.h:226-278).
+ *   mm_classify_run            identity (float + its 6-digit text round trip, bit-identical to glibc's: see mm_classify.h),
+ *                              mapq, nLoc, EM to the reference's stopping rule (em_max_iter <= 0) or for exactly em_max_iter
+ *                              rounds; multi-rank contexts all-reduce the taxon sums every round.  Collective when n_ranks > 1.
+ *   mm_classify_fetch          any pointer may be NULL.  Per mapping (cap >= n_mappings): the arrays of mm_map_fetch_mappings
+ *                              plus mapq (column 14), taxon, nloc, posterior; per mapped read (n_reads_mapped entries):
+ *                              mapped_read = its index in the batch, read_off (+1 entry), best = index of its first maximal
+ *                              posterior, mapq_status; f[n_taxa]; ll_hist[min(em_iters, ll_cap)]. */
+typedef struct mm_classify_summary {
+  int64_t n_mappings;        /* mappings in the table this rank finalised */
+  int64_t n_reads_mapped;    /* reads with at least one of them */
+  int32_t em_iters;          /* EM rounds run */
+  int32_t n_identity_fixups; /* identities settled by the host through glibc (see mm_classify.h; normally 0) */
+  double em_ms;              /* device time of the EM rounds + final pass (CUDA events) */
+  double classify_ms;        /* device time of the whole stage */
+} mm_classify_summary;
+int mm_classify_setup(mm_ctx* ctx, const int64_t* contig_len, const int32_t* contig_taxon, int32_t n_contigs, int32_t n_taxa);
+int mm_classify_begin(mm_ctx* ctx);
+int mm_classify_add_mappings(mm_ctx* ctx, int32_t first_contig_id, int64_t* n_total);
+int mm_classify_exchange(mm_ctx* ctx, int32_t read_lo, int32_t read_hi, int64_t* n_total);
+int mm_classify_run(mm_ctx* ctx, int32_t em_max_iter, mm_classify_summary* out);
+int mm_classify_fetch(mm_ctx* ctx, int32_t* read_idx, int32_t* seq_id, int32_t* ref_start, int32_t* shared, int32_t* sketch, int32_t* strand,
+                      float* identity, double* identity_parsed, double* mapq, int32_t* taxon, double* nloc, double* posterior, int64_t cap,
+                      int32_t* mapped_read, int64_t* read_off, int64_t* best, int32_t* mapq_status, double* f, double* ll_hist, int32_t ll_cap);
 
 /* ---- host helpers of the classify stage (C++/OpenMP, no device work) -------------------------------- */
 /* Runs of equal values in a non-decreasing array (the mappings' read indices): group_value[g], group_off[g..g+1]; arrays of

@@ -28,6 +28,11 @@ class MapSummary(C.Structure):
                 ("n_reads_mapped", C.c_int64), ("total_bases_mapped_reads", C.c_int64)]
 
 
+class ClassifySummary(C.Structure):
+    _fields_ = [("n_mappings", C.c_int64), ("n_reads_mapped", C.c_int64), ("em_iters", C.c_int32), ("n_identity_fixups", C.c_int32),
+                ("em_ms", C.c_double), ("classify_ms", C.c_double)]
+
+
 # every symbol include/metamaps_b200.h declares: (restype, argtypes); None = opaque/void pointers
 SYMBOLS = {
     "mm_last_error": (C.c_char_p, []),
@@ -70,6 +75,12 @@ SYMBOLS = {
     "mm_stat_identity": (None, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mm_mapq_batch": (C.c_int, [C.c_void_p, _f64p, _i32p, _i32p, _i32p, _i64p, C.c_int64, C.c_int, _f64p, _i32p]),
     "mm_em_run": (C.c_int, [C.c_void_p, _i32p, _f64p, _f64p, _i64p, C.c_int64, C.c_int32, C.c_int32, _f64p, _f64p, _i64p, _f64p, C.c_int32, C.POINTER(C.c_int32)]),
+    "mm_classify_setup": (C.c_int, [C.c_void_p, _i64p, _i32p, C.c_int32, C.c_int32]),
+    "mm_classify_begin": (C.c_int, [C.c_void_p]),
+    "mm_classify_add_mappings": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
+    "mm_classify_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "mm_classify_run": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(ClassifySummary)]),
+    "mm_classify_fetch": (C.c_int, [C.c_void_p] + [C.c_void_p] * 12 + [C.c_int64] + [C.c_void_p] * 6 + [C.c_int32]),
     "mm_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mm_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mm_comm_destroy": (C.c_int, [C.c_void_p]),
@@ -180,6 +191,59 @@ class Context:
         it = C.c_int32()
         self._check(self.lib.mm_em_run(self.h, taxon, mapq, nloc, read_off, nr, T, max_iter, f, post, best, ll, len(ll), C.byref(it)))
         return {"f": f, "posterior": post, "best": best[:nr], "ll": ll[:min(it.value, len(ll))].copy(), "iters": it.value}
+
+    # classify stage on the device (mm_classify_*)
+    def classify_setup(self, contig_len, contig_taxon, n_taxa: int):
+        """Contig lengths / taxa (global contig ids) of the reference; cached on the arrays' identity."""
+        key = (id(contig_len), id(contig_taxon), int(n_taxa))
+        if getattr(self, "_taxo_key", None) == key:
+            return
+        cl = np.ascontiguousarray(contig_len, np.int64); ct = np.ascontiguousarray(contig_taxon, np.int32)
+        self._check(self.lib.mm_classify_setup(self.h, cl, ct, len(cl), int(n_taxa)))
+        self._taxo_key = key; self._taxo_keep = (contig_len, contig_taxon); self._n_taxa = int(n_taxa)
+
+    def classify_begin(self):
+        self._check(self.lib.mm_classify_begin(self.h))
+
+    def classify_add(self, first_contig_id: int = 0) -> int:
+        """Append the accepted mappings of the last map call (contig ids + first_contig_id); returns the table size."""
+        n = C.c_int64()
+        self._check(self.lib.mm_classify_add_mappings(self.h, int(first_contig_id), C.byref(n)))
+        return n.value
+
+    def classify_exchange(self, read_lo: int, read_hi: int) -> int:
+        """Collective (contig-sharded ranks): all-gather + merge the tables, keep the reads [read_lo, read_hi)."""
+        n = C.c_int64()
+        self._check(self.lib.mm_classify_exchange(self.h, int(read_lo), int(read_hi), C.byref(n)))
+        return n.value
+
+    def classify_run(self, em_max_iter: int = 0) -> dict:
+        s = ClassifySummary()
+        self._check(self.lib.mm_classify_run(self.h, int(em_max_iter), C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in ClassifySummary._fields_}
+
+    def classify_fetch(self, summary: dict, what=("read", "seq", "pos", "shared", "sketch", "strand", "identity", "identity_parsed", "mapq", "taxon",
+                                                    "nloc", "posterior", "mapped_reads", "read_off", "best", "mapq_status", "f", "ll")) -> dict:
+        """D2H of the finished arrays (one call, one synchronisation)."""
+        M = int(summary["n_mappings"]); G = int(summary["n_reads_mapped"]); T = self._n_taxa
+        per_m = (("read", np.int32), ("seq", np.int32), ("pos", np.int32), ("shared", np.int32), ("sketch", np.int32), ("strand", np.int32),
+                 ("identity", np.float32), ("identity_parsed", np.float64), ("mapq", np.float64), ("taxon", np.int32), ("nloc", np.float64),
+                 ("posterior", np.float64))
+        out = {}; args = []
+        for name, dt in per_m:
+            a = _out("c_" + name, M, dt) if name in what else None
+            out[name] = a; args.append(_ptr(a))
+        mr = _out("c_mapped", G, np.int32) if "mapped_reads" in what else None
+        ro = _out("c_read_off", G + 1, np.int64) if "read_off" in what else None
+        be = _out("c_best", G, np.int64) if "best" in what else None
+        stt = _out("c_status", G, np.int32) if "mapq_status" in what else None
+        f = _out("c_f", T, np.float64) if "f" in what else None
+        ll = np.zeros(4096) if "ll" in what else None
+        self._check(self.lib.mm_classify_fetch(self.h, *args, M, _ptr(mr), _ptr(ro), _ptr(be), _ptr(stt), _ptr(f), _ptr(ll), 4096 if ll is not None else 0))
+        out.update({"mapped_reads": mr, "read_off": ro, "best": be, "mapq_status": stt, "f": f,
+                    "ll": None if ll is None else ll[:min(int(summary["em_iters"]), 4096)].copy()})
+        out["d2h_bytes"] = int(sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray)))
+        return {k_: v for k_, v in out.items() if v is not None}
 
     def comm_init(self, n_ranks: int, rank: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)

@@ -20,7 +20,10 @@
 #include "mm_mapq.h"
 #include "mm_prims.h"
 #include "mm_stats.h"
+#include <algorithm>
 #include <cmath>
+#include <functional>
+#include <vector>
 
 namespace mm {
 
@@ -144,18 +147,19 @@ struct GroupLenFn { const int32_t* grpRead; const int32_t* readLen; int32_t* out
 // ---- K6, one group of G lanes per read -------------------------------------------------------------------------------
 template <int G>
 struct MapqGroupFn {
-  const double* parsed; const int32_t* shared; const int32_t* sketch; const int32_t* grpLen; const int64_t* grpOff; int64_t nGroups; int k;
+  const double* parsed; double div;      // identity = parsed / div: column 10 / 100 (mapWrap.h:229), or a fraction given as such (div = 1)
+  const int32_t* shared; const int32_t* sketch; const int32_t* grpLen; const int64_t* grpOff; int64_t nGroups; int k;
   double* mapq; int32_t* status;
-  MM_HD void operator()(int64_t item) const {
+  MM_HD void operator()(int64_t item) const {       // no lane leaves before the last shuffle of its warp
     const int64_t g = item / G; const int lane = Grp<G>::lane();
     const bool on = g < nGroups;
     const int64_t b = on ? ldg(grpOff + g) : 0, e = on ? ldg(grpOff + g + 1) : 0;
     double maxid = -1;
-    for (int64_t m = b + lane; m < e; m += G) { const double v = ldg(parsed + m) / 100.0; if (v > maxid) maxid = v; }      // column 10 / 100 (mapWrap.h:229)
+    for (int64_t m = b + lane; m < e; m += G) { const double v = ldg(parsed + m) / div; if (v > maxid) maxid = v; }
     maxid = Grp<G>::max(maxid);
-    if (!on || e <= b) { if (on && lane == 0) status[g] = 0; return_sync(); return; }
+    const bool live = on && e > b;
     maxid = exp(-(1 - maxid));
-    const int n_kmers = ldg(grpLen + g) - k + 1;
+    const int n_kmers = (live ? ldg(grpLen + g) : k) - k + 1;
     const double surv = pow(maxid, (double)k);
     const double E = round(surv * n_kmers);
     const double U = n_kmers + (n_kmers - E);
@@ -163,11 +167,11 @@ struct MapqGroupFn {
     double sum = 0;
     for (int64_t m = b + lane; m < e; m += G) { const double l = d_binom_pmf(ldg(shared + m), ldg(sketch + m), p); mapq[m] = l; sum += l; }
     sum = Grp<G>::sum(sum);
+    if (!live) { if (on && lane == 0) status[g] = 0; return; }
     if (!(sum > 0)) { if (lane == 0) status[g] = 1; return; }                                   // the reference asserts (mapWrap.h:298)
     for (int64_t m = b + lane; m < e; m += G) mapq[m] = mapq[m] / sum;
     if (lane == 0) status[g] = 0;
   }
-  MM_HD static void return_sync() {}
 };
 
 // ---- nLoc (fEM.h:324-348) --------------------------------------------------------------------------------------------
@@ -341,5 +345,178 @@ struct EmFinalGroupFn {
     if (on && lane == 0) best[g] = e > b ? bi : b;
   }
 };
+
+
+// ---- host orchestration ------------------------------------------------------------------------------------------------
+struct Taxonomy {       // mm_classify_setup: contig lengths / taxa (global contig ids) + each taxon's contigs sorted by length
+  DevBuf<int64_t> contigLen, lens, start, csum; DevBuf<int32_t> contigTaxon; int32_t nContigs = 0, T = 0; bool set = false;
+  void upload(Runtime& rt, const int64_t* contig_len, const int32_t* contig_taxon, int32_t n_contigs, int32_t T_) {
+    std::vector<int64_t> st((size_t)T_ + 1, 0);
+    for (int32_t c = 0; c < n_contigs; c++) {
+      if (contig_taxon[c] < 0 || contig_taxon[c] >= T_) throw Error(-22, "contig taxon out of range");
+      st[(size_t)contig_taxon[c] + 1]++;
+    }
+    for (int32_t t = 0; t < T_; t++) st[(size_t)t + 1] += st[(size_t)t];
+    std::vector<int64_t> ln((size_t)n_contigs), fill(st.begin(), st.end() - 1), cs((size_t)n_contigs + 1, 0);
+    for (int32_t c = 0; c < n_contigs; c++) ln[(size_t)fill[(size_t)contig_taxon[c]]++] = contig_len[c];
+    for (int32_t t = 0; t < T_; t++) std::sort(ln.begin() + st[(size_t)t], ln.begin() + st[(size_t)t + 1]);
+    for (int32_t c = 0; c < n_contigs; c++) cs[(size_t)c + 1] = cs[(size_t)c] + ln[(size_t)c];
+    contigLen.ensure((size_t)n_contigs + 1); contigTaxon.ensure((size_t)n_contigs + 1); lens.ensure((size_t)n_contigs + 1);
+    start.ensure((size_t)T_ + 1); csum.ensure((size_t)n_contigs + 1);
+    h2d(rt, contigLen.p, contig_len, 8 * (size_t)n_contigs); h2d(rt, contigTaxon.p, contig_taxon, 4 * (size_t)n_contigs);
+    h2d(rt, lens.p, ln.data(), 8 * (size_t)n_contigs); h2d(rt, start.p, st.data(), 8 * ((size_t)T_ + 1)); h2d(rt, csum.p, cs.data(), 8 * ((size_t)n_contigs + 1));
+    rt.sync();
+    nContigs = n_contigs; T = T_; set = true;
+  }
+};
+
+struct Classifier {
+  Runtime& rt; Prims& pr;
+  MapTable tab; Taxonomy taxo;
+  DevBuf<float> id32; DevBuf<double> parsed, mapq, nloc, w, f, acc, post, llHist;
+  DevBuf<int32_t> head, mGrp, grpRead, grpLen, status, tax, fixList, bad, tmpI; DevBuf<uint32_t> keyA, keyB, permA, permB;
+  DevBuf<int64_t> gidx, grpOff, best; DevBuf<unsigned long long> cnt; DevBuf<EmState> st;
+  int64_t nGroups = 0; int32_t iters = 0; int64_t nFix = 0; double emMs = 0; int32_t lastT = 0;
+  std::function<void(double*, size_t)> allreduce;       // sum over ranks of a device buffer (NCCL or the host transport); empty = single rank
+  bool hostTransport = false;
+
+  Classifier(Runtime& r, Prims& p) : rt(r), pr(p) {}
+
+  static int group_size(int64_t M, int64_t groups) {
+#ifdef MM_HOST_EMU
+    (void)M; (void)groups; return 1;
+#else
+    const double avg = groups > 0 ? (double)M / (double)groups : 0;
+    return avg > 12 ? 32 : avg > 3 ? 8 : 4;
+#endif
+  }
+
+  // groups = runs of equal read index in mRead[0..n) (non-decreasing): grpOff, grpRead, mGrp; one host sync for the count
+  void build_groups(const int32_t* mRead, int64_t n) {
+    head.ensure((size_t)n + 2); gidx.ensure((size_t)n + 2); mGrp.ensure((size_t)n + 1);
+    foreach(rt, n + 1, GroupHeadFn{mRead, head.p, n});
+    pr.exclusive_sum<int32_t, int64_t>(head.p, gidx.p, n + 1);
+    d2h(rt, &nGroups, gidx.p + n, sizeof(int64_t));
+    grpOff.ensure((size_t)nGroups + 2); grpRead.ensure((size_t)nGroups + 1); grpLen.ensure((size_t)nGroups + 1);
+    foreach(rt, n + 1, GroupScatterFn{mRead, head.p, gidx.p, n, grpOff.p, grpRead.p, mGrp.p});
+  }
+
+  // nucIdentity + its 6-significant-digit round trip for n (shared, sketch) pairs on the device; the (rare) unsure ones through glibc
+  void identity(const int32_t* shared, const int32_t* sketch, int64_t n, int k) {
+    id32.ensure((size_t)n + 1); parsed.ensure((size_t)n + 1); cnt.ensure(2); fixList.ensure(4096);
+    dev_memset(rt, cnt.p, 0, sizeof(unsigned long long));
+    foreach(rt, n, IdentityFn{shared, sketch, k, id32.p, parsed.p, cnt.p, fixList.p, (int64_t)fixList.cap});
+  }
+  // after a host sync point: settle the flagged identities (count read by the caller together with its other scalars)
+  void identity_fixups(const int32_t* shared, const int32_t* sketch, int64_t n, int k, unsigned long long flagged);
+
+  template <int G>
+  void mapq_t(const double* idArr, double div, const int32_t* shared, const int32_t* sketch, int k) {
+    foreach(rt, round_up32(nGroups * G), MapqGroupFn<G>{idArr, div, shared, sketch, grpLen.p, grpOff.p, nGroups, k, mapq.p, status.p});
+  }
+  void run_mapq(const double* idArr, double div, const int32_t* shared, const int32_t* sketch, int64_t M, int k) {
+    mapq.ensure((size_t)M + 1); status.ensure((size_t)nGroups + 1);
+    const int G = group_size(M, nGroups);
+#ifdef MM_HOST_EMU
+    (void)G; mapq_t<1>(idArr, div, shared, sketch, k);
+#else
+    if (G == 32) mapq_t<32>(idArr, div, shared, sketch, k); else if (G == 8) mapq_t<8>(idArr, div, shared, sketch, k); else mapq_t<4>(idArr, div, shared, sketch, k);
+#endif
+  }
+
+  // EM over M mappings in nG groups (grpOffDev: nG + 1 offsets), weights in w.p, taxa in taxDev.  Leaves f, post, best on the device.
+  void run_em(const int32_t* taxDev, const int64_t* grpOffDev, int64_t nG, int64_t M, int32_t T, int32_t maxIter, int32_t llCap) {
+    f.ensure((size_t)T); acc.ensure((size_t)T + 1); post.ensure((size_t)M + 1); best.ensure((size_t)nG + 1); st.ensure(1);
+    llHist.ensure((size_t)(llCap > 0 ? llCap : 1));
+    foreach(rt, T, EmFillFn{f.p, 1.0 / (double)T});                       // fEM.h:491-495
+    dev_memset(rt, st.p, 0, sizeof(EmState));
+    lastT = T;
+    const int G = group_size(M, nG);
+    EmState hs; memset(&hs, 0, sizeof hs);
+    const int32_t HARD_CAP = 1000000;                                    // the reference has no cap (fEM.h:636); a diverging input must not hang the call
+    int check = hostTransport ? 1 : 4;
+    if (const char* e = getenv("MM_EM_CHECK")) { int v = atoi(e); if (v >= 1) check = v; }
+#ifndef MM_HOST_EMU
+    int copies = 0; size_t smem = 0; int grid = 1;
+    {
+      const size_t per = (size_t)T * sizeof(double);
+      if (per <= 48 * 1024) { copies = (int)((48 * 1024) / per); if (copies > 8) copies = 8; if (copies < 1) copies = 1; }
+      else if (per <= 200 * 1024) copies = 1;
+      smem = (size_t)copies * per;
+      int perSm = smem ? (int)((220 * 1024) / (smem + 1024)) : 8; if (perSm > 8) perSm = 8; if (perSm < 1) perSm = 1;
+      const int64_t need = (nG * G + 255) / 256;
+      grid = (int)std::min<int64_t>(std::max<int64_t>(need, 1), (int64_t)rt.sm_count * perSm);
+      if (smem > 48 * 1024) {
+        if (G == 32 && rt.first((const void*)em_round_kernel<32>)) MM_CUDA(cudaFuncSetAttribute(em_round_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (G == 8 && rt.first((const void*)em_round_kernel<8>)) MM_CUDA(cudaFuncSetAttribute(em_round_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (G == 4 && rt.first((const void*)em_round_kernel<4>)) MM_CUDA(cudaFuncSetAttribute(em_round_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      }
+    }
+#endif
+    {
+      StageTimer tm(rt, &emMs);
+      while (true) {
+        int burst = check;
+        if (maxIter > 0) burst = std::min(check, maxIter - hs.iters);
+        for (int i = 0; i < burst; i++) {
+          dev_memset(rt, acc.p, 0, sizeof(double) * ((size_t)T + 1));
+#ifdef MM_HOST_EMU
+          foreach(rt, nG, EmRoundSeqFn{taxDev, w.p, grpOffDev, f.p, acc.p, T, st.p});
+#else
+          if (G == 32) em_round_kernel<32><<<grid, 256, smem, rt.stream>>>(taxDev, w.p, grpOffDev, nG, f.p, acc.p, T, copies, st.p);
+          else if (G == 8) em_round_kernel<8><<<grid, 256, smem, rt.stream>>>(taxDev, w.p, grpOffDev, nG, f.p, acc.p, T, copies, st.p);
+          else em_round_kernel<4><<<grid, 256, smem, rt.stream>>>(taxDev, w.p, grpOffDev, nG, f.p, acc.p, T, copies, st.p);
+          MM_CUDA(cudaGetLastError());
+          rt.launches++;
+#endif
+          if (allreduce) allreduce(acc.p, (size_t)T + 1);                  // taxon sums + log-likelihood (slot T) over the ranks
+#ifdef MM_HOST_EMU
+          foreach(rt, 1, EmFinishSeqFn{acc.p, f.p, T, st.p, llHist.p, llCap, maxIter});
+#else
+          em_finish_kernel<<<1, 1024, 0, rt.stream>>>(acc.p, f.p, T, st.p, llHist.p, llCap, maxIter);
+          MM_CUDA(cudaGetLastError());
+          rt.launches++;
+#endif
+        }
+        d2h(rt, &hs, st.p, sizeof(EmState));                               // one small read per burst of rounds
+        if (hs.done || hs.iters >= HARD_CAP) break;
+      }
+      iters = hs.iters;
+      if (!hs.bad) {
+#ifdef MM_HOST_EMU
+        foreach(rt, nG, EmFinalGroupFn<1>{taxDev, w.p, grpOffDev, nG, f.p, post.p, best.p});
+#else
+        if (G == 32) foreach(rt, round_up32(nG * 32), EmFinalGroupFn<32>{taxDev, w.p, grpOffDev, nG, f.p, post.p, best.p});
+        else if (G == 8) foreach(rt, round_up32(nG * 8), EmFinalGroupFn<8>{taxDev, w.p, grpOffDev, nG, f.p, post.p, best.p});
+        else foreach(rt, round_up32(nG * 4), EmFinalGroupFn<4>{taxDev, w.p, grpOffDev, nG, f.p, post.p, best.p});
+#endif
+      }
+    }
+    if (hs.bad) throw Error(-22, "EM: a read's likelihood sum is not positive (all its mapping qualities are 0, or an nLoc is 0); the reference asserts here (fEM.h:357)");
+    if (!hs.done) throw Error(-34, "EM did not reach the reference's stopping rule within 1000000 rounds");
+  }
+};
+inline void Classifier::identity_fixups(const int32_t* shared, const int32_t* sketch, int64_t n, int k, unsigned long long flagged) {
+  nFix = (int64_t)flagged;
+  if (!flagged) return;
+  std::vector<int32_t> list;
+  if ((int64_t)flagged > (int64_t)fixList.cap) {      // more than the list holds (identities outside [10,100), e.g. a very low --pi): redo all on the host
+    list.resize((size_t)n); for (int64_t i = 0; i < n; i++) list[(size_t)i] = (int32_t)i;
+  } else { list.resize((size_t)flagged); d2h(rt, list.data(), fixList.p, 4 * (size_t)flagged); }
+  std::vector<int32_t> hs((size_t)n), hk((size_t)n);
+  if (list.size() == (size_t)n) { d2h(rt, hs.data(), shared, 4 * (size_t)n); d2h(rt, hk.data(), sketch, 4 * (size_t)n); }
+  for (size_t i = 0; i < list.size(); i++) {
+    const int64_t m = list[i];
+    int32_t a, b;
+    if (list.size() == (size_t)n) { a = hs[(size_t)m]; b = hk[(size_t)m]; }
+    else { d2h(rt, &a, shared + m, 4); d2h(rt, &b, sketch + m, 4); }
+    float id; stats::identity_only(a, b, k, &id);
+    const double x = (double)id; double pz;
+    if (x >= 10.0 && x < 99.99995) pz = rint(x * 1e4) / 1e4;
+    else { char buf[64]; snprintf(buf, sizeof buf, "%.6g", x); pz = strtod(buf, nullptr); }
+    h2d(rt, id32.p + m, &id, 4); h2d(rt, parsed.p + m, &pz, 8);
+    rt.sync();
+  }
+}
 
 }  // namespace mm

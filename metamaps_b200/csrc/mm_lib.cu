@@ -4,7 +4,7 @@
 //  that library is test infrastructure and is never loaded by the product.)
 #include "../../include/metamaps_b200.h"
 
-#include "mm_em.h"
+#include "mm_classify.h"
 #include "mm_index.h"
 #include "mm_map.h"
 #include "mm_mapq.h"
@@ -29,10 +29,9 @@ struct mm_ctx {
   int64_t last_launches = 0;
   // grow-only scratch of the mapq / EM / fetch entry points (cudaMalloc + cudaFree per call would cost more than the kernels)
   struct {
-    DevBuf<double> dId, dQ, dMq, dNl, dW, dWT, dF, dAcc, dRsum, dLog, dPost, dTot;
-    DevBuf<int32_t> dSh, dSk, dLen, dSt, dTax, dReadOf, dReadT, tmpA, tmpB;
-    DevBuf<int64_t> dOff, dBest;
-    DevBuf<uint32_t> dIota, dPerm, dTaxT;
+    DevBuf<double> dId, dMq, dNl;
+    DevBuf<int32_t> dSh, dSk, dLen, dSt, dTax, tmpA, tmpB;
+    DevBuf<int64_t> dOff;
   } scr;
   // double-buffered input staging (mm_stage_reads_async)
   struct Stage { DevBuf<uint8_t> asc; std::vector<int64_t> off; int32_t n = -1;
@@ -47,7 +46,8 @@ struct mm_ctx {
   // NCCL (multi-GPU EM), bound at run time
   void* comm = nullptr; int nRanks = 1, rank = 0;
   mm_allreduce_fn hostAllreduce = nullptr; void* hostAllreduceUser = nullptr; std::vector<double> hostBuf;
-  mm_ctx() : pr(rt), sk(rt, pr), mp(rt, pr, sk) {}
+  Classifier cls;
+  mm_ctx() : pr(rt), sk(rt, pr), mp(rt, pr, sk), cls(rt, pr) {}
 };
 struct mm_index {
   mm_ctx* ctx;
@@ -674,14 +674,16 @@ int mm_mapq_batch(mm_ctx* c, const double* identity, const int32_t* shared, cons
   if (!c || !read_off || n_reads < 0) throw Error(MM_EINVAL, "mm_mapq_batch: bad arguments");
   begin_call(c);
   int64_t M = read_off[n_reads];
-  auto& dId = c->scr.dId; auto& dQ = c->scr.dQ; auto& dSh = c->scr.dSh; auto& dSk = c->scr.dSk; auto& dLen = c->scr.dLen; auto& dSt = c->scr.dSt; auto& dOff = c->scr.dOff;
-  dId.ensure((size_t)M); dQ.ensure((size_t)M); dSh.ensure((size_t)M); dSk.ensure((size_t)M);
-  dLen.ensure((size_t)n_reads); dSt.ensure((size_t)n_reads); dOff.ensure((size_t)n_reads + 1);
+  Classifier& cl = c->cls;
+  auto& dId = c->scr.dId; auto& dSh = c->scr.dSh; auto& dSk = c->scr.dSk;
+  dId.ensure((size_t)M + 1); dSh.ensure((size_t)M + 1); dSk.ensure((size_t)M + 1);
+  cl.grpLen.ensure((size_t)n_reads + 1); cl.grpOff.ensure((size_t)n_reads + 2);
   h2d(c->rt, dId.p, identity, 8 * (size_t)M); h2d(c->rt, dSh.p, shared, 4 * (size_t)M); h2d(c->rt, dSk.p, sketch, 4 * (size_t)M);
-  h2d(c->rt, dLen.p, read_len, 4 * (size_t)n_reads); h2d(c->rt, dOff.p, read_off, 8 * ((size_t)n_reads + 1));
-  { StageTimer t(c->rt, &c->last_ms); foreach(c->rt, n_reads, MapqFn{dId.p, dSh.p, dSk.p, dLen.p, dOff.p, k, dQ.p, dSt.p}); }
-  d2h(c->rt, mapq, dQ.p, 8 * (size_t)M);
-  if (status) d2h(c->rt, status, dSt.p, 4 * (size_t)n_reads);
+  h2d(c->rt, cl.grpLen.p, read_len, 4 * (size_t)n_reads); h2d(c->rt, cl.grpOff.p, read_off, 8 * ((size_t)n_reads + 1));
+  cl.nGroups = n_reads;
+  { StageTimer t(c->rt, &c->last_ms); cl.run_mapq(dId.p, 1.0, dSh.p, dSk.p, M, k); }
+  d2h(c->rt, mapq, cl.mapq.p, 8 * (size_t)M);
+  if (status) d2h(c->rt, status, cl.status.p, 4 * (size_t)n_reads);
   end_call(c);
   MM_CATCH
 }
@@ -893,58 +895,203 @@ int mm_index_sync_threshold(mm_index* idx, int32_t* global_threshold, int64_t* g
 }
 
 // ------------------------------------------------------------------------------------------------ K7/K8
+static void bind_allreduce(mm_ctx* c) {
+  const bool multi = (c->comm && c->nRanks > 1) || c->hostAllreduce;
+  if (multi) c->cls.allreduce = [c](double* buf, size_t n) { allreduce_sum_f64(c, buf, n); };
+  else c->cls.allreduce = nullptr;
+  c->cls.hostTransport = !c->comm && c->hostAllreduce;
+}
 int mm_em_run(mm_ctx* c, const int32_t* taxon, const double* mapq, const double* nloc, const int64_t* read_off, int64_t n_reads,
               int32_t T, int32_t max_iter, double* f_out, double* posterior, int64_t* best, double* ll_hist, int32_t ll_cap, int32_t* n_iter) {
   MM_TRY
   if (!c || !read_off || n_reads < 0 || T < 1) throw Error(MM_EINVAL, "mm_em_run: bad arguments");
   begin_call(c);
-  Runtime& rt = c->rt; Prims& pr = c->pr;
+  Runtime& rt = c->rt; Classifier& cl = c->cls;
   int64_t M = read_off[n_reads];
-  if (M >= ((int64_t)1 << 32)) throw Error(MM_ERANGE, "more than 2^32 mappings on one rank: partition the reads");
-  auto& dTax = c->scr.dTax; auto& dReadOf = c->scr.dReadOf; auto& dReadT = c->scr.dReadT; auto& dMq = c->scr.dMq; auto& dNl = c->scr.dNl;
-  auto& dW = c->scr.dW; auto& dWT = c->scr.dWT; auto& dF = c->scr.dF; auto& dAcc = c->scr.dAcc; auto& dRsum = c->scr.dRsum; auto& dLog = c->scr.dLog;
-  auto& dPost = c->scr.dPost; auto& dTot = c->scr.dTot; auto& dOff = c->scr.dOff; auto& dBest = c->scr.dBest;
-  auto& dIota = c->scr.dIota; auto& dPerm = c->scr.dPerm; auto& dTaxT = c->scr.dTaxT;
-  dTax.ensure((size_t)M); dReadOf.ensure((size_t)M); dReadT.ensure((size_t)M); dMq.ensure((size_t)M); dNl.ensure((size_t)M);
-  dW.ensure((size_t)M); dWT.ensure((size_t)M); dIota.ensure((size_t)M); dPerm.ensure((size_t)M); dTaxT.ensure((size_t)M);
-  dF.ensure((size_t)T); dAcc.ensure((size_t)T + 1); dRsum.ensure((size_t)n_reads + 1); dLog.ensure((size_t)n_reads + 1);
-  dPost.ensure((size_t)M); dTot.ensure(2); dOff.ensure((size_t)n_reads + 1); dBest.ensure((size_t)n_reads + 1);
+  if (M >= ((int64_t)1 << 31)) throw Error(MM_ERANGE, "more than 2^31 mappings on one rank: partition the reads");
+  auto& dTax = c->scr.dTax; auto& dMq = c->scr.dMq; auto& dNl = c->scr.dNl; auto& dOff = c->scr.dOff;
+  dTax.ensure((size_t)M + 1); dMq.ensure((size_t)M + 1); dNl.ensure((size_t)M + 1); dOff.ensure((size_t)n_reads + 2); cl.w.ensure((size_t)M + 1);
   h2d(rt, dTax.p, taxon, 4 * (size_t)M); h2d(rt, dMq.p, mapq, 8 * (size_t)M); h2d(rt, dNl.p, nloc, 8 * (size_t)M);
   h2d(rt, dOff.p, read_off, 8 * ((size_t)n_reads + 1));
-  int iters = 0;
+  for (int64_t m = 0; m < M; m++) if (taxon[m] < 0 || taxon[m] >= T) throw Error(MM_EINVAL, "mm_em_run: taxon out of range");
+  bind_allreduce(c);
+  cl.emMs = 0;
+  foreach(rt, M, EmWeightFn{dMq.p, dNl.p, cl.w.p});
+  cl.run_em(dTax.p, dOff.p, n_reads, M, T, max_iter, ll_cap > 0 ? ll_cap : 0);
+  if (f_out) d2h(rt, f_out, cl.f.p, 8 * (size_t)T);
+  if (posterior) d2h(rt, posterior, cl.post.p, 8 * (size_t)M);
+  if (best) d2h(rt, best, cl.best.p, 8 * (size_t)n_reads);
+  if (ll_hist && ll_cap > 0) d2h(rt, ll_hist, cl.llHist.p, 8 * (size_t)std::min<int32_t>(cl.iters, ll_cap));
+  if (n_iter) *n_iter = cl.iters;
+  end_call(c);
+  c->last_ms += cl.emMs;
+  MM_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------ classify stage on the device
+struct ReadRangeFn {        // first mapping with read >= lo / >= hi in the read-sorted table
+  const int32_t* mRead; int64_t n; int32_t lo, hi; int64_t* out;
+  MM_HD void operator()(int64_t i) const {
+    const int32_t key = i == 0 ? lo : hi;
+    int64_t a = 0, b = n;
+    while (a < b) { const int64_t m = (a + b) >> 1; if (ldg(mRead + m) < key) a = m + 1; else b = m; }
+    out[i] = a;
+  }
+};
+// table -> sorted by read, stable (a read's mappings keep their part order = contig order)
+static void maptable_sort(mm_ctx* c, int32_t n_reads_hint) {
+  Classifier& cl = c->cls; MapTable& t = cl.tab; Runtime& rt = c->rt;
+  if (t.n <= 1) { t.sorted = true; return; }
+  cl.keyA.ensure((size_t)t.n); cl.keyB.ensure((size_t)t.n); cl.permA.ensure((size_t)t.n); cl.permB.ensure((size_t)t.n); cl.tmpI.ensure((size_t)t.n);
+  foreach(rt, t.n, IotaU32Fn{cl.permA.p});
+  int bits = 1; while (bits < 32 && ((int64_t)1 << bits) <= (int64_t)(n_reads_hint > 1 ? n_reads_hint : 2)) bits++;
+  c->pr.sort_pairs<uint32_t, uint32_t>((const uint32_t*)t.read.p, cl.keyB.p, cl.permA.p, cl.permB.p, t.n, bits);
+  DevBuf<int32_t>* cols[6] = {&t.read, &t.seq, &t.pos, &t.shared, &t.sketch, &t.strand};
+  for (auto* col : cols) {
+    foreach(rt, t.n, GatherI32Fn{cl.permB.p, col->p, cl.tmpI.p});
+    d2d(rt, col->p, cl.tmpI.p, 4 * (size_t)t.n);
+  }
+  t.sorted = true;
+}
+int mm_classify_setup(mm_ctx* c, const int64_t* contig_len, const int32_t* contig_taxon, int32_t n_contigs, int32_t T) {
+  MM_TRY
+  if (!c || !contig_len || !contig_taxon || n_contigs < 0 || T < 1) throw Error(MM_EINVAL, "mm_classify_setup: bad arguments");
+  begin_call(c);
+  c->cls.taxo.upload(c->rt, contig_len, contig_taxon, n_contigs, T);
+  MM_CATCH
+}
+int mm_classify_begin(mm_ctx* c) {
+  if (!c) { g_err = "null ctx"; return MM_EINVAL; }
+  c->cls.tab.n = 0; c->cls.tab.parts = 0; c->cls.tab.sorted = true;
+  return MM_OK;
+}
+int mm_classify_add_mappings(mm_ctx* c, int32_t first_contig_id, int64_t* n_total) {
+  MM_TRY
+  if (!c || first_contig_id < 0) throw Error(MM_EINVAL, "mm_classify_add_mappings: bad arguments");
+  Mapper& m = c->mp; MapTable& t = c->cls.tab; const int64_t nc = m.n_cand;
+  begin_call(c);
+  int64_t nm = 0;
+  auto& idx = c->scr.dOff;
+  if (nc > 0) {
+    idx.ensure((size_t)nc + 2);
+    dev_memset(c->rt, m.oAccept.p + nc, 0, sizeof(int32_t));
+    c->pr.exclusive_sum<int32_t, int64_t>(m.oAccept.p, idx.p, nc + 1);
+    d2h(c->rt, &nm, idx.p + nc, sizeof(int64_t));
+  }
+  if (t.n + nm >= ((int64_t)1 << 31)) throw Error(MM_ERANGE, "more than 2^31 mappings in one classify table: use smaller read batches");
+  if (nm > 0) {
+    t.reserve(c->rt, t.n + nm);
+    StageTimer tm(c->rt, &c->last_ms);
+    foreach(c->rt, nc, MapAppendFn{m.oAccept.p, idx.p, m.cRead.p, m.cSeq.p, m.oPos.p, m.oShared.p, m.oVotes.p, m.sOf.p, first_contig_id, t.n,
+                                   t.read.p, t.seq.p, t.pos.p, t.shared.p, t.sketch.p, t.strand.p});
+  }
+  if (t.parts > 0 && nm > 0 && t.n > 0) t.sorted = false;      // a second part: reads interleave, sort before use
+  t.n += nm; t.parts++;
+  end_call(c);
+  if (n_total) *n_total = t.n;
+  MM_CATCH
+}
+int mm_classify_exchange(mm_ctx* c, int32_t read_lo, int32_t read_hi, int64_t* n_total) {
+  MM_TRY
+  if (!c || read_lo < 0 || read_hi < read_lo) throw Error(MM_EINVAL, "mm_classify_exchange: bad arguments");
+  begin_call(c);
+  Runtime& rt = c->rt; Classifier& cl = c->cls; MapTable& t = cl.tab;
+  const int R = c->nRanks;
+  StageTimer tm(rt, &c->last_ms);
+  if (!t.sorted) maptable_sort(c, c->mp.n_reads);
+  // 1. every rank's count
+  DevBuf<uint32_t> one, all; one.ensure(1); all.ensure((size_t)R);
+  uint32_t mine = (uint32_t)t.n; h2d(rt, one.p, &mine, 4);
+  allgather_u32(c, one.p, all.p, 1);
+  std::vector<uint32_t> cnt((size_t)R); d2h(rt, cnt.data(), all.p, 4 * (size_t)R);
+  uint32_t cap = 0; int64_t tot = 0; for (int r = 0; r < R; r++) { cap = std::max(cap, cnt[(size_t)r]); tot += cnt[(size_t)r]; }
+  if (tot >= ((int64_t)1 << 31)) throw Error(MM_ERANGE, "more than 2^31 mappings in one exchange: use smaller read batches");
+  if (cap > 0) {
+    // 2. one padded slab of 6 columns per rank, all-gathered
+    DevBuf<uint32_t> send, recv; send.ensure((size_t)6 * cap); recv.ensure((size_t)R * 6 * cap);
+    DevBuf<int32_t>* cols[6] = {&t.read, &t.seq, &t.pos, &t.shared, &t.sketch, &t.strand};
+    dev_memset(rt, send.p, 0, 4 * (size_t)6 * cap);
+    for (int a = 0; a < 6; a++) d2d(rt, send.p + (size_t)a * cap, cols[a]->p, 4 * (size_t)t.n);
+    allgather_u32(c, send.p, recv.p, (size_t)6 * cap);
+    // 3. concatenate in rank (= shard) order, then one stable sort by read
+    t.n = 0; t.reserve(rt, tot);
+    int64_t pos = 0;
+    for (int r = 0; r < R; r++) {
+      for (int a = 0; a < 6; a++) d2d(rt, cols[a]->p + pos, recv.p + ((size_t)r * 6 + a) * cap, 4 * (size_t)cnt[(size_t)r]);
+      pos += cnt[(size_t)r];
+    }
+    t.n = tot; t.sorted = false;
+    maptable_sort(c, c->mp.n_reads);
+    // 4. this rank finalises the reads [read_lo, read_hi)
+    DevBuf<int64_t> rg; rg.ensure(2);
+    foreach(rt, 2, ReadRangeFn{t.read.p, t.n, read_lo, read_hi, rg.p});
+    int64_t h[2]; d2h(rt, h, rg.p, sizeof h);
+    const int64_t keep = h[1] - h[0];
+    if (h[0] > 0 && keep > 0) {
+      cl.tmpI.ensure((size_t)keep);
+      for (int a = 0; a < 6; a++) { d2d(rt, cl.tmpI.p, cols[a]->p + h[0], 4 * (size_t)keep); d2d(rt, cols[a]->p, cl.tmpI.p, 4 * (size_t)keep); }
+    }
+    t.n = keep;
+  }
+  tm.stop();
+  end_call(c);
+  if (n_total) *n_total = t.n;
+  MM_CATCH
+}
+int mm_classify_run(mm_ctx* c, int32_t em_max_iter, mm_classify_summary* out) {
+  MM_TRY
+  if (!c) throw Error(MM_EINVAL, "null ctx");
+  Classifier& cl = c->cls; MapTable& t = cl.tab; Runtime& rt = c->rt; Mapper& mp = c->mp;
+  if (!cl.taxo.set) throw Error(MM_EINVAL, "mm_classify_run: call mm_classify_setup first");
+  begin_call(c);
+  bind_allreduce(c);
+  const int64_t M = t.n; const int k = mp.lastK; const int32_t T = cl.taxo.T;
+  cl.emMs = 0; cl.iters = 0; cl.nGroups = 0; cl.nFix = 0;
   {
     StageTimer tm(rt, &c->last_ms);
-    foreach(rt, M, EmPrepFn{dMq.p, dNl.p, dOff.p, n_reads, dW.p, dReadOf.p, dIota.p});
-    int bits = 1; while (bits < 32 && ((int64_t)1 << bits) < T) bits++;
-    pr.sort_pairs<uint32_t, uint32_t>((const uint32_t*)dTax.p, dTaxT.p, dIota.p, dPerm.p, M, bits);
-    foreach(rt, M, EmPermuteFn{dPerm.p, dW.p, dReadOf.p, dWT.p, dReadT.p});
-    foreach(rt, T, EmFillFn{dF.p, 1.0 / (double)T});                       // fEM.h:491-495
-    double ll_last = 0; bool cont = true;
-    int64_t tiles = (M + EM_TILE - 1) / EM_TILE;
-    while (cont) {
-      foreach(rt, n_reads, EmReadSumFn{dTax.p, dW.p, dOff.p, dF.p, dRsum.p, dLog.p});
-      dev_memset(rt, dAcc.p, 0, sizeof(double) * ((size_t)T + 1));
-      if (M > 0) foreach(rt, tiles, EmTaxonSumFn{dTaxT.p, dWT.p, dReadT.p, dRsum.p, dAcc.p, M});
-      foreach(rt, T, EmScaleFn{dF.p, dAcc.p});
-      if (n_reads > 0) pr.reduce_sum<double>(dLog.p, dAcc.p + T, n_reads);   // ll rides in slot T of the all-reduce buffer
-      allreduce_sum_f64(c, dAcc.p, (size_t)T + 1);
-      pr.reduce_sum<double>(dAcc.p, dTot.p, T);
-      foreach(rt, T, EmNormFn{dAcc.p, dTot.p, dF.p});                       // fEM.h:606-615
-      double ll = 0; d2h(rt, &ll, dAcc.p + T, sizeof(double));
-      if (iters < ll_cap && ll_hist) ll_hist[iters] = ll;
-      if (iters > 0 && max_iter <= 0) {                                     // fEM.h:624-640
-        double diff = ll - ll_last, rel = ll / ll_last;
-        if (diff <= 1 && (1 - rel) < 0.0001) cont = false;
-      }
-      iters++; ll_last = ll;
-      if (max_iter > 0 && iters >= max_iter) cont = false;
-    }
-    foreach(rt, n_reads, EmFinalFn{dTax.p, dW.p, dOff.p, dF.p, dPost.p, dBest.p});
+    if (!t.sorted) maptable_sort(c, mp.n_reads);
+    if (M > 0) {
+      cl.identity(t.shared.p, t.sketch.p, M, k);
+      cl.build_groups(t.read.p, M);                                       // host sync: number of mapped reads
+      unsigned long long flagged = 0; d2h(rt, &flagged, cl.cnt.p, sizeof flagged);
+      cl.identity_fixups(t.shared.p, t.sketch.p, M, k, flagged);
+      foreach(rt, cl.nGroups, GroupLenFn{cl.grpRead.p, mp.readLen.p, cl.grpLen.p});
+      cl.run_mapq(cl.parsed.p, 100.0, t.shared.p, t.sketch.p, M, k);
+      cl.tax.ensure((size_t)M + 1); cl.nloc.ensure((size_t)M + 1); cl.w.ensure((size_t)M + 1); cl.bad.ensure(1);
+      dev_memset(rt, cl.bad.p, 0, sizeof(int32_t));
+      foreach(rt, M, NlocFn{t.seq.p, cl.mGrp.p, cl.grpOff.p, cl.grpLen.p, cl.mapq.p, cl.taxo.contigLen.p, cl.taxo.contigTaxon.p, cl.taxo.nContigs,
+                            cl.taxo.lens.p, cl.taxo.start.p, cl.taxo.csum.p, cl.tax.p, cl.nloc.p, cl.w.p, cl.bad.p});
+    } else { cl.grpOff.ensure(2); dev_memset(rt, cl.grpOff.p, 0, 16); cl.w.ensure(1); cl.tax.ensure(1); }
   }
-  if (f_out) d2h(rt, f_out, dF.p, 8 * (size_t)T);
-  if (posterior) d2h(rt, posterior, dPost.p, 8 * (size_t)M);
-  if (best) d2h(rt, best, dBest.p, 8 * (size_t)n_reads);
-  if (n_iter) *n_iter = iters;
+  if (M > 0) { int32_t bad = 0; d2h(rt, &bad, cl.bad.p, sizeof bad); if (bad) throw Error(MM_EINVAL, "mm_classify_run: contig id outside the taxonomy given to mm_classify_setup"); }
+  if (M > 0 || cl.allreduce) cl.run_em(cl.tax.p, cl.grpOff.p, cl.nGroups, M, T, em_max_iter, 4096);
+  end_call(c);
+  c->last_ms += cl.emMs;
+  if (out) { out->n_mappings = M; out->n_reads_mapped = cl.nGroups; out->em_iters = cl.iters; out->n_identity_fixups = (int32_t)cl.nFix; out->em_ms = cl.emMs; out->classify_ms = c->last_ms; }
+  MM_CATCH
+}
+int mm_classify_fetch(mm_ctx* c, int32_t* read_idx, int32_t* seq_id, int32_t* ref_start, int32_t* shared, int32_t* sketch, int32_t* strand,
+                      float* identity, double* parsed, double* mapq, int32_t* taxon, double* nloc, double* posterior, int64_t cap,
+                      int32_t* mapped_read, int64_t* read_off, int64_t* best, int32_t* status, double* f, double* ll_hist, int32_t ll_cap) {
+  MM_TRY
+  if (!c) throw Error(MM_EINVAL, "null ctx");
+  Classifier& cl = c->cls; MapTable& t = cl.tab; Runtime& rt = c->rt;
+  const size_t M = (size_t)t.n, G = (size_t)cl.nGroups;
+  if ((int64_t)M > cap && (read_idx || seq_id || ref_start || shared || sketch || strand || identity || parsed || mapq || taxon || nloc || posterior))
+    throw Error(MM_ERANGE, "mm_classify_fetch: capacity too small");
+  begin_call(c);
+#ifndef MM_HOST_EMU
+  auto get = [&](void* h, const void* d, size_t bytes) { if (h && bytes) MM_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, rt.stream)); };
+#else
+  auto get = [&](void* h, const void* d, size_t bytes) { if (h && bytes) memcpy(h, d, bytes); };
+#endif
+  get(read_idx, t.read.p, 4 * M); get(seq_id, t.seq.p, 4 * M); get(ref_start, t.pos.p, 4 * M); get(shared, t.shared.p, 4 * M);
+  get(sketch, t.sketch.p, 4 * M); get(strand, t.strand.p, 4 * M);
+  if (M) { get(identity, cl.id32.p, 4 * M); get(parsed, cl.parsed.p, 8 * M); get(mapq, cl.mapq.p, 8 * M); get(taxon, cl.tax.p, 4 * M); get(nloc, cl.nloc.p, 8 * M); }
+  if (M && cl.iters > 0) get(posterior, cl.post.p, 8 * M);
+  if (G) { get(mapped_read, cl.grpRead.p, 4 * G); get(status, cl.status.p, 4 * G); if (cl.iters > 0) get(best, cl.best.p, 8 * G); }
+  if (read_off) { if (G) get(read_off, cl.grpOff.p, 8 * (G + 1)); else read_off[0] = 0; }
+  if (cl.iters > 0 && cl.lastT > 0) { get(f, cl.f.p, 8 * (size_t)cl.lastT); if (ll_cap > 0) get(ll_hist, cl.llHist.p, 8 * (size_t)std::min<int32_t>(cl.iters, std::min<int32_t>(ll_cap, 4096))); }
   end_call(c);
   MM_CATCH
 }

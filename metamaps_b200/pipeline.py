@@ -44,37 +44,23 @@ def round_6_significant(x32: np.ndarray) -> np.ndarray:
     return out
 
 
-def classify_mappings(ctx: capi.Context, m: dict, n_reads: int, read_len: np.ndarray, *, k: int, contig_len: np.ndarray, contig_taxon: np.ndarray,
-                      n_taxa: int, em_max_iter: int = 0, wall: dict | None = None) -> dict:
-    """addMappingQualities (K6) -> nLoc (host) -> doEM (K7/K8) over the accepted mappings `m` (capi.fetch_mappings layout,
-    global contig ids, read order)."""
+def _classify_on_device(ctx: capi.Context, *, contig_len, contig_taxon, n_taxa: int, em_max_iter: int, wall: dict | None) -> dict:
+    """mm_classify_run + mm_classify_fetch over the context's mapping table -> the result layout of this module."""
     import time
+    t0 = time.perf_counter()
+    cs = ctx.classify_run(em_max_iter)
+    t1 = time.perf_counter()
+    gpu_ms, launches = ctx.last_timing()
+    r = ctx.classify_fetch(cs)
     t2 = time.perf_counter()
-    m_read = m["read"]
-    # reads with >= 1 mapping, in read order (the mappings file has no lines for the others)
-    mapped, read_off = capi.group_sorted(ctx.lib, m_read)
-    out = {"read": m_read, "seq": m["seq"], "pos": m["pos"], "shared": m["shared"], "sketch": m["sketch"],
-           "strand": m["strand"], "identity": m["identity"], "mapped_reads": mapped, "read_off": read_off}
-    if len(m_read) == 0 and ctx.n_ranks_hint <= 1:
-        out.update({"mapq": np.zeros(0), "em": None, "gpu_ms": 0.0, "launches": 0, "d2h_bytes": 0})
-        return out
-    t3 = time.perf_counter()
-    rl_mapped = np.ascontiguousarray(read_len[mapped], np.int32)
-    ident = np.divide(m["identity_parsed"], 100.0, out=capi._out("ident_frac", len(m_read), np.float64))    # column 10 / 100 (mapWrap.h:229)
-    mapq, status = ctx.mapq(ident, m["shared"], m["sketch"], rl_mapped, read_off, k)
-    t4 = time.perf_counter()
-    launches = ctx.last_timing()[1]; gpu_ms = ctx.last_timing()[0]
-    out["mapq"] = mapq; out["mapq_status"] = status
-    # fEM.h:324-348: possible mapping locations of the mapping's taxon for this read length
-    tax, nloc = capi.nloc_batch(ctx.lib, m["seq"], read_off, rl_mapped, contig_len, contig_taxon, n_taxa)
-    t5 = time.perf_counter()
-    em = ctx.em(tax, mapq, nloc, read_off, n_taxa, em_max_iter)
-    t6 = time.perf_counter()
     if wall is not None:
-        wall.update({"read_offsets": (t3 - t2) * 1e3, "mapq_call": (t4 - t3) * 1e3, "nloc": (t5 - t4) * 1e3, "em_call": (t6 - t5) * 1e3})
-    launches += ctx.last_timing()[1]; gpu_ms += ctx.last_timing()[0]
-    d2h = mapq.nbytes + status.nbytes + em["f"].nbytes + em["posterior"].nbytes + em["best"].nbytes
-    out.update({"taxon": tax, "nloc": nloc, "em": em, "gpu_ms": gpu_ms, "launches": launches, "d2h_bytes": int(d2h)})
+        wall.update({"classify_call": (t1 - t0) * 1e3, "classify_fetch": (t2 - t1) * 1e3})
+    em = None
+    if cs["em_iters"] > 0:
+        em = {"f": r["f"], "posterior": r["posterior"], "best": r["best"], "ll": r["ll"], "iters": cs["em_iters"]}
+    out = {k_: r[k_] for k_ in ("read", "seq", "pos", "shared", "sketch", "strand", "identity", "identity_parsed", "mapq", "taxon", "nloc",
+                                "mapped_reads", "read_off", "mapq_status")}
+    out.update({"em": em, "gpu_ms": gpu_ms, "launches": launches, "d2h_bytes": r["d2h_bytes"], "classify": cs})
     return out
 
 
@@ -83,89 +69,68 @@ def map_and_classify(ctx: capi.Context, index: capi.Index, *, reads=None, dev_pt
                      min_read_len: int = 1000, em_max_iter: int = 0, stats: dict | None = None, staged_slot: int | None = None):
     """One pass of the hot path over one batch of reads.  Returns per-mapping arrays + EM result.
 
-    mm_map_batch (K1,K3-K5) -> mm_map_fetch_mappings (accepted mappings compacted on the device, identities on the host
-    through glibc) -> mm_mapq_batch (K6) -> mm_nloc_batch (host) -> mm_em_run (K7/K8)."""
+    mm_map_batch (K1,K3-K5) -> mm_classify_add_mappings -> mm_classify_run (identity, K6, nLoc, K7/K8: everything stays in
+    HBM) -> mm_classify_fetch (one D2H of the finished arrays)."""
     import time
     t0 = time.perf_counter()
+    ctx.classify_setup(contig_len, contig_taxon, n_taxa)
     res = capi.map_reads(ctx, index, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets, fetch=False,
                          staged_slot=staged_slot)
     t1 = time.perf_counter()
     if stats is not None:
         stats["map"] = res["stats"]
-    n_reads = res["_n"]
-    m = capi.fetch_mappings(ctx, res["summary"]["n_mappings"])
-    t2 = time.perf_counter()
-    if read_len is None:
-        read_len = np.array([len(r) for r in reads], np.int32) if reads is not None else np.diff(offsets).astype(np.int32)
-    wall = {"map_call": (t1 - t0) * 1e3, "fetch_mappings": (t2 - t1) * 1e3}
-    out = classify_mappings(ctx, m, n_reads, read_len, k=index.k, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa,
-                            em_max_iter=em_max_iter, wall=wall)
-    if stats is not None:       # wall-clock split of one step (ms): the C-ABI calls and the glue between them
+    ctx.classify_begin()
+    ctx.classify_add(getattr(index, "first_contig", 0))
+    wall = {"map_call": (t1 - t0) * 1e3}
+    out = _classify_on_device(ctx, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa, em_max_iter=em_max_iter, wall=wall)
+    if stats is not None:       # wall-clock split of one step (ms): the C-ABI calls
         stats["wall_ms"] = wall
     out["summary"] = res["summary"]
-    out["gpu_ms"] += res["gpu_ms"]; out["launches"] += res["launches"]; out["d2h_bytes"] += m["d2h_bytes"]
+    out["gpu_ms"] += res["gpu_ms"]; out["launches"] += res["launches"]
     return out
-
-
-_MAPPING_KEYS = ("read", "seq", "pos", "shared", "sketch", "strand", "identity", "identity_parsed")
-
-
-def merge_shard_mappings(parts: list) -> dict:
-    """Mappings of the same reads against several contig-range shards (each in read order, global contig ids), given in
-    shard order -> one list in the reference's order: per read, the shards' mappings concatenated in shard order, which
-    is (seqId, wpos) order because shards are consecutive contig ranges (computeMap.hpp:352, mapWrap.h:128-132)."""
-    cat = {k_: np.concatenate([p[k_] for p in parts]) if parts else np.zeros(0) for k_ in _MAPPING_KEYS}
-    order = np.argsort(cat["read"], kind="stable")
-    return {k_: np.ascontiguousarray(v[order]) for k_, v in cat.items()}
 
 
 def map_and_classify_sharded(ctx: capi.Context, shards: list, *, reads=None, dev_ptr=None, host_ptr=None, offsets=None, read_len=None,
                              contig_len: np.ndarray, contig_taxon: np.ndarray, n_taxa: int, perc_identity: float = 80.0,
-                             min_read_len: int = 1000, em_max_iter: int = 0, exchange=None, read_range=None, stats: dict | None = None):
+                             min_read_len: int = 1000, em_max_iter: int = 0, read_range=None, stats: dict | None = None):
     """The same pass against a reference split into contig-range shards (capi.Index objects with .first_contig set).
 
-    Every shard maps ALL reads.  Single process: `shards` are walked one after the other (the --maxmemory analogue).
-    Multi-GPU: each rank passes its own shard(s) and `exchange`, a callable that all-gathers a picklable object over the
-    ranks and returns the list in rank order (e.g. torch.distributed.all_gather_object); `read_range = (lo, hi)` is the
-    block of reads this rank finalises (mapping quality needs a read's mappings from all shards, mapWrap.h:226-278); the
-    EM taxon sums are all-reduced inside mm_em_run."""
+    Every shard maps ALL reads; each map call's accepted mappings are appended to the device-resident table with global contig
+    ids (shard order = contig order, the reference's chunk order: mapWrap.h:128-132).  Single process: `shards` are walked one
+    after the other (the --maxmemory analogue).  Multi-GPU (the context has a communicator, `read_range = (lo, hi)`): each rank
+    passes its own shard(s); mm_classify_exchange all-gathers and merges the tables on the device and this rank finalises the
+    reads [lo, hi) (mapping quality needs a read's mappings from all shards, mapWrap.h:226-278); the EM taxon sums are
+    all-reduced inside mm_classify_run."""
     import time
-    gpu_ms = 0.0; launches = 0; d2h = 0; parts = []; summary = None
+    gpu_ms = 0.0; launches = 0; summary = None
     t0 = time.perf_counter()
+    ctx.classify_setup(contig_len, contig_taxon, n_taxa)
+    ctx.classify_begin()
+    n_all = 0
     for ix in shards:
         res = capi.map_reads(ctx, ix, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets, fetch=False)
         gpu_ms += res["gpu_ms"]; launches += res["launches"]
         if stats is not None:
             stats["map"] = res["stats"]
-        m = capi.fetch_mappings(ctx, res["summary"]["n_mappings"])
-        d2h += m.pop("d2h_bytes")
-        m["seq"] = m["seq"] + np.int32(getattr(ix, "first_contig", 0))
-        parts.append(m)
+        n_all = ctx.classify_add(getattr(ix, "first_contig", 0))
+        gpu_ms += ctx.last_timing()[0]; launches += ctx.last_timing()[1]
         if summary is None:
             summary = dict(res["summary"])
         else:
             for k_ in ("n_candidates", "n_mappings"):
                 summary[k_] += res["summary"][k_]
-        n_reads = res["_n"]
     t1 = time.perf_counter()
-    if exchange is not None:
-        parts = [p for rank_parts in exchange(parts) for p in rank_parts]
-    m = merge_shard_mappings(parts)
-    if read_range is not None:
-        lo, hi = read_range
-        keep = (m["read"] >= lo) & (m["read"] < hi)
-        m = {k_: np.ascontiguousarray(v[keep]) for k_, v in m.items()}
+    if read_range is not None and ctx.n_ranks_hint > 1:
+        ctx.classify_exchange(read_range[0], read_range[1])
+        gpu_ms += ctx.last_timing()[0]; launches += ctx.last_timing()[1]
     t2 = time.perf_counter()
-    if read_len is None:
-        read_len = np.array([len(r) for r in reads], np.int32) if reads is not None else np.diff(offsets).astype(np.int32)
     wall = {"map_calls": (t1 - t0) * 1e3, "exchange_merge": (t2 - t1) * 1e3}
-    out = classify_mappings(ctx, m, n_reads, read_len, k=shards[0].k, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa,
-                            em_max_iter=em_max_iter, wall=wall)
+    out = _classify_on_device(ctx, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa, em_max_iter=em_max_iter, wall=wall)
     if stats is not None:
         stats["wall_ms"] = wall
-    summary["n_mappings_all_shards"] = int(sum(len(p["read"]) for p in parts))
+    summary["n_mappings_this_rank_all_shards"] = int(n_all)
     out["summary"] = summary
-    out["gpu_ms"] += gpu_ms; out["launches"] += launches; out["d2h_bytes"] += d2h
+    out["gpu_ms"] += gpu_ms; out["launches"] += launches
     return out
 
 

@@ -305,7 +305,8 @@ def check_shard_walk_equals_full(ctx, contigs, reads, k, w, contig_taxon, contig
     for key in MAPPING_KEYS:
         assert np.array_equal(a[key], b[key]), key
     assert a["em"]["iters"] == b["em"]["iters"]
-    assert np.array_equal(a["em"]["f"], b["em"]["f"]) and np.array_equal(a["em"]["best"], b["em"]["best"])
+    # taxon sums are accumulated with atomics on the device: the order of the additions, hence the last bits, may differ
+    assert np.abs(a["em"]["f"] - b["em"]["f"]).max() <= 1e-12 and np.array_equal(a["em"]["best"], b["em"]["best"])
     return a
 
 

@@ -29,13 +29,9 @@ def main():
     ix = capi.Index(ctx, 16, w); ix.set_shard(c0, keep_counts=True); ix.add(contigs[c0:c1]); ix.finalize()
     thr, uniq = ix.sync_threshold()
 
-    def exchange(obj):
-        out = [None] * world
-        dist.all_gather_object(out, obj)
-        return out
     n = len(reads); lo, hi = rank * n // world, (rank + 1) * n // world
     res = pipeline.map_and_classify_sharded(ctx, [ix], reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=T,
-                                            exchange=exchange, read_range=(lo, hi))
+                                            read_range=(lo, hi))
     # the one-index run, on a second context without a communicator (its EM must not wait for the other ranks)
     ctx1 = capi.Context(local)
     full = common.build_index(ctx1, contigs, 16, w)

@@ -77,13 +77,9 @@ def _shard_worker(rank, world, port, tmp):
     local_thr = ix.stats()["freq_threshold"]
     thr, uniq = ix.sync_threshold()
 
-    def exchange(obj):
-        out = [None] * world
-        dist.all_gather_object(out, obj)
-        return out
     n = len(reads); lo, hi = rank * n // world, (rank + 1) * n // world
     res = pipeline.map_and_classify_sharded(ctx, [ix], reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=T,
-                                            exchange=exchange, read_range=(lo, hi))
+                                            read_range=(lo, hi))
     np.savez(os.path.join(tmp, f"shard{rank}.npz"), thr=thr, uniq=uniq, local_thr=local_thr, lo=lo, hi=hi, f=res["em"]["f"], iters=res["em"]["iters"],
              post=res["em"]["posterior"], **{k_: res[k_] for k_ in common.MAPPING_KEYS})
     dist.destroy_process_group()

@@ -331,6 +331,7 @@ def test_pinned_result_buffers(gpu_ctx, small_workload):
             b = pipeline.map_and_classify(gpu_ctx, ix, reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=len(taxa))
             for key in common.MAPPING_KEYS:
                 assert np.array_equal(a[key], b[key]), key
-            assert np.array_equal(fa, b["em"]["f"]) and np.array_equal(posta, b["em"]["posterior"])
+            # the EM taxon sums are atomics: their last bits depend on the order of the additions
+            assert np.abs(fa - b["em"]["f"]).max() <= 1e-12 and np.abs(posta - b["em"]["posterior"]).max() <= 1e-12
     finally:
         capi.use_pinned_results(False)
