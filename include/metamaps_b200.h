@@ -108,6 +108,10 @@ int mm_index_save(const mm_index* idx, const char* path);
 int mm_index_load(mm_ctx* ctx, const char* path, mm_index** out);
 /* k / w of an index (e.g. after mm_index_load), contig lengths in id order (n_contigs entries, may be NULL). */
 int mm_index_params(const mm_index* idx, int32_t* k, int32_t* w, int32_t* contig_len);
+/* Largest number of reads one mm_map_* call can take against this index: seed hits are sorted as ONE 64-bit key
+ * read | contig | position (computeMap.hpp:352's order in a single radix sort), so reads * contigs * longest contig must fit
+ * 64 bits; a host flushes its read batches below this (a larger batch fails with MM_ERANGE). */
+int mm_index_max_batch_reads(const mm_index* idx, int64_t* max_reads);
 /* minimizerIndex in (seqId,wpos) order, for parity tests. */
 int mm_index_fetch(const mm_index* idx, uint32_t* hash, int32_t* seq_id, int32_t* wpos, int32_t* strand);
 /* minimizerPosLookupIndex probe, for parity tests: count (0 = absent) of each hash. */
@@ -180,14 +184,16 @@ int mm_map_fetch_mappings(mm_ctx* ctx, int32_t* read_idx, int32_t* seq_id, int32
  *                              first_contig_id (0 for an unsharded index; the shard's first contig otherwise).  Shards must be
  *                              added in contig order: a read's lines are its mappings per chunk, in chunk order
  *                              (unifyFiles, mapWrap.h:128-132).
+ *   mm_classify_next_batch     several read batches in one table (a whole sample, one EM over it like `metamaps classify`): after
+ *                              a batch's mm_classify_add_mappings call(s); the next batch's reads are numbered after it
  *   mm_classify_exchange       contig-sharded multi-GPU only (collective over the context's communicator): all ranks mapped
  *                              the same reads against their own shard; the tables are all-gathered (ncclAllGather of padded
  *                              slabs) and merged on the device in shard (= rank) order; this rank keeps the reads
  *                              [read_lo, read_hi) and finalises them (mapping quality needs a read's mappings from all shards,
  *                              mapWrap.h:226-278).
  *   mm_classify_run            identity (float + its 6-digit text round trip, bit-identical to glibc's: see mm_classify.h),
- *                              mapq, nLoc, EM to the reference's stopping rule (em_max_iter <= 0) or for exactly em_max_iter
- *                              rounds; multi-rank contexts all-reduce the taxon sums every round.  Collective when n_ranks > 1.
+ *                              mapq, nLoc, EM to the reference's stopping rule (em_max_iter == 0), for exactly em_max_iter
+ *                              rounds (> 0), or no EM at all (< 0); multi-rank contexts all-reduce the taxon sums every round.  Collective when n_ranks > 1.
  *   mm_classify_fetch          any pointer may be NULL.  Per mapping (cap >= n_mappings): the arrays of mm_map_fetch_mappings
  *                              plus mapq (column 14), taxon, nloc, posterior; per mapped read (n_reads_mapped entries):
  *                              mapped_read = its index in the batch, read_off (+1 entry), best = index of its first maximal
@@ -203,6 +209,7 @@ typedef struct mm_classify_summary {
 int mm_classify_setup(mm_ctx* ctx, const int64_t* contig_len, const int32_t* contig_taxon, int32_t n_contigs, int32_t n_taxa);
 int mm_classify_begin(mm_ctx* ctx);
 int mm_classify_add_mappings(mm_ctx* ctx, int32_t first_contig_id, int64_t* n_total);
+int mm_classify_next_batch(mm_ctx* ctx);
 int mm_classify_exchange(mm_ctx* ctx, int32_t read_lo, int32_t read_hi, int64_t* n_total);
 int mm_classify_run(mm_ctx* ctx, int32_t em_max_iter, mm_classify_summary* out);
 int mm_classify_fetch(mm_ctx* ctx, int32_t* read_idx, int32_t* seq_id, int32_t* ref_start, int32_t* shared, int32_t* sketch, int32_t* strand,

@@ -54,6 +54,7 @@ SYMBOLS = {
     "mm_index_load": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "mm_index_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
     "mm_index_finalize": (C.c_int, [C.c_void_p]),
+    "mm_index_max_batch_reads": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "mm_index_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "mm_index_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mm_index_lookup": (C.c_int, [C.c_void_p, _u32p, C.c_int64, _i32p]),
@@ -78,6 +79,7 @@ SYMBOLS = {
     "mm_classify_setup": (C.c_int, [C.c_void_p, _i64p, _i32p, C.c_int32, C.c_int32]),
     "mm_classify_begin": (C.c_int, [C.c_void_p]),
     "mm_classify_add_mappings": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
+    "mm_classify_next_batch": (C.c_int, [C.c_void_p]),
     "mm_classify_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "mm_classify_run": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(ClassifySummary)]),
     "mm_classify_fetch": (C.c_int, [C.c_void_p] + [C.c_void_p] * 12 + [C.c_int64] + [C.c_void_p] * 6 + [C.c_int32]),
@@ -211,6 +213,10 @@ class Context:
         self._check(self.lib.mm_classify_add_mappings(self.h, int(first_contig_id), C.byref(n)))
         return n.value
 
+    def classify_next_batch(self):
+        """The next map call's reads are numbered after the ones already in the table (several batches, one EM)."""
+        self._check(self.lib.mm_classify_next_batch(self.h))
+
     def classify_exchange(self, read_lo: int, read_hi: int) -> int:
         """Collective (contig-sharded ranks): all-gather + merge the tables, keep the reads [read_lo, read_hi)."""
         n = C.c_int64()
@@ -330,6 +336,11 @@ class Index:
         t = C.c_int32(); u = C.c_int64()
         self.ctx._check(self.lib.mm_index_sync_threshold(self.h, C.byref(t), C.byref(u)))
         return t.value, u.value
+
+    def max_batch_reads(self) -> int:
+        n = C.c_int64()
+        self.ctx._check(self.lib.mm_index_max_batch_reads(self.h, C.byref(n)))
+        return n.value
 
     def stats(self):
         a = C.c_int64(); b = C.c_int64(); c = C.c_int32(); d = C.c_int32(); e = C.c_int64()

@@ -259,10 +259,13 @@ static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& m
       }
       buf.clear(); off.assign(1, 0); names.clear();
     };
+    // batches stay below what the index's 64-bit hit key can number (many / chromosome-scale contigs leave fewer read bits)
+    int64_t maxReads = 1 << 20; ck(mm_index_max_batch_reads(idx, &maxReads), "mm_index_max_batch_reads");
+    if (maxReads > (1 << 20)) maxReads = 1 << 20;
     long len;
     while ((len = rd.read()) >= 0) {
       names.push_back(rd.name); buf += rd.seq; off.push_back((int64_t)buf.size());
-      if (buf.size() >= ((size_t)512 << 20) || names.size() >= (1u << 20)) flush();
+      if (buf.size() >= ((size_t)512 << 20) || (int64_t)names.size() >= maxReads) flush();
     }
     flush();
     out.close(); metaLengths.close();

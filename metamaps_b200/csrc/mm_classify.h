@@ -88,12 +88,12 @@ struct MapTable {
 // candidate -> mapping compaction (the lines of reportReadMappings with --all, computeMap.hpp:546-588)
 struct MapAppendFn {
   const int32_t* oAccept; const int64_t* accIdx; const int32_t* cRead; const int32_t* cSeq; const int32_t* oPos; const int32_t* oShared;
-  const int32_t* oVotes; const int32_t* sOf; int32_t seqBase; int64_t base;
+  const int32_t* oVotes; const int32_t* sOf; int32_t seqBase; int32_t readBase; int64_t base;
   int32_t* mRead; int32_t* mSeq; int32_t* mPos; int32_t* mShared; int32_t* mSketch; int32_t* mStrand;
   MM_HD void operator()(int64_t c) const {
     if (!ldg(oAccept + c)) return;
     const int64_t d = base + ldg(accIdx + c); const int32_t r = ldg(cRead + c);
-    mRead[d] = r; mSeq[d] = ldg(cSeq + c) + seqBase; mPos[d] = ldg(oPos + c); mShared[d] = ldg(oShared + c); mSketch[d] = ldg(sOf + r);
+    mRead[d] = r + readBase; mSeq[d] = ldg(cSeq + c) + seqBase; mPos[d] = ldg(oPos + c); mShared[d] = ldg(oShared + c); mSketch[d] = ldg(sOf + r);
     mStrand[d] = ldg(oVotes + c) > 0 ? 1 : -1;                         // computeMap.hpp:438
   }
 };
@@ -109,7 +109,9 @@ struct IotaU32Fn { uint32_t* a; MM_HD void operator()(int64_t i) const { a[i] = 
 // closed form.  So the arrays are what the reference's files hold, bit for bit, without a host pass over the batch.
 struct IdentityFn {
   const int32_t* shared; const int32_t* sketch; int k; float* identity; double* parsed; unsigned long long* nFix; int32_t* fixList; int64_t fixCap;
+  const int32_t* mask;       // optional: entries with mask[m] == 0 are skipped (identity 0)
   MM_HD void operator()(int64_t m) const {
+    if (mask && !ldg(mask + m)) { identity[m] = 0; parsed[m] = 0; return; }
     const int32_t sh = ldg(shared + m), s = ldg(sketch + m);
     const float j = (float)(1.0 * sh / s);
     float md; bool unsure = false;
@@ -377,6 +379,8 @@ struct Classifier {
   DevBuf<int32_t> head, mGrp, grpRead, grpLen, status, tax, fixList, bad, tmpI; DevBuf<uint32_t> keyA, keyB, permA, permB;
   DevBuf<int64_t> gidx, grpOff, best; DevBuf<unsigned long long> cnt; DevBuf<EmState> st;
   int64_t nGroups = 0; int32_t iters = 0; int64_t nFix = 0; double emMs = 0; int32_t lastT = 0;
+  // several read batches in one table (mm_classify_next_batch): read indices are readBase + index in the batch
+  DevBuf<int32_t> readLenAll; int64_t readBase = 0, readsSeen = 0;
   std::function<void(double*, size_t)> allreduce;       // sum over ranks of a device buffer (NCCL or the host transport); empty = single rank
   bool hostTransport = false;
 
@@ -402,13 +406,13 @@ struct Classifier {
   }
 
   // nucIdentity + its 6-significant-digit round trip for n (shared, sketch) pairs on the device; the (rare) unsure ones through glibc
-  void identity(const int32_t* shared, const int32_t* sketch, int64_t n, int k) {
+  void identity(const int32_t* shared, const int32_t* sketch, int64_t n, int k, const int32_t* mask = nullptr) {
     id32.ensure((size_t)n + 1); parsed.ensure((size_t)n + 1); cnt.ensure(2); fixList.ensure(4096);
     dev_memset(rt, cnt.p, 0, sizeof(unsigned long long));
-    foreach(rt, n, IdentityFn{shared, sketch, k, id32.p, parsed.p, cnt.p, fixList.p, (int64_t)fixList.cap});
+    foreach(rt, n, IdentityFn{shared, sketch, k, id32.p, parsed.p, cnt.p, fixList.p, (int64_t)fixList.cap, mask});
   }
   // after a host sync point: settle the flagged identities (count read by the caller together with its other scalars)
-  void identity_fixups(const int32_t* shared, const int32_t* sketch, int64_t n, int k, unsigned long long flagged);
+  void identity_fixups(const int32_t* shared, const int32_t* sketch, int64_t n, int k, unsigned long long flagged, const int32_t* mask = nullptr);
 
   template <int G>
   void mapq_t(const double* idArr, double div, const int32_t* shared, const int32_t* sketch, int k) {
@@ -496,20 +500,33 @@ struct Classifier {
     if (!hs.done) throw Error(-34, "EM did not reach the reference's stopping rule within 1000000 rounds");
   }
 };
-inline void Classifier::identity_fixups(const int32_t* shared, const int32_t* sketch, int64_t n, int k, unsigned long long flagged) {
+inline void Classifier::identity_fixups(const int32_t* shared, const int32_t* sketch, int64_t n, int k, unsigned long long flagged, const int32_t* mask) {
   nFix = (int64_t)flagged;
   if (!flagged) return;
   std::vector<int32_t> list;
   if ((int64_t)flagged > (int64_t)fixList.cap) {      // more than the list holds (identities outside [10,100), e.g. a very low --pi): redo all on the host
-    list.resize((size_t)n); for (int64_t i = 0; i < n; i++) list[(size_t)i] = (int32_t)i;
-  } else { list.resize((size_t)flagged); d2h(rt, list.data(), fixList.p, 4 * (size_t)flagged); }
-  std::vector<int32_t> hs((size_t)n), hk((size_t)n);
-  if (list.size() == (size_t)n) { d2h(rt, hs.data(), shared, 4 * (size_t)n); d2h(rt, hk.data(), sketch, 4 * (size_t)n); }
+    std::vector<int32_t> hm;
+    if (mask) { hm.resize((size_t)n); d2h(rt, hm.data(), mask, 4 * (size_t)n); }
+    list.reserve((size_t)n);
+    for (int64_t i = 0; i < n; i++) if (!mask || hm[(size_t)i]) list.push_back((int32_t)i);
+    std::vector<int32_t> hs((size_t)n), hk((size_t)n);
+    d2h(rt, hs.data(), shared, 4 * (size_t)n); d2h(rt, hk.data(), sketch, 4 * (size_t)n);
+    std::vector<float> hid((size_t)n, 0.f); std::vector<double> hp((size_t)n, 0.0);
+    for (int32_t m : list) {
+      float id; stats::identity_only(hs[(size_t)m], hk[(size_t)m], k, &id);
+      const double x = (double)id; double pz;
+      if (x >= 10.0 && x < 99.99995) pz = rint(x * 1e4) / 1e4;
+      else { char buf[64]; snprintf(buf, sizeof buf, "%.6g", x); pz = strtod(buf, nullptr); }
+      hid[(size_t)m] = id; hp[(size_t)m] = pz;
+    }
+    h2d(rt, id32.p, hid.data(), 4 * (size_t)n); h2d(rt, parsed.p, hp.data(), 8 * (size_t)n); rt.sync();
+    return;
+  }
+  list.resize((size_t)flagged); d2h(rt, list.data(), fixList.p, 4 * (size_t)flagged);
   for (size_t i = 0; i < list.size(); i++) {
     const int64_t m = list[i];
     int32_t a, b;
-    if (list.size() == (size_t)n) { a = hs[(size_t)m]; b = hk[(size_t)m]; }
-    else { d2h(rt, &a, shared + m, 4); d2h(rt, &b, sketch + m, 4); }
+    d2h(rt, &a, shared + m, 4); d2h(rt, &b, sketch + m, 4);
     float id; stats::identity_only(a, b, k, &id);
     const double x = (double)id; double pz;
     if (x >= 10.0 && x < 99.99995) pz = rint(x * 1e4) / 1e4;

@@ -344,6 +344,13 @@ int mm_index_params(const mm_index* idx, int32_t* k, int32_t* w, int32_t* contig
   if (contig_len) for (int32_t i = 0; i < idx->ix.n_contigs; i++) contig_len[i] = idx->ix.h_contigLen[(size_t)i];
   return MM_OK;
 }
+int mm_index_max_batch_reads(const mm_index* idx, int64_t* max_reads) {
+  if (!idx || !max_reads) { g_err = "mm_index_max_batch_reads: bad arguments"; return MM_EINVAL; }
+  const HitKeyLayout lay = hit_key_layout(idx->ix);
+  const int bits = 64 - lay.seqBits - lay.wsBits;
+  *max_reads = bits >= 31 ? (int64_t)0x7fffffff : (bits < 1 ? 1 : ((int64_t)1 << bits));
+  return MM_OK;
+}
 int mm_index_lookup(const mm_index* idx, const uint32_t* hashes, int64_t n, int32_t* counts) {
   MM_TRY
   if (!idx || !idx->ix.finalized) throw Error(MM_EINVAL, "index not finalized");
@@ -375,6 +382,33 @@ static void check_map_args(mm_ctx* c, const mm_index* idx, const mm_map_params* 
 static void fill_summary(mm_map_summary* out, const int64_t* s) {
   if (out) { out->n_reads = s[0]; out->n_too_short = s[1]; out->n_candidates = s[2]; out->n_mappings = s[3]; out->n_reads_mapped = s[4]; out->total_bases_mapped_reads = s[5]; }
 }
+// --all absent: keep, per read, the mappings with identity >= best - 1.0 (reportReadMappings, computeMap.hpp:551-563); the
+// others leave the accepted set, so every consumer (mm_map_fetch_*, the classify stage) sees what the reference would print
+struct CandSketchFn { const int32_t* cRead; const int32_t* sOf; int32_t* out; MM_HD void operator()(int64_t c) const { out[c] = ldg(sOf + ldg(cRead + c)); } };
+struct BestFilterFn {
+  const int64_t* candOff; const float* identity; int32_t* oAccept;
+  MM_HD void operator()(int64_t r) const {
+    const int64_t b = ldg(candOff + r), e = ldg(candOff + r + 1);
+    float best = 0;
+    for (int64_t x = b; x < e; x++) if (oAccept[x] && ldg(identity + x) > best) best = ldg(identity + x);
+    for (int64_t x = b; x < e; x++) if (oAccept[x] && !(ldg(identity + x) >= best - 1.0)) oAccept[x] = 0;
+  }
+};
+static void apply_best_filter(mm_ctx* c, int64_t* s /*summary[6]*/) {
+  Mapper& m = c->mp; Classifier& cl = c->cls; Runtime& rt = c->rt;
+  const int64_t nc = m.n_cand;
+  if (nc <= 0) return;
+  auto& sk = c->scr.tmpA; sk.ensure((size_t)nc + 1);
+  foreach(rt, nc, CandSketchFn{m.cRead.p, m.sOf.p, sk.p});
+  cl.identity(m.oShared.p, sk.p, nc, m.lastK, m.oAccept.p);
+  unsigned long long flagged = 0; d2h(rt, &flagged, cl.cnt.p, sizeof flagged);
+  cl.identity_fixups(m.oShared.p, sk.p, nc, m.lastK, flagged, m.oAccept.p);
+  foreach(rt, m.n_reads, BestFilterFn{m.candOff.p, cl.id32.p, m.oAccept.p});
+  m.red.ensure(2);
+  c->pr.reduce_sum<int32_t>(m.oAccept.p, m.red.p, nc);
+  int32_t h = 0; d2h(rt, &h, m.red.p, sizeof h);
+  s[3] = h; m.st.counters[4] = h;
+}
 static int map_impl(mm_ctx* c, const mm_index* idx, const char* reads, const void* dev, const int64_t* offsets, int32_t n,
                     const mm_map_params* p, mm_map_summary* out) {
   MM_TRY
@@ -383,7 +417,7 @@ static int map_impl(mm_ctx* c, const mm_index* idx, const char* reads, const voi
   begin_call(c);
   c->sk.load(c->mp.batch, reads, dev, offsets, n);
   int64_t s[6];
-  { StageTimer t(c->rt, &c->last_ms); c->mp.run(idx->ix, c->mp.batch, p->perc_identity, p->min_read_len, s); }
+  { StageTimer t(c->rt, &c->last_ms); c->mp.run(idx->ix, c->mp.batch, p->perc_identity, p->min_read_len, s); if (!p->report_all) apply_best_filter(c, s); }
   end_call(c);
   fill_summary(out, s);
   MM_CATCH
@@ -471,7 +505,7 @@ int mm_map_batch_staged(mm_ctx* c, const mm_index* idx, int slot, const mm_map_p
     begin_call(c);
     c->sk.finish_pack(st.batch, st.hostAsc);                 // on the main stream, after the event
     int64_t s[6];
-    { StageTimer t(c->rt, &c->last_ms); c->mp.run(idx->ix, st.batch, p->perc_identity, p->min_read_len, s); }
+    { StageTimer t(c->rt, &c->last_ms); c->mp.run(idx->ix, st.batch, p->perc_identity, p->min_read_len, s); if (!p->report_all) apply_best_filter(c, s); }
     end_call(c);
     fill_summary(out, s);
     MM_CATCH
@@ -962,7 +996,12 @@ int mm_classify_setup(mm_ctx* c, const int64_t* contig_len, const int32_t* conti
 }
 int mm_classify_begin(mm_ctx* c) {
   if (!c) { g_err = "null ctx"; return MM_EINVAL; }
-  c->cls.tab.n = 0; c->cls.tab.parts = 0; c->cls.tab.sorted = true;
+  c->cls.tab.n = 0; c->cls.tab.parts = 0; c->cls.tab.sorted = true; c->cls.readBase = 0; c->cls.readsSeen = 0;
+  return MM_OK;
+}
+int mm_classify_next_batch(mm_ctx* c) {
+  if (!c) { g_err = "null ctx"; return MM_EINVAL; }
+  c->cls.readBase = c->cls.readsSeen; c->cls.tab.parts = 0;
   return MM_OK;
 }
 int mm_classify_add_mappings(mm_ctx* c, int32_t first_contig_id, int64_t* n_total) {
@@ -979,10 +1018,16 @@ int mm_classify_add_mappings(mm_ctx* c, int32_t first_contig_id, int64_t* n_tota
     d2h(c->rt, &nm, idx.p + nc, sizeof(int64_t));
   }
   if (t.n + nm >= ((int64_t)1 << 31)) throw Error(MM_ERANGE, "more than 2^31 mappings in one classify table: use smaller read batches");
+  Classifier& cl = c->cls;
+  if (cl.readBase + m.n_reads >= ((int64_t)1 << 31)) throw Error(MM_ERANGE, "more than 2^31 reads in one classify table");
+  // the batch's read lengths, at its place in the table's read numbering
+  cl.readLenAll.grow(c->rt, (size_t)(cl.readBase + m.n_reads) + 1, (size_t)cl.readsSeen);
+  d2d(c->rt, cl.readLenAll.p + cl.readBase, m.readLen.p, 4 * (size_t)m.n_reads);
+  cl.readsSeen = std::max<int64_t>(cl.readsSeen, cl.readBase + m.n_reads);
   if (nm > 0) {
     t.reserve(c->rt, t.n + nm);
     StageTimer tm(c->rt, &c->last_ms);
-    foreach(c->rt, nc, MapAppendFn{m.oAccept.p, idx.p, m.cRead.p, m.cSeq.p, m.oPos.p, m.oShared.p, m.oVotes.p, m.sOf.p, first_contig_id, t.n,
+    foreach(c->rt, nc, MapAppendFn{m.oAccept.p, idx.p, m.cRead.p, m.cSeq.p, m.oPos.p, m.oShared.p, m.oVotes.p, m.sOf.p, first_contig_id, (int32_t)cl.readBase, t.n,
                                    t.read.p, t.seq.p, t.pos.p, t.shared.p, t.sketch.p, t.strand.p});
   }
   if (t.parts > 0 && nm > 0 && t.n > 0) t.sorted = false;      // a second part: reads interleave, sort before use
@@ -998,7 +1043,7 @@ int mm_classify_exchange(mm_ctx* c, int32_t read_lo, int32_t read_hi, int64_t* n
   Runtime& rt = c->rt; Classifier& cl = c->cls; MapTable& t = cl.tab;
   const int R = c->nRanks;
   StageTimer tm(rt, &c->last_ms);
-  if (!t.sorted) maptable_sort(c, c->mp.n_reads);
+  if (!t.sorted) maptable_sort(c, (int32_t)cl.readsSeen);
   // 1. every rank's count
   DevBuf<uint32_t> one, all; one.ensure(1); all.ensure((size_t)R);
   uint32_t mine = (uint32_t)t.n; h2d(rt, one.p, &mine, 4);
@@ -1021,7 +1066,7 @@ int mm_classify_exchange(mm_ctx* c, int32_t read_lo, int32_t read_hi, int64_t* n
       pos += cnt[(size_t)r];
     }
     t.n = tot; t.sorted = false;
-    maptable_sort(c, c->mp.n_reads);
+    maptable_sort(c, (int32_t)cl.readsSeen);
     // 4. this rank finalises the reads [read_lo, read_hi)
     DevBuf<int64_t> rg; rg.ensure(2);
     foreach(rt, 2, ReadRangeFn{t.read.p, t.n, read_lo, read_hi, rg.p});
@@ -1049,13 +1094,13 @@ int mm_classify_run(mm_ctx* c, int32_t em_max_iter, mm_classify_summary* out) {
   cl.emMs = 0; cl.iters = 0; cl.nGroups = 0; cl.nFix = 0;
   {
     StageTimer tm(rt, &c->last_ms);
-    if (!t.sorted) maptable_sort(c, mp.n_reads);
+    if (!t.sorted) maptable_sort(c, (int32_t)cl.readsSeen);
     if (M > 0) {
       cl.identity(t.shared.p, t.sketch.p, M, k);
       cl.build_groups(t.read.p, M);                                       // host sync: number of mapped reads
       unsigned long long flagged = 0; d2h(rt, &flagged, cl.cnt.p, sizeof flagged);
       cl.identity_fixups(t.shared.p, t.sketch.p, M, k, flagged);
-      foreach(rt, cl.nGroups, GroupLenFn{cl.grpRead.p, mp.readLen.p, cl.grpLen.p});
+      foreach(rt, cl.nGroups, GroupLenFn{cl.grpRead.p, cl.readLenAll.p, cl.grpLen.p});
       cl.run_mapq(cl.parsed.p, 100.0, t.shared.p, t.sketch.p, M, k);
       cl.tax.ensure((size_t)M + 1); cl.nloc.ensure((size_t)M + 1); cl.w.ensure((size_t)M + 1); cl.bad.ensure(1);
       dev_memset(rt, cl.bad.p, 0, sizeof(int32_t));
@@ -1064,7 +1109,7 @@ int mm_classify_run(mm_ctx* c, int32_t em_max_iter, mm_classify_summary* out) {
     } else { cl.grpOff.ensure(2); dev_memset(rt, cl.grpOff.p, 0, 16); cl.w.ensure(1); cl.tax.ensure(1); }
   }
   if (M > 0) { int32_t bad = 0; d2h(rt, &bad, cl.bad.p, sizeof bad); if (bad) throw Error(MM_EINVAL, "mm_classify_run: contig id outside the taxonomy given to mm_classify_setup"); }
-  if (M > 0 || cl.allreduce) cl.run_em(cl.tax.p, cl.grpOff.p, cl.nGroups, M, T, em_max_iter, 4096);
+  if (em_max_iter >= 0 && (M > 0 || cl.allreduce)) cl.run_em(cl.tax.p, cl.grpOff.p, cl.nGroups, M, T, em_max_iter, 4096);
   end_call(c);
   c->last_ms += cl.emMs;
   if (out) { out->n_mappings = M; out->n_reads_mapped = cl.nGroups; out->em_iters = cl.iters; out->n_identity_fixups = (int32_t)cl.nFix; out->em_ms = cl.emMs; out->classify_ms = c->last_ms; }

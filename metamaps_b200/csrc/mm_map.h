@@ -289,6 +289,13 @@ __global__ void __launch_bounds__(256) l1_probe_tma_kernel(const Slot* table, ui
 // single radix sort over the used bits orders them per read by (seqId, wpos, strand) -- the order std::sort gives
 // the reference (computeMap.hpp:352).
 struct HitKeyLayout { int seqBits, wsBits; };
+inline HitKeyLayout hit_key_layout(const Index& ix) {
+  HitKeyLayout lay; lay.seqBits = 1; lay.wsBits = 2;
+  int64_t nc_ = ix.n_contigs > 1 ? ix.n_contigs : 2; while (((int64_t)1 << lay.seqBits) < nc_) lay.seqBits++;
+  int64_t ml = 2; for (int32_t l : ix.h_contigLen) if (l > ml) ml = l;
+  while (((int64_t)1 << (lay.wsBits - 1)) < ml) lay.wsBits++;
+  return lay;
+}
 struct GatherHitsFn {
   const int32_t* hitCnt; const int64_t* hitStart; const int64_t* hitOff; const int32_t* qRead; const uint64_t* posKey; uint64_t* hits; HitKeyLayout lay;
   MM_HD void operator()(int64_t i) const {
@@ -1543,10 +1550,7 @@ struct Mapper {
     }
     // ---- K4: probe, gather, sort, candidate regions
     candOff.ensure((size_t)n_reads + 2); candCnt.ensure((size_t)n_reads + 2);
-    HitKeyLayout lay; lay.seqBits = 1; lay.wsBits = 2;
-    { int64_t nc_ = ix.n_contigs > 1 ? ix.n_contigs : 2; while (((int64_t)1 << lay.seqBits) < nc_) lay.seqBits++;
-      int64_t ml = 2; for (int32_t l : ix.h_contigLen) if (l > ml) ml = l;
-      while (((int64_t)1 << (lay.wsBits - 1)) < ml) lay.wsBits++; }
+    const HitKeyLayout lay = hit_key_layout(ix);
     int readBits = 1; while (((int64_t)1 << readBits) < (n_reads > 1 ? n_reads : 2)) readBits++;
     if (readBits + lay.seqBits + lay.wsBits > 64) throw Error(-34, "read batch too large for the 64-bit hit key: map fewer reads per call");
     HitDecode dec{lay};

@@ -388,3 +388,53 @@ def check_api_errors(ctx, tmp_path):
     with pytest.raises(capi.MMError):
         capi.nloc_batch(lib, np.array([0], np.int32), np.array([0, 1], np.int64), np.array([100], np.int32), np.array([1000], np.int64),
                         np.array([7], np.int32), 1)                                       # taxon out of range
+
+
+def check_multi_batch_classify(ctx, small):
+    """Two read batches appended to ONE classify table (mm_classify_next_batch) and one EM over both = the one-batch run;
+    and the non---all filter inside the library (mm_map_params.report_all = 0) = reportReadMappings' identity >= best - 1.0."""
+    from metamaps_b200 import capi, pipeline
+    db = small["db"]
+    contigs = [synth.codes_to_ascii(c) for c in db.contig_codes]
+    reads = [synth.codes_to_ascii(r) for r in small["reads"]]
+    taxa = sorted(set(db.contig_taxon)); tidx = {t: i for i, t in enumerate(taxa)}
+    contig_taxon = np.array([tidx[t] for t in db.contig_taxon], np.int32)
+    contig_len = np.array([len(c) for c in db.contig_codes], np.int64)
+    ix = build_index(ctx, contigs, 16, 13)
+    one = pipeline.map_and_classify(ctx, ix, reads=reads, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=len(taxa))
+    one = {k_: (np.array(v) if isinstance(v, np.ndarray) else v) for k_, v in one.items()}
+    one["em"] = {k_: (np.array(v) if isinstance(v, np.ndarray) else v) for k_, v in one["em"].items()}
+    ctx.classify_setup(contig_len, contig_taxon, len(taxa))
+    ctx.classify_begin()
+    cut = len(reads) // 3
+    for part in (reads[:cut], reads[cut:]):
+        capi.map_reads(ctx, ix, part, 80.0, 1000, fetch=False)
+        ctx.classify_add(0); ctx.classify_next_batch()
+    cs = ctx.classify_run(0)
+    two = ctx.classify_fetch(cs)
+    for key in ("read", "seq", "pos", "shared", "sketch", "strand", "identity", "mapq", "taxon", "nloc", "mapped_reads", "read_off"):
+        assert np.array_equal(one[key], two[key]), key
+    assert cs["em_iters"] == one["em"]["iters"]
+    assert np.abs(two["f"] - one["em"]["f"]).max() <= 1e-12 and np.array_equal(two["best"], one["em"]["best"])
+    # em_max_iter < 0: everything but the EM
+    ctx.classify_begin(); capi.map_reads(ctx, ix, reads, 80.0, 1000, fetch=False); ctx.classify_add(0)
+    cs0 = ctx.classify_run(-1)
+    assert cs0["em_iters"] == 0 and cs0["n_mappings"] == len(one["read"])
+    # report_all = 0
+    import ctypes as C
+    p = capi.MapParams(80.0, 1000, 0, 0); s = capi.MapSummary()
+    data, offs = capi._ascii_batch(reads)
+    ctx._check(ctx.lib.mm_map_batch(ctx.h, ix.h, data, offs, len(reads), C.byref(p), C.byref(s)))
+    ctx.classify_begin(); ctx.classify_add(0)
+    top = ctx.classify_fetch(ctx.classify_run(-1))
+    keep = np.zeros(len(one["read"]), bool)
+    for g in range(len(one["mapped_reads"])):
+        a, b = one["read_off"][g], one["read_off"][g + 1]
+        best = np.float32(0)
+        for m in range(a, b):
+            if one["identity"][m] > best:
+                best = one["identity"][m]
+        keep[a:b] = one["identity"][a:b].astype(np.float64) >= float(best) - 1.0
+    assert keep.sum() < len(keep) and s.n_mappings == keep.sum()
+    for key in ("read", "seq", "pos", "shared", "identity"):
+        assert np.array_equal(top[key], one[key][keep]), key

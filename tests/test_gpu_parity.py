@@ -117,9 +117,31 @@ def test_mapq(gpu_ctx, oracle):
 
 
 def test_em(gpu_ctx, oracle):
-    common.check_em_vs_oracle(gpu_ctx, oracle, seed=5)
-    common.check_em_vs_oracle(gpu_ctx, oracle, seed=6, max_iter=50, nr=500, T=7, maxc=30)
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=5)                                            # 8 lanes per read
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=6, max_iter=50, nr=500, T=7, maxc=30)         # 32 lanes per read, fixed round count
     common.check_em_vs_oracle(gpu_ctx, oracle, seed=8, nr=20000, T=300, maxc=40)
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=9, nr=4000, T=50, maxc=4)                     # 4 lanes per read
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=10, nr=3000, T=9000, maxc=12)                 # one 72 KB copy of the taxon sums per CTA
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=11, nr=3000, T=40000, maxc=12)                # taxon sums too large for shared memory
+    common.check_em_vs_oracle(gpu_ctx, oracle, seed=12, nr=300, T=200, maxc=400)                  # config-4-like: hundreds of mappings per read
+
+
+def test_em_stopping_round_is_independent_of_the_host_check_interval(gpu_ctx, oracle, monkeypatch):
+    """The stopping rule (fEM.h:636) runs on the device; rounds launched past it must not change anything."""
+    tax, mq, nloc, off, T = common.random_em_case(5)
+    ref = gpu_ctx.em(tax, mq, nloc, off, T, 0)
+    for chk in ("1", "3", "16"):
+        monkeypatch.setenv("MM_EM_CHECK", chk)
+        r = gpu_ctx.em(tax, mq, nloc, off, T, 0)
+        assert r["iters"] == ref["iters"] and np.abs(r["f"] - ref["f"]).max() <= 1e-12 and len(r["ll"]) == r["iters"]
+
+
+def test_em_rejects_a_read_without_likelihood(gpu_ctx):
+    """All mapping qualities of one read are 0: the reference asserts (fEM.h:357); the library must return an error, not loop."""
+    tax, mq, nloc, off, T = common.random_em_case(5, nr=50)
+    mq = mq.copy(); mq[off[7]:off[8]] = 0.0
+    with pytest.raises(capi.MMError):
+        gpu_ctx.em(tax, mq, nloc, off, T, 0)
 
 
 def test_em_properties_large(gpu_ctx):
@@ -335,3 +357,7 @@ def test_pinned_result_buffers(gpu_ctx, small_workload):
             assert np.abs(fa - b["em"]["f"]).max() <= 1e-12 and np.abs(posta - b["em"]["posterior"]).max() <= 1e-12
     finally:
         capi.use_pinned_results(False)
+
+
+def test_multi_batch_classify_table_and_top_mappings_filter(gpu_ctx, small_workload):
+    common.check_multi_batch_classify(gpu_ctx, small_workload)

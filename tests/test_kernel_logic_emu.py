@@ -98,6 +98,14 @@ def test_em(emu_ctx, oracle):
     common.check_em_vs_oracle(emu_ctx, oracle, seed=6, max_iter=50, nr=500, T=7, maxc=30)
 
 
+def test_em_rejects_a_read_without_likelihood(emu_ctx):
+    from metamaps_b200 import capi
+    tax, mq, nloc, off, T = common.random_em_case(5, nr=50)
+    mq = mq.copy(); mq[off[7]:off[8]] = 0.0
+    with pytest.raises(capi.MMError):
+        emu_ctx.em(tax, mq, nloc, off, T, 0)
+
+
 def test_api_errors(emu_ctx, tmp_path):
     with pytest.raises(capi.MMError):
         emu_ctx.sketch([b"ACGT"], 17, 5)          # k > 16 (parseCmdArgs.hpp:62)
@@ -171,3 +179,7 @@ def test_index_save_load(emu_ctx, small_workload, tmp_path):
     # a reference with same-hash-same-contig minimizers: the loaded index rebuilds its duplicate rank table (Index::build_dup_rank)
     rc, rr = _repetitive_workload()
     common.check_index_save_load(emu_ctx, rc, rr, 16, 5, str(tmp_path / "ix.1"))
+
+
+def test_multi_batch_classify_table_and_top_mappings_filter(emu_ctx, small_workload):
+    common.check_multi_batch_classify(emu_ctx, small_workload)
