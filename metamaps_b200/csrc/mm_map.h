@@ -1276,8 +1276,8 @@ struct RingEv {
 
 // Each warp owns WARP_WORDS of shared memory (32 band states + the rings) and pulls tiles of 32 consecutive work items
 // of `order` (descending work: lanes of a tile run loops of similar length) from a global counter.
-template <int BW, int R>
-__global__ void __launch_bounds__(512, 1) l2_sweep_band_kernel(L2SweepArgs a, const uint32_t* order, int64_t nItems, const int32_t* itemCand,
+template <int BW, int R, int MINB>
+__global__ void __launch_bounds__(MINB == 1 ? 512 : 384, MINB) l2_sweep_band_kernel(L2SweepArgs a, const uint32_t* order, int64_t nItems, const int32_t* itemCand,
                                                                const int32_t* itemSeg, int32_t seg, BandPart* parts, unsigned int* tileCounter) {
   extern __shared__ __align__(16) uint32_t sm[];
   constexpr int ST = ((BW + 4) / 4 + BW / 32 + 1) | 1;       // odd word count: lanes start on different banks
@@ -1856,7 +1856,7 @@ struct Mapper {
   }
 
 #ifndef MM_HOST_EMU
-  template <int BW, int R>
+  template <int BW, int R, int MINB = 1>
   void launch_band_t(const L2SweepArgs& sa, const uint32_t* order, int64_t nc) {
     constexpr int ST = ((BW + 4) / 4 + BW / 32 + 1) | 1;
     constexpr int WARP_BYTES = (2 * R * 32 * 4 + 32 * ST) * 4;
@@ -1864,21 +1864,25 @@ struct Mapper {
     if (!warps) {
       int total = (220 * 1024) / WARP_BYTES;                 // warps that fit one SM's shared memory
       if (total > 32) total = 32;
-      ctasPerSm = total > 16 ? 2 : 1;
+      ctasPerSm = MINB;                                      // MINB = 2: two CTAs of 12 warps (the register cap of launch_bounds(384, 2) makes them fit)
+      if (total > 16 * ctasPerSm) total = 16 * ctasPerSm;
+      if (MINB == 2 && total > 24) total = 24;
       warps = total / ctasPerSm;
       if (const char* e = getenv("MM_SWEEP_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 16) warps = v; }
     }
-    if (rt.first((const void*)l2_sweep_band_kernel<BW, R>)) MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
+    if (rt.first((const void*)l2_sweep_band_kernel<BW, R, MINB>)) MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
     int64_t tiles = (nc + 31) / 32;
     int64_t g = (tiles + warps - 1) / warps; if (g > (int64_t)rt.sm_count * ctasPerSm) g = (int64_t)rt.sm_count * ctasPerSm;
-    l2_sweep_band_kernel<BW, R><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, order, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,
+    l2_sweep_band_kernel<BW, R, MINB><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, order, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,
                                                                                                (unsigned int*)(scal.p + 1));
     MM_CUDA(cudaGetLastError());
     rt.launches++;
   }
   void launch_band(const L2SweepArgs& sa, const uint32_t* order, int64_t nc) {
     const int BAND = sweepBand, RING = sweepRing;
+    static const bool two = getenv("MM_SWEEP_2CTA") != nullptr;        // A/B: 24 warps per SM under an 85-register cap
     if (BAND == 64) launch_band_t<64, 4>(sa, order, nc);
+    else if (BAND == 128 && RING == 4 && two) launch_band_t<128, 4, 2>(sa, order, nc);
     else if (BAND == 128 && RING == 4) launch_band_t<128, 4>(sa, order, nc);
     else if (BAND == 128) launch_band_t<128, 8>(sa, order, nc);
     else if (RING == 4) launch_band_t<256, 4>(sa, order, nc);
