@@ -553,7 +553,26 @@ def same_config_leg(d, wl, bases, ref_map_cls_s, ref_index_s, ref_wall_s, thread
         identical = cli_common.compare_dirs(os.path.join(d, "out"), os.path.join(d, "out_b200"))
     except AssertionError as e:
         ok = False; err = str(e)[:300]
+    # CLI throughput on a read file large enough to amortise process start-up: 20 000 reads of the same recipe against the same DB sample
+    cli = {}
+    try:
+        from metamaps_b200 import synth
+        d2 = os.path.join(d, "cli_e2e"); os.makedirs(d2, exist_ok=True)
+        os.symlink(os.path.join(d, "db"), os.path.join(d2, "db"))
+        sp = max(1, len(open(os.path.join(d, "db", "taxonInfo.txt")).read().splitlines()) // wl["n_strains"])
+        db = synth.make_db(wl["seed"], sp, wl["n_strains"], wl["contig_len"], wl["div"] if not isinstance(wl["div"], tuple) else wl["div"][1])
+        names, reads, _ = synth.make_reads(db, wl["seed"] + 2, 20_000, wl["mean_len"], lognormal_sigma=wl["sigma"])
+        synth.write_fastq(os.path.join(d2, "reads.fq"), names, reads)
+        b2 = int(sum(len(r) for r in reads if len(r) >= wl["min_read_len"]))
+        fq_bytes = os.path.getsize(os.path.join(d2, "reads.fq"))
+        del db, reads
+        _, _, w2 = run_cli_once(build.HOST_BIN, d2, wl, threads, out="out_b200")
+        cli = {"reads": 20_000, "fastq_bytes": fq_bytes, "seconds": w2, "Mbp_per_s": b2 / 1e6 / w2,
+               "what": "metamaps_b200/metamaps mapDirectly --all + classify, FASTQ + FASTA in, ten files out, process start to exit (parser, GPU and writer threads)"}
+    except Exception as e:
+        cli = {"error": "%s: %s" % (type(e).__name__, e)}
     return {"files": "the cpu_baseline sample's db/ + reads.fq, both CLIs: mapDirectly --all -m %d -w %d + classify" % (wl["min_read_len"], wl["w"]),
+            "cli_e2e": cli,
             "gpu_cli_s": g_wall, "ref_s": ref_wall_s, "ratio": ref_wall_s / g_wall if g_wall > 0 else None,
             "ref_map_plus_classify_s": ref_map_cls_s, "ref_index_build_s": ref_index_s, "ref_threads": threads,
             "gpu_cli_Mbp_per_s": bases / 1e6 / g_wall, "ref_Mbp_per_s_whole_run": bases / 1e6 / ref_wall_s,

@@ -9,7 +9,14 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unordered_set>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -144,9 +151,9 @@ static mm_index* build_index_chunk(mm_ctx* ctx, const Params& P, mmhost::FastxRe
     buf.clear(); off.assign(1, 0);
   };
   long len;
-  while (bases < budgetBases && (len = rd.read()) >= 0) {
+  while (bases < budgetBases && (len = rd.read_into(buf)) >= 0) {
     meta.push_back(Contig{rd.name, (int)len});
-    buf += rd.seq; off.push_back((int64_t)buf.size()); bases += (uint64_t)len;
+    off.push_back((int64_t)buf.size()); bases += (uint64_t)len;
     if (buf.size() >= ((size_t)256 << 20)) flush();
   }
   flush();
@@ -165,9 +172,9 @@ static mm_index* build_reference_index(mm_ctx* ctx, const Params& P, std::vector
       buf.clear(); off.assign(1, 0);
     };
     long len;
-    while ((len = rd.read()) >= 0) {
+    while ((len = rd.read_into(buf)) >= 0) {
       meta.push_back(Contig{rd.name, (int)len});
-      buf += rd.seq; off.push_back((int64_t)buf.size());
+      off.push_back((int64_t)buf.size());
       if (buf.size() >= ((size_t)256 << 20)) flush();
     }
     flush();
@@ -187,88 +194,141 @@ static void write_meta_and_parameters(const std::string& prefix, const Params& P
   std::cout << "INFO, skch::Map::mapQuery, [count of mapped reads, reads qualified for mapping, total input reads] = [" << mapped << ", "
             << total - tooShort << ", " << total << "]" << std::endl;
 }
+// ---- host pipeline: parser thread -> GPU thread -> formatter/writer thread, batches handed over in order ----------
+// (the reference: kseq_read on the main thread, a pthread pool with an order-preserving output queue, ThreadPool.hpp:24-33,
+//  computeMap.hpp:118-169; here the "pool" is the GPU and the order is the batch order)
+template <class T>
+class BoundedQueue {
+  std::mutex m_; std::condition_variable cv_; std::deque<T> q_; size_t cap_; bool closed_ = false;
+ public:
+  explicit BoundedQueue(size_t cap) : cap_(cap) {}
+  void push(T v) { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return q_.size() < cap_; }); q_.push_back(std::move(v)); cv_.notify_all(); }
+  bool pop(T& out) {
+    std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return false;
+    out = std::move(q_.front()); q_.pop_front(); cv_.notify_all(); return true;
+  }
+  void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; cv_.notify_all(); }
+};
+struct ReadBatch { std::string buf; std::vector<int64_t> off{0}; std::vector<std::string> names; };
+struct MappedBatch {            // what the GPU thread hands to the formatter
+  std::unique_ptr<ReadBatch> in;
+  std::vector<int32_t> read, seq, pos, shared, sketch, strand, mappedRead, status; std::vector<float> identity; std::vector<double> parsed, mapq;
+  std::vector<int64_t> readOff;
+};
+// default-ostream formatting (6 significant digits, %g) without a stream: std::to_chars(general, 6) is specified as printf("%.6g")
+inline void put_g6(std::string& o, double v) { char b[40]; auto r = std::to_chars(b, b + sizeof b, v, std::chars_format::general, 6); o.append(b, (size_t)(r.ptr - b)); }
+inline void put_int(std::string& o, long long v) { char b[24]; auto r = std::to_chars(b, b + sizeof b, v); o.append(b, (size_t)(r.ptr - b)); }
+
+// parser thread body: FASTA/FASTQ records -> batches below the byte / read caps
+static void parse_batches(const std::string& path, size_t capBytes, int64_t capReads, BoundedQueue<std::unique_ptr<ReadBatch>>& out) {
+  mmhost::FastxReader rd(path);
+  if (!rd.ok()) die("Cannot open " + path);
+  auto cur = std::make_unique<ReadBatch>(); cur->buf.reserve(capBytes + (capBytes >> 3));
+  for (;;) {
+    const long len = rd.read_into(cur->buf);
+    if (len < 0) break;
+    cur->names.push_back(rd.name); cur->off.push_back((int64_t)cur->buf.size());
+    if (cur->buf.size() >= capBytes || (int64_t)cur->names.size() >= capReads) {
+      out.push(std::move(cur));
+      cur = std::make_unique<ReadBatch>(); cur->buf.reserve(capBytes + (capBytes >> 3));
+    }
+  }
+  if (!cur->names.empty()) out.push(std::move(cur));
+  out.close();
+}
+
 // skch::Map over every query file + unifyFiles + addMappingQualities (computeMap.hpp:104-172, mapWrap.h:34-323)
 // chunk < 0: the whole reference is in `idx` -> final files.  chunk >= 0: `idx` is chunk N of the reference -> only the
 // 12-column lines of this chunk go to <prefix>.<N> (skch::Map per chunk, mapWrap.h:425-432); unify_files finishes the job.
 static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& meta, const Params& P, int chunk = -1) {
   std::vector<std::string> queries = split(P.query, ","), prefixes = split(P.out, ",");
   if (queries.size() != prefixes.size()) die("Please specify an equal number of input and output files (as comma-separated lists)");
+  // batches stay below what the index's 64-bit hit key can number (many / chromosome-scale contigs leave fewer read bits)
+  int64_t maxReads = 1 << 20; ck(mm_index_max_batch_reads(idx, &maxReads), "mm_index_max_batch_reads");
+  if (maxReads > (1 << 20)) maxReads = 1 << 20;
+  size_t capBytes = (size_t)256 << 20;
+  if (const char* e = getenv("MM_HOST_BATCH_BYTES")) { long long v = atoll(e); if (v >= 1024) capBytes = (size_t)v; }     // tests: several batches on small inputs
   for (size_t fi = 0; fi < queries.size(); fi++) {
     const std::string prefix = chunk < 0 ? prefixes[fi] : prefixes[fi] + "." + std::to_string(chunk);
-    std::ofstream out(prefix);
-    if (!out.is_open()) die("Cannot open output file " + prefix);
-    std::ofstream metaLengths(chunk < 0 ? prefix + ".meta.unmappedReadsLengths" : std::string("/dev/null"));
+    FILE* out = fopen(prefix.c_str(), "wb");
+    if (!out) die("Cannot open output file " + prefix);
+    FILE* metaLengths = fopen(chunk < 0 ? (prefix + ".meta.unmappedReadsLengths").c_str() : "/dev/null", "wb");
     size_t total = 0, tooShort = 0, mapped = 0, notMapped = 0;
-    std::set<std::string> seenIDs;
-    mmhost::FastxReader rd(queries[fi]);
-    if (!rd.ok()) die("Cannot open " + queries[fi]);
-    std::string buf; std::vector<int64_t> off{0}; std::vector<std::string> names;
-
-    auto flush = [&]() {
-      int32_t n = (int32_t)names.size();
-      if (n == 0) return;
+    std::unordered_set<std::string> seenIDs;
+    BoundedQueue<std::unique_ptr<ReadBatch>> parsed(2);
+    BoundedQueue<std::unique_ptr<MappedBatch>> done(2);
+    std::thread parser([&] { parse_batches(queries[fi], capBytes, maxReads, parsed); });
+    // formatter / writer: reportReadMappings' 12 columns (computeMap.hpp:546-588) + the two of addMappingQualities (mapWrap.h:313-320)
+    std::thread writer([&] {
+      std::unique_ptr<MappedBatch> mb;
+      while (done.pop(mb)) {
+        const ReadBatch& in = *mb->in; const int32_t n = (int32_t)in.names.size();
+        const int64_t G = (int64_t)mb->mappedRead.size();
+        for (int64_t g = 0; g < G; g++) if (mb->status[(size_t)g]) die("WARNING!\n\tlikelihood_sum: 0\n\treadID: " + in.names[(size_t)mb->mappedRead[(size_t)g]] + "\n========= END ==========");
+        // counters, unmapped list, duplicate-id check: in read order
+        std::string um; int64_t g = 0;
+        for (int32_t r = 0; r < n; r++) {
+          const int len = (int)(in.off[(size_t)r + 1] - in.off[(size_t)r]);
+          total++;
+          if (len < P.windowSize || len < P.kmerSize || len < P.minReadLength) { tooShort++; continue; }
+          if (g < G && mb->mappedRead[(size_t)g] == r) {
+            mapped++; g++;
+            if (!seenIDs.insert(in.names[(size_t)r]).second) die("Seems that read ID " + in.names[(size_t)r] + " has already been processed - this target ID " + in.names[(size_t)r] + "\n");
+          } else { notMapped++; put_int(um, len); um += '\t'; um += in.names[(size_t)r]; um += '\n'; }
+        }
+        if (!um.empty()) fwrite(um.data(), 1, um.size(), metaLengths);
+        // the lines: mapped reads cut into one slice per thread, every slice formatted into its own string, written in order
+        int nt = P.threads > 1 ? P.threads : 1; if (nt > 64) nt = 64;
+        if ((int64_t)nt > G) nt = G > 0 ? (int)G : 1;
+        std::vector<std::string> piece((size_t)nt);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+        for (int t = 0; t < nt; t++) {
+          std::string& o = piece[(size_t)t];
+          const int64_t g0 = G * t / nt, g1 = G * (t + 1) / nt;
+          if (g1 > g0) o.reserve((size_t)(mb->readOff[(size_t)g1] - mb->readOff[(size_t)g0]) * 128);
+          for (int64_t gg = g0; gg < g1; gg++) {
+            const int32_t r = mb->mappedRead[(size_t)gg]; const std::string& nm = in.names[(size_t)r];
+            const int len = (int)(in.off[(size_t)r + 1] - in.off[(size_t)r]);
+            for (int64_t m = mb->readOff[(size_t)gg]; m < mb->readOff[(size_t)gg + 1]; m++) {
+              const Contig& cg = meta[(size_t)mb->seq[(size_t)m]]; const int ps = mb->pos[(size_t)m];
+              o += nm; o += ' '; put_int(o, len); o += " 0 "; put_int(o, len - 1); o += (mb->strand[(size_t)m] > 0 ? " + " : " - "); o += cg.name; o += ' ';
+              put_int(o, cg.len); o += ' '; put_int(o, ps); o += ' '; put_int(o, ps + len - 1); o += ' '; put_g6(o, (double)mb->identity[(size_t)m]); o += ' ';
+              put_int(o, mb->shared[(size_t)m]); o += ' '; put_int(o, mb->sketch[(size_t)m]);
+              if (chunk < 0) {                          // mapWrap.h:313-320: identity re-parsed from the printed text, corrected, then the quality
+                const float corrected = (float)exp(-(1 - mb->parsed[(size_t)m] / 100.0));
+                o += ' '; put_g6(o, (double)(corrected * 100)); o += ' '; put_g6(o, mb->mapq[(size_t)m]);
+              }
+              o += '\n';
+            }
+          }
+        }
+        for (const std::string& o : piece) if (!o.empty()) fwrite(o.data(), 1, o.size(), out);
+      }
+    });
+    // GPU thread (this one): K0-K5 + identity + mapping quality per batch, results straight from the device-resident table
+    std::unique_ptr<ReadBatch> rb;
+    while (parsed.pop(rb)) {
+      const int32_t n = (int32_t)rb->names.size();
       mm_map_params mp{P.percentageIdentity, P.minReadLength, P.reportAll ? 1 : 0, 0};
       mm_map_summary sum;
-      ck(mm_map_batch(ctx, idx, buf.data(), off.data(), n, &mp, &sum), "mm_map_batch");
-      std::vector<int32_t> sk((size_t)n); std::vector<int64_t> co((size_t)n + 1);
-      ck(mm_map_fetch_reads(ctx, sk.data(), nullptr, co.data()), "mm_map_fetch_reads");
-      size_t C = (size_t)sum.n_candidates;
-      std::vector<int32_t> seq(C), pos(C), shared(C), votes(C), acc(C);
-      ck(mm_map_fetch_candidates(ctx, seq.data(), nullptr, nullptr, pos.data(), shared.data(), votes.data(), acc.data(), nullptr, nullptr, nullptr), "mm_map_fetch_candidates");
-      // reportReadMappings (computeMap.hpp:546-588) -> 12 columns per kept mapping
-      struct Line { std::string text; double identity; int shared, sketch; };
-      std::vector<Line> lines; std::vector<int64_t> roff{0}; std::vector<int32_t> rlen; std::vector<int32_t> ridx;
-      for (int32_t r = 0; r < n; r++) {
-        int len = (int)(off[(size_t)r + 1] - off[(size_t)r]);
-        total++;
-        if (len < P.windowSize || len < P.kmerSize || len < P.minReadLength) { tooShort++; continue; }
-        std::vector<size_t> keep; std::vector<float> nuc;
-        float best = 0;
-        for (int64_t c = co[(size_t)r]; c < co[(size_t)r + 1]; c++) if (acc[(size_t)c]) {
-          float a, b; mm_stat_identity(shared[(size_t)c], sk[(size_t)r], P.kmerSize, &a, &b);
-          keep.push_back((size_t)c); nuc.push_back(a); if (a > best) best = a;
-        }
-        size_t before = lines.size();
-        for (size_t j = 0; j < keep.size(); j++) {
-          if (!(P.reportAll || nuc[j] >= best - 1.0)) continue;
-          size_t c = keep[j];
-          std::ostringstream l;
-          l << names[(size_t)r] << " " << len << " 0 " << len - 1 << " " << (votes[c] > 0 ? "+" : "-") << " " << meta[(size_t)seq[c]].name << " "
-            << meta[(size_t)seq[c]].len << " " << pos[c] << " " << pos[c] + len - 1 << " " << nuc[j] << " " << shared[c] << " " << sk[(size_t)r];
-          // addMappingQualities re-parses the printed identity (mapWrap.h:229)
-          lines.push_back(Line{l.str(), std::stod(g6(nuc[j])) / 100.0, shared[c], sk[(size_t)r]});
-        }
-        if (lines.size() == before) { notMapped++; metaLengths << len << "\t" << names[(size_t)r] << "\n"; }
-        else {
-          mapped++;
-          if (!seenIDs.insert(names[(size_t)r]).second) die("Seems that read ID " + names[(size_t)r] + " has already been processed - this target ID " + names[(size_t)r] + "\n");
-          roff.push_back((int64_t)lines.size()); rlen.push_back(len); ridx.push_back(r);
-        }
-      }
-      if (chunk >= 0) {
-        for (const Line& l : lines) out << l.text << "\n";
-      } else if (!lines.empty()) {                                     // mapWrap.h:215-323
-        std::vector<double> id(lines.size()), mq(lines.size()); std::vector<int32_t> sh(lines.size()), ss(lines.size()), st(rlen.size());
-        for (size_t i = 0; i < lines.size(); i++) { id[i] = lines[i].identity; sh[i] = lines[i].shared; ss[i] = lines[i].sketch; }
-        ck(mm_mapq_batch(ctx, id.data(), sh.data(), ss.data(), rlen.data(), roff.data(), (int64_t)rlen.size(), P.kmerSize, mq.data(), st.data()), "mm_mapq_batch");
-        for (size_t r = 0; r < rlen.size(); r++) if (st[r]) die("WARNING!\n\tlikelihood_sum: 0\n\treadID: " + names[(size_t)ridx[r]] + "\n========= END ==========");
-        for (size_t i = 0; i < lines.size(); i++) {
-          float corrected = exp(-(1 - id[i]));
-          out << lines[i].text << " " << corrected * 100 << " " << mq[i] << "\n";
-        }
-      }
-      buf.clear(); off.assign(1, 0); names.clear();
-    };
-    // batches stay below what the index's 64-bit hit key can number (many / chromosome-scale contigs leave fewer read bits)
-    int64_t maxReads = 1 << 20; ck(mm_index_max_batch_reads(idx, &maxReads), "mm_index_max_batch_reads");
-    if (maxReads > (1 << 20)) maxReads = 1 << 20;
-    long len;
-    while ((len = rd.read()) >= 0) {
-      names.push_back(rd.name); buf += rd.seq; off.push_back((int64_t)buf.size());
-      if (buf.size() >= ((size_t)512 << 20) || (int64_t)names.size() >= maxReads) flush();
+      ck(mm_map_batch(ctx, idx, rb->buf.data(), rb->off.data(), n, &mp, &sum), "mm_map_batch");
+      ck(mm_classify_begin(ctx), "mm_classify_begin");
+      int64_t M = 0; ck(mm_classify_add_mappings(ctx, 0, &M), "mm_classify_add_mappings");
+      mm_classify_summary cs; ck(mm_classify_run(ctx, -1, &cs), "mm_classify_run");      // identity + mapping quality; the EM belongs to `classify`
+      auto mb = std::make_unique<MappedBatch>();
+      const size_t Mz = (size_t)cs.n_mappings, Gz = (size_t)cs.n_reads_mapped;
+      mb->read.resize(Mz); mb->seq.resize(Mz); mb->pos.resize(Mz); mb->shared.resize(Mz); mb->sketch.resize(Mz); mb->strand.resize(Mz);
+      mb->identity.resize(Mz); mb->parsed.resize(Mz); mb->mapq.resize(Mz); mb->mappedRead.resize(Gz); mb->status.resize(Gz); mb->readOff.resize(Gz + 1);
+      ck(mm_classify_fetch(ctx, mb->read.data(), mb->seq.data(), mb->pos.data(), mb->shared.data(), mb->sketch.data(), mb->strand.data(), mb->identity.data(),
+                           mb->parsed.data(), mb->mapq.data(), nullptr, nullptr, nullptr, (int64_t)Mz, mb->mappedRead.data(), mb->readOff.data(), nullptr,
+                           mb->status.data(), nullptr, nullptr, 0), "mm_classify_fetch");
+      mb->in = std::move(rb);
+      done.push(std::move(mb));
     }
-    flush();
-    out.close(); metaLengths.close();
+    done.close();
+    parser.join(); writer.join();
+    fclose(out); fclose(metaLengths);
     if (chunk < 0) write_meta_and_parameters(prefix, P, queries[fi], total, tooShort, mapped, notMapped);
   }
 }

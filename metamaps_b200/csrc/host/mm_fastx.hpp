@@ -2,13 +2,18 @@
 // reference uses it (src/common/kseq.h:171-208; winSketch.hpp:245-252, computeMap.hpp:125-134):
 //   * a record starts at the next '>' or '@'; the name is everything up to the first white space;
 //   * sequence = all isgraph() characters up to the next '>', '+' or '@' (wherever it occurs);
-//   * after '+': skip that line, then read quality characters (33..127) until as many as bases were read;
+//   * after '+': skip that line, then read quality characters (33..127) until as many as bases were read
+//     (plus the one character kseq's loop consumes when it notices the count is reached);
 //   * return value: sequence length, -1 at end of file, -2 for a truncated quality string.
+// Unlike kseq's character-at-a-time getc loop this reader works on whole buffer spans: lines are found with memchr,
+// a line made of letters only (the normal case) is appended with one memcpy, quality lines are counted, not stored.
+// `append_to` lets the caller have the bases written straight at the end of its own batch buffer (e.g. pinned memory).
 #pragma once
 #include <zlib.h>
 
 #include <cctype>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -17,53 +22,124 @@ namespace mmhost {
 class FastxReader {
   gzFile fp_ = nullptr;
   std::vector<unsigned char> buf_;
-  int begin_ = 0, end_ = 0;
+  size_t begin_ = 0, end_ = 0;
   bool eof_ = false;
   int last_char_ = 0;
 
-  int getc_() {
-    if (begin_ >= end_) {
-      if (eof_) return -1;
-      begin_ = 0;
-      end_ = gzread(fp_, buf_.data(), (unsigned)buf_.size());
-      if (end_ <= 0) { eof_ = true; end_ = 0; return -1; }
-    }
-    return (int)buf_[begin_++];
+  bool fill() {                      // true if at least one byte is available
+    if (begin_ < end_) return true;
+    if (eof_) return false;
+    begin_ = 0;
+    int n = gzread(fp_, buf_.data(), (unsigned)buf_.size());
+    if (n <= 0) { eof_ = true; end_ = 0; return false; }
+    end_ = (size_t)n;
+    return true;
+  }
+  int getc_() { return fill() ? (int)buf_[begin_++] : -1; }
+  // all bytes are letters / other graph characters above '@' (so none of '>' '+' '@', no white space, no control byte)
+  static bool clean_span(const unsigned char* p, size_t n) {
+    unsigned char ok = 1;
+    for (size_t i = 0; i < n; i++) ok &= (unsigned char)((unsigned char)(p[i] - 65) < 62);
+    return ok != 0;
   }
 
  public:
-  std::string name, comment, seq, qual;
+  std::string name, seq;             // seq is filled only by read(); read_into() appends to the caller's buffer instead
 
-  explicit FastxReader(const std::string& path) : buf_(1 << 20) {
+  explicit FastxReader(const std::string& path, size_t bufBytes = (size_t)4 << 20) : buf_(bufBytes) {
     FILE* f = fopen(path.c_str(), "r");
-    if (f) fp_ = gzdopen(fileno(f), "r");
+    if (f) { fp_ = gzdopen(fileno(f), "r"); if (fp_) gzbuffer(fp_, 1 << 20); }
   }
   ~FastxReader() { if (fp_) gzclose(fp_); }
   bool ok() const { return fp_ != nullptr; }
 
-  long read() {
+  long read() { seq.clear(); return read_into(seq); }
+
+  // Appends the record's bases to `out` (std::string-like: size(), resize(), data()).  Returns like kseq_read.
+  template <class Buf>
+  long read_into(Buf& out) {
     int c;
-    if (last_char_ == 0) {
-      while ((c = getc_()) != -1 && c != '>' && c != '@') {}
-      if (c == -1) return -1;
-      last_char_ = c;
+    if (last_char_ == 0) {           // jump to the next header
+      for (;;) {
+        if (!fill()) return -1;
+        const unsigned char* p = buf_.data() + begin_; const unsigned char* e = buf_.data() + end_;
+        while (p < e && *p != '>' && *p != '@') ++p;
+        begin_ = (size_t)(p - buf_.data());
+        if (p < e) { last_char_ = *p; begin_++; break; }
+      }
     }
-    name.clear(); comment.clear(); seq.clear(); qual.clear();
-    while ((c = getc_()) != -1 && !isspace(c)) name.push_back((char)c);
+    name.clear();
+    const size_t base = out.size();
+    // name: up to the first white space
+    c = -1;
+    while (fill()) {
+      const unsigned char* p = buf_.data() + begin_; const unsigned char* e = buf_.data() + end_; const unsigned char* s = p;
+      while (p < e && !isspace(*p)) ++p;
+      name.append((const char*)s, (size_t)(p - s));
+      begin_ = (size_t)(p - buf_.data());
+      if (p < e) { c = *p; begin_++; break; }
+    }
     if (c == -1 && name.empty()) return -1;
-    if (c != '\n' && c != -1)
-      while ((c = getc_()) != -1 && c != '\n') comment.push_back((char)c);
-    while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@')
-      if (isgraph(c)) seq.push_back((char)c);
+    if (c != '\n' && c != -1) {      // rest of the header line (comment): skipped
+      c = -1;
+      while (fill()) {
+        const unsigned char* p = buf_.data() + begin_;
+        const void* nl = memchr(p, '\n', end_ - begin_);
+        if (nl) { begin_ = (size_t)((const unsigned char*)nl - buf_.data()) + 1; c = '\n'; break; }
+        begin_ = end_;
+      }
+    }
+    // sequence: graph characters up to the next '>' '+' '@'
+    c = -1;
+    while (fill()) {
+      const unsigned char* p = buf_.data() + begin_; const size_t avail = end_ - begin_;
+      const void* nl = memchr(p, '\n', avail);
+      const size_t len = nl ? (size_t)((const unsigned char*)nl - p) : avail;
+      if (clean_span(p, len)) {
+        const size_t at = out.size(); out.resize(at + len); memcpy(&out[0] + at, p, len);
+        begin_ += len + (nl ? 1 : 0);
+        continue;
+      }
+      // a line with a marker or a non-letter: character by character, like kseq
+      size_t i = 0; bool stop = false;
+      const size_t lim = len + (nl ? 1 : 0);
+      for (; i < lim; i++) {
+        const unsigned char ch = p[i];
+        if (ch == '>' || ch == '+' || ch == '@') { stop = true; break; }
+        if (isgraph(ch)) { out.resize(out.size() + 1); out[out.size() - 1] = (char)ch; }
+      }
+      if (stop) { c = p[i]; begin_ += i + 1; break; }
+      begin_ += lim;
+    }
+    const size_t n = out.size() - base;
     if (c == '>' || c == '@') last_char_ = c;
-    if (c != '+') { if (c == -1) last_char_ = 0; return (long)seq.size(); }
-    while ((c = getc_()) != -1 && c != '\n') {}
+    if (c != '+') { if (c == -1) last_char_ = 0; return (long)n; }
+    // '+' line
+    c = -1;
+    while (fill()) {
+      const unsigned char* p = buf_.data() + begin_;
+      const void* nl = memchr(p, '\n', end_ - begin_);
+      if (nl) { begin_ = (size_t)((const unsigned char*)nl - buf_.data()) + 1; c = '\n'; break; }
+      begin_ = end_;
+    }
     if (c == -1) return -2;
-    while ((c = getc_()) != -1 && qual.size() < seq.size())
-      if (c >= 33 && c <= 127) qual.push_back((char)c);
+    // quality: count characters in 33..127 until n of them were seen, then kseq consumes one more character
+    size_t q = 0;
+    while (q < n && fill()) {
+      const unsigned char* p = buf_.data() + begin_; const size_t avail = end_ - begin_;
+      const void* nl = memchr(p, '\n', avail);
+      const size_t len = nl ? (size_t)((const unsigned char*)nl - p) : avail;
+      size_t valid = 0;
+      for (size_t i = 0; i < len; i++) valid += (size_t)((unsigned char)(p[i] - 33) < 95);
+      if (q + valid < n) { q += valid; begin_ += len + (nl ? 1 : 0); continue; }
+      size_t i = 0;
+      for (; i < len && q < n; i++) q += (size_t)((unsigned char)(p[i] - 33) < 95);
+      begin_ += i;
+    }
     last_char_ = 0;
-    if (qual.size() != seq.size()) return -2;
-    return (long)seq.size();
+    if (q < n) return -2;
+    (void)getc_();                   // the read kseq's loop does before it sees qual.l == seq.l
+    return (long)n;
   }
 };
 

@@ -1087,10 +1087,10 @@ int mm_classify_run(mm_ctx* c, int32_t em_max_iter, mm_classify_summary* out) {
   MM_TRY
   if (!c) throw Error(MM_EINVAL, "null ctx");
   Classifier& cl = c->cls; MapTable& t = cl.tab; Runtime& rt = c->rt; Mapper& mp = c->mp;
-  if (!cl.taxo.set) throw Error(MM_EINVAL, "mm_classify_run: call mm_classify_setup first");
+  if (em_max_iter >= 0 && !cl.taxo.set) throw Error(MM_EINVAL, "mm_classify_run: call mm_classify_setup first (only em_max_iter < 0 -- identity and mapping quality alone -- works without a taxonomy)");
   begin_call(c);
   bind_allreduce(c);
-  const int64_t M = t.n; const int k = mp.lastK; const int32_t T = cl.taxo.T;
+  const int64_t M = t.n; const int k = mp.lastK; const int32_t T = cl.taxo.set ? cl.taxo.T : 1;
   cl.emMs = 0; cl.iters = 0; cl.nGroups = 0; cl.nFix = 0;
   {
     StageTimer tm(rt, &c->last_ms);
@@ -1104,7 +1104,7 @@ int mm_classify_run(mm_ctx* c, int32_t em_max_iter, mm_classify_summary* out) {
       cl.run_mapq(cl.parsed.p, 100.0, t.shared.p, t.sketch.p, M, k);
       cl.tax.ensure((size_t)M + 1); cl.nloc.ensure((size_t)M + 1); cl.w.ensure((size_t)M + 1); cl.bad.ensure(1);
       dev_memset(rt, cl.bad.p, 0, sizeof(int32_t));
-      foreach(rt, M, NlocFn{t.seq.p, cl.mGrp.p, cl.grpOff.p, cl.grpLen.p, cl.mapq.p, cl.taxo.contigLen.p, cl.taxo.contigTaxon.p, cl.taxo.nContigs,
+      if (cl.taxo.set) foreach(rt, M, NlocFn{t.seq.p, cl.mGrp.p, cl.grpOff.p, cl.grpLen.p, cl.mapq.p, cl.taxo.contigLen.p, cl.taxo.contigTaxon.p, cl.taxo.nContigs,
                             cl.taxo.lens.p, cl.taxo.start.p, cl.taxo.csum.p, cl.tax.p, cl.nloc.p, cl.w.p, cl.bad.p});
     } else { cl.grpOff.ensure(2); dev_memset(rt, cl.grpOff.p, 0, 16); cl.w.ensure(1); cl.tax.ensure(1); }
   }
@@ -1132,7 +1132,7 @@ int mm_classify_fetch(mm_ctx* c, int32_t* read_idx, int32_t* seq_id, int32_t* re
 #endif
   get(read_idx, t.read.p, 4 * M); get(seq_id, t.seq.p, 4 * M); get(ref_start, t.pos.p, 4 * M); get(shared, t.shared.p, 4 * M);
   get(sketch, t.sketch.p, 4 * M); get(strand, t.strand.p, 4 * M);
-  if (M) { get(identity, cl.id32.p, 4 * M); get(parsed, cl.parsed.p, 8 * M); get(mapq, cl.mapq.p, 8 * M); get(taxon, cl.tax.p, 4 * M); get(nloc, cl.nloc.p, 8 * M); }
+  if (M) { get(identity, cl.id32.p, 4 * M); get(parsed, cl.parsed.p, 8 * M); get(mapq, cl.mapq.p, 8 * M); if (cl.taxo.set) { get(taxon, cl.tax.p, 4 * M); get(nloc, cl.nloc.p, 8 * M); } }
   if (M && cl.iters > 0) get(posterior, cl.post.p, 8 * M);
   if (G) { get(mapped_read, cl.grpRead.p, 4 * G); get(status, cl.status.p, 4 * G); if (cl.iters > 0) get(best, cl.best.p, 8 * G); }
   if (read_off) { if (G) get(read_off, cl.grpOff.p, 8 * (G + 1)); else read_off[0] = 0; }

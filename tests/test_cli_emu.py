@@ -78,3 +78,42 @@ def test_cli_config2_shaped_sample_matches_reference_files(tmp_path):
     32-bit hash space starts to saturate, and all ten files must equal what the unmodified reference wrote (fixture)."""
     identical, thr = cli_common.check_config2_golden(build_emu_host(), str(tmp_path))
     assert identical == 10, identical
+
+
+def test_cli_awkward_fastx_formatting_matches_live_reference(tmp_path, monkeypatch):
+    """kseq record semantics (kseq.h:171-208) through the block-wise parser: wrapped FASTQ/FASTA lines, CRLF, blank lines,
+    quality strings containing '@' '>' '+', comments after the name, a '+name' separator, lower case, no trailing newline;
+    read batches of ~20 kB so that the parser / GPU / writer hand-over happens many times."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    import numpy as np
+    binary = build_emu_host()
+    d = str(tmp_path)
+    db = synth.make_db(31, 3, 2, 40_000, 0.02)
+    synth.write_db(db, os.path.join(d, "db"), line_width=61)
+    names, reads, _ = synth.make_reads(db, 32, 90, 2600, lognormal_sigma=0.3, clip=(700, 6000), frac_short=0.05, short_len=500)
+    rng = np.random.default_rng(4)
+    with open(os.path.join(d, "reads.fq"), "wb") as f:
+        for i, (n, r) in enumerate(zip(names, reads)):
+            s = synth.codes_to_ascii(r)
+            if i % 5 == 1:
+                s = s.lower()
+            q = bytes(rng.choice(list(b"@>+I5#~!"), size=len(s)).astype(np.uint8))
+            eol = b"\r\n" if i % 4 == 2 else b"\n"
+            if i % 3 == 0:          # wrapped sequence and quality
+                wrap = lambda x: eol.join(x[j:j + 70] for j in range(0, len(x), 70))
+                f.write(b"@" + n.encode() + b" some comment" + eol + wrap(s) + eol + b"+" + n.encode() + eol + wrap(q) + eol)
+            elif i % 7 == 3:        # a FASTA record in the middle of the FASTQ
+                f.write(b">" + n.encode() + b"\tx=1" + eol + s + eol + eol)
+            else:
+                f.write(b"@" + n.encode() + eol + s + eol + b"+" + eol + q + (b"" if i == len(names) - 1 else eol))
+    for out, b in (("o_ref", pyoracle.REF_BIN), ("o_emu", binary)):
+        os.makedirs(os.path.join(d, out))
+        if b == binary:
+            monkeypatch.setenv("MM_HOST_BATCH_BYTES", "20000")
+        subprocess.run([b, "mapDirectly", "--all", "-r", "db/DB.fa", "-q", "reads.fq", "-o", out + "/ref", "-t", "3"], cwd=d, check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        subprocess.run([b, "classify", "--DB", "db", "--mappings", out + "/ref"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert cli_common.compare_dirs(os.path.join(d, "o_ref"), os.path.join(d, "o_emu")) >= 8
+    assert int(open(os.path.join(d, "o_emu", "ref.meta")).read().split()[1]) == len(names)
