@@ -98,6 +98,14 @@ int mm_index_stats(const mm_index* idx, int64_t* n_minimizers, int64_t* n_unique
  *     mm_comm_init, or mm_comm_set_allreduce + mm_comm_set_rank).  The shards' (hash, count) lists are exchanged by
  *     hash range, merged, the global histogram gives the threshold and the over-frequent hashes are flagged locally. */
 int mm_index_set_shard(mm_index* idx, int32_t first_contig_id, int32_t keep_counts);
+/* The reference's own chunk loop (--maxmemory) does NOT reset its occurrence histogram or threshold between chunks
+ * (winSketch.hpp:302-304,452-495): chunk N's threshold comes from the histograms of chunks 0..N summed, walked against chunk N's
+ * unique count, and keeps chunk N-1's value when the first bucket overshoots.  A host that walks chunks reproduces that by
+ * carrying the state: mm_index_get_freq_hist after chunk N-1's finalize (count_value[i] occurrences are shared by n_hashes[i]
+ * hashes; *n_buckets entries, at most cap are written; *threshold = the chunk's threshold), mm_index_set_freq_carry before chunk
+ * N's finalize.  Without a carry an index computes the threshold of its own contigs, i.e. chunk 0's / the unchunked behaviour. */
+int mm_index_set_freq_carry(mm_index* idx, const int32_t* count_value, const int64_t* n_hashes, int32_t n_buckets, int32_t prev_threshold);
+int mm_index_get_freq_hist(const mm_index* idx, int32_t* count_value, int64_t* n_hashes, int32_t cap, int32_t* n_buckets, int32_t* threshold);
 int mm_index_sync_threshold(mm_index* idx, int32_t* global_threshold, int64_t* global_unique);
 /* Persistent index (replaces the Boost binary archive of skch::Sketch written by `metamaps index`, mapWrap.h:358-405).
  * A GPU-native dump: fixed header + the device arrays as they lie in HBM, so loading is a sequence of plain reads and

@@ -48,6 +48,8 @@ SYMBOLS = {
     "mm_index_add_dev": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, C.c_int32]),
     "mm_index_set_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "mm_index_sync_threshold": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "mm_index_set_freq_carry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "mm_index_get_freq_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mm_comm_set_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mm_ctx_mem_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mm_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -330,6 +332,19 @@ class Index:
         """This index holds the contigs [first_contig_id, ...) of a larger reference (call before finalize)."""
         self.first_contig = int(first_contig_id)
         self.ctx._check(self.lib.mm_index_set_shard(self.h, int(first_contig_id), 1 if keep_counts else 0))
+
+    def set_freq_carry(self, hist, prev_threshold: int):
+        """hist: list of (occurrence count, number of hashes) carried from the previous reference chunks (see the header)."""
+        v = np.array([h[0] for h in hist], np.int32); c = np.array([h[1] for h in hist], np.int64)
+        self.ctx._check(self.lib.mm_index_set_freq_carry(self.h, _ptr(v), _ptr(c), len(v), int(prev_threshold)))
+
+    def freq_hist(self):
+        """(cumulative histogram after this chunk as a list of (count, hashes), this chunk's threshold)."""
+        n = C.c_int32(); t = C.c_int32()
+        self.ctx._check(self.lib.mm_index_get_freq_hist(self.h, None, None, 0, C.byref(n), C.byref(t)))
+        v = np.zeros(n.value, np.int32); c = np.zeros(n.value, np.int64)
+        self.ctx._check(self.lib.mm_index_get_freq_hist(self.h, _ptr(v), _ptr(c), n.value, C.byref(n), C.byref(t)))
+        return [(int(a), int(b)) for a, b in zip(v, c)], t.value
 
     def sync_threshold(self):
         """Collective: occurrence threshold of the whole (sharded) reference; flags the over-frequent hashes locally."""

@@ -142,7 +142,10 @@ static void print_index_info(mm_index* idx) {
 // skch::Sketch over the reference FASTA (winSketch.hpp:180-365) on the device
 // next chunk of the reference (contigs until `budgetBases` bases are in, like winSketch.hpp:284-329 cuts at a memory estimate);
 // returns null when the FASTA is exhausted
-static mm_index* build_index_chunk(mm_ctx* ctx, const Params& P, mmhost::FastxReader& rd, uint64_t budgetBases, std::vector<Contig>& meta) {
+// occurrence histogram + threshold carried from chunk to chunk, like the reference's one Sketch object does (winSketch.hpp:302-304,452-495)
+struct FreqCarry { std::vector<int32_t> v; std::vector<int64_t> c; int32_t thr = 0x7fffffff; };
+static mm_index* build_index_chunk(mm_ctx* ctx, const Params& P, mmhost::FastxReader& rd, uint64_t budgetBases, std::vector<Contig>& meta, FreqCarry& carry,
+                                   size_t maxContigs = 0) {
   mm_index* idx = nullptr; ck(mm_index_create(ctx, P.kmerSize, P.windowSize, &idx), "mm_index_create");
   meta.clear();
   std::string buf; std::vector<int64_t> off{0}; uint64_t bases = 0;
@@ -151,14 +154,18 @@ static mm_index* build_index_chunk(mm_ctx* ctx, const Params& P, mmhost::FastxRe
     buf.clear(); off.assign(1, 0);
   };
   long len;
-  while (bases < budgetBases && (len = rd.read_into(buf)) >= 0) {
+  while (bases < budgetBases && (maxContigs == 0 || meta.size() < maxContigs) && (len = rd.read_into(buf)) >= 0) {
     meta.push_back(Contig{rd.name, (int)len});
     off.push_back((int64_t)buf.size()); bases += (uint64_t)len;
     if (buf.size() >= ((size_t)256 << 20)) flush();
   }
   flush();
   if (meta.empty()) { mm_index_destroy(idx); return nullptr; }
+  ck(mm_index_set_freq_carry(idx, carry.v.data(), carry.c.data(), (int32_t)carry.v.size(), carry.thr), "mm_index_set_freq_carry");
   ck(mm_index_finalize(idx), "mm_index_finalize");
+  int32_t nb = 0; ck(mm_index_get_freq_hist(idx, nullptr, nullptr, 0, &nb, &carry.thr), "mm_index_get_freq_hist");
+  carry.v.resize((size_t)nb); carry.c.resize((size_t)nb);
+  ck(mm_index_get_freq_hist(idx, carry.v.data(), carry.c.data(), nb, &nb, &carry.thr), "mm_index_get_freq_hist");
   return idx;
 }
 static mm_index* build_reference_index(mm_ctx* ctx, const Params& P, std::vector<Contig>& meta) {
@@ -394,6 +401,16 @@ static void unify_files(mm_ctx* ctx, const std::string& prefix, const Params& P,
   write_meta_and_parameters(prefix, P, query, total, tooShort, mapped, notMapped);
 }
 
+// Does the index fit the device?  ~110 bytes per minimizer while it is being built (8 + 8 + 2 resident, up to 64 of table at load
+// 0.25, sort temporaries), 2/(w+1) minimizers per base
+static uint64_t chunk_bases_for(double budgetBytes, const Params& P) { return (uint64_t)(budgetBytes / (110.0 * 2.0 / (P.windowSize + 1))); }
+// MM_HOST_CHUNK_CONTIGS=n0,n1,...: chunk i takes exactly n_i contigs (tests: the chunk boundaries of a reference --maxmemory run,
+// which cuts at its own host-memory estimate, winSketch.hpp:284-329); chunks beyond the list follow the byte budget
+static std::vector<size_t> chunk_contig_counts() {
+  std::vector<size_t> v;
+  if (const char* e = getenv("MM_HOST_CHUNK_CONTIGS")) for (auto& x : split(e, ",")) if (!x.empty()) v.push_back((size_t)strtoull(x.c_str(), nullptr, 10));
+  return v;
+}
 int run_mapDirectly(int argc, char** argv) {
   int device = 0;
   Params P = parse_map_options(argc, argv, 0, &device);
@@ -404,10 +421,10 @@ int run_mapDirectly(int argc, char** argv) {
   int64_t freeB = 0, totalB = 0; ck(mm_ctx_mem_info(ctx, &freeB, &totalB), "mm_ctx_mem_info");
   double budget = 0.6 * (double)freeB;
   if (P.maximumMemory > 0 && (double)P.maximumMemory < budget) budget = (double)P.maximumMemory;
-  uint64_t chunkBases = (uint64_t)(budget / (75.0 * 2.0 / (P.windowSize + 1)));
+  uint64_t chunkBases = chunk_bases_for(budget, P);
   if (const char* e = getenv("MM_HOST_CHUNK_BASES")) chunkBases = strtoull(e, nullptr, 10);       // tests: force chunking
   std::vector<Contig> meta;
-  if (P.referenceSize <= chunkBases) {                               // the usual case: one device-resident index
+  if (P.referenceSize <= chunkBases && !getenv("MM_HOST_CHUNK_CONTIGS")) {      // the usual case: one device-resident index
     mm_index* idx = build_reference_index(ctx, P, meta);
     print_index_info(idx);
     map_queries(ctx, idx, meta, P);
@@ -418,8 +435,9 @@ int run_mapDirectly(int argc, char** argv) {
     mmhost::FastxReader rd(P.ref);
     if (!rd.ok()) die("Cannot open " + P.ref);
     std::vector<std::vector<std::string>> chunkFiles(prefixes.size());
-    int N = 0;
-    for (mm_index* idx; (idx = build_index_chunk(ctx, P, rd, chunkBases, meta)) != nullptr; N++) {
+    int N = 0; FreqCarry carry;
+    const std::vector<size_t> cuts = chunk_contig_counts();
+    for (mm_index* idx; (idx = build_index_chunk(ctx, P, rd, chunkBases, meta, carry, (size_t)N < cuts.size() ? cuts[(size_t)N] : 0)) != nullptr; N++) {
       std::cout << "Index chunk " << N << ": " << meta.size() << " contigs\n";
       print_index_info(idx);
       map_queries(ctx, idx, meta, P, N);
@@ -450,19 +468,39 @@ int run_index(int argc, char** argv) {
       << "\nrefSequences " << P.ref << "\n";
   }
   mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
-  std::vector<Contig> meta;
-  mm_index* idx = build_reference_index(ctx, P, meta);
-  print_index_info(idx);
-  const std::string chunk = P.index + ".0";
-  ck(mm_index_save(idx, chunk.c_str()), "mm_index_save");
-  {
+  int64_t freeB = 0, totalB = 0; ck(mm_ctx_mem_info(ctx, &freeB, &totalB), "mm_ctx_mem_info");
+  double budget = 0.6 * (double)freeB;
+  if (P.maximumMemory > 0 && (double)P.maximumMemory < budget) budget = (double)P.maximumMemory;
+  uint64_t chunkBases = chunk_bases_for(budget, P);
+  if (const char* e = getenv("MM_HOST_CHUNK_BASES")) chunkBases = strtoull(e, nullptr, 10);
+  std::vector<Contig> meta; std::vector<std::string> written;
+  auto store = [&](mm_index* idx, int N) {                       // <prefix>.N + its contig list (mapWrap.h:380-393)
+    print_index_info(idx);
+    const std::string chunk = P.index + "." + std::to_string(N);
+    ck(mm_index_save(idx, chunk.c_str()), "mm_index_save");
     std::ofstream c(chunk + ".contigs");
     if (!c.is_open()) die("Cannot open file " + chunk + ".contigs for serialization.");
     for (const Contig& m : meta) c << m.len << "\t" << m.name << "\n";
+    std::cout << "Stored state in file " << chunk << "\n" << std::flush;
+    written.push_back(chunk);
+  };
+  if (P.referenceSize <= chunkBases && !getenv("MM_HOST_CHUNK_CONTIGS")) {
+    mm_index* idx = build_reference_index(ctx, P, meta);
+    store(idx, 0);
+    mm_index_destroy(idx);
+  } else {                                                       // one file per chunk of the reference, thresholds carried like mapDirectly's loop
+    mmhost::FastxReader rd(P.ref);
+    if (!rd.ok()) die("Cannot open " + P.ref);
+    FreqCarry carry; const std::vector<size_t> cuts = chunk_contig_counts();
+    int N = 0;
+    for (mm_index* idx; (idx = build_index_chunk(ctx, P, rd, chunkBases, meta, carry, (size_t)N < cuts.size() ? cuts[(size_t)N] : 0)) != nullptr; N++) {
+      store(idx, N);
+      mm_index_destroy(idx);
+    }
   }
-  std::cout << "Stored state in file " << chunk << "\n" << std::flush;
-  { std::ofstream st(P.index + ".index"); st << 1 << "\n" << chunk << "\n"; }
-  mm_index_destroy(idx); mm_ctx_destroy(ctx);
+  { std::ofstream st(P.index + ".index"); st << 1 << "\n"; for (auto& f : written) st << f << "\n"; }      // mapWrap.h:397-404
+  std::cout << "\nIndex construction DONE, wrote " << written.size() << " files.\n\n" << std::flush;
+  mm_ctx_destroy(ctx);
   return 0;
 }
 // mapWrap::mapAgainstIndex (mapWrap.h:443-554)
@@ -477,7 +515,6 @@ int run_mapAgainstIndex(int argc, char** argv) {
   }
   if (lines.empty() || lines[0] != "1") die("The file " + P.index + ".index does not indicate that index " + P.index + " was built successfully, abort.");
   if (lines.size() < 2) die("Index " + P.index + " was built successfully, but no index files present?");
-  if (lines.size() > 2) die("Index " + P.index + " lists several chunk files; this build writes and reads single-chunk (device-resident) indices");
   {
     std::ifstream a(P.index + ".arguments");
     if (!a.is_open()) die("Expected file " + P.index + ".arguments not found - have you supplied a valid index?");
@@ -497,22 +534,32 @@ int run_mapAgainstIndex(int argc, char** argv) {
             << "\n\t- minReadLength: " << P.minReadLength << "\n\t- p_value: " << P.p_value << "\n\t- percentageIdentity: " << P.percentageIdentity
             << "\n\t- windowSize: " << P.windowSize << "\n\n" << std::flush;
   mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
-  mm_index* idx = nullptr;
-  ck(mm_index_load(ctx, lines[1].c_str(), &idx), "mm_index_load");
-  int32_t k = 0, w = 0; mm_index_params(idx, &k, &w, nullptr);
-  if (k != P.kmerSize || w != P.windowSize) die("Index file " + lines[1] + " does not match " + P.index + ".arguments");
-  std::vector<Contig> meta;
-  {
-    std::ifstream c(lines[1] + ".contigs");
-    if (!c.is_open()) die("Cannot open file " + lines[1] + ".contigs for reading -- invalid index " + P.index);
-    std::string l;
-    while (std::getline(c, l)) { erase_nl(l); size_t t = l.find('\t'); if (t == std::string::npos) continue; meta.push_back(Contig{l.substr(t + 1), atoi(l.substr(0, t).c_str())}); }
+  const size_t nChunks = lines.size() - 1;
+  std::vector<std::string> queries = split(P.query, ","), prefixes = split(P.out, ",");
+  if (queries.size() != prefixes.size()) die("Please specify an equal number of input and output files (as comma-separated lists)");
+  std::vector<std::vector<std::string>> chunkFiles(prefixes.size());
+  for (size_t ci = 0; ci < nChunks; ci++) {                      // mapWrap.h:500-540: every chunk file in turn, then unifyFiles
+    const std::string& file = lines[ci + 1];
+    mm_index* idx = nullptr;
+    ck(mm_index_load(ctx, file.c_str(), &idx), "mm_index_load");
+    int32_t k = 0, w = 0; mm_index_params(idx, &k, &w, nullptr);
+    if (k != P.kmerSize || w != P.windowSize) die("Index file " + file + " does not match " + P.index + ".arguments");
+    std::vector<Contig> meta;
+    {
+      std::ifstream c(file + ".contigs");
+      if (!c.is_open()) die("Cannot open file " + file + ".contigs for reading -- invalid index " + P.index);
+      std::string l;
+      while (std::getline(c, l)) { erase_nl(l); size_t t = l.find('\t'); if (t == std::string::npos) continue; meta.push_back(Contig{l.substr(t + 1), atoi(l.substr(0, t).c_str())}); }
+    }
+    int32_t nCont = 0; mm_index_stats(idx, nullptr, nullptr, nullptr, &nCont, nullptr);
+    if ((size_t)nCont != meta.size()) die("Index file " + file + " and its .contigs file disagree");
+    print_index_info(idx);
+    map_queries(ctx, idx, meta, P, nChunks > 1 ? (int)ci : -1);
+    if (nChunks > 1) for (size_t fi = 0; fi < prefixes.size(); fi++) chunkFiles[fi].push_back(prefixes[fi] + "." + std::to_string(ci));
+    mm_index_destroy(idx);
   }
-  int32_t nCont = 0; mm_index_stats(idx, nullptr, nullptr, nullptr, &nCont, nullptr);
-  if ((size_t)nCont != meta.size()) die("Index file " + lines[1] + " and its .contigs file disagree");
-  print_index_info(idx);
-  map_queries(ctx, idx, meta, P);
-  mm_index_destroy(idx); mm_ctx_destroy(ctx);
+  if (nChunks > 1) for (size_t fi = 0; fi < prefixes.size(); fi++) unify_files(ctx, prefixes[fi], P, chunkFiles[fi], queries[fi]);
+  mm_ctx_destroy(ctx);
   return 0;
 }
 

@@ -158,6 +158,12 @@ struct Index {
   // contig-range shard of a larger reference: the sorted unique hashes and their local counts are kept after finalize() so
   // that mm_index_sync_threshold can derive the occurrence threshold of the WHOLE reference (winSketch.hpp:452-495)
   bool keepUnique = false; int32_t firstContig = 0; bool globalSynced = false; int32_t globalThreshold = 0x7fffffff;
+  // The reference under --maxmemory builds one Sketch object chunk after chunk WITHOUT resetting its occurrence histogram or its
+  // threshold (only minimizerIndex, minimizerPosLookupIndex and metadata are cleared, winSketch.hpp:302-304): chunk N's histogram is
+  // added to those of chunks 0..N-1 (:458-459), the walk uses chunk N's own unique count (:465-466), and freqThreshold keeps its
+  // previous value when the first bucket already overshoots (:471-488).  carryHist / carryThreshold = that state before this chunk,
+  // histCum = after it (mm_index_set_freq_carry / mm_index_get_freq_hist).
+  std::vector<std::pair<uint32_t, int64_t>> carryHist, histCum; int32_t carryThreshold = 0x7fffffff;
   DevBuf<uint32_t> uHash; DevBuf<int32_t> uCnt;
   // dups
   DevBuf<uint32_t> dupBits, dupIdx; DevBuf<uint64_t> dupLinks; DevBuf<uint2> dupRB; int64_t n_dup = 0;
@@ -189,6 +195,7 @@ struct Index {
     contigStart.ensure(h_contigStart.size()); h2d(rt, contigStart.p, h_contigStart.data(), sizeof(int64_t) * h_contigStart.size());
     contigLen.ensure(h_contigLen.size() + 1); h2d(rt, contigLen.p, h_contigLen.data(), sizeof(int32_t) * h_contigLen.size());
     finalized = true;
+    if (n == 0) { histCum = carryHist; freqThreshold = carryThreshold; }      // computeFreqHist does nothing on an empty chunk (:455)
     if (n == 0) {          // no minimizers (no contigs, or all shorter than w / k): every array exists, zeroed, so that save / load / map work
       table.ensure(1024); dev_memset(rt, table.p, 0, sizeof(Slot) * 1024); tableMask = 1023;
       miHash.ensure(1); miWs.ensure(1); posKey.ensure(1); hasSeq16 = n_contigs <= 65536; if (hasSeq16) posSeq16.ensure(8);
@@ -219,20 +226,29 @@ struct Index {
       std::vector<uint32_t> hv((size_t)nb); std::vector<int32_t> hc((size_t)nb);
       d2h(rt, hv.data(), cntUniq.p, sizeof(uint32_t) * (size_t)nb);
       d2h(rt, hc.data(), cntRuns.p, sizeof(int32_t) * (size_t)nb);
+      // this chunk's histogram on top of the carried one (empty unless the host walks reference chunks)
+      histCum = carryHist;
+      for (int64_t b = 0; b < nb; b++) histCum.emplace_back(hv[(size_t)b], (int64_t)hc[(size_t)b]);
+      std::sort(histCum.begin(), histCum.end());
+      { std::vector<std::pair<uint32_t, int64_t>> m; for (auto& p : histCum) { if (!m.empty() && m.back().first == p.first) m.back().second += p.second; else m.push_back(p); } histCum.swap(m); }
       float percentageThreshold = 0.001f;
       int64_t toIgnore = (int64_t)(n_unique * percentageThreshold / 100);
       int64_t sum = 0;
-      freqThreshold = 0x7fffffff;
-      for (int64_t b = nb - 1; b >= 0; b--) {
-        sum += hc[(size_t)b];
-        if (sum < toIgnore) freqThreshold = (int32_t)hv[(size_t)b];
-        else if (sum == toIgnore) { freqThreshold = (int32_t)hv[(size_t)b]; break; }
+      freqThreshold = carryThreshold;
+      for (int64_t b = (int64_t)histCum.size() - 1; b >= 0; b--) {
+        sum += histCum[(size_t)b].second;
+        if (sum < toIgnore) freqThreshold = (int32_t)histCum[(size_t)b].first;
+        else if (sum == toIgnore) { freqThreshold = (int32_t)histCum[(size_t)b].first; break; }
         else break;
       }
       cntSorted.release(); cntUniq.release(); cntRuns.release();
     }
 
-    uint64_t slots = 1024; while (slots < (uint64_t)n_unique * 2) slots <<= 1;
+    // load factor <= 0.25 (MM_TABLE_MULT=2: <= 0.5): most probes of a read MISS or collide in the saturated low end of the 32-bit
+    // hash space, and an unsuccessful linear probe walks (1 + 1/(1-a)^2)/2 slots: 2.7 at a = 0.52, 1.4 at a = 0.26 -- half the sectors
+    uint64_t mult = 4; if (const char* e = getenv("MM_TABLE_MULT")) { int v = atoi(e); if (v >= 2 && v <= 16) mult = (uint64_t)v; }
+    uint64_t slots = 1024; while (slots < (uint64_t)n_unique * mult) slots <<= 1;
+    if (slots > (1ull << 32)) { slots = 1024; while (slots < (uint64_t)n_unique * 2) slots <<= 1; }
     if (slots > (1ull << 32)) throw Error(-34, "hash table too large");
     table.ensure((size_t)slots); dev_memset(rt, table.p, 0, sizeof(Slot) * (size_t)slots);
     tableMask = (uint32_t)(slots - 1);

@@ -837,6 +837,22 @@ int mm_index_set_shard(mm_index* idx, int32_t first_contig_id, int32_t keep_coun
   idx->ix.firstContig = first_contig_id; idx->ix.keepUnique = keep_counts != 0;
   return MM_OK;
 }
+int mm_index_set_freq_carry(mm_index* idx, const int32_t* v, const int64_t* c, int32_t n, int32_t prev_threshold) {
+  if (!idx || n < 0 || (n > 0 && (!v || !c))) { g_err = "mm_index_set_freq_carry: bad arguments"; return MM_EINVAL; }
+  if (idx->ix.finalized) { g_err = "mm_index_set_freq_carry: call before mm_index_finalize"; return MM_EINVAL; }
+  idx->ix.carryHist.clear();
+  for (int32_t i = 0; i < n; i++) idx->ix.carryHist.emplace_back((uint32_t)v[i], c[i]);
+  idx->ix.carryThreshold = prev_threshold;
+  return MM_OK;
+}
+int mm_index_get_freq_hist(const mm_index* idx, int32_t* v, int64_t* c, int32_t cap, int32_t* n, int32_t* threshold) {
+  if (!idx || !idx->ix.finalized || !n) { g_err = "mm_index_get_freq_hist: index not finalized"; return MM_EINVAL; }
+  const auto& h = idx->ix.histCum;
+  *n = (int32_t)h.size();
+  for (int32_t i = 0; i < (int32_t)h.size() && i < cap; i++) { if (v) v[i] = (int32_t)h[(size_t)i].first; if (c) c[i] = h[(size_t)i].second; }
+  if (threshold) *threshold = idx->ix.freqThreshold;
+  return MM_OK;
+}
 int mm_index_sync_threshold(mm_index* idx, int32_t* global_threshold, int64_t* global_unique) {
   MM_TRY
   if (!idx || !idx->ix.finalized) throw Error(MM_EINVAL, "mm_index_sync_threshold: index not finalized");

@@ -1018,6 +1018,10 @@ struct BandSweep {
   // lands in the dummy slots.  An insertion can push q_istar out of the bottom-s, a deletion can let q_{istar+1} in;
   // both consult one gap counter and one match bit: rank istar-1 for the insertion, rank istar for the deletion.
   MM_HD void apply(uint32_t code, int32_t isDel) {
+    // the slots the move test may consult depend on istar alone: both are loaded up front, off the event's decode chain
+    const int32_t t0 = (istar > 0 ? istar - 1 : 0) - lo, t1 = istar - lo;       // insertion consults rank istar-1, deletion rank istar
+    const int32_t c0 = (int32_t)cnt[t0], c1 = (int32_t)cnt[t1];
+    const uint32_t w0 = mb[t0 >> 5], w1 = mb[t1 >> 5];
     const bool live = (code & (isDel ? CODE_DEL_NOP : CODE_INS_NOP)) == 0;
     const bool isM = (int32_t)code < 0;
     const int32_t idx = (int32_t)(code & CODE_IDX);
@@ -1031,10 +1035,9 @@ struct BandSweep {
     cnt[gslot] = (uint8_t)(v + d);
     const bool below = gv && idx < istar;
     C += below ? d : 0;
-    int32_t t = istar - 1 + isDel; t = t < 0 ? 0 : t;
-    const int32_t trel = t - lo;                             // inside the band by the out_of_band() invariant
-    const int32_t cX = (int32_t)cnt[trel];                   // after the update above (the gap may be the consulted one)
-    const int32_t mX = (int32_t)bit(trel);
+    const int32_t trel = isDel ? t1 : t0;                    // inside the band by the out_of_band() invariant
+    const int32_t cX = (isDel ? c1 : c0) + ((gin && gslot == trel) ? d : 0);   // after the update above (the gap may be the consulted one)
+    const int32_t mX = (int32_t)(((isDel ? w1 : w0) >> (trel & 31)) & 1u);
     const bool move = isDel ? (gv && istar < s && istar + 1 + C + cX <= s) : (below && istar + C > s);
     C -= move ? d * cX : 0; shared -= move ? d * mX : 0; istar -= move ? d : 0;
     const bool mv = live && isM;                             // a hash of the read sketch, rank idx
@@ -1103,13 +1106,35 @@ MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0
     if (z.fail || z.bad) { fail = true; active = false; }
   }
   int32_t best = 0, bpos = 0, lpos = 0, bistar = s, optS = 0, optE = 0, any = 0;
+  // The ORDER of the events (which cursor moves next, MIIteratorL2::next, MIIteratorL2.hpp:74-96) depends on the positions alone,
+  // not on the band state.  The loop is software-pipelined on that: while event k is applied to the state, event k+1 is
+  // already being merged out of the two streams, so the two dependency chains (merge, apply) overlap instead of adding up.
+  // merge side (one event ahead): evBeg / evBeg1 / evEnd, sw_pos, mbeg / mend;  p*: the event about to be applied.
   uint2 evBeg = make_uint2(0, 0), evBeg1 = evBeg, evEnd = evBeg;
   if (active) {
     ev.init(beg + 1, end);
     evBeg = ldg(e + beg); evBeg1 = ev.fetch(0, beg + 1); evEnd = ev.fetch(1, end);
   }
   int32_t sw_pos = (int32_t)(evBeg.y >> 1);
-  bool doEval = true;
+  int32_t mbeg = beg, mend = end;
+  uint32_t pCode = 0; int32_t pIsDel = 0, pWb = 0; bool pEval = false;
+  auto merge_step = [&]() {
+    const int32_t nb = (int32_t)(evBeg1.y >> 1) - sw_pos;      // MIIteratorL2::next
+    const int32_t ne = (int32_t)(evEnd.y >> 1) - (sw_pos + cmw - 1);
+    const int32_t isDel = nb <= ne ? 1 : 0;
+    pEval = nb != ne;                                           // a step that deletes AND inserts is evaluated after the insert
+    sw_pos += isDel ? nb : ne;
+    pCode = isDel ? evBeg.x : evEnd.x; pIsDel = isDel;
+    mbeg += isDel; mend += 1 - isDel;
+    const uint2 nx = ev.fetch(1 - isDel, isDel ? mbeg + 1 : mend);
+    evBeg = isDel ? evBeg1 : evBeg; evBeg1 = isDel ? nx : evBeg1; evEnd = isDel ? evEnd : nx;
+    pWb = (int32_t)(evBeg.y >> 1);                              // first element of the window after this event
+  };
+  if (active) {                                                 // the first window is evaluated before any event (computeMap.hpp:496-510)
+    lpos = sw_pos; any = 1;
+    if (z.shared > 0) { best = z.shared; bpos = sw_pos; optS = beg; optE = end; bistar = z.istar; }
+    merge_step();
+  }
 #ifdef MM_BAND_DEBUG
   int dbgIters = 0, dbgWin = end - beg, dbgReb = 0;
 #endif
@@ -1118,24 +1143,13 @@ MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0
 #ifdef MM_BAND_DEBUG
       dbgIters++;
 #endif
-      if (doEval) {
-        const int32_t wb = (int32_t)(evBeg.y >> 1);
-        const bool better = z.shared > best;
-        lpos = (z.shared >= best) ? wb : lpos;
-        if (better) { best = z.shared; optS = beg; optE = end; bpos = wb; bistar = z.istar; }
-        any = 1;
-      }
-      const int32_t nb = (int32_t)(evBeg1.y >> 1) - sw_pos;    // MIIteratorL2::next (MIIteratorL2.hpp:74-96)
-      const int32_t ne = (int32_t)(evEnd.y >> 1) - (sw_pos + cmw - 1);
-      const int32_t isDel = nb <= ne ? 1 : 0;
-      doEval = nb != ne;                                        // a step that deletes AND inserts is evaluated after the insert
-      sw_pos += isDel ? nb : ne;
-      z.apply(isDel ? evBeg.x : evEnd.x, isDel);
-      beg += isDel; end += 1 - isDel;
-      const uint2 nx = ev.fetch(1 - isDel, isDel ? beg + 1 : end);
-      evBeg = isDel ? evBeg1 : evBeg; evBeg1 = isDel ? nx : evBeg1; evEnd = isDel ? evEnd : nx;
+      const uint32_t code = pCode; const int32_t isDel = pIsDel, wb = pWb; const bool doEval = pEval;
+      beg += isDel; end += 1 - isDel;                           // the window this event produces
+      const bool more = end < last && beg < B1;
+      if (more) merge_step();                                   // event k+1: independent of the band state
+      z.apply(code, isDel);
 #if !defined(__CUDA_ARCH__)
-      if (z.out_of_band() && !z.fail) {
+      if (z.out_of_band() && !z.fail && more) {
 #ifdef MM_BAND_DEBUG
         dbgReb += end - beg;
 #endif
@@ -1143,7 +1157,12 @@ MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0
         if (z.bad) z.fail = true;
       }
 #endif
-      active = !z.fail && end < last && beg < B1;
+      active = !z.fail && more;
+      if (active && doEval) {
+        const bool better = z.shared > best;
+        lpos = (z.shared >= best) ? wb : lpos;
+        if (better) { best = z.shared; optS = beg; optE = end; bpos = wb; bistar = z.istar; }
+      }
     }
 #if defined(__CUDA_ARCH__)
     // istar left the band on some lanes: the whole warp rebuilds their states one after the other
@@ -1249,8 +1268,8 @@ struct RingEv {
   MM_DEV RingEv(const uint2* evArray, int64_t off, uint4* ring) : gbase(evArray + (off & ~(int64_t)1)), par((int32_t)(off & 1)), sb((uint32_t)__cvta_generic_to_shared(ring)) {}
   MM_DEV void load_pair(int32_t stream, int32_t pair) {
     const uint32_t dst = sb + (uint32_t)((stream * R + (pair & (R - 1))) * 512);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gbase + 2 * (int64_t)pair) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gbase + 2 * (int64_t)pair));
+    asm volatile("cp.async.commit_group;" ::);
   }
   MM_DEV void init(int32_t jb, int32_t je) {
     const int32_t pb = (jb + par) >> 1, pe = (je + par) >> 1;
@@ -1265,11 +1284,11 @@ struct RingEv {
     const int32_t jj = j + par;
     if ((jj & 1) == 0) {                      // entered a new pair: the one behind it is dead, reuse its slot
       load_pair(stream, (jj >> 1) + R - 1);
-      asm volatile("cp.async.wait_group %0;" ::"n"(R - 1) : "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(R - 1));
     }
     const uint32_t addr = sb + (uint32_t)((stream * R + ((jj >> 1) & (R - 1))) * 512 + (jj & 1) * 8);
     uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
   }
 };

@@ -167,3 +167,39 @@ def check_config2_golden(binary, workdir):
     assert mine and mine[0].strip() == thr[0].strip(), (mine, thr)          # same computeFreqHist line as the reference
     subprocess.run([binary, "classify", "--DB", "db", "--mappings", "out_b200/ref"], cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     return compare_dirs(gold, out), thr[0].strip()
+
+
+def check_maxmemory_golden(binary, workdir):
+    """The reference's --maxmemory chunk loop, including the occurrence histogram / threshold that it does NOT reset between
+    chunks (winSketch.hpp:302-304,452-495): our host, cutting at the same contig counts, must print the reference's three
+    thresholds (4, 7, 23) and write its mapping file byte for byte (tests/golden/ref_maxmemory, make_golden_maxmemory.py)."""
+    import gzip
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    import make_golden_maxmemory as g
+    g.maxmemory_sample(workdir)
+    src = os.path.join(root, "tests", "golden", "ref_maxmemory")
+    log = open(os.path.join(src, "map.log")).read().splitlines()
+    cuts = [l.split()[-1] for l in log if "storeCurrentState" in l]
+    thr = [l.strip() for l in log if "computeFreqHist" in l]
+    assert len(cuts) == 3 and len(thr) == 3 and len(set(thr)) == 3
+    out = os.path.join(workdir, "o_b200"); os.makedirs(out, exist_ok=True)
+    env = dict(os.environ, MM_HOST_CHUNK_CONTIGS=",".join(cuts))
+    p = subprocess.run([binary, "mapDirectly", *g.MAP_ARGS, "-r", "db/DB.fa", "-q", "reads.fq", "-o", "o_b200/ref", "-t", "4"], cwd=workdir, check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    mine = [l.strip() for l in p.stdout.splitlines() if "computeFreqHist" in l]
+    assert mine == thr, (mine, thr)
+    for fn in ("ref", "ref.meta", "ref.meta.unmappedReadsLengths"):
+        want = gzip.open(os.path.join(src, fn + ".gz"), "rb").read()
+        assert open(os.path.join(out, fn), "rb").read() == want, fn
+    # the same chunks through the persistent-index route: `index` writes three chunk files, `mapAgainstIndex` walks them
+    ix = os.path.join(workdir, "o_ix"); os.makedirs(ix, exist_ok=True)
+    subprocess.run([binary, "index", "-w", "2", "-r", "db/DB.fa", "-i", "o_ix/idx"], cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+    manifest = open(os.path.join(ix, "idx.index")).read().split()
+    assert manifest[0] == "1" and len(manifest) == 4, manifest                  # mapWrap.h:397-404: "1" + one line per chunk file
+    subprocess.run([binary, "mapAgainstIndex", "--all", "-i", "o_ix/idx", "-q", "reads.fq", "-o", "o_ix/ref", "-t", "4"], cwd=workdir, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    for fn in ("ref", "ref.meta", "ref.meta.unmappedReadsLengths"):
+        assert open(os.path.join(ix, fn), "rb").read() == open(os.path.join(out, fn), "rb").read(), fn
+    return thr

@@ -117,3 +117,8 @@ def test_cli_awkward_fastx_formatting_matches_live_reference(tmp_path, monkeypat
         subprocess.run([b, "classify", "--DB", "db", "--mappings", out + "/ref"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     assert cli_common.compare_dirs(os.path.join(d, "o_ref"), os.path.join(d, "o_emu")) >= 8
     assert int(open(os.path.join(d, "o_emu", "ref.meta")).read().split()[1]) == len(names)
+
+
+def test_cli_maxmemory_chunk_loop_matches_reference_fixture(tmp_path):
+    thr = cli_common.check_maxmemory_golden(build_emu_host(), str(tmp_path))
+    assert [t.split(">= ")[1].split()[0] for t in thr] == ["4", "7", "23"]

@@ -361,3 +361,14 @@ def test_pinned_result_buffers(gpu_ctx, small_workload):
 
 def test_multi_batch_classify_table_and_top_mappings_filter(gpu_ctx, small_workload):
     common.check_multi_batch_classify(gpu_ctx, small_workload)
+
+
+def test_cli_maxmemory_chunk_loop_matches_reference_fixture(tmp_path):
+    """--maxmemory analogue on the GPU: three reference chunks with the reference's carried (non-reset) occurrence histogram,
+    through mapDirectly's chunk loop and through a three-file persistent index; see cli_common.check_maxmemory_golden."""
+    import os
+    from metamaps_b200 import build
+    from tests import cli_common
+    assert os.path.exists(build.HOST_BIN), "metamaps_b200/metamaps not built"
+    thr = cli_common.check_maxmemory_golden(build.HOST_BIN, str(tmp_path))
+    assert [t.split(">= ")[1].split()[0] for t in thr] == ["4", "7", "23"]
