@@ -103,7 +103,8 @@ int mm_index_set_shard(mm_index* idx, int32_t first_contig_id, int32_t keep_coun
  * unique count, and keeps chunk N-1's value when the first bucket overshoots.  A host that walks chunks reproduces that by
  * carrying the state: mm_index_get_freq_hist after chunk N-1's finalize (count_value[i] occurrences are shared by n_hashes[i]
  * hashes; *n_buckets entries, at most cap are written; *threshold = the chunk's threshold), mm_index_set_freq_carry before chunk
- * N's finalize.  Without a carry an index computes the threshold of its own contigs, i.e. chunk 0's / the unchunked behaviour. */
+ * N's finalize -- or after it (the threshold is applied at probe time), which is what ranks building their chunks concurrently
+ * do once the earlier chunks' histograms are known.  Without a carry an index computes the threshold of its own contigs, i.e. chunk 0's / the unchunked behaviour. */
 int mm_index_set_freq_carry(mm_index* idx, const int32_t* count_value, const int64_t* n_hashes, int32_t n_buckets, int32_t prev_threshold);
 int mm_index_get_freq_hist(const mm_index* idx, int32_t* count_value, int64_t* n_hashes, int32_t cap, int32_t* n_buckets, int32_t* threshold);
 int mm_index_sync_threshold(mm_index* idx, int32_t* global_threshold, int64_t* global_unique);

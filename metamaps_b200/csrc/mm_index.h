@@ -163,7 +163,26 @@ struct Index {
   // added to those of chunks 0..N-1 (:458-459), the walk uses chunk N's own unique count (:465-466), and freqThreshold keeps its
   // previous value when the first bucket already overshoots (:471-488).  carryHist / carryThreshold = that state before this chunk,
   // histCum = after it (mm_index_set_freq_carry / mm_index_get_freq_hist).
-  std::vector<std::pair<uint32_t, int64_t>> carryHist, histCum; int32_t carryThreshold = 0x7fffffff;
+  std::vector<std::pair<uint32_t, int64_t>> carryHist, histOwn, histCum; int32_t carryThreshold = 0x7fffffff;
+  // histCum / freqThreshold from histOwn + the carry (finalize, and again whenever the carry is set on a finalized index: ranks
+  // that build their chunks concurrently learn the earlier chunks' histograms afterwards)
+  void apply_carry() {
+    if (n == 0) { histCum = carryHist; freqThreshold = carryThreshold; return; }      // computeFreqHist does nothing on an empty chunk (:455)
+    histCum = carryHist;
+    histCum.insert(histCum.end(), histOwn.begin(), histOwn.end());
+    std::sort(histCum.begin(), histCum.end());
+    { std::vector<std::pair<uint32_t, int64_t>> m; for (auto& p : histCum) { if (!m.empty() && m.back().first == p.first) m.back().second += p.second; else m.push_back(p); } histCum.swap(m); }
+    float percentageThreshold = 0.001f;
+    int64_t toIgnore = (int64_t)(n_unique * percentageThreshold / 100);
+    int64_t sum = 0;
+    freqThreshold = carryThreshold;
+    for (int64_t b = (int64_t)histCum.size() - 1; b >= 0; b--) {
+      sum += histCum[(size_t)b].second;
+      if (sum < toIgnore) freqThreshold = (int32_t)histCum[(size_t)b].first;
+      else if (sum == toIgnore) { freqThreshold = (int32_t)histCum[(size_t)b].first; break; }
+      else break;
+    }
+  }
   DevBuf<uint32_t> uHash; DevBuf<int32_t> uCnt;
   // dups
   DevBuf<uint32_t> dupBits, dupIdx; DevBuf<uint64_t> dupLinks; DevBuf<uint2> dupRB; int64_t n_dup = 0;
@@ -195,7 +214,7 @@ struct Index {
     contigStart.ensure(h_contigStart.size()); h2d(rt, contigStart.p, h_contigStart.data(), sizeof(int64_t) * h_contigStart.size());
     contigLen.ensure(h_contigLen.size() + 1); h2d(rt, contigLen.p, h_contigLen.data(), sizeof(int32_t) * h_contigLen.size());
     finalized = true;
-    if (n == 0) { histCum = carryHist; freqThreshold = carryThreshold; }      // computeFreqHist does nothing on an empty chunk (:455)
+    if (n == 0) apply_carry();
     if (n == 0) {          // no minimizers (no contigs, or all shorter than w / k): every array exists, zeroed, so that save / load / map work
       table.ensure(1024); dev_memset(rt, table.p, 0, sizeof(Slot) * 1024); tableMask = 1023;
       miHash.ensure(1); miWs.ensure(1); posKey.ensure(1); hasSeq16 = n_contigs <= 65536; if (hasSeq16) posSeq16.ensure(8);
@@ -227,20 +246,9 @@ struct Index {
       d2h(rt, hv.data(), cntUniq.p, sizeof(uint32_t) * (size_t)nb);
       d2h(rt, hc.data(), cntRuns.p, sizeof(int32_t) * (size_t)nb);
       // this chunk's histogram on top of the carried one (empty unless the host walks reference chunks)
-      histCum = carryHist;
-      for (int64_t b = 0; b < nb; b++) histCum.emplace_back(hv[(size_t)b], (int64_t)hc[(size_t)b]);
-      std::sort(histCum.begin(), histCum.end());
-      { std::vector<std::pair<uint32_t, int64_t>> m; for (auto& p : histCum) { if (!m.empty() && m.back().first == p.first) m.back().second += p.second; else m.push_back(p); } histCum.swap(m); }
-      float percentageThreshold = 0.001f;
-      int64_t toIgnore = (int64_t)(n_unique * percentageThreshold / 100);
-      int64_t sum = 0;
-      freqThreshold = carryThreshold;
-      for (int64_t b = (int64_t)histCum.size() - 1; b >= 0; b--) {
-        sum += histCum[(size_t)b].second;
-        if (sum < toIgnore) freqThreshold = (int32_t)histCum[(size_t)b].first;
-        else if (sum == toIgnore) { freqThreshold = (int32_t)histCum[(size_t)b].first; break; }
-        else break;
-      }
+      histOwn.clear();
+      for (int64_t b = 0; b < nb; b++) histOwn.emplace_back(hv[(size_t)b], (int64_t)hc[(size_t)b]);
+      apply_carry();
       cntSorted.release(); cntUniq.release(); cntRuns.release();
     }
 

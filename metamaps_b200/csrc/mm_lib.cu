@@ -839,10 +839,11 @@ int mm_index_set_shard(mm_index* idx, int32_t first_contig_id, int32_t keep_coun
 }
 int mm_index_set_freq_carry(mm_index* idx, const int32_t* v, const int64_t* c, int32_t n, int32_t prev_threshold) {
   if (!idx || n < 0 || (n > 0 && (!v || !c))) { g_err = "mm_index_set_freq_carry: bad arguments"; return MM_EINVAL; }
-  if (idx->ix.finalized) { g_err = "mm_index_set_freq_carry: call before mm_index_finalize"; return MM_EINVAL; }
+  if (idx->ix.globalSynced) { g_err = "mm_index_set_freq_carry: the index already carries the threshold of the unchunked reference (mm_index_sync_threshold)"; return MM_EINVAL; }
   idx->ix.carryHist.clear();
   for (int32_t i = 0; i < n; i++) idx->ix.carryHist.emplace_back((uint32_t)v[i], c[i]);
   idx->ix.carryThreshold = prev_threshold;
+  if (idx->ix.finalized) idx->ix.apply_carry();       // the threshold is applied at probe time: it may be settled after the build
   return MM_OK;
 }
 int mm_index_get_freq_hist(const mm_index* idx, int32_t* v, int64_t* c, int32_t cap, int32_t* n, int32_t* threshold) {
@@ -988,19 +989,25 @@ struct ReadRangeFn {        // first mapping with read >= lo / >= hi in the read
     out[i] = a;
   }
 };
-// table -> sorted by read, stable (a read's mappings keep their part order = contig order)
-static void maptable_sort(mm_ctx* c, int32_t n_reads_hint) {
+// table -> sorted by read, stable (a read's mappings keep their part order = contig order).  bySeq: the parts did not arrive in
+// contig order (ranks that own interleaved chunks of the reference): order by (read, contig) with two stable passes -- mappings on
+// the same contig come from one part and keep their (position) order
+static void maptable_sort(mm_ctx* c, int32_t n_reads_hint, bool bySeq = false) {
   Classifier& cl = c->cls; MapTable& t = cl.tab; Runtime& rt = c->rt;
   if (t.n <= 1) { t.sorted = true; return; }
   cl.keyA.ensure((size_t)t.n); cl.keyB.ensure((size_t)t.n); cl.permA.ensure((size_t)t.n); cl.permB.ensure((size_t)t.n); cl.tmpI.ensure((size_t)t.n);
-  foreach(rt, t.n, IotaU32Fn{cl.permA.p});
-  int bits = 1; while (bits < 32 && ((int64_t)1 << bits) <= (int64_t)(n_reads_hint > 1 ? n_reads_hint : 2)) bits++;
-  c->pr.sort_pairs<uint32_t, uint32_t>((const uint32_t*)t.read.p, cl.keyB.p, cl.permA.p, cl.permB.p, t.n, bits);
   DevBuf<int32_t>* cols[6] = {&t.read, &t.seq, &t.pos, &t.shared, &t.sketch, &t.strand};
-  for (auto* col : cols) {
-    foreach(rt, t.n, GatherI32Fn{cl.permB.p, col->p, cl.tmpI.p});
-    d2d(rt, col->p, cl.tmpI.p, 4 * (size_t)t.n);
-  }
+  auto pass = [&](const int32_t* key, int bits) {
+    foreach(rt, t.n, IotaU32Fn{cl.permA.p});
+    c->pr.sort_pairs<uint32_t, uint32_t>((const uint32_t*)key, cl.keyB.p, cl.permA.p, cl.permB.p, t.n, bits);
+    for (auto* col : cols) {
+      foreach(rt, t.n, GatherI32Fn{cl.permB.p, col->p, cl.tmpI.p});
+      d2d(rt, col->p, cl.tmpI.p, 4 * (size_t)t.n);
+    }
+  };
+  if (bySeq) pass(t.seq.p, 31);
+  int bits = 1; while (bits < 32 && ((int64_t)1 << bits) <= (int64_t)(n_reads_hint > 1 ? n_reads_hint : 2)) bits++;
+  pass(t.read.p, bits);
   t.sorted = true;
 }
 int mm_classify_setup(mm_ctx* c, const int64_t* contig_len, const int32_t* contig_taxon, int32_t n_contigs, int32_t T) {
@@ -1082,7 +1089,7 @@ int mm_classify_exchange(mm_ctx* c, int32_t read_lo, int32_t read_hi, int64_t* n
       pos += cnt[(size_t)r];
     }
     t.n = tot; t.sorted = false;
-    maptable_sort(c, (int32_t)cl.readsSeen);
+    maptable_sort(c, (int32_t)cl.readsSeen, true);      // ranks may own interleaved contig ranges: order by (read, contig)
     // 4. this rank finalises the reads [read_lo, read_hi)
     DevBuf<int64_t> rg; rg.ensure(2);
     foreach(rt, 2, ReadRangeFn{t.read.p, t.n, read_lo, read_hi, rg.p});

@@ -175,3 +175,86 @@ def _nloc(tax, m_seq, m_read, L, contig_len, contig_taxon, n_taxa):
         pos = np.minimum(pos, len(u) - 1)
         seen = np.where(u[pos] == allkey, cnt[pos], 0)
     return (big + seen).astype(np.float64)
+
+
+# ---- the reference's --maxmemory chunk chain (winSketch.hpp:284-329,452-495) for chunks built anywhere ------------------------
+def walk_freq_threshold(cum_hist: dict, n_unique: int, prev_threshold: int) -> int:
+    """computeFreqHist's walk (winSketch.hpp:462-488): cumulative histogram {occurrences: hashes}, THIS chunk's unique count,
+    the threshold left by the previous chunk."""
+    to_ignore = int(np.float32(np.float32(n_unique) * np.float32(0.001)) / np.float32(100))      # int64 * float -> float, / int -> float
+    thr = prev_threshold; s_ = 0
+    for k_ in sorted(cum_hist, reverse=True):
+        s_ += cum_hist[k_]
+        if s_ < to_ignore:
+            thr = k_
+        elif s_ == to_ignore:
+            thr = k_
+            break
+        else:
+            break
+    return thr
+
+
+def chunk_chain(own_hists: list, n_uniques: list):
+    """own_hists[c] = [(occurrences, hashes)] of chunk c alone, in chunk order.  Returns per chunk (carry histogram before it,
+    threshold before it, its own threshold) -- what mm_index_set_freq_carry needs for chunk c and what it must then report."""
+    INT_MAX = 0x7fffffff
+    cum: dict = {}; thr = INT_MAX; out = []
+    for own, nu in zip(own_hists, n_uniques):
+        carry = sorted(cum.items()); prev = thr
+        if nu > 0:
+            for k_, v in own:
+                cum[k_] = cum.get(k_, 0) + v
+            thr = walk_freq_threshold(cum, nu, prev)
+        out.append((carry, prev, thr))
+    return out
+
+
+def map_and_classify_streamed(ctx: capi.Context, build_chunk, chunk_ids: list, n_chunks: int, all_gather, *, dev_ptr=None, reads=None, offsets=None,
+                              contig_len, contig_taxon, n_taxa: int, perc_identity: float = 80.0, min_read_len: int = 1000, em_max_iter: int = 0,
+                              read_range=None, stats: dict | None = None):
+    """Config 5's shape: a reference too large to be resident is walked as `n_chunks` contig-range chunks, one resident at a time
+    per GPU (`build_chunk(c)` -> capi.Index with .first_contig set, NOT carrying a threshold yet), this rank owning `chunk_ids`
+    (ascending; ranks interleave: rank g of N owns g, g + N, ...).  Thresholds follow the reference's chunk chain (non-reset
+    histogram): after each round of builds the ranks all-gather (`all_gather(obj) -> list`, e.g. torch.distributed
+    all_gather_object; identity for one rank) the own histograms of that round's chunks and settle their carries.  Every chunk
+    maps ALL reads; the tables are exchanged and merged by (read, contig) on the device at the end."""
+    ctx.classify_setup(contig_len, contig_taxon, n_taxa)
+    ctx.classify_begin()
+    rounds = max(len(ids) for ids in all_gather(list(chunk_ids)))
+    known: dict = {}                       # chunk id -> (own histogram, n_unique), learnt round by round
+    gpu_ms = 0.0; launches = 0; summary = None; thresholds = {}
+    for t in range(rounds):
+        c = chunk_ids[t] if t < len(chunk_ids) else None
+        ix = None; mine = None
+        if c is not None:
+            ix = build_chunk(c)
+            mine = (c, ix.freq_hist()[0], ix.stats()["n_unique"])
+        for item in all_gather(mine):
+            if item is not None:
+                known[item[0]] = (item[1], item[2])
+        if c is not None:
+            upto = sorted(k_ for k_ in known if k_ <= c)
+            assert upto == list(range(c + 1)), "chunks must become known in order (interleaved ownership, one round at a time)"
+            chain = chunk_chain([known[k_][0] for k_ in upto], [known[k_][1] for k_ in upto])
+            carry, prev, thr = chain[c]
+            ix.set_freq_carry(carry, prev)
+            assert ix.stats()["freq_threshold"] == thr, (ix.stats()["freq_threshold"], thr)
+            thresholds[c] = thr
+            res = capi.map_reads(ctx, ix, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, offsets=offsets, fetch=False)
+            gpu_ms += res["gpu_ms"]; launches += res["launches"]
+            if stats is not None:
+                stats["map"] = res["stats"]
+            ctx.classify_add(ix.first_contig)
+            if summary is None:
+                summary = dict(res["summary"])
+            else:
+                for k_ in ("n_candidates", "n_mappings"):
+                    summary[k_] += res["summary"][k_]
+            ix.close()
+    if read_range is not None and ctx.n_ranks_hint > 1:
+        ctx.classify_exchange(read_range[0], read_range[1])
+    out = _classify_on_device(ctx, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa, em_max_iter=em_max_iter, wall=None)
+    out["summary"] = summary; out["thresholds"] = thresholds
+    out["gpu_ms"] += gpu_ms; out["launches"] += launches
+    return out

@@ -113,3 +113,85 @@ def test_contig_shards_two_ranks_equal_unsharded_reference(tmp_path):
         assert np.abs(p["post"] - ref["em"]["posterior"][sel]).max() <= 1e-6
     assert np.array_equal(parts[0]["f"], parts[1]["f"])
     assert sum(len(p["read"]) for p in parts) == len(ref["read"])
+
+
+# ---------------------------------------------------------------------------------------------- streamed, interleaved chunks
+def _stream_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from metamaps_b200 import capi, pipeline
+    from tests.conftest import build_emu
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    lib = capi.load(build_emu())
+    ctx = capi.Context(0, lib)
+
+    def allreduce(a):
+        dist.all_reduce(torch.from_numpy(a))
+    ctx.set_allreduce(allreduce); ctx.set_rank(world, rank)
+    contigs, reads, cuts, contig_taxon, contig_len, T = _stream_case()
+    bounds = np.concatenate([[0], np.cumsum(cuts)])
+
+    def build_chunk(c):
+        ix = capi.Index(ctx, 16, 10); ix.set_shard(int(bounds[c]), keep_counts=False); ix.add(contigs[bounds[c]:bounds[c + 1]]); ix.finalize()
+        return ix
+
+    def all_gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    n = len(reads); lo, hi = rank * n // world, (rank + 1) * n // world
+    res = pipeline.map_and_classify_streamed(ctx, build_chunk, list(range(rank, len(cuts), world)), len(cuts), all_gather, reads=reads, contig_len=contig_len,
+                                             contig_taxon=contig_taxon, n_taxa=T, read_range=(lo, hi))
+    from tests import common
+    np.savez(os.path.join(tmp, f"stream{rank}.npz"), lo=lo, hi=hi, f=res["em"]["f"], iters=res["em"]["iters"], thr=np.array(sorted(res["thresholds"].items())),
+             **{k_: res[k_] for k_ in common.MAPPING_KEYS})
+    dist.destroy_process_group()
+
+
+def _stream_case():
+    """Five chunks of a small reference with planted repeats, so that the carried (non-reset) histogram changes the thresholds."""
+    rng = np.random.default_rng(17)
+    from metamaps_b200 import synth
+    n_contigs, L = 10, 600_000
+    contigs = [rng.integers(0, 4, L, dtype=np.uint8) for _ in range(n_contigs)]
+    for copies in (60, 45, 30):
+        u = rng.integers(0, 4, 25, dtype=np.uint8)
+        for _ in range(copies):
+            ci = int(rng.integers(0, n_contigs)); pos = int(rng.integers(0, L - 50)); contigs[ci][pos:pos + 25] = u
+    db = synth.SynthDB([f"C{i}|kraken:taxid|{i + 1}|x" for i in range(n_contigs)], [str(i + 1) for i in range(n_contigs)], contigs)
+    _, reads, _ = synth.make_reads(db, 18, 50, 2500, err=0.08)
+    return ([synth.codes_to_ascii(c) for c in contigs], [synth.codes_to_ascii(r) for r in reads], [2, 2, 2, 2, 2],
+            np.arange(n_contigs, dtype=np.int32), np.full(n_contigs, L, np.int64), n_contigs)
+
+
+def test_streamed_interleaved_chunks_two_ranks_equal_the_one_process_chunk_walk(tmp_path):
+    """Config 5's driver logic at world size 2 (gloo): rank g owns chunks g, g+2, ...; after every round of builds the ranks
+    exchange the chunks' own occurrence histograms and settle the reference's carried thresholds; all reads are mapped against
+    every chunk; the tables are merged by (read, contig).  Must equal ONE process walking the five chunks in order."""
+    from metamaps_b200 import capi, pipeline
+    from tests import common
+    from tests.conftest import build_emu
+    lib = capi.load(build_emu())
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_stream_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ctx = capi.Context(0, lib)
+    contigs, reads, cuts, contig_taxon, contig_len, T = _stream_case()
+    bounds = np.concatenate([[0], np.cumsum(cuts)])
+
+    def build_chunk(c):
+        ix = capi.Index(ctx, 16, 10); ix.set_shard(int(bounds[c]), keep_counts=False); ix.add(contigs[bounds[c]:bounds[c + 1]]); ix.finalize()
+        return ix
+    ref = pipeline.map_and_classify_streamed(ctx, build_chunk, list(range(len(cuts))), len(cuts), lambda o: [o], reads=reads, contig_len=contig_len,
+                                             contig_taxon=contig_taxon, n_taxa=T)
+    thr = sorted(ref["thresholds"].items())
+    assert len(set(t for _, t in thr)) > 1, thr            # the carried histogram really changes the thresholds along the chain
+    parts = [np.load(os.path.join(str(tmp_path), f"stream{r}.npz")) for r in range(2)]
+    seen = {}
+    for p in parts:
+        seen.update({int(a): int(b) for a, b in p["thr"]})
+        sel = (ref["read"] >= int(p["lo"])) & (ref["read"] < int(p["hi"]))
+        for key in common.MAPPING_KEYS:
+            assert np.array_equal(p[key], ref[key][sel]), key
+        assert int(p["iters"]) == ref["em"]["iters"] and np.abs(p["f"] - ref["em"]["f"]).max() <= 1e-6
+    assert sorted(seen.items()) == thr
