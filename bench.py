@@ -192,23 +192,28 @@ def reference_sample(wl, n_contigs, n_reads, outdir):
     return fa, fq, bases, len(db.contig_codes)
 
 
-def run_cli_once(binary, d, wl, threads, out="out"):
+def run_cli_once(binary, d, wl, threads, out="out", timing=None):
     """mapDirectly + classify with a `metamaps` CLI (the reference's, or this repo's).  Returns (seconds spent mapping +
     classifying, seconds of index build, wall seconds of both commands).  The reference builds its index inside mapDirectly;
     its own log line gives the mapping time."""
     import re
     os.makedirs(os.path.join(d, out), exist_ok=True)
+    env = dict(os.environ, MM_HOST_TIMING="1") if timing is not None else None
     t0 = time.time()
     p = subprocess.run([binary, "mapDirectly", "--all", "-r", "db/DB.fa", "-q", "reads.fq", "-o", out + "/ref", "-m", str(wl["min_read_len"]),
-                        "-w", str(wl["w"]), "-t", str(threads)], cwd=d, capture_output=True, text=True)
+                        "-w", str(wl["w"]), "-t", str(threads)], cwd=d, capture_output=True, text=True, env=env)
     t_map_total = time.time() - t0
     if p.returncode != 0:
         raise RuntimeError(os.path.basename(binary) + " mapDirectly failed: " + p.stderr[-500:])
     m = re.search(r"Time spent mapping the query : ([0-9.eE+-]+) sec", p.stdout)
     t_map = float(m.group(1)) if m else t_map_total
     t1 = time.time()
-    p = subprocess.run([binary, "classify", "--DB", "db", "--mappings", out + "/ref", "-t", str(threads)], cwd=d, capture_output=True, text=True)
+    if timing is not None:
+        timing.append("mapDirectly %.3f s: " % t_map_total + "; ".join(l[len("[host timing] "):] for l in p.stderr.splitlines() if l.startswith("[host timing]")))
+    p = subprocess.run([binary, "classify", "--DB", "db", "--mappings", out + "/ref", "-t", str(threads)], cwd=d, capture_output=True, text=True, env=env)
     t_cls = time.time() - t1
+    if timing is not None:
+        timing.append("classify %.3f s: " % t_cls + "; ".join(l[len("[host timing] "):] for l in p.stderr.splitlines() if l.startswith("[host timing]")))
     if p.returncode != 0:
         raise RuntimeError(os.path.basename(binary) + " classify failed: " + p.stderr[-500:])
     return t_map + t_cls, t_map_total - t_map, t_map_total + t_cls
@@ -562,7 +567,8 @@ def same_config_leg(d, wl, bases, ref_map_cls_s, ref_index_s, ref_wall_s, thread
     if not os.path.exists(build.HOST_BIN):
         return {"error": "metamaps_b200/metamaps not built"}
     run_cli_once(build.HOST_BIN, d, wl, threads, out="out_b200")          # warm-up: CUDA context creation, page cache
-    g_map_cls, _, g_wall = run_cli_once(build.HOST_BIN, d, wl, threads, out="out_b200")
+    host_timing = []
+    g_map_cls, _, g_wall = run_cli_once(build.HOST_BIN, d, wl, threads, out="out_b200", timing=host_timing)
     ok = True; identical = 0; err = None
     try:
         identical = cli_common.compare_dirs(os.path.join(d, "out"), os.path.join(d, "out_b200"))
@@ -591,7 +597,7 @@ def same_config_leg(d, wl, bases, ref_map_cls_s, ref_index_s, ref_wall_s, thread
             "gpu_cli_s": g_wall, "ref_s": ref_wall_s, "ratio": ref_wall_s / g_wall if g_wall > 0 else None,
             "ref_map_plus_classify_s": ref_map_cls_s, "ref_index_build_s": ref_index_s, "ref_threads": threads,
             "gpu_cli_Mbp_per_s": bases / 1e6 / g_wall, "ref_Mbp_per_s_whole_run": bases / 1e6 / ref_wall_s,
-            "outputs_match": ok, "files_identical": identical, "files_compared": 10, "mismatch": err,
+            "gpu_cli_phases": host_timing, "outputs_match": ok, "files_identical": identical, "files_compared": 10, "mismatch": err,
             "note": "wall clock of the two commands of each CLI, process start to exit (the GPU side includes CUDA context creation, FASTA parsing and its index build)"}
 
 

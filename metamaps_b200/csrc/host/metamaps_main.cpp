@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <charconv>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <deque>
@@ -33,6 +34,14 @@
 #include "mm_fastx.hpp"
 
 namespace {
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// MM_HOST_TIMING=1: wall-clock split of the host stages on stderr (the bench's same-config leg records it)
+struct PhaseTimer {
+  const char* name; double t0; bool on;
+  explicit PhaseTimer(const char* n) : name(n), t0(now_s()), on(getenv("MM_HOST_TIMING") != nullptr) {}
+  ~PhaseTimer() { if (on) fprintf(stderr, "[host timing] %s %.3f s\n", name, now_s() - t0); }
+};
 
 [[noreturn]] void die(const std::string& m) { std::cerr << m << std::endl; exit(1); }
 void ck(int rc, const char* what) { if (rc != 0) die(std::string(what) + ": " + mm_last_error()); }
@@ -169,6 +178,7 @@ static mm_index* build_index_chunk(mm_ctx* ctx, const Params& P, mmhost::FastxRe
   return idx;
 }
 static mm_index* build_reference_index(mm_ctx* ctx, const Params& P, std::vector<Contig>& meta) {
+  PhaseTimer pt("reference: parse FASTA + index build");
   mm_index* idx = nullptr; ck(mm_index_create(ctx, P.kmerSize, P.windowSize, &idx), "mm_index_create");
   {
     mmhost::FastxReader rd(P.ref);
@@ -257,6 +267,7 @@ static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& m
   size_t capBytes = (size_t)256 << 20;
   if (const char* e = getenv("MM_HOST_BATCH_BYTES")) { long long v = atoll(e); if (v >= 1024) capBytes = (size_t)v; }     // tests: several batches on small inputs
   for (size_t fi = 0; fi < queries.size(); fi++) {
+    PhaseTimer pt("queries: parse + map + format + write");
     const std::string prefix = chunk < 0 ? prefixes[fi] : prefixes[fi] + "." + std::to_string(chunk);
     FILE* out = fopen(prefix.c_str(), "wb");
     if (!out) die("Cannot open output file " + prefix);
@@ -316,6 +327,7 @@ static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& m
     // GPU thread (this one): K0-K5 + identity + mapping quality per batch, results straight from the device-resident table
     std::unique_ptr<ReadBatch> rb;
     while (parsed.pop(rb)) {
+      PhaseTimer pb("  batch: GPU calls");
       const int32_t n = (int32_t)rb->names.size();
       mm_map_params mp{P.percentageIdentity, P.minReadLength, P.reportAll ? 1 : 0, 0};
       mm_map_summary sum;
@@ -415,7 +427,8 @@ int run_mapDirectly(int argc, char** argv) {
   int device = 0;
   Params P = parse_map_options(argc, argv, 0, &device);
   print_params(P);
-  mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
+  mm_ctx* ctx = nullptr;
+  { PhaseTimer pt("mm_ctx_create (CUDA context)"); ck(mm_ctx_create(device, &ctx), "mm_ctx_create"); }
   // Does the index fit the device?  ~75 bytes per minimizer while it is being built (8 + 8 + 2 resident, 32 of table at load
   // 0.5, sort temporaries), 2/(w+1) minimizers per base; --maxmemory (GB) caps the budget like in the reference.
   int64_t freeB = 0, totalB = 0; ck(mm_ctx_mem_info(ctx, &freeB, &totalB), "mm_ctx_mem_info");
@@ -628,6 +641,7 @@ double binom_cdf_host(long k, long n, double p) {
 }
 
 void classify_one(const std::string& DB, const std::string& mapped, int device, size_t minReadsPerBest) {
+  PhaseTimer pt("classify: whole");
   // ---- read the mappings file, grouped by consecutive read id (fEM.h:1167-1214)
   std::vector<std::vector<std::string>> fields; std::vector<int64_t> readOff{0}; std::vector<std::string> lines;
   {
@@ -693,6 +707,7 @@ void classify_one(const std::string& DB, const std::string& mapped, int device, 
   }
   // ---- EM on the GPU (fEM.h:491-661)
   std::cout << "Starting EM..." << std::endl;
+  PhaseTimer pem("classify: CUDA context + EM");
   mm_ctx* ctx = nullptr; ck(mm_ctx_create(device, &ctx), "mm_ctx_create");
   int32_t Tn = (int32_t)taxa.size(), iters = 0;
   std::vector<double> f((size_t)Tn), post(M), ll(4096); std::vector<int64_t> best((size_t)std::max<int64_t>(nReads, 1));

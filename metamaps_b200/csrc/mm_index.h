@@ -252,9 +252,9 @@ struct Index {
       cntSorted.release(); cntUniq.release(); cntRuns.release();
     }
 
-    // load factor <= 0.25 (MM_TABLE_MULT=2: <= 0.5): most probes of a read MISS or collide in the saturated low end of the 32-bit
-    // hash space, and an unsuccessful linear probe walks (1 + 1/(1-a)^2)/2 slots: 2.7 at a = 0.52, 1.4 at a = 0.26 -- half the sectors
-    uint64_t mult = 4; if (const char* e = getenv("MM_TABLE_MULT")) { int v = atoi(e); if (v >= 2 && v <= 16) mult = (uint64_t)v; }
+    // load factor <= 0.5.  (MM_TABLE_MULT=4 halves it: measured on config 2, the probe kernel went 2.90 -> 2.71 ms for 10 GB more
+    // table -- its 135 B of DRAM traffic per probe are 64-byte bursts around random 16-byte slots, not probe-sequence length)
+    uint64_t mult = 2; if (const char* e = getenv("MM_TABLE_MULT")) { int v = atoi(e); if (v >= 2 && v <= 16) mult = (uint64_t)v; }
     uint64_t slots = 1024; while (slots < (uint64_t)n_unique * mult) slots <<= 1;
     if (slots > (1ull << 32)) { slots = 1024; while (slots < (uint64_t)n_unique * 2) slots <<= 1; }
     if (slots > (1ull << 32)) throw Error(-34, "hash table too large");
