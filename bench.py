@@ -521,13 +521,13 @@ def main():
         "detail": detail,
     }
     extra = {}
+    del r_asc, r_host, out, o2
+    holder = [ix]; del ix
+    torch.cuda.empty_cache()
     if not args.no_extras:
-        try:
-            extra.update(extra_legs(args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, codes, asc, offsets, ix, by_contigs, build_index, own,
-                                    all_blocks_reads, common, barrier, max_over_ranks, sum_over_ranks, n_contigs))
-        except Exception as e:          # an extra leg never costs the bench line
-            extra["error"] = "%s: %s" % (type(e).__name__, e)
-    del ix
+        extra_legs(extra, args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, codes, asc, offsets, holder, by_contigs, build_index, own,
+                   all_blocks_reads, common, barrier, max_over_ranks, sum_over_ranks, n_contigs)
+    holder.clear()
     if rank == 0 and world == 1 and not args.no_extras and args.workload == "config2":
         try:
             extra["config4_em"] = config4_run(args, dict(WORKLOADS["config4"], n_reads=args.config4_reads), torch, dev, ctx, capi, pipeline, full=False)
@@ -602,9 +602,10 @@ def same_config_leg(d, wl, bases, ref_map_cls_s, ref_index_s, ref_wall_s, thread
 
 
 # ------------------------------------------------------------------------------------------ extra legs
-def extra_legs(args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, codes, asc, offsets, ix_main, by_contigs, build_index, own, all_blocks_reads,
+def extra_legs(extra, args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, codes, asc, offsets, holder, by_contigs, build_index, own, all_blocks_reads,
                common, barrier, max_over_ranks, sum_over_ranks, n_contigs):
-    extra = {}
+    """Fills `extra` leg by leg; a failing leg leaves its error string and the others still run (every rank takes the same path:
+    the legs are collective)."""
     # ---- config 3: 10 x the reads of a step in total (1 M for config 2), strong scaling over the ranks, one EM over all mappings
     n_blocks = 16
     per_block = max(1, wl["n_reads"] * 10 // n_blocks)
@@ -612,6 +613,7 @@ def extra_legs(args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, cod
     def config3(mode, ix):
         mine = list(range(n_blocks)) if mode == "contigs" else list(range(rank, n_blocks, world))
         data = [gen_reads(torch, dev, wl, codes, 100 + b, per_block) for b in mine]
+        torch.cuda.empty_cache()
         tot_reads = per_block * n_blocks
         lo, hi = rank * tot_reads // world, (rank + 1) * tot_reads // world
 
@@ -619,7 +621,11 @@ def extra_legs(args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, cod
             ctx.classify_begin()
             nb = 0
             for (a, off) in data:
-                res = capi.map_reads(ctx, ix, None, PI, wl["min_read_len"], dev_ptr=a.data_ptr(), offsets=off, fetch=False)
+                if mode == "contigs":                # every rank sketches its slice of the block; the sketches are all-gathered
+                    nr = len(off) - 1; b0, b1 = rank * nr // world, (rank + 1) * nr // world
+                    res = capi.map_reads_sharded(ctx, ix, a.data_ptr() + int(off[b0]), off[b0:b1 + 1] - off[b0], PI, wl["min_read_len"])
+                else:
+                    res = capi.map_reads(ctx, ix, None, PI, wl["min_read_len"], dev_ptr=a.data_ptr(), offsets=off, fetch=False)
                 ctx.classify_add(getattr(ix, "first_contig", 0)); ctx.classify_next_batch()
                 nb += int(res["summary"]["total_bases_mapped_reads"])
             if mode == "contigs":
@@ -640,24 +646,40 @@ def extra_legs(args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, cod
                                                                        else "reads sharded, index replicated"),
                 "seconds": sec, "value": bases / 1e6 / sec, "unit": "Mbp/s", "scaling": "strong", "em_iters": int(cs["em_iters"]),
                 "mappings_this_rank": int(cs["n_mappings"]), "f_sum": float(np.sum(r["f"]))}
+
+    def leg(name, fn):
+        try:
+            extra[name] = fn()
+        except Exception as e:
+            extra[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        torch.cuda.empty_cache()
     if not by_contigs:
-        extra["config3"] = config3("reads", ix_main)
-    if world > 1:
-        # ---- north_star's split: contig-range shards.  Same total reads per step as the read-sharded `value` (N batches).
-        if by_contigs:
-            ix_sh = ix_main
-        else:
-            del ix_main
-            torch.cuda.empty_cache()
-            ix_sh = build_index(own[0], own[1], True)
-        r_asc, r_off, blk = all_blocks_reads(world)
-        read_len = np.diff(r_off).astype(np.int32)
-        my = (int(blk[rank]), int(blk[rank + 1]))
+        leg("config3", lambda: config3("reads", holder[0]))
+    if world == 1:
+        return
+    # ---- north_star's split: contig-range shards.  Same total reads per step as the read-sharded `value` (N batches).
+    if not by_contigs:
+        holder.clear()                              # the replicated index goes before the shard is built
+        torch.cuda.empty_cache()
+        try:
+            holder.append(build_index(own[0], own[1], True))
+        except Exception as e:
+            extra["shard_contigs"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            return
+    ix_sh = holder[0]
+
+    def shard_leg():
+        # every rank holds ITS block of the step's reads (block `rank` of the recipe, the batch of the read-sharded `value`); it
+        # sketches that block once, the sketches are all-gathered, all reads are mapped against the rank's shard
+        r_asc, r_off = gen_reads(torch, dev, wl, codes, rank)
+        torch.cuda.empty_cache()
         r_host = torch.empty(r_asc.numel(), dtype=torch.uint8, pin_memory=True); r_host.copy_(r_asc); torch.cuda.synchronize()
+        stage = torch.empty_like(r_asc)
 
         def step(host):
-            return pipeline.map_and_classify_sharded(ctx, [ix_sh], host_ptr=r_host.data_ptr() if host else None, dev_ptr=None if host else r_asc.data_ptr(),
-                                                     offsets=r_off, read_len=read_len, read_range=my, **common)
+            if host:                                   # e2e: the block comes from pinned host memory every step
+                stage.copy_(r_host, non_blocking=True); torch.cuda.current_stream().synchronize()
+            return pipeline.map_and_classify_sharded(ctx, [ix_sh], my_block=((stage if host else r_asc).data_ptr(), r_off), **common)
         res = {}
         for name, host in (("value", False), ("e2e", True)):
             for _ in range(2):
@@ -671,14 +693,14 @@ def extra_legs(args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, cod
             sec = max_over_ranks(time.perf_counter() - t0)
             res[name] = float(o["summary"]["total_bases_mapped_reads"]) * n_it / 1e6 / sec
             res["ms_per_step" if not host else "e2e_ms_per_step"] = sec / n_it * 1e3
-        res.update({"unit": "Mbp/s", "reads_per_step": int(len(read_len)), "mappings_all_shards_this_rank": int(o["summary"]["n_mappings_this_rank_all_shards"]),
-                    "parallelism": f"index sharded by contig range x{world}; every rank maps all {len(read_len)} reads against its shard; accepted mappings "
-                                   "all-gathered (ncclAllGather) and merged on the device; each rank finalises its block of reads; EM all-reduce per round"})
-        extra["shard_contigs"] = res
-        del r_asc, r_host
-        torch.cuda.empty_cache()
-        extra["config3_shard_contigs"] = config3("contigs", ix_sh)
-    return extra
+        res.update({"unit": "Mbp/s", "reads_per_step": int(o["summary"]["n_reads"]), "mappings_all_shards_this_rank": int(o["summary"]["n_mappings_this_rank_all_shards"]),
+                    "wall_ms_last_step": {k_: round(v, 2) for k_, v in o.get("wall_ms", {}).items()},
+                    "parallelism": f"index sharded by contig range x{world}; every rank sketches its own block of {len(r_off) - 1} reads once, the sketches are "
+                                   "all-gathered (ncclAllGather), all reads are mapped against the rank's shard; accepted mappings all-gathered and merged on "
+                                   "the device; each rank finalises its block; EM all-reduce per round"})
+        return res
+    leg("shard_contigs", shard_leg)
+    leg("config3_shard_contigs", lambda: config3("contigs", ix_sh))
 
 
 # ------------------------------------------------------------------------------------------ config 5 (streamed reference chunks)

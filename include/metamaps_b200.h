@@ -152,6 +152,15 @@ int mm_map_batch(mm_ctx* ctx, const mm_index* idx, const char* reads, const int6
 int mm_map_batch_dev(mm_ctx* ctx, const mm_index* idx, const void* reads_dev, const int64_t* offsets_host,
                      int32_t n_reads, const mm_map_params* params, mm_map_summary* summary);
 
+/* Contig-sharded ranks (collective over the context's communicator; the index is this rank's shard): every rank passes ITS block of
+ * the batch -- blocks in rank order make up the batch, n_my_reads may differ between ranks -- and sketches only that block
+ * (K0, K1, K3); the sorted unique sketches, sketch sizes and read lengths of all blocks are then all-gathered (ncclAllGather of
+ * padded slabs) and every rank maps ALL reads of the batch against its shard (K4, K5).  Results are those of mm_map_batch_dev on
+ * the concatenated reads: read indices run over the whole batch (rank 0's block first).  first_read = index of this rank's
+ * first read in the batch (may be NULL). */
+int mm_map_batch_sharded_dev(mm_ctx* ctx, const mm_index* idx, const void* my_reads_dev, const int64_t* my_offsets_host, int32_t n_my_reads,
+                             const mm_map_params* params, mm_map_summary* summary, int64_t* first_read);
+
 /* Double-buffered input staging (the pinned, double-buffered H2D of a streaming host).  mm_stage_reads_async starts the
  * upload of a batch of reads on the context's copy stream and returns at once; mm_map_batch_staged maps the batch staged
  * in `slot` (0 or 1) -- the upload is awaited on the device, so staging batch i+1 before mapping batch i overlaps the

@@ -63,6 +63,7 @@ SYMBOLS = {
     "mm_index_destroy": (None, [C.c_void_p]),
     "mm_map_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, _i64p, C.c_int32, C.POINTER(MapParams), C.POINTER(MapSummary)]),
     "mm_map_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _i64p, C.c_int32, C.POINTER(MapParams), C.POINTER(MapSummary)]),
+    "mm_map_batch_sharded_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _i64p, C.c_int32, C.POINTER(MapParams), C.POINTER(MapSummary), C.POINTER(C.c_int64)]),
     "mm_stage_reads_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _i64p, C.c_int32]),
     "mm_map_batch_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(MapParams), C.POINTER(MapSummary)]),
     "mm_map_fetch_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -478,6 +479,18 @@ def nloc_batch(lib, seq, read_off, read_len, contig_len, contig_taxon, n_taxa: i
     if rc != 0:
         raise MMError(rc, (lib.mm_last_error() or b"").decode())
     return tax, nloc
+
+
+def map_reads_sharded(ctx: Context, index: Index, dev_ptr: int, offsets, perc_identity: float = 80.0, min_read_len: int = 1000):
+    """Collective over contig-sharded ranks: `dev_ptr` / `offsets` are THIS rank's block of the batch (device ASCII); every rank ends
+    with the map results of the whole batch against its shard (mm_map_batch_sharded_dev).  Returns like map_reads(fetch=False) plus
+    "first_read" = index of this rank's first read in the batch."""
+    p = MapParams(perc_identity, min_read_len, 1, 0); s = MapSummary(); first = C.c_int64()
+    offs = np.ascontiguousarray(offsets, np.int64)
+    ctx._check(ctx.lib.mm_map_batch_sharded_dev(ctx.h, index.h, C.c_void_p(dev_ptr), offs, len(offs) - 1, C.byref(p), C.byref(s), C.byref(first)))
+    gpu_ms, launches = ctx.last_timing()
+    return {"summary": {f[0]: getattr(s, f[0]) for f in MapSummary._fields_}, "gpu_ms": gpu_ms, "launches": launches, "stats": ctx.last_map_stats(),
+            "_n": int(s.n_reads), "_nc": int(s.n_candidates), "first_read": first.value}
 
 
 def map_reads(ctx: Context, index: Index, reads=None, perc_identity: float = 80.0, min_read_len: int = 1000,

@@ -430,6 +430,79 @@ int mm_map_batch_dev(mm_ctx* c, const mm_index* idx, const void* dev, const int6
   if (!dev) { g_err = "mm_map_batch_dev: null device pointer"; return MM_EINVAL; }
   return map_impl(c, idx, nullptr, dev, offsets, n, p, out);
 }
+// ---- contig-sharded ranks: sketch the own block once, all-gather the sketches, map everything against the own shard
+struct QReadFillFn {        // qRead[e] = r for e in [qOff[r], qOff[r+1])
+  const int64_t* qOff; int32_t* qRead;
+  MM_HD void operator()(int64_t r) const { for (int64_t e = ldg(qOff + r), e1 = ldg(qOff + r + 1); e < e1; e++) qRead[e] = (int32_t)r; }
+};
+struct PackBytesFn { const uint8_t* in; uint32_t* out; int64_t n; MM_HD void operator()(int64_t w) const {
+  uint32_t v = 0; for (int j = 0; j < 4; j++) { const int64_t i = 4 * w + j; if (i < n) v |= (uint32_t)ldg(in + i) << (8 * j); } out[w] = v; } };
+struct UnpackBytesFn { const uint32_t* in; uint8_t* out; MM_HD void operator()(int64_t i) const { out[i] = (uint8_t)(ldg(in + (i >> 2)) >> (8 * (i & 3))); } };
+static void allgather_u32(mm_ctx* c, const uint32_t* send, uint32_t* recv, size_t count);
+int mm_map_batch_sharded_dev(mm_ctx* c, const mm_index* idx, const void* dev, const int64_t* offsets, int32_t n, const mm_map_params* p, mm_map_summary* out,
+                             int64_t* first_read) {
+  MM_TRY
+  if (!offsets || n < 0 || (!dev && n > 0)) throw Error(MM_EINVAL, "mm_map_batch_sharded_dev: bad arguments");
+  check_map_args(c, idx, p);
+  begin_call(c);
+  Runtime& rt = c->rt; Mapper& m = c->mp; const int R = c->nRanks;
+  c->sk.load(m.batch, nullptr, dev, offsets, n);
+  int64_t s[6];
+  {
+    StageTimer t(rt, &c->last_ms);
+    m.sketch_reads(idx->ix.k, idx->ix.w, m.batch, p->min_read_len);
+    if (R > 1) {
+      m.join_sketch();                                           // the gathered strands must be final
+      // 1. per-rank scalars
+      DevBuf<uint32_t> one, all; one.ensure(8); all.ensure((size_t)8 * R);
+      uint32_t h[8] = {(uint32_t)m.n_reads, (uint32_t)(m.n_q & 0xffffffffu), (uint32_t)((uint64_t)m.n_q >> 32), (uint32_t)m.maxSketch, (uint32_t)m.nShort_,
+                       (uint32_t)((uint64_t)m.basesOk_ & 0xffffffffu), (uint32_t)((uint64_t)m.basesOk_ >> 32), (uint32_t)m.n_ambig};
+      h2d(rt, one.p, h, sizeof h); allgather_u32(c, one.p, all.p, 8);
+      std::vector<uint32_t> ha((size_t)8 * R); d2h(rt, ha.data(), all.p, 4 * ha.size());
+      int64_t totReads = 0, totQ = 0, capN = 0, capQ = 0, nShort = 0, bases = 0, nAmb = 0; int32_t maxS = 0; int64_t myFirst = 0;
+      std::vector<int64_t> nr((size_t)R), nq((size_t)R);
+      for (int r = 0; r < R; r++) {
+        nr[(size_t)r] = ha[(size_t)8 * r]; nq[(size_t)r] = (int64_t)(((uint64_t)ha[(size_t)8 * r + 2] << 32) | ha[(size_t)8 * r + 1]);
+        if (r < c->rank) myFirst += nr[(size_t)r];
+        totReads += nr[(size_t)r]; totQ += nq[(size_t)r]; capN = std::max(capN, nr[(size_t)r]); capQ = std::max(capQ, nq[(size_t)r]);
+        maxS = std::max(maxS, (int32_t)ha[(size_t)8 * r + 3]); nShort += ha[(size_t)8 * r + 4];
+        bases += (int64_t)(((uint64_t)ha[(size_t)8 * r + 6] << 32) | ha[(size_t)8 * r + 5]); nAmb += ha[(size_t)8 * r + 7];
+      }
+      if (totReads >= ((int64_t)1 << 31)) throw Error(MM_ERANGE, "more than 2^31 reads in one sharded batch");
+      if (first_read) *first_read = myFirst;
+      // 2. padded slabs: [readLen | sOf] (2 capN words) and [qHash | qStrand packed 4 per word] (capQ + capQ/4 + 1 words)
+      const size_t wq = (size_t)capQ + (size_t)(capQ + 3) / 4;
+      DevBuf<uint32_t> sendA, recvA, sendB, recvB;
+      sendA.ensure((size_t)2 * capN + 1); recvA.ensure(((size_t)2 * capN + 1) * R); sendB.ensure(wq + 1); recvB.ensure((wq + 1) * R);
+      dev_memset(rt, sendA.p, 0, 4 * ((size_t)2 * capN + 1)); dev_memset(rt, sendB.p, 0, 4 * (wq + 1));
+      d2d(rt, sendA.p, m.readLen.p, 4 * (size_t)m.n_reads); d2d(rt, sendA.p + capN, m.sOf.p, 4 * (size_t)m.n_reads);
+      d2d(rt, sendB.p, m.qHash.p, 4 * (size_t)m.n_q);
+      if (m.n_q > 0) foreach(rt, (m.n_q + 3) / 4, PackBytesFn{m.qStrand.p, sendB.p + capQ, m.n_q});
+      if (capN > 0) allgather_u32(c, sendA.p, recvA.p, (size_t)2 * capN);
+      if (wq > 0) allgather_u32(c, sendB.p, recvB.p, wq);
+      // 3. the batch's arrays, blocks in rank order
+      m.readLen.ensure((size_t)totReads + 1); m.sOf.ensure((size_t)totReads + 1); m.qOff.ensure((size_t)totReads + 2);
+      m.qHash.ensure((size_t)totQ + 1); m.qStrand.ensure((size_t)totQ + 4); m.qRead.ensure((size_t)totQ + 1);
+      int64_t pr = 0, pq = 0;
+      for (int r = 0; r < R; r++) {
+        const uint32_t* a = recvA.p + (size_t)r * 2 * capN; const uint32_t* b = recvB.p + (size_t)r * wq;
+        d2d(rt, m.readLen.p + pr, a, 4 * (size_t)nr[(size_t)r]); d2d(rt, m.sOf.p + pr, a + capN, 4 * (size_t)nr[(size_t)r]);
+        d2d(rt, m.qHash.p + pq, b, 4 * (size_t)nq[(size_t)r]);
+        if (nq[(size_t)r] > 0) foreach(rt, nq[(size_t)r], UnpackBytesFn{b + capQ, m.qStrand.p + pq});
+        pr += nr[(size_t)r]; pq += nq[(size_t)r];
+      }
+      dev_memset(rt, m.sOf.p + totReads, 0, sizeof(int32_t));
+      c->pr.exclusive_sum<int32_t, int64_t>(m.sOf.p, m.qOff.p, totReads + 1);
+      if (totReads > 0) foreach(rt, totReads, QReadFillFn{m.qOff.p, m.qRead.p});
+      m.n_reads = (int32_t)totReads; m.n_q = totQ; m.maxSketch = maxS; m.nShort_ = nShort; m.basesOk_ = bases; m.n_ambig = nAmb;
+    } else if (first_read) *first_read = 0;
+    m.map_sketched(idx->ix, p->perc_identity, s);
+    if (!p->report_all) apply_best_filter(c, s);
+  }
+  end_call(c);
+  fill_summary(out, s);
+  MM_CATCH
+}
 int mm_stage_reads_async(mm_ctx* c, int slot, const char* reads, const int64_t* offsets, int32_t n) {
   MM_TRY
   if (!c || slot < 0 || slot > 1 || !offsets || n < 0 || (!reads && n > 0)) throw Error(MM_EINVAL, "mm_stage_reads_async: bad arguments");

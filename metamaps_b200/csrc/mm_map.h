@@ -494,108 +494,6 @@ __global__ void __launch_bounds__(256) l1_filter_gather16_kernel(const int32_t* 
 }
 #endif
 
-#ifndef MM_HOST_EMU
-// Same filter, one position list per GROUP OF 8 LANES (a list holds 7.5 entries on average on the 12 Gbp reference): lane j of a
-// group reads entry j, j + 8, ... of its list -- no search for "which list does my flattened hit belong to" (40 % of the
-// instructions of the kernel above), and the hit's rank within the read is simply hitOff[q] - h0 + j.  Four lists per warp and
-// trip, U trips in flight.  Same bins, same shared-memory cache of contig ids, same survivors, same order-free output.
-__global__ void __launch_bounds__(256) l1_filter_gather16g_kernel(const int32_t* hitCnt, const int64_t* hitStart, const int64_t* hitOff, const int64_t* qOff,
-                                                                  const int32_t* sOf, const int32_t* minHitsTab, const uint16_t* posSeq16, const uint64_t* posKey,
-                                                                  HitKeyLayout lay, int32_t n_reads, uint32_t binMask, unsigned long long* cursor,
-                                                                  uint64_t* hitsOut, int32_t* keptPerRead, uint32_t cacheCap) {
-  extern __shared__ uint32_t bins[];
-  uint16_t* cache = reinterpret_cast<uint16_t*>(bins + (binMask + 1) / 2);
-  __shared__ unsigned int smTotal, smPos; __shared__ unsigned long long smBase;
-  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3, wid = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
-  constexpr int U = 4;
-  for (int32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
-    const int32_t s = sOf[r];
-    const int64_t q0 = qOff[r], q1 = qOff[r + 1];
-    if (s == 0 || q1 <= q0) { if (threadIdx.x == 0) keptPerRead[r] = 0; continue; }
-    int32_t mh = minHitsTab[s]; if (mh < 1) mh = 1;
-    const int64_t h0 = hitOff[q0]; const int64_t nHits = hitOff[q1] - h0;
-    if (nHits == 0) { if (threadIdx.x == 0) keptPerRead[r] = 0; continue; }
-    const bool anySat = nHits >= 0xFFF0;        // a 16-bit bin could wrap: keep everything for this read
-    for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) bins[i] = 0;
-    if (threadIdx.x == 0) { smTotal = 0; smPos = 0; }
-    __syncthreads();
-    const uint64_t hiKey = (uint64_t)r << (lay.seqBits + lay.wsBits);
-    unsigned int local = 0;
-    for (int pass = 0; pass < 2; pass++) {
-      if (pass == 1) {
-        if (!anySat) {
-          __syncthreads();
-          for (uint32_t i = threadIdx.x; i < (binMask + 1) / 2; i += blockDim.x) {
-            const uint32_t w = bins[i], lo = w & 0xFFFFu, hi = w >> 16;
-            local += (lo >= (uint32_t)mh) ? lo : 0u;
-            local += (hi >= (uint32_t)mh) ? hi : 0u;
-          }
-        } else if (threadIdx.x == 0) local = (unsigned int)nHits;
-        if (local) atomicAdd(&smTotal, local);
-        __syncthreads();
-        if (threadIdx.x == 0) { smBase = atomicAdd(cursor, (unsigned long long)smTotal); keptPerRead[r] = (int32_t)smTotal; }
-        __syncthreads();
-        if (smTotal == 0) break;
-      } else if (anySat) continue;
-      // every warp walks blocks of 4 * U probes; the trip count is the same for all lanes of a warp (the ballots below need that)
-      for (int64_t qb = q0 + (int64_t)wid * 4 * U; qb < q1; qb += (int64_t)nWarps * 4 * U) {
-        int32_t c[U]; int64_t st[U]; uint32_t rk[U]; int32_t maxc = 0;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int64_t q = qb + u * 4 + grp;
-          c[u] = q < q1 ? hitCnt[q] : 0;
-          st[u] = c[u] ? hitStart[q] : 0;
-          rk[u] = c[u] ? (uint32_t)(hitOff[q] - h0) : 0u;
-          maxc = c[u] > maxc ? c[u] : maxc;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const int32_t v = __shfl_xor_sync(0xffffffffu, maxc, o); maxc = v > maxc ? v : maxc; }
-        for (int32_t j0 = 0; j0 < maxc; j0 += 8) {
-          const int32_t j = j0 + sub;
-          if (pass == 0) {
-            uint32_t sq[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) sq[u] = j < c[u] ? (uint32_t)__ldg(posSeq16 + st[u] + j) : 0u;
-#pragma unroll
-            for (int u = 0; u < U; u++) if (j < c[u]) {
-              const uint32_t rank = rk[u] + (uint32_t)j;
-              if (rank < cacheCap) cache[rank] = (uint16_t)sq[u];
-              const uint32_t b_ = sq[u] & binMask;
-              atomicAdd(&bins[b_ >> 1], (b_ & 1u) ? 0x10000u : 1u);
-            }
-          } else {
-            bool keep[U]; uint64_t pk[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-              keep[u] = j < c[u] && anySat;
-              if (j < c[u] && !anySat) {
-                const uint32_t rank = rk[u] + (uint32_t)j;
-                const uint32_t sq = (rank < cacheCap) ? (uint32_t)cache[rank] : (uint32_t)__ldg(posSeq16 + st[u] + j);
-                const uint32_t b_ = sq & binMask;
-                keep[u] = ((bins[b_ >> 1] >> ((b_ & 1u) * 16)) & 0xFFFFu) >= (uint32_t)mh;
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) pk[u] = keep[u] ? __ldg(posKey + st[u] + j) : 0ull;
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-              const unsigned int m = __ballot_sync(0xffffffffu, keep[u]);
-              if (m) {                                      // one cursor bump per warp and trip
-                unsigned int base = 0;
-                if (lane == __ffs(m) - 1) base = atomicAdd(&smPos, (unsigned int)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                if (keep[u]) hitsOut[smBase + base + __popc(m & ((1u << lane) - 1u))] = hiKey | ((pk[u] >> 32) << lay.wsBits) | (pk[u] & 0xFFFFFFFFull);
-              }
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-#endif
-
 // computeL1CandidateRegions (computeMap.hpp:346-386), one item per sorted hit:
 //   hit i opens a candidate iff hits i and i+minimumHits-1 lie on the same contig less than a read length apart;
 //   consecutive such candidates are merged while prev.end >= start (ends are non-decreasing, so "prev" is simply
@@ -1538,8 +1436,15 @@ struct Mapper {
 
   // `batch` must already be loaded (Sketcher::load, or prepare + pack_async + finish_pack)
   void run(const Index& ix, SeqBatch& batch, float pi, int32_t minReadLen, int64_t* summary /*6*/) {
+    sketch_reads(ix.k, ix.w, batch, minReadLen);
+    map_sketched(ix, pi, summary);
+  }
+  // K0/K1/K3 of a read batch: leaves readLen, sOf, qOff, qHash, qStrand, qRead, n_q, maxSketch (and, pending on the side stream,
+  // the std::sort replay of the ambiguous reads).  A contig-sharded rank runs this on ITS block of the reads only; the sketches
+  // of all blocks are then all-gathered (mm_map_batch_sharded_dev) before map_sketched.
+  int64_t nShort_ = 0, basesOk_ = 0, nExc_ = 0, nMinimizers_ = 0; bool ambigPending_ = false;
+  void sketch_reads(int k, int w, SeqBatch& batch, int32_t minReadLen) {
     memset(&st, 0, sizeof(st));
-    const int k = ix.k, w = ix.w;
     lastK = k;
     n_reads = batch.n_seqs;
     // reads shorter than w, k or -m are skipped (computeMap.hpp:137): hide them from K1 by zeroing their length
@@ -1559,8 +1464,10 @@ struct Mapper {
       sk.chunkMs = nullptr;
     }
     batch.h_len = saveLen;
+    nShort_ = nShort; basesOk_ = basesOk; nExc_ = batch.n_exc;
     // ---- K3: sort by (read, hash), unique
     int64_t nm = rs.n_total;
+    nMinimizers_ = nm;
     sOf.ensure((size_t)n_reads + 1); qOff.ensure((size_t)n_reads + 2);
     bool ambigPending = false;
     {
@@ -1664,11 +1571,27 @@ struct Mapper {
 #endif
           ambigPending = true;
         }
-        // minimumHits[s] / acceptMin[s] tables up to the largest sketch of the batch (host, map_stats.hpp)
-        ensure_tables(k, pi, maxS);
         maxSketch = maxS;
       }
     }
+    ambigPending_ = ambigPending;
+  }
+  // the std::sort replay of sketch_reads (side stream) must be complete before qStrand is read by anything but K5c
+  void join_sketch() {
+    if (ambigPending_) {
+#ifndef MM_HOST_EMU
+      MM_CUDA(cudaStreamWaitEvent(rt.stream, evJoin(), 0));
+#endif
+      ambigPending_ = false;
+    }
+  }
+  // K4 + K5 over the sketches sketch_reads (or the all-gather of several ranks' sketch_reads) left in this object
+  void map_sketched(const Index& ix, float pi, int64_t* summary /*6*/) {
+    const int k = ix.k, w = ix.w;
+    bool ambigPending = ambigPending_;
+    const int64_t nShort = nShort_, basesOk = basesOk_;
+    // minimumHits[s] / acceptMin[s] tables up to the largest sketch of the batch (host, map_stats.hpp)
+    ensure_tables(k, pi, maxSketch);
     // ---- K4: probe, gather, sort, candidate regions
     candOff.ensure((size_t)n_reads + 2); candCnt.ensure((size_t)n_reads + 2);
     const HitKeyLayout lay = hit_key_layout(ix);
@@ -1709,15 +1632,10 @@ struct Mapper {
           size_t smem = (size_t)binsN * 2 + (size_t)cacheCap * 2;
           int perSm = (int)((220 * 1024) / (smem + 1024)); if (perSm > 8) perSm = 8; if (perSm < 1) perSm = 1;
           int grid = n_reads < rt.sm_count * perSm ? n_reads : rt.sm_count * perSm;
-          static const bool flat = [] { const char* e = getenv("MM_L1_FILTER"); return e && !strcmp(e, "flat"); }();      // A/B: the flattened-hits walk
-          if (flat) {
-            l1_filter_gather16_kernel<<<grid, 256, smem, rt.stream>>>(hitCnt.p, hitStart.p, hitOff.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p, ix.posKey.p, lay, n_reads,
-                                                                      binsN - 1, scal.p, hits.p, keptPerRead.p, (uint32_t)cacheCap);
-          } else {
-            if (rt.first((const void*)l1_filter_gather16g_kernel)) MM_CUDA(cudaFuncSetAttribute(l1_filter_gather16g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            l1_filter_gather16g_kernel<<<grid, 256, smem, rt.stream>>>(hitCnt.p, hitStart.p, hitOff.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p, ix.posKey.p, lay, n_reads,
-                                                                       binsN - 1, scal.p, hits.p, keptPerRead.p, (uint32_t)cacheCap);
-          }
+          // (one list per group of 8 lanes instead of the flattened walk -- no search, direct ranks -- was measured on config 2:
+          //  the L1 stage went 10.0 -> 15.5 ms: with 7.5 entries per list on average too many lanes idle; removed)
+          l1_filter_gather16_kernel<<<grid, 256, smem, rt.stream>>>(hitCnt.p, hitStart.p, hitOff.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p, ix.posKey.p, lay, n_reads,
+                                                                    binsN - 1, scal.p, hits.p, keptPerRead.p, (uint32_t)cacheCap);
         } else {
           int grid = n_reads < rt.sm_count * 8 ? n_reads : rt.sm_count * 8;
           l1_filter_gather_kernel<<<grid, 256, binsN * 2, rt.stream>>>(hitCnt.p, hitStart.p, qOff.p, sOf.p, dMinHits.p, ix.posKey.p, lay, n_reads, binsN - 1,
@@ -1866,7 +1784,8 @@ struct Mapper {
     }
     rt.sync();
     st.counters[0] = n_q; st.counters[1] = n_hits_all; st.counters[10] = n_hits; st.counters[2] = n_cand; st.counters[3] = totalEv; st.counters[4] = nMap;
-    st.counters[5] = rs.n_total; st.counters[6] = basesOk; st.counters[7] = batch.n_exc; st.counters[8] = n_ambig; st.counters[9] = smemSwept;
+    st.counters[5] = nMinimizers_; st.counters[6] = basesOk; st.counters[7] = nExc_; st.counters[8] = n_ambig; st.counters[9] = smemSwept;
+    ambigPending_ = false;
     summary[0] = n_reads; summary[1] = nShort; summary[2] = n_cand; summary[3] = nMap; summary[4] = nReadsMapped; summary[5] = basesOk;
   }
 

@@ -92,7 +92,7 @@ def map_and_classify(ctx: capi.Context, index: capi.Index, *, reads=None, dev_pt
 
 def map_and_classify_sharded(ctx: capi.Context, shards: list, *, reads=None, dev_ptr=None, host_ptr=None, offsets=None, read_len=None,
                              contig_len: np.ndarray, contig_taxon: np.ndarray, n_taxa: int, perc_identity: float = 80.0,
-                             min_read_len: int = 1000, em_max_iter: int = 0, read_range=None, stats: dict | None = None):
+                             min_read_len: int = 1000, em_max_iter: int = 0, read_range=None, stats: dict | None = None, my_block=None):
     """The same pass against a reference split into contig-range shards (capi.Index objects with .first_contig set).
 
     Every shard maps ALL reads; each map call's accepted mappings are appended to the device-resident table with global contig
@@ -100,7 +100,10 @@ def map_and_classify_sharded(ctx: capi.Context, shards: list, *, reads=None, dev
     after the other (the --maxmemory analogue).  Multi-GPU (the context has a communicator, `read_range = (lo, hi)`): each rank
     passes its own shard(s); mm_classify_exchange all-gathers and merges the tables on the device and this rank finalises the
     reads [lo, hi) (mapping quality needs a read's mappings from all shards, mapWrap.h:226-278); the EM taxon sums are
-    all-reduced inside mm_classify_run."""
+    all-reduced inside mm_classify_run.
+    `my_block = (dev_ptr, offsets)` (multi-GPU, one shard per rank): the rank holds only ITS block of the batch, sketches it once
+    and the sketches are all-gathered (mm_map_batch_sharded_dev) instead of every rank re-sketching every read; read_range is
+    then this rank's block."""
     import time
     gpu_ms = 0.0; launches = 0; summary = None
     t0 = time.perf_counter()
@@ -108,7 +111,11 @@ def map_and_classify_sharded(ctx: capi.Context, shards: list, *, reads=None, dev
     ctx.classify_begin()
     n_all = 0
     for ix in shards:
-        res = capi.map_reads(ctx, ix, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets, fetch=False)
+        if my_block is not None:
+            res = capi.map_reads_sharded(ctx, ix, my_block[0], my_block[1], perc_identity, min_read_len)
+            read_range = (res["first_read"], res["first_read"] + len(my_block[1]) - 1)
+        else:
+            res = capi.map_reads(ctx, ix, reads, perc_identity, min_read_len, dev_ptr=dev_ptr, host_ptr=host_ptr, offsets=offsets, fetch=False)
         gpu_ms += res["gpu_ms"]; launches += res["launches"]
         if stats is not None:
             stats["map"] = res["stats"]
@@ -128,8 +135,9 @@ def map_and_classify_sharded(ctx: capi.Context, shards: list, *, reads=None, dev
     out = _classify_on_device(ctx, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa, em_max_iter=em_max_iter, wall=wall)
     if stats is not None:
         stats["wall_ms"] = wall
+    out["wall_ms"] = wall
     summary["n_mappings_this_rank_all_shards"] = int(n_all)
-    out["summary"] = summary
+    out["summary"] = summary; out["read_range"] = read_range
     out["gpu_ms"] += gpu_ms; out["launches"] += launches
     return out
 

@@ -44,6 +44,18 @@ def main():
     assert res["em"]["iters"] == ref["em"]["iters"]
     assert np.abs(res["em"]["f"] - ref["em"]["f"]).max() <= 1e-6
     assert np.abs(res["em"]["posterior"] - ref["em"]["posterior"][sel]).max() <= 1e-6
+    # sketch once: the rank holds only its (unequal) block of the reads on the device; the sketches are all-gathered over NCCL
+    cut = 25
+    mine = reads[:cut] if rank == 0 else reads[cut:]
+    blk = torch.frombuffer(bytearray(b"".join(mine)), dtype=torch.uint8).cuda()
+    off = np.zeros(len(mine) + 1, np.int64); off[1:] = np.cumsum([len(x) for x in mine])
+    res2 = pipeline.map_and_classify_sharded(ctx, [ix], contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=T, my_block=(blk.data_ptr(), off))
+    lo2, hi2 = res2["read_range"]
+    assert (lo2, hi2) == ((0, cut) if rank == 0 else (cut, n)), (lo2, hi2)
+    sel2 = (ref["read"] >= lo2) & (ref["read"] < hi2)
+    for key in common.MAPPING_KEYS:
+        assert np.array_equal(res2[key], ref[key][sel2]), ("sketch-once", key)
+    assert res2["em"]["iters"] == ref["em"]["iters"] and np.abs(res2["em"]["f"] - ref["em"]["f"]).max() <= 1e-6
     print(f"rank {rank}: contig shards [{c0},{c1}) ok, global threshold {thr}, {int(sel.sum())} mappings of reads [{lo},{hi})", flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -82,6 +82,16 @@ def _shard_worker(rank, world, port, tmp):
                                             read_range=(lo, hi))
     np.savez(os.path.join(tmp, f"shard{rank}.npz"), thr=thr, uniq=uniq, local_thr=local_thr, lo=lo, hi=hi, f=res["em"]["f"], iters=res["em"]["iters"],
              post=res["em"]["posterior"], **{k_: res[k_] for k_ in common.MAPPING_KEYS})
+    # sketch-once variant: the rank holds only ITS (unequal) block of the reads; sketches are all-gathered (mm_map_batch_sharded_dev)
+    cut = 25
+    mine = reads[:cut] if rank == 0 else reads[cut:]
+    data = np.frombuffer(b"".join(mine), np.uint8).copy()
+    off = np.zeros(len(mine) + 1, np.int64); off[1:] = np.cumsum([len(x) for x in mine])
+    res2 = pipeline.map_and_classify_sharded(ctx, [ix], contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=T, my_block=(data.ctypes.data, off))
+    assert res2["read_range"] == ((0, cut) if rank == 0 else (cut, n)), res2["read_range"]
+    assert res2["summary"]["n_reads"] == n
+    np.savez(os.path.join(tmp, f"shardB{rank}.npz"), lo=res2["read_range"][0], hi=res2["read_range"][1], f=res2["em"]["f"], iters=res2["em"]["iters"],
+             post=res2["em"]["posterior"], **{k_: res2[k_] for k_ in common.MAPPING_KEYS})
     dist.destroy_process_group()
 
 
@@ -113,6 +123,14 @@ def test_contig_shards_two_ranks_equal_unsharded_reference(tmp_path):
         assert np.abs(p["post"] - ref["em"]["posterior"][sel]).max() <= 1e-6
     assert np.array_equal(parts[0]["f"], parts[1]["f"])
     assert sum(len(p["read"]) for p in parts) == len(ref["read"])
+    partsB = [np.load(os.path.join(str(tmp_path), f"shardB{r}.npz")) for r in range(2)]
+    for p in partsB:                                                    # sketch once + all-gather of the sketches: the same results
+        sel = (ref["read"] >= int(p["lo"])) & (ref["read"] < int(p["hi"]))
+        for key in common.MAPPING_KEYS:
+            assert np.array_equal(p[key], ref[key][sel]), key
+        assert int(p["iters"]) == ref["em"]["iters"] and np.abs(p["f"] - ref["em"]["f"]).max() <= 1e-6
+        assert np.abs(p["post"] - ref["em"]["posterior"][sel]).max() <= 1e-6
+    assert sum(len(p["read"]) for p in partsB) == len(ref["read"])
 
 
 # ---------------------------------------------------------------------------------------------- streamed, interleaved chunks
