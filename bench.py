@@ -682,15 +682,16 @@ def extra_legs(extra, args, wl, torch, dist, dev, ctx, capi, pipeline, world, ra
             return pipeline.map_and_classify_sharded(ctx, [ix_sh], my_block=((stage if host else r_asc).data_ptr(), r_off), **common)
         res = {}
         for name, host in (("value", False), ("e2e", True)):
-            for _ in range(2):
+            for _ in range(3):
                 o = step(host)
             barrier()
             t0 = time.perf_counter()
-            n_it = max(2, min(args.steps, 5))
+            n_it = max(2, min(args.steps, 5)); per = []
             for _ in range(n_it):
-                o = step(host)
+                ts = time.perf_counter(); o = step(host); per.append(round((time.perf_counter() - ts) * 1e3, 1))
             torch.cuda.synchronize()
             sec = max_over_ranks(time.perf_counter() - t0)
+            res[name + "_step_ms_rank0"] = per
             res[name] = float(o["summary"]["total_bases_mapped_reads"]) * n_it / 1e6 / sec
             res["ms_per_step" if not host else "e2e_ms_per_step"] = sec / n_it * 1e3
         res.update({"unit": "Mbp/s", "reads_per_step": int(o["summary"]["n_reads"]), "mappings_all_shards_this_rank": int(o["summary"]["n_mappings_this_rank_all_shards"]),

@@ -30,6 +30,7 @@ struct mm_ctx {
   // grow-only scratch of the mapq / EM / fetch entry points (cudaMalloc + cudaFree per call would cost more than the kernels)
   struct {
     DevBuf<double> dId, dMq, dNl;
+    DevBuf<uint32_t> gOne, gAll, gSendA, gRecvA, gSendB, gRecvB; DevBuf<int64_t> gRange;      // collectives' slabs (grow-only: no cudaMalloc / cudaFree per batch)
     DevBuf<int32_t> dSh, dSk, dLen, dSt, dTax, tmpA, tmpB;
     DevBuf<int64_t> dOff;
   } scr;
@@ -454,7 +455,7 @@ int mm_map_batch_sharded_dev(mm_ctx* c, const mm_index* idx, const void* dev, co
     if (R > 1) {
       m.join_sketch();                                           // the gathered strands must be final
       // 1. per-rank scalars
-      DevBuf<uint32_t> one, all; one.ensure(8); all.ensure((size_t)8 * R);
+      auto& one = c->scr.gOne; auto& all = c->scr.gAll; one.ensure(8); all.ensure((size_t)8 * R);
       uint32_t h[8] = {(uint32_t)m.n_reads, (uint32_t)(m.n_q & 0xffffffffu), (uint32_t)((uint64_t)m.n_q >> 32), (uint32_t)m.maxSketch, (uint32_t)m.nShort_,
                        (uint32_t)((uint64_t)m.basesOk_ & 0xffffffffu), (uint32_t)((uint64_t)m.basesOk_ >> 32), (uint32_t)m.n_ambig};
       h2d(rt, one.p, h, sizeof h); allgather_u32(c, one.p, all.p, 8);
@@ -472,7 +473,7 @@ int mm_map_batch_sharded_dev(mm_ctx* c, const mm_index* idx, const void* dev, co
       if (first_read) *first_read = myFirst;
       // 2. padded slabs: [readLen | sOf] (2 capN words) and [qHash | qStrand packed 4 per word] (capQ + capQ/4 + 1 words)
       const size_t wq = (size_t)capQ + (size_t)(capQ + 3) / 4;
-      DevBuf<uint32_t> sendA, recvA, sendB, recvB;
+      auto& sendA = c->scr.gSendA; auto& recvA = c->scr.gRecvA; auto& sendB = c->scr.gSendB; auto& recvB = c->scr.gRecvB;
       sendA.ensure((size_t)2 * capN + 1); recvA.ensure(((size_t)2 * capN + 1) * R); sendB.ensure(wq + 1); recvB.ensure((wq + 1) * R);
       dev_memset(rt, sendA.p, 0, 4 * ((size_t)2 * capN + 1)); dev_memset(rt, sendB.p, 0, 4 * (wq + 1));
       d2d(rt, sendA.p, m.readLen.p, 4 * (size_t)m.n_reads); d2d(rt, sendA.p + capN, m.sOf.p, 4 * (size_t)m.n_reads);
@@ -1141,7 +1142,7 @@ int mm_classify_exchange(mm_ctx* c, int32_t read_lo, int32_t read_hi, int64_t* n
   StageTimer tm(rt, &c->last_ms);
   if (!t.sorted) maptable_sort(c, (int32_t)cl.readsSeen);
   // 1. every rank's count
-  DevBuf<uint32_t> one, all; one.ensure(1); all.ensure((size_t)R);
+  auto& one = c->scr.gOne; auto& all = c->scr.gAll; one.ensure(8); all.ensure((size_t)8 * R);
   uint32_t mine = (uint32_t)t.n; h2d(rt, one.p, &mine, 4);
   allgather_u32(c, one.p, all.p, 1);
   std::vector<uint32_t> cnt((size_t)R); d2h(rt, cnt.data(), all.p, 4 * (size_t)R);
@@ -1149,7 +1150,7 @@ int mm_classify_exchange(mm_ctx* c, int32_t read_lo, int32_t read_hi, int64_t* n
   if (tot >= ((int64_t)1 << 31)) throw Error(MM_ERANGE, "more than 2^31 mappings in one exchange: use smaller read batches");
   if (cap > 0) {
     // 2. one padded slab of 6 columns per rank, all-gathered
-    DevBuf<uint32_t> send, recv; send.ensure((size_t)6 * cap); recv.ensure((size_t)R * 6 * cap);
+    auto& send = c->scr.gSendA; auto& recv = c->scr.gRecvA; send.ensure((size_t)6 * cap); recv.ensure((size_t)R * 6 * cap);
     DevBuf<int32_t>* cols[6] = {&t.read, &t.seq, &t.pos, &t.shared, &t.sketch, &t.strand};
     dev_memset(rt, send.p, 0, 4 * (size_t)6 * cap);
     for (int a = 0; a < 6; a++) d2d(rt, send.p + (size_t)a * cap, cols[a]->p, 4 * (size_t)t.n);
@@ -1164,7 +1165,7 @@ int mm_classify_exchange(mm_ctx* c, int32_t read_lo, int32_t read_hi, int64_t* n
     t.n = tot; t.sorted = false;
     maptable_sort(c, (int32_t)cl.readsSeen, true);      // ranks may own interleaved contig ranges: order by (read, contig)
     // 4. this rank finalises the reads [read_lo, read_hi)
-    DevBuf<int64_t> rg; rg.ensure(2);
+    auto& rg = c->scr.gRange; rg.ensure(2);
     foreach(rt, 2, ReadRangeFn{t.read.p, t.n, read_lo, read_hi, rg.p});
     int64_t h[2]; d2h(rt, h, rg.p, sizeof h);
     const int64_t keep = h[1] - h[0];
