@@ -14,6 +14,7 @@
 // dupIdx/dupPrev/dupNext give the distance (in index entries) to the previous/next such occurrence.
 #pragma once
 #include "mm_sketch.h"
+#include <algorithm>
 
 namespace mm {
 

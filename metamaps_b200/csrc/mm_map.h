@@ -22,6 +22,9 @@
 #include "mm_stdsort.h"
 
 namespace mm {
+#ifdef MM_HOST_EMU
+static long long g_emu_sweep_iters = 0;      // test hook: events applied by the banded sweep (how much the window skipping saves)
+#endif
 
 // event code of one reference minimizer of a span: bit 31 = its hash is in the read sketch (idx = 1-based query rank),
 // else idx = gap (number of query hashes below it); bits 30/29 = its insertion / deletion does not change the window's
@@ -626,6 +629,18 @@ struct L2ClassifyFn {
   const int64_t* beg0; const int32_t* cRead; const uint32_t* qHash; const int64_t* qOff; const int32_t* sOf;
   uint2* ev;
   const int64_t* fe; const int64_t* le; const int32_t* readLen; const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; int k, w;
+  // Per group of 32 consecutive span elements of a candidate (K5b's window skipping, see l2_sweep_band): low 16 bits = how many
+  // of them are in the read sketch, high 16 bits = element count of the window that starts at the group's first element
+  // (clipped).  Candidate c's groups start at grp_base(c); may be null.
+  uint32_t* grp;
+  MM_HD int64_t grp_base(int64_t c) const { return ((ldg(evOff + c) - evBase) >> 5) + (c - cand0); }
+  MM_HD uint32_t window_len(int64_t j, int64_t last, int32_t cmw) const {       // elements of [j, first element with wpos >= wpos[j] + cmw)
+    const int64_t lim = (int64_t)(ldg(miWs + j) >> 1) + cmw;
+    int64_t lo = j, hi = last;
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if ((int64_t)(ldg(miWs + m) >> 1) < lim) lo = m + 1; else hi = m; }
+    const int64_t n = lo - j;
+    return n > 65535 ? 65535u : (uint32_t)n;
+  }
   MM_HD void operator()(int64_t t) const {
     int64_t c = cand0 + upper_bound_idx(evOff + cand0, nCand + 1, t + evBase) - 1;
     int64_t j = ldg(beg0 + c) + (t + evBase - ldg(evOff + c));
@@ -638,6 +653,12 @@ struct L2ClassifyFn {
     if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u)
       code |= CODE_DUP | dup_event_flags(miWs, dupRB, dupLinks, n_dup, j, ldg(beg0 + c), ldg(fe + c), ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1));
     ev[t] = make_uint2(code, ldg(miWs + j));
+    if (grp) {                                    // element-wise form of the summaries (the array is zeroed before the pass)
+      const int64_t rel = j - ldg(beg0 + c);
+      uint32_t add = (code & CODE_MATCH) ? 1u : 0u;
+      if ((rel & 31) == 0) add += window_len(j, ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1)) << 16;
+      if (add) atomic_add(grp + grp_base(c) + (rel >> 5), add);
+    }
   }
 };
 
@@ -678,7 +699,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
       return (lo < s && smq[lo] == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
     };
     // four elements per thread and trip: the twelve global loads are issued before the first search needs one
-    for (int32_t t0 = threadIdx.x; t0 < n; t0 += 4 * blockDim.x) {
+    for (int32_t t0 = threadIdx.x; (t0 & ~31) < n; t0 += 4 * blockDim.x) {      // warp-uniform bound: the ballots below need the whole warp
       uint32_t h[4], wsv[4], db[4]; bool on[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -686,13 +707,20 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
         const int64_t j = b0 + (on[u] ? t : 0);
         h[u] = __ldg(a.miHash + j); wsv[u] = __ldg(a.miWs + j); db[u] = (__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u;
       }
+      const int64_t gb = a.grp ? a.grp_base(c) : 0;
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        if (!on[u]) continue;
         const int32_t t = t0 + u * (int32_t)blockDim.x;
-        uint32_t code = rank_code(h[u]);
-        if (db[u]) code |= CODE_DUP | dup_event_flags(a.miWs, a.dupRB, a.dupLinks, a.n_dup, b0 + t, b0, fe, le, cmw);
-        a.ev[e0 + t] = make_uint2(code, wsv[u]);
+        uint32_t code = 0;
+        if (on[u]) {
+          code = rank_code(h[u]);
+          if (db[u]) code |= CODE_DUP | dup_event_flags(a.miWs, a.dupRB, a.dupLinks, a.n_dup, b0 + t, b0, fe, le, cmw);
+          a.ev[e0 + t] = make_uint2(code, wsv[u]);
+        }
+        if (a.grp) {                                // the warp's 32 lanes hold one group: its lane 0 writes the summary (plain store)
+          const unsigned m = __ballot_sync(0xffffffffu, on[u] && (code & CODE_MATCH));
+          if ((threadIdx.x & 31) == 0 && on[u]) a.grp[gb + (t >> 5)] = (uint32_t)__popc(m) | (a.window_len(b0 + t, le, cmw) << 16);
+        }
       }
     }
   }
@@ -711,6 +739,7 @@ struct L2SweepArgs {
   const int64_t* beg0; const int64_t* fe; const int64_t* le; const int32_t* cRead; const int32_t* sOf; const int32_t* readLen;
   const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; int k, w;
   int32_t* oShared; int32_t* oPos; int32_t* oValid; int64_t* oOptS; int64_t* oOptE; int32_t* oIstar;
+  const uint32_t* grp;       // K5a's per-32-element summaries (match count | window length << 16), or null: no window skipping
 };
 
 // Branch-free updates: every lane of a warp runs the same instruction stream whatever the event is.  cnt[] has
@@ -1098,6 +1127,72 @@ MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0
     active = end < last;                                     // else the reference's loop is over before this window is evaluated
   }
   BandSweep<Ev> z{a, e, ev, cnt, mb, BW, b0, s, sh, 0, 0, 0, 0, false, false};
+  // ---- window skipping.  shared(W) <= number of span elements of W whose hash is in the read sketch =: M(W), and every window the
+  // loop evaluates while its first element is b lies inside [b, E(b)), E(b) = first element at or beyond wpos[b] + cmw.  So with
+  // T = the shared count of ANY evaluated window (a lower bound of the optimum), a window start b with M([b, E(b))) < T can
+  // neither be the optimum nor tie with it (computeMap.hpp:510-533 compares with > and ==): it need not be visited.  K5a left, per
+  // group of 32 span elements, the group's match count and E of its first element; per group g of window starts the bound
+  // U(g) = matches in [32 g, E(32 (g+1))) covers all its windows.  T = the window at the middle of the group with the largest U
+  // (one state build); the sweep then runs from the first to the last group with U >= T only.  On a true locus about half of
+  // the span qualifies; where nothing matches T is 0 and everything is swept as before.
+  if (active && a.grp) {
+    const uint32_t* G = a.grp + (((ldg(a.evOff + c) - a.evBase) >> 5) + (c - a.cand0));
+    const int32_t nG = (last + 31) >> 5;
+    const int32_t sEnd = B1 < last ? B1 : last;
+    const int32_t g0 = B0 >> 5, g1 = (sEnd + 31) >> 5;
+    if (g1 - g0 >= 4) {
+      int32_t gMax = g0, uMax = -1;
+      auto scan = [&](int32_t thr, int32_t& gF, int32_t& gL) {     // thr < 0: locate the maximum; else first / last group with U >= thr
+        int32_t hi = g0, S = 0;
+        for (int32_t g = g0; g < g1; g++) {
+          int32_t R = nG;
+          if (g + 1 < nG) { const uint32_t wl = ldg(G + g + 1) >> 16; if (wl != 65535u) { const int32_t r_ = (32 * (g + 1) + (int32_t)wl + 31) >> 5; R = r_ < nG ? r_ : nG; } }
+          if (R < g + 1) R = g + 1;
+          for (; hi < R; hi++) S += (int32_t)(ldg(G + hi) & 0xFFFFu);
+          if (thr < 0) { if (S > uMax) { uMax = S; gMax = g; } }
+          else if (S >= thr) { if (gF < 0) gF = g; gL = g; }
+          S -= (int32_t)(ldg(G + g) & 0xFFFFu);
+        }
+      };
+      int32_t dF = -1, dL = -1;
+      scan(-1, dF, dL);
+      int32_t T = 0;
+      if (uMax > 0) {
+        int32_t bs = 32 * gMax + 16; if (bs < B0) bs = B0; if (bs >= sEnd) bs = sEnd - 1;
+        int32_t es = last;
+        if (bs == 0) es = (int32_t)(ldg(a.fe + c) - b0);
+        else {
+          const int32_t lim = (int32_t)(ldg(&e[bs].y) >> 1) + cmw;
+          int32_t l = bs, h = last;
+          while (l < h) { const int32_t m = (l + h) >> 1; if ((int32_t)(ldg(&e[m].y) >> 1) < lim) l = m + 1; else h = m; }
+          es = l;
+        }
+        if (es < last) {                                          // a window the loop does evaluate
+          z.rebuild(bs, es, (int32_t)(((int64_t)s * s) / (s + (es - bs) + 1)), 0);
+          if (z.bad || z.out_of_band()) z.rebuild(bs, es, -1, 0);
+          if (!(z.fail || z.bad)) T = z.shared;
+          z.fail = false; z.bad = false;                          // the sweep proper builds its own first window below
+        }
+      }
+      if (T > 0) {
+        int32_t gF = -1, gL = -1;
+        scan(T, gF, gL);
+        if (gF >= 0) {
+          if (32 * gF > B0) B0 = 32 * gF;
+          if (32 * (gL + 1) < B1) B1 = 32 * (gL + 1);
+          beg = B0; end = last;
+          if (B0 == 0) end = (int32_t)(ldg(a.fe + c) - b0);
+          else if (B0 < last) {
+            const int32_t lim = (int32_t)(ldg(&e[B0].y) >> 1) + cmw;
+            int32_t l = B0, h = last;
+            while (l < h) { const int32_t m = (l + h) >> 1; if ((int32_t)(ldg(&e[m].y) >> 1) < lim) l = m + 1; else h = m; }
+            end = l;
+          }
+          active = end < last;
+        }
+      }
+    }
+  }
   if (active) {
     // slidemap.insert_ref(sw_beg, sw_end) (computeMap.hpp:488).  With every window minimizer W-only, F(i) ~ i*(1 + nW/s):
     // try the band around that istar first (one scan); if the guess misses, locate istar with the histogram (two scans).
@@ -1144,6 +1239,9 @@ MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0
       dbgIters++;
 #endif
       const uint32_t code = pCode; const int32_t isDel = pIsDel, wb = pWb; const bool doEval = pEval;
+#ifdef MM_HOST_EMU
+      g_emu_sweep_iters++;
+#endif
       beg += isDel; end += 1 - isDel;                           // the window this event produces
       const bool more = end < last && beg < B1;
       if (more) merge_step();                                   // event k+1: independent of the band state
@@ -1408,6 +1506,7 @@ struct Mapper {
   MapStats st;
   int sweepBand = 256, sweepRing = 8, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT, sweepWideFrom = 0x7fffffff;   // wide-band class: measured neutral on config 2, off unless MM_SWEEP_WIDE_FROM is set
   DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemSeg, segCnt; DevBuf<BandPart> bandParts; std::vector<int64_t> hEvSpan;
+  DevBuf<uint32_t> grpSum; bool sweepSkip = true;      // K5a's per-group summaries for K5b's window skipping (MM_SWEEP_SKIP=0: off)
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
   Mapper(Runtime& r, Prims& p, Sketcher& s) : rt(r), pr(p), sk(s) {
@@ -1415,9 +1514,10 @@ struct Mapper {
     if (const char* e = getenv("MM_EV_BUDGET")) { long long v = atoll(e); if (v > 0) evBudget = v; }   // tests: force several L2 passes
     // K5b variants (tests and A/B measurements): band width, event-ring depth, and which sweep runs first
     if (const char* e = getenv("MM_SWEEP_BAND")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) sweepBand = v; }
-    if (const char* e = getenv("MM_SWEEP_RING")) { int v = atoi(e); if (v == 4 || v == 8) sweepRing = v; }
+    if (const char* e = getenv("MM_SWEEP_RING")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) sweepRing = v; }
     if (const char* e = getenv("MM_SWEEP_WIDE_FROM")) { int v = atoi(e); if (v >= 1) sweepWideFrom = v; }
     if (const char* e = getenv("MM_SWEEP_SEG")) { int v = atoi(e); if (v >= 64) sweepSeg = v; }
+    if (const char* e = getenv("MM_SWEEP_SKIP")) sweepSkip = atoi(e) != 0;
     if (const char* e = getenv("MM_SWEEP")) sweepMode = !strcmp(e, "full") ? 1 : !strcmp(e, "global") ? 2 : 0;
   }
 
@@ -1721,8 +1821,9 @@ struct Mapper {
         ev.ensure((size_t)nEv + 64);      // the sweeps prefetch a few events past the end of a span
         {
           StageTimer t(rt, &st.ms[6]);
+          if (sweepSkip) { grpSum.ensure((size_t)(nEv >> 5) + (size_t)nc + 4); dev_memset(rt, grpSum.p, 0, 4 * ((size_t)(nEv >> 5) + (size_t)nc + 4)); }
           L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p,
-                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w};
+                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, sweepSkip ? grpSum.p : nullptr};
 #ifndef MM_HOST_EMU
           if ((int64_t)maxSketch * 4 <= 200 * 1024 && maxSketch < 65535) {      // bucket starts are 16-bit ranks
             if (rt.first((const void*)l2_classify_smem_kernel)) MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1737,7 +1838,7 @@ struct Mapper {
             foreach(rt, nEv, cf);
         }
         L2SweepArgs sa{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, le.p, cRead.p, sOf.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w,
-                       oShared.p, oPos.p, oValid.p, oOptS.p, oOptE.p, oIstar.p};
+                       oShared.p, oPos.p, oValid.p, oOptS.p, oOptE.p, oIstar.p, sweepSkip ? grpSum.p : nullptr};
         {
           StageTimer t(rt, &st.ms[7]);
           smemSwept += sweep_pass(sa, nc, cntBytes);
@@ -1932,6 +2033,7 @@ struct Mapper {
     else if (BAND == 128 && RING == 4 && two) launch_band_t<128, 4, 2>(sa, order, nc);
     else if (BAND == 128 && RING == 4) launch_band_t<128, 4>(sa, order, nc);
     else if (BAND == 128) launch_band_t<128, 8>(sa, order, nc);
+    else if (RING == 2) launch_band_t<256, 2>(sa, order, nc);
     else if (RING == 4) launch_band_t<256, 4>(sa, order, nc);
     else launch_band_t<256, 8>(sa, order, nc);
   }
