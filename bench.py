@@ -653,6 +653,22 @@ def extra_legs(extra, args, wl, torch, dist, dev, ctx, capi, pipeline, world, ra
         except Exception as e:
             extra[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
         torch.cuda.empty_cache()
+    def h2d_probe():
+        """What the host side can deliver when all ranks upload at once (what bounds `e2e` at N = 8): every rank copies 1 GiB of
+        pinned host memory to its GPU five times, all ranks together; GB/s per rank = bytes / the slowest rank's time."""
+        nb = 1 << 30
+        hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True); dbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
+        dbuf.copy_(hbuf, non_blocking=True); torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            dbuf.copy_(hbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        del hbuf, dbuf
+        return {"GBps_per_rank_all_ranks_uploading": 5 * nb / sec / 1e9, "GBps_aggregate": 5 * nb * world / sec / 1e9, "ranks": world,
+                "what": "cudaMemcpyAsync pinned host -> device, 1 GiB x 5 per rank, all ranks concurrently (DMA; the e2e leg's K0 reads the same pinned pages over PCIe)"}
+    leg("h2d_probe", h2d_probe)
     if not by_contigs:
         leg("config3", lambda: config3("reads", holder[0]))
     if world == 1:

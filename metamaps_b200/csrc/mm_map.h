@@ -1506,7 +1506,11 @@ struct Mapper {
   MapStats st;
   int sweepBand = 256, sweepRing = 8, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT, sweepWideFrom = 0x7fffffff;   // wide-band class: measured neutral on config 2, off unless MM_SWEEP_WIDE_FROM is set
   DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemSeg, segCnt; DevBuf<BandPart> bandParts; std::vector<int64_t> hEvSpan;
-  DevBuf<uint32_t> grpSum; bool sweepSkip = true;      // K5a's per-group summaries for K5b's window skipping (MM_SWEEP_SKIP=0: off)
+  // K5a's per-group summaries for K5b's window skipping.  OFF unless MM_SWEEP_SKIP=1: exact (parity-tested) and it halves the
+  // events on config-2-like data, but measured on config 2 it LOSES: K5a 5.1 -> 14.8 ms (one lane per group runs the
+  // window-length search), K5b 12.7 -> 17.1 ms (a second state build per item, and in a tile of 32 lanes the slowest lane --
+  // a candidate that skips nothing -- still sets the tile's time).  Kept as the starting point for a two-kernel version.
+  DevBuf<uint32_t> grpSum; bool sweepSkip = false;
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
   Mapper(Runtime& r, Prims& p, Sketcher& s) : rt(r), pr(p), sk(s) {

@@ -137,7 +137,7 @@ def _repetitive_workload():
     return [synth.codes_to_ascii(c) for c in db.contig_codes], [synth.codes_to_ascii(r) for r in reads]
 
 
-@pytest.mark.parametrize("env", [{"MM_SWEEP_SKIP": "0"}, {"MM_SWEEP_BAND": "64"}, {"MM_SWEEP_BAND": "128", "MM_SWEEP_SEG": "100"}, {"MM_SWEEP_SEG": "64"},
+@pytest.mark.parametrize("env", [{"MM_SWEEP_SKIP": "1"}, {"MM_SWEEP_BAND": "64"}, {"MM_SWEEP_BAND": "128", "MM_SWEEP_SEG": "100"}, {"MM_SWEEP_SEG": "64"},
                                  {"MM_SWEEP": "global"}])
 def test_sweep_variants(oracle, small_workload, monkeypatch, env):
     """K5b: a narrow band (the state is rebuilt from the window again and again) and the full-state sweep must both
