@@ -41,7 +41,7 @@ def build_host(lib_dir: str = HERE, lib_name: str = "metamaps_b200", out: str = 
     deps = [HOST_SRC, os.path.join(HERE, "csrc", "host", "mm_fastx.hpp"), os.path.join(ROOT, "include", "metamaps_b200.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-pthread", HOST_SRC, "-o", out, "-L" + lib_dir, "-l" + lib_name,
+    subprocess.run(["/usr/bin/g++", "-O3", "-std=c++17", "-fopenmp", "-pthread", HOST_SRC, "-o", out, "-L" + lib_dir, "-l" + lib_name,
                     "-Wl,-rpath," + lib_dir + ":$ORIGIN", "-lz"], check=True)
     return out
 

@@ -237,19 +237,26 @@ struct MappedBatch {            // what the GPU thread hands to the formatter
 inline void put_g6(std::string& o, double v) { char b[40]; auto r = std::to_chars(b, b + sizeof b, v, std::chars_format::general, 6); o.append(b, (size_t)(r.ptr - b)); }
 inline void put_int(std::string& o, long long v) { char b[24]; auto r = std::to_chars(b, b + sizeof b, v); o.append(b, (size_t)(r.ptr - b)); }
 
-// parser thread body: FASTA/FASTQ records -> batches below the byte / read caps
-static void parse_batches(const std::string& path, size_t capBytes, int64_t capReads, BoundedQueue<std::unique_ptr<ReadBatch>>& out) {
+// parser thread body: FASTA/FASTQ records -> batches below the byte / read caps.  Batch objects come back from the writer through
+// `recycled` so that their (hundreds of MB of) text buffers are touched-in once, not mapped and faulted again for every batch.
+static void parse_batches(const std::string& path, size_t capBytes, int64_t capReads, BoundedQueue<std::unique_ptr<ReadBatch>>& out,
+                          BoundedQueue<std::unique_ptr<ReadBatch>>& recycled, int poolSize) {
   mmhost::FastxReader rd(path);
   if (!rd.ok()) die("Cannot open " + path);
-  auto cur = std::make_unique<ReadBatch>(); cur->buf.reserve(capBytes + (capBytes >> 3));
+  int made = 0;
+  auto fresh = [&]() {
+    std::unique_ptr<ReadBatch> b;
+    if (made < poolSize) { made++; b = std::make_unique<ReadBatch>(); b->buf.reserve(capBytes + (capBytes >> 3)); }
+    else if (!recycled.pop(b)) { b = std::make_unique<ReadBatch>(); }
+    b->buf.clear(); b->off.assign(1, 0); b->names.clear();
+    return b;
+  };
+  auto cur = fresh();
   for (;;) {
     const long len = rd.read_into(cur->buf);
     if (len < 0) break;
     cur->names.push_back(rd.name); cur->off.push_back((int64_t)cur->buf.size());
-    if (cur->buf.size() >= capBytes || (int64_t)cur->names.size() >= capReads) {
-      out.push(std::move(cur));
-      cur = std::make_unique<ReadBatch>(); cur->buf.reserve(capBytes + (capBytes >> 3));
-    }
+    if (cur->buf.size() >= capBytes || (int64_t)cur->names.size() >= capReads) { out.push(std::move(cur)); cur = fresh(); }
   }
   if (!cur->names.empty()) out.push(std::move(cur));
   out.close();
@@ -274,9 +281,9 @@ static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& m
     FILE* metaLengths = fopen(chunk < 0 ? (prefix + ".meta.unmappedReadsLengths").c_str() : "/dev/null", "wb");
     size_t total = 0, tooShort = 0, mapped = 0, notMapped = 0;
     std::unordered_set<std::string> seenIDs;
-    BoundedQueue<std::unique_ptr<ReadBatch>> parsed(2);
+    BoundedQueue<std::unique_ptr<ReadBatch>> parsed(2), recycled(8);
     BoundedQueue<std::unique_ptr<MappedBatch>> done(2);
-    std::thread parser([&] { parse_batches(queries[fi], capBytes, maxReads, parsed); });
+    std::thread parser([&] { parse_batches(queries[fi], capBytes, maxReads, parsed, recycled, /*pool*/6); });
     // formatter / writer: reportReadMappings' 12 columns (computeMap.hpp:546-588) + the two of addMappingQualities (mapWrap.h:313-320)
     std::thread writer([&] {
       std::unique_ptr<MappedBatch> mb;
@@ -322,7 +329,9 @@ static void map_queries(mm_ctx* ctx, mm_index* idx, const std::vector<Contig>& m
           }
         }
         for (const std::string& o : piece) if (!o.empty()) fwrite(o.data(), 1, o.size(), out);
+        recycled.push(std::move(mb->in));                    // the text buffer goes back to the parser
       }
+      recycled.close();
     });
     // GPU thread (this one): K0-K5 + identity + mapping quality per batch, results straight from the device-resident table
     std::unique_ptr<ReadBatch> rb;

@@ -7,7 +7,7 @@
 //   * return value: sequence length, -1 at end of file, -2 for a truncated quality string.
 // Unlike kseq's character-at-a-time getc loop this reader works on whole buffer spans: lines are found with memchr,
 // a line made of letters only (the normal case) is appended with one memcpy, quality lines are counted, not stored.
-// `append_to` lets the caller have the bases written straight at the end of its own batch buffer (e.g. pinned memory).
+// `read_into` appends the bases straight to the caller's batch buffer.  Plain files bypass zlib.
 #pragma once
 #include <zlib.h>
 
@@ -21,6 +21,7 @@ namespace mmhost {
 
 class FastxReader {
   gzFile fp_ = nullptr;
+  FILE* raw_ = nullptr;              // plain (not gzip) input: read() straight into the buffer, no pass through zlib
   std::vector<unsigned char> buf_;
   size_t begin_ = 0, end_ = 0;
   bool eof_ = false;
@@ -30,7 +31,7 @@ class FastxReader {
     if (begin_ < end_) return true;
     if (eof_) return false;
     begin_ = 0;
-    int n = gzread(fp_, buf_.data(), (unsigned)buf_.size());
+    int n = raw_ ? (int)fread(buf_.data(), 1, buf_.size(), raw_) : gzread(fp_, buf_.data(), (unsigned)buf_.size());
     if (n <= 0) { eof_ = true; end_ = 0; return false; }
     end_ = (size_t)n;
     return true;
@@ -48,14 +49,19 @@ class FastxReader {
 
   explicit FastxReader(const std::string& path, size_t bufBytes = (size_t)4 << 20) : buf_(bufBytes) {
     FILE* f = fopen(path.c_str(), "r");
-    if (f) { fp_ = gzdopen(fileno(f), "r"); if (fp_) gzbuffer(fp_, 1 << 20); }
+    if (!f) return;
+    unsigned char magic[2] = {0, 0};
+    const size_t got = fread(magic, 1, 2, f);
+    rewind(f);
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) { fp_ = gzdopen(fileno(f), "r"); if (fp_) gzbuffer(fp_, 1 << 20); }
+    else { raw_ = f; setvbuf(raw_, nullptr, _IONBF, 0); }
   }
-  ~FastxReader() { if (fp_) gzclose(fp_); }
-  bool ok() const { return fp_ != nullptr; }
+  ~FastxReader() { if (fp_) gzclose(fp_); if (raw_) fclose(raw_); }
+  bool ok() const { return fp_ != nullptr || raw_ != nullptr; }
 
   long read() { seq.clear(); return read_into(seq); }
 
-  // Appends the record's bases to `out` (std::string-like: size(), resize(), data()).  Returns like kseq_read.
+  // Appends the record's bases to `out` (std::string-like: size(), append(), push_back()).  Returns like kseq_read.
   template <class Buf>
   long read_into(Buf& out) {
     int c;
@@ -96,7 +102,7 @@ class FastxReader {
       const void* nl = memchr(p, '\n', avail);
       const size_t len = nl ? (size_t)((const unsigned char*)nl - p) : avail;
       if (clean_span(p, len)) {
-        const size_t at = out.size(); out.resize(at + len); memcpy(&out[0] + at, p, len);
+        out.append((const char*)p, len);
         begin_ += len + (nl ? 1 : 0);
         continue;
       }
@@ -106,7 +112,7 @@ class FastxReader {
       for (; i < lim; i++) {
         const unsigned char ch = p[i];
         if (ch == '>' || ch == '+' || ch == '@') { stop = true; break; }
-        if (isgraph(ch)) { out.resize(out.size() + 1); out[out.size() - 1] = (char)ch; }
+        if (isgraph(ch)) out.push_back((char)ch);
       }
       if (stop) { c = p[i]; begin_ += i + 1; break; }
       begin_ += lim;
@@ -133,7 +139,8 @@ class FastxReader {
       for (size_t i = 0; i < len; i++) valid += (size_t)((unsigned char)(p[i] - 33) < 95);
       if (q + valid < n) { q += valid; begin_ += len + (nl ? 1 : 0); continue; }
       size_t i = 0;
-      for (; i < len && q < n; i++) q += (size_t)((unsigned char)(p[i] - 33) < 95);
+      if (valid == len) { i = n - q; q = n; }                 // a line of quality characters only: the count is reached after n - q of them
+      else for (; i < len && q < n; i++) q += (size_t)((unsigned char)(p[i] - 33) < 95);
       begin_ += i;
     }
     last_char_ = 0;
