@@ -668,6 +668,7 @@ struct L2ClassifyFn {
 // on the top 11 hash bits (first sketch rank of every bucket), so the rank search of a reference minimizer is a lookup
 // plus a short binary search inside one bucket instead of log2(s) steps.  Same codes as L2ClassifyFn.
 static const int CLS_BUCKET_BITS = 11, CLS_BUCKETS = 1 << CLS_BUCKET_BITS;
+template <bool GRP>
 __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, int32_t perCta) {
   extern __shared__ uint32_t smq[];
   __shared__ uint16_t bstart[CLS_BUCKETS + 2];
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
       return (lo < s && smq[lo] == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
     };
     // four elements per thread and trip: the twelve global loads are issued before the first search needs one
-    for (int32_t t0 = threadIdx.x; (t0 & ~31) < n; t0 += 4 * blockDim.x) {      // warp-uniform bound: the ballots below need the whole warp
+    for (int32_t t0 = threadIdx.x; GRP ? ((t0 & ~31) < n) : (t0 < n); t0 += 4 * blockDim.x) {      // GRP: warp-uniform bound, the ballots below need the whole warp
       uint32_t h[4], wsv[4], db[4]; bool on[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
         const int64_t j = b0 + (on[u] ? t : 0);
         h[u] = __ldg(a.miHash + j); wsv[u] = __ldg(a.miWs + j); db[u] = (__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u;
       }
-      const int64_t gb = a.grp ? a.grp_base(c) : 0;
+      const int64_t gb = GRP ? a.grp_base(c) : 0;
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int32_t t = t0 + u * (int32_t)blockDim.x;
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
           if (db[u]) code |= CODE_DUP | dup_event_flags(a.miWs, a.dupRB, a.dupLinks, a.n_dup, b0 + t, b0, fe, le, cmw);
           a.ev[e0 + t] = make_uint2(code, wsv[u]);
         }
-        if (a.grp) {                                // the warp's 32 lanes hold one group: its lane 0 writes the summary (plain store)
+        if (GRP) {                                  // the warp's 32 lanes hold one group: its lane 0 writes the summary (plain store)
           const unsigned m = __ballot_sync(0xffffffffu, on[u] && (code & CODE_MATCH));
           if ((threadIdx.x & 31) == 0 && on[u]) a.grp[gb + (t >> 5)] = (uint32_t)__popc(m) | (a.window_len(b0 + t, le, cmw) << 16);
         }
@@ -1100,7 +1101,7 @@ static const int32_t BAND_LAST_SEG = 1 << 30;
 #else
 #define MM_WARP_ANY(x) (x)
 #endif
-template <class Ev>
+template <class Ev, bool SKIP = false>
 MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0, int32_t B1, uint8_t* cnt, uint32_t* mb, int32_t BW, Ev& ev, BandPart& out) {
   out.shared = 0; out.bpos = 0; out.lpos = 0; out.optS = 0; out.optE = 0; out.istar = 0; out.any = 0; out.fail = 0;
   if (!valid) c = a.cand0;                                   // harmless loads; the lane never becomes active
@@ -1135,7 +1136,7 @@ MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0
   // U(g) = matches in [32 g, E(32 (g+1))) covers all its windows.  T = the window at the middle of the group with the largest U
   // (one state build); the sweep then runs from the first to the last group with U >= T only.  On a true locus about half of
   // the span qualifies; where nothing matches T is 0 and everything is swept as before.
-  if (active && a.grp) {
+  if (SKIP && active && a.grp) {       // compiled out of the default kernel: the unused path cost 0.7 ms of register pressure
     const uint32_t* G = a.grp + (((ldg(a.evOff + c) - a.evBase) >> 5) + (c - a.cand0));
     const int32_t nG = (last + 31) >> 5;
     const int32_t sEnd = B1 < last ? B1 : last;
@@ -1347,7 +1348,8 @@ struct L2SweepBandFn {
 #ifdef MM_BAND_DEBUG
     ::g_band_dbg_cur[0] = ::g_band_dbg_cur[1] = ::g_band_dbg_cur[2] = 0;
 #endif
-    l2_sweep_band(a, true, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
+    if (a.grp) l2_sweep_band<DirectEv, true>(a, true, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
+    else l2_sweep_band<DirectEv, false>(a, true, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
 #ifdef MM_BAND_DEBUG
     if (i < 1000000) { ::g_band_dbg_n = i; ::g_band_dbg_it[i] = ::g_band_dbg_cur[0]; ::g_band_dbg_win[i] = ::g_band_dbg_cur[1]; ::g_band_dbg_reb[i] = ::g_band_dbg_cur[2]; }
 #endif
@@ -1393,7 +1395,7 @@ struct RingEv {
 
 // Each warp owns WARP_WORDS of shared memory (32 band states + the rings) and pulls tiles of 32 consecutive work items
 // of `order` (descending work: lanes of a tile run loops of similar length) from a global counter.
-template <int BW, int R, int MINB>
+template <int BW, int R, int MINB, bool SKIP = false>
 __global__ void __launch_bounds__(MINB == 1 ? 512 : 384, MINB) l2_sweep_band_kernel(L2SweepArgs a, const uint32_t* order, int64_t nItems, const int32_t* itemCand,
                                                                const int32_t* itemSeg, int32_t seg, BandPart* parts, unsigned int* tileCounter) {
   extern __shared__ __align__(16) uint32_t sm[];
@@ -1416,7 +1418,7 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 384, MINB) l2_sweep_band_ker
     const int32_t sgl = valid ? itemSeg[i] : 0, sg = sgl & ~BAND_LAST_SEG;
     RingEv<R> ev(a.ev, a.evOff[c] - a.evBase, ring);
     BandPart p;
-    l2_sweep_band(a, valid, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)my, my + (BW + 4) / 4, BW, ev, p);
+    l2_sweep_band<RingEv<R>, SKIP>(a, valid, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)my, my + (BW + 4) / 4, BW, ev, p);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (valid) parts[i] = p;
     __syncwarp();
@@ -1830,11 +1832,15 @@ struct Mapper {
                           fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, sweepSkip ? grpSum.p : nullptr};
 #ifndef MM_HOST_EMU
           if ((int64_t)maxSketch * 4 <= 200 * 1024 && maxSketch < 65535) {      // bucket starts are 16-bit ranks
-            if (rt.first((const void*)l2_classify_smem_kernel)) MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (rt.first((const void*)l2_classify_smem_kernel<false>)) {
+              MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+              MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            }
             // contiguous runs of candidates per CTA, ~8 waves of CTAs so that uneven runs average out
             int64_t g = (int64_t)rt.sm_count * 64; if (g > nc) g = nc;
             int32_t perCta = (int32_t)((nc + g - 1) / g); g = (nc + perCta - 1) / perCta;
-            l2_classify_smem_kernel<<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
+            if (cf.grp) l2_classify_smem_kernel<true><<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
+            else l2_classify_smem_kernel<false><<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
             MM_CUDA(cudaGetLastError());
             rt.launches++;
           } else
@@ -2008,7 +2014,7 @@ struct Mapper {
   }
 
 #ifndef MM_HOST_EMU
-  template <int BW, int R, int MINB = 1>
+  template <int BW, int R, int MINB = 1, bool SKIP = false>
   void launch_band_t(const L2SweepArgs& sa, const uint32_t* order, int64_t nc) {
     constexpr int ST = ((BW + 4) / 4 + BW / 32 + 1) | 1;
     constexpr int WARP_BYTES = (2 * R * 32 * 4 + 32 * ST) * 4;
@@ -2022,10 +2028,10 @@ struct Mapper {
       warps = total / ctasPerSm;
       if (const char* e = getenv("MM_SWEEP_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 16) warps = v; }
     }
-    if (rt.first((const void*)l2_sweep_band_kernel<BW, R, MINB>)) MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
+    if (rt.first((const void*)l2_sweep_band_kernel<BW, R, MINB, SKIP>)) MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R, MINB, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
     int64_t tiles = (nc + 31) / 32;
     int64_t g = (tiles + warps - 1) / warps; if (g > (int64_t)rt.sm_count * ctasPerSm) g = (int64_t)rt.sm_count * ctasPerSm;
-    l2_sweep_band_kernel<BW, R, MINB><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, order, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,
+    l2_sweep_band_kernel<BW, R, MINB, SKIP><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, order, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,
                                                                                                (unsigned int*)(scal.p + 1));
     MM_CUDA(cudaGetLastError());
     rt.launches++;
@@ -2039,6 +2045,7 @@ struct Mapper {
     else if (BAND == 128) launch_band_t<128, 8>(sa, order, nc);
     else if (RING == 2) launch_band_t<256, 2>(sa, order, nc);
     else if (RING == 4) launch_band_t<256, 4>(sa, order, nc);
+    else if (sa.grp) launch_band_t<256, 8, 1, true>(sa, order, nc);      // MM_SWEEP_SKIP=1: the only instantiation with window skipping
     else launch_band_t<256, 8>(sa, order, nc);
   }
 #endif
