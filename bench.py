@@ -587,8 +587,9 @@ def same_config_leg(d, wl, bases, ref_map_cls_s, ref_index_s, ref_wall_s, thread
         b2 = int(sum(len(r) for r in reads if len(r) >= wl["min_read_len"]))
         fq_bytes = os.path.getsize(os.path.join(d2, "reads.fq"))
         del db, reads
-        _, _, w2 = run_cli_once(build.HOST_BIN, d2, wl, threads, out="out_b200")
-        cli = {"reads": 20_000, "fastq_bytes": fq_bytes, "seconds": w2, "Mbp_per_s": b2 / 1e6 / w2,
+        ph = []
+        _, _, w2 = run_cli_once(build.HOST_BIN, d2, wl, threads, out="out_b200", timing=ph)
+        cli = {"reads": 20_000, "fastq_bytes": fq_bytes, "seconds": w2, "Mbp_per_s": b2 / 1e6 / w2, "phases": ph,
                "what": "metamaps_b200/metamaps mapDirectly --all + classify, FASTQ + FASTA in, ten files out, process start to exit (parser, GPU and writer threads)"}
     except Exception as e:
         cli = {"error": "%s: %s" % (type(e).__name__, e)}

@@ -347,11 +347,26 @@ def check_index_save_load(ctx, contigs, reads, k, w, path):
     for key in ("s", "cand_off", "seq", "start", "end", "pos", "shared", "votes", "accepted", "valid", "optStart", "optEnd"):
         assert np.array_equal(r1[key], r2[key]), key
     assert r1["summary"]["n_mappings"] > 0
+    import os
+    import pytest
+    size = os.path.getsize(path)
+    with open(path, "r+b") as f:          # a truncated file is refused before anything is allocated from its header
+        f.truncate(size - 64)
+    with pytest.raises(capi.MMError, match="file size"):
+        capi.Index.load(ctx, path)
     with open(path, "r+b") as f:          # a damaged file is refused, not loaded
         f.write(b"XXXX")
-    import pytest
     with pytest.raises(capi.MMError):
         capi.Index.load(ctx, path)
+    # an index without minimizers (every contig shorter than w / k) saves, loads and maps: nothing is found
+    empty = capi.Index(ctx, k, w); empty.add([b"ACGTACG", b"TTGA"]); empty.finalize()
+    assert empty.stats()["n_minimizers"] == 0 and empty.stats()["n_contigs"] == 2
+    empty.save(path + ".empty")
+    e2 = capi.Index.load(ctx, path + ".empty")
+    assert e2.stats()["n_minimizers"] == 0 and e2.stats()["n_contigs"] == 2
+    for ie in (empty, e2):
+        r0 = capi.map_reads(ctx, ie, reads[:5], 80.0, 1000)
+        assert r0["summary"]["n_candidates"] == 0 and r0["summary"]["n_mappings"] == 0
 
 
 def check_api_errors(ctx, tmp_path):
