@@ -497,6 +497,203 @@ __global__ void __launch_bounds__(256) l1_filter_gather16_kernel(const int32_t* 
 }
 #endif
 
+#ifndef MM_HOST_EMU
+// K4 in ONE kernel: probe + contig filter + survivor gather, one CTA per read.  The read's sorted sketch is walked in chunks of
+// PF_CHUNK keys: the chunk is staged into shared memory by the TMA engine (cp.async.bulk + mbarrier, like l1_probe_tma_kernel),
+// every thread keeps four random 16-byte slot reads in flight, and the (start, count) of every probe stays in shared memory for
+// the counting walk over the position lists (pass 1 of l1_filter_gather16_kernel, same flattened walk) -- so the per-probe
+// hitCnt / hitStart / hitOff arrays (20 B per probe written, read twice) and the global prefix sum between the two kernels
+// are gone; the rank of a hit within the read comes from per-chunk prefix sums in shared memory.  The 8-byte (start, count)
+// pairs are spilled to `probeOut` for pass 2 (written and re-read by the same CTA a few microseconds apart: L2).
+// Survivors are appended at a global cursor; if the output buffer is too small the kernel still counts (cursor[0] = survivors
+// needed, cursor[2] = 1) and the host re-runs it with a larger one.  cursor[1] += all seed hits (the H of SURVEY 8d).
+static const int PF_CHUNK = 1024;
+__global__ void __launch_bounds__(256) l1_probe_filter_kernel(const Slot* table, uint32_t mask, int32_t freqThreshold, const uint32_t* qHash, const int64_t* qOff,
+                                                              const int32_t* sOf, const int32_t* minHitsTab, const uint16_t* posSeq16, const uint64_t* posKey,
+                                                              HitKeyLayout lay, int32_t n_reads, uint32_t binMask, unsigned long long* cursor, uint64_t* hitsOut,
+                                                              unsigned long long hitsCap, int32_t* keptPerRead, uint32_t cacheCap, uint2* probeOut) {
+  extern __shared__ __align__(128) uint32_t bins[];            // bins | contig-id cache | chunk keys | chunk counts | chunk starts
+  const uint32_t binWords = (binMask + 1) / 2;
+  uint16_t* cache = reinterpret_cast<uint16_t*>(bins + binWords);
+  uint32_t* keys = bins + binWords + cacheCap / 2;
+  uint32_t* pCnt = keys + PF_CHUNK + 8;
+  uint32_t* pStart = pCnt + PF_CHUNK;
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ unsigned int smTotal, smPos, grpBase[PF_CHUNK / 32 + 1]; __shared__ unsigned long long smBase; __shared__ int smSkip;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  uint32_t phase = 0;
+  for (int32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+    const int32_t s = sOf[r];
+    const int64_t q0 = qOff[r], q1 = qOff[r + 1];
+    if (s == 0 || q1 <= q0) { if (threadIdx.x == 0) keptPerRead[r] = 0; continue; }
+    int32_t mh = minHitsTab[s]; if (mh < 1) mh = 1;
+    for (uint32_t i = threadIdx.x; i < binWords; i += blockDim.x) bins[i] = 0;
+    if (threadIdx.x == 0) { smTotal = 0; smPos = 0; smSkip = 0; }
+    __syncthreads();
+    const uint64_t hiKey = (uint64_t)r << (lay.seqBits + lay.wsBits);
+    uint32_t running = 0;                        // hits of the chunks before the current one (block-uniform)
+    bool anySat = false;
+    // group bases of the chunk in shared memory: hits before each group of 32 probes, and the chunk's total
+    auto chunk_bases = [&](int32_t nchunk) -> uint32_t {
+      const int32_t nG = (nchunk + 31) >> 5;
+      for (int32_t gi = wid; gi < nG; gi += nWarps) {
+        const int32_t i = gi * 32 + lane;
+        uint32_t v = i < nchunk ? pCnt[i] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) grpBase[gi + 1] = v;
+      }
+      __syncthreads();
+      if (wid == 0) {                              // 32 groups at most: one warp scans them
+        uint32_t v = lane < nG ? grpBase[lane + 1] : 0u, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane < nG) grpBase[lane + 1] = running + incl;
+        if (lane == 0) grpBase[0] = running;
+      }
+      __syncthreads();
+      return grpBase[nG] - running;
+    };
+    // the flattened walk over the position lists of the chunk's probes (see l1_filter_gather16_kernel); pass 0 counts, pass 1 gathers
+    auto walk = [&](int pass, int32_t nchunk) {
+      const int32_t nG = (nchunk + 31) >> 5;
+      for (int32_t gi = wid; gi < nG; gi += nWarps) {
+        const int32_t i = gi * 32 + lane;
+        const int32_t c = i < nchunk ? (int32_t)pCnt[i] : 0;
+        const int64_t st = c ? (int64_t)pStart[i] : 0;
+        int32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int32_t ex = incl - c;
+        const int32_t T = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t rankBase = grpBase[gi];
+        constexpr int U = 4;
+        for (int32_t t0 = 0; t0 < T; t0 += 32 * U) {
+          int64_t idx[U]; uint32_t rank[U]; bool ok[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const int32_t t = t0 + 32 * u + lane;
+            int32_t j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+              const int32_t cand = j + step;
+              const int32_t v = __shfl_sync(0xffffffffu, ex, cand & 31);
+              if (cand < 32 && v <= t) j = cand;
+            }
+            const int64_t stj = __shfl_sync(0xffffffffu, st, j);
+            const int32_t exj = __shfl_sync(0xffffffffu, ex, j);
+            ok[u] = t < T; idx[u] = stj + (t - exj); rank[u] = rankBase + (uint32_t)t;
+          }
+          if (pass == 0) {
+            uint32_t sq[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) sq[u] = ok[u] ? (uint32_t)__ldg(posSeq16 + idx[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < U; u++) if (ok[u]) {
+              if (rank[u] < cacheCap) cache[rank[u]] = (uint16_t)sq[u];
+              const uint32_t b_ = sq[u] & binMask;
+              atomicAdd(&bins[b_ >> 1], (b_ & 1u) ? 0x10000u : 1u);
+            }
+          } else {
+            bool keep[U]; uint64_t pk[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              keep[u] = ok[u] && anySat;
+              if (ok[u] && !anySat) {
+                const uint32_t sq = (rank[u] < cacheCap) ? (uint32_t)cache[rank[u]] : (uint32_t)__ldg(posSeq16 + idx[u]);
+                const uint32_t b_ = sq & binMask;
+                keep[u] = ((bins[b_ >> 1] >> ((b_ & 1u) * 16)) & 0xFFFFu) >= (uint32_t)mh;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) pk[u] = keep[u] ? __ldg(posKey + idx[u]) : 0ull;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              const unsigned int m = __ballot_sync(0xffffffffu, keep[u]);
+              if (m) {
+                unsigned int base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(&smPos, (unsigned int)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (keep[u]) hitsOut[smBase + base + __popc(m & ((1u << lane) - 1u))] = hiKey | ((pk[u] >> 32) << lay.wsBits) | (pk[u] & 0xFFFFFFFFull);
+              }
+            }
+          }
+        }
+      }
+    };
+    // ---- pass 0, chunk by chunk: stage keys, probe, count
+    for (int64_t c0 = q0; c0 < q1; c0 += PF_CHUNK) {
+      const int32_t nchunk = (int32_t)((q1 - c0) < PF_CHUNK ? (q1 - c0) : PF_CHUNK);
+      const int64_t a0 = c0 & ~(int64_t)3; const int32_t shift = (int32_t)(c0 - a0);
+      if (threadIdx.x == 0) tma_load_1d(keys, qHash + a0, (uint32_t)(((shift + nchunk + 3) & ~3) * 4), &bar);
+      mbar_wait(&bar, phase); phase ^= 1;
+      for (int32_t i0 = threadIdx.x; i0 < nchunk; i0 += 4 * blockDim.x) {
+        uint32_t h[4]; uint4 v[4]; uint32_t sl[4]; bool act[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int32_t i = i0 + u * (int32_t)blockDim.x;
+          act[u] = i < nchunk;
+          h[u] = act[u] ? keys[shift + i] : 0u;
+          sl[u] = slot_of(h[u], mask);
+          if (act[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(table + sl[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (!act[u]) continue;
+          const int32_t i = i0 + u * (int32_t)blockDim.x;
+          uint4 w = v[u]; uint32_t s_ = sl[u];
+          while (w.y != 0 && w.x != h[u]) { s_ = (s_ + 1) & mask; w = __ldg(reinterpret_cast<const uint4*>(table + s_)); }
+          uint32_t c = 0;
+          if (w.y != 0 && (int64_t)w.y < (int64_t)freqThreshold) c = w.y;        // computeMap.hpp:314 (flagged counts compare above everything)
+          pCnt[i] = c; pStart[i] = w.z;                                            // CSR start < n < 2^32
+          probeOut[c0 + i] = make_uint2(w.z, c);
+        }
+      }
+      __syncthreads();
+      const uint32_t tot = chunk_bases(nchunk);
+      walk(0, nchunk);
+      running += tot;
+      __syncthreads();                             // the chunk arrays are free again
+    }
+    const uint32_t nHits = running;
+    if (nHits == 0) { if (threadIdx.x == 0) keptPerRead[r] = 0; __syncthreads(); continue; }
+    anySat = nHits >= 0xFFF0u;                      // a 16-bit bin may have wrapped: keep everything for this read
+    unsigned int local = 0;
+    if (!anySat) {
+      for (uint32_t i = threadIdx.x; i < binWords; i += blockDim.x) {
+        const uint32_t w = bins[i], lo = w & 0xFFFFu, hi = w >> 16;
+        local += (lo >= (uint32_t)mh) ? lo : 0u;
+        local += (hi >= (uint32_t)mh) ? hi : 0u;
+      }
+    } else if (threadIdx.x == 0) local = nHits;
+    if (local) atomicAdd(&smTotal, local);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      smBase = atomicAdd(cursor, (unsigned long long)smTotal); keptPerRead[r] = (int32_t)smTotal;
+      atomicAdd(cursor + 1, (unsigned long long)nHits);
+      if (smBase + smTotal > hitsCap) { smSkip = 1; cursor[2] = 1ull; }
+    }
+    __syncthreads();
+    if (smTotal != 0 && !smSkip) {
+      // ---- pass 1: the (start, count) pairs come back from probeOut
+      running = 0;
+      for (int64_t c0 = q0; c0 < q1; c0 += PF_CHUNK) {
+        const int32_t nchunk = (int32_t)((q1 - c0) < PF_CHUNK ? (q1 - c0) : PF_CHUNK);
+        for (int32_t i = threadIdx.x; i < nchunk; i += blockDim.x) { const uint2 pc = probeOut[c0 + i]; pStart[i] = pc.x; pCnt[i] = pc.y; }
+        __syncthreads();
+        const uint32_t tot = chunk_bases(nchunk);
+        walk(1, nchunk);
+        running += tot;
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+}
+#endif
+
 // computeL1CandidateRegions (computeMap.hpp:346-386), one item per sorted hit:
 //   hit i opens a candidate iff hits i and i+minimumHits-1 lie on the same contig less than a read length apart;
 //   consecutive such candidates are merged while prev.end >= start (ends are non-decreasing, so "prev" is simply
@@ -1513,6 +1710,7 @@ struct Mapper {
   // window-length search), K5b 12.7 -> 17.1 ms (a second state build per item, and in a tile of 32 lanes the slowest lane --
   // a candidate that skips nothing -- still sets the tile's time).  Kept as the starting point for a two-kernel version.
   DevBuf<uint32_t> grpSum; bool sweepSkip = false;
+  DevBuf<uint2> probeOut;      // (CSR start, count) of every probe of the batch: l1_probe_filter_kernel's spill between its two passes
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
   Mapper(Runtime& r, Prims& p, Sketcher& s) : rt(r), pr(p), sk(s) {
@@ -1706,6 +1904,45 @@ struct Mapper {
     HitDecode dec{lay};
     {
       StageTimer t(rt, &st.ms[2]);
+      readHitOff.ensure((size_t)n_reads + 2);
+      bool fusedDone = false;
+#ifndef MM_HOST_EMU
+      {
+        // K4 in one kernel (l1_probe_filter_kernel) whenever the 2-byte contig ids exist; MM_L1_FUSED=0 = the two-kernel route below
+        static const bool fusedOff = [] { const char* e = getenv("MM_L1_FUSED"); return e && atoi(e) == 0; }();
+        const char* lf = getenv("MM_L1_FILTER"); const bool legacy = lf && !strcmp(lf, "legacy");
+        if (!fusedOff && !legacy && ix.hasSeq16 && n_q > 0 && n_reads > 0 && ix.n < ((int64_t)1 << 32)) {
+          uint32_t binsN = 64; while (binsN < (uint32_t)ix.n_contigs && binsN < 32768u) binsN <<= 1;
+          static int cacheCap = 0;
+          if (!cacheCap) { const char* e = getenv("MM_L1_CACHE"); cacheCap = e ? atoi(e) : 12288; if (cacheCap < 0 || cacheCap > 14336) cacheCap = 12288; cacheCap &= ~7; }
+          const size_t smem = (size_t)binsN * 2 + (size_t)cacheCap * 2 + (size_t)(3 * PF_CHUNK + 8) * 4;
+          if (rt.first((const void*)l1_probe_filter_kernel)) MM_CUDA(cudaFuncSetAttribute(l1_probe_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+          int perSm = (int)((220 * 1024) / (smem + 2048)); if (perSm > 8) perSm = 8; if (perSm < 1) perSm = 1;
+          const int grid = n_reads < rt.sm_count * perSm ? n_reads : rt.sm_count * perSm;
+          probeOut.ensure((size_t)n_q + 8); keptPerRead.ensure((size_t)n_reads + 2); scal.ensure(4);
+          if (hits.cap < (size_t)n_q + 1) hits.ensure((size_t)n_q + 1);          // first guess: one survivor per sketch element; grow-only
+          unsigned long long hs[3] = {0, 0, 0};
+          for (int attempt = 0; attempt < 2; attempt++) {
+            dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 3);
+            l1_probe_filter_kernel<<<grid, 256, smem, rt.stream>>>(ix.table.p, ix.tableMask, ix.freqThreshold, qHash.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p,
+                                                                   ix.posKey.p, lay, n_reads, binsN - 1, scal.p, hits.p, (unsigned long long)hits.cap, keptPerRead.p,
+                                                                   (uint32_t)cacheCap, probeOut.p);
+            MM_CUDA(cudaGetLastError());
+            rt.launches++;
+            d2h(rt, hs, scal.p, sizeof(hs));
+            if (!hs[2]) break;
+            hits.ensure((size_t)hs[0] + 1);                                        // the survivors did not fit: now they do
+          }
+          if (hs[2]) throw Error(-12, "l1_probe_filter_kernel: survivor buffer overflow after growing it");
+          n_hits = (int64_t)hs[0]; n_hits_all = (int64_t)hs[1];
+          dev_memset(rt, keptPerRead.p + n_reads, 0, sizeof(int32_t));
+          pr.exclusive_sum<int32_t, int64_t>(keptPerRead.p, readHitOff.p, (int64_t)n_reads + 1);
+          hits2.ensure((size_t)n_hits + 1);
+          fusedDone = true;
+        }
+      }
+#endif
+      if (!fusedDone) {
       hitCnt.ensure((size_t)n_q + 2); hitStart.ensure((size_t)n_q + 2); hitOff.ensure((size_t)n_q + 2);
 #ifndef MM_HOST_EMU
       if (n_q > 0) {
@@ -1721,7 +1958,6 @@ struct Mapper {
 #endif
       pr.exclusive_sum<int32_t, int64_t>(hitCnt.p, hitOff.p, n_q + 1);
       d2h(rt, &n_hits, hitOff.p + n_q, sizeof(int64_t));
-      readHitOff.ensure((size_t)n_reads + 2);
       n_hits_all = n_hits;
 #ifndef MM_HOST_EMU
       if (n_hits > 0 && n_reads > 0) {
@@ -1761,6 +1997,7 @@ struct Mapper {
         foreach(rt, n_q, GatherHitsFn{hitCnt.p, hitStart.p, hitOff.p, qRead.p, ix.posKey.p, hits.p, lay});
         foreach(rt, (int64_t)n_reads + 1, ReadHitOffFn{qOff.p, hitOff.p, readHitOff.p});
       }
+      }   // !fusedDone
     }
     {
       StageTimer t(rt, &st.ms[3]);
