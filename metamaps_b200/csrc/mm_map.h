@@ -112,14 +112,25 @@ struct K3Block {
 template <int ITEMS>
 __global__ void __launch_bounds__(256) read_sketch_block_kernel(const uint32_t* hash, const uint32_t* ws, const int64_t* seqOff, int32_t n_reads, int32_t nLo,
                                                                 int32_t nHi, uint32_t* tHash, uint8_t* tStrand, int32_t* sOf, unsigned long long* ambCount,
-                                                                int32_t* ambList, int64_t ambCap) {
+                                                                int32_t* ambList, int64_t ambCap, unsigned long long* readCursor) {
   typedef K3Block<ITEMS> B;
   typedef cub::BlockScan<int32_t, 256> Scan;
   extern __shared__ __align__(16) unsigned char dyn[];
   typename B::Temp& tmp = *reinterpret_cast<typename B::Temp*>(dyn);
   __shared__ typename Scan::TempStorage scanTmp;
   __shared__ uint32_t lastKey[256], lastVal[256];
-  for (int32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+  __shared__ int smR0;
+  // reads are handed out eight at a time (readCursor): the reads of one size class are scattered over the batch and a static
+  // stride leaves some CTAs with several of the long ones
+  for (int32_t rr = 0;; rr++) {
+    if ((rr & 7) == 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) smR0 = (int)atomicAdd(readCursor, 8ull);
+      __syncthreads();
+    }
+    const int32_t r = smR0 + (rr & 7);
+    if (smR0 >= n_reads) break;
+    if (r >= n_reads) continue;
     const int64_t b = seqOff[r]; const int32_t n = (int32_t)(seqOff[r + 1] - b);
     if (n <= nLo || n > nHi) continue;
     uint32_t keys[ITEMS], vals[ITEMS];
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(256) l1_filter_gather16_kernel(const int32_t* 
 // pairs are spilled to `probeOut` for pass 2 (written and re-read by the same CTA a few microseconds apart: L2).
 // Survivors are appended at a global cursor; if the output buffer is too small the kernel still counts (cursor[0] = survivors
 // needed, cursor[2] = 1) and the host re-runs it with a larger one.  cursor[1] += all seed hits (the H of SURVEY 8d).
-static const int PF_CHUNK = 1024;
+template <int PF_CHUNK>
 __global__ void __launch_bounds__(256) l1_probe_filter_kernel(const Slot* table, uint32_t mask, int32_t freqThreshold, const uint32_t* qHash, const int64_t* qOff,
                                                               const int32_t* sOf, const int32_t* minHitsTab, const uint16_t* posSeq16, const uint64_t* posKey,
                                                               HitKeyLayout lay, int32_t n_reads, uint32_t binMask, unsigned long long* cursor, uint64_t* hitsOut,
@@ -524,7 +535,13 @@ __global__ void __launch_bounds__(256) l1_probe_filter_kernel(const Slot* table,
   if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
   uint32_t phase = 0;
-  for (int32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+  __shared__ int smRead;
+  for (;;) {                                     // reads are handed out one at a time (cursor[3]): their hit counts differ 30-fold
+    __syncthreads();
+    if (threadIdx.x == 0) smRead = (int)atomicAdd(cursor + 3, 1ull);
+    __syncthreads();
+    const int32_t r = smRead;
+    if (r >= n_reads) break;
     const int32_t s = sOf[r];
     const int64_t q0 = qOff[r], q1 = qOff[r + 1];
     if (s == 0 || q1 <= q0) { if (threadIdx.x == 0) keptPerRead[r] = 0; continue; }
@@ -1778,13 +1795,13 @@ struct Mapper {
       StageTimer t(rt, &st.ms[1]);
       bool blockPath = false;
       unsigned long long na = 0; int32_t maxS = 0;
-      ambig.ensure((size_t)n_reads + 1); ambigList.ensure(4096); scal.ensure(4);
+      ambig.ensure((size_t)n_reads + 1); ambigList.ensure(4096); scal.ensure(16);
       key.ensure((size_t)nm + 1);                     // scratch of the std::sort replay
 #ifndef MM_HOST_EMU
       if (!getenv("MM_K3_GLOBAL") && nm > 0) {
         // per-read block sort (read_sketch_block_kernel); scal[0] = ambiguous reads, [1] = max sketch, [2] = oversize reads, [3] = n_q
         ws2.ensure((size_t)nm + 1); tStrand.ensure((size_t)nm + 1);
-        dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);
+        dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 12);             // [8..10] = the read cursors of the three size classes
         if (rt.first((const void*)read_sketch_block_kernel<24>))
           MM_CUDA(cudaFuncSetAttribute(read_sketch_block_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Block<24>::Temp)));
         int ambCap = (int)ambigList.cap;
@@ -1795,12 +1812,12 @@ struct Mapper {
         cudaStream_t s2 = fork ? rt.side : rt.stream;
         if (fork) { MM_CUDA(cudaEventRecord(evFork(), rt.stream)); MM_CUDA(cudaStreamWaitEvent(s2, evFork(), 0)); }
         read_sketch_block_kernel<24><<<grid, 256, sizeof(K3Block<24>::Temp), s2>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 2048, 6144, ws2.p, tStrand.p,
-                                                                                   sOf.p, scal.p, ambigList.p, ambCap);
+                                                                                   sOf.p, scal.p, ambigList.p, ambCap, scal.p + 8);
         read_sketch_block_kernel<8><<<grid, 256, sizeof(K3Block<8>::Temp), s2>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 1024, 2048, ws2.p, tStrand.p, sOf.p,
-                                                                                 scal.p, ambigList.p, ambCap);
+                                                                                 scal.p, ambigList.p, ambCap, scal.p + 9);
         if (fork) MM_CUDA(cudaEventRecord(evJoin(), s2));
         read_sketch_block_kernel<4><<<grid, 256, sizeof(K3Block<4>::Temp), rt.stream>>>(rs.hash.p, rs.ws.p, rs.seqOff.p, n_reads, 0, 1024, ws2.p, tStrand.p, sOf.p,
-                                                                                        scal.p, ambigList.p, ambCap);
+                                                                                        scal.p, ambigList.p, ambCap, scal.p + 10);
         if (fork) MM_CUDA(cudaStreamWaitEvent(rt.stream, evJoin(), 0));
         MM_CUDA(cudaGetLastError());
         rt.launches += 3;
@@ -1913,20 +1930,30 @@ struct Mapper {
         const char* lf = getenv("MM_L1_FILTER"); const bool legacy = lf && !strcmp(lf, "legacy");
         if (!fusedOff && !legacy && ix.hasSeq16 && n_q > 0 && n_reads > 0 && ix.n < ((int64_t)1 << 32)) {
           uint32_t binsN = 64; while (binsN < (uint32_t)ix.n_contigs && binsN < 32768u) binsN <<= 1;
-          static int cacheCap = 0;
-          if (!cacheCap) { const char* e = getenv("MM_L1_CACHE"); cacheCap = e ? atoi(e) : 12288; if (cacheCap < 0 || cacheCap > 14336) cacheCap = 12288; cacheCap &= ~7; }
-          const size_t smem = (size_t)binsN * 2 + (size_t)cacheCap * 2 + (size_t)(3 * PF_CHUNK + 8) * 4;
-          if (rt.first((const void*)l1_probe_filter_kernel)) MM_CUDA(cudaFuncSetAttribute(l1_probe_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+          static int cacheCap = 0;        // contig ids cached between the passes: 8192 of the ~7000 hits of a read (12288: one CTA fewer per SM, 10.9 ms; 4096: 10.8; 8192: 8.6)
+          if (!cacheCap) { const char* e = getenv("MM_L1_CACHE"); cacheCap = e ? atoi(e) : 8192; if (cacheCap < 0 || cacheCap > 14336) cacheCap = 8192; cacheCap &= ~7; }
+          static const int pfChunk = [] { const char* e = getenv("MM_L1_CHUNK"); return (e && atoi(e) == 1024) ? 1024 : 512; }();
+          const size_t smem = (size_t)binsN * 2 + (size_t)cacheCap * 2 + (size_t)(3 * pfChunk + 8) * 4;
+          if (rt.first((const void*)l1_probe_filter_kernel<512>)) {
+            MM_CUDA(cudaFuncSetAttribute(l1_probe_filter_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            MM_CUDA(cudaFuncSetAttribute(l1_probe_filter_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+          }
           int perSm = (int)((220 * 1024) / (smem + 2048)); if (perSm > 8) perSm = 8; if (perSm < 1) perSm = 1;
+          if (const char* e = getenv("MM_L1_CTAS")) { int v = atoi(e); if (v >= 1 && v <= perSm) perSm = v; }
           const int grid = n_reads < rt.sm_count * perSm ? n_reads : rt.sm_count * perSm;
           probeOut.ensure((size_t)n_q + 8); keptPerRead.ensure((size_t)n_reads + 2); scal.ensure(4);
           if (hits.cap < (size_t)n_q + 1) hits.ensure((size_t)n_q + 1);          // first guess: one survivor per sketch element; grow-only
           unsigned long long hs[3] = {0, 0, 0};
           for (int attempt = 0; attempt < 2; attempt++) {
-            dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 3);
-            l1_probe_filter_kernel<<<grid, 256, smem, rt.stream>>>(ix.table.p, ix.tableMask, ix.freqThreshold, qHash.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p,
-                                                                   ix.posKey.p, lay, n_reads, binsN - 1, scal.p, hits.p, (unsigned long long)hits.cap, keptPerRead.p,
-                                                                   (uint32_t)cacheCap, probeOut.p);
+            dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);
+            if (pfChunk == 512)
+              l1_probe_filter_kernel<512><<<grid, 256, smem, rt.stream>>>(ix.table.p, ix.tableMask, ix.freqThreshold, qHash.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p,
+                                                                          ix.posKey.p, lay, n_reads, binsN - 1, scal.p, hits.p, (unsigned long long)hits.cap,
+                                                                          keptPerRead.p, (uint32_t)cacheCap, probeOut.p);
+            else
+              l1_probe_filter_kernel<1024><<<grid, 256, smem, rt.stream>>>(ix.table.p, ix.tableMask, ix.freqThreshold, qHash.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p,
+                                                                           ix.posKey.p, lay, n_reads, binsN - 1, scal.p, hits.p, (unsigned long long)hits.cap,
+                                                                           keptPerRead.p, (uint32_t)cacheCap, probeOut.p);
             MM_CUDA(cudaGetLastError());
             rt.launches++;
             d2h(rt, hs, scal.p, sizeof(hs));
