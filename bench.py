@@ -473,7 +473,7 @@ def main():
         "K1 stage (pack + sketch + compaction)": {"ms": ms["sketch_ms"], "bytes": 1.25 * ms["bases"] + 8 * ms["read_minimizers"]},
         "K3 read sketch": {"ms": ms["read_sketch_ms"], "bytes": 2 * 8 * ms["read_minimizers"]},
         "K4 L1 (probe + filter + sort + loci)": {"ms": ms["l1_probe_ms"] + ms["l1_sort_ms"] + ms["l1_candidates_ms"], "bytes": 16 * s_tot + 8 * H + 12 * C_},
-        "K5 L2 (setup + classify + sweep + strand)": {"ms": ms["l2_setup_ms"] + ms["l2_classify_ms"] + ms["l2_sweep_ms"] + ms["l2_strand_ms"], "bytes": k5_bytes},
+        "K5 L2 (setup + classify + prune + sweep + strand)": {"ms": ms["l2_setup_ms"] + ms["l2_classify_ms"] + ms["l2_prune_ms"] + ms["l2_sweep_ms"] + ms["l2_strand_ms"], "bytes": k5_bytes},
         "K5a l2_classify_smem_kernel": {"ms": ms["l2_classify_ms"], "bytes": 8 * span},
         "K5b l2_sweep_band_kernel": {"ms": ms["sweep_kernel_ms"], "bytes": k5_bytes},
         "K5c l2_strand_warp_kernel": {"ms": ms["l2_strand_ms"], "bytes": 8 * span / 2.8},
@@ -488,7 +488,7 @@ def main():
     dom_ms, dom_bytes = table[dom]["ms"], table[dom]["bytes"]
     achieved = table[dom]["GBps"]
     step_bytes = sum(table[k_]["bytes"] for k_ in ("K1 stage (pack + sketch + compaction)", "K3 read sketch", "K4 L1 (probe + filter + sort + loci)",
-                                                    "K5 L2 (setup + classify + sweep + strand)", "K6-K8 classify stage (identity, mapq, nLoc, EM)"))
+                                                    "K5 L2 (setup + classify + prune + sweep + strand)", "K6-K8 classify stage (identity, mapq, nLoc, EM)"))
     detail = {"reads_per_gpu": wl["n_reads"], "db_gbp": n_contigs * wl["contig_len"] / 1e9,
               "parallelism": (f"index sharded by contig range x{world}, every rank maps all {world}x{wl['n_reads']} reads, mappings all-gathered on the device"
                               if by_contigs else f"reads sharded x{world}, index replicated"),
@@ -496,6 +496,7 @@ def main():
               "mappings_per_step": int(out["summary"]["n_mappings"]), "candidates_per_step": int(out["summary"]["n_candidates"]),
               "em_iters": rounds, "identity_fixups": int(cs["n_identity_fixups"]), "smem_swept": ms["smem_swept"], "ambiguous_reads": ms["ambiguous_reads"],
               "span_elems": span, "hits": H, "hits_kept": ms["hits_kept"], "sketch_elems": s_tot, "sweep_items": ms["sweep_items"],
+              "window_starts": ms["window_starts"], "window_starts_swept": ms["window_starts_swept"],
               "stage_ms": {k_: ms[k_] for k_ in ms if k_.endswith("_ms")}, "classify_ms": cs["classify_ms"], "em_ms": cs["em_ms"],
               "kernel_ms_per_step": gpu_ms / args.steps, "step_algorithmic_GB": step_bytes / 1e9,
               "step_algorithmic_frac_of_hbm": step_bytes / (wall / args.steps) / 1e9 / peak,

@@ -23,6 +23,7 @@
 
 namespace mm {
 #ifdef MM_HOST_EMU
+static long long g_emu_rebuild_calls = 0, g_emu_rebuild_elems = 0;
 static long long g_emu_sweep_iters = 0;      // test hook: events applied by the banded sweep (how much the window skipping saves)
 #endif
 
@@ -771,11 +772,16 @@ struct LocusWriteFn {
   const uint64_t* hits; const int64_t* flagged; const int32_t* sOf; const int32_t* readLen; const int32_t* minHitsTab; HitDecode dec;
   const int32_t* head; const int64_t* lidx; int64_t n;
   int32_t* cRead; int32_t* cSeq; int32_t* cStart; int32_t* cEnd; int32_t* candCnt;
+  int64_t* cHitLo; int64_t* cHitHi;                            // the candidate's L1 hits are hits[cHitLo, cHitHi) (K5's prune pass estimates matches from their number)
   MM_HD void operator()(int64_t f) const {
     int32_t r, sq, st, en; hit_candidate(hits, sOf, readLen, minHitsTab, dec, ldg(flagged + f), &r, &sq, &st, &en);
     int64_t l = ldg(lidx + f) + (ldg(head + f) ? 0 : -1);      // lidx = exclusive scan of head
-    if (ldg(head + f)) { cRead[l] = r; cSeq[l] = sq; cStart[l] = st; atomic_add(candCnt + r, 1); }
-    if (f + 1 == n || ldg(head + f + 1)) cEnd[l] = en;          // last flagged hit of the group carries the largest end
+    if (ldg(head + f)) { cRead[l] = r; cSeq[l] = sq; cStart[l] = st; cHitLo[l] = ldg(flagged + f); atomic_add(candCnt + r, 1); }
+    if (f + 1 == n || ldg(head + f + 1)) {                      // last flagged hit of the group carries the largest end
+      cEnd[l] = en;
+      int32_t mh = ldg(minHitsTab + ldg(sOf + r)); if (mh < 1) mh = 1;
+      cHitHi[l] = ldg(flagged + f) + mh;
+    }
   }
 };
 
@@ -789,8 +795,10 @@ struct L2SetupFn {          // computeMap.hpp:465-480
   const uint32_t* miWs; const int64_t* contigStart; const int32_t* cRead; const int32_t* cSeq; const int32_t* cStart; const int32_t* cEnd;
   const int32_t* readLen; const int32_t* sOf; int k, w;
   int64_t* beg0; int64_t* fe; int64_t* le; int32_t* spanN; int64_t n;
+  const int64_t* cHitLo; const int64_t* cHitHi; int32_t* cHits;
   MM_HD void operator()(int64_t c) const {
     if (c >= n) { spanN[c] = 0; return; }
+    { const int64_t nh = ldg(cHitHi + c) - ldg(cHitLo + c); cHits[c] = nh < 0 ? 0 : nh > 0x3fffffff ? 0x3fffffff : (int32_t)nh; }
     int32_t r = ldg(cRead + c), sq = ldg(cSeq + c); int32_t len = ldg(readLen + r);
     int64_t b = search_index(miWs, contigStart, sq, ldg(cStart + c));
     int32_t cmw = len - (w - 1) - (k - 1);
@@ -836,6 +844,121 @@ MM_HD uint32_t dup_event_flags(const uint32_t* miWs, const uint2* dupRB, const u
   return f;
 }
 
+// ---------------------------------------------------------------------------------------------- K5 prune
+// Which window starts can hold the optimum?  computeL2MappedRegions keeps the FIRST window with the maximal shared count and the
+// LAST one that ties with it (computeMap.hpp:510-533), so a window start whose windows cannot reach the count T of some window
+// the loop does evaluate need not be visited at all.  Bounds from counts alone, with the read sketch q_1 < ... < q_s, F(i) =
+// i + #{distinct W-only hashes below q_i} and istar = max{i : F(i) <= s} (see "L2 restated" in DESIGN.md):
+//   lower: if i + (W-only ELEMENTS with gap <= i) <= s then istar >= i, and shared >= the window's non-duplicated matches of rank <= i;
+//   upper: if i + (non-duplicated W-only elements with gap < i) > s then istar < i, and shared <= the window's matches of rank < i
+//          (without the premise: <= all its matches).
+// The ranks i come from where istar is expected (prune_thresholds: the L1 hit count of the candidate estimates the matches of its
+// best window); exactness does not depend on them -- a premise that fails leaves the trivial bound.  K5a counts the seven
+// indicators per group of 32 consecutive span elements while it classifies them; prefix sums over the groups give every window's
+// counts up to a group at either end (rounded to the safe side).  The lower bound is taken on the first window of every group of
+// window starts (an evaluated window: its end lies inside the span), the upper bound on the union of a group's windows; the
+// sweep (K5b) covers the hull of the groups whose upper bound reaches the best lower bound.
+static const int PR_GMAX = 256;            // groups per candidate the prune pass takes (8192 span elements); longer spans are swept whole
+static const int PR_NS = 7;                // series: see PruneView
+struct PruneThr { int32_t i0, i1, i1b; };  // upper-bound rank; lower-bound ranks (i1 from the estimate, i1b < i1 holds whatever matches)
+MM_HD int32_t prune_istar_est(int32_t s, int32_t win, int32_t m) {
+  if (m < 0) m = 0;
+  if (m > win) m = win;
+  const int64_t e = ((int64_t)s * s) / ((int64_t)s + (win - m) + 1);      // F(i) ~ i (1 + (win - m) / s) = s
+  return (int32_t)e;
+}
+MM_HD PruneThr prune_thresholds(int32_t s, int32_t win, int32_t mest) {
+  PruneThr t;
+  const int32_t e0 = prune_istar_est(s, win, 0), e1 = prune_istar_est(s, win, mest);
+  // spread of istar around the estimate: a binomial count of W-only hashes below q_istar, divided by the slope of F; plus what
+  // the rounding of the window's ends to groups of 32 elements can move
+  const float p = s > 0 ? (float)e1 / (float)s : 0.f, nw = (float)(win - (mest < win ? mest : win));
+  const float sd = sqrtf(nw * p * (1.f - p) + 1.f) / (1.f + nw / (float)(s > 0 ? s : 1));
+  // measured on config-2-like data (emulation): 2 sd + 24 above / 2 sd - 4 below sweeps 19 % of the window starts; 3 sd + 20 both ways 23 %
+  const int32_t m2 = (int32_t)(2.f * sd);
+  t.i0 = e1 + m2 + 24; t.i1 = e1 - m2 + 4; t.i1b = e0 - m2 - 12;
+  if (t.i1b > t.i1) t.i1b = t.i1;
+  return t;
+}
+// per-group indicator counts, 6 bits each (0..32): word 0 = A | B << 6 | C << 12 | D << 18 | M << 24, word 1 = C2 | D2 << 6 with
+//   A  non-duplicated W-only elements with gap < i0        B  matches with rank < i0          M  all matches
+//   C  W-only elements with gap <= i1                      D  non-duplicated matches with rank <= i1      (C2, D2: the same for i1b)
+// (W-only: not in the read sketch and not in gap s, which SlideMapper never counts; duplicated: CODE_DUP)
+MM_HD void prune_count(uint32_t code, int32_t s, const PruneThr& th, uint32_t& w0, uint32_t& w1) {
+  const bool isM = (code & CODE_MATCH) != 0, dup = (code & CODE_DUP) != 0;
+  const int32_t idx = (int32_t)(code & CODE_IDX);
+  const bool isW = !isM && idx < s;
+  if (isW && !dup && idx < th.i0) w0 += 1u;
+  if (isM && idx < th.i0) w0 += 1u << 6;
+  if (isW && idx <= th.i1) w0 += 1u << 12;
+  if (isM && !dup && idx <= th.i1) w0 += 1u << 18;
+  if (isM) w0 += 1u << 24;
+  if (isW && idx <= th.i1b) w1 += 1u;
+  if (isM && !dup && idx <= th.i1b) w1 += 1u << 6;
+}
+MM_HD uint32_t prune_series_of(uint32_t w0, uint32_t w1, int q) { return q < 5 ? (w0 >> (6 * q)) & 63u : (w1 >> (6 * (q - 5))) & 63u; }
+// P[q * ld + g] = sum of series q over groups [0, g); H[g] = the last group whose first element lies at or below pos[32 g] + cmw, so
+// that the first element E(32 g) at or beyond that position (the end of the first window that starts at 32 g) has 32 H <= E <= 32 (H + 1)
+struct PruneView {
+  const uint16_t* P; int32_t ld; const uint16_t* H; int32_t nG, s; PruneThr th;
+  MM_HD int32_t rng(int q, int32_t ga, int32_t gb) const { return gb > ga ? (int32_t)P[q * ld + gb] - (int32_t)P[q * ld + ga] : 0; }
+  // lower bound of the shared count of the window [32 g, E(32 g)): it lies inside groups [g, h] and contains groups [g, h)
+  MM_HD int32_t lb(int32_t g) const {
+    const int32_t h = H[g];
+    if (h + 1 >= nG) return 0;                               // E(32 g) may be the end of the span: that window is not evaluated
+    if (th.i1 >= 0 && th.i1 <= s && th.i1 + rng(2, g, h + 1) <= s) return rng(3, g, h);
+    if (th.i1b >= 0 && th.i1b <= s && th.i1b + rng(5, g, h + 1) <= s) return rng(6, g, h);
+    return 0;
+  }
+  // upper bound over every window that starts in group g: they contain groups [g + 1, H[g]) and lie inside groups [g, H[g + 1] + 1)
+  MM_HD int32_t ub(int32_t g) const {
+    const int32_t hLo = H[g];
+    int32_t hUp = nG;
+    if (g + 1 < nG) { hUp = (int32_t)H[g + 1] + 1; if (hUp > nG) hUp = nG; }
+    if (th.i0 + rng(0, g + 1, hLo) > s) return rng(1, g, hUp);
+    return rng(4, g, hUp);
+  }
+};
+MM_HD int32_t prune_window_group(const uint32_t* pos, int32_t nG, int32_t g, int32_t cmw) {
+  const uint32_t target = pos[g] + (uint32_t)cmw;
+  int32_t lo = g, hi = nG - 1;
+  while (lo < hi) { const int32_t m = (lo + hi + 1) >> 1; if (pos[m] <= target) lo = m; else hi = m - 1; }
+  return lo;
+}
+#ifdef MM_HOST_EMU
+// serial form of what the device's K5a does besides classifying: the window starts [swB0, swB1) of a candidate worth sweeping
+struct L2PruneFn {
+  const uint2* ev; const int64_t* evOff; int64_t evBase; int64_t cand0;
+  const int64_t* beg0; const int64_t* fe; const int32_t* cRead; const int32_t* sOf; const int32_t* readLen; const int32_t* cHits; int k, w;
+  int32_t* swB0; int32_t* swB1;                              // indexed by the candidate's number within the pass
+  void operator()(int64_t ci) const {
+    const int64_t c = cand0 + ci;
+    const int32_t n = (int32_t)(evOff[c + 1] - evOff[c]), nG = (n + 31) >> 5;
+    swB0[ci] = 0; swB1[ci] = 0x7fffffff;
+    if (nG < 1 || nG > PR_GMAX) return;
+    const int32_t r = cRead[c], s = sOf[r], cmw = readLen[r] - (w - 1) - (k - 1);
+    const PruneThr th = prune_thresholds(s, (int32_t)(fe[c] - beg0[c]), cHits ? cHits[c] : 0);
+    const uint2* e = ev + (evOff[c] - evBase);
+    const int32_t ld = nG + 1;
+    std::vector<uint16_t> P((size_t)PR_NS * ld, 0), H((size_t)nG); std::vector<uint32_t> pos((size_t)nG);
+    for (int32_t g = 0; g < nG; g++) {
+      uint32_t w0 = 0, w1 = 0;
+      for (int32_t j = 32 * g; j < n && j < 32 * g + 32; j++) prune_count(e[j].x, s, th, w0, w1);
+      pos[g] = e[32 * g].y >> 1;
+      for (int q = 0; q < PR_NS; q++) P[(size_t)q * ld + g + 1] = (uint16_t)(P[(size_t)q * ld + g] + prune_series_of(w0, w1, q));
+    }
+    for (int32_t g = 0; g < nG; g++) H[g] = (uint16_t)prune_window_group(pos.data(), nG, g, cmw);
+    const PruneView v{P.data(), ld, H.data(), nG, s, th};
+    int32_t T = 0;
+    for (int32_t g = 0; g < nG; g++) { const int32_t l = v.lb(g); if (l > T) T = l; }
+    if (T <= 0) return;
+    int32_t gF = nG, gL = -1;
+    for (int32_t g = 0; g < nG; g++) if (v.ub(g) >= T) { if (g < gF) gF = g; if (g > gL) gL = g; }
+    if (gL >= gF) { swB0[ci] = 32 * gF; swB1[ci] = 32 * (gL + 1); }
+  }
+};
+#endif
+
 // phase A: one item per reference minimizer of a candidate span
 struct L2ClassifyFn {
   const uint32_t* miHash; const uint32_t* miWs; const uint32_t* dupBits;
@@ -843,18 +966,9 @@ struct L2ClassifyFn {
   const int64_t* beg0; const int32_t* cRead; const uint32_t* qHash; const int64_t* qOff; const int32_t* sOf;
   uint2* ev;
   const int64_t* fe; const int64_t* le; const int32_t* readLen; const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; int k, w;
-  // Per group of 32 consecutive span elements of a candidate (K5b's window skipping, see l2_sweep_band): low 16 bits = how many
-  // of them are in the read sketch, high 16 bits = element count of the window that starts at the group's first element
-  // (clipped).  Candidate c's groups start at grp_base(c); may be null.
-  uint32_t* grp;
-  MM_HD int64_t grp_base(int64_t c) const { return ((ldg(evOff + c) - evBase) >> 5) + (c - cand0); }
-  MM_HD uint32_t window_len(int64_t j, int64_t last, int32_t cmw) const {       // elements of [j, first element with wpos >= wpos[j] + cmw)
-    const int64_t lim = (int64_t)(ldg(miWs + j) >> 1) + cmw;
-    int64_t lo = j, hi = last;
-    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if ((int64_t)(ldg(miWs + m) >> 1) < lim) lo = m + 1; else hi = m; }
-    const int64_t n = lo - j;
-    return n > 65535 ? 65535u : (uint32_t)n;
-  }
+  // the device kernel also counts the prune pass's indicators and decides the window starts worth sweeping (swB0 / swB1, indexed by
+  // the candidate's number within the pass; null: no pruning); cHits: L1 hits of the candidate (estimate of its best window's matches)
+  const int32_t* cHits; int32_t* swB0; int32_t* swB1;
   MM_HD void operator()(int64_t t) const {
     int64_t c = cand0 + upper_bound_idx(evOff + cand0, nCand + 1, t + evBase) - 1;
     int64_t j = ldg(beg0 + c) + (t + evBase - ldg(evOff + c));
@@ -867,12 +981,6 @@ struct L2ClassifyFn {
     if ((ldg(dupBits + (j >> 5)) >> (j & 31)) & 1u)
       code |= CODE_DUP | dup_event_flags(miWs, dupRB, dupLinks, n_dup, j, ldg(beg0 + c), ldg(fe + c), ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1));
     ev[t] = make_uint2(code, ldg(miWs + j));
-    if (grp) {                                    // element-wise form of the summaries (the array is zeroed before the pass)
-      const int64_t rel = j - ldg(beg0 + c);
-      uint32_t add = (code & CODE_MATCH) ? 1u : 0u;
-      if ((rel & 31) == 0) add += window_len(j, ldg(le + c), ldg(readLen + r) - (w - 1) - (k - 1)) << 16;
-      if (add) atomic_add(grp + grp_base(c) + (rel >> 5), add);
-    }
   }
 };
 
@@ -882,10 +990,18 @@ struct L2ClassifyFn {
 // on the top 11 hash bits (first sketch rank of every bucket), so the rank search of a reference minimizer is a lookup
 // plus a short binary search inside one bucket instead of log2(s) steps.  Same codes as L2ClassifyFn.
 static const int CLS_BUCKET_BITS = 11, CLS_BUCKETS = 1 << CLS_BUCKET_BITS;
-template <bool GRP>
+// PRUNE: the warp's 32 lanes hold one group of 32 span elements: seven ballots count the prune pass's indicators (prune_count) into
+// shared memory; after the candidate's last element the CTA scans the seven series over the groups, takes the bounds (PruneView) and
+// writes the window starts worth sweeping.  Four barriers per candidate.
+template <bool PRUNE>
 __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, int32_t perCta) {
   extern __shared__ uint32_t smq[];
   __shared__ uint16_t bstart[CLS_BUCKETS + 2];
+  constexpr int GM = PRUNE ? PR_GMAX : 1, LD = GM + 1;
+  __shared__ uint32_t gw0[GM], gw1[GM], gpos[GM];
+  __shared__ uint16_t gP[PR_NS * LD], gH[GM];
+  __shared__ int32_t red[3];                             // best lower bound, first / last surviving group
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int32_t curRead = -1, s = 0;
   const int64_t ciEnd = ((int64_t)blockIdx.x + 1) * perCta < a.nCand ? ((int64_t)blockIdx.x + 1) * perCta : a.nCand;
   for (int64_t ci = (int64_t)blockIdx.x * perCta; ci < ciEnd; ci++) {
@@ -907,6 +1023,10 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
     const int64_t b0 = a.beg0[c];
     const int64_t e0 = a.evOff[c] - a.evBase; const int32_t n = (int32_t)(a.evOff[c + 1] - a.evOff[c]);
     const int64_t fe = a.fe[c], le = a.le[c]; const int32_t cmw = a.readLen[r] - (a.w - 1) - (a.k - 1);
+    const int32_t nG = (n + 31) >> 5;
+    const bool doPrune = PRUNE && nG >= 1 && nG <= PR_GMAX;        // CTA-uniform
+    PruneThr th{0, 0, 0};
+    if (doPrune) th = prune_thresholds(s, (int32_t)(fe - b0), a.cHits ? a.cHits[c] : 0);
     auto rank_code = [&](uint32_t h) -> uint32_t {
       const uint32_t bk = h >> (32 - CLS_BUCKET_BITS);
       int32_t lo = bstart[bk], hi = bstart[bk + 1];
@@ -914,7 +1034,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
       return (lo < s && smq[lo] == h) ? (CODE_MATCH | (uint32_t)(lo + 1)) : (uint32_t)lo;
     };
     // four elements per thread and trip: the twelve global loads are issued before the first search needs one
-    for (int32_t t0 = threadIdx.x; GRP ? ((t0 & ~31) < n) : (t0 < n); t0 += 4 * blockDim.x) {      // GRP: warp-uniform bound, the ballots below need the whole warp
+    for (int32_t t0 = threadIdx.x; PRUNE ? ((t0 & ~31) < n) : (t0 < n); t0 += 4 * blockDim.x) {      // PRUNE: warp-uniform bound, the ballots below need the whole warp
       uint32_t h[4], wsv[4], db[4]; bool on[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
@@ -922,7 +1042,6 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
         const int64_t j = b0 + (on[u] ? t : 0);
         h[u] = __ldg(a.miHash + j); wsv[u] = __ldg(a.miWs + j); db[u] = (__ldg(a.dupBits + (j >> 5)) >> (j & 31)) & 1u;
       }
-      const int64_t gb = GRP ? a.grp_base(c) : 0;
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int32_t t = t0 + u * (int32_t)blockDim.x;
@@ -932,11 +1051,57 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
           if (db[u]) code |= CODE_DUP | dup_event_flags(a.miWs, a.dupRB, a.dupLinks, a.n_dup, b0 + t, b0, fe, le, cmw);
           a.ev[e0 + t] = make_uint2(code, wsv[u]);
         }
-        if (GRP) {                                  // the warp's 32 lanes hold one group: its lane 0 writes the summary (plain store)
-          const unsigned m = __ballot_sync(0xffffffffu, on[u] && (code & CODE_MATCH));
-          if ((threadIdx.x & 31) == 0 && on[u]) a.grp[gb + (t >> 5)] = (uint32_t)__popc(m) | (a.window_len(b0 + t, le, cmw) << 16);
+        if (PRUNE && doPrune && (t & ~31) < n) {         // warp-uniform: t & ~31 is the group's first element
+          const bool isM = on[u] && (code & CODE_MATCH) != 0, dup = (code & CODE_DUP) != 0;
+          const int32_t idx = (int32_t)(code & CODE_IDX);
+          const bool isW = on[u] && !isM && idx < s;
+          const uint32_t cA = (uint32_t)__popc(__ballot_sync(0xffffffffu, isW && !dup && idx < th.i0));
+          const uint32_t cB = (uint32_t)__popc(__ballot_sync(0xffffffffu, isM && idx < th.i0));
+          const uint32_t cC = (uint32_t)__popc(__ballot_sync(0xffffffffu, isW && idx <= th.i1));
+          const uint32_t cD = (uint32_t)__popc(__ballot_sync(0xffffffffu, isM && !dup && idx <= th.i1));
+          const uint32_t cM = (uint32_t)__popc(__ballot_sync(0xffffffffu, isM));
+          const uint32_t cC2 = (uint32_t)__popc(__ballot_sync(0xffffffffu, isW && idx <= th.i1b));
+          const uint32_t cD2 = (uint32_t)__popc(__ballot_sync(0xffffffffu, isM && !dup && idx <= th.i1b));
+          if (lane == 0) { const int32_t g = t >> 5; gw0[g] = cA | (cB << 6) | (cC << 12) | (cD << 18) | (cM << 24); gw1[g] = cC2 | (cD2 << 6); gpos[g] = wsv[u] >> 1; }
         }
       }
+    }
+    if (PRUNE) {
+      int32_t B0 = 0, B1 = 0x7fffffff;
+      if (doPrune) {
+        __syncthreads();                                 // the group counts are complete
+        for (int q = wid; q < PR_NS; q += 4) {           // one warp per series: lane l scans groups [8 l, 8 l + 8), the lane totals are scanned with shuffles
+          uint32_t v[8]; uint32_t tot = 0;
+#pragma unroll
+          for (int j = 0; j < 8; j++) { const int32_t g = 8 * lane + j; v[j] = g < nG ? prune_series_of(gw0[g], gw1[g], q) : 0u; tot += v[j]; v[j] = tot; }
+          uint32_t inc = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+          const uint32_t base = inc - tot;
+          if (lane == 0) gP[q * LD] = 0;
+#pragma unroll
+          for (int j = 0; j < 8; j++) { const int32_t g = 8 * lane + j; if (g < nG) gP[q * LD + g + 1] = (uint16_t)(base + v[j]); }
+        }
+        for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) gH[g] = (uint16_t)prune_window_group(gpos, nG, g, cmw);
+        if (threadIdx.x == 0) { red[0] = 0; red[1] = nG; red[2] = -1; }
+        __syncthreads();
+        const PruneView pv{gP, LD, gH, nG, s, th};
+        int32_t lbv = 0;
+        for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) { const int32_t l = pv.lb(g); lbv = l > lbv ? l : lbv; }
+        lbv = __reduce_max_sync(0xffffffffu, lbv);
+        if (lane == 0 && lbv > 0) atomicMax(&red[0], lbv);
+        __syncthreads();
+        const int32_t T = red[0];
+        if (T > 0) {
+          int32_t gF = nG, gL = -1;
+          for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) if (pv.ub(g) >= T) { gF = g < gF ? g : gF; gL = g > gL ? g : gL; }
+          gF = __reduce_min_sync(0xffffffffu, gF); gL = __reduce_max_sync(0xffffffffu, gL);
+          if (lane == 0 && gL >= 0) { atomicMin(&red[1], gF); atomicMax(&red[2], gL); }
+        }
+        __syncthreads();
+        if (T > 0 && red[2] >= red[1]) { B0 = 32 * red[1]; B1 = 32 * (red[2] + 1); }
+      }
+      if (threadIdx.x == 0) { a.swB0[ci] = B0; a.swB1[ci] = B1; }
     }
   }
 }
@@ -954,7 +1119,6 @@ struct L2SweepArgs {
   const int64_t* beg0; const int64_t* fe; const int64_t* le; const int32_t* cRead; const int32_t* sOf; const int32_t* readLen;
   const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; int k, w;
   int32_t* oShared; int32_t* oPos; int32_t* oValid; int64_t* oOptS; int64_t* oOptE; int32_t* oIstar;
-  const uint32_t* grp;       // K5a's per-32-element summaries (match count | window length << 16), or null: no window skipping
 };
 
 // Branch-free updates: every lane of a warp runs the same instruction stream whatever the event is.  cnt[] has
@@ -1139,6 +1303,9 @@ struct BandSweep {
   // histogram of the gap indices).  Sets `bad` when istar turns out to lie outside the band (only possible when the
   // caller guessed the center).  Event codes are fetched eight at a time so that the loads overlap.
   MM_HD void rebuild(int32_t beg, int32_t end, int32_t center, int32_t bias) {
+#ifdef MM_HOST_EMU
+    g_emu_rebuild_calls++; g_emu_rebuild_elems += (center < 0 ? 2 : 1) * (long long)(end - beg);
+#endif
     bad = false;
     const uint32_t SKIP = (uint32_t)s;                       // "W-only hash in gap s": ignored everywhere
     if (center < 0) {
@@ -1301,8 +1468,9 @@ struct BandSweep {
 // sweeps on its own, and L2BandMergeFn combines them: the optimum is the FIRST window with the maximal count, the
 // reported last position the LAST window with that count (computeMap.hpp:510-533), whichever segments they fall in.
 struct BandPart { int32_t shared, bpos, lpos, optS, optE, istar, any, fail; };
-static const int BAND_SEG_DEFAULT = 4096;   // window starts per segment: 2048 12.9 ms, 3072 12.5, 4096 12.2, 6144 13.2, 8192 15.3 (config 2)
-static const int32_t BAND_LAST_SEG = 1 << 30;
+// window starts per segment.  With the prune pass most items are a few hundred window starts and the longest single item is the kernel's critical
+// path (one lane, ~1000 cycles per event): 256 / 512 / 1024 / 2048 / 4096 = 5.3 / 4.4 / 4.3 / 5.3 / 7.7 ms on config 2 (unpruned: 4096 was best, 12.2 ms)
+static const int BAND_SEG_DEFAULT = 1024;
 
 // one segment; cnt: BW+1 (+3 pad) bytes, mb: BW/32+1 words.  part.fail: the candidate must go through the full-state
 // sweep instead (sketch too large for the band, a gap counter passing 255, a span beyond 65534 elements).
@@ -1315,7 +1483,7 @@ static const int32_t BAND_LAST_SEG = 1 << 30;
 #else
 #define MM_WARP_ANY(x) (x)
 #endif
-template <class Ev, bool SKIP = false>
+template <class Ev>
 MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0, int32_t B1, uint8_t* cnt, uint32_t* mb, int32_t BW, Ev& ev, BandPart& out) {
   out.shared = 0; out.bpos = 0; out.lpos = 0; out.optS = 0; out.optE = 0; out.istar = 0; out.any = 0; out.fail = 0;
   if (!valid) c = a.cand0;                                   // harmless loads; the lane never becomes active
@@ -1342,72 +1510,6 @@ MM_HD void l2_sweep_band(const L2SweepArgs& a, bool valid, int64_t c, int32_t B0
     active = end < last;                                     // else the reference's loop is over before this window is evaluated
   }
   BandSweep<Ev> z{a, e, ev, cnt, mb, BW, b0, s, sh, 0, 0, 0, 0, false, false};
-  // ---- window skipping.  shared(W) <= number of span elements of W whose hash is in the read sketch =: M(W), and every window the
-  // loop evaluates while its first element is b lies inside [b, E(b)), E(b) = first element at or beyond wpos[b] + cmw.  So with
-  // T = the shared count of ANY evaluated window (a lower bound of the optimum), a window start b with M([b, E(b))) < T can
-  // neither be the optimum nor tie with it (computeMap.hpp:510-533 compares with > and ==): it need not be visited.  K5a left, per
-  // group of 32 span elements, the group's match count and E of its first element; per group g of window starts the bound
-  // U(g) = matches in [32 g, E(32 (g+1))) covers all its windows.  T = the window at the middle of the group with the largest U
-  // (one state build); the sweep then runs from the first to the last group with U >= T only.  On a true locus about half of
-  // the span qualifies; where nothing matches T is 0 and everything is swept as before.
-  if (SKIP && active && a.grp) {       // compiled out of the default kernel: the unused path cost 0.7 ms of register pressure
-    const uint32_t* G = a.grp + (((ldg(a.evOff + c) - a.evBase) >> 5) + (c - a.cand0));
-    const int32_t nG = (last + 31) >> 5;
-    const int32_t sEnd = B1 < last ? B1 : last;
-    const int32_t g0 = B0 >> 5, g1 = (sEnd + 31) >> 5;
-    if (g1 - g0 >= 4) {
-      int32_t gMax = g0, uMax = -1;
-      auto scan = [&](int32_t thr, int32_t& gF, int32_t& gL) {     // thr < 0: locate the maximum; else first / last group with U >= thr
-        int32_t hi = g0, S = 0;
-        for (int32_t g = g0; g < g1; g++) {
-          int32_t R = nG;
-          if (g + 1 < nG) { const uint32_t wl = ldg(G + g + 1) >> 16; if (wl != 65535u) { const int32_t r_ = (32 * (g + 1) + (int32_t)wl + 31) >> 5; R = r_ < nG ? r_ : nG; } }
-          if (R < g + 1) R = g + 1;
-          for (; hi < R; hi++) S += (int32_t)(ldg(G + hi) & 0xFFFFu);
-          if (thr < 0) { if (S > uMax) { uMax = S; gMax = g; } }
-          else if (S >= thr) { if (gF < 0) gF = g; gL = g; }
-          S -= (int32_t)(ldg(G + g) & 0xFFFFu);
-        }
-      };
-      int32_t dF = -1, dL = -1;
-      scan(-1, dF, dL);
-      int32_t T = 0;
-      if (uMax > 0) {
-        int32_t bs = 32 * gMax + 16; if (bs < B0) bs = B0; if (bs >= sEnd) bs = sEnd - 1;
-        int32_t es = last;
-        if (bs == 0) es = (int32_t)(ldg(a.fe + c) - b0);
-        else {
-          const int32_t lim = (int32_t)(ldg(&e[bs].y) >> 1) + cmw;
-          int32_t l = bs, h = last;
-          while (l < h) { const int32_t m = (l + h) >> 1; if ((int32_t)(ldg(&e[m].y) >> 1) < lim) l = m + 1; else h = m; }
-          es = l;
-        }
-        if (es < last) {                                          // a window the loop does evaluate
-          z.rebuild(bs, es, (int32_t)(((int64_t)s * s) / (s + (es - bs) + 1)), 0);
-          if (z.bad || z.out_of_band()) z.rebuild(bs, es, -1, 0);
-          if (!(z.fail || z.bad)) T = z.shared;
-          z.fail = false; z.bad = false;                          // the sweep proper builds its own first window below
-        }
-      }
-      if (T > 0) {
-        int32_t gF = -1, gL = -1;
-        scan(T, gF, gL);
-        if (gF >= 0) {
-          if (32 * gF > B0) B0 = 32 * gF;
-          if (32 * (gL + 1) < B1) B1 = 32 * (gL + 1);
-          beg = B0; end = last;
-          if (B0 == 0) end = (int32_t)(ldg(a.fe + c) - b0);
-          else if (B0 < last) {
-            const int32_t lim = (int32_t)(ldg(&e[B0].y) >> 1) + cmw;
-            int32_t l = B0, h = last;
-            while (l < h) { const int32_t m = (l + h) >> 1; if ((int32_t)(ldg(&e[m].y) >> 1) < lim) l = m + 1; else h = m; }
-            end = l;
-          }
-          active = end < last;
-        }
-      }
-    }
-  }
   if (active) {
     // slidemap.insert_ref(sw_beg, sw_end) (computeMap.hpp:488).  With every window minimizer W-only, F(i) ~ i*(1 + nW/s):
     // try the band around that istar first (one scan); if the guess misses, locate istar with the histogram (two scans).
@@ -1498,28 +1600,45 @@ MM_HD int32_t band_state_words(int32_t BW) { return (BW + 4) / 4 + BW / 32 + 1; 
 // work items: a candidate's window start ("beg") runs over [0, span - window) (the loop ends when the window's end reaches the
 // end of the span), cut into segments of `seg`; itemOff = prefix sum of the segment counts over the pass
 MM_HD int32_t band_beg_range(int32_t span, int32_t win) { const int32_t v = span - win; return v > 0 ? v : 0; }
+// the window starts a candidate's items cover: the whole range, or the hull the prune pass left (swB0 / swB1, indexed like nSeg)
+MM_HD void band_clip(const int32_t* swB0, const int32_t* swB1, int64_t ci, int32_t range, int32_t& lo, int32_t& hi, bool& open) {
+  lo = 0; hi = range; open = true;                           // open: the last segment runs to the end of the span (the window may shrink there)
+  if (swB0) {
+    const int32_t b0 = ldg(swB0 + ci), b1 = ldg(swB1 + ci);
+    if (b0 > 0 && b0 < range) lo = b0;
+    if (b1 < range && b1 > lo) { hi = b1; open = false; }
+  }
+}
 struct BandSegCountFn {
   const int32_t* spanN; const int64_t* beg0; const int64_t* fe; int64_t cand0, nCand; int32_t seg; int32_t* nSeg;
+  const int32_t* swB0; const int32_t* swB1; unsigned long long* tot;     // tot[0] += window starts to sweep, tot[1] += window starts in all
   MM_HD void operator()(int64_t ci) const {
     if (ci >= nCand) { nSeg[ci] = 0; return; }
     const int64_t c = cand0 + ci;
     const int32_t range = band_beg_range(ldg(spanN + c), (int32_t)(ldg(fe + c) - ldg(beg0 + c)));
-    const int32_t n = (range + seg - 1) / seg;
+    int32_t lo, hi; bool open;
+    band_clip(swB0, swB1, ci, range, lo, hi, open);
+    const int32_t n = (hi - lo + seg - 1) / seg;
     nSeg[ci] = n < 1 ? 1 : n;
+    if (tot) { atomic_add_u64(tot, (unsigned long long)(hi - lo)); atomic_add_u64(tot + 1, (unsigned long long)range); }
   }
 };
-struct BandItemFn {         // item -> (candidate, segment) + sort key (wide-band class first, then descending work)
+struct BandItemFn {         // item -> candidate, window starts [B0, B1) + sort key (wide-band class first, then descending work)
   const int64_t* itemOff; int64_t nCand; const int32_t* spanN; const int64_t* beg0; const int64_t* fe; int64_t cand0; int32_t seg;
-  uint32_t* key; uint32_t* val; int32_t* itemCand; int32_t* itemSeg;
+  uint32_t* key; uint32_t* val; int32_t* itemCand; int32_t* itemB0; int32_t* itemB1;
   const int32_t* cRead; const int32_t* sOf; int32_t wideFrom; unsigned long long* nWide;
+  const int32_t* swB0; const int32_t* swB1;
   MM_HD void operator()(int64_t i) const {
     const int64_t ci = upper_bound_idx(itemOff, nCand + 1, i) - 1;
     const int32_t sg = (int32_t)(i - ldg(itemOff + ci));
     const int64_t c = cand0 + ci;
-    // the candidate's last segment is open-ended (the window may shrink towards the end of the span)
-    itemCand[i] = (int32_t)ci; itemSeg[i] = sg | ((i + 1 == ldg(itemOff + ci + 1)) ? BAND_LAST_SEG : 0);
     const int32_t win = (int32_t)(ldg(fe + c) - ldg(beg0 + c));
-    int32_t rest = band_beg_range(ldg(spanN + c), win) - sg * seg; if (rest > seg) rest = seg; if (rest < 0) rest = 0;
+    int32_t lo, hi; bool open;
+    band_clip(swB0, swB1, ci, band_beg_range(ldg(spanN + c), win), lo, hi, open);
+    const bool lastSeg = i + 1 == ldg(itemOff + ci + 1);
+    const int32_t B0 = lo + sg * seg;
+    itemCand[i] = (int32_t)ci; itemB0[i] = B0; itemB1[i] = lastSeg ? (open ? 0x7fffffff : hi) : B0 + seg;
+    int32_t rest = hi - B0; if (rest > seg) rest = seg; if (rest < 0) rest = 0;
     // ~2 loop iterations per window start (one delete, one insert), and a rebuild scan of the window (cheaper per element)
     // large sketches drift further than the narrow band tolerates: they run in the wide-band instantiation, sorted first
     const bool wide = ldg(sOf + ldg(cRead + c)) >= wideFrom;
@@ -1552,18 +1671,16 @@ struct L2BandMergeFn {      // candidate ci: combine its segments (in time order
 
 // global-memory band state (host emulation and tests): item i of the pass
 struct L2SweepBandFn {
-  L2SweepArgs a; uint32_t* state; int32_t BW; int32_t seg; const int32_t* itemCand; const int32_t* itemSeg; BandPart* parts;
+  L2SweepArgs a; uint32_t* state; int32_t BW; const int32_t* itemCand; const int32_t* itemB0; const int32_t* itemB1; BandPart* parts;
   MM_HD void operator()(int64_t i) const {
     const int64_t c = a.cand0 + ldg(itemCand + i);
-    const int32_t sgl = ldg(itemSeg + i), sg = sgl & ~BAND_LAST_SEG;
     uint32_t* stp = state + i * band_state_words(BW);
     DirectEv ev{a.ev + (ldg(a.evOff + c) - a.evBase)};
     BandPart p;
 #ifdef MM_BAND_DEBUG
     ::g_band_dbg_cur[0] = ::g_band_dbg_cur[1] = ::g_band_dbg_cur[2] = 0;
 #endif
-    if (a.grp) l2_sweep_band<DirectEv, true>(a, true, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
-    else l2_sweep_band<DirectEv, false>(a, true, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
+    l2_sweep_band<DirectEv>(a, true, c, ldg(itemB0 + i), ldg(itemB1 + i), (uint8_t*)stp, stp + (BW + 4) / 4, BW, ev, p);
 #ifdef MM_BAND_DEBUG
     if (i < 1000000) { ::g_band_dbg_n = i; ::g_band_dbg_it[i] = ::g_band_dbg_cur[0]; ::g_band_dbg_win[i] = ::g_band_dbg_cur[1]; ::g_band_dbg_reb[i] = ::g_band_dbg_cur[2]; }
 #endif
@@ -1609,9 +1726,9 @@ struct RingEv {
 
 // Each warp owns WARP_WORDS of shared memory (32 band states + the rings) and pulls tiles of 32 consecutive work items
 // of `order` (descending work: lanes of a tile run loops of similar length) from a global counter.
-template <int BW, int R, int MINB, bool SKIP = false>
+template <int BW, int R, int MINB>
 __global__ void __launch_bounds__(MINB == 1 ? 512 : 384, MINB) l2_sweep_band_kernel(L2SweepArgs a, const uint32_t* order, int64_t nItems, const int32_t* itemCand,
-                                                               const int32_t* itemSeg, int32_t seg, BandPart* parts, unsigned int* tileCounter) {
+                                                               const int32_t* itemB0, const int32_t* itemB1, BandPart* parts, unsigned int* tileCounter) {
   extern __shared__ __align__(16) uint32_t sm[];
   constexpr int ST = ((BW + 4) / 4 + BW / 32 + 1) | 1;       // odd word count: lanes start on different banks
   constexpr int WARP_WORDS = 2 * R * 32 * 4 + 32 * ST;
@@ -1629,10 +1746,9 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 384, MINB) l2_sweep_band_ker
     const bool valid = t < nItems;
     const int64_t i = valid ? (int64_t)order[t] : 0;
     const int64_t c = a.cand0 + (valid ? itemCand[i] : 0);
-    const int32_t sgl = valid ? itemSeg[i] : 0, sg = sgl & ~BAND_LAST_SEG;
     RingEv<R> ev(a.ev, a.evOff[c] - a.evBase, ring);
     BandPart p;
-    l2_sweep_band<RingEv<R>, SKIP>(a, valid, c, sg * seg, (sgl & BAND_LAST_SEG) ? 0x7fffffff : (sg + 1) * seg, (uint8_t*)my, my + (BW + 4) / 4, BW, ev, p);
+    l2_sweep_band<RingEv<R>>(a, valid, c, valid ? itemB0[i] : 0, valid ? itemB1[i] : 0, (uint8_t*)my, my + (BW + 4) / 4, BW, ev, p);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (valid) parts[i] = p;
     __syncwarp();
@@ -1721,12 +1837,10 @@ struct Mapper {
   std::vector<int32_t> h_effLen;
   MapStats st;
   int sweepBand = 256, sweepRing = 8, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT, sweepWideFrom = 0x7fffffff;   // wide-band class: measured neutral on config 2, off unless MM_SWEEP_WIDE_FROM is set
-  DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemSeg, segCnt; DevBuf<BandPart> bandParts; std::vector<int64_t> hEvSpan;
-  // K5a's per-group summaries for K5b's window skipping.  OFF unless MM_SWEEP_SKIP=1: exact (parity-tested) and it halves the
-  // events on config-2-like data, but measured on config 2 it LOSES: K5a 5.1 -> 14.8 ms (one lane per group runs the
-  // window-length search), K5b 12.7 -> 17.1 ms (a second state build per item, and in a tile of 32 lanes the slowest lane --
-  // a candidate that skips nothing -- still sets the tile's time).  Kept as the starting point for a two-kernel version.
-  DevBuf<uint32_t> grpSum; bool sweepSkip = false;
+  DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemB0, itemB1, segCnt, swB0, swB1, cHits; DevBuf<int64_t> cHitLo, cHitHi; DevBuf<BandPart> bandParts; std::vector<int64_t> hEvSpan;
+  // K5a also bounds every window's shared count and K5b sweeps only the window starts that can hold the optimum (l2 prune, PruneView);
+  // MM_SWEEP_PRUNE=0 sweeps every window start as the reference does
+  bool sweepPrune = true, prunedPass = false;
   DevBuf<uint2> probeOut;      // (CSR start, count) of every probe of the batch: l1_probe_filter_kernel's spill between its two passes
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
@@ -1738,7 +1852,7 @@ struct Mapper {
     if (const char* e = getenv("MM_SWEEP_RING")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) sweepRing = v; }
     if (const char* e = getenv("MM_SWEEP_WIDE_FROM")) { int v = atoi(e); if (v >= 1) sweepWideFrom = v; }
     if (const char* e = getenv("MM_SWEEP_SEG")) { int v = atoi(e); if (v >= 64) sweepSeg = v; }
-    if (const char* e = getenv("MM_SWEEP_SKIP")) sweepSkip = atoi(e) != 0;
+    if (const char* e = getenv("MM_SWEEP_PRUNE")) sweepPrune = atoi(e) != 0;
     if (const char* e = getenv("MM_SWEEP")) sweepMode = !strcmp(e, "full") ? 1 : !strcmp(e, "global") ? 2 : 0;
   }
 
@@ -2046,8 +2160,9 @@ struct Mapper {
           pr.exclusive_sum<int32_t, int64_t>(lhead.p, lidx.p, nFlag + 1);
           d2h(rt, &n_cand, lidx.p + nFlag, sizeof(int64_t));
           cRead.ensure((size_t)n_cand + 1); cSeq.ensure((size_t)n_cand + 1); cStart.ensure((size_t)n_cand + 1); cEnd.ensure((size_t)n_cand + 1);
+          cHitLo.ensure((size_t)n_cand + 1); cHitHi.ensure((size_t)n_cand + 1);
           foreach(rt, nFlag, LocusWriteFn{hits2.p, flagged.p, sOf.p, readLen.p, dMinHits.p, dec, lhead.p, lidx.p, nFlag,
-                                          cRead.p, cSeq.p, cStart.p, cEnd.p, candCnt.p});
+                                          cRead.p, cSeq.p, cStart.p, cEnd.p, candCnt.p, cHitLo.p, cHitHi.p});
         }
       }
       pr.exclusive_sum<int32_t, int64_t>(candCnt.p, candOff.p, (int64_t)n_reads + 1);
@@ -2060,12 +2175,12 @@ struct Mapper {
     oVotes.ensure((size_t)n_cand + 1); oAccept.ensure((size_t)n_cand + 1); oOptS.ensure((size_t)n_cand + 1); oOptE.ensure((size_t)n_cand + 1);
     readMapped.ensure((size_t)n_reads + 1); dev_memset(rt, readMapped.p, 0, sizeof(int32_t) * ((size_t)n_reads + 1));
     if (n_cand > 0) {
-      beg0.ensure((size_t)n_cand + 1); fe.ensure((size_t)n_cand + 1); le.ensure((size_t)n_cand + 1);
+      beg0.ensure((size_t)n_cand + 1); fe.ensure((size_t)n_cand + 1); le.ensure((size_t)n_cand + 1); cHits.ensure((size_t)n_cand + 1);
       spanN.ensure((size_t)n_cand + 2); stWords.ensure((size_t)n_cand + 2); evOff.ensure((size_t)n_cand + 2); stOff.ensure((size_t)n_cand + 2);
       {
         StageTimer t(rt, &st.ms[5]);
         foreach(rt, n_cand + 1, L2SetupFn{ix.miWs.p, ix.contigStart.p, cRead.p, cSeq.p, cStart.p, cEnd.p, readLen.p, sOf.p, k, w,
-                                           beg0.p, fe.p, le.p, spanN.p, n_cand});
+                                           beg0.p, fe.p, le.p, spanN.p, n_cand, cHitLo.p, cHitHi.p, cHits.p});
         pr.exclusive_sum<int32_t, int64_t>(spanN.p, evOff.p, n_cand + 1);
       }
       // the usual case is ONE pass over all candidates: only the total and the largest span come to the host then; the full
@@ -2091,11 +2206,17 @@ struct Mapper {
         ev.ensure((size_t)nEv + 64);      // the sweeps prefetch a few events past the end of a span
         {
           StageTimer t(rt, &st.ms[6]);
-          if (sweepSkip) { grpSum.ensure((size_t)(nEv >> 5) + (size_t)nc + 4); dev_memset(rt, grpSum.p, 0, 4 * ((size_t)(nEv >> 5) + (size_t)nc + 4)); }
-          L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p,
-                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, sweepSkip ? grpSum.p : nullptr};
+          bool prune = sweepPrune && sweepMode == 0 && nc < ((int64_t)1 << 31);
 #ifndef MM_HOST_EMU
-          if ((int64_t)maxSketch * 4 <= 200 * 1024 && maxSketch < 65535) {      // bucket starts are 16-bit ranks
+          const bool fast = (int64_t)maxSketch * 4 <= 200 * 1024 && maxSketch < 65535;      // bucket starts are 16-bit ranks
+          prune = prune && fast;                           // the prune pass is part of the shared-memory kernel
+#endif
+          if (prune) { swB0.ensure((size_t)nc + 1); swB1.ensure((size_t)nc + 1); }
+          prunedPass = prune;
+          L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p,
+                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, cHits.p, prune ? swB0.p : nullptr, prune ? swB1.p : nullptr};
+#ifndef MM_HOST_EMU
+          if (fast) {
             if (rt.first((const void*)l2_classify_smem_kernel<false>)) {
               MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
               MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -2103,16 +2224,19 @@ struct Mapper {
             // contiguous runs of candidates per CTA, ~8 waves of CTAs so that uneven runs average out
             int64_t g = (int64_t)rt.sm_count * 64; if (g > nc) g = nc;
             int32_t perCta = (int32_t)((nc + g - 1) / g); g = (nc + perCta - 1) / perCta;
-            if (cf.grp) l2_classify_smem_kernel<true><<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
+            if (prune) l2_classify_smem_kernel<true><<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
             else l2_classify_smem_kernel<false><<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
             MM_CUDA(cudaGetLastError());
             rt.launches++;
           } else
 #endif
             foreach(rt, nEv, cf);
+#ifdef MM_HOST_EMU
+          if (prune) foreach(rt, nc, L2PruneFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, cRead.p, sOf.p, readLen.p, cHits.p, k, w, swB0.p, swB1.p});
+#endif
         }
         L2SweepArgs sa{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, le.p, cRead.p, sOf.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w,
-                       oShared.p, oPos.p, oValid.p, oOptS.p, oOptE.p, oIstar.p, sweepSkip ? grpSum.p : nullptr};
+                       oShared.p, oPos.p, oValid.p, oOptS.p, oOptE.p, oIstar.p};
         {
           StageTimer t(rt, &st.ms[7]);
           smemSwept += sweep_pass(sa, nc, cntBytes);
@@ -2173,21 +2297,22 @@ struct Mapper {
     int64_t done_fast = 0;
     const int32_t* redoList = nullptr; int64_t nRedo = nc;        // default: everything through the global-memory functor
     const int BAND = sweepBand, MODE = sweepMode;                 // MODE 0 band, 1 full-state smem, 2 global only
-    swRedo.ensure((size_t)nc + 1); scal.ensure(4);
+    swRedo.ensure((size_t)nc + 1); scal.ensure(8);
     if (MODE == 0 && nc > 0 && nc < ((int64_t)1 << 31) && maxSketch < (1 << 20)) {
       // work items = segments of candidates
       segCnt.ensure((size_t)nc + 2); itemOff.ensure((size_t)nc + 2);
-      foreach(rt, nc + 1, BandSegCountFn{spanN.p, beg0.p, fe.p, sa.cand0, nc, sweepSeg, segCnt.p});
+      const int32_t* cb0 = prunedPass ? swB0.p : nullptr; const int32_t* cb1 = prunedPass ? swB1.p : nullptr;
+      dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 6);          // scal[0] = redo count, [1] = tile counter, [2] = wide-band items, [4] / [5] = window starts to sweep / in all
+      foreach(rt, nc + 1, BandSegCountFn{spanN.p, beg0.p, fe.p, sa.cand0, nc, sweepSeg, segCnt.p, cb0, cb1, scal.p + 4});
       pr.exclusive_sum<int32_t, int64_t>(segCnt.p, itemOff.p, nc + 1);
       int64_t nItems = 0; d2h(rt, &nItems, itemOff.p + nc, sizeof(int64_t));
-      itemCand.ensure((size_t)nItems); itemSeg.ensure((size_t)nItems); bandParts.ensure((size_t)nItems);
+      itemCand.ensure((size_t)nItems); itemB0.ensure((size_t)nItems); itemB1.ensure((size_t)nItems); bandParts.ensure((size_t)nItems);
       swKey.ensure((size_t)nItems); swKey2.ensure((size_t)nItems); swVal.ensure((size_t)nItems); swOrder.ensure((size_t)nItems);
-      dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);          // scal[0] = redo count, [1] = tile counter, [2] = wide-band items
-      foreach(rt, nItems, BandItemFn{itemOff.p, nc, spanN.p, beg0.p, fe.p, sa.cand0, sweepSeg, swKey.p, swVal.p, itemCand.p, itemSeg.p,
-                                     cRead.p, sOf.p, sweepWideFrom, scal.p + 2});
+      foreach(rt, nItems, BandItemFn{itemOff.p, nc, spanN.p, beg0.p, fe.p, sa.cand0, sweepSeg, swKey.p, swVal.p, itemCand.p, itemB0.p, itemB1.p,
+                                     cRead.p, sOf.p, sweepWideFrom, scal.p + 2, cb0, cb1});
 #ifdef MM_HOST_EMU
       state.ensure((size_t)nItems * band_state_words(BAND) + 1);
-      foreach(rt, nItems, L2SweepBandFn{sa, state.p, BAND, sweepSeg, itemCand.p, itemSeg.p, bandParts.p});
+      foreach(rt, nItems, L2SweepBandFn{sa, state.p, BAND, itemCand.p, itemB0.p, itemB1.p, bandParts.p});
 #else
       pr.sort_pairs<uint32_t, uint32_t>(swKey.p, swKey2.p, swVal.p, swOrder.p, nItems, 32);
       unsigned long long nWide = 0; d2h(rt, &nWide, scal.p + 2, sizeof(nWide));
@@ -2202,8 +2327,9 @@ struct Mapper {
       st.counters[11] += nItems;
 #endif
       foreach(rt, nc, L2BandMergeFn{sa, bandParts.p, itemOff.p, swRedo.p, scal.p});
-      unsigned long long nr = 0; d2h(rt, &nr, scal.p, sizeof(nr));
-      nRedo = (int64_t)nr; redoList = swRedo.p; done_fast = nc - nRedo;
+      unsigned long long nr[6] = {0, 0, 0, 0, 0, 0}; d2h(rt, nr, scal.p, sizeof(nr));
+      nRedo = (int64_t)nr[0]; redoList = swRedo.p; done_fast = nc - nRedo;
+      st.counters[12] += (int64_t)nr[4]; st.counters[13] += (int64_t)nr[5];
     }
 #ifndef MM_HOST_EMU
     if (MODE == 1 && nc >= 1 && nc < ((int64_t)1 << 31) && maxSketch < (1 << 20)) {
@@ -2278,7 +2404,7 @@ struct Mapper {
   }
 
 #ifndef MM_HOST_EMU
-  template <int BW, int R, int MINB = 1, bool SKIP = false>
+  template <int BW, int R, int MINB = 1>
   void launch_band_t(const L2SweepArgs& sa, const uint32_t* order, int64_t nc) {
     constexpr int ST = ((BW + 4) / 4 + BW / 32 + 1) | 1;
     constexpr int WARP_BYTES = (2 * R * 32 * 4 + 32 * ST) * 4;
@@ -2292,10 +2418,10 @@ struct Mapper {
       warps = total / ctasPerSm;
       if (const char* e = getenv("MM_SWEEP_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 16) warps = v; }
     }
-    if (rt.first((const void*)l2_sweep_band_kernel<BW, R, MINB, SKIP>)) MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R, MINB, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
+    if (rt.first((const void*)l2_sweep_band_kernel<BW, R, MINB>)) MM_CUDA(cudaFuncSetAttribute(l2_sweep_band_kernel<BW, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * WARP_BYTES));
     int64_t tiles = (nc + 31) / 32;
     int64_t g = (tiles + warps - 1) / warps; if (g > (int64_t)rt.sm_count * ctasPerSm) g = (int64_t)rt.sm_count * ctasPerSm;
-    l2_sweep_band_kernel<BW, R, MINB, SKIP><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, order, nc, itemCand.p, itemSeg.p, sweepSeg, bandParts.p,
+    l2_sweep_band_kernel<BW, R, MINB><<<(int)g, warps * 32, (size_t)warps * WARP_BYTES, rt.stream>>>(sa, order, nc, itemCand.p, itemB0.p, itemB1.p, bandParts.p,
                                                                                                (unsigned int*)(scal.p + 1));
     MM_CUDA(cudaGetLastError());
     rt.launches++;
@@ -2309,7 +2435,6 @@ struct Mapper {
     else if (BAND == 128) launch_band_t<128, 8>(sa, order, nc);
     else if (RING == 2) launch_band_t<256, 2>(sa, order, nc);
     else if (RING == 4) launch_band_t<256, 4>(sa, order, nc);
-    else if (sa.grp) launch_band_t<256, 8, 1, true>(sa, order, nc);      // MM_SWEEP_SKIP=1: the only instantiation with window skipping
     else launch_band_t<256, 8>(sa, order, nc);
   }
 #endif

@@ -205,7 +205,7 @@ def test_multiple_l2_passes(oracle, small_workload, monkeypatch):
     ctx.close()
 
 
-@pytest.mark.parametrize("env", [{"MM_SWEEP_SKIP": "1"}, {"MM_SWEEP_BAND": "64"}, {"MM_SWEEP_BAND": "128", "MM_SWEEP_RING": "4", "MM_SWEEP_SEG": "100"},
+@pytest.mark.parametrize("env", [{"MM_SWEEP_PRUNE": "0"}, {"MM_SWEEP_SEG": "100"}, {"MM_SWEEP_BAND": "64"}, {"MM_SWEEP_BAND": "128", "MM_SWEEP_RING": "4", "MM_SWEEP_SEG": "100"},
                                  {"MM_SWEEP_SEG": "64"}, {"MM_SWEEP_WIDE_FROM": "300"}, {"MM_SWEEP": "full"},
                                  {"MM_SWEEP": "global"}, {"MM_L1_FILTER": "legacy"}, {"MM_K3_GLOBAL": "1"}])
 def test_kernel_variants(oracle, small_workload, monkeypatch, env):
