@@ -887,27 +887,38 @@ MM_HD PruneThr prune_thresholds(int32_t s, int32_t win, int32_t mest) {
 MM_HD void prune_count(uint32_t code, int32_t s, const PruneThr& th, uint32_t& w0, uint32_t& w1) {
   const bool isM = (code & CODE_MATCH) != 0, dup = (code & CODE_DUP) != 0;
   const int32_t idx = (int32_t)(code & CODE_IDX);
-  const bool isW = !isM && idx < s;
-  if (isW && !dup && idx < th.i0) w0 += 1u;
-  if (isM && idx < th.i0) w0 += 1u << 6;
-  if (isW && idx <= th.i1) w0 += 1u << 12;
-  if (isM && !dup && idx <= th.i1) w0 += 1u << 18;
-  if (isM) w0 += 1u << 24;
-  if (isW && idx <= th.i1b) w1 += 1u;
-  if (isM && !dup && idx <= th.i1b) w1 += 1u << 6;
+  const bool v1 = isM || (idx < s && !dup);                  // counts for A / B
+  const bool v2 = isM ? !dup : idx < s;                      // counts for C / D and C2 / D2
+  const uint32_t f0 = (v1 && idx < th.i0) ? 1u : 0u, f1 = (v2 && idx <= th.i1) ? 1u : 0u, f2 = (v2 && idx <= th.i1b) ? 1u : 0u;
+  const int sh = isM ? 6 : 0;
+  w0 += (f0 << sh) + (f1 << (12 + sh)) + (isM ? (1u << 24) : 0u);
+  w1 += f2 << sh;
 }
-MM_HD uint32_t prune_series_of(uint32_t w0, uint32_t w1, int q) { return q < 5 ? (w0 >> (6 * q)) & 63u : (w1 >> (6 * (q - 5))) & 63u; }
-// P[q * ld + g] = sum of series q over groups [0, g); H[g] = the last group whose first element lies at or below pos[32 g] + cmw, so
-// that the first element E(32 g) at or beyond that position (the end of the first window that starts at 32 g) has 32 H <= E <= 32 (H + 1)
-struct PruneView {
-  const uint16_t* P; int32_t ld; const uint16_t* H; int32_t nG, s; PruneThr th;
+MM_HD uint32_t prune_series_of(uint32_t w0, uint32_t w1, int q) { return q < 5 ? (w0 >> (6 * q)) & 63u : (w1 >> (6 * (q - 5))) & 63u; }      // q = 0..6: A, B, C, D, M, C2, D2
+// Series q = 0..6: A, B, C, D, M, C2, D2.  Acc::rng(q, ga, gb) = sum of series q over groups [ga, gb) (from prefix sums over the groups);
+// H[g] = the last group whose first element lies at or below pos[32 g] + cmw, so that the first element E(32 g) at or beyond that
+// position (the end of the first window that starts at 32 g) has 32 H <= E <= 32 (H + 1)
+struct PrunePrefix16 {       // P[q * ld + g] = sum over groups [0, g)
+  const uint16_t* P; int32_t ld;
   MM_HD int32_t rng(int q, int32_t ga, int32_t gb) const { return gb > ga ? (int32_t)P[q * ld + gb] - (int32_t)P[q * ld + ga] : 0; }
+};
+struct PrunePrefixPair {     // two series per word: P[(q >> 1) * ld + g], series q in the half q & 1
+  const uint32_t* P; int32_t ld;
+  MM_HD int32_t rng(int q, int32_t ga, int32_t gb) const {
+    if (gb <= ga) return 0;
+    const int sh = 16 * (q & 1);
+    return (int32_t)((P[(q >> 1) * ld + gb] >> sh) & 0xffffu) - (int32_t)((P[(q >> 1) * ld + ga] >> sh) & 0xffffu);
+  }
+};
+template <class Acc>
+struct PruneView {
+  Acc acc; const uint16_t* H; int32_t nG, s; PruneThr th;
   // lower bound of the shared count of the window [32 g, E(32 g)): it lies inside groups [g, h] and contains groups [g, h)
   MM_HD int32_t lb(int32_t g) const {
     const int32_t h = H[g];
     if (h + 1 >= nG) return 0;                               // E(32 g) may be the end of the span: that window is not evaluated
-    if (th.i1 >= 0 && th.i1 <= s && th.i1 + rng(2, g, h + 1) <= s) return rng(3, g, h);
-    if (th.i1b >= 0 && th.i1b <= s && th.i1b + rng(5, g, h + 1) <= s) return rng(6, g, h);
+    if (th.i1 >= 0 && th.i1 <= s && th.i1 + acc.rng(2, g, h + 1) <= s) return acc.rng(3, g, h);
+    if (th.i1b >= 0 && th.i1b <= s && th.i1b + acc.rng(5, g, h + 1) <= s) return acc.rng(6, g, h);
     return 0;
   }
   // upper bound over every window that starts in group g: they contain groups [g + 1, H[g]) and lie inside groups [g, H[g + 1] + 1)
@@ -915,14 +926,14 @@ struct PruneView {
     const int32_t hLo = H[g];
     int32_t hUp = nG;
     if (g + 1 < nG) { hUp = (int32_t)H[g + 1] + 1; if (hUp > nG) hUp = nG; }
-    if (th.i0 + rng(0, g + 1, hLo) > s) return rng(1, g, hUp);
-    return rng(4, g, hUp);
+    if (th.i0 + acc.rng(0, g + 1, hLo) > s) return acc.rng(1, g, hUp);
+    return acc.rng(4, g, hUp);
   }
 };
-MM_HD int32_t prune_window_group(const uint32_t* pos, int32_t nG, int32_t g, int32_t cmw) {
-  const uint32_t target = pos[g] + (uint32_t)cmw;
+MM_HD int32_t prune_window_group(const uint32_t* pos, int32_t stride, int32_t nG, int32_t g, int32_t cmw) {      // pos[stride * g]: position of group g's first element
+  const uint32_t target = pos[stride * g] + (uint32_t)cmw;
   int32_t lo = g, hi = nG - 1;
-  while (lo < hi) { const int32_t m = (lo + hi + 1) >> 1; if (pos[m] <= target) lo = m; else hi = m - 1; }
+  while (lo < hi) { const int32_t m = (lo + hi + 1) >> 1; if (pos[stride * m] <= target) lo = m; else hi = m - 1; }
   return lo;
 }
 #ifdef MM_HOST_EMU
@@ -947,8 +958,8 @@ struct L2PruneFn {
       pos[g] = e[32 * g].y >> 1;
       for (int q = 0; q < PR_NS; q++) P[(size_t)q * ld + g + 1] = (uint16_t)(P[(size_t)q * ld + g] + prune_series_of(w0, w1, q));
     }
-    for (int32_t g = 0; g < nG; g++) H[g] = (uint16_t)prune_window_group(pos.data(), nG, g, cmw);
-    const PruneView v{P.data(), ld, H.data(), nG, s, th};
+    for (int32_t g = 0; g < nG; g++) H[g] = (uint16_t)prune_window_group(pos.data(), 1, nG, g, cmw);
+    const PruneView<PrunePrefix16> v{PrunePrefix16{P.data(), ld}, H.data(), nG, s, th};
     int32_t T = 0;
     for (int32_t g = 0; g < nG; g++) { const int32_t l = v.lb(g); if (l > T) T = l; }
     if (T <= 0) return;
@@ -990,16 +1001,17 @@ struct L2ClassifyFn {
 // on the top 11 hash bits (first sketch rank of every bucket), so the rank search of a reference minimizer is a lookup
 // plus a short binary search inside one bucket instead of log2(s) steps.  Same codes as L2ClassifyFn.
 static const int CLS_BUCKET_BITS = 11, CLS_BUCKETS = 1 << CLS_BUCKET_BITS;
-// PRUNE: the warp's 32 lanes hold one group of 32 span elements: seven ballots count the prune pass's indicators (prune_count) into
-// shared memory; after the candidate's last element the CTA scans the seven series over the groups, takes the bounds (PruneView) and
+// PRUNE: the warp's 32 lanes hold one group of 32 span elements: two warp-wide adds of packed 6-bit fields count the prune pass's
+// indicators (prune_count) into shared memory; after the candidate's last element the CTA scans the seven series over the groups, takes the bounds (PruneView) and
 // writes the window starts worth sweeping.  Four barriers per candidate.
 template <bool PRUNE>
 __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, int32_t perCta) {
   extern __shared__ uint32_t smq[];
   __shared__ uint16_t bstart[CLS_BUCKETS + 2];
   constexpr int GM = PRUNE ? PR_GMAX : 1, LD = GM + 1;
-  __shared__ uint32_t gw0[GM], gw1[GM], gpos[GM];
-  __shared__ uint16_t gP[PR_NS * LD], gH[GM];
+  __shared__ uint4 gq[GM];                               // per group: {count words 0 and 1, position of its first element, -}
+  __shared__ uint32_t gP[4 * LD];                        // prefix sums over the groups, two series per word (PrunePrefixPair)
+  __shared__ uint16_t gH[GM];
   __shared__ int32_t red[3];                             // best lower bound, first / last surviving group
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int32_t curRead = -1, s = 0;
@@ -1052,17 +1064,10 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
           a.ev[e0 + t] = make_uint2(code, wsv[u]);
         }
         if (PRUNE && doPrune && (t & ~31) < n) {         // warp-uniform: t & ~31 is the group's first element
-          const bool isM = on[u] && (code & CODE_MATCH) != 0, dup = (code & CODE_DUP) != 0;
-          const int32_t idx = (int32_t)(code & CODE_IDX);
-          const bool isW = on[u] && !isM && idx < s;
-          const uint32_t cA = (uint32_t)__popc(__ballot_sync(0xffffffffu, isW && !dup && idx < th.i0));
-          const uint32_t cB = (uint32_t)__popc(__ballot_sync(0xffffffffu, isM && idx < th.i0));
-          const uint32_t cC = (uint32_t)__popc(__ballot_sync(0xffffffffu, isW && idx <= th.i1));
-          const uint32_t cD = (uint32_t)__popc(__ballot_sync(0xffffffffu, isM && !dup && idx <= th.i1));
-          const uint32_t cM = (uint32_t)__popc(__ballot_sync(0xffffffffu, isM));
-          const uint32_t cC2 = (uint32_t)__popc(__ballot_sync(0xffffffffu, isW && idx <= th.i1b));
-          const uint32_t cD2 = (uint32_t)__popc(__ballot_sync(0xffffffffu, isM && !dup && idx <= th.i1b));
-          if (lane == 0) { const int32_t g = t >> 5; gw0[g] = cA | (cB << 6) | (cC << 12) | (cD << 18) | (cM << 24); gw1[g] = cC2 | (cD2 << 6); gpos[g] = wsv[u] >> 1; }
+          uint32_t w0 = 0, w1 = 0;                         // the lane's own indicators, 6-bit fields; one warp-wide add per word gives the group's counts (<= 32 each)
+          if (on[u]) prune_count(code, s, th, w0, w1);
+          w0 = __reduce_add_sync(0xffffffffu, w0); w1 = __reduce_add_sync(0xffffffffu, w1);
+          if (lane == 0) gq[t >> 5] = make_uint4(w0, w1, wsv[u] >> 1, 0u);
         }
       }
     }
@@ -1070,22 +1075,37 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
       int32_t B0 = 0, B1 = 0x7fffffff;
       if (doPrune) {
         __syncthreads();                                 // the group counts are complete
-        for (int q = wid; q < PR_NS; q += 4) {           // one warp per series: lane l scans groups [8 l, 8 l + 8), the lane totals are scanned with shuffles
-          uint32_t v[8]; uint32_t tot = 0;
-#pragma unroll
-          for (int j = 0; j < 8; j++) { const int32_t g = 8 * lane + j; v[j] = g < nG ? prune_series_of(gw0[g], gw1[g], q) : 0u; tot += v[j]; v[j] = tot; }
+        {                                                // warp w scans the pair of series (2 w, 2 w + 1): lane l takes groups [J l, J l + J), the lane totals are scanned with shuffles
+          const int32_t J = (nG + 31) >> 5, g0 = J * lane;
+          const int shA = wid < 2 ? 12 * wid : 24, shB = wid < 2 ? 12 * wid + 6 : 0;       // pair 0: A, B; 1: C, D; 2: M (word 0), C2 (word 1); 3: D2 (word 1, bits 6..11)
+          uint32_t tot = 0;
+          for (int32_t j = 0; j < J; j++) {
+            const int32_t g = g0 + j;
+            if (g < nG) {
+              const uint4 v = gq[g];
+              const uint32_t a_ = wid < 3 ? (v.x >> shA) & 63u : (v.y >> 6) & 63u, b_ = wid < 2 ? (v.x >> shB) & 63u : wid == 2 ? v.y & 63u : 0u;
+              tot += a_ | (b_ << 16);
+            }
+          }
           uint32_t inc = tot;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-          const uint32_t base = inc - tot;
-          if (lane == 0) gP[q * LD] = 0;
-#pragma unroll
-          for (int j = 0; j < 8; j++) { const int32_t g = 8 * lane + j; if (g < nG) gP[q * LD + g + 1] = (uint16_t)(base + v[j]); }
+          uint32_t run = inc - tot;
+          if (lane == 0) gP[wid * LD] = 0;
+          for (int32_t j = 0; j < J; j++) {
+            const int32_t g = g0 + j;
+            if (g < nG) {
+              const uint4 v = gq[g];
+              const uint32_t a_ = wid < 3 ? (v.x >> shA) & 63u : (v.y >> 6) & 63u, b_ = wid < 2 ? (v.x >> shB) & 63u : wid == 2 ? v.y & 63u : 0u;
+              run += a_ | (b_ << 16);
+              gP[wid * LD + g + 1] = run;
+            }
+          }
         }
-        for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) gH[g] = (uint16_t)prune_window_group(gpos, nG, g, cmw);
+        for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) gH[g] = (uint16_t)prune_window_group(&gq[0].z, 4, nG, g, cmw);
         if (threadIdx.x == 0) { red[0] = 0; red[1] = nG; red[2] = -1; }
         __syncthreads();
-        const PruneView pv{gP, LD, gH, nG, s, th};
+        const PruneView<PrunePrefixPair> pv{PrunePrefixPair{gP, LD}, gH, nG, s, th};
         int32_t lbv = 0;
         for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) { const int32_t l = pv.lb(g); lbv = l > lbv ? l : lbv; }
         lbv = __reduce_max_sync(0xffffffffu, lbv);

@@ -1,0 +1,7 @@
+#!/bin/bash
+# Round 2, GPU call R (1 x B200): K5a prune pass variants (REDUX counts; packed prefix pairs).
+set -x
+mkdir -p gpurun_out
+(timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "map or variants or fallback or passes or cli" > gpurun_out/r2r2_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2r2_tests.log)
+timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2r2_bench.json 2> gpurun_out/r2r2_bench.err
+ls gpurun_out | grep r2r
