@@ -474,7 +474,9 @@ def main():
         "K3 read sketch": {"ms": ms["read_sketch_ms"], "bytes": 2 * 8 * ms["read_minimizers"]},
         "K4 L1 (probe + filter + sort + loci)": {"ms": ms["l1_probe_ms"] + ms["l1_sort_ms"] + ms["l1_candidates_ms"], "bytes": 16 * s_tot + 8 * H + 12 * C_},
         "K5 L2 (setup + classify + prune + sweep + strand)": {"ms": ms["l2_setup_ms"] + ms["l2_classify_ms"] + ms["l2_prune_ms"] + ms["l2_sweep_ms"] + ms["l2_strand_ms"], "bytes": k5_bytes},
+        "K4 l1_probe_filter_kernel": {"ms": ms["l1_kernel_ms"], "bytes": 16 * s_tot + 8 * H + 12 * C_},
         "K5a l2_classify_smem_kernel": {"ms": ms["l2_classify_ms"], "bytes": 8 * span},
+        "K5p l2_prune_warp_kernel": {"ms": ms["l2_prune_ms"], "bytes": 16 * span / 32 + 8 * C_},
         "K5b l2_sweep_band_kernel": {"ms": ms["sweep_kernel_ms"], "bytes": k5_bytes},
         "K5c l2_strand_warp_kernel": {"ms": ms["l2_strand_ms"], "bytes": 8 * span / 2.8},
         "K6-K8 classify stage (identity, mapq, nLoc, EM)": {"ms": cs["classify_ms"], "bytes": 24 * A + (12 * A + 4 * R_ + 16 * n_taxa) * rounds + 8 * A},
@@ -484,7 +486,7 @@ def main():
         v["frac"] = v["GBps"] / peak
         if "imad_roof_ms" in v:
             v["imad_frac"] = v["imad_roof_ms"] / v["ms"] if v["ms"] > 0 else 0.0
-    dom = max(("K1 sketch_blockmin_kernel", "K5a l2_classify_smem_kernel", "K5b l2_sweep_band_kernel"), key=lambda k_: table[k_]["ms"])
+    dom = max(("K1 sketch_blockmin_kernel", "K4 l1_probe_filter_kernel", "K5a l2_classify_smem_kernel", "K5b l2_sweep_band_kernel"), key=lambda k_: table[k_]["ms"])
     dom_ms, dom_bytes = table[dom]["ms"], table[dom]["bytes"]
     achieved = table[dom]["GBps"]
     step_bytes = sum(table[k_]["bytes"] for k_ in ("K1 stage (pack + sketch + compaction)", "K3 read sketch", "K4 L1 (probe + filter + sort + loci)",
@@ -514,7 +516,8 @@ def main():
                      "frac": achieved / peak if peak else None,
                      "traffic": (traffic.get(dom, {}).get("dram_bytes_per_launch") if args.workload == traffic.get("workload") else None),
                      "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_launch": dom_ms,
-                     "algorithmic_bytes_formula": "SURVEY.md 8(d): K5 = 8*sum N_c + 4*s + 20*C (the whole L2 row, charged to the sweep kernel); K1 = bases/4 + 8*n_min",
+                     "algorithmic_bytes_formula": "SURVEY.md 8(d): K4 = 16*s + 8*H + 12*C (the whole L1 row, charged to the fused probe + filter kernel); K5 = 8*sum N_c + 4*s + 20*C "
+                                                  "(the whole L2 row, charged to the sweep kernel); K1 = bases/4 + 8*n_min",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md, of fallback)",
                      "note": "integer / latency-bound work: the HBM fraction is reported as measured; K1 is bound by the IMAD pipe (imad_frac = its share of that roof); "
                              "kernel and stage times are CUDA events of the last timed step",

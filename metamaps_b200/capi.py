@@ -165,7 +165,7 @@ class Context:
                 "sketch_elems": int(ct[0]), "hits": int(ct[1]), "candidates": int(ct[2]), "span_elems": int(ct[3]),
                 "mappings": int(ct[4]), "read_minimizers": int(ct[5]), "bases": int(ct[6]), "exceptions": int(ct[7]),
                 "ambiguous_reads": int(ct[8]), "smem_swept": int(ct[9]), "hits_kept": int(ct[10]), "sweep_items": int(ct[11]),
-                "k1_kernel_ms": ms[10], "sweep_kernel_ms": ms[11], "l2_prune_ms": ms[12],
+                "k1_kernel_ms": ms[10], "sweep_kernel_ms": ms[11], "l2_prune_ms": ms[12], "l1_kernel_ms": ms[13],
                 "window_starts_swept": int(ct[12]), "window_starts": int(ct[13])}
 
     # K1

@@ -518,14 +518,15 @@ int mm_stage_reads_async(mm_ctx* c, int slot, const char* reads, const int64_t* 
   if (!st.ready) MM_CUDA(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
   st.join();
   st.feedErr = 0; st.packed = false;
-  // Pinned (mapped) host memory: no DMA at all -- K0 itself pulls the bytes over PCIe on the copy stream and writes the
-  // 2-bit words, so the upload of the next batch neither queues in front of the small copies of the batch being mapped
-  // nor leaves K0 on that batch's critical path.  MM_STAGE=copy (or pageable memory) selects the DMA path below.
+  // Default: DMA (copy engine) into a device slot, in pieces (below); K0 then packs from device memory at the start of the batch's
+  // own step (0.7 ms).  MM_STAGE=zerocopy: for pinned (mapped) host memory K0 itself pulls the bytes over PCIe on the copy stream
+  // while the previous batch is mapped -- no K0 on the critical path, but its CTAs sit on the SMs for the whole transfer and
+  // slow K1 / K3 of the batch being mapped by 4 ms (config 2: e2e 17 614 Mbp/s against 18 590 with the DMA path, call T).
   cudaPointerAttributes attr; memset(&attr, 0, sizeof attr);
   const bool mapped = bytes > 0 && cudaPointerGetAttributes(&attr, reads + offsets[0]) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer;
   cudaGetLastError();
   const char* mode = getenv("MM_STAGE");
-  if (mapped && !(mode && !strcmp(mode, "copy"))) {
+  if (mapped && mode && !strcmp(mode, "zerocopy")) {
     const uint8_t* dp = (const uint8_t*)attr.devicePointer - offsets[0];       // PackFn indexes with the caller's offsets
     std::swap(c->rt.stream, c->rt.copy);                                         // issue on the copy stream
     try {

@@ -968,6 +968,74 @@ struct L2PruneFn {
     if (gL >= gF) { swB0[ci] = 32 * gF; swB1[ci] = 32 * (gL + 1); }
   }
 };
+#else
+// one warp per candidate: prefix sums of the seven series over the groups (two series per word, lane l takes groups [J l, J l + J)),
+// the window extents, the best lower bound, the hull of the groups whose upper bound reaches it
+static const int PRUNE_WARPS = 8;
+struct L2PruneArgs {
+  const uint4* grp; const int64_t* evOff; int64_t evBase; int64_t cand0;
+  const int64_t* beg0; const int64_t* fe; const int32_t* cRead; const int32_t* sOf; const int32_t* readLen; const int32_t* cHits; int k, w;
+  int32_t* swB0; int32_t* swB1;
+};
+MM_HD size_t prune_warp_words(int32_t gmax) { return (size_t)4 * (gmax + 1) + (size_t)gmax + (size_t)(gmax + 1) / 2; }      // P pairs, positions, H (16-bit)
+__global__ void __launch_bounds__(PRUNE_WARPS * 32) l2_prune_warp_kernel(L2PruneArgs a, int64_t nCand, int32_t gmax) {
+  extern __shared__ __align__(16) uint32_t prsm[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t LD = gmax + 1;
+  uint32_t* P = prsm + (size_t)wid * prune_warp_words(gmax);
+  uint32_t* POS = P + (size_t)4 * LD;
+  uint16_t* H = reinterpret_cast<uint16_t*>(POS + gmax);
+  for (int64_t ci = (int64_t)blockIdx.x * PRUNE_WARPS + wid; ci < nCand; ci += (int64_t)gridDim.x * PRUNE_WARPS) {
+    const int64_t c = a.cand0 + ci;
+    const int32_t n = (int32_t)(a.evOff[c + 1] - a.evOff[c]), nG = (n + 31) >> 5;
+    int32_t B0 = 0, B1 = 0x7fffffff;
+    if (nG >= 1 && nG <= gmax) {
+      const int32_t r = a.cRead[c], s = a.sOf[r], cmw = a.readLen[r] - (a.w - 1) - (a.k - 1);
+      const PruneThr th = prune_thresholds(s, (int32_t)(a.fe[c] - a.beg0[c]), a.cHits ? a.cHits[c] : 0);
+      const uint4* G = a.grp + (((a.evOff[c] - a.evBase) >> 5) + ci);
+      const int32_t J = (nG + 31) >> 5, g0 = J * lane;             // J <= 8
+      uint32_t pr[4][8];
+      uint32_t tot[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int32_t g = g0 + j;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (j < J && g < nG) { v = __ldg(G + g); POS[g] = v.z; }
+        tot[0] += (v.x & 63u) | (((v.x >> 6) & 63u) << 16);        // A, B
+        tot[1] += ((v.x >> 12) & 63u) | (((v.x >> 18) & 63u) << 16);   // C, D
+        tot[2] += ((v.x >> 24) & 63u) | ((v.y & 63u) << 16);       // M, C2
+        tot[3] += (v.y >> 6) & 63u;                                // D2
+#pragma unroll
+        for (int q = 0; q < 4; q++) pr[q][j] = tot[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        uint32_t inc = tot[q];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+        const uint32_t base = inc - tot[q];
+        if (lane == 0) P[q * LD] = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const int32_t g = g0 + j; if (j < J && g < nG) P[q * LD + g + 1] = base + pr[q][j]; }
+      }
+      __syncwarp();
+      for (int32_t g = lane; g < nG; g += 32) H[g] = (uint16_t)prune_window_group(POS, 1, nG, g, cmw);
+      __syncwarp();
+      const PruneView<PrunePrefixPair> pv{PrunePrefixPair{P, LD}, H, nG, s, th};
+      int32_t T = 0;
+      for (int32_t g = lane; g < nG; g += 32) { const int32_t l = pv.lb(g); T = l > T ? l : T; }
+      T = __reduce_max_sync(0xffffffffu, T);
+      if (T > 0) {
+        int32_t gF = nG, gL = -1;
+        for (int32_t g = lane; g < nG; g += 32) if (pv.ub(g) >= T) { gF = g < gF ? g : gF; gL = g > gL ? g : gL; }
+        gF = __reduce_min_sync(0xffffffffu, gF); gL = __reduce_max_sync(0xffffffffu, gL);
+        if (gL >= gF) { B0 = 32 * gF; B1 = 32 * (gL + 1); }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) { a.swB0[ci] = B0; a.swB1[ci] = B1; }
+  }
+}
 #endif
 
 // phase A: one item per reference minimizer of a candidate span
@@ -977,9 +1045,10 @@ struct L2ClassifyFn {
   const int64_t* beg0; const int32_t* cRead; const uint32_t* qHash; const int64_t* qOff; const int32_t* sOf;
   uint2* ev;
   const int64_t* fe; const int64_t* le; const int32_t* readLen; const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; int k, w;
-  // the device kernel also counts the prune pass's indicators and decides the window starts worth sweeping (swB0 / swB1, indexed by
-  // the candidate's number within the pass; null: no pruning); cHits: L1 hits of the candidate (estimate of its best window's matches)
-  const int32_t* cHits; int32_t* swB0; int32_t* swB1;
+  // the device kernel also counts the prune pass's indicators: one record per group of 32 span elements, candidate c's groups start
+  // at grp_base(c) (null: no pruning); cHits: L1 hits of the candidate (estimate of its best window's matches)
+  const int32_t* cHits; uint4* grp;
+  MM_HD int64_t grp_base(int64_t c) const { return ((ldg(evOff + c) - evBase) >> 5) + (c - cand0); }
   MM_HD void operator()(int64_t t) const {
     int64_t c = cand0 + upper_bound_idx(evOff + cand0, nCand + 1, t + evBase) - 1;
     int64_t j = ldg(beg0 + c) + (t + evBase - ldg(evOff + c));
@@ -1002,18 +1071,13 @@ struct L2ClassifyFn {
 // plus a short binary search inside one bucket instead of log2(s) steps.  Same codes as L2ClassifyFn.
 static const int CLS_BUCKET_BITS = 11, CLS_BUCKETS = 1 << CLS_BUCKET_BITS;
 // PRUNE: the warp's 32 lanes hold one group of 32 span elements: two warp-wide adds of packed 6-bit fields count the prune pass's
-// indicators (prune_count) into shared memory; after the candidate's last element the CTA scans the seven series over the groups, takes the bounds (PruneView) and
-// writes the window starts worth sweeping.  Four barriers per candidate.
+// indicators (prune_count); lane 0 writes the group's record {count words 0 and 1, position of its first element, -} for
+// l2_prune_warp_kernel.  (Deciding inside this kernel cost four barriers per candidate: 8.0 ms against 4.9 without pruning.)
 template <bool PRUNE>
 __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, int32_t perCta) {
   extern __shared__ uint32_t smq[];
   __shared__ uint16_t bstart[CLS_BUCKETS + 2];
-  constexpr int GM = PRUNE ? PR_GMAX : 1, LD = GM + 1;
-  __shared__ uint4 gq[GM];                               // per group: {count words 0 and 1, position of its first element, -}
-  __shared__ uint32_t gP[4 * LD];                        // prefix sums over the groups, two series per word (PrunePrefixPair)
-  __shared__ uint16_t gH[GM];
-  __shared__ int32_t red[3];                             // best lower bound, first / last surviving group
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   int32_t curRead = -1, s = 0;
   const int64_t ciEnd = ((int64_t)blockIdx.x + 1) * perCta < a.nCand ? ((int64_t)blockIdx.x + 1) * perCta : a.nCand;
   for (int64_t ci = (int64_t)blockIdx.x * perCta; ci < ciEnd; ci++) {
@@ -1039,6 +1103,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
     const bool doPrune = PRUNE && nG >= 1 && nG <= PR_GMAX;        // CTA-uniform
     PruneThr th{0, 0, 0};
     if (doPrune) th = prune_thresholds(s, (int32_t)(fe - b0), a.cHits ? a.cHits[c] : 0);
+    const int64_t gb = PRUNE ? a.grp_base(c) : 0;
     auto rank_code = [&](uint32_t h) -> uint32_t {
       const uint32_t bk = h >> (32 - CLS_BUCKET_BITS);
       int32_t lo = bstart[bk], hi = bstart[bk + 1];
@@ -1067,61 +1132,9 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
           uint32_t w0 = 0, w1 = 0;                         // the lane's own indicators, 6-bit fields; one warp-wide add per word gives the group's counts (<= 32 each)
           if (on[u]) prune_count(code, s, th, w0, w1);
           w0 = __reduce_add_sync(0xffffffffu, w0); w1 = __reduce_add_sync(0xffffffffu, w1);
-          if (lane == 0) gq[t >> 5] = make_uint4(w0, w1, wsv[u] >> 1, 0u);
+          if (lane == 0) a.grp[gb + (t >> 5)] = make_uint4(w0, w1, wsv[u] >> 1, 0u);
         }
       }
-    }
-    if (PRUNE) {
-      int32_t B0 = 0, B1 = 0x7fffffff;
-      if (doPrune) {
-        __syncthreads();                                 // the group counts are complete
-        {                                                // warp w scans the pair of series (2 w, 2 w + 1): lane l takes groups [J l, J l + J), the lane totals are scanned with shuffles
-          const int32_t J = (nG + 31) >> 5, g0 = J * lane;
-          const int shA = wid < 2 ? 12 * wid : 24, shB = wid < 2 ? 12 * wid + 6 : 0;       // pair 0: A, B; 1: C, D; 2: M (word 0), C2 (word 1); 3: D2 (word 1, bits 6..11)
-          uint32_t tot = 0;
-          for (int32_t j = 0; j < J; j++) {
-            const int32_t g = g0 + j;
-            if (g < nG) {
-              const uint4 v = gq[g];
-              const uint32_t a_ = wid < 3 ? (v.x >> shA) & 63u : (v.y >> 6) & 63u, b_ = wid < 2 ? (v.x >> shB) & 63u : wid == 2 ? v.y & 63u : 0u;
-              tot += a_ | (b_ << 16);
-            }
-          }
-          uint32_t inc = tot;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-          uint32_t run = inc - tot;
-          if (lane == 0) gP[wid * LD] = 0;
-          for (int32_t j = 0; j < J; j++) {
-            const int32_t g = g0 + j;
-            if (g < nG) {
-              const uint4 v = gq[g];
-              const uint32_t a_ = wid < 3 ? (v.x >> shA) & 63u : (v.y >> 6) & 63u, b_ = wid < 2 ? (v.x >> shB) & 63u : wid == 2 ? v.y & 63u : 0u;
-              run += a_ | (b_ << 16);
-              gP[wid * LD + g + 1] = run;
-            }
-          }
-        }
-        for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) gH[g] = (uint16_t)prune_window_group(&gq[0].z, 4, nG, g, cmw);
-        if (threadIdx.x == 0) { red[0] = 0; red[1] = nG; red[2] = -1; }
-        __syncthreads();
-        const PruneView<PrunePrefixPair> pv{PrunePrefixPair{gP, LD}, gH, nG, s, th};
-        int32_t lbv = 0;
-        for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) { const int32_t l = pv.lb(g); lbv = l > lbv ? l : lbv; }
-        lbv = __reduce_max_sync(0xffffffffu, lbv);
-        if (lane == 0 && lbv > 0) atomicMax(&red[0], lbv);
-        __syncthreads();
-        const int32_t T = red[0];
-        if (T > 0) {
-          int32_t gF = nG, gL = -1;
-          for (int32_t g = threadIdx.x; g < nG; g += blockDim.x) if (pv.ub(g) >= T) { gF = g < gF ? g : gF; gL = g > gL ? g : gL; }
-          gF = __reduce_min_sync(0xffffffffu, gF); gL = __reduce_max_sync(0xffffffffu, gL);
-          if (lane == 0 && gL >= 0) { atomicMin(&red[1], gF); atomicMax(&red[2], gL); }
-        }
-        __syncthreads();
-        if (T > 0 && red[2] >= red[1]) { B0 = 32 * red[1]; B1 = 32 * (red[2] + 1); }
-      }
-      if (threadIdx.x == 0) { a.swB0[ci] = B0; a.swB1[ci] = B1; }
     }
   }
 }
@@ -1860,7 +1873,7 @@ struct Mapper {
   DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemB0, itemB1, segCnt, swB0, swB1, cHits; DevBuf<int64_t> cHitLo, cHitHi; DevBuf<BandPart> bandParts; std::vector<int64_t> hEvSpan;
   // K5a also bounds every window's shared count and K5b sweeps only the window starts that can hold the optimum (l2 prune, PruneView);
   // MM_SWEEP_PRUNE=0 sweeps every window start as the reference does
-  bool sweepPrune = true, prunedPass = false;
+  DevBuf<uint4> grpSum; bool sweepPrune = true, prunedPass = false;
   DevBuf<uint2> probeOut;      // (CSR start, count) of every probe of the batch: l1_probe_filter_kernel's spill between its two passes
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
@@ -2080,6 +2093,7 @@ struct Mapper {
           unsigned long long hs[3] = {0, 0, 0};
           for (int attempt = 0; attempt < 2; attempt++) {
             dev_memset(rt, scal.p, 0, sizeof(unsigned long long) * 4);
+            StageTimer tk(rt, &st.ms[13]);                                          // the fused kernel proper
             if (pfChunk == 512)
               l1_probe_filter_kernel<512><<<grid, 256, smem, rt.stream>>>(ix.table.p, ix.tableMask, ix.freqThreshold, qHash.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p,
                                                                           ix.posKey.p, lay, n_reads, binsN - 1, scal.p, hits.p, (unsigned long long)hits.cap,
@@ -2090,6 +2104,7 @@ struct Mapper {
                                                                            keptPerRead.p, (uint32_t)cacheCap, probeOut.p);
             MM_CUDA(cudaGetLastError());
             rt.launches++;
+            tk.stop();
             d2h(rt, hs, scal.p, sizeof(hs));
             if (!hs[2]) break;
             hits.ensure((size_t)hs[0] + 1);                                        // the survivors did not fit: now they do
@@ -2231,10 +2246,10 @@ struct Mapper {
           const bool fast = (int64_t)maxSketch * 4 <= 200 * 1024 && maxSketch < 65535;      // bucket starts are 16-bit ranks
           prune = prune && fast;                           // the prune pass is part of the shared-memory kernel
 #endif
-          if (prune) { swB0.ensure((size_t)nc + 1); swB1.ensure((size_t)nc + 1); }
+          if (prune) { swB0.ensure((size_t)nc + 1); swB1.ensure((size_t)nc + 1); grpSum.ensure((size_t)(nEv >> 5) + (size_t)nc + 4); }
           prunedPass = prune;
           L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p,
-                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, cHits.p, prune ? swB0.p : nullptr, prune ? swB1.p : nullptr};
+                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, cHits.p, prune ? grpSum.p : nullptr};
 #ifndef MM_HOST_EMU
           if (fast) {
             if (rt.first((const void*)l2_classify_smem_kernel<false>)) {
@@ -2251,8 +2266,19 @@ struct Mapper {
           } else
 #endif
             foreach(rt, nEv, cf);
+        }
+        if (prunedPass) {
+          StageTimer tp(rt, &st.ms[12]);
 #ifdef MM_HOST_EMU
-          if (prune) foreach(rt, nc, L2PruneFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, cRead.p, sOf.p, readLen.p, cHits.p, k, w, swB0.p, swB1.p});
+          foreach(rt, nc, L2PruneFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, cRead.p, sOf.p, readLen.p, cHits.p, k, w, swB0.p, swB1.p});
+#else
+          int32_t gmax = (maxSpan + 31) >> 5; if (gmax > PR_GMAX) gmax = PR_GMAX; if (gmax < 1) gmax = 1;
+          const size_t smem = prune_warp_words(gmax) * 4 * PRUNE_WARPS;
+          if (rt.first((const void*)l2_prune_warp_kernel)) MM_CUDA(cudaFuncSetAttribute(l2_prune_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prune_warp_words(PR_GMAX) * 4 * PRUNE_WARPS)));
+          int64_t g = (nc + PRUNE_WARPS - 1) / PRUNE_WARPS; if (g > (int64_t)rt.sm_count * 8) g = (int64_t)rt.sm_count * 8;
+          l2_prune_warp_kernel<<<(int)g, PRUNE_WARPS * 32, smem, rt.stream>>>(L2PruneArgs{grpSum.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, cRead.p, sOf.p, readLen.p, cHits.p, k, w, swB0.p, swB1.p}, nc, gmax);
+          MM_CUDA(cudaGetLastError());
+          rt.launches++;
 #endif
         }
         L2SweepArgs sa{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, le.p, cRead.p, sOf.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w,

@@ -311,8 +311,9 @@ def test_api_errors(gpu_ctx, tmp_path):
 
 
 def test_staged_reads_pinned_zero_copy(gpu_ctx, small_workload, monkeypatch):
-    """Pinned host memory: mm_stage_reads_async packs straight from host memory over PCIe (no DMA); same results as the direct
-    call, including reads with non-ACGT bytes (the exception side list is settled at map time); MM_STAGE=copy too."""
+    """Pinned host memory through both staging modes -- DMA in pieces into a device slot (the default) and MM_STAGE=zerocopy (K0 packs
+    straight from host memory over PCIe): same results as the direct call, including reads with non-ACGT bytes (the exception
+    side list is settled at map time)."""
     import torch
     contigs = [synth.codes_to_ascii(c) for c in small_workload["db"].contig_codes]
     reads = [synth.codes_to_ascii(r) for r in small_workload["reads"][:120]]
@@ -322,7 +323,7 @@ def test_staged_reads_pinned_zero_copy(gpu_ctx, small_workload, monkeypatch):
     off = np.zeros(len(reads) + 1, np.int64); off[1:] = np.cumsum([len(x) for x in reads])
     pinned = torch.empty(int(off[-1]) + 64, dtype=torch.uint8, pin_memory=True)
     pinned[:int(off[-1])] = torch.frombuffer(bytearray(b"".join(reads)), dtype=torch.uint8)
-    for mode in (None, "copy"):
+    for mode in (None, "zerocopy"):
         if mode:
             monkeypatch.setenv("MM_STAGE", mode)
         for slot in (0, 1):
