@@ -1869,7 +1869,7 @@ struct Mapper {
   std::vector<uint32_t> hk; std::vector<int32_t> tileStartH, localOffH;
   std::vector<int32_t> h_effLen;
   MapStats st;
-  int sweepBand = 256, sweepRing = 8, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT, sweepWideFrom = 0x7fffffff;   // wide-band class: measured neutral on config 2, off unless MM_SWEEP_WIDE_FROM is set
+  int sweepBand = 256, sweepRing = 4, sweepMode = 0, sweepSeg = BAND_SEG_DEFAULT, sweepWideFrom = 0x7fffffff;   // wide-band class: measured neutral on config 2, off unless MM_SWEEP_WIDE_FROM is set
   DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemB0, itemB1, segCnt, swB0, swB1, cHits; DevBuf<int64_t> cHitLo, cHitHi; DevBuf<BandPart> bandParts; std::vector<int64_t> hEvSpan;
   // K5a also bounds every window's shared count and K5b sweeps only the window starts that can hold the optimum (l2 prune, PruneView);
   // MM_SWEEP_PRUNE=0 sweeps every window start as the reference does

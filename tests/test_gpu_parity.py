@@ -246,7 +246,7 @@ def test_index_save_load(gpu_ctx, small_workload, tmp_path):
 
 def test_map_at_scale_independent_paths_agree(oracle, monkeypatch):
     """Config-2-shaped workload at a size the oracle cannot finish (360 Mbp, 4 000 log-normal reads up to 40 kb, w = 16):
-    the fast kernel chain (block-sort K3, 16-bit contig filter, banded + segmented sweep) and the independent general chain
+    the fast kernel chain (block-sort K3, 16-bit contig filter, window pruning, banded + segmented sweep) and the independent general chain
     (global sort, 8-byte filter, full-state sweep in global memory) must agree on every candidate; size-independent
     properties hold; a random subsample is checked against the oracle."""
     import torch
@@ -269,6 +269,7 @@ def test_map_at_scale_independent_paths_agree(oracle, monkeypatch):
             assert res["stats"]["smem_swept"] == 0
         else:
             assert res["stats"]["smem_swept"] == len(res["shared"]) and res["stats"]["sweep_items"] > len(res["shared"])   # segments were cut
+            assert 0 < res["stats"]["window_starts_swept"] < 0.5 * res["stats"]["window_starts"]                      # the prune pass dropped most window starts
         ix.close(); ctx.close()
     a, b = results
     assert len(a["shared"]) > 8000
