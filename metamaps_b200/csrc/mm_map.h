@@ -1068,13 +1068,14 @@ struct L2ClassifyFn {
 // Device fast path of phase A: each CTA takes a contiguous run of candidates (candidates are ordered by read, so the read
 // sketch staged in shared memory is reused by the read's other candidates).  Next to the sketch sits a 2048-bucket index
 // on the top 11 hash bits (first sketch rank of every bucket), so the rank search of a reference minimizer is a lookup
-// plus a short binary search inside one bucket instead of log2(s) steps.  Same codes as L2ClassifyFn.
-static const int CLS_BUCKET_BITS = 11, CLS_BUCKETS = 1 << CLS_BUCKET_BITS;
+// plus a short binary search inside one bucket instead of log2(s) steps.  Same codes as L2ClassifyFn.  2048 buckets (CLS_BUCKET_BITS = 11): 4096 / 8192
+// buckets measured 7.3 / 10.1 ms against 6.4 (the per-read fill and the lost residency outweigh the shorter searches).
 // PRUNE: the warp's 32 lanes hold one group of 32 span elements: two warp-wide adds of packed 6-bit fields count the prune pass's
 // indicators (prune_count); lane 0 writes the group's record {count words 0 and 1, position of its first element, -} for
 // l2_prune_warp_kernel.  (Deciding inside this kernel cost four barriers per candidate: 8.0 ms against 4.9 without pruning.)
-template <bool PRUNE>
+template <bool PRUNE, int CLS_BUCKET_BITS>
 __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, int32_t perCta) {
+  constexpr int CLS_BUCKETS = 1 << CLS_BUCKET_BITS;
   extern __shared__ uint32_t smq[];
   __shared__ uint16_t bstart[CLS_BUCKETS + 2];
   const int lane = threadIdx.x & 31;
@@ -2252,15 +2253,14 @@ struct Mapper {
                           fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, cHits.p, prune ? grpSum.p : nullptr};
 #ifndef MM_HOST_EMU
           if (fast) {
-            if (rt.first((const void*)l2_classify_smem_kernel<false>)) {
-              MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-              MM_CUDA(cudaFuncSetAttribute(l2_classify_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            }
             // contiguous runs of candidates per CTA, ~8 waves of CTAs so that uneven runs average out
             int64_t g = (int64_t)rt.sm_count * 64; if (g > nc) g = nc;
             int32_t perCta = (int32_t)((nc + g - 1) / g); g = (nc + perCta - 1) / perCta;
-            if (prune) l2_classify_smem_kernel<true><<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
-            else l2_classify_smem_kernel<false><<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
+            auto launch = [&](auto kern) {
+              if (rt.first((const void*)kern)) MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+              kern<<<(int)g, 128, (size_t)(maxSketch > 0 ? maxSketch : 1) * 4, rt.stream>>>(cf, perCta);
+            };
+            if (prune) launch(l2_classify_smem_kernel<true, 11>); else launch(l2_classify_smem_kernel<false, 11>);
             MM_CUDA(cudaGetLastError());
             rt.launches++;
           } else
