@@ -10,7 +10,7 @@ import shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
-TAG = "r2h4"
+TAG = "r2z"
 
 
 def last_json(fn):
@@ -76,7 +76,7 @@ def main():
     md = ["# Round 2 — profiles and measurements (1 x B200 unless stated; scripts `profiles/r2_run_*.sh`)", ""]
     b = last_json(f"{TAG}_bench.json")
     if b:
-        md += ["## The bench line of the final tree (`bench.py --steps 20 --warmup 5`, call H)", "",
+        md += ["## The bench line of the final tree (`bench.py --steps 20 --warmup 5`, call Z)", "",
                f"`value` {b['value']:.0f} Mbp/s ({b['ms_per_step']:.2f} ms/step), `e2e` {b['e2e']['value']:.0f} Mbp/s, {b['gpu_launches']} launches in the timed region, "
                f"SM clock {b['clocks']['sm_mhz']:.0f} / {b['clocks']['sm_max_mhz']} MHz, throttle reasons {b['clocks']['reasons']}.", "",
                "| kernel / stage | ms | algorithmic GB (SURVEY 8d) | GB/s | fraction of 6549.8 GB/s | other roof |", "|---|---|---|---|---|---|"]
@@ -89,15 +89,17 @@ def main():
         t, agg, tot = launch_table(lp)
         md += ["## Launch list of one config-2 step (`ncu --metrics gpu__time_duration.sum --clock-control none`, `profiles/r2_launches_config2.csv`)", "", t, ""]
         if b:
-            k5b = next((v[1] for k, v in agg.items() if "l2_sweep_band" in k), 0)
-            md += [f"Share check: K5b is {100 * k5b / tot:.1f} % of the launch list and {100 * b['roofline']['kernels']['K5b l2_sweep_band_kernel']['ms'] / b['detail']['kernel_ms_per_step']:.1f} % of the "
+            dom = b["roofline"]["kernel"]; pat = dom.split()[1].replace("_kernel", "")
+            kd = next((v[1] for k, v in agg.items() if pat in k), 0)
+            md += [f"Share check: the dominant kernel of the bench line ({dom}) is {100 * kd / tot:.1f} % of the launch list and {100 * b['roofline']['kernels'][dom]['ms'] / b['detail']['kernel_ms_per_step']:.1f} % of the "
                    f"CUDA-event kernel time of a bench step ({b['detail']['kernel_ms_per_step']:.1f} ms).", ""]
     rp = os.path.join(G, f"{TAG}_full_raw.csv")
-    traffic = {"workload": "config2", "source": f"profiles/r2_full_raw.csv: ncu --set full --clock-control none, one step of bench.py --profile-step (round 2, call H)"}
+    traffic = {"workload": "config2", "source": f"profiles/r2_full_raw.csv: ncu --set full --clock-control none, one step of bench.py --profile-step (round 2, call Z)"}
     if os.path.exists(rp):
         shutil.copy(rp, os.path.join(P, "r2_full_raw.csv"))
-        t, tr = metric_block(rp, {"sketch_blockmin": "K1 sketch_blockmin_kernel", "l1_probe_tma": "K4 l1_probe_tma_kernel", "l1_filter_gather16": "K4 l1_filter_gather16_kernel",
-                                  "l2_classify_smem": "K5a l2_classify_smem_kernel", "l2_sweep_band": "K5b l2_sweep_band_kernel"})
+        t, tr = metric_block(rp, {"sketch_blockmin": "K1 sketch_blockmin_kernel", "read_sketch_block_kernel<(int)4": "K3 read_sketch_block_kernel<4>",
+                                  "l1_probe_filter": "K4 l1_probe_filter_kernel", "l2_classify_smem": "K5a l2_classify_smem_kernel",
+                                  "l2_prune_warp": "K5p l2_prune_warp_kernel", "l2_sweep_band": "K5b l2_sweep_band_kernel"})
         traffic.update(tr)
         md += ["## `ncu --set full` of the dominant kernels (`profiles/r2_full_raw.csv` = the raw page)", "", t]
         json.dump(traffic, open(os.path.join(P, "r2_traffic.json"), "w"), indent=1)
@@ -112,16 +114,25 @@ def main():
           ("band 128, ring 4, 16 warps (call A build)", "r2a_bench_b128_r4_c0.json"), ("band 128, ring 4, 2 CTAs x 12 warps, 80 registers (call A build)", "r2a_bench_b128_r4_c1.json"),
           ("window skipping ON (call G)", "r2g_bench.json"), ("window skipping off, same build (call G)", "r2g_bench_noskip.json"),
           ("hash table load 0.25 (call B)", "r2b_bench.json"), ("hash table load 0.5, same build (call B)", "r2b_bench_mult2.json"),
-          ("L1 filter: one list per 8 lanes (call C)", "r2c_bench_n1.json"), ("L1 filter: flattened walk, same build (call C)", "r2c_bench_flat.json")]
-    md += ["## A/B measurements (config 2, CUDA events inside `bench.py`)", "", "| variant | ms/step | K5a ms | K5b ms | L1 stage ms | `value` Mbp/s |", "|---|---|---|---|---|---|"]
+          ("L1 filter: one list per 8 lanes (call C)", "r2c_bench_n1.json"), ("L1 filter: flattened walk, same build (call C)", "r2c_bench_flat.json"),
+          ("K4 as two kernels (call L)", "r2l_bench_twokernels.json"), ("K4 fused, same build (call L)", "r2l_bench.json"),
+          ("K3 radix 4 / 5 / 6 bits per pass (call M)", "r2m_k3radix4.json"), ("", "r2m_k3radix5.json"), ("", "r2m_k3radix6.json"),
+          ("window pruning, ladder of 16 ranks + separate kernel, 4096 starts / segment (call N)", "r2n_bench.json"), ("no pruning, same build (call N)", "r2n_bench_noprune.json"),
+          ("pruned, 256 window starts / segment (call P)", "r2p_seg256.json"), ("pruned, 512 (call P)", "r2p_seg512.json"), ("pruned, 1024 (call P)", "r2p_seg1024.json"), ("pruned, 2048 (call P)", "r2p_seg2048.json"),
+          ("prune decision inside K5a, ballots (call Q)", "r2q_bench.json"), ("the same, REDUX counts + packed prefix pairs (call R)", "r2r2_bench.json"),
+          ("prune decision in its own light kernel (call T)", "r2t_bench.json"), ("the same with DMA staging (e2e) (call T)", "r2t_bench_dma.json"),
+          ("cooperative first-window build in K5b (call U)", "r2u_bench.json"),
+          ("K5b ring 4 x 12 warps (call V)", "r2v_ring4_w12.json"), ("K5b ring 4 x 16 warps (call V)", "r2v_ring4_w16.json"), ("K5b ring 2 x 16 warps (call V)", "r2v_ring2_w16.json"),
+          ("K5a 4096 buckets (call W)", "r2w_bits12.json"), ("K5a 8192 buckets (call W)", "r2w_bits13.json"), ("K5a buckets on 1 - (1 - x)^32 (call X)", "r2x_bench.json")]
+    md += ["## A/B measurements (config 2, CUDA events inside `bench.py`)", "", "| variant | ms/step | K5a ms | K5b ms | L1 stage ms | `value` Mbp/s | `e2e` Mbp/s |", "|---|---|---|---|---|---|---|"]
     for name, fn in ab:
         d = last_json(fn)
         if d:
             st = d["detail"]["stage_ms"]
-            md.append(f"| {name} | {d['ms_per_step']:.2f} | {st['l2_classify_ms']:.2f} | {d['roofline']['kernels']['K5b l2_sweep_band_kernel']['ms']:.2f} | {st['l1_probe_ms']:.2f} | {d['value']:.0f} |")
+            md.append(f"| {name or fn} | {d['ms_per_step']:.2f} | {st['l2_classify_ms']:.2f} | {d['roofline']['kernels']['K5b l2_sweep_band_kernel']['ms']:.2f} | {st['l1_probe_ms']:.2f} | {d['value']:.0f} | {d['e2e']['value']:.0f} |")
     md.append("")
     # multi-GPU
-    md += ["## Multi-GPU (calls D: 2 x B200, E: 8 x B200)", "", "| N | `value` Mbp/s | ms/step | `e2e` | config 3 (1 M reads) | contig shards `value` / ms | contig shards config 3 | config 5 slice ms/step |", "|---|---|---|---|---|---|---|---|"]
+    md += ["## Multi-GPU (N = 1: call Z; N = 2 / 8: calls D / E, the build of call H, before the window pruning)", "", "| N | `value` Mbp/s | ms/step | `e2e` | config 3 (1 M reads) | contig shards `value` / ms | contig shards config 3 | config 5 slice ms/step |", "|---|---|---|---|---|---|---|---|"]
     for n, fn, c5 in ((1, f"{TAG}_bench.json", "r2b_config5.json"), (2, "r2d2_bench_n2.json", "r2c_config5_n2.json"), (8, "r2e_bench_n8.json", "r2e_config5_n8.json")):
         d = last_json(fn); c = last_json(c5)
         if d:
@@ -131,10 +142,13 @@ def main():
                       + (f"{sc['value']:.0f} / {sc['ms_per_step']:.1f}" if "value" in sc else "—") + " | " + (f"{c3s['value']:.0f}" if "value" in c3s else "—") + " | "
                       + (f"{c['ms_per_step']:.0f}" + (f" (check: {c['detail']['check']})" if c['detail'].get('check') else "") if c else "—") + " |")
     md.append("")
-    c4 = last_json("r2b_config4.json")
-    if c4:
+    for c4fn, c4title in (("r2b_config4.json", "## Config 4 at full size (`bench.py --workload config4`, call B, before the window pruning)"),
+                          (f"{TAG}_config4_100k.json", "## Config 4 on 100 k reads, final tree (`bench.py --workload config4 --reads 100000`, call Z)")):
+        c4 = last_json(c4fn)
+        if not c4:
+            continue
         dd = c4["detail"]
-        md += ["## Config 4 at full size (`bench.py --workload config4`, call B)", "",
+        md += [c4title, "",
                f"{dd['reads']} reads, {dd['mappings']} mappings ({dd['mappings_per_read']:.1f} per read), T = {dd['strains']}; EM {dd['em_rounds']} rounds = {dd['em_ms_total']:.1f} ms = "
                f"{dd['em_ms_per_round']:.3f} ms/round = {dd['em_GBps']:.0f} GB/s = {dd['em_frac_of_hbm_peak']:.3f} of the HBM peak; the reference's stopping rule needs "
                f"{dd['rounds_to_reference_stopping_rule']} rounds; mapping {dd['map_s']:.1f} s; whole workload {c4['value']:.0f} Mbp/s.", ""]
