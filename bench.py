@@ -751,8 +751,11 @@ def config5_run(args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, ba
     common = dict(dev_ptr=r_asc.data_ptr(), offsets=r_off, contig_len=contig_len, contig_taxon=contig_taxon, n_taxa=n_taxa, perc_identity=PI,
                   min_read_len=wl["min_read_len"])
 
+    st5 = {}
+
     def run():
-        return pipeline.map_and_classify_streamed(ctx, build_chunk, list(range(rank, n_chunks, world)), n_chunks, all_gather, read_range=(lo, hi), **common)
+        st5.clear()
+        return pipeline.map_and_classify_streamed(ctx, build_chunk, list(range(rank, n_chunks, world)), n_chunks, all_gather, read_range=(lo, hi), stats=st5, **common)
     setup_s = time.time() - t0
     for _ in range(max(1, min(args.warmup, 2))):
         out = run()
@@ -793,7 +796,7 @@ def config5_run(args, wl, torch, dist, dev, ctx, capi, pipeline, world, rank, ba
                        "thresholds": "reference --maxmemory chain (histogram and threshold carried from chunk to chunk, winSketch.hpp:302-304,452-495)",
                        "chunks_with_finite_threshold": finite, "threshold_values": sorted(set(int(v) for v in thr.values())),
                        "reads": n, "mappings_this_rank": int(out["classify"]["n_mappings"]), "em_iters": int(out["classify"]["em_iters"]),
-                       "setup_s": setup_s, "check": check,
+                       "setup_s": setup_s, "check": check, "map_stage_ms_last_step": {k_: round(v, 1) for k_, v in st5.get("map_sum_ms", {}).items()},
                        "timed_region": "per step: every chunk of this rank built from the device-resident DB text, settled, mapped against all reads, freed; "
                                        "mappings exchanged and merged by (read, contig) on the device; mapq, EM (all-reduce per round); one D2H"}}
 

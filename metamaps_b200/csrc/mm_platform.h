@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 #include <list>
+#include <map>
+#include <mutex>
 #include <set>
 
 #ifdef MM_HOST_EMU
@@ -87,6 +89,28 @@ struct Runtime {
 };
 
 // ---- memory --------------------------------------------------------------------------------------
+#ifndef MM_HOST_EMU
+// Freed device blocks of 1 MB and more are kept (per device, up to MM_ALLOC_CACHE_GB, default 16) and handed out again to requests
+// of about their size: cudaMalloc / cudaFree of GB-sized blocks cost milliseconds each with 100 GB in use, which is what a
+// chunk-streamed reference (one index built and freed per chunk) and growing scratch buffers spend their time on otherwise
+// (config-5 slice: 1.3-3.2 s per step from run to run with the same 0.5 s of kernels).  A block is cached only after a device
+// synchronisation (what cudaFree does implicitly), so no kernel of any stream can still be using it when it is handed out again.
+struct DevCache {
+  struct Dev { std::multimap<size_t, void*> free; size_t cached = 0; };
+  std::mutex m;
+  std::map<int, Dev> dev;
+  std::map<void*, std::pair<int, size_t>> live;         // block -> (device, size) of every block this allocator handed out
+  size_t cap;
+  DevCache() { const char* e = getenv("MM_ALLOC_CACHE_GB"); cap = (size_t)((e ? atof(e) : 16.0) * (double)(1ull << 30)); }
+  static DevCache& get() { static DevCache* c = new DevCache(); return *c; }       // never destroyed: the CUDA context may be gone at exit
+  static size_t round_up(size_t b) {                    // sixteenths of the power of two below the size (<= 6 % slack), 2 MB at least
+    size_t p2 = 1; while ((p2 << 1) <= b) p2 <<= 1;
+    size_t q = p2 >> 4; if (q < ((size_t)2 << 20)) q = (size_t)2 << 20;
+    return (b + q - 1) / q * q;
+  }
+  void flush(Dev& d) { for (auto& kv : d.free) cudaFree(kv.second); d.free.clear(); d.cached = 0; cudaGetLastError(); }
+};
+#endif
 inline void* dev_alloc(size_t bytes) {
   if (bytes == 0) bytes = 16;
 #ifdef MM_HOST_EMU
@@ -94,12 +118,29 @@ inline void* dev_alloc(size_t bytes) {
   if (!p) throw Error(-12, "host-emu alloc failed");
   return p;
 #else
+  DevCache& C = DevCache::get();
+  int dv = 0; cudaGetDevice(&dv);
+  const bool big = bytes >= ((size_t)1 << 20) && C.cap > 0;
+  const size_t want = big ? DevCache::round_up(bytes) : bytes;
+  std::lock_guard<std::mutex> lk(C.m);
+  DevCache::Dev& d = C.dev[dv];
+  if (big) {
+    auto it = d.free.lower_bound(want);
+    if (it != d.free.end() && it->first <= want + want / 4) {
+      void* p = it->second; const size_t sz = it->first;
+      d.free.erase(it); d.cached -= sz;
+      C.live[p] = std::make_pair(dv, sz);
+      return p;
+    }
+  }
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes);
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess && d.cached > 0) { cudaGetLastError(); C.flush(d); e = cudaMalloc(&p, want); }
   if (e != cudaSuccess) {
     cudaGetLastError();
-    throw Error(-12, "cudaMalloc(" + std::to_string(bytes) + " B) failed: " + cudaGetErrorString(e));
+    throw Error(-12, "cudaMalloc(" + std::to_string(want) + " B) failed: " + cudaGetErrorString(e));
   }
+  C.live[p] = std::make_pair(dv, want);
   return p;
 #endif
 }
@@ -108,6 +149,29 @@ inline void dev_free(void* p) {
 #ifdef MM_HOST_EMU
   free(p);
 #else
+  DevCache& C = DevCache::get();
+  std::unique_lock<std::mutex> lk(C.m);
+  auto it = C.live.find(p);
+  if (it != C.live.end()) {
+    const int dv = it->second.first; const size_t sz = it->second.second;
+    C.live.erase(it);
+    DevCache::Dev& d = C.dev[dv];
+    if (sz >= ((size_t)1 << 20) && d.cached + sz <= C.cap) {
+      lk.unlock();
+      int cur = 0; cudaGetDevice(&cur);
+      if (cur != dv) cudaSetDevice(dv);
+      const cudaError_t es = cudaDeviceSynchronize();   // as cudaFree would: nothing in flight may still touch the block
+      if (cur != dv) cudaSetDevice(cur);
+      if (es == cudaSuccess) {
+        lk.lock();
+        d.free.emplace(sz, p); d.cached += sz;
+        return;
+      }
+      cudaGetLastError();
+      lk.lock();
+    }
+  }
+  lk.unlock();
   cudaError_t e = cudaFree(p);
   if (e != cudaSuccess) { fprintf(stderr, "[metamaps_b200] cudaFree(%p) failed: %s\n", p, cudaGetErrorString(e)); cudaGetLastError(); }
 #endif

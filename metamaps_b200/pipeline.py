@@ -253,6 +253,10 @@ def map_and_classify_streamed(ctx: capi.Context, build_chunk, chunk_ids: list, n
             gpu_ms += res["gpu_ms"]; launches += res["launches"]
             if stats is not None:
                 stats["map"] = res["stats"]
+                acc = stats.setdefault("map_sum_ms", {})
+                for k_, v in res["stats"].items():
+                    if k_.endswith("_ms"):
+                        acc[k_] = acc.get(k_, 0.0) + float(v)
             ctx.classify_add(ix.first_contig)
             if summary is None:
                 summary = dict(res["summary"])
