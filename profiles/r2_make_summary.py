@@ -132,13 +132,15 @@ def main():
             md.append(f"| {name or fn} | {d['ms_per_step']:.2f} | {st['l2_classify_ms']:.2f} | {d['roofline']['kernels']['K5b l2_sweep_band_kernel']['ms']:.2f} | {st['l1_probe_ms']:.2f} | {d['value']:.0f} | {d['e2e']['value']:.0f} |")
     md.append("")
     # multi-GPU
-    md += ["## Multi-GPU (N = 1: call Z; N = 2 / 8: calls D / E, the build of call H, before the window pruning)", "", "| N | `value` Mbp/s | ms/step | `e2e` | config 3 (1 M reads) | contig shards `value` / ms | contig shards config 3 | config 5 slice ms/step |", "|---|---|---|---|---|---|---|---|"]
-    for n, fn, c5 in ((1, f"{TAG}_bench.json", "r2b_config5.json"), (2, "r2d2_bench_n2.json", "r2c_config5_n2.json"), (8, "r2e_bench_n8.json", "r2e_config5_n8.json")):
-        d = last_json(fn); c = last_json(c5)
+    md += ["## Multi-GPU (final tree: calls Z, AC, AF; calls D / E: the build of call H, before the window pruning)", "", "| N | `value` Mbp/s | ms/step | `e2e` | config 3 (1 M reads) | contig shards `value` / ms | contig shards config 3 | config 5 slice ms/step |", "|---|---|---|---|---|---|---|---|"]
+    for n, fn, c5 in ((1, f"{TAG}_bench.json", "r2ae_c5_1.json"), ("2 (final tree, call AC)", "r2ac_bench_n2.json", "r2ac_config5_n2.json"),
+                      ("8 (final tree, call AF, no extra legs)", "r2af_bench_n8.json", None), ("8, zero-copy staging (call AF)", "r2af_bench_n8_zerocopy.json", None),
+                      ("2 (call D)", "r2d2_bench_n2.json", "r2c_config5_n2.json"), ("8 (call E)", "r2e_bench_n8.json", "r2e_config5_n8.json")):
+        d = last_json(fn); c = last_json(c5) if c5 else None
         if d:
             ex = d.get("extra", {})
             sc = ex.get("shard_contigs", {}); c3 = ex.get("config3", {}); c3s = ex.get("config3_shard_contigs", {})
-            md.append(f"| {n} | {d['value']:.0f} | {d['ms_per_step']:.2f} | {d['e2e']['value']:.0f} | {c3.get('value', 0):.0f} ({c3.get('seconds', 0):.3f} s) | "
+            md.append(f"| {n} | {d['value']:.0f} | {d['ms_per_step']:.2f} | {d['e2e']['value']:.0f} | " + (f"{c3['value']:.0f} ({c3['seconds']:.3f} s)" if "value" in c3 else "—") + " | "
                       + (f"{sc['value']:.0f} / {sc['ms_per_step']:.1f}" if "value" in sc else "—") + " | " + (f"{c3s['value']:.0f}" if "value" in c3s else "—") + " | "
                       + (f"{c['ms_per_step']:.0f}" + (f" (check: {c['detail']['check']})" if c['detail'].get('check') else "") if c else "—") + " |")
     md.append("")
