@@ -453,3 +453,38 @@ def check_multi_batch_classify(ctx, small):
     assert keep.sum() < len(keep) and s.n_mappings == keep.sum()
     for key in ("read", "seq", "pos", "shared", "identity"):
         assert np.array_equal(top[key], one[key][keep]), key
+
+
+def check_prune_fuzz(make_ctx, monkeypatch, cases):
+    """MM_SWEEP_PRUNE=1 against MM_SWEEP_PRUNE=0 on random repeat-rich references (a fresh context per run: the switch is read at creation)."""
+    from metamaps_b200 import capi, synth
+    rng = np.random.default_rng(20261017)
+    swept = total = 0
+    for case in range(cases):
+        w = int(rng.choice([3, 5, 8, 13, 16, 24])); k = int(rng.choice([12, 14, 16]))
+        L = int(rng.integers(20000, 90000))
+        base = rng.integers(0, 4, L, dtype=np.uint8)
+        for _ in range(int(rng.integers(0, 6))):
+            u = int(rng.integers(50, 2500)); a = int(rng.integers(0, L - u)); b = int(rng.integers(0, L - u))
+            seg = base[a:a + u].copy(); m = rng.random(u) < rng.choice([0.0, 0.01, 0.05]); seg[m] = (seg[m] + 1) % 4
+            base[b:b + u] = seg
+        contigs = [base]
+        for _ in range(int(rng.integers(0, 3))):
+            c = base.copy(); m = rng.random(L) < rng.choice([0.002, 0.01, 0.03]); c[m] = (c[m] + rng.integers(1, 4, int(m.sum()))) % 4
+            a = int(rng.integers(0, L // 2)); contigs.append(c[a:a + int(rng.integers(L // 4, L // 2))])
+        db = synth.SynthDB([f"C{i}|kraken:taxid|{i + 1}|x" for i in range(len(contigs))], [str(i + 1) for i in range(len(contigs))], contigs)
+        _, reads, _ = synth.make_reads(db, int(rng.integers(1, 1 << 30)), int(rng.integers(10, 30)), int(rng.choice([1500, 3000, 6000])),
+                                       err=float(rng.choice([0.0, 0.02, 0.08, 0.15])))
+        asc = [synth.codes_to_ascii(c) for c in contigs]; rasc = [synth.codes_to_ascii(r) for r in reads]
+        out = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("MM_SWEEP_PRUNE", flag)
+            ctx = make_ctx()
+            ix = build_index(ctx, asc, k, w)
+            out[flag] = capi.map_reads(ctx, ix, rasc, 80.0, 1000)
+            if flag == "1":
+                st = ctx.last_map_stats(); swept += st["window_starts_swept"]; total += st["window_starts"]
+            ix.close(); ctx.close()
+        for key in ("seq", "start", "end", "shared", "valid", "votes", "optStart", "optEnd", "pos", "accepted"):
+            assert np.array_equal(out["1"][key], out["0"][key]), (case, key, k, w)
+    assert 0 < swept < 0.8 * total, (swept, total)

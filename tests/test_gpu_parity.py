@@ -374,3 +374,9 @@ def test_cli_maxmemory_chunk_loop_matches_reference_fixture(tmp_path):
     assert os.path.exists(build.HOST_BIN), "metamaps_b200/metamaps not built"
     thr = cli_common.check_maxmemory_golden(build.HOST_BIN, str(tmp_path))
     assert [t.split(">= ")[1].split()[0] for t in thr] == ["4", "7", "23"]
+
+
+def test_window_pruning_fuzz(monkeypatch):
+    """The prune pass on the device (K5a's group counts, l2_prune_warp_kernel) against the sweep over every window start, on random
+    repeat-rich references with k in {12, 14, 16}, w from 3 to 24 and reads with 0 - 15 % errors."""
+    common.check_prune_fuzz(lambda: capi.Context(0), monkeypatch, 24)

@@ -204,3 +204,11 @@ def test_window_pruning_changes_nothing_but_the_work(oracle, monkeypatch):
     for key in ("seq", "pos", "shared", "votes", "accepted", "valid", "optStart", "optEnd"):
         assert np.array_equal(got["0"][0][key], got["1"][0][key]), key
     assert got["1"][1] < 0.4 * got["0"][1], (got["0"][1], got["1"][1])
+
+
+def test_window_pruning_fuzz(monkeypatch):
+    """Random references with tandem / dispersed repeats and near-identical contigs (duplicate hashes inside windows), k in {12, 14, 16},
+    w from 3 to 24, reads with 0 - 15 % errors: the pruned sweep and the sweep over every window start agree on every output."""
+    from tests.conftest import build_emu
+    lib = capi.load(build_emu())
+    common.check_prune_fuzz(lambda: capi.Context(0, lib), monkeypatch, 16)
