@@ -858,7 +858,8 @@ MM_HD uint32_t dup_event_flags(const uint32_t* miWs, const uint2* dupRB, const u
 // counts up to a group at either end (rounded to the safe side).  The lower bound is taken on the first window of every group of
 // window starts (an evaluated window: its end lies inside the span), the upper bound on the union of a group's windows; the
 // sweep (K5b) covers the hull of the groups whose upper bound reaches the best lower bound.
-static const int PR_GMAX = 256;            // groups per candidate the prune pass takes (8192 span elements); longer spans are swept whole
+static const int PR_GMAX = 512;            // most groups per candidate the prune pass can take (MM_PRUNE_GMAX; default 256 = 8192 span elements:
+                                           // pruning the longer spans too visits 7 % fewer window starts but K5b takes 5.1 instead of 4.6 ms, call AK)
 static const int PR_NS = 7;                // series: see PruneView
 struct PruneThr { int32_t i0, i1, i1b; };  // upper-bound rank; lower-bound ranks (i1 from the estimate, i1b < i1 holds whatever matches)
 MM_HD int32_t prune_istar_est(int32_t s, int32_t win, int32_t m) {
@@ -941,12 +942,12 @@ MM_HD int32_t prune_window_group(const uint32_t* pos, int32_t stride, int32_t nG
 struct L2PruneFn {
   const uint2* ev; const int64_t* evOff; int64_t evBase; int64_t cand0;
   const int64_t* beg0; const int64_t* fe; const int32_t* cRead; const int32_t* sOf; const int32_t* readLen; const int32_t* cHits; int k, w;
-  int32_t* swB0; int32_t* swB1;                              // indexed by the candidate's number within the pass
+  int32_t* swB0; int32_t* swB1; int32_t gmax;                // indexed by the candidate's number within the pass
   void operator()(int64_t ci) const {
     const int64_t c = cand0 + ci;
     const int32_t n = (int32_t)(evOff[c + 1] - evOff[c]), nG = (n + 31) >> 5;
     swB0[ci] = 0; swB1[ci] = 0x7fffffff;
-    if (nG < 1 || nG > PR_GMAX) return;
+    if (nG < 1 || nG > gmax) return;
     const int32_t r = cRead[c], s = sOf[r], cmw = readLen[r] - (w - 1) - (k - 1);
     const PruneThr th = prune_thresholds(s, (int32_t)(fe[c] - beg0[c]), cHits ? cHits[c] : 0);
     const uint2* e = ev + (evOff[c] - evBase);
@@ -993,30 +994,39 @@ __global__ void __launch_bounds__(PRUNE_WARPS * 32) l2_prune_warp_kernel(L2Prune
       const int32_t r = a.cRead[c], s = a.sOf[r], cmw = a.readLen[r] - (a.w - 1) - (a.k - 1);
       const PruneThr th = prune_thresholds(s, (int32_t)(a.fe[c] - a.beg0[c]), a.cHits ? a.cHits[c] : 0);
       const uint4* G = a.grp + (((a.evOff[c] - a.evBase) >> 5) + ci);
-      const int32_t J = (nG + 31) >> 5, g0 = J * lane;             // J <= 8
-      uint32_t pr[4][8];
+      const int32_t J = (nG + 31) >> 5, g0 = J * lane;             // lane l owns groups [J l, J l + J)
+      auto unpack = [](const uint4& v, uint32_t* o) {
+        o[0] = (v.x & 63u) | (((v.x >> 6) & 63u) << 16);           // A, B
+        o[1] = ((v.x >> 12) & 63u) | (((v.x >> 18) & 63u) << 16);  // C, D
+        o[2] = ((v.x >> 24) & 63u) | ((v.y & 63u) << 16);          // M, C2
+        o[3] = (v.y >> 6) & 63u;                                   // D2
+      };
       uint32_t tot[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
+      for (int32_t j = 0; j < J; j++) {
         const int32_t g = g0 + j;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (j < J && g < nG) { v = __ldg(G + g); POS[g] = v.z; }
-        tot[0] += (v.x & 63u) | (((v.x >> 6) & 63u) << 16);        // A, B
-        tot[1] += ((v.x >> 12) & 63u) | (((v.x >> 18) & 63u) << 16);   // C, D
-        tot[2] += ((v.x >> 24) & 63u) | ((v.y & 63u) << 16);       // M, C2
-        tot[3] += (v.y >> 6) & 63u;                                // D2
+        if (g < nG) {
+          const uint4 v = __ldg(G + g); POS[g] = v.z;
+          uint32_t o[4]; unpack(v, o);
 #pragma unroll
-        for (int q = 0; q < 4; q++) pr[q][j] = tot[q];
+          for (int q = 0; q < 4; q++) tot[q] += o[q];
+        }
       }
+      uint32_t run[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         uint32_t inc = tot[q];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-        const uint32_t base = inc - tot[q];
+        run[q] = inc - tot[q];
         if (lane == 0) P[q * LD] = 0;
+      }
+      for (int32_t j = 0; j < J; j++) {                            // second pass over the lane's own records (L1)
+        const int32_t g = g0 + j;
+        if (g < nG) {
+          uint32_t o[4]; unpack(__ldg(G + g), o);
 #pragma unroll
-        for (int j = 0; j < 8; j++) { const int32_t g = g0 + j; if (j < J && g < nG) P[q * LD + g + 1] = base + pr[q][j]; }
+          for (int q = 0; q < 4; q++) { run[q] += o[q]; P[q * LD + g + 1] = run[q]; }
+        }
       }
       __syncwarp();
       for (int32_t g = lane; g < nG; g += 32) H[g] = (uint16_t)prune_window_group(POS, 1, nG, g, cmw);
@@ -1047,7 +1057,7 @@ struct L2ClassifyFn {
   const int64_t* fe; const int64_t* le; const int32_t* readLen; const uint2* dupRB; const uint64_t* dupLinks; int64_t n_dup; int k, w;
   // the device kernel also counts the prune pass's indicators: one record per group of 32 span elements, candidate c's groups start
   // at grp_base(c) (null: no pruning); cHits: L1 hits of the candidate (estimate of its best window's matches)
-  const int32_t* cHits; uint4* grp;
+  const int32_t* cHits; uint4* grp; int32_t gmax;          // gmax: groups per candidate the prune pass takes (<= PR_GMAX)
   MM_HD int64_t grp_base(int64_t c) const { return ((ldg(evOff + c) - evBase) >> 5) + (c - cand0); }
   MM_HD void operator()(int64_t t) const {
     int64_t c = cand0 + upper_bound_idx(evOff + cand0, nCand + 1, t + evBase) - 1;
@@ -1101,7 +1111,7 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
     const int64_t e0 = a.evOff[c] - a.evBase; const int32_t n = (int32_t)(a.evOff[c + 1] - a.evOff[c]);
     const int64_t fe = a.fe[c], le = a.le[c]; const int32_t cmw = a.readLen[r] - (a.w - 1) - (a.k - 1);
     const int32_t nG = (n + 31) >> 5;
-    const bool doPrune = PRUNE && nG >= 1 && nG <= PR_GMAX;        // CTA-uniform
+    const bool doPrune = PRUNE && nG >= 1 && nG <= a.gmax;         // CTA-uniform
     PruneThr th{0, 0, 0};
     if (doPrune) th = prune_thresholds(s, (int32_t)(fe - b0), a.cHits ? a.cHits[c] : 0);
     const int64_t gb = PRUNE ? a.grp_base(c) : 0;
@@ -1883,7 +1893,7 @@ struct Mapper {
   DevBuf<int64_t> itemOff; DevBuf<int32_t> itemCand, itemB0, itemB1, segCnt, swB0, swB1, cHits; DevBuf<int64_t> cHitLo, cHitHi; DevBuf<BandPart> bandParts; std::vector<int64_t> hEvSpan;
   // K5a also bounds every window's shared count and K5b sweeps only the window starts that can hold the optimum (l2 prune, PruneView);
   // MM_SWEEP_PRUNE=0 sweeps every window start as the reference does
-  DevBuf<uint4> grpSum; bool sweepPrune = true, prunedPass = false;
+  DevBuf<uint4> grpSum; bool sweepPrune = true, prunedPass = false; int32_t pruneGmax = 256;
   DevBuf<uint2> probeOut;      // (CSR start, count) of every probe of the batch: l1_probe_filter_kernel's spill between its two passes
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
@@ -1896,6 +1906,7 @@ struct Mapper {
     if (const char* e = getenv("MM_SWEEP_WIDE_FROM")) { int v = atoi(e); if (v >= 1) sweepWideFrom = v; }
     if (const char* e = getenv("MM_SWEEP_SEG")) { int v = atoi(e); if (v >= 64) sweepSeg = v; }
     if (const char* e = getenv("MM_SWEEP_PRUNE")) sweepPrune = atoi(e) != 0;
+    if (const char* e = getenv("MM_PRUNE_GMAX")) { int v = atoi(e); if (v >= 1 && v <= PR_GMAX) pruneGmax = v; }
     if (const char* e = getenv("MM_SWEEP")) sweepMode = !strcmp(e, "full") ? 1 : !strcmp(e, "global") ? 2 : 0;
   }
 
@@ -2259,7 +2270,7 @@ struct Mapper {
           if (prune) { swB0.ensure((size_t)nc + 1); swB1.ensure((size_t)nc + 1); grpSum.ensure((size_t)(nEv >> 5) + (size_t)nc + 4); }
           prunedPass = prune;
           L2ClassifyFn cf{ix.miHash.p, ix.miWs.p, ix.dupBits.p, evOff.p, c0, nc, hEv[(size_t)c0], beg0.p, cRead.p, qHash.p, qOff.p, sOf.p, ev.p,
-                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, cHits.p, prune ? grpSum.p : nullptr};
+                          fe.p, le.p, readLen.p, ix.dupRB.p, ix.dupLinks.p, ix.n_dup, k, w, cHits.p, prune ? grpSum.p : nullptr, pruneGmax};
 #ifndef MM_HOST_EMU
           if (fast) {
             // contiguous runs of candidates per CTA, ~8 waves of CTAs so that uneven runs average out
@@ -2279,9 +2290,9 @@ struct Mapper {
         if (prunedPass) {
           StageTimer tp(rt, &st.ms[12]);
 #ifdef MM_HOST_EMU
-          foreach(rt, nc, L2PruneFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, cRead.p, sOf.p, readLen.p, cHits.p, k, w, swB0.p, swB1.p});
+          foreach(rt, nc, L2PruneFn{ev.p, evOff.p, hEv[(size_t)c0], c0, beg0.p, fe.p, cRead.p, sOf.p, readLen.p, cHits.p, k, w, swB0.p, swB1.p, pruneGmax});
 #else
-          int32_t gmax = (maxSpan + 31) >> 5; if (gmax > PR_GMAX) gmax = PR_GMAX; if (gmax < 1) gmax = 1;
+          int32_t gmax = (maxSpan + 31) >> 5; if (gmax > pruneGmax) gmax = pruneGmax; if (gmax < 1) gmax = 1;
           const size_t smem = prune_warp_words(gmax) * 4 * PRUNE_WARPS;
           if (rt.first((const void*)l2_prune_warp_kernel)) MM_CUDA(cudaFuncSetAttribute(l2_prune_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prune_warp_words(PR_GMAX) * 4 * PRUNE_WARPS)));
           int64_t g = (nc + PRUNE_WARPS - 1) / PRUNE_WARPS; if (g > (int64_t)rt.sm_count * 8) g = (int64_t)rt.sm_count * 8;
