@@ -10,7 +10,8 @@ import shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
-TAG = "r2z"
+TAG = "r2z"          # ncu --set full raw / source pages, config 4 leg (call Z)
+BTAG = "r2al"        # bench line + launch list of the committed tree (call AL)
 
 
 def last_json(fn):
@@ -74,16 +75,16 @@ def metric_block(path, names):
 
 def main():
     md = ["# Round 2 — profiles and measurements (1 x B200 unless stated; scripts `profiles/r2_run_*.sh`)", ""]
-    b = last_json(f"{TAG}_bench.json")
+    b = last_json(f"{BTAG}_bench.json")
     if b:
-        md += ["## The bench line of the final tree (`bench.py --steps 20 --warmup 5`, call Z)", "",
+        md += ["## The bench line of the final tree (`bench.py --gpus 1 --steps 20 --warmup 5`, call AL)", "",
                f"`value` {b['value']:.0f} Mbp/s ({b['ms_per_step']:.2f} ms/step), `e2e` {b['e2e']['value']:.0f} Mbp/s, {b['gpu_launches']} launches in the timed region, "
                f"SM clock {b['clocks']['sm_mhz']:.0f} / {b['clocks']['sm_max_mhz']} MHz, throttle reasons {b['clocks']['reasons']}.", "",
                "| kernel / stage | ms | algorithmic GB (SURVEY 8d) | GB/s | fraction of 6549.8 GB/s | other roof |", "|---|---|---|---|---|---|"]
         for k, v in b["roofline"]["kernels"].items():
             md.append(f"| {k} | {v['ms']:.2f} | {v['bytes'] / 1e9:.2f} | {v['GBps']:.0f} | {v['frac']:.3f} | " + (f"IMAD pipe: {v['imad_frac']:.2f} of its roof ({v['imad_roof_ms']:.2f} ms)" if "imad_frac" in v else "") + " |")
         md += ["", "Extra legs of the same run: " + json.dumps({k: ({kk: vv for kk, vv in v.items() if kk in ("value", "seconds", "em_ms_per_round", "em_GBps", "em_frac_of_hbm_peak", "ratio", "gpu_cli_s", "ref_s", "files_identical", "GBps_per_rank_all_ranks_uploading", "mappings", "rounds_to_reference_stopping_rule")} if isinstance(v, dict) else v) for k, v in b.get("extra", {}).items()}), ""]
-    lp = os.path.join(G, f"{TAG}_launches.csv")
+    lp = os.path.join(G, f"{BTAG}_launches.csv")
     if os.path.exists(lp):
         shutil.copy(lp, os.path.join(P, "r2_launches_config2.csv"))
         t, agg, tot = launch_table(lp)
@@ -123,7 +124,9 @@ def main():
           ("prune decision in its own light kernel (call T)", "r2t_bench.json"), ("the same with DMA staging (e2e) (call T)", "r2t_bench_dma.json"),
           ("cooperative first-window build in K5b (call U)", "r2u_bench.json"),
           ("K5b ring 4 x 12 warps (call V)", "r2v_ring4_w12.json"), ("K5b ring 4 x 16 warps (call V)", "r2v_ring4_w16.json"), ("K5b ring 2 x 16 warps (call V)", "r2v_ring2_w16.json"),
-          ("K5a 4096 buckets (call W)", "r2w_bits12.json"), ("K5a 8192 buckets (call W)", "r2w_bits13.json"), ("K5a buckets on 1 - (1 - x)^32 (call X)", "r2x_bench.json")]
+          ("K5a 4096 buckets (call W)", "r2w_bits12.json"), ("K5a 8192 buckets (call W)", "r2w_bits13.json"), ("K5a buckets on 1 - (1 - x)^32 (call X)", "r2x_bench.json"),
+          ("32-byte slots with inline contig ids (call AH)", "r2ah_bench.json"), ("the same, inline ids ignored (call AI)", "r2ai_inline0.json"),
+          ("prune pass up to 512 groups per candidate (call AK)", "r2ak_g512_1.json"), ("up to 256, same build (call AK)", "r2ak_g256_1.json")]
     md += ["## A/B measurements (config 2, CUDA events inside `bench.py`)", "", "| variant | ms/step | K5a ms | K5b ms | L1 stage ms | `value` Mbp/s | `e2e` Mbp/s |", "|---|---|---|---|---|---|---|"]
     for name, fn in ab:
         d = last_json(fn)
@@ -133,7 +136,7 @@ def main():
     md.append("")
     # multi-GPU
     md += ["## Multi-GPU (final tree: calls Z, AC, AF; calls D / E: the build of call H, before the window pruning)", "", "| N | `value` Mbp/s | ms/step | `e2e` | config 3 (1 M reads) | contig shards `value` / ms | contig shards config 3 | config 5 slice ms/step |", "|---|---|---|---|---|---|---|---|"]
-    for n, fn, c5 in ((1, f"{TAG}_bench.json", "r2ae_c5_1.json"), ("2 (final tree, call AC)", "r2ac_bench_n2.json", "r2ac_config5_n2.json"),
+    for n, fn, c5 in ((1, f"{BTAG}_bench.json", "r2ae_c5_1.json"), ("2 (final tree, call AC)", "r2ac_bench_n2.json", "r2ac_config5_n2.json"),
                       ("8 (final tree, call AF, no extra legs)", "r2af_bench_n8.json", None), ("8, zero-copy staging (call AF)", "r2af_bench_n8_zerocopy.json", None),
                       ("2 (call D)", "r2d2_bench_n2.json", "r2c_config5_n2.json"), ("8 (call E)", "r2e_bench_n8.json", "r2e_config5_n8.json")):
         d = last_json(fn); c = last_json(c5) if c5 else None
