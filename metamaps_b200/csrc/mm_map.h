@@ -523,7 +523,8 @@ template <int PF_CHUNK>
 __global__ void __launch_bounds__(256) l1_probe_filter_kernel(const Slot* table, uint32_t mask, int32_t freqThreshold, const uint32_t* qHash, const int64_t* qOff,
                                                               const int32_t* sOf, const int32_t* minHitsTab, const uint16_t* posSeq16, const uint64_t* posKey,
                                                               HitKeyLayout lay, int32_t n_reads, uint32_t binMask, unsigned long long* cursor, uint64_t* hitsOut,
-                                                              unsigned long long hitsCap, int32_t* keptPerRead, uint32_t cacheCap, uint2* probeOut) {
+                                                              unsigned long long hitsCap, int32_t* keptPerRead, uint32_t cacheCap, uint2* probeOut,
+                                                              unsigned long long* segStart) {
   extern __shared__ __align__(128) uint32_t bins[];            // bins | contig-id cache | chunk keys | chunk counts | chunk starts
   const uint32_t binWords = (binMask + 1) / 2;
   uint16_t* cache = reinterpret_cast<uint16_t*>(bins + binWords);
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(256) l1_probe_filter_kernel(const Slot* table,
     if (local) atomicAdd(&smTotal, local);
     __syncthreads();
     if (threadIdx.x == 0) {
-      smBase = atomicAdd(cursor, (unsigned long long)smTotal); keptPerRead[r] = (int32_t)smTotal;
+      smBase = atomicAdd(cursor, (unsigned long long)smTotal); keptPerRead[r] = (int32_t)smTotal; segStart[r] = smBase;
       atomicAdd(cursor + 1, (unsigned long long)nHits);
       if (smBase + smTotal > hitsCap) { smSkip = 1; cursor[2] = 1ull; }
     }
@@ -708,6 +709,62 @@ __global__ void __launch_bounds__(256) l1_probe_filter_kernel(const Slot* table,
       }
     }
     __syncthreads();
+  }
+}
+#endif
+
+#ifndef MM_HOST_EMU
+// The fused kernel leaves every read's survivors in one contiguous segment (at segStart[r], in no particular order, reads in the order
+// their CTAs finished).  The order the candidate stage needs -- (read, contig, position) -- is a sort WITHIN each segment plus a move of
+// the segment to readHitOff[r] (the prefix sum of the kept counts): a bitonic sort in shared memory by the group that owns the read
+// (a warp for up to SEG_SORT_WARP_CAP keys, a CTA for up to SEG_SORT_CTA_CAP; keys are unique, so any sort gives the radix sort's result)
+// instead of seven passes of the device-wide radix sort over all 52 key bits.  Reads beyond the CTA capacity raise `overflow`: the
+// host then runs the radix sort after all.
+static const int SEG_SORT_WARP_CAP = 1024, SEG_SORT_CTA_CAP = 8192;
+template <bool CTA>
+__device__ __forceinline__ void seg_sort_one(const uint64_t* in, uint64_t* out, uint64_t* buf, int32_t n, int lane, int width) {
+  int32_t P = 32; while (P < n) P <<= 1;
+  for (int32_t i = lane; i < P; i += width) buf[i] = i < n ? in[i] : ~0ull;
+  if (CTA) __syncthreads(); else __syncwarp();
+  for (int32_t k = 2; k <= P; k <<= 1) {
+    for (int32_t j = k >> 1; j > 0; j >>= 1) {
+      for (int32_t t = lane; t < (P >> 1); t += width) {
+        const int32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), x = i | j;
+        const uint64_t a = buf[i], b = buf[x];
+        if ((a > b) == ((i & k) == 0)) { buf[i] = b; buf[x] = a; }
+      }
+      if (CTA) __syncthreads(); else __syncwarp();
+    }
+  }
+  for (int32_t i = lane; i < n; i += width) out[i] = buf[i];
+  if (CTA) __syncthreads(); else __syncwarp();
+}
+__global__ void __launch_bounds__(256) l1_sort_segments_warp_kernel(const uint64_t* in, const unsigned long long* segStart, const int32_t* kept, const int64_t* readHitOff,
+                                                                    int32_t n_reads, uint64_t* out, int32_t* bigList, unsigned long long* bigCount, unsigned long long* readCursor) {
+  extern __shared__ __align__(16) uint64_t segbuf[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t* buf = segbuf + (size_t)wid * SEG_SORT_WARP_CAP;
+  for (;;) {                                     // reads are handed out eight at a time: their survivor counts differ widely
+    unsigned long long r0 = 0;
+    if (lane == 0) r0 = atomicAdd(readCursor, 8ull);
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    if (r0 >= (unsigned long long)n_reads) break;
+    for (int32_t r = (int32_t)r0; r < n_reads && r < (int32_t)r0 + 8; r++) {
+      const int32_t n = kept[r];
+      if (n <= 0) continue;
+      if (n > SEG_SORT_WARP_CAP) { if (lane == 0) bigList[atomicAdd(bigCount, 1ull)] = r; continue; }
+      seg_sort_one<false>(in + segStart[r], out + readHitOff[r], buf, n, lane, 32);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) l1_sort_segments_cta_kernel(const uint64_t* in, const unsigned long long* segStart, const int32_t* kept, const int64_t* readHitOff,
+                                                                   uint64_t* out, const int32_t* bigList, const unsigned long long* bigCount, int32_t* overflow) {
+  extern __shared__ __align__(16) uint64_t segbuf[];
+  const unsigned long long nb = *bigCount;
+  for (unsigned long long b = blockIdx.x; b < nb; b += gridDim.x) {
+    const int32_t r = bigList[b], n = kept[r];
+    if (n > SEG_SORT_CTA_CAP) { if (threadIdx.x == 0) *overflow = 1; continue; }
+    seg_sort_one<true>(in + segStart[r], out + readHitOff[r], segbuf, n, (int)threadIdx.x, (int)blockDim.x);
   }
 }
 #endif
@@ -1894,6 +1951,7 @@ struct Mapper {
   // K5a also bounds every window's shared count and K5b sweeps only the window starts that can hold the optimum (l2 prune, PruneView);
   // MM_SWEEP_PRUNE=0 sweeps every window start as the reference does
   DevBuf<uint4> grpSum; bool sweepPrune = true, prunedPass = false; int32_t pruneGmax = 256;
+  DevBuf<unsigned long long> segStart; DevBuf<int32_t> segBig; bool segSorted = false;
   DevBuf<uint2> probeOut;      // (CSR start, count) of every probe of the batch: l1_probe_filter_kernel's spill between its two passes
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
@@ -2109,7 +2167,7 @@ struct Mapper {
           int perSm = (int)((220 * 1024) / (smem + 2048)); if (perSm > 8) perSm = 8; if (perSm < 1) perSm = 1;
           if (const char* e = getenv("MM_L1_CTAS")) { int v = atoi(e); if (v >= 1 && v <= perSm) perSm = v; }
           const int grid = n_reads < rt.sm_count * perSm ? n_reads : rt.sm_count * perSm;
-          probeOut.ensure((size_t)n_q + 8); keptPerRead.ensure((size_t)n_reads + 2); scal.ensure(4);
+          probeOut.ensure((size_t)n_q + 8); keptPerRead.ensure((size_t)n_reads + 2); scal.ensure(8); segStart.ensure((size_t)n_reads + 2);
           if (hits.cap < (size_t)n_q + 1) hits.ensure((size_t)n_q + 1);          // first guess: one survivor per sketch element; grow-only
           unsigned long long hs[3] = {0, 0, 0};
           for (int attempt = 0; attempt < 2; attempt++) {
@@ -2118,11 +2176,11 @@ struct Mapper {
             if (pfChunk == 512)
               l1_probe_filter_kernel<512><<<grid, 256, smem, rt.stream>>>(ix.table.p, ix.tableMask, ix.freqThreshold, qHash.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p,
                                                                           ix.posKey.p, lay, n_reads, binsN - 1, scal.p, hits.p, (unsigned long long)hits.cap,
-                                                                          keptPerRead.p, (uint32_t)cacheCap, probeOut.p);
+                                                                          keptPerRead.p, (uint32_t)cacheCap, probeOut.p, segStart.p);
             else
               l1_probe_filter_kernel<1024><<<grid, 256, smem, rt.stream>>>(ix.table.p, ix.tableMask, ix.freqThreshold, qHash.p, qOff.p, sOf.p, dMinHits.p, ix.posSeq16.p,
                                                                            ix.posKey.p, lay, n_reads, binsN - 1, scal.p, hits.p, (unsigned long long)hits.cap,
-                                                                           keptPerRead.p, (uint32_t)cacheCap, probeOut.p);
+                                                                           keptPerRead.p, (uint32_t)cacheCap, probeOut.p, segStart.p);
             MM_CUDA(cudaGetLastError());
             rt.launches++;
             tk.stop();
@@ -2135,7 +2193,7 @@ struct Mapper {
           dev_memset(rt, keptPerRead.p + n_reads, 0, sizeof(int32_t));
           pr.exclusive_sum<int32_t, int64_t>(keptPerRead.p, readHitOff.p, (int64_t)n_reads + 1);
           hits2.ensure((size_t)n_hits + 1);
-          fusedDone = true;
+          fusedDone = true; segSorted = true;
         }
       }
 #endif
@@ -2198,7 +2256,27 @@ struct Mapper {
     }
     {
       StageTimer t(rt, &st.ms[3]);
-      pr.sort_keys<uint64_t>(hits.p, hits2.p, n_hits, readBits + lay.seqBits + lay.wsBits);
+      bool sorted = false;
+#ifndef MM_HOST_EMU
+      static const bool segOff = [] { const char* e = getenv("MM_L1_SEGSORT"); return e && atoi(e) == 0; }();
+      if (segSorted && !segOff && n_hits > 0) {            // the fused kernel left one segment per read: sort inside the segments (l1_sort_segments_*)
+        segBig.ensure((size_t)n_reads + 1);
+        dev_memset(rt, scal.p + 4, 0, sizeof(unsigned long long) * 3);       // [4] = big reads, [5] = read cursor, [6] = overflow flag
+        const size_t smW = (size_t)8 * SEG_SORT_WARP_CAP * 8, smC = (size_t)SEG_SORT_CTA_CAP * 8;
+        if (rt.first((const void*)l1_sort_segments_warp_kernel)) {
+          MM_CUDA(cudaFuncSetAttribute(l1_sort_segments_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smW));
+          MM_CUDA(cudaFuncSetAttribute(l1_sort_segments_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smC));
+        }
+        l1_sort_segments_warp_kernel<<<rt.sm_count * 3, 256, smW, rt.stream>>>(hits.p, segStart.p, keptPerRead.p, readHitOff.p, n_reads, hits2.p, segBig.p, scal.p + 4, scal.p + 5);
+        l1_sort_segments_cta_kernel<<<rt.sm_count * 3, 256, smC, rt.stream>>>(hits.p, segStart.p, keptPerRead.p, readHitOff.p, hits2.p, segBig.p, scal.p + 4, (int32_t*)(scal.p + 6));
+        MM_CUDA(cudaGetLastError());
+        rt.launches += 2;
+        unsigned long long ovf = 0; d2h(rt, &ovf, scal.p + 6, sizeof(ovf));
+        sorted = (ovf & 0xffffffffull) == 0;               // a read with more survivors than a CTA sorts: the radix sort below does the whole batch
+      }
+#endif
+      segSorted = false;
+      if (!sorted) pr.sort_keys<uint64_t>(hits.p, hits2.p, n_hits, readBits + lay.seqBits + lay.wsBits);
     }
     {
       StageTimer t(rt, &st.ms[4]);
