@@ -721,17 +721,25 @@ __global__ void __launch_bounds__(256) l1_probe_filter_kernel(const Slot* table,
 // instead of seven passes of the device-wide radix sort over all 52 key bits.  Reads beyond the CTA capacity raise `overflow`: the
 // host then runs the radix sort after all.
 static const int SEG_SORT_WARP_CAP = 1024, SEG_SORT_CTA_CAP = 8192;
+// Bitonic network with every compare-exchange ascending (the first step of a merge pairs i with i ^ (k - 1), the others with i ^ j): the
+// keys beyond n then behave like +infinity at the end of the array, so a pair whose upper index is >= n is skipped and nothing is padded.
 template <bool CTA>
 __device__ __forceinline__ void seg_sort_one(const uint64_t* in, uint64_t* out, uint64_t* buf, int32_t n, int lane, int width) {
-  int32_t P = 32; while (P < n) P <<= 1;
-  for (int32_t i = lane; i < P; i += width) buf[i] = i < n ? in[i] : ~0ull;
+  int32_t P = 2; while (P < n) P <<= 1;
+  for (int32_t i = lane; i < n; i += width) buf[i] = in[i];
   if (CTA) __syncthreads(); else __syncwarp();
-  for (int32_t k = 2; k <= P; k <<= 1) {
-    for (int32_t j = k >> 1; j > 0; j >>= 1) {
+  int lh = 0;                                                  // log2 of half the merge size
+  for (int32_t k = 2; k <= P; k <<= 1, lh++) {
+    const int32_t h = k >> 1;
+    for (int32_t t = lane; t < (P >> 1); t += width) {       // flip step
+      const int32_t base = (t >> lh) << (lh + 1), off = t & (h - 1), i = base + off, x = base + (k - 1 - off);
+      if (x < n) { const uint64_t a = buf[i], b = buf[x]; if (a > b) { buf[i] = b; buf[x] = a; } }
+    }
+    if (CTA) __syncthreads(); else __syncwarp();
+    for (int32_t j = h >> 1; j > 0; j >>= 1) {
       for (int32_t t = lane; t < (P >> 1); t += width) {
         const int32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), x = i | j;
-        const uint64_t a = buf[i], b = buf[x];
-        if ((a > b) == ((i & k) == 0)) { buf[i] = b; buf[x] = a; }
+        if (x < n) { const uint64_t a = buf[i], b = buf[x]; if (a > b) { buf[i] = b; buf[x] = a; } }
       }
       if (CTA) __syncthreads(); else __syncwarp();
     }
