@@ -850,6 +850,72 @@ struct LocusWriteFn {
   }
 };
 
+#ifndef MM_HOST_EMU
+// computeL1CandidateRegions for one read per warp, over the read's sorted hits (same rules as HitFlagFn / LocusHeadFn / LocusWriteFn above,
+// which the host emulation and MM_L1_CAND=legacy still run): hit i opens a window iff hits i and i + minimumHits - 1 lie on one contig
+// less than a read length apart; consecutive windows merge while prev.end >= start.  The warp walks the hits 32 at a time, carrying the
+// last flagged hit across chunks, and writes the read's k-th candidate to scratch slot readHitOff[r] + k; CandGatherFn moves them to
+// their final places once the per-read counts are scanned.  One pass over the hits instead of four kernels and two scans over 28 M flags.
+__global__ void __launch_bounds__(256) l1_candidates_warp_kernel(const uint64_t* hits, const int64_t* readHitOff, const int32_t* sOf, const int32_t* readLen,
+                                                                 const int32_t* minHitsTab, HitDecode dec, int32_t n_reads, int32_t* tSeq, int32_t* tStart, int32_t* tEnd,
+                                                                 int32_t* tLo, int32_t* tHi, int32_t* candCnt, unsigned long long* readCursor) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long r0 = 0;
+    if (lane == 0) r0 = atomicAdd(readCursor, 8ull);
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    if (r0 >= (unsigned long long)n_reads) break;
+    for (int32_t r = (int32_t)r0; r < n_reads && r < (int32_t)r0 + 8; r++) {
+      const int64_t b = readHitOff[r];
+      const int32_t n = (int32_t)(readHitOff[r + 1] - b);
+      if (n <= 0) { if (lane == 0) candCnt[r] = 0; continue; }
+      const int32_t len = readLen[r];
+      int32_t mh = minHitsTab[sOf[r]]; if (mh < 1) mh = 1;
+      bool havePrev = false; int32_t prevSeq = 0, prevEnd = 0, nCand = 0;
+      for (int32_t i0 = 0; i0 < n; i0 += 32) {
+        const int32_t i = i0 + lane, j = i + mh - 1;
+        bool flag = false; int32_t seqA = 0, en = 0, st = 0;
+        if (j < n) {
+          const uint64_t ka = hits[b + i], kb = hits[b + j];
+          seqA = dec.seq(ka); en = dec.wpos(ka);
+          flag = seqA == dec.seq(kb) && dec.wpos(kb) - en < len;
+          st = dec.wpos(kb) - len + 1; if (st < 0) st = 0;
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, flag);
+        if (fm == 0) continue;
+        const unsigned below = fm & ((1u << lane) - 1u);
+        const int p = below ? 31 - __clz(below) : 0;
+        int32_t pSeq = __shfl_sync(0xffffffffu, seqA, p), pEn = __shfl_sync(0xffffffffu, en, p);
+        bool hasP = below != 0;
+        if (!hasP) { pSeq = prevSeq; pEn = prevEnd; hasP = havePrev; }
+        const bool head = flag && !(hasP && pSeq == seqA && pEn >= st);
+        const unsigned hm = __ballot_sync(0xffffffffu, head);
+        const int32_t k = nCand + __popc(hm & ((2u << lane) - 1u)) - 1;       // heads up to and including this lane: the group this flagged hit belongs to
+        const unsigned above = lane < 31 ? (fm & ~((2u << lane) - 1u)) : 0u;
+        const bool lastHere = flag && (above == 0 || ((hm >> (__ffs(above) - 1)) & 1u));
+        if (head) { tSeq[b + k] = seqA; tStart[b + k] = st; tLo[b + k] = i; }
+        if (lastHere) { tEnd[b + k] = en; tHi[b + k] = i + mh; }          // a later chunk's hits of the same group overwrite this
+        const int top = 31 - __clz(fm);
+        prevSeq = __shfl_sync(0xffffffffu, seqA, top); prevEnd = __shfl_sync(0xffffffffu, en, top); havePrev = true;
+        nCand += __popc(hm);
+        __syncwarp();
+      }
+      if (lane == 0) candCnt[r] = nCand;
+    }
+  }
+}
+struct CandGatherFn {       // candidate c -> (read, k-th of the read) -> its scratch slot
+  const int64_t* candOff; int32_t n_reads; const int64_t* readHitOff; const int32_t* tSeq; const int32_t* tStart; const int32_t* tEnd; const int32_t* tLo; const int32_t* tHi;
+  int32_t* cRead; int32_t* cSeq; int32_t* cStart; int32_t* cEnd; int64_t* cHitLo; int64_t* cHitHi;
+  MM_HD void operator()(int64_t c) const {
+    const int64_t r = upper_bound_idx(candOff, (int64_t)n_reads + 1, c) - 1;
+    const int64_t src = ldg(readHitOff + r) + (c - ldg(candOff + r));
+    cRead[c] = (int32_t)r; cSeq[c] = ldg(tSeq + src); cStart[c] = ldg(tStart + src); cEnd[c] = ldg(tEnd + src);
+    cHitLo[c] = (int64_t)ldg(tLo + src); cHitHi[c] = (int64_t)ldg(tHi + src);
+  }
+};
+#endif
+
 // ---------------------------------------------------------------------------------------------- K5
 MM_HD int64_t search_index(const uint32_t* miWs, const int64_t* contigStart, int32_t seq, int64_t wpos) {   // winSketch.hpp:506-517
   int64_t lo = ldg(contigStart + seq), hi = ldg(contigStart + seq + 1);
@@ -1959,7 +2025,7 @@ struct Mapper {
   // K5a also bounds every window's shared count and K5b sweeps only the window starts that can hold the optimum (l2 prune, PruneView);
   // MM_SWEEP_PRUNE=0 sweeps every window start as the reference does
   DevBuf<uint4> grpSum; bool sweepPrune = true, prunedPass = false; int32_t pruneGmax = 256;
-  DevBuf<unsigned long long> segStart; DevBuf<int32_t> segBig; bool segSorted = false;
+  DevBuf<unsigned long long> segStart; DevBuf<int32_t> segBig, candTmp; bool segSorted = false;
   DevBuf<uint2> probeOut;      // (CSR start, count) of every probe of the batch: l1_probe_filter_kernel's spill between its two passes
   int64_t evBudget = (int64_t)1 << 30;       // span elements classified per L2 pass (8 B each: at most 8.6 GB of scratch)
 
@@ -2290,7 +2356,26 @@ struct Mapper {
       StageTimer t(rt, &st.ms[4]);
       n_cand = 0;
       dev_memset(rt, candCnt.p, 0, sizeof(int32_t) * ((size_t)n_reads + 1));
-      if (n_hits > 0) {
+      bool candDone = false;
+#ifndef MM_HOST_EMU
+      static const bool candLegacy = [] { const char* e = getenv("MM_L1_CAND"); return e && !strcmp(e, "legacy"); }();
+      if (!candLegacy && n_hits > 0 && n_hits < ((int64_t)1 << 31)) {          // one warp per read over its sorted hits (l1_candidates_warp_kernel)
+        candTmp.ensure((size_t)5 * ((size_t)n_hits + 2));
+        int32_t* tSeq = candTmp.p; int32_t* tStart = tSeq + n_hits + 2; int32_t* tEnd = tStart + n_hits + 2; int32_t* tLo = tEnd + n_hits + 2; int32_t* tHi = tLo + n_hits + 2;
+        scal.ensure(8); dev_memset(rt, scal.p + 7, 0, sizeof(unsigned long long));
+        l1_candidates_warp_kernel<<<rt.sm_count * 8, 256, 0, rt.stream>>>(hits2.p, readHitOff.p, sOf.p, readLen.p, dMinHits.p, dec, n_reads, tSeq, tStart, tEnd, tLo, tHi,
+                                                                          candCnt.p, scal.p + 7);
+        MM_CUDA(cudaGetLastError());
+        rt.launches++;
+        pr.exclusive_sum<int32_t, int64_t>(candCnt.p, candOff.p, (int64_t)n_reads + 1);
+        d2h(rt, &n_cand, candOff.p + n_reads, sizeof(int64_t));
+        cRead.ensure((size_t)n_cand + 1); cSeq.ensure((size_t)n_cand + 1); cStart.ensure((size_t)n_cand + 1); cEnd.ensure((size_t)n_cand + 1);
+        cHitLo.ensure((size_t)n_cand + 1); cHitHi.ensure((size_t)n_cand + 1);
+        if (n_cand > 0) foreach(rt, n_cand, CandGatherFn{candOff.p, n_reads, readHitOff.p, tSeq, tStart, tEnd, tLo, tHi, cRead.p, cSeq.p, cStart.p, cEnd.p, cHitLo.p, cHitHi.p});
+        candDone = true;
+      }
+#endif
+      if (!candDone && n_hits > 0) {
         hflag.ensure((size_t)n_hits + 2); hfidx.ensure((size_t)n_hits + 2);
         foreach(rt, n_hits + 1, HitFlagFn{hits2.p, readHitOff.p, sOf.p, readLen.p, dMinHits.p, dec, hflag.p, n_hits});
         pr.exclusive_sum<int32_t, int64_t>(hflag.p, hfidx.p, n_hits + 1);
@@ -2307,8 +2392,9 @@ struct Mapper {
                                           cRead.p, cSeq.p, cStart.p, cEnd.p, candCnt.p, cHitLo.p, cHitHi.p});
         }
       }
-      pr.exclusive_sum<int32_t, int64_t>(candCnt.p, candOff.p, (int64_t)n_reads + 1);
+      if (!candDone) pr.exclusive_sum<int32_t, int64_t>(candCnt.p, candOff.p, (int64_t)n_reads + 1);
       cRead.ensure((size_t)n_cand + 1); cSeq.ensure((size_t)n_cand + 1); cStart.ensure((size_t)n_cand + 1); cEnd.ensure((size_t)n_cand + 1);
+      cHitLo.ensure((size_t)n_cand + 1); cHitHi.ensure((size_t)n_cand + 1);
     }
     // ---- K5
     int64_t totalEv = 0, smemSwept = 0;
