@@ -207,7 +207,8 @@ def test_multiple_l2_passes(oracle, small_workload, monkeypatch):
 
 @pytest.mark.parametrize("env", [{"MM_SWEEP_PRUNE": "0"}, {"MM_SWEEP_SEG": "100"}, {"MM_SWEEP_BAND": "64"}, {"MM_SWEEP_BAND": "128", "MM_SWEEP_RING": "4", "MM_SWEEP_SEG": "100"},
                                  {"MM_SWEEP_SEG": "64"}, {"MM_SWEEP_WIDE_FROM": "300"}, {"MM_SWEEP": "full"},
-                                 {"MM_SWEEP": "global"}, {"MM_L1_FILTER": "legacy"}, {"MM_K3_GLOBAL": "1"}])
+                                 {"MM_SWEEP": "global"}, {"MM_L1_FILTER": "legacy"}, {"MM_K3_GLOBAL": "1"}, {"MM_L1_SEGSORT": "0"}, {"MM_L1_CAND": "legacy"},
+                                 {"MM_L1_FUSED": "0"}])
 def test_kernel_variants(oracle, small_workload, monkeypatch, env):
     """Every selectable variant of K4/K5b (band width / ring depth of the banded sweep, the full-state shared-memory
     sweep, the global-memory sweep, the 8-byte L1 filter) gives the oracle's results."""
