@@ -136,8 +136,8 @@ def main():
     md.append("")
     # multi-GPU
     md += ["## Multi-GPU (final tree: calls Z, AC, AF; calls D / E: the build of call H, before the window pruning)", "", "| N | `value` Mbp/s | ms/step | `e2e` | config 3 (1 M reads) | contig shards `value` / ms | contig shards config 3 | config 5 slice ms/step |", "|---|---|---|---|---|---|---|---|"]
-    for n, fn, c5 in ((1, f"{BTAG}_bench.json", "r2ae_c5_1.json"), ("2 (final tree, call AC)", "r2ac_bench_n2.json", "r2ac_config5_n2.json"),
-                      ("8 (final tree, call AF, no extra legs)", "r2af_bench_n8.json", None), ("8, zero-copy staging (call AF)", "r2af_bench_n8_zerocopy.json", None),
+    for n, fn, c5 in ((1, f"{BTAG}_bench.json", "r2ae_c5_1.json"), ("2 (final tree, call AR)", "r2ar_bench_n2.json", None), ("2 (call AC, before the per-read survivor sort)", "r2ac_bench_n2.json", "r2ac_config5_n2.json"),
+                      ("8 (call AF, before the per-read survivor sort, no extra legs)", "r2af_bench_n8.json", None), ("8, zero-copy staging (call AF)", "r2af_bench_n8_zerocopy.json", None),
                       ("2 (call D)", "r2d2_bench_n2.json", "r2c_config5_n2.json"), ("8 (call E)", "r2e_bench_n8.json", "r2e_config5_n8.json")):
         d = last_json(fn); c = last_json(c5) if c5 else None
         if d:
