@@ -1231,11 +1231,14 @@ __global__ void __launch_bounds__(128) l2_classify_smem_kernel(L2ClassifyFn a, i
       const uint32_t* q = a.qHash + a.qOff[r];
       for (int32_t i = threadIdx.x; i < s; i += blockDim.x) smq[i] = __ldg(q + i);
       __syncthreads();
-      for (int32_t i = threadIdx.x; i <= s; i += blockDim.x) {      // bucket b starts at the first rank whose hash is in bucket >= b
+      for (int32_t i = threadIdx.x; i < s; i += blockDim.x) {       // bucket b starts at the first rank whose hash is in bucket >= b
         const int32_t bPrev = i > 0 ? (int32_t)(smq[i - 1] >> (32 - CLS_BUCKET_BITS)) : -1;
-        const int32_t bCur = i < s ? (int32_t)(smq[i] >> (32 - CLS_BUCKET_BITS)) : CLS_BUCKETS;
+        const int32_t bCur = (int32_t)(smq[i] >> (32 - CLS_BUCKET_BITS));
         for (int32_t bb = bPrev + 1; bb <= bCur; bb++) bstart[bb] = (uint16_t)i;
       }
+      // the buckets above the largest hash start at s: minimizer hashes crowd the bottom of the range, so this run is most of the table --
+      // filled by the whole CTA (left to the thread that holds rank s it was ~1800 serial stores behind a barrier at every read change)
+      for (int32_t bb = (s > 0 ? (int32_t)(smq[s - 1] >> (32 - CLS_BUCKET_BITS)) : -1) + 1 + (int32_t)threadIdx.x; bb <= CLS_BUCKETS; bb += blockDim.x) bstart[bb] = (uint16_t)s;
       __syncthreads();
     }
     const int64_t b0 = a.beg0[c];
