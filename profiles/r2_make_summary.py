@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 TAG = "r2z"          # ncu --set full raw / source pages, config 4 leg (call Z)
-BTAG = "r2aq"        # bench line + launch list of the committed tree (call AQ)
+BTAG = "r2av"        # bench line + launch list of the committed tree (call AV; reference arm: call AQ)
 
 
 def last_json(fn):
@@ -77,7 +77,7 @@ def main():
     md = ["# Round 2 — profiles and measurements (1 x B200 unless stated; scripts `profiles/r2_run_*.sh`)", ""]
     b = last_json(f"{BTAG}_bench.json")
     if b:
-        md += ["## The bench line of the final tree (`bench.py --gpus 1 --steps 20 --warmup 5`, call AQ)", "",
+        md += ["## The bench line of the final tree (`bench.py --gpus 1 --steps 20 --warmup 5`, call AV)", "",
                f"`value` {b['value']:.0f} Mbp/s ({b['ms_per_step']:.2f} ms/step), `e2e` {b['e2e']['value']:.0f} Mbp/s, {b['gpu_launches']} launches in the timed region, "
                f"SM clock {b['clocks']['sm_mhz']:.0f} / {b['clocks']['sm_max_mhz']} MHz, throttle reasons {b['clocks']['reasons']}.", "",
                "| kernel / stage | ms | algorithmic GB (SURVEY 8d) | GB/s | fraction of 6549.8 GB/s | other roof |", "|---|---|---|---|---|---|"]
