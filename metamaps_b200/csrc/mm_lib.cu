@@ -1242,6 +1242,7 @@ int mm_classify_fetch(mm_ctx* c, int32_t* read_idx, int32_t* seq_id, int32_t* re
 #ifdef MM_HOST_EMU
 // test hook (host-emulation build only): the std::sort replay, checked against the real std::sort by tests
 void mm_emu_stdsort(uint64_t* a, int64_t n) { mm::stdsort::sort(a, n); }
+void mm_emu_prune_shift(int upper, int lower) { mm::g_emu_prune_shift[0] = upper; mm::g_emu_prune_shift[1] = lower; }
 long long mm_emu_rebuild_calls(int reset) { long long v = mm::g_emu_rebuild_calls; if (reset) mm::g_emu_rebuild_calls = 0; return v; }
 long long mm_emu_rebuild_elems(int reset) { long long v = mm::g_emu_rebuild_elems; if (reset) mm::g_emu_rebuild_elems = 0; return v; }
 long long mm_emu_sweep_iters(int reset) { long long v = mm::g_emu_sweep_iters; if (reset) mm::g_emu_sweep_iters = 0; return v; }

@@ -24,6 +24,7 @@
 namespace mm {
 #ifdef MM_HOST_EMU
 static long long g_emu_rebuild_calls = 0, g_emu_rebuild_elems = 0;
+static int g_emu_prune_shift[2] = {0, 0};   // test hook: moves the prune pass's upper / lower ranks off their estimates (exactness must not depend on them)
 static long long g_emu_sweep_iters = 0;      // test hook: events applied by the banded sweep (how much the window skipping saves)
 #endif
 
@@ -1009,6 +1010,9 @@ MM_HD PruneThr prune_thresholds(int32_t s, int32_t win, int32_t mest) {
   // measured on config-2-like data (emulation): 2 sd + 24 above / 2 sd - 4 below sweeps 19 % of the window starts; 3 sd + 20 both ways 23 %
   const int32_t m2 = (int32_t)(2.f * sd);
   t.i0 = e1 + m2 + 24; t.i1 = e1 - m2 + 4; t.i1b = e0 - m2 - 12;
+#ifdef MM_HOST_EMU
+  t.i0 += g_emu_prune_shift[0]; t.i1 += g_emu_prune_shift[1]; t.i1b += g_emu_prune_shift[1];
+#endif
   if (t.i1b > t.i1) t.i1b = t.i1;
   return t;
 }

@@ -212,3 +212,18 @@ def test_window_pruning_fuzz(monkeypatch):
     from tests.conftest import build_emu
     lib = capi.load(build_emu())
     common.check_prune_fuzz(lambda: capi.Context(0, lib), monkeypatch, 16)
+
+
+def test_window_pruning_is_exact_whatever_its_ranks(monkeypatch):
+    """The prune pass places its upper / lower ranks from an ESTIMATE of istar; its bounds hold only where their premises are checked to hold.
+    Moving the ranks far off the estimate (test hook of the emulation build) must therefore change how much is swept, never a result."""
+    import ctypes
+    from tests.conftest import build_emu
+    lib = capi.load(build_emu())
+    lib.mm_emu_prune_shift.argtypes = [ctypes.c_int, ctypes.c_int]; lib.mm_emu_prune_shift.restype = None
+    shifts = [(-400, 0), (0, 400), (-60, 60), (60, -60), (-25, 25), (300, -300), (-1000, -1000), (1000, 1000)]
+    try:
+        common.check_prune_fuzz(lambda: capi.Context(0, lib), monkeypatch, 16, before_pruned=lambda case: lib.mm_emu_prune_shift(*shifts[case % len(shifts)]))
+    finally:
+        lib.mm_emu_prune_shift(0, 0)
+
