@@ -10,7 +10,8 @@ import shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
-TAG = "r2z"          # ncu --set full raw / source pages, config 4 leg (call Z)
+TAG = "r2z"          # config 4 leg (call Z)
+RTAG = "r2ba"        # ncu --set full raw / source pages of the committed tree (call BA)
 BTAG = "r2av"        # bench line + launch list of the committed tree (call AV; reference arm: call AQ)
 
 
@@ -94,12 +95,13 @@ def main():
             kd = next((v[1] for k, v in agg.items() if pat in k), 0)
             md += [f"Share check: the dominant kernel of the bench line ({dom}) is {100 * kd / tot:.1f} % of the launch list and {100 * b['roofline']['kernels'][dom]['ms'] / b['detail']['kernel_ms_per_step']:.1f} % of the "
                    f"CUDA-event kernel time of a bench step ({b['detail']['kernel_ms_per_step']:.1f} ms).", ""]
-    rp = os.path.join(G, f"{TAG}_full_raw.csv")
-    traffic = {"workload": "config2", "source": f"profiles/r2_full_raw.csv: ncu --set full --clock-control none, one step of bench.py --profile-step (round 2, call Z)"}
+    rp = os.path.join(G, f"{RTAG}_full_raw.csv")
+    traffic = {"workload": "config2", "source": f"profiles/r2_full_raw.csv: ncu --set full --clock-control none, one step of bench.py --profile-step (round 2, call BA)"}
     if os.path.exists(rp):
         shutil.copy(rp, os.path.join(P, "r2_full_raw.csv"))
         t, tr = metric_block(rp, {"sketch_blockmin": "K1 sketch_blockmin_kernel", "read_sketch_block_kernel<(int)4": "K3 read_sketch_block_kernel<4>",
                                   "l1_probe_filter": "K4 l1_probe_filter_kernel", "l2_classify_smem": "K5a l2_classify_smem_kernel",
+                                  "l1_sort_segments_warp": "K4 l1_sort_segments_warp_kernel", "l1_candidates_warp": "K4 l1_candidates_warp_kernel",
                                   "l2_prune_warp": "K5p l2_prune_warp_kernel", "l2_sweep_band": "K5b l2_sweep_band_kernel"})
         traffic.update(tr)
         md += ["## `ncu --set full` of the dominant kernels (`profiles/r2_full_raw.csv` = the raw page)", "", t]
