@@ -1,0 +1,6 @@
+#!/bin/bash
+# Round 2, GPU call AZ (1 x B200): K5b first-window build with the next sixteen event codes fetched while the current sixteen are applied.  (variant not kept; the code it measured is described in DESIGN.md section 4 and was reverted)
+set -x
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "map or variants or fallback" > gpurun_out/r2az_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2az_tests.log)
+timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2az_bench.json 2> gpurun_out/r2az_bench.err
